@@ -1,0 +1,119 @@
+/*
+ * ik_oracle.h -- CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * Plain-C FP64 restatement of the reference's damped-least-squares IK path
+ * (dazzmo/ik: ik/ik/dls.cpp:5-78, data.cpp:25-58, frame.hpp:37-62,152-182,
+ * posture.hpp:50-67, common.hpp:47-56, visitor.hpp:15-21) and of the
+ * Pinocchio / Eigen algorithms that path calls (neither library is vendored in
+ * the reference nor installed here).
+ *
+ * PARITY UNPINNED: the reference's own tests hold no golden vector for this
+ * path (every TEST body is commented out, ik/test/dls.cpp:10-76) and the
+ * reference cannot be compiled here (needs Pinocchio, Eigen>=3.4, Boost, glog).
+ * The oracle is therefore validated from first principles in tests/ (exp/log
+ * round trips, finite-difference Jacobians, hand-derived FK) and against the
+ * provisional known answers recorded in SURVEY.md 8c.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs may load this library; the product (ik_b200/) never does.
+ *
+ * Conventions: SE3 = 12 doubles, rotation row-major R[0..8] then p[0..2];
+ * motion vectors are [linear; angular]; free-flyer q = [p(3), quat x,y,z,w].
+ */
+#ifndef IK_ORACLE_H
+#define IK_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { IKO_J_UNIVERSE = 0, IKO_J_FREEFLYER = 1, IKO_J_RX = 2, IKO_J_RY = 3, IKO_J_RZ = 4,
+       IKO_J_REV_UNALIGNED = 5, IKO_J_PX = 6, IKO_J_PY = 7, IKO_J_PZ = 8, IKO_J_PRIS_UNALIGNED = 9 };
+
+enum { IKO_TASK_FRAME = 0, IKO_TASK_ALIGN_AXIS = 1, IKO_TASK_POSTURE = 2 };
+enum { IKO_POSITION = 0, IKO_ORIENTATION = 1, IKO_FULL = 2 };
+
+typedef struct {
+    int njoints; /* including the universe joint 0 */
+    int nq, nv;
+    const int *parent;       /* [njoints] */
+    const int *jtype;        /* [njoints] */
+    const int *idx_q;        /* [njoints] */
+    const int *idx_v;        /* [njoints] */
+    const double *placement; /* [njoints][12] joint placement in the parent joint frame */
+    const double *axis;      /* [njoints][3] (unaligned joints) */
+    const double *lower;     /* [nq] */
+    const double *upper;     /* [nq] */
+    int nframes;
+    const int *frame_parent;       /* [nframes] supporting joint */
+    const double *frame_placement; /* [nframes][12] */
+} iko_model;
+
+typedef struct {
+    int ntasks;
+    int max_priority_level;
+    const int *kind;     /* [ntasks] IKO_TASK_* */
+    const int *frame;    /* [ntasks] task frame (FRAME, ALIGN_AXIS) */
+    const int *ref;      /* [ntasks] reference frame */
+    const int *type;     /* [ntasks] FRAME: IKO_POSITION/ORIENTATION/FULL; ALIGN_AXIS: axis 0/1/2; POSTURE: nj */
+    const int *priority; /* [ntasks] */
+    const double *weight; /* concatenated per-row weights, task insertion order */
+    const double *mask;   /* concatenated posture masks (POSTURE tasks only, insertion order) */
+} iko_problem;
+
+typedef struct {
+    int max_iterations;  /* common.hpp:61 (default 100) */
+    double step_length;  /* common.hpp:65 (default 1.0) */
+    double damping;      /* dls.hpp:25 (default 1e-2) */
+    double tolerance;    /* visitor.hpp:19: squared-norm threshold, 1e-4 */
+} iko_params;
+
+/* sizes */
+int iko_task_dim(const iko_problem *pb, int t);
+int iko_task_target_size(const iko_problem *pb, int t);
+int iko_target_size(const iko_problem *pb);          /* doubles per problem */
+int iko_e_size(const iko_problem *pb, int priority); /* problem.hpp:34-40 */
+int iko_total_rows(const iko_problem *pb);
+
+/* Lie-group primitives (Pinocchio explog.hpp restated) */
+void iko_exp3(const double w[3], double R[9]);
+void iko_log3(const double R[9], double w[3], double *theta);
+void iko_exp6(const double v[6], double M[12]);
+void iko_log6(const double M[12], double v[6]);
+void iko_Jlog3(double theta, const double w[3], double J[9]);
+void iko_Jlog6(const double M[12], double J[36]);
+void iko_se3_mul(const double A[12], const double B[12], double C[12]);    /* A*B */
+void iko_se3_actinv(const double A[12], const double B[12], double C[12]); /* A^-1*B */
+void iko_quat_to_rot(const double q_xyzw[4], double R[9]);
+void iko_rot_to_quat(const double R[9], double q_xyzw[4]);
+
+/* kinematics */
+void iko_fk(const iko_model *m, const double *q, double *oMi /*[njoints][12]*/);
+void iko_frame_placement(const iko_model *m, const double *oMi, int frame, double oMf[12]);
+void iko_joint_jacobians(const iko_model *m, const double *oMi, double *J /*[6][nv] row-major, world*/);
+void iko_frame_jacobian_local(const iko_model *m, const double *oMi, const double *Jworld, int frame,
+                              double *Jf /*[6][nv]*/);
+void iko_integrate(const iko_model *m, const double *q, const double *v, double *qout);
+void iko_clip(const iko_model *m, double *q);
+
+/* one evaluate_problem_data() (data.cpp:25-58): stacked e [rows] and J [rows][nv] */
+void iko_evaluate(const iko_model *m, const iko_problem *pb, const double *q, const double *targets,
+                  double *e, double *J);
+
+/* Eigen LDLT (pivoted, lower, unblocked) restated: solves A x = b, A n x n row-major (destroyed) */
+void iko_ldlt_solve(int n, double *A, const double *b, double *x);
+
+/* ik::dls (dls.cpp:5-78).  Returns success (1/0).  iters = steps taken; resid = ||e[0]||^2 at the last
+ * evaluation; dq_out (optional, nv) = last step direction. */
+int iko_dls(const iko_model *m, const iko_problem *pb, const iko_params *prm, const double *q0,
+            const double *targets, double *q_out, int *iters, double *resid, double *dq_out);
+
+/* Loop of iko_dls over a batch, AoS: q0 [B][nq], targets [B][tsz]; nthreads >= 1 (pthreads). */
+void iko_dls_batch(const iko_model *m, const iko_problem *pb, const iko_params *prm, int B,
+                   const double *q0, const double *targets, double *q_out, unsigned char *success,
+                   int *iters, double *resid, int nthreads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,282 @@
+"""CPU ORACLE (test infrastructure, NOT product code): ctypes front-end of oracle/libik_oracle.so.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+PARITY UNPINNED -- see oracle/ik_oracle.h.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import urdf_flatten
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+TASK_FRAME, TASK_ALIGN_AXIS, TASK_POSTURE = 0, 1, 2
+POSITION, ORIENTATION, FULL = 0, 1, 2
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class _CModel(C.Structure):
+    _fields_ = [("njoints", C.c_int), ("nq", C.c_int), ("nv", C.c_int), ("parent", _ip), ("jtype", _ip),
+                ("idx_q", _ip), ("idx_v", _ip), ("placement", _dp), ("axis", _dp), ("lower", _dp), ("upper", _dp),
+                ("nframes", C.c_int), ("frame_parent", _ip), ("frame_placement", _dp)]
+
+
+class _CProblem(C.Structure):
+    _fields_ = [("ntasks", C.c_int), ("max_priority_level", C.c_int), ("kind", _ip), ("frame", _ip), ("ref", _ip),
+                ("type", _ip), ("priority", _ip), ("weight", _dp), ("mask", _dp)]
+
+
+class _CParams(C.Structure):
+    _fields_ = [("max_iterations", C.c_int), ("step_length", C.c_double), ("damping", C.c_double),
+                ("tolerance", C.c_double)]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libik_oracle.so")
+    src = os.path.join(_HERE, "ik_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.iko_dls.restype = C.c_int
+    return _LIB
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _pd(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _pi(a):
+    return a.ctypes.data_as(_ip)
+
+
+class Model:
+    def __init__(self, flat):
+        self.flat = flat
+        self.nq, self.nv, self.njoints, self.nframes = flat["nq"], flat["nv"], flat["njoints"], flat["nframes"]
+        self._keep = {k: np.ascontiguousarray(flat[k]) for k in
+                      ("parent", "jtype", "idx_q", "idx_v", "placement", "axis", "lower", "upper", "frame_parent",
+                       "frame_placement")}
+        k = self._keep
+        self.c = _CModel(self.njoints, self.nq, self.nv, _pi(k["parent"]), _pi(k["jtype"]), _pi(k["idx_q"]),
+                         _pi(k["idx_v"]), _pd(k["placement"]), _pd(k["axis"]), _pd(k["lower"]), _pd(k["upper"]),
+                         self.nframes, _pi(k["frame_parent"]), _pd(k["frame_placement"]))
+
+    @classmethod
+    def from_urdf(cls, xml_text, free_flyer=True):
+        return cls(urdf_flatten.flatten_urdf(xml_text, free_flyer))
+
+    def frame_id(self, name):
+        return urdf_flatten.frame_id(self.flat, name)
+
+    def neutral(self):
+        q = np.zeros(self.nq)
+        for j in range(self.njoints):
+            if self.flat["jtype"][j] == urdf_flatten.J_FREEFLYER:
+                q[self.flat["idx_q"][j] + 6] = 1.0
+        return q
+
+    def fk(self, q):
+        out = np.zeros((self.njoints, 12))
+        lib().iko_fk(C.byref(self.c), _pd(_d(q)), _pd(out))
+        return out
+
+    def frame_placement(self, q, frame):
+        oMi = self.fk(q)
+        out = np.zeros(12)
+        lib().iko_frame_placement(C.byref(self.c), _pd(oMi), C.c_int(frame), _pd(out))
+        return out
+
+    def frame_jacobian_local(self, q, frame):
+        oMi = self.fk(q)
+        Jw = np.zeros((6, self.nv))
+        Jf = np.zeros((6, self.nv))
+        lib().iko_joint_jacobians(C.byref(self.c), _pd(oMi), _pd(Jw))
+        lib().iko_frame_jacobian_local(C.byref(self.c), _pd(oMi), _pd(Jw), C.c_int(frame), _pd(Jf))
+        return Jf
+
+    def integrate(self, q, v):
+        out = np.zeros(self.nq)
+        lib().iko_integrate(C.byref(self.c), _pd(_d(q)), _pd(_d(v)), _pd(out))
+        return out
+
+    def clip(self, q):
+        out = _d(q).copy()
+        lib().iko_clip(C.byref(self.c), _pd(out))
+        return out
+
+
+class Problem:
+    """Mirror of ik::InverseKinematicsProblem restricted to what the oracle needs (problem.hpp:9-206)."""
+
+    def __init__(self, model, max_priority_level=0):
+        self.model = model
+        self.max_priority_level = max_priority_level
+        self.tasks = []
+        self._c = None
+
+    def add_frame_task(self, frame, ktype=FULL, ref="universe", priority=0, weight=None):
+        f, r = self._fid(frame), self._fid(ref)
+        dim = 6 if ktype == FULL else 3
+        self.tasks.append(dict(kind=TASK_FRAME, frame=f, ref=r, type=ktype, priority=priority, dim=dim, tsz=12,
+                               weight=np.ones(dim) if weight is None else _d(weight), mask=np.zeros(0)))
+        self._c = None
+        return len(self.tasks) - 1
+
+    def add_align_axis_task(self, frame, axis, ref="universe", priority=0, weight=None):
+        f, r = self._fid(frame), self._fid(ref)
+        self.tasks.append(dict(kind=TASK_ALIGN_AXIS, frame=f, ref=r, type=axis, priority=priority, dim=1, tsz=3,
+                               weight=np.ones(1) if weight is None else _d(weight), mask=np.zeros(0)))
+        self._c = None
+        return len(self.tasks) - 1
+
+    def add_posture_task(self, nj, priority=0, weight=None, mask=None):
+        self.tasks.append(dict(kind=TASK_POSTURE, frame=0, ref=0, type=nj, priority=priority, dim=nj, tsz=nj,
+                               weight=np.ones(nj) if weight is None else _d(weight),
+                               mask=np.ones(nj) if mask is None else _d(mask)))
+        self._c = None
+        return len(self.tasks) - 1
+
+    def _fid(self, name):
+        if isinstance(name, int):
+            return name
+        f = self.model.frame_id(name)
+        if f >= self.model.nframes:
+            raise KeyError("unknown frame %r" % name)
+        return f
+
+    @property
+    def c(self):
+        if self._c is None:
+            t = self.tasks
+            arr = lambda key: np.array([x[key] for x in t], dtype=np.int32)
+            self._keep = dict(kind=arr("kind"), frame=arr("frame"), ref=arr("ref"), type=arr("type"),
+                              priority=arr("priority"),
+                              weight=_d(np.concatenate([x["weight"] for x in t]) if t else np.zeros(0)),
+                              mask=_d(np.concatenate([x["mask"] for x in t] + [np.zeros(1)])))
+            k = self._keep
+            self._c = _CProblem(len(t), self.max_priority_level, _pi(k["kind"]), _pi(k["frame"]), _pi(k["ref"]),
+                                _pi(k["type"]), _pi(k["priority"]), _pd(k["weight"]), _pd(k["mask"]))
+        return self._c
+
+    @property
+    def target_size(self):
+        return sum(x["tsz"] for x in self.tasks)
+
+    @property
+    def rows(self):
+        return sum(x["dim"] for x in self.tasks)
+
+    def e_size(self, priority):
+        return sum(x["dim"] for x in self.tasks if x["priority"] == priority)
+
+    def evaluate(self, q, targets):
+        e = np.zeros(self.rows)
+        J = np.zeros((self.rows, self.model.nv))
+        lib().iko_evaluate(C.byref(self.model.c), C.byref(self.c), _pd(_d(q)), _pd(_d(targets)), _pd(e), _pd(J))
+        return e, J
+
+
+def params(max_iterations=100, step_length=1.0, damping=1e-2, tolerance=1e-4):
+    """Library defaults: common.hpp:61-65, dls.hpp:25, visitor.hpp:19."""
+    return _CParams(max_iterations, step_length, damping, tolerance)
+
+
+def dls(problem, q0, targets, prm=None):
+    """ik::dls (dls.cpp:5-78) on one problem.  Returns q, success, iterations, resid, dq."""
+    prm = prm or params()
+    m = problem.model
+    q = np.zeros(m.nq)
+    dq = np.zeros(m.nv)
+    it = C.c_int(0)
+    res = C.c_double(0)
+    ok = lib().iko_dls(C.byref(m.c), C.byref(problem.c), C.byref(prm), _pd(_d(q0)), _pd(_d(targets)), _pd(q),
+                       C.byref(it), C.byref(res), _pd(dq))
+    return q, bool(ok), it.value, res.value, dq
+
+
+def dls_batch(problem, q0, targets, prm=None, nthreads=1):
+    """Loop of ik::dls over a batch.  q0 [B, nq], targets [B, target_size] (AoS)."""
+    prm = prm or params()
+    m = problem.model
+    q0 = _d(q0)
+    targets = _d(targets)
+    B = q0.shape[0]
+    assert q0.shape == (B, m.nq) and targets.shape == (B, problem.target_size)
+    q = np.zeros((B, m.nq))
+    ok = np.zeros(B, dtype=np.uint8)
+    it = np.zeros(B, dtype=np.int32)
+    res = np.zeros(B)
+    lib().iko_dls_batch(C.byref(m.c), C.byref(problem.c), C.byref(prm), C.c_int(B), _pd(q0), _pd(targets), _pd(q),
+                        ok.ctypes.data_as(C.POINTER(C.c_ubyte)), _pi(it), _pd(res), C.c_int(nthreads))
+    return q, ok.astype(bool), it, res
+
+
+def ldlt_solve(A, b):
+    A = _d(A).copy()
+    n = A.shape[0]
+    x = np.zeros(n)
+    lib().iko_ldlt_solve(C.c_int(n), _pd(A), _pd(_d(b)), _pd(x))
+    return x
+
+
+def _unary(name, x, nout):
+    out = np.zeros(nout)
+    getattr(lib(), name)(_pd(_d(x)), _pd(out))
+    return out
+
+
+def exp3(w):
+    return _unary("iko_exp3", w, 9).reshape(3, 3)
+
+
+def exp6(v):
+    return _unary("iko_exp6", v, 12)
+
+
+def log6(M):
+    return _unary("iko_log6", M, 6)
+
+
+def Jlog6(M):
+    return _unary("iko_Jlog6", M, 36).reshape(6, 6)
+
+
+def log3(R):
+    w = np.zeros(3)
+    t = C.c_double(0)
+    lib().iko_log3(_pd(_d(R).reshape(-1)), _pd(w), C.byref(t))
+    return w, t.value
+
+
+def se3_mul(A, B):
+    out = np.zeros(12)
+    lib().iko_se3_mul(_pd(_d(A)), _pd(_d(B)), _pd(out))
+    return out
+
+
+def se3_actinv(A, B):
+    out = np.zeros(12)
+    lib().iko_se3_actinv(_pd(_d(A)), _pd(_d(B)), _pd(out))
+    return out
+
+
+def se3(R=None, p=None):
+    R = np.eye(3) if R is None else np.asarray(R, dtype=np.float64).reshape(3, 3)
+    p = np.zeros(3) if p is None else np.asarray(p, dtype=np.float64)
+    return np.concatenate([R.reshape(-1), p])
