@@ -1,0 +1,718 @@
+// C ABI of libikb200.so (see include/ikb200.h for the contract and the reference interfaces replaced).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <type_traits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/ikb200.h"
+#include "dev_problem.hpp"
+#include "dls_generic.cuh"
+#include "model.hpp"
+#include "specialized.hpp"
+
+using namespace ikb;
+
+// ---------------------------------------------------------------------------------------------------
+// handles
+// ---------------------------------------------------------------------------------------------------
+struct ikb_model {
+    HostModel m;
+};
+
+namespace {
+constexpr int kTicketSlots = 64;
+
+template <typename T> struct Staging {
+    T *q0 = nullptr, *targets = nullptr, *q = nullptr, *resid = nullptr;
+    size_t q0_cap = 0, tg_cap = 0, q_cap = 0, b_cap = 0;
+};
+}  // namespace
+
+struct ikb_problem {
+    HostProblem hp;
+    bool finalized = false;
+    int device = -1;
+    int size_class = -1;
+    int sm_count = 0;
+    DevProblem<double> *d64 = nullptr;
+    DevProblem<float> *d32 = nullptr;
+    int *d_frame_parent = nullptr;  // all model frames (for ikb_fk_batch)
+    double *d_frame_pl64 = nullptr;
+    float *d_frame_pl32 = nullptr;
+    unsigned long long *d_tickets = nullptr;
+    std::atomic<unsigned> ticket_next{0};
+    const SpecializedKernel *spec = nullptr;
+    std::string kernel_name[2];
+    // host-path staging (ikb_dls_solve_batch_host)
+    cudaStream_t stream = nullptr;
+    Staging<double> st64;
+    Staging<float> st32;
+    unsigned char *st_success = nullptr;
+    int *st_iters = nullptr;
+    size_t st_flag_cap = 0;
+};
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char *what) {
+    return fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? IKB_ERR_NO_DEVICE : IKB_ERR_CUDA,
+                std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define IKB_CUDA(call)                                        \
+    do {                                                      \
+        cudaError_t e_ = (call);                              \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);   \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+struct SizeClass {
+    int nj, nv, m;
+};
+const SizeClass kClasses[] = {{10, 8, 6}, {20, 24, 12}, {32, 36, 30}};
+
+template <typename T>
+void fill_dev_problem(const HostProblem &hp, const std::vector<int> &order, const std::vector<int> &used_frames,
+                      DevProblem<T> &P) {
+    const HostModel &m = hp.model;
+    std::memset(&P, 0, sizeof(P));
+    P.njoints = m.njoints();
+    P.nq = m.nq;
+    P.nv = m.nv;
+    P.nframes = (int)used_frames.size();
+    P.ntasks = (int)hp.tasks.size();
+    P.rows = hp.rows();
+    P.rows_p0 = hp.e_size(0);
+    P.tsz = hp.target_size();
+    for (int j = 0; j < m.njoints(); ++j) {
+        P.parent[j] = m.parent[j];
+        P.jtype[j] = m.jtype[j];
+        P.idx_q[j] = m.idx_q[j];
+        P.idx_v[j] = m.idx_v[j];
+        for (int k = 0; k < 12; ++k) P.placement[j][k] = (T)m.placement[j][k];
+        for (int k = 0; k < 3; ++k) P.axis[j][k] = (T)m.axis[j][k];
+    }
+    const double big = (double)std::numeric_limits<T>::max();
+    for (int k = 0; k < m.nq; ++k) {
+        P.lower[k] = (T)std::max(m.lower[k], -big);
+        P.upper[k] = (T)std::min(m.upper[k], big);
+    }
+    for (size_t f = 0; f < used_frames.size(); ++f) {
+        P.f_parent[f] = m.frame_parent[used_frames[f]];
+        for (int k = 0; k < 12; ++k) P.f_placement[f][k] = (T)m.frame_placement[used_frames[f]][k];
+    }
+    auto local_frame = [&](int fid) {
+        return (int)(std::find(used_frames.begin(), used_frames.end(), fid) - used_frames.begin());
+    };
+    int row = 0, moff = 0;
+    for (size_t s = 0; s < order.size(); ++s) {
+        const HostTask &t = hp.tasks[order[s]];
+        P.t_kind[s] = t.kind;
+        P.t_frame[s] = t.kind == IKB_TASK_POSTURE ? 0 : local_frame(t.frame);
+        P.t_ref[s] = t.kind == IKB_TASK_POSTURE ? 0 : local_frame(t.ref);
+        P.t_type[s] = t.type;
+        P.t_row[s] = row;
+        P.t_dim[s] = t.dim;
+        P.t_toff[s] = hp.target_offset(order[s]);
+        P.t_moff[s] = moff;
+        for (int i = 0; i < t.dim; ++i) P.weight[row + i] = (T)t.weight[i];
+        if (t.kind == IKB_TASK_POSTURE) {
+            for (int i = 0; i < t.type; ++i) P.mask[moff + i] = (T)t.mask[i];
+            moff += t.type;
+        }
+        row += t.dim;
+    }
+}
+
+template <typename T> struct KernelTable {
+    using Fn = void (*)(const DevProblem<T> *, SolveArgs<T>);
+    static Fn dls(int cls) {
+        switch (cls) {
+            case 0: return dls_generic_kernel<T, 10, 8, 6>;
+            case 1: return dls_generic_kernel<T, 20, 24, 12>;
+            default: return dls_generic_kernel<T, 32, 36, 30>;
+        }
+    }
+};
+
+template <typename T> DevProblem<T> *dev_blob(const ikb_problem *p);
+template <> DevProblem<double> *dev_blob<double>(const ikb_problem *p) { return p->d64; }
+template <> DevProblem<float> *dev_blob<float>(const ikb_problem *p) { return p->d32; }
+
+template <typename T>
+int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io, cudaStream_t s) {
+    SolveArgs<T> a;
+    a.q0 = (const T *)io->q0; a.q0_es = io->q0_elem_stride; a.q0_bs = io->q0_batch_stride;
+    a.targets = (const T *)io->targets; a.tg_es = io->targets_elem_stride; a.tg_bs = io->targets_batch_stride;
+    a.q = (T *)io->q; a.q_es = io->q_elem_stride; a.q_bs = io->q_batch_stride;
+    a.success = io->success;
+    a.iters = io->iters;
+    a.resid = (T *)io->resid;
+    a.B = B;
+    a.max_iterations = prm->max_iterations;
+    a.step_length = (T)prm->step_length;
+    a.damping2 = (T)(prm->damping * prm->damping);
+    a.tolerance = (T)prm->tolerance;
+    const unsigned slot = const_cast<ikb_problem *>(p)->ticket_next.fetch_add(1) % kTicketSlots;
+    a.ticket = p->d_tickets + slot * 16;  // 128 B apart
+    IKB_CUDA(cudaMemsetAsync(a.ticket, 0, sizeof(unsigned long long), s));
+
+    if (p->spec) {
+        int rc = launch_specialized<T>(*p->spec, dev_blob<T>(p), a, p->sm_count, s);
+        if (rc != IKB_OK) return cuda_fail(cudaGetLastError(), "specialised kernel launch");
+        g_launches.fetch_add(1);
+        return IKB_OK;
+    }
+    auto fn = KernelTable<T>::dls(p->size_class);
+    const int threads = 128;
+    const size_t smem = sizeof(DevProblem<T>) + 16;
+    int per_sm = 0;
+    IKB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = (B + threads - 1) / threads;
+    blocks = std::min<long long>(blocks, (long long)per_sm * p->sm_count);
+    fn<<<(unsigned)blocks, threads, smem, s>>>(dev_blob<T>(p), a);
+    IKB_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return IKB_OK;
+}
+
+size_t view_extent(int64_t n_elem, int64_t es, int64_t bs, int64_t B) {
+    return (size_t)((n_elem - 1) * es + (B - 1) * bs + 1);
+}
+
+template <typename T> int ensure(T *&ptr, size_t &cap, size_t need) {
+    if (need <= cap) return IKB_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    size_t want = std::max(need, (size_t)1024);
+    IKB_CUDA(cudaMalloc(&ptr, want * sizeof(T)));
+    cap = want;
+    return IKB_OK;
+}
+
+template <typename T> Staging<T> &staging(ikb_problem *p);
+template <> Staging<double> &staging<double>(ikb_problem *p) { return p->st64; }
+template <> Staging<float> &staging<float>(ikb_problem *p) { return p->st32; }
+
+template <typename T>
+int solve_host(ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io) {
+    const int nq = p->hp.model.nq, tsz = p->hp.target_size();
+    Staging<T> &st = staging<T>(p);
+    const size_t n_q0 = view_extent(nq, io->q0_elem_stride, io->q0_batch_stride, B);
+    const size_t n_tg = tsz > 0 ? view_extent(tsz, io->targets_elem_stride, io->targets_batch_stride, B) : 0;
+    const size_t n_q = view_extent(nq, io->q_elem_stride, io->q_batch_stride, B);
+    int rc;
+    if ((rc = ensure(st.q0, st.q0_cap, n_q0)) || (rc = ensure(st.targets, st.tg_cap, std::max<size_t>(n_tg, 1))) ||
+        (rc = ensure(st.q, st.q_cap, n_q)) || (rc = ensure(st.resid, st.b_cap, (size_t)B)))
+        return rc;
+    if ((size_t)B > p->st_flag_cap) {
+        if (p->st_success) cudaFree(p->st_success);
+        if (p->st_iters) cudaFree(p->st_iters);
+        p->st_success = nullptr; p->st_iters = nullptr; p->st_flag_cap = 0;
+        IKB_CUDA(cudaMalloc(&p->st_success, (size_t)B));
+        IKB_CUDA(cudaMalloc(&p->st_iters, (size_t)B * sizeof(int)));
+        p->st_flag_cap = (size_t)B;
+    }
+    cudaStream_t s = p->stream;
+    IKB_CUDA(cudaMemcpyAsync(st.q0, io->q0, n_q0 * sizeof(T), cudaMemcpyHostToDevice, s));
+    if (n_tg) IKB_CUDA(cudaMemcpyAsync(st.targets, io->targets, n_tg * sizeof(T), cudaMemcpyHostToDevice, s));
+    ikb_batch_io dio = *io;
+    dio.q0 = st.q0;
+    dio.targets = st.targets;
+    dio.q = st.q;
+    dio.success = p->st_success;
+    dio.iters = p->st_iters;
+    dio.resid = st.resid;
+    if ((rc = launch_solve<T>(p, prm, B, &dio, s))) return rc;
+    IKB_CUDA(cudaMemcpyAsync(io->q, st.q, n_q * sizeof(T), cudaMemcpyDeviceToHost, s));
+    if (io->success) IKB_CUDA(cudaMemcpyAsync(io->success, p->st_success, (size_t)B, cudaMemcpyDeviceToHost, s));
+    if (io->iters) IKB_CUDA(cudaMemcpyAsync(io->iters, p->st_iters, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (io->resid) IKB_CUDA(cudaMemcpyAsync(io->resid, st.resid, (size_t)B * sizeof(T), cudaMemcpyDeviceToHost, s));
+    IKB_CUDA(cudaStreamSynchronize(s));
+    return IKB_OK;
+}
+
+struct FrameList {
+    int n;
+    int id[16];
+};
+
+template <typename T, int NJ>
+__global__ void __launch_bounds__(128) fk_model_frames_kernel(const DevProblem<T> *__restrict__ gP, const T *__restrict__ q,
+                                                              long long q_es, long long q_bs, long long B, FrameList fl,
+                                                              const int *__restrict__ frame_parent,
+                                                              const T *__restrict__ frame_placement, T *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DevProblem<T> &P = *reinterpret_cast<DevProblem<T> *>(smem_raw);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem_raw + sizeof(DevProblem<T>));
+    stage_blob_tma(&P, gP, (unsigned)sizeof(DevProblem<T>), bar);
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    T ql[NJ + 8];
+    T oR[NJ][9], op[NJ][3];
+    for (int k = 0; k < P.nq; ++k) ql[k] = q[k * q_es + b * q_bs];
+    fk_all<T, NJ>(P, ql, oR, op);
+    for (int f = 0; f < fl.n; ++f) {
+        const int fid = fl.id[f], pj = frame_parent[fid];
+        T R[9], p[3];
+        se3_mul(oR[pj], op[pj], frame_placement + 12 * fid, frame_placement + 12 * fid + 9, R, p);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) out[((long long)f * 12 + i) * B + b] = R[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) out[((long long)f * 12 + 9 + i) * B + b] = p[i];
+    }
+}
+
+template <typename T>
+int launch_fk(const ikb_problem *p, int64_t B, const void *q, int64_t es, int64_t bs, const FrameList &fl, void *out,
+              cudaStream_t s) {
+    const int threads = 128;
+    const size_t smem = sizeof(DevProblem<T>) + 16;
+    const unsigned blocks = (unsigned)((B + threads - 1) / threads);
+    const T *pl = std::is_same<T, double>::value ? (const T *)p->d_frame_pl64 : (const T *)p->d_frame_pl32;
+    if (p->size_class <= 1)
+        fk_model_frames_kernel<T, 20><<<blocks, threads, smem, s>>>(dev_blob<T>(p), (const T *)q, es, bs, B, fl,
+                                                                     p->d_frame_parent, pl, (T *)out);
+    else
+        fk_model_frames_kernel<T, 32><<<blocks, threads, smem, s>>>(dev_blob<T>(p), (const T *)q, es, bs, B, fl,
+                                                                     p->d_frame_parent, pl, (T *)out);
+    IKB_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return IKB_OK;
+}
+
+int check_weights(const double *w, int dim, std::vector<double> &out) {
+    out.assign(dim, 1.0);
+    if (w) std::copy(w, w + dim, out.begin());
+    return IKB_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// exported functions
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *ikb_last_error(void) { return g_err.c_str(); }
+int ikb_version(void) { return IKB_VERSION; }
+int64_t ikb_kernel_launch_count(void) { return g_launches.load(); }
+
+int ikb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void *ikb_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        g_err = "cudaMallocHost failed";
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void ikb_host_free(void *ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
+void ikb_dls_params_default(ikb_dls_params *p) {
+    if (!p) return;
+    p->max_iterations = 100;  // common.hpp:61
+    p->random_restart = 0;    // dls.hpp:27
+    p->max_time = 1.0;        // common.hpp:63
+    p->step_length = 1.0;     // common.hpp:65
+    p->damping = 1e-2;        // dls.hpp:25
+    p->tolerance = 1e-4;      // visitor.hpp:19
+}
+
+int ikb_model_from_urdf(const char *xml, size_t len, int free_flyer, ikb_model **out) {
+    if (!xml || !out) return fail(IKB_ERR_INVALID_ARG, "ikb_model_from_urdf: null argument");
+    try {
+        auto *h = new ikb_model();
+        h->m = model_from_urdf(std::string(xml, len), free_flyer != 0);
+        *out = h;
+        return IKB_OK;
+    } catch (const std::exception &e) {
+        return fail(IKB_ERR_PARSE, e.what());
+    }
+}
+
+int ikb_model_from_desc(const ikb_model_desc *d, ikb_model **out) {
+    if (!d || !out || d->njoints < 1 || !d->parent || !d->jtype || !d->placement)
+        return fail(IKB_ERR_INVALID_ARG, "ikb_model_from_desc: null / empty description");
+    if (d->jtype[0] != IKB_J_UNIVERSE) return fail(IKB_ERR_INVALID_ARG, "joint 0 must be the universe");
+    auto *h = new ikb_model();
+    HostModel &m = h->m;
+    int iq = 0;
+    for (int j = 0; j < d->njoints; ++j) {
+        const int t = d->jtype[j];
+        if (t < IKB_J_UNIVERSE || t > IKB_J_PRIS_UNALIGNED || (j > 0 && (d->parent[j] < 0 || d->parent[j] >= j))) {
+            delete h;
+            return fail(IKB_ERR_INVALID_ARG, "ikb_model_from_desc: bad joint type or parent index (parents must precede children)");
+        }
+        SE3d pl;
+        std::copy(d->placement + 12 * j, d->placement + 12 * j + 12, pl.begin());
+        std::array<double, 3> ax{0, 0, 0};
+        if (d->axis) ax = {d->axis[3 * j], d->axis[3 * j + 1], d->axis[3 * j + 2]};
+        const int n = HostModel::joint_nq(t);
+        std::vector<double> lo(n), hi(n);
+        for (int k = 0; k < n; ++k) {
+            lo[k] = d->lower ? d->lower[iq + k] : -1e300;
+            hi[k] = d->upper ? d->upper[iq + k] : 1e300;
+        }
+        iq += n;
+        m.add_joint(d->joint_names && d->joint_names[j] ? d->joint_names[j] : ("joint" + std::to_string(j)), t,
+                    j == 0 ? 0 : d->parent[j], pl, ax, lo, hi);
+    }
+    for (int f = 0; f < d->nframes; ++f) {
+        if (d->frame_parent[f] < 0 || d->frame_parent[f] >= d->njoints) {
+            delete h;
+            return fail(IKB_ERR_INVALID_ARG, "ikb_model_from_desc: frame parent out of range");
+        }
+        SE3d pl;
+        std::copy(d->frame_placement + 12 * f, d->frame_placement + 12 * f + 12, pl.begin());
+        m.add_frame(d->frame_names && d->frame_names[f] ? d->frame_names[f] : ("frame" + std::to_string(f)),
+                    d->frame_parent[f], pl, FRAME_OP);
+    }
+    if (m.nframes() == 0) m.add_frame("universe", 0, se3_identity(), FRAME_OP);
+    *out = h;
+    return IKB_OK;
+}
+
+void ikb_model_free(ikb_model *m) { delete m; }
+int ikb_model_njoints(const ikb_model *m) { return m ? m->m.njoints() : -IKB_ERR_INVALID_ARG; }
+int ikb_model_nq(const ikb_model *m) { return m ? m->m.nq : -IKB_ERR_INVALID_ARG; }
+int ikb_model_nv(const ikb_model *m) { return m ? m->m.nv : -IKB_ERR_INVALID_ARG; }
+int ikb_model_nframes(const ikb_model *m) { return m ? m->m.nframes() : -IKB_ERR_INVALID_ARG; }
+int ikb_model_frame_id(const ikb_model *m, const char *name) {
+    if (!m || !name) return -IKB_ERR_INVALID_ARG;
+    return m->m.frame_id(name);
+}
+const char *ikb_model_joint_name(const ikb_model *m, int j) {
+    return (m && j >= 0 && j < m->m.njoints()) ? m->m.joint_names[j].c_str() : nullptr;
+}
+const char *ikb_model_frame_name(const ikb_model *m, int f) {
+    return (m && f >= 0 && f < m->m.nframes()) ? m->m.frame_names[f].c_str() : nullptr;
+}
+int ikb_model_get_topology(const ikb_model *m, int32_t *parent, int32_t *jtype, int32_t *idx_q, int32_t *idx_v) {
+    if (!m) return fail(IKB_ERR_INVALID_ARG, "null model");
+    const int n = m->m.njoints();
+    if (parent) std::copy(m->m.parent.begin(), m->m.parent.end(), parent);
+    if (jtype) std::copy(m->m.jtype.begin(), m->m.jtype.end(), jtype);
+    if (idx_q) std::copy(m->m.idx_q.begin(), m->m.idx_q.end(), idx_q);
+    if (idx_v) std::copy(m->m.idx_v.begin(), m->m.idx_v.end(), idx_v);
+    (void)n;
+    return IKB_OK;
+}
+int ikb_model_get_placements(const ikb_model *m, double *placement, double *axis) {
+    if (!m) return fail(IKB_ERR_INVALID_ARG, "null model");
+    for (int j = 0; j < m->m.njoints(); ++j) {
+        if (placement) std::copy(m->m.placement[j].begin(), m->m.placement[j].end(), placement + 12 * j);
+        if (axis) std::copy(m->m.axis[j].begin(), m->m.axis[j].end(), axis + 3 * j);
+    }
+    return IKB_OK;
+}
+int ikb_model_get_limits(const ikb_model *m, double *lower, double *upper) {
+    if (!m) return fail(IKB_ERR_INVALID_ARG, "null model");
+    if (lower) std::copy(m->m.lower.begin(), m->m.lower.end(), lower);
+    if (upper) std::copy(m->m.upper.begin(), m->m.upper.end(), upper);
+    return IKB_OK;
+}
+int ikb_model_set_limits(ikb_model *m, const double *lower, const double *upper) {
+    if (!m) return fail(IKB_ERR_INVALID_ARG, "null model");
+    if (lower) std::copy(lower, lower + m->m.nq, m->m.lower.begin());
+    if (upper) std::copy(upper, upper + m->m.nq, m->m.upper.begin());
+    return IKB_OK;
+}
+int ikb_model_get_frames(const ikb_model *m, int32_t *parent_joint, int32_t *type, double *placement) {
+    if (!m) return fail(IKB_ERR_INVALID_ARG, "null model");
+    for (int f = 0; f < m->m.nframes(); ++f) {
+        if (parent_joint) parent_joint[f] = m->m.frame_parent[f];
+        if (type) type[f] = m->m.frame_type[f];
+        if (placement) std::copy(m->m.frame_placement[f].begin(), m->m.frame_placement[f].end(), placement + 12 * f);
+    }
+    return IKB_OK;
+}
+int ikb_model_neutral(const ikb_model *m, double *q) {
+    if (!m || !q) return fail(IKB_ERR_INVALID_ARG, "null argument");
+    std::fill(q, q + m->m.nq, 0.0);
+    for (int j = 0; j < m->m.njoints(); ++j)
+        if (m->m.jtype[j] == IKB_J_FREEFLYER) q[m->m.idx_q[j] + 6] = 1.0;
+    return IKB_OK;
+}
+
+int ikb_problem_create(const ikb_model *m, int max_priority_level, ikb_problem **out) {
+    if (!m || !out || max_priority_level < 0) return fail(IKB_ERR_INVALID_ARG, "ikb_problem_create: bad argument");
+    auto *p = new ikb_problem();
+    p->hp.model = m->m;  // copy, like InverseKinematicsProblem (problem.hpp:183)
+    p->hp.max_priority_level = max_priority_level;
+    *out = p;
+    return IKB_OK;
+}
+
+void ikb_problem_free(ikb_problem *p) {
+    if (!p) return;
+    if (p->finalized) {
+        DeviceGuard g(p->device);
+        cudaFree(p->d64); cudaFree(p->d32); cudaFree(p->d_frame_parent); cudaFree(p->d_frame_pl64);
+        cudaFree(p->d_frame_pl32); cudaFree(p->d_tickets);
+        cudaFree(p->st64.q0); cudaFree(p->st64.targets); cudaFree(p->st64.q); cudaFree(p->st64.resid);
+        cudaFree(p->st32.q0); cudaFree(p->st32.targets); cudaFree(p->st32.q); cudaFree(p->st32.resid);
+        cudaFree(p->st_success); cudaFree(p->st_iters);
+        if (p->stream) cudaStreamDestroy(p->stream);
+    }
+    delete p;
+}
+
+static int add_task_common(ikb_problem *p, HostTask &t, int priority, const double *weights) {
+    if (p->finalized) return -fail(IKB_ERR_INVALID_ARG, "problem is finalized (immutable)");
+    if (priority < 0 || priority > p->hp.max_priority_level)
+        return -fail(IKB_ERR_INVALID_ARG, "priority exceeds max_priority_level (problem.hpp:160-164)");
+    t.priority = priority;
+    check_weights(weights, t.dim, t.weight);
+    p->hp.tasks.push_back(t);
+    return (int)p->hp.tasks.size() - 1;
+}
+
+int ikb_problem_add_frame_task(ikb_problem *p, int frame, int ktype, int ref, int priority, const double *weights) {
+    if (!p) return -fail(IKB_ERR_INVALID_ARG, "null problem");
+    const int nf = p->hp.model.nframes();
+    if (frame < 0 || frame >= nf || ref < 0 || ref >= nf) return -fail(IKB_ERR_UNKNOWN_FRAME, "frame index out of range");
+    if (ktype < IKB_POSITION || ktype > IKB_FULL) return -fail(IKB_ERR_INVALID_ARG, "bad kinematic type");
+    HostTask t;
+    t.kind = IKB_TASK_FRAME;
+    t.frame = frame;
+    t.ref = ref;
+    t.type = ktype;
+    t.dim = ktype == IKB_FULL ? 6 : 3;  // frame.hpp:100-107
+    t.target_size = 12;
+    return add_task_common(p, t, priority, weights);
+}
+
+int ikb_problem_add_align_axis_task(ikb_problem *p, int frame, int axis, int ref, int priority, const double *weights) {
+    if (!p) return -fail(IKB_ERR_INVALID_ARG, "null problem");
+    const int nf = p->hp.model.nframes();
+    if (frame < 0 || frame >= nf || ref < 0 || ref >= nf) return -fail(IKB_ERR_UNKNOWN_FRAME, "frame index out of range");
+    if (axis < 0 || axis > 2) return -fail(IKB_ERR_INVALID_ARG, "bad axis");
+    HostTask t;
+    t.kind = IKB_TASK_ALIGN_AXIS;
+    t.frame = frame;
+    t.ref = ref;
+    t.type = axis;
+    t.dim = 1;  // frame.hpp:226
+    t.target_size = 3;
+    return add_task_common(p, t, priority, weights);
+}
+
+int ikb_problem_add_posture_task(ikb_problem *p, int nj, int priority, const double *weights, const double *mask) {
+    if (!p) return -fail(IKB_ERR_INVALID_ARG, "null problem");
+    if (nj < 1 || nj > p->hp.model.nv || nj > p->hp.model.nq) return -fail(IKB_ERR_INVALID_ARG, "posture size out of range");
+    HostTask t;
+    t.kind = IKB_TASK_POSTURE;
+    t.type = nj;
+    t.dim = nj;  // posture.hpp:32
+    t.target_size = nj;
+    t.mask.assign(nj, 1.0);
+    if (mask) std::copy(mask, mask + nj, t.mask.begin());
+    return add_task_common(p, t, priority, weights);
+}
+
+int ikb_problem_num_tasks(const ikb_problem *p) { return p ? (int)p->hp.tasks.size() : -IKB_ERR_INVALID_ARG; }
+int ikb_problem_task_dim(const ikb_problem *p, int t) {
+    return (p && t >= 0 && t < (int)p->hp.tasks.size()) ? p->hp.tasks[t].dim : -IKB_ERR_INVALID_ARG;
+}
+int ikb_problem_e_size(const ikb_problem *p, int priority) { return p ? p->hp.e_size(priority) : -IKB_ERR_INVALID_ARG; }
+int ikb_problem_rows(const ikb_problem *p) { return p ? p->hp.rows() : -IKB_ERR_INVALID_ARG; }
+int ikb_problem_target_size(const ikb_problem *p) { return p ? p->hp.target_size() : -IKB_ERR_INVALID_ARG; }
+int ikb_problem_task_target_offset(const ikb_problem *p, int t) {
+    return (p && t >= 0 && t < (int)p->hp.tasks.size()) ? p->hp.target_offset(t) : -IKB_ERR_INVALID_ARG;
+}
+
+int ikb_problem_finalize(ikb_problem *p, int device) {
+    if (!p) return fail(IKB_ERR_INVALID_ARG, "null problem");
+    if (p->finalized) return fail(IKB_ERR_INVALID_ARG, "problem already finalized");
+    const HostProblem &hp = p->hp;
+    const HostModel &m = hp.model;
+    if (hp.tasks.empty()) return fail(IKB_ERR_INVALID_ARG, "problem has no tasks");
+    // stacked order: priority level, then insertion order (dls.cpp:18-24)
+    std::vector<int> order(hp.tasks.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return hp.tasks[a].priority < hp.tasks[b].priority; });
+    std::vector<int> used;
+    for (const auto &t : hp.tasks)
+        if (t.kind != IKB_TASK_POSTURE)
+            for (int f : {t.frame, t.ref})
+                if (std::find(used.begin(), used.end(), f) == used.end()) used.push_back(f);
+    if (used.empty()) used.push_back(0);
+    if (m.njoints() > kMaxJoints || m.nq > kMaxNq || (int)hp.tasks.size() > kMaxTasks || (int)used.size() > kMaxFrames ||
+        hp.rows() > kMaxRows)
+        return fail(IKB_ERR_UNSUPPORTED, "problem exceeds the compiled capacities of the constant blob");
+    int cls = -1;
+    for (int c = 0; c < 3; ++c)
+        if (m.njoints() <= kClasses[c].nj && m.nv <= kClasses[c].nv && hp.rows() <= kClasses[c].m) {
+            cls = c;
+            break;
+        }
+    if (cls < 0)
+        return fail(IKB_ERR_UNSUPPORTED, "problem larger than the generic kernel's largest size class (32 joints, nv 36, 30 rows)");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(IKB_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(IKB_ERR_INVALID_ARG, "device index out of range");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(IKB_ERR_CUDA, "cudaSetDevice failed");
+    cudaDeviceProp prop;
+    IKB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(IKB_ERR_NO_DEVICE, std::string("device ") + prop.name + " is not Blackwell-class (sm_100a code only)");
+    p->sm_count = prop.multiProcessorCount;
+
+    auto *h64 = new DevProblem<double>();
+    auto *h32 = new DevProblem<float>();
+    fill_dev_problem(hp, order, used, *h64);
+    fill_dev_problem(hp, order, used, *h32);
+    IKB_CUDA(cudaMalloc(&p->d64, sizeof(*h64)));
+    IKB_CUDA(cudaMalloc(&p->d32, sizeof(*h32)));
+    IKB_CUDA(cudaMemcpy(p->d64, h64, sizeof(*h64), cudaMemcpyHostToDevice));
+    IKB_CUDA(cudaMemcpy(p->d32, h32, sizeof(*h32), cudaMemcpyHostToDevice));
+    delete h64;
+    delete h32;
+
+    const int nf = m.nframes();
+    std::vector<double> pl64((size_t)nf * 12);
+    std::vector<float> pl32((size_t)nf * 12);
+    for (int f = 0; f < nf; ++f)
+        for (int k = 0; k < 12; ++k) {
+            pl64[12 * f + k] = m.frame_placement[f][k];
+            pl32[12 * f + k] = (float)m.frame_placement[f][k];
+        }
+    IKB_CUDA(cudaMalloc(&p->d_frame_parent, nf * sizeof(int)));
+    IKB_CUDA(cudaMalloc(&p->d_frame_pl64, pl64.size() * sizeof(double)));
+    IKB_CUDA(cudaMalloc(&p->d_frame_pl32, pl32.size() * sizeof(float)));
+    IKB_CUDA(cudaMemcpy(p->d_frame_parent, m.frame_parent.data(), nf * sizeof(int), cudaMemcpyHostToDevice));
+    IKB_CUDA(cudaMemcpy(p->d_frame_pl64, pl64.data(), pl64.size() * sizeof(double), cudaMemcpyHostToDevice));
+    IKB_CUDA(cudaMemcpy(p->d_frame_pl32, pl32.data(), pl32.size() * sizeof(float), cudaMemcpyHostToDevice));
+    IKB_CUDA(cudaMalloc(&p->d_tickets, kTicketSlots * 16 * sizeof(unsigned long long)));
+    IKB_CUDA(cudaMemset(p->d_tickets, 0, kTicketSlots * 16 * sizeof(unsigned long long)));
+    IKB_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+
+    p->size_class = cls;
+    p->device = device;
+    p->spec = find_specialized(hp);
+    char buf[96];
+    std::snprintf(buf, sizeof buf, "generic<NJ=%d,NV=%d,M=%d>", kClasses[cls].nj, kClasses[cls].nv, kClasses[cls].m);
+    p->kernel_name[0] = p->spec ? p->spec->name : buf;
+    p->kernel_name[1] = p->kernel_name[0];
+    p->finalized = true;
+    return IKB_OK;
+}
+
+const char *ikb_problem_kernel_name(const ikb_problem *p, int dtype) {
+    if (!p || !p->finalized || dtype < 0 || dtype > 1) return nullptr;
+    return p->kernel_name[dtype].c_str();
+}
+
+static int check_solve_args(const ikb_problem *p, int dtype, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io) {
+    if (!p || !prm || !io) return fail(IKB_ERR_INVALID_ARG, "null argument");
+    if (!p->finalized) return fail(IKB_ERR_NOT_FINALIZED, "call ikb_problem_finalize first");
+    if (dtype != IKB_F64 && dtype != IKB_F32) return fail(IKB_ERR_INVALID_ARG, "dtype must be IKB_F64 or IKB_F32");
+    if (B < 0 || prm->max_iterations < 0) return fail(IKB_ERR_INVALID_ARG, "negative batch size or iteration count");
+    if (B > 0 && (!io->q0 || !io->q || (!io->targets && p->hp.target_size() > 0)))
+        return fail(IKB_ERR_INVALID_ARG, "q0, targets and q must be non-null");
+    return IKB_OK;
+}
+
+int ikb_dls_solve_batch(const ikb_problem *p, int dtype, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io,
+                        void *cuda_stream) {
+    int rc = check_solve_args(p, dtype, prm, B, io);
+    if (rc) return rc;
+    if (B == 0) return IKB_OK;
+    DeviceGuard g(p->device);
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    return dtype == IKB_F64 ? launch_solve<double>(p, prm, B, io, s) : launch_solve<float>(p, prm, B, io, s);
+}
+
+int ikb_dls_solve_batch_host(ikb_problem *p, int dtype, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io) {
+    int rc = check_solve_args(p, dtype, prm, B, io);
+    if (rc) return rc;
+    if (B == 0) return IKB_OK;
+    DeviceGuard g(p->device);
+    return dtype == IKB_F64 ? solve_host<double>(p, prm, B, io) : solve_host<float>(p, prm, B, io);
+}
+
+int ikb_dls_solve(ikb_problem *p, const ikb_dls_params *prm, const double *q0, const double *targets, double *q_out,
+                  int *success, int *iters, double *resid) {
+    if (!p) return fail(IKB_ERR_INVALID_ARG, "null problem");
+    ikb_dls_params dflt;
+    ikb_dls_params_default(&dflt);
+    const int nq = p->hp.model.nq, tsz = p->hp.target_size();
+    uint8_t ok = 0;
+    int32_t it = 0;
+    double r = 0;
+    ikb_batch_io io;
+    io.q0 = q0; io.q0_elem_stride = 1; io.q0_batch_stride = nq;
+    io.targets = targets; io.targets_elem_stride = 1; io.targets_batch_stride = tsz;
+    io.q = q_out; io.q_elem_stride = 1; io.q_batch_stride = nq;
+    io.success = &ok; io.iters = &it; io.resid = &r;
+    int rc = ikb_dls_solve_batch_host(p, IKB_F64, prm ? prm : &dflt, 1, &io);
+    if (rc) return rc;
+    if (success) *success = ok;
+    if (iters) *iters = it;
+    if (resid) *resid = r;
+    return IKB_OK;
+}
+
+int ikb_fk_batch(const ikb_problem *p, int dtype, int64_t B, const void *q, int64_t es, int64_t bs, int nf,
+                 const int32_t *frames, void *out, void *cuda_stream) {
+    if (!p || !q || !out || !frames) return fail(IKB_ERR_INVALID_ARG, "null argument");
+    if (!p->finalized) return fail(IKB_ERR_NOT_FINALIZED, "call ikb_problem_finalize first");
+    if (nf < 1 || nf > 16) return fail(IKB_ERR_INVALID_ARG, "between 1 and 16 frames per call");
+    FrameList fl;
+    fl.n = nf;
+    for (int i = 0; i < nf; ++i) {
+        if (frames[i] < 0 || frames[i] >= p->hp.model.nframes()) return fail(IKB_ERR_UNKNOWN_FRAME, "frame index out of range");
+        fl.id[i] = frames[i];
+    }
+    if (B <= 0) return IKB_OK;
+    DeviceGuard g(p->device);
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    return dtype == IKB_F64 ? launch_fk<double>(p, B, q, es, bs, fl, out, s) : launch_fk<float>(p, B, q, es, bs, fl, out, s);
+}
+
+}  // extern "C"

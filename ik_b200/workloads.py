@@ -1,0 +1,131 @@
+"""Synthetic IK workloads of BASELINE.json, generated identically for the CPU oracle and the GPU.
+
+Per problem b (counter-based SplitMix64 keyed by (seed, b, k), so any shard of a batch can be generated
+independently): a reachable configuration q* with revolute joints uniform inside the URDF limits, base
+position uniform in [-0.2, 0.2]^3 m and base orientation exp3(u), u uniform in [-0.3, 0.3]^3 rad; the task
+targets are the task frames' placements at q* expressed in ``universe``.  Position tasks get the target
+(Identity, p) -- the reference's FrameTask keeps ``target`` at se3_t::Identity() and callers only set the
+translation (ik_ros/src/cassie.cpp:95-96).  The initial guess is the SRDF standing pose with an identity base.
+"""
+import numpy as np
+
+from .api import FrameTask, InverseKinematicsProblem, KinematicType, Model
+
+# cassie-description/srdf/cassie.srdf:22-39 (group_state "default"), in model joint order
+CASSIE_STANDING = [0.0045, 0.0, 0.4973, -1.1997, 0.0, 1.4267, 0.0, -1.5968,
+                   -0.0045, 0.0, 0.4973, -1.1997, 0.0, 1.4267, 0.0, -1.5968]
+
+J_FREEFLYER = 1
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def splitmix64(x):
+    """SplitMix64 finaliser on uint64 arrays."""
+    with np.errstate(over="ignore"):
+        z = (x + np.uint64(0x9E3779B97F4A7C15)) & _M64
+        z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+        z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+        return z ^ (z >> np.uint64(31))
+
+
+def uniform01(seed, b, k):
+    """Deterministic U[0,1) for problem index array ``b`` and stream index ``k``."""
+    with np.errstate(over="ignore"):
+        key = splitmix64(np.uint64(seed) + np.uint64(0x632BE59BD9B4E019) * np.uint64(k + 1))
+        x = splitmix64(key ^ (b.astype(np.uint64) * np.uint64(0xD1342543DE82EF95)))
+    return (x >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def sample_configurations(model, B, seed=12345, b0=0, margin=0.0):
+    """q* [B, nq] as described in the module docstring (problem indices b0 .. b0+B-1)."""
+    b = np.arange(b0, b0 + B, dtype=np.uint64)
+    q = np.zeros((B, model.nq))
+    lo, hi = model.lowerPositionLimit, model.upperPositionLimit
+    k = 0
+    for j in range(1, model.njoints):
+        iq = int(model.idx_qs[j])
+        if model.jtypes[j] == J_FREEFLYER:
+            for i in range(3):
+                q[:, iq + i] = -0.2 + 0.4 * uniform01(seed, b, k)
+                k += 1
+            u = np.stack([-0.3 + 0.6 * uniform01(seed, b, k + i) for i in range(3)], axis=1)
+            k += 3
+            th = np.linalg.norm(u, axis=1)
+            s = np.where(th > 1e-12, np.sin(th / 2) / np.maximum(th, 1e-300), 0.5)
+            q[:, iq + 3:iq + 6] = u * s[:, None]
+            q[:, iq + 6] = np.cos(th / 2)
+        else:
+            w = hi[iq] - lo[iq]
+            q[:, iq] = lo[iq] + margin * w + (1 - 2 * margin) * w * uniform01(seed, b, k)
+            k += 1
+    return q
+
+
+def standing_configuration(model, standing=None):
+    q0 = model.neutral()
+    if standing is not None:
+        q0[model.nq - len(standing):] = standing
+    return q0
+
+
+def cassie_model():
+    return Model.builtin("cassie", free_flyer=True)
+
+
+def cassie_feet_pelvis_problem(model=None):
+    """BASELINE.json configs 1-3: pelvis pose (Full) + both foot-front positions, all in ``universe``."""
+    model = model or cassie_model()
+    pb = InverseKinematicsProblem(model, 0)
+    pb.add_frame_task("pelvis", FrameTask(model, "pelvis", KinematicType.Full))
+    pb.add_frame_task("fl", FrameTask(model, "LeftFootFront", KinematicType.Position))
+    pb.add_frame_task("fr", FrameTask(model, "RightFootFront", KinematicType.Position))
+    return pb
+
+
+def humanoid_problem(model=None, root_task=True):
+    """BASELINE.json config 4: 4 end-effector poses (Full) (+ root pose) on the 32-DoF humanoid: 24 / 30 rows."""
+    model = model or Model.builtin("humanoid", free_flyer=True)
+    pb = InverseKinematicsProblem(model, 0)
+    if root_task:
+        pb.add_frame_task("root", FrameTask(model, "torso_root", KinematicType.Full))
+    for ee in ("lleg_effector", "rleg_effector", "larm_effector", "rarm_effector"):
+        pb.add_frame_task(ee, FrameTask(model, ee, KinematicType.Full))
+    return pb
+
+
+def manipulator_problem(model=None):
+    """BASELINE.json config 5: one Full frame task on the fixed-base 7-DoF arm."""
+    model = model or Model.builtin("manipulator", free_flyer=False)
+    pb = InverseKinematicsProblem(model, 0)
+    pb.add_frame_task("tool", FrameTask(model, "tool", KinematicType.Full))
+    return pb
+
+
+def frame_task_list(problem):
+    return [(t, problem.target_offset(t)) for _, t, _ in problem._tasks if isinstance(t, FrameTask)]
+
+
+def targets_from_frame_poses(problem, poses):
+    """poses: dict frame name -> [B, 12] world placements at q*.  Returns targets [B, tsz] (AoS)."""
+    B = next(iter(poses.values())).shape[0]
+    tg = np.zeros((B, problem.target_size))
+    for t, off in frame_task_list(problem):
+        M = poses[t.frame]
+        if t.type == KinematicType.Full:
+            tg[:, off:off + 12] = M
+        else:
+            tg[:, off:off + 9] = np.eye(3).reshape(-1)
+            if t.type == KinematicType.Position:
+                tg[:, off + 9:off + 12] = M[:, 9:12]
+            else:
+                tg[:, off:off + 9] = M[:, :9]
+    return tg
+
+
+def task_frames(problem):
+    names = []
+    for t, _ in frame_task_list(problem):
+        if t.frame not in names:
+            names.append(t.frame)
+    return names

@@ -1,0 +1,184 @@
+/*
+ * ikb200.h -- C ABI of the B200-native batched inverse-kinematics engine (libikb200.so).
+ *
+ * This is the drop-in boundary for the damped-least-squares IK path of dazzmo/ik ("Puppeteer").  The
+ * reference has no FFI of its own: its boundary is the C++ API in namespace ik (target ik::ik,
+ * ik/ik/CMakeLists.txt:37).  Each entry point below names the reference interface it replaces; the C++
+ * facade in include/ik/ re-creates the reference's class names on top of these calls and
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Rules of the ABI: plain pointers and sizes only; opaque handles; every call returns an ikb_status (or a
+ * non-negative index / size where documented; negative values are -ikb_status); no exceptions cross the
+ * boundary; ikb_last_error() returns a thread-local message for the last failing call.  A model / problem
+ * handle is immutable once ikb_problem_finalize() has run, so concurrent solves on different CUDA streams
+ * are safe.  There is NO CPU fallback: solve entry points fail with IKB_ERR_CUDA / IKB_ERR_NO_DEVICE when
+ * no B200-class device is usable.
+ *
+ * Conventions (same as Pinocchio's, which the reference inherits): SE3 = 12 scalars, rotation row-major
+ * R[0..8] then translation p[0..2]; spatial vectors are [linear; angular]; a free-flyer root uses
+ * q = [x y z, qx qy qz qw] (reference ik_ros/src/cassie.cpp:68-70) and a LOCAL-frame 6-vector tangent.
+ */
+#ifndef IKB200_H
+#define IKB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IKB_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+    IKB_OK = 0,
+    IKB_ERR_INVALID_ARG = 1,
+    IKB_ERR_PARSE = 2,         /* malformed URDF */
+    IKB_ERR_UNKNOWN_FRAME = 3, /* the reference silently indexes out of range here (problem.hpp:85-92) */
+    IKB_ERR_UNSUPPORTED = 4,   /* joint type / size outside what the kernels handle */
+    IKB_ERR_CUDA = 5,
+    IKB_ERR_NO_DEVICE = 6,
+    IKB_ERR_NOT_FINALIZED = 7
+} ikb_status;
+
+/* joint types of the flattened tree (Pinocchio JointModel* equivalents) */
+typedef enum {
+    IKB_J_UNIVERSE = 0, IKB_J_FREEFLYER = 1, IKB_J_RX = 2, IKB_J_RY = 3, IKB_J_RZ = 4, IKB_J_REV_UNALIGNED = 5,
+    IKB_J_PX = 6, IKB_J_PY = 7, IKB_J_PZ = 8, IKB_J_PRIS_UNALIGNED = 9
+} ikb_joint_type;
+
+/* ik::KinematicType, reference ik/ik/frame.hpp:20 */
+typedef enum { IKB_POSITION = 0, IKB_ORIENTATION = 1, IKB_FULL = 2 } ikb_kinematic_type;
+/* ik::AlignAxisType, reference ik/ik/frame.hpp:202 */
+typedef enum { IKB_AXIS_X = 0, IKB_AXIS_Y = 1, IKB_AXIS_Z = 2 } ikb_axis;
+typedef enum { IKB_TASK_FRAME = 0, IKB_TASK_ALIGN_AXIS = 1, IKB_TASK_POSTURE = 2 } ikb_task_kind;
+typedef enum { IKB_F64 = 0, IKB_F32 = 1 } ikb_dtype;
+
+typedef struct ikb_model ikb_model;     /* replaces ik::model_t = pinocchio::Model (common.hpp:17) */
+typedef struct ikb_problem ikb_problem; /* replaces ik::InverseKinematicsProblem (problem.hpp:9-206) */
+
+/* ik::dls_parameters : default_solver_parameters (dls.hpp:24-28, common.hpp:59-66).  max_time and
+ * random_restart are carried for layout compatibility; the reference never reads them either. */
+typedef struct {
+    int32_t max_iterations; /* 100 */
+    int32_t random_restart; /* 0, unused */
+    double max_time;        /* 1.0, unused */
+    double step_length;     /* 1.0 */
+    double damping;         /* 1e-2 */
+    double tolerance;       /* squared-norm stop threshold of inverse_kinematics_visitor::should_stop, 1e-4 (visitor.hpp:19) */
+} ikb_dls_params;
+
+void ikb_dls_params_default(ikb_dls_params *p);
+
+/* Flat description of a kinematic tree, for callers that already own a parsed model. */
+typedef struct {
+    int32_t njoints; /* including universe joint 0 */
+    const int32_t *parent;   /* [njoints] */
+    const int32_t *jtype;    /* [njoints] ikb_joint_type */
+    const double *placement; /* [njoints][12] */
+    const double *axis;      /* [njoints][3], unaligned joints only (may be NULL otherwise) */
+    const double *lower;     /* [nq] */
+    const double *upper;     /* [nq] */
+    const char *const *joint_names; /* [njoints] or NULL */
+    int32_t nframes;
+    const int32_t *frame_parent;     /* [nframes] supporting joint */
+    const double *frame_placement;   /* [nframes][12] */
+    const char *const *frame_names;  /* [nframes] */
+} ikb_model_desc;
+
+/* ---- model (host only) ------------------------------------------------------------------------- */
+/* pinocchio::urdf::buildModelFromXML(xml, JointModelFreeFlyer(), model), reference ik_ros/src/cassie.cpp:34-35.
+ * free_flyer = 0 builds the fixed-base model (buildModelFromXML(xml, model)). */
+int ikb_model_from_urdf(const char *xml, size_t len, int free_flyer, ikb_model **out);
+int ikb_model_from_desc(const ikb_model_desc *desc, ikb_model **out);
+void ikb_model_free(ikb_model *m);
+int ikb_model_njoints(const ikb_model *m);
+int ikb_model_nq(const ikb_model *m); /* model.nq */
+int ikb_model_nv(const ikb_model *m); /* model.nv */
+int ikb_model_nframes(const ikb_model *m);
+/* model.getFrameId(name) (reference common.hpp:50): index of the first frame with that name, nframes if absent */
+int ikb_model_frame_id(const ikb_model *m, const char *name);
+const char *ikb_model_joint_name(const ikb_model *m, int joint);
+const char *ikb_model_frame_name(const ikb_model *m, int frame);
+int ikb_model_get_topology(const ikb_model *m, int32_t *parent, int32_t *jtype, int32_t *idx_q, int32_t *idx_v);
+int ikb_model_get_placements(const ikb_model *m, double *placement /*[njoints][12]*/, double *axis /*[njoints][3]*/);
+/* model.lowerPositionLimit / upperPositionLimit (reference common.hpp:54-55) */
+int ikb_model_get_limits(const ikb_model *m, double *lower, double *upper);
+int ikb_model_set_limits(ikb_model *m, const double *lower, const double *upper);
+int ikb_model_get_frames(const ikb_model *m, int32_t *parent_joint, int32_t *type, double *placement /*[nframes][12]*/);
+int ikb_model_neutral(const ikb_model *m, double *q); /* pinocchio::neutral: zeros, unit quaternion */
+
+/* ---- problem (host only until finalize) --------------------------------------------------------- */
+/* InverseKinematicsProblem(model, max_priority_level), reference problem.hpp:17-22 (copies the model) */
+int ikb_problem_create(const ikb_model *m, int max_priority_level, ikb_problem **out);
+void ikb_problem_free(ikb_problem *p);
+/* FrameTask(model, frame, type, reference_frame) + add_frame_task(name, task, priority): frame.hpp:89-111,
+ * problem.hpp:55-66.  weights: `dim` per-row weights (Task::weighting(), task.hpp:40) or NULL for ones.
+ * Returns the task index (>= 0) or -ikb_status. */
+int ikb_problem_add_frame_task(ikb_problem *p, int frame, int kinematic_type, int reference_frame, int priority,
+                               const double *weights);
+/* AlignAxisTask + add_align_axis_task: frame.hpp:210-319, problem.hpp:94-105 */
+int ikb_problem_add_align_axis_task(ikb_problem *p, int frame, int axis, int reference_frame, int priority,
+                                    const double *weights);
+/* PostureTask(model, nj) + add_posture_task: posture.hpp:17-86, problem.hpp:134-145.  mask: nj entries or NULL */
+int ikb_problem_add_posture_task(ikb_problem *p, int nj, int priority, const double *weights, const double *mask);
+int ikb_problem_num_tasks(const ikb_problem *p);
+int ikb_problem_task_dim(const ikb_problem *p, int task);            /* Task::dimension(), task.hpp:38 */
+int ikb_problem_e_size(const ikb_problem *p, int priority);          /* problem.hpp:34-40 */
+int ikb_problem_rows(const ikb_problem *p);                          /* sum of e_size over levels (dls.hpp:37-41) */
+int ikb_problem_target_size(const ikb_problem *p);                   /* scalars of target data per IK problem */
+int ikb_problem_task_target_offset(const ikb_problem *p, int task);  /* FRAME: 12 (SE3), ALIGN_AXIS: 3, POSTURE: nj */
+/* Upload the problem constants to CUDA device `device` and select the kernel.  After this the handle is immutable. */
+int ikb_problem_finalize(ikb_problem *p, int device);
+/* Name of the kernel variant ikb_dls_solve_batch will launch for `dtype` ("generic<...>", "cassie_feet_pelvis", ...) */
+const char *ikb_problem_kernel_name(const ikb_problem *p, int dtype);
+
+/* ---- batched solve ------------------------------------------------------------------------------- */
+/* Strided views: element k of problem b lives at base[k*elem_stride + b*batch_stride] (strides in elements).
+ * SoA batch-major [k][B] is (elem_stride=B, batch_stride=1) -- the coalesced layout the kernels are tuned for;
+ * AoS [B][k] is (1, k_count).  batch_stride = 0 broadcasts one vector to the whole batch. */
+typedef struct {
+    const void *q0;      int64_t q0_elem_stride, q0_batch_stride;           /* nq scalars per problem */
+    const void *targets; int64_t targets_elem_stride, targets_batch_stride; /* ikb_problem_target_size scalars */
+    void *q;             int64_t q_elem_stride, q_batch_stride;             /* result configuration (dls.cpp:63,77) */
+    uint8_t *success;  /* [B] problem_data::success (data.hpp:18); may be NULL */
+    int32_t *iters;    /* [B] steps taken (dls.cpp:14 loop index at exit); may be NULL */
+    void *resid;       /* [B] ||e[0]||^2 at the last evaluation (visitor.hpp:19); may be NULL */
+} ikb_batch_io;
+
+/* Batched ik::dls (reference dls.cpp:5-78 looped over B independent problems).  All pointers in `io` are DEVICE
+ * pointers of scalar type `dtype`; the call enqueues on `cuda_stream` (a cudaStream_t, NULL = default stream)
+ * and returns without synchronising. */
+int ikb_dls_solve_batch(const ikb_problem *p, int dtype, const ikb_dls_params *params, int64_t B,
+                        const ikb_batch_io *io, void *cuda_stream);
+/* Same with HOST pointers: copies inputs to the device, solves, copies results back and synchronises.  This is
+ * the call a user of the reference's API makes; staging buffers are owned by the problem handle.
+ * Not re-entrant on one handle (like ik::dls on one dls_data, SURVEY 8b "Threading"). */
+int ikb_dls_solve_batch_host(ikb_problem *p, int dtype, const ikb_dls_params *params, int64_t B,
+                             const ikb_batch_io *io);
+/* vector_t ik::dls(problem, q0, data, visitor, params) for ONE problem in FP64 (reference dls.hpp:111-114):
+ * a batch of 1 through the host path.  dq (nv, may be NULL) receives problem_data::dq. */
+int ikb_dls_solve(ikb_problem *p, const ikb_dls_params *params, const double *q0, const double *targets,
+                  double *q_out, int *success, int *iters, double *resid);
+
+/* pinocchio::framesForwardKinematics (reference data.cpp:28-29) for a batch: placements of `nf` frames.
+ * q: device, strided as above; out: device SoA [nf*12][B] (frame-major, then the 12 SE3 scalars). */
+int ikb_fk_batch(const ikb_problem *p, int dtype, int64_t B, const void *q, int64_t q_elem_stride,
+                 int64_t q_batch_stride, int nf, const int32_t *frames, void *out, void *cuda_stream);
+
+/* ---- utilities ------------------------------------------------------------------------------------ */
+const char *ikb_last_error(void);
+int ikb_version(void);
+int ikb_device_count(void);
+void *ikb_host_alloc(size_t bytes); /* pinned host memory for the *_host entry points */
+void ikb_host_free(void *ptr);
+/* FMA-pipe throughput of `device` in TFLOP/s for IKB_F64 / IKB_F32 (mul+add = 2 FLOP): the measured denominator
+ * of the compute roofline the IK kernels are judged against. */
+int ikb_measure_fma_peak(int dtype, int device, double *tflops);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+int64_t ikb_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IKB200_H */

@@ -1,0 +1,234 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): converged/failed flags exactly equal; final joint vectors within 1e-6 rad (FP64)
+/ 1e-4 rad (FP32) wherever the two solvers stopped at the same iteration; residuals within the stated tolerance.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import ik_b200 as ik
+from ik_b200 import workloads as W
+from oracle import oracle as O
+from tests.common import make_workload, oracle_model, oracle_problem_like
+
+pytestmark = pytest.mark.gpu
+NT = os.cpu_count() or 1
+
+
+def _torch():
+    import torch
+
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _solve_gpu(pb, q0, tg, params=None, dtype="f64"):
+    torch = _torch()
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    dev = torch.device("cuda:0")
+    out = ik.dls_batch(pb, torch.tensor(q0.T.copy(), dtype=tdt, device=dev),
+                       torch.tensor(tg.T.copy(), dtype=tdt, device=dev), params)
+    torch.cuda.synchronize()
+    return (out["q"].cpu().numpy().T.astype(np.float64), out["success"].cpu().numpy().astype(bool),
+            out["iters"].cpu().numpy(), out["resid"].cpu().numpy().astype(np.float64))
+
+
+def _compare(name, gpu, ref, qtol, flag_mismatch_allowed=0, min_same_frac=0.99):
+    q, ok, it, res = gpu
+    q_ref, ok_ref, it_ref, res_ref = ref
+    B = len(ok)
+    flag_mismatch = int((ok != ok_ref).sum())
+    same = (it == it_ref) & (ok == ok_ref)
+    qerr = float(np.abs(q[same] - q_ref[same]).max()) if same.any() else 0.0
+    conv = same & ok
+    rerr = float(np.abs(res[conv] - res_ref[conv]).max()) if conv.any() else 0.0
+    print("%s: B=%d converged gpu/ref=%d/%d flag mismatches=%d same-iteration=%d (%.4f) max|q-q_ref|=%.3e "
+          "max|resid diff|=%.3e mean iters=%.2f" % (name, B, ok.sum(), ok_ref.sum(), flag_mismatch, same.sum(),
+                                                    same.mean(), qerr, rerr, it_ref.mean()))
+    assert flag_mismatch <= flag_mismatch_allowed
+    assert same.mean() >= min_same_frac
+    assert qerr < qtol
+    return qerr
+
+
+def test_fk_matches_oracle():
+    torch = _torch()
+    pb = W.cassie_feet_pelvis_problem()
+    om = oracle_model("cassie")
+    qs = W.sample_configurations(pb.model(), 512, seed=7)
+    names = ["pelvis", "LeftFootFront", "RightFootFront", "LeftFootBack", "VectorNav"]
+    out = ik.fk_batch(pb, torch.tensor(qs.T.copy(), device="cuda:0"), names)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().reshape(len(names), 12, -1)
+    for i, n in enumerate(names):
+        ref = np.stack([om.frame_placement(q, om.frame_id(n)) for q in qs])
+        assert np.abs(got[i].T - ref).max() < 1e-13, n
+
+
+def test_single_solve_known_answer():
+    """BASELINE config 1 / SURVEY 8c: one Cassie solve, library defaults -> success after 1 step."""
+    pb = W.cassie_feet_pelvis_problem()
+    om = oracle_model("cassie")
+    q0 = W.standing_configuration(pb.model(), W.CASSIE_STANDING)
+    lf = om.frame_placement(q0, om.frame_id("LeftFootFront"))[9:]
+    rf = om.frame_placement(q0, om.frame_id("RightFootFront"))[9:]
+    pb.get_frame_task("fl").target[9:] = lf + np.array([0.05, 0.0, 0.10])
+    pb.get_frame_task("fr").target[9:] = rf
+    data = ik.dls_data(pb)
+    q = ik.dls(pb, q0, data)
+    assert data.success and data.iterations == 1
+    assert abs(data.residual - 5.5754e-05) < 1e-8
+    np.testing.assert_allclose(q[7:11], [1.034213001968e-02, -2.487453189466e-03, 4.961980803968e-01,
+                                         -1.227703791318], atol=1e-9)
+    opb = oracle_problem_like(pb, om)
+    q_ref, ok, it, res, _ = O.dls(opb, q0, pb.gather_targets())
+    assert ok and it == 1 and np.abs(q - q_ref).max() < 1e-12
+    # demo parameters (cassie.cpp:107-109) -> success at iteration 27
+    data2 = ik.dls_data(pb)
+    ik.dls(pb, q0, data2, p=ik.dls_parameters(max_iterations=200, step_length=0.1, damping=0.1))
+    assert data2.success and data2.iterations == 27
+
+
+def test_start_converged_returns_q0():
+    """A solve that starts converged returns q0 with zero iterations (dls.cpp:52-63)."""
+    pb = W.cassie_feet_pelvis_problem()
+    om = oracle_model("cassie")
+    q0 = W.standing_configuration(pb.model(), W.CASSIE_STANDING)
+    for name, frame in (("fl", "LeftFootFront"), ("fr", "RightFootFront")):
+        pb.get_frame_task(name).target[9:] = om.frame_placement(q0, om.frame_id(frame))[9:]
+    data = ik.dls_data(pb)
+    q = ik.dls(pb, q0, data)
+    assert data.success and data.iterations == 0 and np.array_equal(q, q0)
+
+
+@pytest.mark.parametrize("B", [1, 33, 4096])
+def test_cassie_f64_defaults(B):
+    pb = W.cassie_feet_pelvis_problem()
+    om = oracle_model("cassie")
+    opb = oracle_problem_like(pb, om)
+    q0, tg, _ = make_workload(pb, om, B, standing=W.CASSIE_STANDING)
+    ref = O.dls_batch(opb, q0, tg, nthreads=NT)
+    _compare("cassie f64 defaults B=%d" % B, _solve_gpu(pb, q0, tg), ref, 1e-6)
+
+
+def test_cassie_f64_demo_params():
+    pb = W.cassie_feet_pelvis_problem()
+    om = oracle_model("cassie")
+    opb = oracle_problem_like(pb, om)
+    q0, tg, _ = make_workload(pb, om, 1024, seed=99, standing=W.CASSIE_STANDING)
+    prm = ik.dls_parameters(max_iterations=200, step_length=0.1, damping=0.1)
+    ref = O.dls_batch(opb, q0, tg, O.params(200, 0.1, 0.1), nthreads=NT)
+    _compare("cassie f64 demo params", _solve_gpu(pb, q0, tg, prm), ref, 1e-6)
+
+
+def test_cassie_f32_defaults():
+    """FP32: 1e-4 rad where the stop iteration agrees; the discrete stop decision may differ on a few problems
+    (SURVEY 7 'FP32 parity of the discrete stop decision') -- the mismatch rate is printed and bounded."""
+    pb = W.cassie_feet_pelvis_problem()
+    om = oracle_model("cassie")
+    opb = oracle_problem_like(pb, om)
+    B = 4096
+    q0, tg, _ = make_workload(pb, om, B, standing=W.CASSIE_STANDING)
+    ref = O.dls_batch(opb, q0, tg, nthreads=NT)
+    gpu = _solve_gpu(pb, q0, tg, dtype="f32")
+    q, ok, it, res = gpu
+    q_ref, ok_ref, it_ref, res_ref = ref
+    same = (it == it_ref) & ok & ok_ref
+    qerr = np.abs(q[same] - q_ref[same]).max()
+    print("cassie f32: converged gpu/ref=%d/%d flag mismatches=%d same-iteration=%.4f max|q-q_ref|=%.3e"
+          % (ok.sum(), ok_ref.sum(), (ok != ok_ref).sum(), same.mean(), qerr))
+    assert same.mean() > 0.95
+    assert qerr < 1e-4
+    assert (ok != ok_ref).mean() < 0.01
+    assert np.all(res[ok] < 1e-4)
+
+
+def test_host_path_layouts_agree():
+    pb = W.cassie_feet_pelvis_problem()
+    om = oracle_model("cassie")
+    q0, tg, _ = make_workload(pb, om, 257, seed=3, standing=W.CASSIE_STANDING)
+    a = ik.dls_batch_host(pb, q0, tg, layout="aos")
+    s = ik.dls_batch_host(pb, q0.T, tg.T, layout="soa")
+    d = _solve_gpu(pb, q0, tg)
+    assert np.array_equal(a["q"], s["q"].T) and np.array_equal(a["q"], d[0])
+    assert np.array_equal(a["success"], s["success"]) and np.array_equal(a["iters"], d[2])
+    assert np.array_equal(a["resid"], d[3])
+
+
+def test_humanoid_f64():
+    pb = W.humanoid_problem()
+    om = oracle_model("humanoid")
+    opb = oracle_problem_like(pb, om)
+    q0, tg, _ = make_workload(pb, om, 512, seed=5)
+    ref = O.dls_batch(opb, q0, tg, nthreads=NT)
+    _compare("humanoid f64", _solve_gpu(pb, q0, tg), ref, 1e-6, min_same_frac=0.97)
+
+
+def test_manipulator_f64():
+    pb = W.manipulator_problem()
+    om = oracle_model("manipulator", free_flyer=False)
+    opb = oracle_problem_like(pb, om)
+    q0, tg, _ = make_workload(pb, om, 2048, seed=11)
+    ref = O.dls_batch(opb, q0, tg, nthreads=NT)
+    _compare("manipulator f64", _solve_gpu(pb, q0, tg), ref, 1e-6, min_same_frac=0.97)
+
+
+def test_ur5_orientation_and_weights():
+    """Second parser fixture (RY joints, ur5.urdf:93) with an Orientation task, a Position task and row weights."""
+    m = ik.Model.builtin("ur5", free_flyer=False)
+    pb = ik.InverseKinematicsProblem(m, 1)
+    t_ori = ik.FrameTask(m, "ee_link", ik.KinematicType.Orientation)
+    t_pos = ik.FrameTask(m, "tool0", ik.KinematicType.Position)
+    t_pos.weighting()[:] = [1.0, 0.5, 2.0]
+    pb.add_frame_task("ori", t_ori, 1)
+    pb.add_frame_task("pos", t_pos, 0)
+    om = oracle_model("ur5", free_flyer=False)
+    opb = oracle_problem_like(pb, om)
+    B = 1024
+    lo = m.lowerPositionLimit
+    hi = m.upperPositionLimit
+    m.set_limits(np.maximum(lo, -3.0), np.minimum(hi, 3.0))
+    om.flat["lower"][:] = np.maximum(lo, -3.0)
+    om.flat["upper"][:] = np.minimum(hi, 3.0)
+    om = O.Model(om.flat)
+    opb = oracle_problem_like(pb, om)
+    q0, tg, _ = make_workload(pb, om, B, seed=21)
+    q0[:] = 0.3
+    ref = O.dls_batch(opb, q0, tg, nthreads=NT)
+    _compare("ur5 mixed tasks", _solve_gpu(pb, q0, tg), ref, 1e-6, min_same_frac=0.9)
+
+
+def test_full_size_properties():
+    """BASELINE full size (65,536): size-independent properties instead of a CPU loop -- every converged problem
+    satisfies ||e||^2 < 1e-4 when its residual is recomputed by GPU FK from the returned q, flags/iteration counts
+    are consistent, and the first 2,048 problems equal a separate small solve (batch-size independence)."""
+    torch = _torch()
+    pb = W.cassie_feet_pelvis_problem()
+    om = oracle_model("cassie")
+    B = 65536
+    m = pb.model()
+    qstar = W.sample_configurations(m, B)
+    dev = torch.device("cuda:0")
+    names = W.task_frames(pb)
+    poses_t = ik.fk_batch(pb, torch.tensor(qstar.T.copy(), device=dev), names)
+    poses = {n: poses_t[12 * i:12 * i + 12].T.cpu().numpy() for i, n in enumerate(names)}
+    tg = W.targets_from_frame_poses(pb, poses)
+    q0 = np.tile(W.standing_configuration(m, W.CASSIE_STANDING), (B, 1))
+    q, ok, it, res = _solve_gpu(pb, q0, tg)
+    assert ok.mean() > 0.97
+    assert np.all(res[ok] < 1e-4) and np.all(it[~ok] == 100) and np.all(it[ok] < 100)
+    # recompute the position residual of the feet at the returned q
+    got = ik.fk_batch(pb, torch.tensor(q.T.copy(), device=dev), names).cpu().numpy()
+    for i, n in enumerate(names):
+        if n == "pelvis":
+            continue
+        perr = np.linalg.norm(got[12 * i + 9:12 * i + 12].T - poses[n][:, 9:12], axis=1)
+        assert np.all(perr[ok] < 2e-2)
+    q2, ok2, it2, res2 = _solve_gpu(pb, q0[:2048], tg[:2048])
+    assert np.array_equal(q2, q[:2048]) and np.array_equal(ok2, ok[:2048]) and np.array_equal(it2, it[:2048])
+    # lower/upper limits hold for every returned revolute joint (common.hpp:53-56)
+    lo, hi = m.lowerPositionLimit, m.upperPositionLimit
+    moved = it > 0
+    assert np.all(q[moved][:, 7:] >= lo[7:] - 1e-15) and np.all(q[moved][:, 7:] <= hi[7:] + 1e-15)
