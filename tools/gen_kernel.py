@@ -1,0 +1,499 @@
+#!/usr/bin/env python3
+"""Generate a topology-specialised DLS IK kernel body (CUDA C++) for one (robot, task list) pair.
+
+    python tools/gen_kernel.py <flat_model.json> <spec.json> <out.cuh>
+
+The generic kernel (ik_b200/csrc/dls_generic.cuh) walks the kinematic tree through tables and keeps its
+per-problem scratch in local memory.  For the benchmark robots that is 50x away from the FP64 roofline, so the
+hot path is specialised: this script unrolls the reference's evaluate -> solve iteration (dls.cpp:14-64,
+data.cpp:25-58, frame.hpp:37-62,152-182) for a FIXED tree and FIXED frame-task list into straight-line code:
+
+* joint placements are compile-time constants, folded into the arithmetic (exact zeros / ones of the URDF vanish);
+* only joints that support a task frame are visited, only structurally non-zero Jacobian entries exist;
+* the task Jacobian never materialises the 6 x nv frame Jacobian: with M1 = A R_f^T, M2 = B R_f^T (A, B the blocks
+  of Jlog6(tMf)) a revolute column is  top = -(M1 ((p_j - p_f) x z_j) + M2 z_j),  bottom = -(M1 z_j);
+* the non-zero entries of the weighted task Jacobian go to a per-thread strip of shared memory (slot k of thread t
+  at sJ[k * BLOCK + t]: conflict-free), the Gram matrix is accumulated from them into REGISTERS (packed lower
+  triangle, fully unrolled), factorised there (LDL^T) and the step dq = -J^T y re-reads the strip once.
+
+The emitted struct is consumed by dls_spec.cuh (thread-per-problem persistent kernel with lane refill) and -- being
+__host__ __device__ -- by the CPU unit-test harness.  Supported: free-flyer or fixed base; RX/RY/RZ/unaligned
+revolute and prismatic joints; FrameTask (Position / Orientation / Full) with the `universe` reference frame.
+Anything else runs on the generic kernel.
+"""
+import json
+import sys
+
+J_UNIVERSE, J_FF, J_RX, J_RY, J_RZ, J_RU, J_PX, J_PY, J_PZ, J_PU = range(10)
+POSITION, ORIENTATION, FULL = 0, 1, 2
+
+
+# ------------------------------------------------------------------------------------------------------------
+# tiny symbolic layer: a value is a python float (compile-time constant) or a str (name of a `const T` variable)
+# ------------------------------------------------------------------------------------------------------------
+class Emitter:
+    def __init__(self):
+        self.lines = []
+        self.n = 0
+        self.indent = "        "
+
+    def comment(self, text):
+        self.lines.append("%s// %s" % (self.indent, text))
+
+    def raw(self, text):
+        self.lines.append(self.indent + text)
+
+    def var(self, expr, hint="t"):
+        """Materialise an expression string as a named const variable."""
+        name = "%s_%d" % (hint, self.n)
+        self.n += 1
+        self.lines.append("%sconst T %s = %s;" % (self.indent, name, expr))
+        return name
+
+
+def is_const(x):
+    return isinstance(x, (int, float))
+
+
+def lit(x):
+    if is_const(x):
+        return "T(%r)" % float(x)
+    return x
+
+
+def neg(E, a, hint="n"):
+    if is_const(a):
+        return -a
+    return E.var("-%s" % a, hint)
+
+
+def sop(E, terms, hint="t", add=None):
+    """Signed sum of products: terms are (a, b) or (a, b, sign) with sign = +1/-1; result = sum sign*a*b (+ add).
+    Constant-folds, drops zero terms, strips unit factors; returns a float or the name of a (new) variable."""
+    const_part = 0.0
+    parts = []  # (sign, coeff or None, var expression)
+    if add is not None:
+        if is_const(add):
+            const_part += add
+        else:
+            parts.append((1, None, add))
+    for term in terms:
+        a, b = term[0], term[1]
+        sign = term[2] if len(term) > 2 else 1
+        if is_const(a) and is_const(b):
+            const_part += sign * a * b
+            continue
+        if is_const(b):
+            a, b = b, a
+        if is_const(a):
+            if a == 0:
+                continue
+            if a < 0:
+                a, sign = -a, -sign
+            parts.append((sign, None if a == 1.0 else a, b))
+        else:
+            parts.append((sign, None, "%s * %s" % (a, b)))
+    if not parts:
+        return const_part
+    if len(parts) == 1 and parts[0][0] == 1 and parts[0][1] is None and " " not in parts[0][2] and const_part == 0:
+        return parts[0][2]  # plain alias, no new variable
+    expr = ""
+    for k, (sign, coeff, body) in enumerate(parts):
+        body = body if coeff is None else "%s * %s" % (lit(coeff), body)
+        if k == 0:
+            expr = body if sign > 0 else "-" + (body if " " not in body else "(%s)" % body)
+        else:
+            expr += " %s %s" % ("+" if sign > 0 else "-", body)
+    if const_part != 0:
+        expr += (" + %s" % lit(const_part)) if const_part > 0 else (" - %s" % lit(-const_part))
+    return E.var(expr, hint)
+
+
+def matmul(E, A, B, hint="m"):
+    return [sop(E, [(A[3 * i + k], B[3 * k + j]) for k in range(3)], hint) for i in range(3) for j in range(3)]
+
+
+def matvec(E, R, v, hint="v", add=None):
+    return [sop(E, [(R[3 * i + k], v[k]) for k in range(3)], hint, None if add is None else add[i]) for i in range(3)]
+
+
+def _cross_comp(E, a, b, i, hint):
+    """component i of a x b"""
+    j, k = (i + 1) % 3, (i + 2) % 3
+    return sop(E, [(a[j], b[k]), (a[k], b[j], -1)], hint)
+
+
+def sub3(E, a, b, hint="d"):
+    out = []
+    for x, y in zip(a, b):
+        if is_const(x) and is_const(y):
+            out.append(x - y)
+        elif is_const(y) and y == 0:
+            out.append(x)
+        else:
+            out.append(E.var("%s - %s" % (lit(x), lit(y)), hint))
+    return out
+
+
+def arr(E, name, vals):
+    E.raw("const T %s[%d] = {%s};" % (name, len(vals), ", ".join(lit(v) for v in vals)))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# generator
+# ------------------------------------------------------------------------------------------------------------
+class Generator:
+    def __init__(self, model, spec):
+        self.m = model
+        self.spec = spec
+        self.joints = model["joints"]
+        self.frames = {f["name"]: f for f in model["frames"]}
+        self.nq, self.nv = model["nq"], model["nv"]
+        self.tasks = []
+        row = 0
+        toff = 0
+        for t in spec["tasks"]:
+            f = self.frames[t["frame"]]
+            ktype = {"position": POSITION, "orientation": ORIENTATION, "full": FULL}[t["type"]]
+            dim = 6 if ktype == FULL else 3
+            chain = []
+            j = f["parent"]
+            while j > 0:
+                chain.append(j)
+                j = self.joints[j]["parent"]
+            chain.reverse()
+            self.tasks.append(dict(frame=f, ktype=ktype, dim=dim, row=row, toff=toff, chain=chain, name=t["frame"]))
+            row += dim
+            toff += 12
+        self.rows = row
+        self.tsz = toff
+        self.slots = {}  # (row, col) -> slot index
+
+    def slot(self, row, col):
+        key = (row, col)
+        if key not in self.slots:
+            self.slots[key] = len(self.slots)
+        return self.slots[key]
+
+    # ---- FK of one joint (memoised) ----
+    def fk_joint(self, E, j, world):
+        """Emit the world placement of joint j; returns dict(R=[9], p=[3], z=[3] axis in world)."""
+        if j in world:
+            return world[j]
+        jt = self.joints[j]
+        par = jt["parent"]
+        P = jt["placement"]
+        PR, Pp = P[:9], P[9:]
+        if par > 0:
+            pw = self.fk_joint(E, par, world)
+            parR, parp = pw["R"], pw["p"]
+        else:
+            parR, parp = [1.0, 0, 0, 0, 1.0, 0, 0, 0, 1.0], [0.0, 0.0, 0.0]
+        E.comment("joint %d %s (type %d, parent %d)" % (j, jt["name"], jt["type"], par))
+        t = jt["type"]
+        iq = jt["idx_q"]
+        A = matmul(E, parR, PR, "A%d" % j)
+        p = matvec(E, parR, Pp, "p%d" % j, add=parp)
+        if t == J_FF:
+            E.raw("T Rq%d[9];" % j)
+            E.raw("quat_to_rot(q[%d], q[%d], q[%d], q[%d], Rq%d);" % (iq + 3, iq + 4, iq + 5, iq + 6, j))
+            Rq = ["Rq%d[%d]" % (j, k) for k in range(9)]
+            R = matmul(E, A, Rq, "R%d" % j)
+            p = matvec(E, A, ["q[%d]" % (iq + k) for k in range(3)], "p%d" % j, add=p)
+            w = dict(R=R, p=p, z=None, type=t)
+        elif t in (J_RX, J_RY, J_RZ, J_RU):
+            E.raw("T s%d, c%d;" % (j, j))
+            E.raw("sincos_(q[%d], &s%d, &c%d);" % (iq, j, j))
+            s, c = "s%d" % j, "c%d" % j
+            if t == J_RU:
+                a = jt["axis"]
+                v = E.var("T(1) - %s" % c, "v%d" % j)
+                Rj = [sop(E, [(a[0] * a[0], v)], "r", c), sop(E, [(a[0] * a[1], v), (-a[2], s)], "r"),
+                      sop(E, [(a[0] * a[2], v), (a[1], s)], "r"),
+                      sop(E, [(a[0] * a[1], v), (a[2], s)], "r"), sop(E, [(a[1] * a[1], v)], "r", c),
+                      sop(E, [(a[1] * a[2], v), (-a[0], s)], "r"),
+                      sop(E, [(a[0] * a[2], v), (-a[1], s)], "r"), sop(E, [(a[1] * a[2], v), (a[0], s)], "r"),
+                      sop(E, [(a[2] * a[2], v)], "r", c)]
+                R = matmul(E, A, Rj, "R%d" % j)
+                z = matvec(E, A, a, "z%d" % j)
+            else:
+                # A * Rot(axis, q): the axis column is unchanged, the other two mix with (c, s)
+                k = {J_RX: 0, J_RY: 1, J_RZ: 2}[t]
+                u, v2 = (k + 1) % 3, (k + 2) % 3  # Rot maps e_u -> c e_u + s e_v, e_v -> -s e_u + c e_v
+                R = [None] * 9
+                for i in range(3):
+                    R[3 * i + k] = A[3 * i + k]
+                    R[3 * i + u] = sop(E, [(A[3 * i + u], c), (A[3 * i + v2], s)], "R%d" % j)
+                    R[3 * i + v2] = sop(E, [(A[3 * i + v2], c), (A[3 * i + u], s, -1)], "R%d" % j)
+                z = [A[k], A[3 + k], A[6 + k]]
+            w = dict(R=R, p=p, z=z, type=t)
+        elif t in (J_PX, J_PY, J_PZ, J_PU):
+            a = jt["axis"] if t == J_PU else [1.0 if i == t - J_PX else 0.0 for i in range(3)]
+            z = matvec(E, A, a, "z%d" % j)
+            p = [sop(E, [(z[i], "q[%d]" % iq)], "p%d" % j, p[i]) for i in range(3)]
+            w = dict(R=A, p=p, z=z, type=t)
+        else:
+            raise ValueError("unsupported joint type %d" % t)
+        world[j] = w
+        return w
+
+    def gen_evaluate(self):
+        """evaluate(): e[], res and the J strip."""
+        E = Emitter()
+        world = {}
+        for ti, task in enumerate(self.tasks):
+            f = task["frame"]
+            E.comment("==== task %d: frame %s, %s ====" % (ti, task["name"], ["Position", "Orientation", "Full"][task["ktype"]]))
+            jf = f["parent"]
+            if jf > 0:
+                w = self.fk_joint(E, jf, world)
+                # make sure every joint of the chain is emitted (memoised)
+                jR, jp = w["R"], w["p"]
+            else:
+                jR, jp = [1.0, 0, 0, 0, 1.0, 0, 0, 0, 1.0], [0.0, 0.0, 0.0]
+            FP = f["placement"]
+            ident = FP == [1.0, 0, 0, 0, 1.0, 0, 0, 0, 1.0, 0, 0, 0]
+            Rf = matmul(E, jR, FP[:9], "Rf")
+            pf = matvec(E, jR, FP[9:], "pf", add=jp)
+            n = ti
+            toff = task["toff"]
+            E.raw("T Rt%d[9], pt%d[3];" % (n, n))
+            E.raw("for (int k = 0; k < 9; ++k) Rt%d[k] = tg[%d + k];" % (n, toff))
+            E.raw("for (int k = 0; k < 3; ++k) pt%d[k] = tg[%d + k];" % (n, toff + 9))
+            arr(E, "Rf%d" % n, Rf)
+            arr(E, "pf%d" % n, pf)
+            # fMt = oMf^-1 * oMt  (frame.hpp:48-50, universe reference => oMt = target)
+            E.raw("T Re%d[9], d%d[3], pe%d[3], w%d[3], th%d, lin%d[3];" % (n, n, n, n, n, n))
+            E.raw("mat3T_mul(Rf%d, Rt%d, Re%d);" % (n, n, n))
+            E.raw("for (int k = 0; k < 3; ++k) d%d[k] = pt%d[k] - pf%d[k];" % (n, n, n))
+            E.raw("rotT_vec(Rf%d, d%d, pe%d);" % (n, n, n))
+            E.raw("log3(Re%d, w%d, th%d);" % (n, n, n))
+            E.raw("const LogCoeffs<T> lc%d = log_coeffs(th%d);" % (n, n))
+            E.raw("log6_from(w%d, lc%d, pe%d, lin%d);" % (n, n, n, n))
+            # tMf = fMt^-1: rotation Re^T (log3 = -w, same angle), translation Rt^T (pf - pt)
+            E.raw("T nw%d[3] = {-w%d[0], -w%d[1], -w%d[2]}, nd%d[3] = {-d%d[0], -d%d[1], -d%d[2]}, p2%d[3], A%dm[9], B%dm[9];"
+                  % (n, n, n, n, n, n, n, n, n, n, n))
+            E.raw("rotT_vec(Rt%d, nd%d, p2%d);" % (n, n, n))
+            E.raw("jlog6_blocks(nw%d, th%d, lc%d, p2%d, A%dm, B%dm);" % (n, n, n, n, n, n))
+            kt, row = task["ktype"], task["row"]
+            # error rows, weighted (data.cpp:49)
+            src = {POSITION: ["lin%d[%d]" % (n, i) for i in range(3)], ORIENTATION: ["w%d[%d]" % (n, i) for i in range(3)],
+                   FULL: ["lin%d[%d]" % (n, i) for i in range(3)] + ["w%d[%d]" % (n, i) for i in range(3)]}[kt]
+            for i, s in enumerate(src):
+                E.raw("e[%d] = c.weight[%d] * %s;" % (row + i, row + i, s))
+            top = kt in (POSITION, FULL)
+            bot = kt in (ORIENTATION, FULL)
+            brow = row + (3 if kt == FULL else 0)
+            A = ["A%dm[%d]" % (n, k) for k in range(9)]
+            Bm = ["B%dm[%d]" % (n, k) for k in range(9)]
+
+            def store(r, col, val):
+                k = self.slot(r, col)
+                E.raw("sJ.set(%d, c.weight[%d] * %s);  // J[%d][%d]" % (k, r, lit(val), r, col))
+
+            chain = task["chain"]
+            ff_self = ident and len(chain) == 1 and self.joints[chain[0]]["type"] == J_FF
+            if ff_self:
+                # frame == the free-flyer joint frame: Jf_LOCAL = I6, J = -Jlog6 = -[[A, B], [0, A]]
+                iv = self.joints[chain[0]]["idx_v"]
+                for i in range(3):
+                    for k in range(3):
+                        if top:
+                            store(row + i, iv + k, E.var("-%s" % A[3 * i + k], "j"))
+                            store(row + i, iv + 3 + k, E.var("-%s" % Bm[3 * i + k], "j"))
+                        if bot:
+                            store(brow + i, iv + 3 + k, E.var("-%s" % A[3 * i + k], "j"))
+                continue
+            # M1 = A Rf^T, M2 = B Rf^T
+            RfT = [Rf[3 * j_ + i] for i in range(3) for j_ in range(3)]
+            M1 = matmul(E, A, RfT, "M1_")
+            M2 = matmul(E, Bm, RfT, "M2_") if top else None
+            for j in chain:
+                w = world[j] if j in world else self.fk_joint(E, j, world)
+                jt = self.joints[j]
+                iv = jt["idx_v"]
+                if jt["type"] == J_FF:
+                    dpf = sub3(E, w["p"], pf, "dp")
+                    for k in range(3):
+                        rk = [w["R"][k], w["R"][3 + k], w["R"][6 + k]]
+                        m1r = matvec(E, M1, rk, "m1r")
+                        if top:
+                            for i in range(3):
+                                store(row + i, iv + k, neg(E, m1r[i]))
+                            cx = [_cross_comp(E, dpf, rk, i, "cx") for i in range(3)]
+                            m1c = matvec(E, M1, cx, "m1c")
+                            m2r = matvec(E, M2, rk, "m2r")
+                            for i in range(3):
+                                store(row + i, iv + 3 + k, E.var("-(%s + %s)" % (lit(m1c[i]), lit(m2r[i])), "j"))
+                        if bot:
+                            for i in range(3):
+                                store(brow + i, iv + 3 + k, neg(E, m1r[i]))
+                elif jt["type"] in (J_RX, J_RY, J_RZ, J_RU):
+                    z = w["z"]
+                    m1z = matvec(E, M1, z, "m1z")
+                    if top:
+                        dpf = sub3(E, w["p"], pf, "dp")
+                        cx = [_cross_comp(E, dpf, z, i, "cx") for i in range(3)]
+                        m1c = matvec(E, M1, cx, "m1c")
+                        m2z = matvec(E, M2, z, "m2z")
+                        for i in range(3):
+                            store(row + i, iv, E.var("-(%s + %s)" % (lit(m1c[i]), lit(m2z[i])), "j"))
+                    if bot:
+                        for i in range(3):
+                            store(brow + i, iv, neg(E, m1z[i]))
+                else:  # prismatic: world column [z; 0]
+                    if top:
+                        m1z = matvec(E, M1, w["z"], "m1z")
+                        for i in range(3):
+                            store(row + i, iv, neg(E, m1z[i]))
+        self.R0 = None
+        for j, w in world.items():
+            if self.joints[j]["type"] == J_FF:
+                self.ff_joint = j
+        return E.lines
+
+    def gen_gram(self):
+        """Gram matrix from the strip -> packed lower triangle in registers, + damping."""
+        L = []
+        ind = "        "
+        rows = self.rows
+        L.append(ind + "TG G[%d];" % (rows * (rows + 1) // 2))
+        L.append(ind + "#pragma unroll")
+        L.append(ind + "for (int k = 0; k < %d; ++k) G[k] = TG(0);" % (rows * (rows + 1) // 2))
+        L.append(ind + "#pragma unroll")
+        L.append(ind + "for (int i = 0; i < %d; ++i) G[i * (i + 1) / 2 + i] = damping2;" % rows)
+        cols = sorted(set(c for (_, c) in self.slots))
+        nfma = 0
+        for c in cols:
+            rs = sorted(r for (r, cc) in self.slots if cc == c)
+            L.append(ind + "{  // column %d: rows %s" % (c, rs))
+            for r in rs:
+                L.append(ind + "    const TG a%d = TG(sJ.get(%d));" % (r, self.slots[(r, c)]))
+            for i in rs:
+                for j in rs:
+                    if j <= i:
+                        L.append(ind + "    G[%d] += a%d * a%d;" % (i * (i + 1) // 2 + j, i, j))
+                        nfma += 1
+            L.append(ind + "}")
+        self.gram_fma = nfma
+        return L
+
+    def gen_dq(self):
+        L = []
+        ind = "        "
+        for c in range(self.nv):
+            rs = sorted(r for (r, cc) in self.slots if cc == c)
+            if not rs:
+                L.append(ind + "dq[%d] = T(0);" % c)
+                continue
+            expr = " + ".join("sJ.get(%d) * y[%d]" % (self.slots[(r, c)], r) for r in rs)
+            L.append(ind + "dq[%d] = -(%s);" % (c, expr))
+        return L
+
+    def gen_integrate(self):
+        """pinocchio::integrate (dls.cpp:67-68) + clamp (common.hpp:53-56), joint by joint."""
+        L = []
+        ind = "        "
+        for j, jt in enumerate(self.joints):
+            if jt["type"] == J_UNIVERSE:
+                continue
+            iq, iv = jt["idx_q"], jt["idx_v"]
+            if jt["type"] == J_FF:
+                L.append(ind + "{")
+                L.append(ind + "    T v6[6], R0[9];")
+                L.append(ind + "    for (int k = 0; k < 6; ++k) v6[k] = step * dq[%d + k];" % iv)
+                L.append(ind + "    quat_to_rot(q[%d], q[%d], q[%d], q[%d], R0);" % (iq + 3, iq + 4, iq + 5, iq + 6))
+                L.append(ind + "    integrate_freeflyer(R0, &q[%d], &q[%d], v6);" % (iq, iq + 3))
+                L.append(ind + "}")
+            else:
+                L.append(ind + "q[%d] += step * dq[%d];" % (iq, iv))
+        L.append(ind + "#pragma unroll")
+        L.append(ind + "for (int k = 0; k < %d; ++k) q[k] = min_(c.upper[k], max_(q[k], c.lower[k]));" % self.nq)
+        return L
+
+    def signature(self):
+        """C++ initialisers used by matches(): the specialisation is only valid for exactly this tree / task list."""
+        used = sorted(set(j for t in self.tasks for j in t["chain"]))
+        return used
+
+    def emit(self, struct_name, display_name):
+        ev = self.gen_evaluate()
+        gram = self.gen_gram()
+        dq = self.gen_dq()
+        integ = self.gen_integrate()
+        rows, nslot = self.rows, len(self.slots)
+        used = self.signature()
+        out = []
+        out.append("// GENERATED by tools/gen_kernel.py -- do not edit.  Specialisation: %s" % display_name)
+        out.append("// rows=%d nv=%d nq=%d non-zero Jacobian entries=%d Gram FMAs=%d" % (rows, self.nv, self.nq, nslot, self.gram_fma))
+        out.append("#pragma once")
+        out.append('#include "../../ik_b200/csrc/se3_math.cuh"')
+        out.append('#include "../../ik_b200/csrc/dls_spec.cuh"')
+        out.append("namespace ikb {")
+        out.append("struct %s {" % struct_name)
+        out.append("    static constexpr int NQ = %d, NV = %d, M = %d, M0 = %d, TSZ = %d, NSLOT = %d;" %
+                   (self.nq, self.nv, rows, rows, self.tsz, nslot))
+        out.append('    static const char *name() { return "%s"; }' % display_name)
+        out.append("    // FK + task errors + weighted task Jacobian (non-zero entries -> strip sJ)")
+        out.append("    template <typename T, typename JS, typename TGT>")
+        out.append("    static IKB_HD void evaluate(const T (&q)[NQ], const TGT &tg, const SpecConsts<T, NQ, M> &c, JS &sJ, T (&e)[M]) {")
+        out.extend(ev)
+        out.append("    }")
+        out.append("    // Gram matrix (registers, packed lower triangle) from the strip, with damping on the diagonal")
+        out.append("    template <typename TG, typename JS>")
+        out.append("    static IKB_HD void gram(const JS &sJ, TG damping2, TG (&Gout)[M * (M + 1) / 2]) {")
+        out.extend(gram)
+        out.append("#pragma unroll")
+        out.append("        for (int k = 0; k < M * (M + 1) / 2; ++k) Gout[k] = G[k];")
+        out.append("    }")
+        out.append("    // dq = -J^T y from the strip (dls.cpp:52)")
+        out.append("    template <typename T, typename JS>")
+        out.append("    static IKB_HD void step_direction(const JS &sJ, const T (&y)[M], T (&dq)[NV]) {")
+        out.extend(dq)
+        out.append("    }")
+        out.append("    // q <- clamp(integrate(q, step*dq))")
+        out.append("    template <typename T>")
+        out.append("    static IKB_HD void integrate(T (&q)[NQ], const T (&dq)[NV], T step, const SpecConsts<T, NQ, M> &c) {")
+        out.extend(integ)
+        out.append("    }")
+        # signature data for matches()
+        out.append("    // ---- signature (host): the tree and task list this code was generated for ----")
+        out.append("    static constexpr int NJOINTS = %d, NTASKS = %d;" % (len(self.joints), len(self.tasks)))
+        out.append("    static const int *sig_parent() { static const int v[] = {%s}; return v; }" %
+                   ", ".join(str(j["parent"]) for j in self.joints))
+        out.append("    static const int *sig_type() { static const int v[] = {%s}; return v; }" %
+                   ", ".join(str(j["type"]) for j in self.joints))
+        out.append("    static const int *sig_used() { static const int v[] = {%s, -1}; return v; }" % ", ".join(map(str, used)))
+        pl = []
+        for j in self.joints:
+            pl.extend(j["placement"])
+            pl.extend(j["axis"])
+        out.append("    static const double *sig_placement() { static const double v[] = {%s}; return v; }" %
+                   ", ".join(repr(float(x)) for x in pl))
+        out.append("    static const int *sig_task_type() { static const int v[] = {%s}; return v; }" %
+                   ", ".join(str(t["ktype"]) for t in self.tasks))
+        out.append("    static const int *sig_task_joint() { static const int v[] = {%s}; return v; }" %
+                   ", ".join(str(t["frame"]["parent"]) for t in self.tasks))
+        fpl = []
+        for t in self.tasks:
+            fpl.extend(t["frame"]["placement"])
+        out.append("    static const double *sig_task_placement() { static const double v[] = {%s}; return v; }" %
+                   ", ".join(repr(float(x)) for x in fpl))
+        out.append("};")
+        out.append("}  // namespace ikb")
+        return "\n".join(out) + "\n"
+
+
+def main():
+    model = json.load(open(sys.argv[1]))
+    spec = json.load(open(sys.argv[2]))
+    g = Generator(model, spec)
+    text = g.emit(spec["struct"], spec["name"])
+    with open(sys.argv[3], "w") as f:
+        f.write(text)
+    print("gen_kernel: %s -> %s (%d rows, %d Jacobian slots, %d lines)" % (spec["name"], sys.argv[3], g.rows, len(g.slots),
+                                                                           text.count("\n")))
+
+
+if __name__ == "__main__":
+    main()
