@@ -80,6 +80,7 @@ SIGNATURES = {
     "ikb_problem_task_target_offset": (C.c_int, [_vp, C.c_int]),
     "ikb_problem_finalize": (C.c_int, [_vp, C.c_int]),
     "ikb_problem_kernel_name": (C.c_char_p, [_vp, C.c_int]),
+    "ikb_problem_specialisation": (C.c_char_p, [_vp]),
     "ikb_dls_solve_batch": (C.c_int, [_vp, C.c_int, C.POINTER(DlsParams), C.c_int64, C.POINTER(BatchIO), _vp]),
     "ikb_dls_solve_batch_host": (C.c_int, [_vp, C.c_int, C.POINTER(DlsParams), C.c_int64, C.POINTER(BatchIO)]),
     "ikb_dls_solve": (C.c_int, [_vp, C.POINTER(DlsParams), _dp, _dp, _dp, C.POINTER(C.c_int), C.POINTER(C.c_int), _dp]),

@@ -261,10 +261,8 @@ class InverseKinematicsProblem:  # problem.hpp:9-206
         parts = [_as_f64(t.target).reshape(-1) for _, t, _ in self._tasks]
         return np.concatenate(parts) if parts else np.zeros(0)
 
-    # ---- device side ----
-    def finalize(self, device=0):
-        if self._h is not None:
-            return self
+    def _build_handle(self, device):
+        """Create the C-ABI problem handle; device=None stops before ikb_problem_finalize (host-only handle)."""
         lib = capi.lib
         h = C.c_void_p()
         capi.check(lib.ikb_problem_create(self._model._h, self._max_priority_level, C.byref(h)), "ikb_problem_create")
@@ -286,11 +284,27 @@ class InverseKinematicsProblem:  # problem.hpp:9-206
                 else:
                     capi.check_index(lib.ikb_problem_add_align_axis_task(h, f, int(t.axis), r, prio, _dptr(w)),
                                      "ikb_problem_add_align_axis_task")
-            capi.check(lib.ikb_problem_finalize(h, device), "ikb_problem_finalize")
+            if device is not None:
+                capi.check(lib.ikb_problem_finalize(h, device), "ikb_problem_finalize")
         except Exception:
             lib.ikb_problem_free(h)
             raise
-        self._h = h
+        return h
+
+    def specialisation(self):
+        """Name of the compiled topology-specialised kernel matching this problem, or None (host-only query)."""
+        h = self._build_handle(None)
+        try:
+            n = capi.lib.ikb_problem_specialisation(h)
+            return n.decode() if n else None
+        finally:
+            capi.lib.ikb_problem_free(h)
+
+    # ---- device side ----
+    def finalize(self, device=0):
+        if self._h is not None:
+            return self
+        self._h = self._build_handle(device)
         self._device = device
         return self
 

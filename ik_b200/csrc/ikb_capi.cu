@@ -50,6 +50,7 @@ struct ikb_problem {
     unsigned long long *d_tickets = nullptr;
     std::atomic<unsigned> ticket_next{0};
     const SpecializedKernel *spec = nullptr;
+    std::vector<double> weight_stacked;  // Task::weighting() rows in stacked order (constants of the specialised kernels)
     std::string kernel_name[2];
     // host-path staging (ikb_dls_solve_batch_host)
     cudaStream_t stream = nullptr;
@@ -160,6 +161,16 @@ template <typename T> struct KernelTable {
     }
 };
 
+// max_iterations <= 0: the reference returns q0 untouched, success = false, nothing evaluated
+template <typename T> __global__ void passthrough_kernel(SolveArgs<T> a, int nq) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    for (int k = 0; k < nq; ++k) a.q[k * a.q_es + b * a.q_bs] = a.q0[k * a.q0_es + b * a.q0_bs];
+    if (a.success) a.success[b] = 0;
+    if (a.iters) a.iters[b] = 0;
+    if (a.resid) a.resid[b] = T(0);
+}
+
 template <typename T> DevProblem<T> *dev_blob(const ikb_problem *p);
 template <> DevProblem<double> *dev_blob<double>(const ikb_problem *p) { return p->d64; }
 template <> DevProblem<float> *dev_blob<float>(const ikb_problem *p) { return p->d32; }
@@ -182,8 +193,17 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
     a.ticket = p->d_tickets + slot * 16;  // 128 B apart
     IKB_CUDA(cudaMemsetAsync(a.ticket, 0, sizeof(unsigned long long), s));
 
+    if (prm->max_iterations <= 0) {
+        // dls.cpp:14 never enters the loop: q0 is returned with success = false (dls.cpp:76-77)
+        const int threads = 128;
+        passthrough_kernel<T><<<(unsigned)((B + threads - 1) / threads), threads, 0, s>>>(a, p->hp.model.nq);
+        IKB_CUDA(cudaGetLastError());
+        g_launches.fetch_add(1);
+        return IKB_OK;
+    }
     if (p->spec) {
-        int rc = launch_specialized<T>(*p->spec, dev_blob<T>(p), a, p->sm_count, s);
+        const SpecHostConsts hc{p->hp.model.lower.data(), p->hp.model.upper.data(), p->weight_stacked.data()};
+        int rc = launch_specialized<T>(*p->spec, hc, a, p->sm_count, s);
         if (rc != IKB_OK) return cuda_fail(cudaGetLastError(), "specialised kernel launch");
         g_launches.fetch_add(1);
         return IKB_OK;
@@ -306,6 +326,14 @@ int launch_fk(const ikb_problem *p, int64_t B, const void *q, int64_t es, int64_
     IKB_CUDA(cudaGetLastError());
     g_launches.fetch_add(1);
     return IKB_OK;
+}
+
+// The specialised bodies lay targets out in stacked order, the ABI in insertion order: only problems whose tasks
+// were added in non-decreasing priority (stacked order == insertion order) can take the fast path.
+const SpecializedKernel *select_specialized(const HostProblem &hp) {
+    for (size_t i = 1; i < hp.tasks.size(); ++i)
+        if (hp.tasks[i].priority < hp.tasks[i - 1].priority) return nullptr;
+    return find_specialized(hp);
 }
 
 int check_weights(const double *w, int dim, std::vector<double> &out) {
@@ -634,13 +662,22 @@ int ikb_problem_finalize(ikb_problem *p, int device) {
 
     p->size_class = cls;
     p->device = device;
-    p->spec = find_specialized(hp);
+    p->weight_stacked.clear();
+    for (int t : order)
+        for (double w : hp.tasks[t].weight) p->weight_stacked.push_back(w);
+    p->spec = select_specialized(hp);
     char buf[96];
     std::snprintf(buf, sizeof buf, "generic<NJ=%d,NV=%d,M=%d>", kClasses[cls].nj, kClasses[cls].nv, kClasses[cls].m);
     p->kernel_name[0] = p->spec ? p->spec->name : buf;
     p->kernel_name[1] = p->kernel_name[0];
     p->finalized = true;
     return IKB_OK;
+}
+
+const char *ikb_problem_specialisation(const ikb_problem *p) {
+    if (!p || p->hp.tasks.empty()) return nullptr;
+    const SpecializedKernel *k = select_specialized(p->hp);
+    return k ? k->name : nullptr;
 }
 
 const char *ikb_problem_kernel_name(const ikb_problem *p, int dtype) {

@@ -1,20 +1,27 @@
-// Registry of specialised kernels (see specialized.hpp).
+// Registry of specialised kernels (see specialized.hpp).  Each specialisation is one generated header
+// (ik_b200/csrc/gen/<name>.cuh, emitted at build time by tools/gen_kernel.py from ik_b200/specs/<name>.json and the
+// product's own URDF flattener) compiled in its own translation unit (spec_<name>.cu) so they build in parallel.
 #include "specialized.hpp"
 
 #include <cstdlib>
 
 namespace ikb {
 
+extern const SpecializedKernel kSpecCassieFeetPelvis;
+extern const SpecializedKernel kSpecManipulatorTool;
+
 namespace {
-const SpecializedKernel *const kRegistry[] = {nullptr};
+const SpecializedKernel *const kRegistry[] = {&kSpecCassieFeetPelvis, &kSpecManipulatorTool, nullptr};
 }
+
+const SpecializedKernel *const *specialized_registry() { return kRegistry; }
 
 const SpecializedKernel *find_specialized(const HostProblem &hp) {
     // IKB_FORCE_GENERIC=1 pins the table-driven kernel (used by the parity tests to cover both paths)
     const char *force = std::getenv("IKB_FORCE_GENERIC");
     if (force && force[0] == '1') return nullptr;
-    for (const SpecializedKernel *k : kRegistry)
-        if (k && k->matches(hp)) return k;
+    for (const SpecializedKernel *const *k = kRegistry; *k; ++k)
+        if ((*k)->matches(hp)) return *k;
     return nullptr;
 }
 

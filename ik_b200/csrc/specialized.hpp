@@ -9,27 +9,35 @@
 
 namespace ikb {
 
+// Host copies of the run-time constants a specialised kernel takes as a by-value parameter (spec_common.hpp).
+struct SpecHostConsts {
+    const double *lower, *upper;  // [nq]
+    const double *weight;         // [rows], stacked order
+};
+
 struct SpecializedKernel {
     const char *name;
     bool (*matches)(const HostProblem &hp);
-    int (*launch64)(const DevProblem<double> *P, const SolveArgs<double> &a, int sm_count, cudaStream_t s);
-    int (*launch32)(const DevProblem<float> *P, const SolveArgs<float> &a, int sm_count, cudaStream_t s);
+    int (*launch64)(const SpecHostConsts &hc, const SolveArgs<double> &a, int sm_count, cudaStream_t s);
+    int (*launch32)(const SpecHostConsts &hc, const SolveArgs<float> &a, int sm_count, cudaStream_t s);
 };
 
 const SpecializedKernel *find_specialized(const HostProblem &hp);
+// all compiled specialisations (NULL-terminated), for introspection / tests
+const SpecializedKernel *const *specialized_registry();
 
 template <typename T>
-inline int launch_specialized(const SpecializedKernel &k, const DevProblem<T> *P, const SolveArgs<T> &a, int sm_count,
+inline int launch_specialized(const SpecializedKernel &k, const SpecHostConsts &hc, const SolveArgs<T> &a, int sm_count,
                               cudaStream_t s);
 template <>
-inline int launch_specialized<double>(const SpecializedKernel &k, const DevProblem<double> *P, const SolveArgs<double> &a,
+inline int launch_specialized<double>(const SpecializedKernel &k, const SpecHostConsts &hc, const SolveArgs<double> &a,
                                       int sm_count, cudaStream_t s) {
-    return k.launch64(P, a, sm_count, s);
+    return k.launch64(hc, a, sm_count, s);
 }
 template <>
-inline int launch_specialized<float>(const SpecializedKernel &k, const DevProblem<float> *P, const SolveArgs<float> &a,
+inline int launch_specialized<float>(const SpecializedKernel &k, const SpecHostConsts &hc, const SolveArgs<float> &a,
                                      int sm_count, cudaStream_t s) {
-    return k.launch32(P, a, sm_count, s);
+    return k.launch32(hc, a, sm_count, s);
 }
 
 }  // namespace ikb

@@ -69,6 +69,26 @@ def standing_configuration(model, standing=None):
     return q0
 
 
+def near_start(model, qstar, seed=12345, b0=0, radius=0.3):
+    """Warm-start initial guesses (the reference's only caller warm-starts every solve, ik_ros/src/cassie.cpp:112):
+    revolute joints = q* + U[-radius, radius] clipped to the limits, floating base at the identity.  Used for the
+    robots that have no SRDF standing pose; starting the serial arm at its singular zero configuration with full
+    undamped-ish steps gives chaotic trajectories on which no two floating-point implementations agree."""
+    B = qstar.shape[0]
+    b = np.arange(b0, b0 + B, dtype=np.uint64)
+    q0 = np.tile(model.neutral(), (B, 1))
+    lo, hi = model.lowerPositionLimit, model.upperPositionLimit
+    k = 1000
+    for j in range(1, model.njoints):
+        iq = int(model.idx_qs[j])
+        if model.jtypes[j] == J_FREEFLYER:
+            continue
+        d = -radius + 2 * radius * uniform01(seed, b, k)
+        k += 1
+        q0[:, iq] = np.minimum(hi[iq], np.maximum(lo[iq], qstar[:, iq] + d))
+    return q0
+
+
 def cassie_model():
     return Model.builtin("cassie", free_flyer=True)
 

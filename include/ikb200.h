@@ -130,6 +130,9 @@ int ikb_problem_target_size(const ikb_problem *p);                   /* scalars 
 int ikb_problem_task_target_offset(const ikb_problem *p, int task);  /* FRAME: 12 (SE3), ALIGN_AXIS: 3, POSTURE: nj */
 /* Upload the problem constants to CUDA device `device` and select the kernel.  After this the handle is immutable. */
 int ikb_problem_finalize(ikb_problem *p, int device);
+/* Host-only query (no device needed, before or after finalize): name of the compiled topology-specialised kernel
+ * that matches this problem's tree and task list exactly, or NULL when the generic table-driven kernel will run. */
+const char *ikb_problem_specialisation(const ikb_problem *p);
 /* Name of the kernel variant ikb_dls_solve_batch will launch for `dtype` ("generic<...>", "cassie_feet_pelvis", ...) */
 const char *ikb_problem_kernel_name(const ikb_problem *p, int dtype);
 

@@ -43,11 +43,15 @@ def oracle_frame_poses(omodel, qs, names):
     return out
 
 
-def make_workload(problem, omodel, B, seed=12345, standing=None, b0=0):
-    """q0 [B,nq], targets [B,tsz] (AoS, float64) with targets = oracle FK of seeded reachable configurations."""
+def make_workload(problem, omodel, B, seed=12345, standing=None, b0=0, start="standing"):
+    """q0 [B,nq], targets [B,tsz] (AoS, float64) with targets = oracle FK of seeded reachable configurations.
+    start="standing": q0 = standing / neutral pose for every problem; start="near": W.near_start (warm start)."""
     m = problem.model()
     qstar = W.sample_configurations(m, B, seed, b0)
     poses = oracle_frame_poses(omodel, qstar, W.task_frames(problem))
     targets = W.targets_from_frame_poses(problem, poses)
-    q0 = np.tile(W.standing_configuration(m, standing), (B, 1))
+    if start == "near":
+        q0 = W.near_start(m, qstar, seed, b0)
+    else:
+        q0 = np.tile(W.standing_configuration(m, standing), (B, 1))
     return q0, targets, qstar

@@ -1,0 +1,76 @@
+// TEST-ONLY: compiles the GENERATED solver bodies (ik_b200/csrc/gen/*.cuh -- the very source the CUDA kernel in
+// dls_spec.cuh instantiates) with g++ and drives them with the same loop as the kernel, so the generated arithmetic
+// can be checked against the oracle on the GPU-less build box.  Never linked into libikb200.so; the product has no
+// CPU path.
+#include <vector>
+
+#include "../../ik_b200/csrc/gen/cassie_feet_pelvis.cuh"
+#include "../../ik_b200/csrc/gen/manipulator_tool.cuh"
+
+using namespace ikb;
+
+template <class Spec, typename T>
+static int spec_solve(const double *lower, const double *upper, const double *weight, const double *q0, const double *targets,
+                      int max_it, double step, double damping, double tol, double *q_out, int *iters, double *resid,
+                      double *e_first) {
+    constexpr int NQ = Spec::NQ, NV = Spec::NV, M = Spec::M;
+    SpecConsts<T, NQ, M> c;
+    for (int k = 0; k < NQ; ++k) { c.lower[k] = (T)lower[k]; c.upper[k] = (T)upper[k]; }
+    for (int i = 0; i < M; ++i) c.weight[i] = (T)weight[i];
+    std::vector<T> bufJ(Spec::NSLOT), bufL(Spec::NFACT), bufT(Spec::TSZ);
+    for (int k = 0; k < Spec::TSZ; ++k) bufT[k] = (T)targets[k];
+    const Strip<T, 1> sJ{bufJ.data()}, sL{bufL.data()}, sT{bufT.data()};
+    T q[NQ];
+    for (int k = 0; k < NQ; ++k) q[k] = (T)q0[k];
+    int it = 0, success = 0;
+    T res = 0;
+    while (it < max_it) {
+        T e[M];
+        Spec::evaluate(q, sT, c, sJ, e);
+        if (it == 0 && e_first) for (int i = 0; i < M; ++i) e_first[i] = (double)e[i];
+        res = 0;
+        for (int i = 0; i < Spec::M0; ++i) res += e[i] * e[i];
+        if (res < (T)tol) { success = 1; break; }
+        T y[M], dq[NV];
+        Spec::solve(sJ, sL, (T)(damping * damping), e, y);
+        Spec::step_direction(sJ, y, dq);
+        Spec::integrate(q, dq, (T)step, c);
+        ++it;
+    }
+    for (int k = 0; k < NQ; ++k) q_out[k] = (double)q[k];
+    *iters = it;
+    *resid = (double)res;
+    return success;
+}
+
+// one evaluation: weighted error e[M] and the dense weighted task Jacobian J[M][NV] rebuilt from the strip
+template <class Spec>
+static void spec_eval(const double *weight, const double *q0, const double *targets, double *e_out, double *J_out) {
+    constexpr int NQ = Spec::NQ, NV = Spec::NV, M = Spec::M;
+    SpecConsts<double, NQ, M> c{};
+    for (int i = 0; i < M; ++i) c.weight[i] = weight[i];
+    std::vector<double> bufJ(Spec::NSLOT), bufT(targets, targets + Spec::TSZ);
+    const Strip<double, 1> sJ{bufJ.data()}, sT{bufT.data()};
+    double q[NQ], e[M];
+    for (int k = 0; k < NQ; ++k) q[k] = q0[k];
+    Spec::evaluate(q, sT, c, sJ, e);
+    for (int i = 0; i < M; ++i) e_out[i] = e[i];
+    for (int i = 0; i < M * NV; ++i) J_out[i] = 0;
+    for (int k = 0; k < Spec::NSLOT; ++k) J_out[Spec::slot_rc()[2 * k] * NV + Spec::slot_rc()[2 * k + 1]] = bufJ[k];
+}
+
+#define IKB_SPEC_EXPORT(fn, Spec)                                                                                        \
+    extern "C" int fn##_d(const double *lo, const double *hi, const double *w, const double *q0, const double *tg, int mi, \
+                          double st, double da, double tol, double *q, int *it, double *res, double *e0) {               \
+        return spec_solve<Spec, double>(lo, hi, w, q0, tg, mi, st, da, tol, q, it, res, e0);                             \
+    }                                                                                                                    \
+    extern "C" int fn##_f(const double *lo, const double *hi, const double *w, const double *q0, const double *tg, int mi, \
+                          double st, double da, double tol, double *q, int *it, double *res, double *e0) {               \
+        return spec_solve<Spec, float>(lo, hi, w, q0, tg, mi, st, da, tol, q, it, res, e0);                              \
+    }                                                                                                                    \
+    extern "C" void fn##_eval(const double *w, const double *q0, const double *tg, double *e, double *J) {               \
+        spec_eval<Spec>(w, q0, tg, e, J);                                                                                \
+    }
+
+IKB_SPEC_EXPORT(h_spec_cassie_feet_pelvis, SpecCassieFeetPelvis)
+IKB_SPEC_EXPORT(h_spec_manipulator_tool, SpecManipulatorTool)

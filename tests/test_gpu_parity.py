@@ -103,9 +103,24 @@ def test_start_converged_returns_q0():
     assert data.success and data.iterations == 0 and np.array_equal(q, q0)
 
 
+@pytest.fixture(params=["specialised", "generic"])
+def kernel_path(request, monkeypatch):
+    """Both solve kernels must meet the same bar: the generated topology-specialised one (the default for the
+    benchmark problems) and the table-driven generic one (IKB_FORCE_GENERIC=1 is read by ikb_problem_finalize)."""
+    monkeypatch.setenv("IKB_FORCE_GENERIC", "1" if request.param == "generic" else "0")
+    return request.param
+
+
+def _check_path(pb, kernel_path, spec_name):
+    pb.finalize(0)
+    name = pb.kernel_name()
+    assert (name == spec_name) if kernel_path == "specialised" else name.startswith("generic<"), name
+
+
 @pytest.mark.parametrize("B", [1, 33, 4096])
-def test_cassie_f64_defaults(B):
+def test_cassie_f64_defaults(B, kernel_path):
     pb = W.cassie_feet_pelvis_problem()
+    _check_path(pb, kernel_path, "cassie_feet_pelvis")
     om = oracle_model("cassie")
     opb = oracle_problem_like(pb, om)
     q0, tg, _ = make_workload(pb, om, B, standing=W.CASSIE_STANDING)
@@ -113,8 +128,9 @@ def test_cassie_f64_defaults(B):
     _compare("cassie f64 defaults B=%d" % B, _solve_gpu(pb, q0, tg), ref, 1e-6)
 
 
-def test_cassie_f64_demo_params():
+def test_cassie_f64_demo_params(kernel_path):
     pb = W.cassie_feet_pelvis_problem()
+    _check_path(pb, kernel_path, "cassie_feet_pelvis")
     om = oracle_model("cassie")
     opb = oracle_problem_like(pb, om)
     q0, tg, _ = make_workload(pb, om, 1024, seed=99, standing=W.CASSIE_STANDING)
@@ -158,21 +174,33 @@ def test_host_path_layouts_agree():
 
 
 def test_humanoid_f64():
+    """BASELINE config 4 (warm-started: W.near_start)."""
     pb = W.humanoid_problem()
     om = oracle_model("humanoid")
     opb = oracle_problem_like(pb, om)
-    q0, tg, _ = make_workload(pb, om, 512, seed=5)
+    q0, tg, _ = make_workload(pb, om, 512, seed=5, start="near")
     ref = O.dls_batch(opb, q0, tg, nthreads=NT)
     _compare("humanoid f64", _solve_gpu(pb, q0, tg), ref, 1e-6, min_same_frac=0.97)
 
 
-def test_manipulator_f64():
+def test_manipulator_f64(kernel_path):
+    """BASELINE config 5 (warm-started: W.near_start -- the zero configuration of a serial arm is singular)."""
     pb = W.manipulator_problem()
+    _check_path(pb, kernel_path, "manipulator_tool")
     om = oracle_model("manipulator", free_flyer=False)
     opb = oracle_problem_like(pb, om)
-    q0, tg, _ = make_workload(pb, om, 2048, seed=11)
+    q0, tg, _ = make_workload(pb, om, 2048, seed=11, start="near")
     ref = O.dls_batch(opb, q0, tg, nthreads=NT)
     _compare("manipulator f64", _solve_gpu(pb, q0, tg), ref, 1e-6, min_same_frac=0.97)
+
+
+def test_zero_iterations_returns_q0():
+    """max_iterations = 0: the loop of dls.cpp:14 never runs -- q0 comes back, success = false, 0 iterations."""
+    pb = W.cassie_feet_pelvis_problem()
+    om = oracle_model("cassie")
+    q0, tg, _ = make_workload(pb, om, 64, standing=W.CASSIE_STANDING)
+    q, ok, it, res = _solve_gpu(pb, q0, tg, ik.dls_parameters(max_iterations=0))
+    assert np.array_equal(q, q0) and not ok.any() and not it.any()
 
 
 def test_ur5_orientation_and_weights():

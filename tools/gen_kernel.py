@@ -16,6 +16,12 @@ data.cpp:25-58, frame.hpp:37-62,152-182) for a FIXED tree and FIXED frame-task l
   at sJ[k * BLOCK + t]: conflict-free), the Gram matrix is accumulated from them into REGISTERS (packed lower
   triangle, fully unrolled), factorised there (LDL^T) and the step dq = -J^T y re-reads the strip once.
 
+* the damped normal equations (dls.cpp:39-53) never materialise the Gram matrix either: it is accumulated block column
+  by block column (width W) into registers straight from the strip, each block column is updated left-looking from
+  the factor columns already stored, factorised in registers (LDL^T, no pivoting: G is SPD thanks to the damping) and
+  written to a second strip; the right-hand side rides along as an extra row, so the forward substitution and the
+  D^-1 scaling come for free and only the back substitution re-reads the factor.
+
 The emitted struct is consumed by dls_spec.cuh (thread-per-problem persistent kernel with lane refill) and -- being
 __host__ __device__ -- by the CPU unit-test harness.  Supported: free-flyer or fixed base; RX/RY/RZ/unaligned
 revolute and prismatic joints; FrameTask (Position / Orientation / Full) with the `universe` reference frame.
@@ -152,6 +158,11 @@ class Generator:
         self.tasks = []
         row = 0
         toff = 0
+        self.rows_p0 = 0
+        # tasks are listed in STACKED order: priority level, then insertion order (dls.cpp:18-24)
+        prios = [int(t.get("priority", 0)) for t in spec["tasks"]]
+        if prios != sorted(prios):
+            raise ValueError("spec tasks must be listed in stacked (priority) order")
         for t in spec["tasks"]:
             f = self.frames[t["frame"]]
             ktype = {"position": POSITION, "orientation": ORIENTATION, "full": FULL}[t["type"]]
@@ -162,7 +173,10 @@ class Generator:
                 chain.append(j)
                 j = self.joints[j]["parent"]
             chain.reverse()
-            self.tasks.append(dict(frame=f, ktype=ktype, dim=dim, row=row, toff=toff, chain=chain, name=t["frame"]))
+            self.tasks.append(dict(frame=f, ktype=ktype, dim=dim, row=row, toff=toff, chain=chain, name=t["frame"],
+                                   priority=int(t.get("priority", 0))))
+            if int(t.get("priority", 0)) == 0:
+                self.rows_p0 += dim
             row += dim
             toff += 12
         self.rows = row
@@ -243,6 +257,8 @@ class Generator:
         world = {}
         for ti, task in enumerate(self.tasks):
             f = task["frame"]
+            if ti > 0:
+                E.raw("IKB_PHASE_FENCE();")
             E.comment("==== task %d: frame %s, %s ====" % (ti, task["name"], ["Position", "Orientation", "Full"][task["ktype"]]))
             jf = f["parent"]
             if jf > 0:
@@ -352,35 +368,92 @@ class Generator:
                 self.ff_joint = j
         return E.lines
 
-    def gen_gram(self):
-        """Gram matrix from the strip -> packed lower triangle in registers, + damping."""
-        L = []
+    def gen_solve(self, W):
+        """y = (J J^T + damping^2 I)^-1 e  (dls.cpp:39-41,53) -- fused Gram / blocked left-looking LDL^T / substitutions.
+
+        Strip sL layout: strictly-lower L[i][k] at i*(i-1)/2 + k, then d[k] at M*(M-1)/2 + k."""
+        M = self.rows
         ind = "        "
-        rows = self.rows
-        L.append(ind + "TG G[%d];" % (rows * (rows + 1) // 2))
-        L.append(ind + "#pragma unroll")
-        L.append(ind + "for (int k = 0; k < %d; ++k) G[k] = TG(0);" % (rows * (rows + 1) // 2))
-        L.append(ind + "#pragma unroll")
-        L.append(ind + "for (int i = 0; i < %d; ++i) G[i * (i + 1) / 2 + i] = damping2;" % rows)
-        cols = sorted(set(c for (_, c) in self.slots))
+        L = []
+        nstrict = M * (M - 1) // 2
+
+        def Lidx(i, k):
+            return i * (i - 1) // 2 + k
+
+        col_rows = {}
+        for (r, c) in self.slots:
+            col_rows.setdefault(c, []).append(r)
+        for c in col_rows:
+            col_rows[c].sort()
         nfma = 0
-        for c in cols:
-            rs = sorted(r for (r, cc) in self.slots if cc == c)
-            L.append(ind + "{  // column %d: rows %s" % (c, rs))
-            for r in rs:
-                L.append(ind + "    const TG a%d = TG(sJ.get(%d));" % (r, self.slots[(r, c)]))
-            for i in rs:
-                for j in rs:
-                    if j <= i:
-                        L.append(ind + "    G[%d] += a%d * a%d;" % (i * (i + 1) // 2 + j, i, j))
+        L.append(ind + "T yp[%d];  // D^-1 L^-1 e, produced as the extra row of the factorisation" % M)
+        for j0 in range(0, M, W):
+            j1 = min(j0 + W, M)
+            blk = list(range(j0, j1))
+            L.append(ind + "IKB_PHASE_FENCE();")
+            L.append(ind + "// ---- block column %d..%d ----" % (j0, j1 - 1))
+            for j in blk:
+                for i in range(j, M):
+                    L.append(ind + "T g_%d_%d = %s;" % (i, j, "damping2" if i == j else "T(0)"))
+                L.append(ind + "T g_e_%d = e[%d];" % (j, j))
+            # Gram part: G[i][j] = sum_c J[i][c] J[j][c]
+            for c in sorted(col_rows):
+                rs = col_rows[c]
+                bj = [j for j in rs if j0 <= j < j1]
+                if not bj:
+                    continue
+                need = [i for i in rs if i >= bj[0]]
+                L.append(ind + "{  // J column %d" % c)
+                for i in need:
+                    L.append(ind + "    const T a%d = sJ.get(%d);" % (i, self.slots[(i, c)]))
+                for j in bj:
+                    for i in need:
+                        if i >= j:
+                            L.append(ind + "    g_%d_%d += a%d * a%d;" % (i, j, i, j))
+                            nfma += 1
+                L.append(ind + "}")
+            # left-looking update from the factor columns k < j0
+            for k in range(j0):
+                L.append(ind + "{  // minus column %d of the factor" % k)
+                L.append(ind + "    const T dk = sL.get(%d);" % (nstrict + k))
+                for i in range(j0, M):
+                    L.append(ind + "    const T l%d = sL.get(%d);" % (i, Lidx(i, k)))
+                for j in blk:
+                    L.append(ind + "    const T v%d = l%d * dk;" % (j, j))
+                for j in blk:
+                    for i in range(j, M):
+                        L.append(ind + "    g_%d_%d -= l%d * v%d;" % (i, j, i, j))
                         nfma += 1
-            L.append(ind + "}")
-        self.gram_fma = nfma
+                    L.append(ind + "    g_e_%d -= yp[%d] * v%d;" % (j, k, j))
+                L.append(ind + "}")
+            # factorise the block column in registers
+            for j in blk:
+                L.append(ind + "sL.set(%d, g_%d_%d);" % (nstrict + j, j, j))
+                L.append(ind + "const T inv_%d = T(1) / g_%d_%d;" % (j, j, j))
+                for i in range(j + 1, M):
+                    L.append(ind + "const T l_%d_%d = g_%d_%d * inv_%d;" % (i, j, i, j, j))
+                    L.append(ind + "sL.set(%d, l_%d_%d);" % (Lidx(i, j), i, j))
+                L.append(ind + "yp[%d] = g_e_%d * inv_%d;" % (j, j, j))
+                for j2 in range(j + 1, j1):
+                    for i in range(j2, M):
+                        L.append(ind + "g_%d_%d -= l_%d_%d * g_%d_%d;" % (i, j2, i, j, j2, j))
+                        nfma += 1
+                    L.append(ind + "g_e_%d -= yp[%d] * g_%d_%d;" % (j2, j, j2, j))
+        # back substitution y = L^-T yp, column oriented
+        L.append(ind + "IKB_PHASE_FENCE();")
+        L.append(ind + "// ---- back substitution ----")
+        for k in range(M - 1, -1, -1):
+            L.append(ind + "y[%d] = yp[%d];" % (k, k))
+            for i in range(k):
+                L.append(ind + "yp[%d] -= sL.get(%d) * y[%d];" % (i, Lidx(k, i), k))
+                nfma += 1
+        self.solve_fma = nfma
         return L
 
     def gen_dq(self):
         L = []
         ind = "        "
+        L.append(ind + "IKB_PHASE_FENCE();")
         for c in range(self.nv):
             rs = sorted(r for (r, cc) in self.slots if cc == c)
             if not rs:
@@ -418,33 +491,31 @@ class Generator:
 
     def emit(self, struct_name, display_name):
         ev = self.gen_evaluate()
-        gram = self.gen_gram()
         dq = self.gen_dq()
         integ = self.gen_integrate()
         rows, nslot = self.rows, len(self.slots)
+        solve = self.gen_solve(int(self.spec.get("block_width", 4)))
         used = self.signature()
         out = []
         out.append("// GENERATED by tools/gen_kernel.py -- do not edit.  Specialisation: %s" % display_name)
-        out.append("// rows=%d nv=%d nq=%d non-zero Jacobian entries=%d Gram FMAs=%d" % (rows, self.nv, self.nq, nslot, self.gram_fma))
+        out.append("// rows=%d nv=%d nq=%d non-zero Jacobian entries=%d solve FMAs=%d" % (rows, self.nv, self.nq, nslot, self.solve_fma))
         out.append("#pragma once")
-        out.append('#include "../../ik_b200/csrc/se3_math.cuh"')
-        out.append('#include "../../ik_b200/csrc/dls_spec.cuh"')
+        out.append('#include "../se3_math.cuh"')
+        out.append('#include "../spec_common.hpp"')
         out.append("namespace ikb {")
         out.append("struct %s {" % struct_name)
-        out.append("    static constexpr int NQ = %d, NV = %d, M = %d, M0 = %d, TSZ = %d, NSLOT = %d;" %
-                   (self.nq, self.nv, rows, rows, self.tsz, nslot))
+        out.append("    static constexpr int NQ = %d, NV = %d, M = %d, M0 = %d, TSZ = %d, NSLOT = %d, NFACT = %d;" %
+                   (self.nq, self.nv, rows, self.rows_p0, self.tsz, nslot, rows * (rows + 1) // 2))
         out.append('    static const char *name() { return "%s"; }' % display_name)
         out.append("    // FK + task errors + weighted task Jacobian (non-zero entries -> strip sJ)")
         out.append("    template <typename T, typename JS, typename TGT>")
         out.append("    static IKB_HD void evaluate(const T (&q)[NQ], const TGT &tg, const SpecConsts<T, NQ, M> &c, JS &sJ, T (&e)[M]) {")
         out.extend(ev)
         out.append("    }")
-        out.append("    // Gram matrix (registers, packed lower triangle) from the strip, with damping on the diagonal")
-        out.append("    template <typename TG, typename JS>")
-        out.append("    static IKB_HD void gram(const JS &sJ, TG damping2, TG (&Gout)[M * (M + 1) / 2]) {")
-        out.extend(gram)
-        out.append("#pragma unroll")
-        out.append("        for (int k = 0; k < M * (M + 1) / 2; ++k) Gout[k] = G[k];")
+        out.append("    // y = (J J^T + damping^2 I)^-1 e: fused Gram + blocked LDL^T (factor -> strip sL) + substitutions")
+        out.append("    template <typename T, typename JS, typename LS>")
+        out.append("    static IKB_HD void solve(const JS &sJ, LS &sL, T damping2, const T (&e)[M], T (&y)[M]) {")
+        out.extend(solve)
         out.append("    }")
         out.append("    // dq = -J^T y from the strip (dls.cpp:52)")
         out.append("    template <typename T, typename JS>")
@@ -470,8 +541,14 @@ class Generator:
             pl.extend(j["axis"])
         out.append("    static const double *sig_placement() { static const double v[] = {%s}; return v; }" %
                    ", ".join(repr(float(x)) for x in pl))
+        inv = sorted(self.slots.items(), key=lambda kv: kv[1])
+        out.append("    // (row, col) of every strip slot, for tests that rebuild the dense task Jacobian")
+        out.append("    static const int *slot_rc() { static const int v[] = {%s}; return v; }" %
+                   ", ".join("%d, %d" % rc for rc, _ in inv))
         out.append("    static const int *sig_task_type() { static const int v[] = {%s}; return v; }" %
                    ", ".join(str(t["ktype"]) for t in self.tasks))
+        out.append("    static const int *sig_task_priority() { static const int v[] = {%s}; return v; }" %
+                   ", ".join(str(t["priority"]) for t in self.tasks))
         out.append("    static const int *sig_task_joint() { static const int v[] = {%s}; return v; }" %
                    ", ".join(str(t["frame"]["parent"]) for t in self.tasks))
         fpl = []
