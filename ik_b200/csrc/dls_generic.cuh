@@ -166,10 +166,10 @@ __global__ void __launch_bounds__(128) dls_generic_kernel(const DevProblem<T> *_
                         for (int i = 0; i < 3; ++i) ptg[i] = tg[(toff + 9 + i) * es];
                         se3_mul(Rr, pr, Rtg, ptg, Rt, pt);  // oMt = oMr * target
                         // error: log6(fMt)
-                        T Re[9], pe[3], w[3], th, lin[3];
+                        T Re[9], pe[3], w[3], th, sth, cth, lin[3];
                         se3_actinv(Rf, pf, Rt, pt, Re, pe);
-                        log3(Re, w, th);
-                        LogCoeffs<T> lc = log_coeffs(th);
+                        log3(Re, w, th, sth, cth);
+                        LogCoeffs<T> lc = log_coeffs(th, sth, cth);
                         log6_from(w, lc, pe, lin);
                         const int ktype = P.t_type[t];
                         if (ktype == IKB_POSITION) { e[row] = lin[0]; e[row + 1] = lin[1]; e[row + 2] = lin[2]; }
@@ -179,10 +179,10 @@ __global__ void __launch_bounds__(128) dls_generic_kernel(const DevProblem<T> *_
                             e[row + 3] = w[0]; e[row + 4] = w[1]; e[row + 5] = w[2];
                         }
                         // Jacobian: rows of -Jlog6(tMf) * Jf_LOCAL
-                        T Rm[9], pm[3], w2[3], th2, A[9], Bm[9];
+                        T Rm[9], pm[3], w2[3], th2, sth2, cth2, A[9], Bm[9];
                         se3_actinv(Rt, pt, Rf, pf, Rm, pm);
-                        log3(Rm, w2, th2);
-                        LogCoeffs<T> lc2 = log_coeffs(th2);
+                        log3(Rm, w2, th2, sth2, cth2);
+                        LogCoeffs<T> lc2 = log_coeffs(th2, sth2, cth2);
                         jlog6_blocks(w2, th2, lc2, pm, A, Bm);
                         for (int j = fj; j > 0; j = P.parent[j]) {
                             const int c0 = P.idx_v[j], jt = P.jtype[j];
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(128) dls_generic_kernel(const DevProblem<T> *_
                     d -= l * l * G[k * (k + 1) / 2 + k];
                 }
                 G[j * (j + 1) / 2 + j] = d;
-                const T inv = T(1) / d;
+                const T inv = rcp_(d);
                 for (int i = j + 1; i < rows; ++i) {
                     T s = G[i * (i + 1) / 2 + j];
                     for (int k = 0; k < j; ++k) s -= G[i * (i + 1) / 2 + k] * G[j * (j + 1) / 2 + k] * G[k * (k + 1) / 2 + k];
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(128) dls_generic_kernel(const DevProblem<T> *_
                 for (int k = 0; k < i; ++k) s -= G[i * (i + 1) / 2 + k] * y[k];
                 y[i] = s;
             }
-            for (int i = 0; i < rows; ++i) y[i] /= G[i * (i + 1) / 2 + i];
+            for (int i = 0; i < rows; ++i) y[i] *= rcp_(G[i * (i + 1) / 2 + i]);
             for (int i = rows - 1; i >= 0; --i) {
                 T s = y[i];
                 for (int k = i + 1; k < rows; ++k) s -= G[k * (k + 1) / 2 + i] * y[k];

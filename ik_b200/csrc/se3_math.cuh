@@ -9,13 +9,7 @@
 // The functions are __host__ __device__ so tests/cpu_harness can unit-test the very same source on the CPU
 // build box (no GPU there); the product only ever calls them from device code.
 #pragma once
-#include <cmath>
-
-#if defined(__CUDACC__)
-#define IKB_HD __host__ __device__ __forceinline__
-#else
-#define IKB_HD inline
-#endif
+#include "fast_math.cuh"
 
 namespace ikb {
 
@@ -25,39 +19,14 @@ template <> struct Num<double> {
     static IKB_HD double taylor3() { return 1.220703125e-4; }
     static IKB_HD double taylor2() { return 6.0554544523933395e-6; }
     static IKB_HD double pi() { return 3.14159265358979323846; }
+    static IKB_HD double tiny() { return 1e-290; }
 };
 template <> struct Num<float> {
     static IKB_HD float taylor3() { return 1.8581361e-2f; }
     static IKB_HD float taylor2() { return 4.9215666e-3f; }
     static IKB_HD float pi() { return 3.14159265358979323846f; }
+    static IKB_HD float tiny() { return 1e-30f; }
 };
-
-IKB_HD void sincos_(double x, double *s, double *c) {
-#if defined(__CUDA_ARCH__)
-    sincos(x, s, c);
-#else
-    *s = std::sin(x); *c = std::cos(x);
-#endif
-}
-IKB_HD void sincos_(float x, float *s, float *c) {
-#if defined(__CUDA_ARCH__)
-    sincosf(x, s, c);
-#else
-    *s = std::sin(x); *c = std::cos(x);
-#endif
-}
-IKB_HD double sin_(double x) { return sin(x); }
-IKB_HD float sin_(float x) { return sinf(x); }
-IKB_HD double sqrt_(double x) { return sqrt(x); }
-IKB_HD float sqrt_(float x) { return sqrtf(x); }
-IKB_HD double acos_(double x) { return acos(x); }
-IKB_HD float acos_(float x) { return acosf(x); }
-IKB_HD double abs_(double x) { return fabs(x); }
-IKB_HD float abs_(float x) { return fabsf(x); }
-IKB_HD double min_(double a, double b) { return fmin(a, b); }
-IKB_HD float min_(float a, float b) { return fminf(a, b); }
-IKB_HD double max_(double a, double b) { return fmax(a, b); }
-IKB_HD float max_(float a, float b) { return fmaxf(a, b); }
 
 template <typename T> IKB_HD T dot3(const T *a, const T *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 template <typename T> IKB_HD void cross3(const T *a, const T *b, T *c) {
@@ -128,53 +97,49 @@ template <typename T> IKB_HD void rot_to_quat(const T *R, T *q) {
     if (t > T(0)) {
         t = sqrt_(t + T(1));
         q[3] = T(0.5) * t;
-        t = T(0.5) / t;
+        t = T(0.5) * rcp_(t);
         q[0] = (R[7] - R[5]) * t;
         q[1] = (R[2] - R[6]) * t;
         q[2] = (R[3] - R[1]) * t;
     } else if (R[0] >= R[4] && R[0] >= R[8]) {
         t = sqrt_(R[0] - R[4] - R[8] + T(1));
         q[0] = T(0.5) * t;
-        t = T(0.5) / t;
+        t = T(0.5) * rcp_(t);
         q[3] = (R[7] - R[5]) * t;
         q[1] = (R[3] + R[1]) * t;
         q[2] = (R[6] + R[2]) * t;
     } else if (R[4] > R[0] && R[4] >= R[8]) {
         t = sqrt_(R[4] - R[8] - R[0] + T(1));
         q[1] = T(0.5) * t;
-        t = T(0.5) / t;
+        t = T(0.5) * rcp_(t);
         q[3] = (R[2] - R[6]) * t;
         q[2] = (R[7] + R[5]) * t;
         q[0] = (R[1] + R[3]) * t;
     } else {
         t = sqrt_(R[8] - R[0] - R[4] + T(1));
         q[2] = T(0.5) * t;
-        t = T(0.5) / t;
+        t = T(0.5) * rcp_(t);
         q[3] = (R[3] - R[1]) * t;
         q[0] = (R[2] + R[6]) * t;
         q[1] = (R[5] + R[7]) * t;
     }
 }
 
-// exp6([v; w]) -> (R, p)   
+// exp6([v; w]) -> (R, p)   (SURVEY 8c.6).  Branch-free: both the closed form and the small-angle series are
+// evaluated and selected (the closed form's denominators are guarded; its value is discarded below the threshold).
 template <typename T> IKB_HD void exp6(const T *v, const T *w, T *R, T *p) {
     const T t2 = dot3(w, w);
-    T a_wxv, a_v, a_w, diag;
-    if (t2 < Num<T>::taylor3() * Num<T>::taylor3()) {
-        a_wxv = T(0.5) - t2 / 24;
-        a_v = 1 - t2 / 6;
-        a_w = T(1) / 6 - t2 / 120;
-        diag = 1 - t2 / 2;
-    } else {
-        const T t = sqrt_(t2);
-        T st, ct;
-        sincos_(t, &st, &ct);
-        const T inv_t2 = 1 / t2;
-        a_wxv = (1 - ct) * inv_t2;
-        a_v = st / t;
-        a_w = (1 - a_v) * inv_t2;
-        diag = ct;
-    }
+    const bool small = t2 < Num<T>::taylor3() * Num<T>::taylor3();
+    const T t = sqrt_(t2);
+    T st, ct;
+    sincos_(t, &st, &ct);
+    const T inv_t = rcp_(max_(t, Num<T>::tiny()));
+    const T inv_t2 = inv_t * inv_t;
+    const T g_av = st * inv_t;
+    const T a_wxv = small ? T(0.5) - t2 * T(1.0 / 24) : (1 - ct) * inv_t2;
+    const T a_v = small ? 1 - t2 * T(1.0 / 6) : g_av;
+    const T a_w = small ? T(1.0 / 6) - t2 * T(1.0 / 120) : (1 - g_av) * inv_t2;
+    const T diag = small ? 1 - t2 * T(0.5) : ct;
     T wxv[3];
     cross3(w, v, wxv);
     const T wv = a_w * dot3(w, v);
@@ -190,13 +155,19 @@ template <typename T> IKB_HD void exp6(const T *v, const T *w, T *R, T *p) {
     R[0] += diag; R[4] += diag; R[8] += diag;
 }
 
-// log3(R) -> w, theta   (diagonal formula within 1e-2 of pi)
-template <typename T> IKB_HD void log3(const T *R, T *w, T &theta) {
+// log3(R) -> w, theta, and (sin, cos) of theta   (diagonal formula within 1e-2 of pi).
+// theta = acos((tr R - 1)/2) exactly as Pinocchio computes it -- the closed-form coefficients below cancel
+// catastrophically for small angles (1/t^2 - ..., -2/t^4 + ...), so two implementations only agree closely if they
+// feed those formulas the same way; the acos / sincos used are the branch-free ones of fast_math.cuh.  The hot path
+// has no branch; the near-pi formula stays behind a (cold) one.
+template <typename T> IKB_HD void log3(const T *R, T *w, T &theta, T &st, T &ct) {
     const T tr = R[0] + R[4] + R[8];
-    T t;
-    if (tr >= T(3)) t = T(0);
-    else if (tr <= T(-1)) t = Num<T>::pi();
-    else t = acos_((tr - 1) / 2);
+    const T t = acos_(min_(T(1), max_(T(-1), T(0.5) * (tr - 1))));
+    sincos_(t, &st, &ct);
+    const T s = t > Num<T>::taylor2() ? T(0.5) * t * rcp_(max_(st, Num<T>::tiny())) : T(0.5);
+    w[0] = s * (R[7] - R[5]);
+    w[1] = s * (R[2] - R[6]);
+    w[2] = s * (R[3] - R[1]);
     if (t >= Num<T>::pi() - T(1e-2)) {
         const T cphi = -(tr - 1) / 2;
         const T beta = t * t / (1 + cphi);
@@ -204,14 +175,12 @@ template <typename T> IKB_HD void log3(const T *R, T *w, T &theta) {
         w[0] = (R[7] > R[5] ? T(1) : T(-1)) * (d0 > 0 ? sqrt_(d0) : T(0));
         w[1] = (R[2] > R[6] ? T(1) : T(-1)) * (d1 > 0 ? sqrt_(d1) : T(0));
         w[2] = (R[3] > R[1] ? T(1) : T(-1)) * (d2 > 0 ? sqrt_(d2) : T(0));
-    } else {
-        T s = T(0.5);
-        if (t > Num<T>::taylor2()) s = T(0.5) * t / sin_(t);
-        w[0] = s * (R[7] - R[5]);
-        w[1] = s * (R[2] - R[6]);
-        w[2] = s * (R[3] - R[1]);
     }
     theta = t;
+}
+template <typename T> IKB_HD void log3(const T *R, T *w, T &theta) {
+    T st, ct;
+    log3(R, w, theta, st, ct);
 }
 
 // Shared trigonometric coefficients of log6 / Jlog3 / Jlog6 for one rotation angle.
@@ -222,27 +191,27 @@ template <typename T> struct LogCoeffs {
     T a3;        // Jlog3 alpha: 1/t^2 - sin t/(1-cos t)/(2 t)   (== beta)
     T diag3;     // Jlog3 diagonal: t sin t /(2 (1 - cos t))     (== alpha)
 };
-template <typename T> IKB_HD LogCoeffs<T> log_coeffs(T t) {
+// (st, ct) = (sin t, cos t) as returned by log3.  Branch-free select between closed form and series.
+template <typename T> IKB_HD LogCoeffs<T> log_coeffs(T t, T st, T ct) {
     LogCoeffs<T> c;
     const T t2 = t * t;
-    if (t < Num<T>::taylor3()) {
-        c.alpha = 1 - t2 / 12 - t2 * t2 / 720;
-        c.beta = T(1) / 12 + t2 / 720;
-        c.bdot = T(1) / 360;
-        c.a3 = T(1) / 12 + t2 / 720;
-        c.diag3 = T(0.5) * (2 - t2 / 6);
-    } else {
-        T st, ct;
-        sincos_(t, &st, &ct);
-        const T tinv = 1 / t, t2inv = tinv * tinv;
-        const T inv_2_2ct = 1 / (2 * (1 - ct));
-        c.alpha = t * st * inv_2_2ct;
-        c.beta = t2inv - st * tinv * inv_2_2ct;
-        c.bdot = -2 * t2inv * t2inv + (1 + st * tinv) * t2inv * inv_2_2ct;
-        c.a3 = c.beta;
-        c.diag3 = c.alpha;
-    }
+    const bool small = t < Num<T>::taylor3();
+    const T tinv = rcp_(max_(t, Num<T>::tiny())), t2inv = tinv * tinv;
+    const T inv_2_2ct = rcp_(max_(2 * (1 - ct), Num<T>::tiny()));
+    const T g_alpha = t * st * inv_2_2ct;
+    const T g_beta = t2inv - st * tinv * inv_2_2ct;
+    const T g_bdot = -2 * t2inv * t2inv + (1 + st * tinv) * t2inv * inv_2_2ct;
+    c.alpha = small ? 1 - t2 * T(1.0 / 12) - t2 * t2 * T(1.0 / 720) : g_alpha;
+    c.beta = small ? T(1.0 / 12) + t2 * T(1.0 / 720) : g_beta;
+    c.bdot = small ? T(1.0 / 360) : g_bdot;
+    c.a3 = c.beta;
+    c.diag3 = small ? T(0.5) * (2 - t2 * T(1.0 / 6)) : g_alpha;
     return c;
+}
+template <typename T> IKB_HD LogCoeffs<T> log_coeffs(T t) {
+    T st, ct;
+    sincos_(t, &st, &ct);
+    return log_coeffs(t, st, ct);
 }
 
 // log6 given log3 output
@@ -295,7 +264,7 @@ template <typename T> IKB_HD void integrate_freeflyer(const T *R0, T *pos, T *qu
     const T d = qn[0] * quat[0] + qn[1] * quat[1] + qn[2] * quat[2] + qn[3] * quat[3];
     const T sgn = d < T(0) ? T(-1) : T(1);
     const T n2 = qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3];
-    const T a = sgn * (3 - n2) / 2;
+    const T a = sgn * (3 - n2) * T(0.5);
 #pragma unroll
     for (int i = 0; i < 4; ++i) quat[i] = qn[i] * a;
 #pragma unroll

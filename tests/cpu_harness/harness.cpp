@@ -6,16 +6,16 @@
 using namespace ikb;
 
 template <typename T> static void log6_t(const T *M, T *out) {
-    T w[3], th;
-    log3(M, w, th);
-    LogCoeffs<T> c = log_coeffs(th);
+    T w[3], th, st, ct;
+    log3(M, w, th, st, ct);
+    LogCoeffs<T> c = log_coeffs(th, st, ct);
     log6_from(w, c, M + 9, out);
     out[3] = w[0]; out[4] = w[1]; out[5] = w[2];
 }
 template <typename T> static void jlog6_t(const T *M, T *J) {
-    T w[3], th, A[9], B[9];
-    log3(M, w, th);
-    LogCoeffs<T> c = log_coeffs(th);
+    T w[3], th, st, ct, A[9], B[9];
+    log3(M, w, th, st, ct);
+    LogCoeffs<T> c = log_coeffs(th, st, ct);
     jlog6_blocks(w, th, c, M + 9, A, B);
     for (int i = 0; i < 36; ++i) J[i] = 0;
     for (int i = 0; i < 3; ++i)
@@ -45,5 +45,8 @@ void h_integrate_ff_f(const float *q, const float *v, float *o) { integrate_ff_t
 void h_rot_to_quat_d(const double *R, double *q) { rot_to_quat(R, q); }
 void h_quat_to_rot_d(const double *q, double *R) { quat_to_rot(q[0], q[1], q[2], q[3], R); }
 void h_se3_actinv_d(const double *A, const double *B, double *C) { se3_actinv(A, A + 9, B, B + 9, C, C + 9); }
+void h_sincos_d(double x, double *s, double *c) { sincos_(x, s, c); }
+double h_acos_d(double x) { return acos_(x); }
+double h_atan2pos_d(double y, double x) { return atan2pos_(y, x); }
 void h_se3_mul_d(const double *A, const double *B, double *C) { se3_mul(A, A + 9, B, B + 9, C, C + 9); }
 }

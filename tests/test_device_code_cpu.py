@@ -53,8 +53,9 @@ def test_device_exp6_log6_jlog6_match_oracle(math_lib):
             v = np.concatenate([RNG.uniform(-1, 1, 3), RNG.uniform(-1, 1, 3) * scale])
             M = np.zeros(12)
             math_lib.h_exp6_d(_pd(v), _pd(M))
-            assert np.abs(M - O.exp6(v)).max() < 1e-14
+            assert np.abs(M - O.exp6(v)).max() < 1e-12  # (1 - sin t / t) / t^2 amplifies 1-ulp sin differences
             lg = np.zeros(6)
+            M = O.exp6(v)
             math_lib.h_log6_d(_pd(M), _pd(lg))
             assert np.abs(lg - O.log6(M)).max() < 1e-12
             J = np.zeros(36)
@@ -185,3 +186,29 @@ def test_specialisation_matching_is_exact():
     pb = ik.InverseKinematicsProblem(mf, 0)
     pb.add_frame_task("fl", ik.FrameTask(mf, "LeftFootFront", ik.KinematicType.Position))
     assert pb.specialisation() is None
+
+
+def test_branch_free_sincos_and_atan2(math_lib):
+    """ik_b200/csrc/fast_math.cuh against libm over the ranges the IK path uses."""
+    math_lib.h_atan2pos_d.restype = C.c_double
+    math_lib.h_atan2pos_d.argtypes = [C.c_double, C.c_double]
+    math_lib.h_sincos_d.argtypes = [C.c_double, _dp, _dp]
+    xs = np.concatenate([RNG.uniform(-7, 7, 4000), RNG.uniform(-1e-3, 1e-3, 500), RNG.uniform(-3000, 3000, 500),
+                         np.array([0.0, np.pi / 4, -np.pi / 4, np.pi / 2, np.pi, -np.pi, 1e-300, 2 * np.pi])])
+    s, c = np.zeros(1), np.zeros(1)
+    for x in xs:
+        math_lib.h_sincos_d(float(x), _pd(s), _pd(c))
+        assert abs(s[0] - np.sin(x)) < 4e-16 * max(1.0, abs(x) / 10) and abs(c[0] - np.cos(x)) < 4e-16 * max(1.0, abs(x) / 10)
+    th = np.concatenate([RNG.uniform(0, np.pi, 4000), RNG.uniform(0, 1e-6, 300), np.pi - RNG.uniform(0, 1e-6, 300),
+                         np.array([0.0, np.pi / 8, np.pi / 4, np.pi / 2, 3 * np.pi / 4, np.pi])])
+    for t in th:
+        for scale in (1.0, 1e-3, 7.0):
+            got = math_lib.h_atan2pos_d(float(scale * np.sin(t)), float(scale * np.cos(t)))
+            assert abs(got - np.arctan2(np.sin(t), np.cos(t))) < 5e-16
+    assert math_lib.h_atan2pos_d(0.0, 0.0) == 0.0
+    math_lib.h_acos_d.restype = C.c_double
+    math_lib.h_acos_d.argtypes = [C.c_double]
+    for x in np.concatenate([RNG.uniform(-1, 1, 4000), 1 - RNG.uniform(0, 1e-8, 500), -1 + RNG.uniform(0, 1e-8, 200),
+                             np.array([1.0, -1.0, 0.0, 0.5, -0.5, 0.5000001, 1 - 1e-16])]):
+        ref = np.arccos(x)
+        assert abs(math_lib.h_acos_d(float(x)) - ref) <= 4e-16 * max(ref, 1e-8) + 1e-300, x

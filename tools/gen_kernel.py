@@ -279,12 +279,12 @@ class Generator:
             arr(E, "Rf%d" % n, Rf)
             arr(E, "pf%d" % n, pf)
             # fMt = oMf^-1 * oMt  (frame.hpp:48-50, universe reference => oMt = target)
-            E.raw("T Re%d[9], d%d[3], pe%d[3], w%d[3], th%d, lin%d[3];" % (n, n, n, n, n, n))
+            E.raw("T Re%d[9], d%d[3], pe%d[3], w%d[3], th%d, st%d, ct%d, lin%d[3];" % (n, n, n, n, n, n, n, n))
             E.raw("mat3T_mul(Rf%d, Rt%d, Re%d);" % (n, n, n))
             E.raw("for (int k = 0; k < 3; ++k) d%d[k] = pt%d[k] - pf%d[k];" % (n, n, n))
             E.raw("rotT_vec(Rf%d, d%d, pe%d);" % (n, n, n))
-            E.raw("log3(Re%d, w%d, th%d);" % (n, n, n))
-            E.raw("const LogCoeffs<T> lc%d = log_coeffs(th%d);" % (n, n))
+            E.raw("log3(Re%d, w%d, th%d, st%d, ct%d);" % (n, n, n, n, n))
+            E.raw("const LogCoeffs<T> lc%d = log_coeffs(th%d, st%d, ct%d);" % (n, n, n, n))
             E.raw("log6_from(w%d, lc%d, pe%d, lin%d);" % (n, n, n, n))
             # tMf = fMt^-1: rotation Re^T (log3 = -w, same angle), translation Rt^T (pf - pt)
             E.raw("T nw%d[3] = {-w%d[0], -w%d[1], -w%d[2]}, nd%d[3] = {-d%d[0], -d%d[1], -d%d[2]}, p2%d[3], A%dm[9], B%dm[9];"
@@ -429,7 +429,7 @@ class Generator:
             # factorise the block column in registers
             for j in blk:
                 L.append(ind + "sL.set(%d, g_%d_%d);" % (nstrict + j, j, j))
-                L.append(ind + "const T inv_%d = T(1) / g_%d_%d;" % (j, j, j))
+                L.append(ind + "const T inv_%d = rcp_(g_%d_%d);" % (j, j, j))
                 for i in range(j + 1, M):
                     L.append(ind + "const T l_%d_%d = g_%d_%d * inv_%d;" % (i, j, i, j, j))
                     L.append(ind + "sL.set(%d, l_%d_%d);" % (Lidx(i, j), i, j))
