@@ -50,6 +50,8 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.stop_flag = threading.Event()
+        self.armed = threading.Event()   # samples are recorded only while the timed region runs
+        self.ready = threading.Event()   # NVML initialised (takes longer than a whole timed region)
         self.sm = []
         self.reasons = set()
         self.max_mhz = None
@@ -69,7 +71,11 @@ class ClockSampler(threading.Thread):
                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
             }
+            self.ready.set()
             while not self.stop_flag.is_set():
+                if not self.armed.is_set():
+                    time.sleep(0.0005)
+                    continue
                 self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 try:
                     self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
@@ -79,9 +85,10 @@ class ClockSampler(threading.Thread):
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.02)
+                time.sleep(0.001)
         except Exception as e:  # pragma: no cover
             self.reasons.add("sampler_error:%s" % type(e).__name__)
+            self.ready.set()
 
     def summary(self):
         sm = sorted(self.sm)
@@ -208,12 +215,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident arm ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sampler.ready.wait(10.0)
     for w in range(args.warmup):
         q0_d, tg_d, out, _ = sets[w % nsets]
         ik.dls_batch(pb, q0_d, tg_d, prm, out)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.armed.set()
     launches0 = ik.kernel_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev[0].record()
@@ -224,8 +233,7 @@ def main():
     barrier()
     launches = ik.kernel_launch_count() - launches0
     elapsed_ms = ev[0].elapsed_time(ev[-1])
-    sampler.stop_flag.set()
-    sampler.join()
+    sampler.armed.clear()
     kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
 
     conv = 0
@@ -251,6 +259,7 @@ def main():
         h_tg[:] = host_sets[w % len(host_sets)]
         ik.dls_batch_host(pb, h_q0, h_tg, prm, args.dtype, "soa", h_out)
     barrier()
+    sampler.armed.set()  # the clocks record covers both timed regions (device-resident steps and e2e steps)
     t0 = time.perf_counter()
     e2e_conv = 0
     for k in range(e2e_steps):
@@ -258,6 +267,9 @@ def main():
         e2e_conv += int(h_out["success"].sum())
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    sampler.armed.clear()
+    sampler.stop_flag.set()
+    sampler.join()
 
     # ---- reduce over ranks ----
     stats = torch.tensor([elapsed_ms, e2e_s], dtype=torch.float64, device=dev)

@@ -1,0 +1,72 @@
+// The reference's only caller of ik::dls -- CassieIK::init / CassieIK::loop, ik_ros/src/cassie.cpp:19-130 -- without
+// ROS, written against include/ik/*.hpp (same names, same calls).  Each tick moves the left-foot target
+// (cassie.cpp:95-96), warm-starts from the previous solution (cassie.cpp:112) and solves with the demo parameters
+// (damping 1e-1, 200 iterations, step 1e-1; cassie.cpp:105-109).
+//
+//   g++ -std=c++17 -Iinclude examples/cassie_ik_demo.cpp -Lik_b200 -likb200 -Wl,-rpath,$PWD/ik_b200 -o build/cassie_ik_demo
+//   build/cassie_ik_demo ik_b200/data/cassie.urdf [ticks]
+//
+// Prints one line per tick: tick, success, iterations, ||e||^2, q[7..10]; and a final "batch" line from ik::dls_batch.
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <sstream>
+
+#include "ik/dls.hpp"
+#include "ik/frame.hpp"
+#include "ik/problem.hpp"
+
+int main(int argc, char **argv) {
+    if (argc < 2) {
+        std::fprintf(stderr, "usage: %s <cassie.urdf> [ticks]\n", argv[0]);
+        return 2;
+    }
+    const int ticks = argc > 2 ? std::atoi(argv[2]) : 10;
+    std::ifstream f(argv[1]);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    try {
+        ik::model_t model;
+        ik::urdf::buildModelFromXML(ss.str(), /*free_flyer=*/true, model);  // cassie.cpp:34-35
+        ik::InverseKinematicsProblem problem(model, 1);                      // cassie.cpp:43
+
+        auto fl = ik::FrameTask::create(model, "LeftFootFront", ik::KinematicType::Position, "pelvis");  // cassie.cpp:45-46
+        auto pelvis = ik::FrameTask::create(model, "pelvis", ik::KinematicType::Full);                   // cassie.cpp:54
+        auto align = ik::AlignAxisTask::create(model, "LeftFootFront", ik::AlignAxisType::AxisY);        // cassie.cpp:60-62
+        align->target = {1.0, 0.0, 0.0};
+        problem.add_frame_task("fl", fl);          // cassie.cpp:73
+        problem.add_frame_task("pelvis", pelvis);  // cassie.cpp:77
+        problem.add_align_axis_task("fl_align", align);  // cassie.cpp:81
+
+        ik::vector_t q = model.neutral();  // zeros, q[6] = 1 (cassie.cpp:68-70)
+        ik::dls_data data(problem);        // cassie.cpp:86
+        ik::dls_parameters p;
+        p.damping = 1e-1;
+        p.max_iterations = 200;
+        p.step_length = 1e-1;
+        for (int k = 0; k < ticks; ++k) {
+            const double t = 0.02 * k;
+            problem.get_frame_task("fl")->target.translation() = {0.0, 0.1, -0.6 + 0.2 * std::sin(0.5 * t)};  // cassie.cpp:95-96
+            problem.get_frame_task("pelvis")->target = ik::se3_t::Identity();                                // cassie.cpp:98-99
+            q = ik::dls(problem, q, data, ik::inverse_kinematics_visitor(), p);                              // cassie.cpp:112
+            std::printf("tick %d success %d iterations %d resid %.12e q7..10 %.12e %.12e %.12e %.12e\n", k, (int)data.success,
+                        data.info.iterations, data.residual, q[7], q[8], q[9], q[10]);
+        }
+        // batched extension: the same problem for 4 foot heights at once
+        const int B = 4, nq = model.nq;
+        std::vector<double> q0(B * nq), tg;
+        for (int b = 0; b < B; ++b) {
+            std::copy(q.begin(), q.end(), q0.begin() + b * nq);
+            problem.get_frame_task("fl")->target.translation() = {0.0, 0.1, -0.7 + 0.05 * b};
+            const ik::vector_t t = problem.gather_targets();
+            tg.insert(tg.end(), t.begin(), t.end());
+        }
+        const ik::dls_batch_result r = ik::dls_batch(problem, B, q0.data(), tg.data(), ik::inverse_kinematics_visitor(), p);
+        for (int b = 0; b < B; ++b)
+            std::printf("batch %d success %d iterations %d resid %.12e\n", b, (int)r.success[b], r.iterations[b], r.residual[b]);
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "error: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

@@ -1,0 +1,124 @@
+"""The drop-in boundary: the C-ABI shared library exports every entry point include/ikb200.h declares, its host-only
+calls behave as documented, the solve entry points FAIL LOUDLY without a GPU (no CPU fallback), and the C++ facade
+(include/ik/*.hpp, the reference's class names) compiles against it.  GPU: the facade demo -- the reference's only
+caller, ik_ros/src/cassie.cpp, minus ROS -- runs and agrees with the oracle."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import ik_b200 as ik
+from ik_b200 import _capi as capi
+from ik_b200 import workloads as W
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "ik_b200", "libikb200.so")
+DEMO = os.path.join(ROOT, "build", "cassie_ik_demo")
+
+
+def _has_gpu():
+    return capi.lib.ikb_device_count() > 0
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "ikb200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(ikb_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 35
+    lib = C.CDLL(LIB)
+    missing = [n for n in declared if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_version_and_defaults():
+    assert capi.lib.ikb_version() == 100
+    p = capi.DlsParams()
+    capi.lib.ikb_dls_params_default(C.byref(p))
+    # common.hpp:61-65, dls.hpp:25, visitor.hpp:19
+    assert (p.max_iterations, p.step_length, p.damping, p.tolerance, p.max_time) == (100, 1.0, 1e-2, 1e-4, 1.0)
+
+
+def test_unknown_frame_and_bad_priority_are_hard_errors():
+    m = W.cassie_model()
+    assert m.getFrameId("no_such_frame") == m.nframes  # model.getFrameId semantics (common.hpp:50)
+    pb = ik.InverseKinematicsProblem(m, 0)
+    pb.add_frame_task("x", ik.FrameTask(m, "no_such_frame"))
+    with pytest.raises(KeyError):
+        pb.specialisation()
+    h = C.c_void_p()
+    capi.check(capi.lib.ikb_problem_create(m._h, 0, C.byref(h)), "create")
+    try:
+        assert capi.lib.ikb_problem_add_frame_task(h, 1, 2, 0, 3, None) == -1  # priority > max_priority_level
+        assert b"priority" in capi.lib.ikb_last_error()
+        assert capi.lib.ikb_problem_add_frame_task(h, 10 ** 6, 2, 0, 0, None) == -3  # IKB_ERR_UNKNOWN_FRAME
+    finally:
+        capi.lib.ikb_problem_free(h)
+
+
+def test_problem_sizes_follow_the_reference():
+    pb = W.cassie_feet_pelvis_problem()
+    h = pb._build_handle(None)
+    try:
+        lib = capi.lib
+        assert lib.ikb_problem_num_tasks(h) == 3 and lib.ikb_problem_rows(h) == 12 and lib.ikb_problem_e_size(h, 0) == 12
+        assert [lib.ikb_problem_task_dim(h, t) for t in range(3)] == [6, 3, 3]  # frame.hpp:100-107
+        assert lib.ikb_problem_target_size(h) == 36
+        assert [lib.ikb_problem_task_target_offset(h, t) for t in range(3)] == [0, 12, 24]
+    finally:
+        capi.lib.ikb_problem_free(h)
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_solve_fails_loudly_without_a_gpu():
+    pb = W.cassie_feet_pelvis_problem()
+    with pytest.raises(RuntimeError, match="no CUDA device|CUDA"):
+        pb.finalize(0)
+
+
+def _build_demo():
+    os.makedirs(os.path.dirname(DEMO), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "cassie_ik_demo.cpp"), "-L" + os.path.join(ROOT, "ik_b200"),
+                           "-likb200", "-Wl,-rpath," + os.path.join(ROOT, "ik_b200"), "-o", DEMO])
+
+
+def test_cpp_facade_compiles_and_links():
+    """include/ik/*.hpp under the reference's include paths; without a GPU the demo must stop at finalize."""
+    _build_demo()
+    if not _has_gpu():
+        r = subprocess.run([DEMO, os.path.join(ROOT, "ik_b200", "data", "cassie.urdf"), "1"], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_facade_demo_matches_oracle():
+    """The reference's demo loop (moving-reference foot task + pelvis pose + axis alignment, warm-started, demo
+    parameters) through the C++ facade equals the oracle tick by tick."""
+    from oracle import oracle as O
+    from tests.common import oracle_model
+
+    _build_demo()
+    ticks = 6
+    r = subprocess.run([DEMO, os.path.join(ROOT, "ik_b200", "data", "cassie.urdf"), str(ticks)], capture_output=True,
+                       text=True, check=True)
+    lines = [l.split() for l in r.stdout.splitlines() if l.startswith("tick")]
+    assert len(lines) == ticks
+    om = oracle_model("cassie")
+    opb = O.Problem(om, 1)
+    opb.add_frame_task("LeftFootFront", O.POSITION, "pelvis", 0)
+    opb.add_frame_task("pelvis", O.FULL, "universe", 0)
+    opb.add_align_axis_task("LeftFootFront", 1, "universe", 0)
+    q = om.neutral()
+    prm = O.params(200, 1e-1, 1e-1)
+    for k, l in enumerate(lines):
+        t = 0.02 * k
+        tg = np.concatenate([np.eye(3).reshape(-1), [0.0, 0.1, -0.6 + 0.2 * np.sin(0.5 * t)],
+                             np.eye(3).reshape(-1), np.zeros(3), [1.0, 0.0, 0.0]])
+        q, ok, it, res, _ = O.dls(opb, q, tg, prm)
+        assert int(l[3]) == int(ok) and int(l[5]) == it
+        assert abs(float(l[7]) - res) < 1e-9
+        assert np.abs(np.array([float(x) for x in l[9:13]]) - q[7:11]).max() < 1e-6
+    assert len([l for l in r.stdout.splitlines() if l.startswith("batch")]) == 4
