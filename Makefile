@@ -11,7 +11,7 @@ CSRC := ik_b200/csrc
 OBJ := build/obj
 LIB := ik_b200/libikb200.so
 GEN := $(CSRC)/gen
-SPECS := cassie_feet_pelvis manipulator_tool
+SPECS := cassie_feet_pelvis cassie_feet_pelvis_w1 cassie_feet_pelvis_w2 manipulator_tool
 GEN_HDRS := $(patsubst %,$(GEN)/%.cuh,$(SPECS))
 
 SRCS_CU := $(wildcard $(CSRC)/*.cu)
@@ -34,7 +34,7 @@ $(GEN)/%.cuh: ik_b200/specs/%.json tools/gen_kernel.py build/ikb_flatten
 
 gen: $(GEN_HDRS)
 
-$(OBJ)/spec_%.cu.o: $(CSRC)/spec_%.cu $(GEN)/%.cuh $(HDRS)
+$(OBJ)/spec_%.cu.o: $(CSRC)/spec_%.cu $(GEN_HDRS) $(HDRS)
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> $(OBJ)/spec_$*.ptxas.log || (cat $(OBJ)/spec_$*.ptxas.log; exit 1)
 

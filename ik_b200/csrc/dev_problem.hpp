@@ -44,6 +44,14 @@ template <typename T> struct SolveArgs {
     long long B;
     int max_iterations;
     T step_length, damping2, tolerance;
+    // Two-phase scheduling of the specialised kernels (dls_spec.cuh): the BULK launch suspends a problem that has not
+    // finished after `it_cap` steps (its iterate goes to `q`, its step count to `iters_ws`, its index to `list`); the
+    // TAIL launch (`resume` = 1) takes its problems from `list` and continues them from `q` / `iters_ws`.
+    int it_cap;                       // >= max_iterations: never suspend
+    int resume;                       // 0: tickets are problem indices 0..B-1; 1: tickets index `list`
+    unsigned int *list;               // suspended problem indices
+    unsigned long long *list_count;   // number of entries in `list` (zeroed before the BULK launch)
+    int *iters_ws;                    // step counts of suspended problems (the caller's `iters` or scratch)
 };
 
 }  // namespace ikb

@@ -1,20 +1,27 @@
 // Topology-specialised batched DLS IK kernel: the fast path of ikb_dls_solve_batch.
 //
-// One IK problem per THREAD, the whole ik::dls loop (reference dls.cpp:14-74) in-kernel, exactly like the generic
-// kernel -- but the per-iteration body is straight-line code generated for one fixed (tree, task list) pair by
-// tools/gen_kernel.py (see its header for the arithmetic), so:
-//   * there are no tables, no dynamic indexing and no local memory: FK, task errors and the Gram / LDL^T block
-//     columns live in registers;
-//   * the non-zero entries of the weighted task Jacobian, the LDL^T factor and the problem's target poses live in
-//     thread-private strips of shared memory (element k of thread t at base[k * BLOCK + t]: conflict-free);
-//   * limits and task weights arrive as a __grid_constant__ parameter, i.e. as constant-bank operands.
-// Per-thread state for the Cassie feet+pelvis problem in FP64: 105 (J) + 78 (factor) + 36 (targets) doubles of shared
-// memory = 1752 B, so 128 threads fill the 227 KB an SM offers; the register file holds the rest (255 regs/thread).
+// The whole ik::dls loop (reference dls.cpp:14-74) runs in-kernel; its body is straight-line code generated for one
+// fixed (tree, task list) pair by tools/gen_kernel.py (see its header for the arithmetic), so there are no tables, no
+// dynamic indexing and no local memory.  Work decomposition:
 //
-// Scheduling: persistent CTAs (one per SM for FP64); every LANE pulls problem indices from a global ticket counter
-// and refills itself the moment its problem converges or runs out of iterations, so all lanes of a warp execute the
-// same evaluate -> solve -> integrate body on every trip although iteration counts differ wildly across problems
-// (median 4, p95 13, max 100 on the Cassie workload).
+//   * a GROUP of NWARPS warps owns 32 problem slots; lane l of every warp of the group works on slot l.  The warps
+//     have ROLES (MPMD, no divergence: different warps may run different code): role k evaluates the tasks the
+//     generator assigned to it -- FK of their supporting joints, SE3-log errors, weighted Jacobian non-zeros -- while
+//     the other roles do theirs (Cassie: pelvis pose | left foot | right foot).  Role SOLVER then runs the fused
+//     Gram + blocked LDL^T + substitutions and the step dq = -J^T y; every role integrates its own register copy of q
+//     (bit-identical, same code and inputs), so no role ever waits for q.  Two named barriers per iteration
+//     (bar.sync id, NWARPS*32): after evaluate (J, e visible) and after solve (dq, ||e||^2 visible).
+//   * per-problem state lives in strips of shared memory (element k of slot s at base[k * SLOTS + s]:
+//     conflict-free): weighted J non-zeros, the LDL^T factor (whose storage first carries e and finally dq), the
+//     target poses; plus ||e||^2 and a prefetched ticket per slot.  Cassie FP64: 219 doubles + 16 B = 1768 B per
+//     problem -> 128 problems (4 groups, 12 warps) fill the 227 KB of an SM.
+//   * limits and task weights arrive as a __grid_constant__ parameter, i.e. as constant-bank operands.
+//
+// Scheduling: persistent CTAs, one per SM; every SLOT pulls problem indices from a global ticket counter and refills
+// itself the moment its problem converges or runs out of iterations, so all lanes execute the same body on every trip
+// although iteration counts differ wildly across problems (median 4, p95 15, max 100 on the Cassie workload).  The
+// SOLVER role knows ||e||^2 before everybody else and pulls the slot's next ticket right then (only if the slot is
+// about to finish), so a refill costs no extra barrier and the atomic's latency hides behind the solve.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -25,78 +32,142 @@
 
 namespace ikb {
 
-constexpr int kSmemPerSm = 228 * 1024;   // B200: 228 KB per SM, 1 KB reserved per resident CTA
-constexpr int kSmemPerCtaMax = 227 * 1024;
+constexpr int kSmemPerCtaMax = 227 * 1024;  // B200: 228 KB per SM, 227 KB usable by one CTA
 
 template <class Spec, typename T> struct SpecLaunch {
-    static constexpr int kStrip = Spec::NSLOT + Spec::NFACT + Spec::TSZ;  // scalars per thread
-    static constexpr int kBytesPerThread = kStrip * (int)sizeof(T);
-    static constexpr int kFit = kSmemPerCtaMax / kBytesPerThread;  // threads one CTA could hold
-    static constexpr int BLOCK = kFit >= 128 ? 128 : (kFit / 32) * 32;
-    static constexpr int kSmemBytes = BLOCK > 0 ? BLOCK * kBytesPerThread : 0;
-    // resident CTAs per SM: shared-memory bound, capped at 2 (256 threads x 255 registers is the whole register file)
-    static constexpr int kBySmem = BLOCK > 0 ? kSmemPerSm / (kSmemBytes + 1024) : 0;
-    static constexpr int MINB = kBySmem >= 2 ? 2 : 1;
-    static constexpr bool kFits = BLOCK >= 32;
+    static constexpr int NW = Spec::NWARPS;
+    static constexpr int kStrip = Spec::NSLOT + Spec::NFACT + Spec::TSZ + 1;              // scalars per problem (+ ||e||^2)
+    static constexpr int kBytesPerProblem = kStrip * (int)sizeof(T) + (int)sizeof(long long);  // + prefetched ticket
+    static constexpr int kBySmem = kSmemPerCtaMax / (32 * kBytesPerProblem);               // groups that fit
+    // register budget: 168 per thread for double, 128 for float -> at most 384 / 512 threads per (single) CTA
+    static constexpr int kMaxThreads = sizeof(T) == 8 ? 384 : 512;
+    static constexpr int kByRegs = kMaxThreads / (32 * NW);
+    static constexpr int kG0 = kBySmem < kByRegs ? kBySmem : kByRegs;
+    static constexpr int GROUPS = kG0 > 15 ? 15 : kG0;  // one named barrier per group (ids 1..15)
+    static constexpr bool kFits = GROUPS >= 1;
+    static constexpr int smem_bytes(int groups) { return groups * 32 * kBytesPerProblem; }
 };
 
-template <class Spec, typename T, int BLOCK, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB)
+template <class Spec, typename T, int GROUPS, int MINB>
+__global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
     dls_spec_kernel(const __grid_constant__ SpecConsts<T, Spec::NQ, Spec::M> c, const __grid_constant__ SolveArgs<T> a) {
-    constexpr int NQ = Spec::NQ, NV = Spec::NV, M = Spec::M, M0 = Spec::M0, TSZ = Spec::TSZ;
+    constexpr int NQ = Spec::NQ, NV = Spec::NV, M = Spec::M, NW = Spec::NWARPS, SLOTS = GROUPS * 32;
+    static_assert(Spec::NFACT >= M + NV, "factor strip must also hold e and dq");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *sm = reinterpret_cast<T *>(smem_raw) + threadIdx.x;
-    const Strip<T, BLOCK> sJ{sm};                                          // weighted task Jacobian, non-zeros only
-    const Strip<T, BLOCK> sL{sm + Spec::NSLOT * BLOCK};                    // LDL^T factor
-    const Strip<T, BLOCK> sT{sm + (Spec::NSLOT + Spec::NFACT) * BLOCK};    // this problem's target poses
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group = warp / NW, role = warp % NW;
+    const int slot = group * 32 + lane;
+    T *sm = reinterpret_cast<T *>(smem_raw) + slot;
+    using S = Strip<T, SLOTS>;
+    const S sJ{sm};                                         // weighted task Jacobian, non-zeros only
+    const S sL{sm + Spec::NSLOT * SLOTS};                   // LDL^T factor
+    const S sE = sL;                                        //   ... whose first M slots carry e until the solve starts
+    const S sD{sm + (Spec::NSLOT + M) * SLOTS};             //   ... and whose next NV slots carry dq after it
+    const S sT{sm + (Spec::NSLOT + Spec::NFACT) * SLOTS};   // target poses
+    T *sRes = sm + (Spec::NSLOT + Spec::NFACT + Spec::TSZ) * SLOTS;  // ||e[0]||^2 of the current evaluation
+    long long *sNext = reinterpret_cast<long long *>(smem_raw + (size_t)(Spec::NSLOT + Spec::NFACT + Spec::TSZ + 1) * SLOTS * sizeof(T)) + slot;
+
+    auto group_sync = [&]() {
+        if constexpr (NW > 1)
+            asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(NW * 32) : "memory");
+        else
+            __syncwarp();
+    };
 
     T q[NQ];
     long long b;
     int it = 0;
     bool have;
 
-    auto fetch = [&]() {
-        b = (long long)atomicAdd(a.ticket, 1ULL);
-        have = b < a.B;
+    // b holds a ticket on entry: a problem index (fresh problems) or an index into the suspended list (tail launch)
+    auto load_problem = [&]() {
         it = 0;
-        if (have) {
-            const T *q0 = a.q0 + b * a.q0_bs;
+        if (!a.resume) {
+            have = b < a.B;
+            if (have) {
+                const T *q0 = a.q0 + b * a.q0_bs;
 #pragma unroll
-            for (int k = 0; k < NQ; ++k) q[k] = __ldg(q0 + k * a.q0_es);
-            const T *tg = a.targets + b * a.tg_bs;
-#pragma unroll 4
-            for (int k = 0; k < TSZ; ++k) sT.set(k, __ldg(tg + k * a.tg_es));
+                for (int k = 0; k < NQ; ++k) q[k] = __ldg(q0 + k * a.q0_es);
+            }
+        } else {
+            have = b < (long long)*a.list_count;
+            if (have) {
+                b = a.list[b];
+                it = a.iters_ws[b];
+                const T *qs = a.q + b * a.q_bs;
+#pragma unroll
+                for (int k = 0; k < NQ; ++k) q[k] = qs[k * a.q_es];
+            }
         }
+        if (have) Spec::load_targets(role, a.targets + b * a.tg_bs, a.tg_es, sT);
     };
-    fetch();
+    // first ticket of every slot (the SOLVER role owns the ticket counter)
+    if (role == Spec::SOLVER) *sNext = (long long)atomicAdd(a.ticket, 1ULL);
+    group_sync();
+    b = *sNext;
+    load_problem();
 
-    while (__any_sync(0xffffffffu, have)) {
-        if (have) {
-            T e[M];
-            Spec::evaluate(q, sT, c, sJ, e);                    // data.cpp:25-58
+    // CTA-wide barrier at the top of every trip: the body is ~100 KB of straight-line code, far more than the 32 KB
+    // instruction cache in front of L2, so every warp streams it from L2 on every trip.  Warps that start a trip together
+    // stay in step (same instruction count whatever their lanes do) and share each fetched line; left alone they drift
+    // apart and each pulls its own copy (ncu: no_instruction stalls 0.4 -> 1.1 per issue).
+    while (__syncthreads_or(have)) {
+        if (have) Spec::evaluate(role, q, sT, c, sJ, sE);  // data.cpp:25-58, this role's tasks
+        group_sync();                                       // J and e of all roles visible
+        if (role == Spec::SOLVER && have) {
+            // The stop-test quantity first: a slot that is about to finish (converged, or on its last iteration) pulls
+            // its next ticket NOW, so the atomic's latency hides behind the solve and no slot ever hoards a ticket.
             T res = T(0);
 #pragma unroll
-            for (int i = 0; i < M0; ++i) res += e[i] * e[i];    // visitor.hpp:19 (priority-0 rows)
-            const bool converged = res < a.tolerance;
-            bool finished = converged;
-            if (!converged) {
-                // dq is not part of the batch result, so the solve of a converged problem (dls.cpp:52-53 runs before
-                // the stop test) is skipped: the returned q is the un-stepped iterate either way (dls.cpp:62-63).
-                T y[M], dq[NV];
-                Spec::solve(sJ, sL, a.damping2, e, y);          // dls.cpp:39-41,53
-                Spec::step_direction(sJ, y, dq);                // dls.cpp:52
-                Spec::integrate(q, dq, a.step_length, c);       // dls.cpp:67-71
-                ++it;
-                finished = it >= a.max_iterations;              // dls.cpp:14,76-77
+            for (int i = 0; i < Spec::M0; ++i) {
+                const T ei = sE.get(i);
+                res += ei * ei;                                     // visitor.hpp:19 (priority-0 rows)
             }
-            if (finished) {
-                T *qo = a.q + b * a.q_bs;
+            // Bulk launch only: once the ticket queue has run dry, a problem that has already taken it_cap steps is a
+            // straggler -- suspend it after this step and let the tail launch continue it (res >= tolerance > 0 here, so
+            // the decision travels to the other roles in the sign of the residual).
+            bool susp = false;
+            if (it + 1 >= a.it_cap && !(res < a.tolerance) && it + 1 < a.max_iterations)
+                susp = *(volatile unsigned long long *)a.ticket >= (unsigned long long)a.B;
+            if (res < a.tolerance || it + 1 >= a.max_iterations || susp) *sNext = (long long)atomicAdd(a.ticket, 1ULL);
+            T y[M], dq[NV];
+            Spec::solve(sJ, sL, sE, a.damping2, y);                 // dls.cpp:39-41,53
+            Spec::step_direction(sJ, y, dq);                        // dls.cpp:52
+            *sRes = susp ? -res : res;
 #pragma unroll
-                for (int k = 0; k < NQ; ++k) qo[k * a.q_es] = q[k];
-                if (a.success) a.success[b] = converged ? 1 : 0;
-                if (a.iters) a.iters[b] = it;
-                if (a.resid) a.resid[b] = res;
-                fetch();
+            for (int k = 0; k < NV; ++k) sD.set(k, dq[k]);
+        }
+        group_sync();                                       // ||e||^2, dq (and the next ticket) visible; J, e, factor dead
+        if (have) {
+            const T sres = *sRes;
+            const bool suspend = sres < T(0);               // bulk launch: hand the straggler to the tail launch
+            const T res = abs_(sres);
+            const bool converged = res < a.tolerance;       // visitor.hpp:19
+            bool finished = converged;                      // dls.cpp:61-64: the un-stepped iterate is returned
+            if (!converged) {
+                T dq[NV];
+#pragma unroll
+                for (int k = 0; k < NV; ++k) dq[k] = sD.get(k);
+                Spec::integrate(q, dq, a.step_length, c);   // dls.cpp:67-71
+                ++it;
+                finished = it >= a.max_iterations;          // dls.cpp:14,76-77
+            }
+            if (finished || suspend) {
+                if (role == Spec::SOLVER) {
+                    T *qo = a.q + b * a.q_bs;
+#pragma unroll
+                    for (int k = 0; k < NQ; ++k) qo[k * a.q_es] = q[k];
+                    if (suspend) {
+                        a.iters_ws[b] = it;
+                        a.list[atomicAdd(a.list_count, 1ULL)] = (unsigned int)b;
+                    } else {
+                        if (a.success) a.success[b] = converged ? 1 : 0;
+                        if (a.iters) a.iters[b] = it;
+                        if (a.resid) a.resid[b] = res;
+                    }
+                }
+                b = *sNext;
+                load_problem();
             }
         }
     }
@@ -138,13 +209,18 @@ template <class Spec> bool spec_matches(const HostProblem &hp) {
     return true;
 }
 
-template <class Spec, typename T> int launch_spec(const SpecHostConsts &hc, const SolveArgs<T> &a, int sm_count, cudaStream_t s) {
+// GROUPS = 32-problem groups per CTA, MINB = CTAs per SM the register allocation must allow.  The throughput
+// configuration is one big CTA per SM (GROUPS = SpecLaunch::GROUPS); the latency configuration is GROUPS = 1, so that
+// few problems spread over all SMs and every group has its schedulers to itself.
+template <class Spec, typename T, int GROUPS, int MINB>
+int launch_spec_cfg(const SpecHostConsts &hc, const SolveArgs<T> &a, long long ctas, cudaStream_t s) {
     using L = SpecLaunch<Spec, T>;
-    static_assert(L::kFits, "per-thread strips do not fit in shared memory for this scalar type");
-    auto fn = dls_spec_kernel<Spec, T, L::BLOCK, L::MINB>;
-    static bool attr_set = false;  // per (Spec, T) instantiation
+    static_assert(L::kFits && GROUPS <= L::GROUPS, "per-problem strips do not fit in shared memory for this scalar type");
+    constexpr int kSmem = L::smem_bytes(GROUPS);
+    auto fn = dls_spec_kernel<Spec, T, GROUPS, MINB>;
+    static bool attr_set = false;  // per instantiation
     if (!attr_set) {
-        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes) != cudaSuccess) return 1;
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess) return 1;
         attr_set = true;
     }
     SpecConsts<T, Spec::NQ, Spec::M> c;
@@ -153,11 +229,23 @@ template <class Spec, typename T> int launch_spec(const SpecHostConsts &hc, cons
         c.upper[k] = (T)hc.upper[k];
     }
     for (int i = 0; i < Spec::M; ++i) c.weight[i] = (T)hc.weight[i];
-    long long blocks = (a.B + L::BLOCK - 1) / L::BLOCK;
-    const long long resident = (long long)L::MINB * sm_count;
-    if (blocks > resident) blocks = resident;
-    fn<<<(unsigned)blocks, L::BLOCK, L::kSmemBytes, s>>>(c, a);
+    if (ctas < 1) ctas = 1;
+    fn<<<(unsigned)ctas, GROUPS * Spec::NWARPS * 32, kSmem, s>>>(c, a);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+// Throughput configuration: persistent, one CTA per SM.
+template <class Spec, typename T> int launch_spec_bulk(const SpecHostConsts &hc, const SolveArgs<T> &a, long long n, int sm_count, cudaStream_t s) {
+    using L = SpecLaunch<Spec, T>;
+    long long ctas = (n + L::GROUPS * 32 - 1) / (L::GROUPS * 32);
+    if (ctas > sm_count) ctas = sm_count;
+    return launch_spec_cfg<Spec, T, L::GROUPS, 1>(hc, a, ctas, s);
+}
+// Latency configuration: one 32-problem group per CTA, at most 2 CTAs per SM (full register budget per thread).
+template <class Spec, typename T> int launch_spec_tail(const SpecHostConsts &hc, const SolveArgs<T> &a, long long n, int sm_count, cudaStream_t s) {
+    long long ctas = (n + 31) / 32;
+    if (ctas > 2LL * sm_count) ctas = 2LL * sm_count;
+    return launch_spec_cfg<Spec, T, 1, 2>(hc, a, ctas, s);
 }
 
 }  // namespace ikb

@@ -3,6 +3,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <climits>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <limits>
@@ -30,6 +32,17 @@ struct ikb_model {
 namespace {
 constexpr int kTicketSlots = 64;
 
+constexpr int kScratchSlots = 8;
+
+// Device scratch of one in-flight two-phase solve: the suspended-problem list and (when the caller passes no `iters`)
+// the step counts the tail launch resumes from.  Slots rotate; `ev` marks the end of the slot's last user.
+struct SolveScratch {
+    unsigned int *list = nullptr;
+    int *iters = nullptr;
+    size_t cap = 0;
+    cudaEvent_t ev = nullptr;
+};
+
 template <typename T> struct Staging {
     T *q0 = nullptr, *targets = nullptr, *q = nullptr, *resid = nullptr;
     size_t q0_cap = 0, tg_cap = 0, q_cap = 0, b_cap = 0;
@@ -49,6 +62,8 @@ struct ikb_problem {
     float *d_frame_pl32 = nullptr;
     unsigned long long *d_tickets = nullptr;
     std::atomic<unsigned> ticket_next{0};
+    SolveScratch scratch[kScratchSlots];
+    std::mutex scratch_mu;
     const SpecializedKernel *spec = nullptr;
     std::vector<double> weight_stacked;  // Task::weighting() rows in stacked order (constants of the specialised kernels)
     std::string kernel_name[2];
@@ -201,11 +216,67 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
         g_launches.fetch_add(1);
         return IKB_OK;
     }
+    a.it_cap = INT_MAX;
+    a.resume = 0;
+    a.list = nullptr;
+    a.list_count = nullptr;
+    a.iters_ws = io->iters;
     if (p->spec) {
         const SpecHostConsts hc{p->hp.model.lower.data(), p->hp.model.upper.data(), p->weight_stacked.data()};
-        int rc = launch_specialized<T>(*p->spec, hc, a, p->sm_count, s);
+        // Scheduling.  A batch that the latency configuration keeps resident in one wave runs there
+        // directly.  A larger batch runs BULK (throughput configuration) with a step cap: the few problems still
+        // unfinished after `cap` steps -- the reference lets them run to max_iterations, 100 by default -- are suspended
+        // and a TAIL launch continues all of them at once, each group of 32 with an SM's schedulers to itself, instead
+        // of letting them trickle out of the bulk kernel one 100-step straggler at a time.
+        const long long wave = 2LL * 32 * p->sm_count;
+        const char *cap_env = std::getenv("IKB_BULK_CAP");
+        const int cap = cap_env ? std::atoi(cap_env) : 16;
+        int rc;
+        if (B <= wave) {
+            rc = launch_specialized<T>(*p->spec, hc, a, SPEC_TAIL, B, p->sm_count, s);
+            if (rc == IKB_OK) g_launches.fetch_add(1);
+        } else if (cap <= 0 || prm->max_iterations <= cap) {
+            rc = launch_specialized<T>(*p->spec, hc, a, SPEC_BULK, B, p->sm_count, s);
+            if (rc == IKB_OK) g_launches.fetch_add(1);
+        } else {
+            ikb_problem *mp = const_cast<ikb_problem *>(p);
+            SolveScratch *sc;
+            {
+                std::lock_guard<std::mutex> lk(mp->scratch_mu);
+                if (mp->scratch[0].cap < (size_t)B) {
+                    // grow every slot at once (one synchronisation, on the first large batch only)
+                    IKB_CUDA(cudaDeviceSynchronize());
+                    for (auto &x : mp->scratch) {
+                        if (x.list) cudaFree(x.list);
+                        if (x.iters) cudaFree(x.iters);
+                        x.list = nullptr; x.iters = nullptr; x.cap = 0;
+                        IKB_CUDA(cudaMalloc(&x.list, (size_t)B * sizeof(unsigned int)));
+                        IKB_CUDA(cudaMalloc(&x.iters, (size_t)B * sizeof(int)));
+                        x.cap = (size_t)B;
+                        if (!x.ev) IKB_CUDA(cudaEventCreateWithFlags(&x.ev, cudaEventDisableTiming));
+                    }
+                }
+                sc = &mp->scratch[slot % kScratchSlots];
+                IKB_CUDA(cudaStreamWaitEvent(s, sc->ev, 0));  // the slot's previous user (any stream) must be done
+            }
+            IKB_CUDA(cudaMemsetAsync(a.ticket, 0, 3 * sizeof(unsigned long long), s));  // bulk ticket, tail ticket, list count
+            a.it_cap = cap;
+            a.list = sc->list;
+            a.list_count = a.ticket + 2;
+            a.iters_ws = io->iters ? io->iters : sc->iters;
+            rc = launch_specialized<T>(*p->spec, hc, a, SPEC_BULK, B, p->sm_count, s);
+            if (rc == IKB_OK) {
+                g_launches.fetch_add(1);
+                SolveArgs<T> t = a;
+                t.resume = 1;
+                t.it_cap = INT_MAX;
+                t.ticket = a.ticket + 1;
+                rc = launch_specialized<T>(*p->spec, hc, t, SPEC_TAIL, B, p->sm_count, s);
+                if (rc == IKB_OK) g_launches.fetch_add(1);
+            }
+            IKB_CUDA(cudaEventRecord(sc->ev, s));
+        }
         if (rc != IKB_OK) return cuda_fail(cudaGetLastError(), "specialised kernel launch");
-        g_launches.fetch_add(1);
         return IKB_OK;
     }
     auto fn = KernelTable<T>::dls(p->size_class);
@@ -519,6 +590,10 @@ void ikb_problem_free(ikb_problem *p) {
         cudaFree(p->st64.q0); cudaFree(p->st64.targets); cudaFree(p->st64.q); cudaFree(p->st64.resid);
         cudaFree(p->st32.q0); cudaFree(p->st32.targets); cudaFree(p->st32.q); cudaFree(p->st32.resid);
         cudaFree(p->st_success); cudaFree(p->st_iters);
+        for (auto &sc : p->scratch) {
+            cudaFree(sc.list); cudaFree(sc.iters);
+            if (sc.ev) cudaEventDestroy(sc.ev);
+        }
         if (p->stream) cudaStreamDestroy(p->stream);
     }
     delete p;

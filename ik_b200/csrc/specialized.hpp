@@ -15,11 +15,16 @@ struct SpecHostConsts {
     const double *weight;         // [rows], stacked order
 };
 
+// BULK: throughput configuration (persistent, one CTA per SM).  TAIL: latency configuration (one 32-problem group per
+// CTA, more warp roles) -- used for the stragglers a BULK launch suspends and for batches too small to fill the GPU.
+enum SpecVariant { SPEC_BULK = 0, SPEC_TAIL = 1 };
+
 struct SpecializedKernel {
     const char *name;
     bool (*matches)(const HostProblem &hp);
-    int (*launch64)(const SpecHostConsts &hc, const SolveArgs<double> &a, int sm_count, cudaStream_t s);
-    int (*launch32)(const SpecHostConsts &hc, const SolveArgs<float> &a, int sm_count, cudaStream_t s);
+    // n = upper bound on the number of problems the launch will see (sizes the grid)
+    int (*launch64)(const SpecHostConsts &hc, const SolveArgs<double> &a, int variant, long long n, int sm_count, cudaStream_t s);
+    int (*launch32)(const SpecHostConsts &hc, const SolveArgs<float> &a, int variant, long long n, int sm_count, cudaStream_t s);
 };
 
 const SpecializedKernel *find_specialized(const HostProblem &hp);
@@ -27,17 +32,17 @@ const SpecializedKernel *find_specialized(const HostProblem &hp);
 const SpecializedKernel *const *specialized_registry();
 
 template <typename T>
-inline int launch_specialized(const SpecializedKernel &k, const SpecHostConsts &hc, const SolveArgs<T> &a, int sm_count,
-                              cudaStream_t s);
+inline int launch_specialized(const SpecializedKernel &k, const SpecHostConsts &hc, const SolveArgs<T> &a, int variant,
+                              long long n, int sm_count, cudaStream_t s);
 template <>
 inline int launch_specialized<double>(const SpecializedKernel &k, const SpecHostConsts &hc, const SolveArgs<double> &a,
-                                      int sm_count, cudaStream_t s) {
-    return k.launch64(hc, a, sm_count, s);
+                                      int variant, long long n, int sm_count, cudaStream_t s) {
+    return k.launch64(hc, a, variant, n, sm_count, s);
 }
 template <>
 inline int launch_specialized<float>(const SpecializedKernel &k, const SpecHostConsts &hc, const SolveArgs<float> &a,
-                                     int sm_count, cudaStream_t s) {
-    return k.launch32(hc, a, sm_count, s);
+                                     int variant, long long n, int sm_count, cudaStream_t s) {
+    return k.launch32(hc, a, variant, n, sm_count, s);
 }
 
 }  // namespace ikb

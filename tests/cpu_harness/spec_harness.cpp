@@ -5,6 +5,8 @@
 #include <vector>
 
 #include "../../ik_b200/csrc/gen/cassie_feet_pelvis.cuh"
+#include "../../ik_b200/csrc/gen/cassie_feet_pelvis_w1.cuh"
+#include "../../ik_b200/csrc/gen/cassie_feet_pelvis_w2.cuh"
 #include "../../ik_b200/csrc/gen/manipulator_tool.cuh"
 
 using namespace ikb;
@@ -17,22 +19,20 @@ static int spec_solve(const double *lower, const double *upper, const double *we
     SpecConsts<T, NQ, M> c;
     for (int k = 0; k < NQ; ++k) { c.lower[k] = (T)lower[k]; c.upper[k] = (T)upper[k]; }
     for (int i = 0; i < M; ++i) c.weight[i] = (T)weight[i];
-    std::vector<T> bufJ(Spec::NSLOT), bufL(Spec::NFACT), bufT(Spec::TSZ);
-    for (int k = 0; k < Spec::TSZ; ++k) bufT[k] = (T)targets[k];
+    std::vector<T> bufJ(Spec::NSLOT), bufL(Spec::NFACT), bufT(Spec::TSZ), tgt(targets, targets + Spec::TSZ);
     const Strip<T, 1> sJ{bufJ.data()}, sL{bufL.data()}, sT{bufT.data()};
+    const Strip<T, 1> sE = sL;  // e aliases the start of the factor strip, as in the kernel
+    for (int role = 0; role < Spec::NWARPS; ++role) Spec::load_targets(role, tgt.data(), 1LL, sT);
     T q[NQ];
     for (int k = 0; k < NQ; ++k) q[k] = (T)q0[k];
     int it = 0, success = 0;
     T res = 0;
     while (it < max_it) {
-        T e[M];
-        Spec::evaluate(q, sT, c, sJ, e);
-        if (it == 0 && e_first) for (int i = 0; i < M; ++i) e_first[i] = (double)e[i];
-        res = 0;
-        for (int i = 0; i < Spec::M0; ++i) res += e[i] * e[i];
-        if (res < (T)tol) { success = 1; break; }
+        for (int role = 0; role < Spec::NWARPS; ++role) Spec::evaluate(role, q, sT, c, sJ, sE);  // the warp roles, in turn
+        if (it == 0 && e_first) for (int i = 0; i < M; ++i) e_first[i] = (double)sE.get(i);
         T y[M], dq[NV];
-        Spec::solve(sJ, sL, (T)(damping * damping), e, y);
+        res = Spec::solve(sJ, sL, sE, (T)(damping * damping), y);
+        if (res < (T)tol) { success = 1; break; }
         Spec::step_direction(sJ, y, dq);
         Spec::integrate(q, dq, (T)step, c);
         ++it;
@@ -49,12 +49,12 @@ static void spec_eval(const double *weight, const double *q0, const double *targ
     constexpr int NQ = Spec::NQ, NV = Spec::NV, M = Spec::M;
     SpecConsts<double, NQ, M> c{};
     for (int i = 0; i < M; ++i) c.weight[i] = weight[i];
-    std::vector<double> bufJ(Spec::NSLOT), bufT(targets, targets + Spec::TSZ);
-    const Strip<double, 1> sJ{bufJ.data()}, sT{bufT.data()};
-    double q[NQ], e[M];
+    std::vector<double> bufJ(Spec::NSLOT), bufT(targets, targets + Spec::TSZ), bufE(M);
+    const Strip<double, 1> sJ{bufJ.data()}, sT{bufT.data()}, sE{bufE.data()};
+    double q[NQ];
     for (int k = 0; k < NQ; ++k) q[k] = q0[k];
-    Spec::evaluate(q, sT, c, sJ, e);
-    for (int i = 0; i < M; ++i) e_out[i] = e[i];
+    for (int role = 0; role < Spec::NWARPS; ++role) Spec::evaluate(role, q, sT, c, sJ, sE);
+    for (int i = 0; i < M; ++i) e_out[i] = bufE[i];
     for (int i = 0; i < M * NV; ++i) J_out[i] = 0;
     for (int k = 0; k < Spec::NSLOT; ++k) J_out[Spec::slot_rc()[2 * k] * NV + Spec::slot_rc()[2 * k + 1]] = bufJ[k];
 }
@@ -73,4 +73,6 @@ static void spec_eval(const double *weight, const double *q0, const double *targ
     }
 
 IKB_SPEC_EXPORT(h_spec_cassie_feet_pelvis, SpecCassieFeetPelvis)
+IKB_SPEC_EXPORT(h_spec_cassie_feet_pelvis_w1, SpecCassieFeetPelvisW1)
+IKB_SPEC_EXPORT(h_spec_cassie_feet_pelvis_w2, SpecCassieFeetPelvisW2)
 IKB_SPEC_EXPORT(h_spec_manipulator_tool, SpecManipulatorTool)

@@ -109,7 +109,9 @@ def _spec_solve(lib, name, dtype, pb, q0, tg, prm):
     return q, ok, it, res, e0
 
 
-CASES = [("cassie_feet_pelvis", "cassie", True, W.cassie_feet_pelvis_problem, W.CASSIE_STANDING),
+CASES = [("cassie_feet_pelvis", "cassie", True, W.cassie_feet_pelvis_problem, W.CASSIE_STANDING),      # 3 warp roles
+         ("cassie_feet_pelvis_w1", "cassie", True, W.cassie_feet_pelvis_problem, W.CASSIE_STANDING),   # 1 role, legs interleaved
+         ("cassie_feet_pelvis_w2", "cassie", True, W.cassie_feet_pelvis_problem, W.CASSIE_STANDING),   # 2 roles
          ("manipulator_tool", "manipulator", False, W.manipulator_problem, "near")]
 
 

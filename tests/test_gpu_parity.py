@@ -35,12 +35,17 @@ def _solve_gpu(pb, q0, tg, params=None, dtype="f64"):
             out["iters"].cpu().numpy(), out["resid"].cpu().numpy().astype(np.float64))
 
 
-def _compare(name, gpu, ref, qtol, flag_mismatch_allowed=0, min_same_frac=0.99):
+def _compare(name, gpu, ref, qtol, flag_mismatch_allowed=0, min_same_frac=0.99, converged_only=False):
+    """converged_only: compare q on converged problems only -- a FAILED solve of a 6R arm bounces between joint limits
+    for 100 iterations (chaotic: two FP64 implementations end at different limits), unlike Cassie's failures, which
+    stagnate at a fixed point and are compared too."""
     q, ok, it, res = gpu
     q_ref, ok_ref, it_ref, res_ref = ref
     B = len(ok)
     flag_mismatch = int((ok != ok_ref).sum())
     same = (it == it_ref) & (ok == ok_ref)
+    if converged_only:
+        same &= ok.astype(bool)
     qerr = float(np.abs(q[same] - q_ref[same]).max()) if same.any() else 0.0
     conv = same & ok
     rerr = float(np.abs(res[conv] - res_ref[conv]).max()) if conv.any() else 0.0
@@ -236,7 +241,7 @@ def test_ur5_orientation_and_weights():
     opb = oracle_problem_like(pb, om)
     q0, tg, _ = make_workload(pb, om, B, seed=21, start="near")  # warm start: far starts are chaotic for a 6R arm
     ref = O.dls_batch(opb, q0, tg, nthreads=NT)
-    _compare("ur5 mixed tasks", _solve_gpu(pb, q0, tg), ref, 1e-6, min_same_frac=0.97)
+    _compare("ur5 mixed tasks", _solve_gpu(pb, q0, tg), ref, 1e-6, min_same_frac=0.97, converged_only=True)
 
 
 def test_full_size_properties():
@@ -271,3 +276,24 @@ def test_full_size_properties():
     lo, hi = m.lowerPositionLimit, m.upperPositionLimit
     moved = it > 0
     assert np.all(q[moved][:, 7:] >= lo[7:] - 1e-15) and np.all(q[moved][:, 7:] <= hi[7:] + 1e-15)
+
+
+@pytest.mark.parametrize("params", ["defaults", "demo"])
+def test_two_phase_scheduling_matches_oracle(params):
+    """A batch larger than one resident wave runs BULK (with suspension of stragglers once the ticket queue is dry) +
+    TAIL (continuation) -- results must be those of the plain loop: same flags, same iteration counts, same q."""
+    pb = W.cassie_feet_pelvis_problem()
+    om = oracle_model("cassie")
+    opb = oracle_problem_like(pb, om)
+    B = 24000
+    q0, tg, _ = make_workload(pb, om, B, seed=4242, standing=W.CASSIE_STANDING)
+    if params == "defaults":
+        prm, oprm = None, O.params()
+    else:
+        prm, oprm = ik.dls_parameters(max_iterations=200, step_length=0.1, damping=0.1), O.params(200, 0.1, 0.1)
+    ref = O.dls_batch(opb, q0, tg, oprm, nthreads=NT)
+    _compare("cassie two-phase %s" % params, _solve_gpu(pb, q0, tg, prm), ref, 1e-6)
+    # the host path without an `iters` output uses the internal step-count scratch
+    out = ik.dls_batch_host(pb, q0[:20000], tg[:20000], prm, "f64", "aos")
+    assert np.array_equal(out["success"].astype(bool), ref[1][:20000].astype(bool))
+    assert np.abs(out["q"] - ref[0][:20000]).max() < 1e-6

@@ -38,10 +38,11 @@ POSITION, ORIENTATION, FULL = 0, 1, 2
 # tiny symbolic layer: a value is a python float (compile-time constant) or a str (name of a `const T` variable)
 # ------------------------------------------------------------------------------------------------------------
 class Emitter:
-    def __init__(self):
+    def __init__(self, prefix=""):
         self.lines = []
         self.n = 0
         self.indent = "        "
+        self.prefix = prefix  # keeps the temporaries of interleaved emitters apart
 
     def comment(self, text):
         self.lines.append("%s// %s" % (self.indent, text))
@@ -51,7 +52,7 @@ class Emitter:
 
     def var(self, expr, hint="t"):
         """Materialise an expression string as a named const variable."""
-        name = "%s_%d" % (hint, self.n)
+        name = "%s%s_%d" % (self.prefix, hint, self.n)
         self.n += 1
         self.lines.append("%sconst T %s = %s;" % (self.indent, name, expr))
         return name
@@ -251,14 +252,52 @@ class Generator:
         world[j] = w
         return w
 
-    def gen_evaluate(self):
-        """evaluate(): e[], res and the J strip."""
+    def gen_evaluate(self, task_ids):
+        """evaluate_w<k>(): FK of the joints supporting the tasks of one warp role, their weighted error rows (-> strip sE)
+        and the non-zero entries of their weighted Jacobian rows (-> strip sJ)."""
         E = Emitter()
         world = {}
-        for ti, task in enumerate(self.tasks):
-            f = task["frame"]
-            if ti > 0:
+        inter = [g for g in self.spec.get("interleave", []) if all(t in task_ids for t in g)]
+        done = set()
+        for cnt, ti in enumerate(task_ids):
+            if ti in done:
+                continue
+            if cnt > 0:
                 E.raw("IKB_PHASE_FENCE();")
+            grp = next((g for g in inter if ti in g), None)
+            if grp is None:
+                self.gen_task(E, ti, world)
+                done.add(ti)
+                continue
+            # Independent tasks with the same shape (Cassie's two legs): emit them in lock step, statement by statement, so
+            # that ptxas sees two independent dependency chains side by side (a lone warp per scheduler has no other
+            # source of latency hiding).  Joints common to their chains are emitted once, up front.
+            common = set(self.tasks[grp[0]]["chain"])
+            for t in grp[1:]:
+                common &= set(self.tasks[t]["chain"])
+            for j in sorted(common):
+                self.fk_joint(E, j, world)
+            subs = []
+            for k, t in enumerate(grp):
+                Ek = Emitter(prefix="%c" % (ord("a") + k))
+                wk = dict(world)
+                self.gen_task(Ek, t, wk)
+                subs.append((Ek, wk))
+                done.add(t)
+            n = max(len(Ek.lines) for Ek, _ in subs)
+            for i in range(n):
+                for Ek, _ in subs:
+                    if i < len(Ek.lines):
+                        E.lines.append(Ek.lines[i])
+            for _, wk in subs:
+                world.update(wk)
+        return E.lines
+
+    def gen_task(self, E, ti, world):
+        """Error rows and Jacobian non-zeros of task ti (FK of its chain memoised in `world`)."""
+        if True:
+            task = self.tasks[ti]
+            f = task["frame"]
             E.comment("==== task %d: frame %s, %s ====" % (ti, task["name"], ["Position", "Orientation", "Full"][task["ktype"]]))
             jf = f["parent"]
             if jf > 0:
@@ -296,7 +335,7 @@ class Generator:
             src = {POSITION: ["lin%d[%d]" % (n, i) for i in range(3)], ORIENTATION: ["w%d[%d]" % (n, i) for i in range(3)],
                    FULL: ["lin%d[%d]" % (n, i) for i in range(3)] + ["w%d[%d]" % (n, i) for i in range(3)]}[kt]
             for i, s in enumerate(src):
-                E.raw("e[%d] = c.weight[%d] * %s;" % (row + i, row + i, s))
+                E.raw("sE.set(%d, c.weight[%d] * %s);" % (row + i, row + i, s))
             top = kt in (POSITION, FULL)
             bot = kt in (ORIENTATION, FULL)
             brow = row + (3 if kt == FULL else 0)
@@ -319,7 +358,7 @@ class Generator:
                             store(row + i, iv + 3 + k, E.var("-%s" % Bm[3 * i + k], "j"))
                         if bot:
                             store(brow + i, iv + 3 + k, E.var("-%s" % A[3 * i + k], "j"))
-                continue
+                return
             # M1 = A Rf^T, M2 = B Rf^T
             RfT = [Rf[3 * j_ + i] for i in range(3) for j_ in range(3)]
             M1 = matmul(E, A, RfT, "M1_")
@@ -362,11 +401,6 @@ class Generator:
                         m1z = matvec(E, M1, w["z"], "m1z")
                         for i in range(3):
                             store(row + i, iv, neg(E, m1z[i]))
-        self.R0 = None
-        for j, w in world.items():
-            if self.joints[j]["type"] == J_FF:
-                self.ff_joint = j
-        return E.lines
 
     def gen_solve(self, W):
         """y = (J J^T + damping^2 I)^-1 e  (dls.cpp:39-41,53) -- fused Gram / blocked left-looking LDL^T / substitutions.
@@ -386,7 +420,13 @@ class Generator:
         for c in col_rows:
             col_rows[c].sort()
         nfma = 0
-        L.append(ind + "T yp[%d];  // D^-1 L^-1 e, produced as the extra row of the factorisation" % M)
+        L.append(ind + "T e[%d], yp[%d];  // yp = D^-1 L^-1 e, produced as the extra row of the factorisation" % (M, M))
+        L.append(ind + "#pragma unroll")
+        L.append(ind + "for (int i = 0; i < %d; ++i) e[i] = sE.get(i);" % M)
+        L.append(ind + "T res = T(0);")
+        L.append(ind + "#pragma unroll")
+        L.append(ind + "for (int i = 0; i < %d; ++i) res += e[i] * e[i];  // visitor.hpp:19 (priority-0 rows)" % self.rows_p0)
+        L.append(ind + "IKB_PHASE_FENCE();  // sE may alias the factor strip: every e is in a register from here on")
         for j0 in range(0, M, W):
             j1 = min(j0 + W, M)
             blk = list(range(j0, j1))
@@ -443,10 +483,12 @@ class Generator:
         L.append(ind + "IKB_PHASE_FENCE();")
         L.append(ind + "// ---- back substitution ----")
         for k in range(M - 1, -1, -1):
-            L.append(ind + "y[%d] = yp[%d];" % (k, k))
             for i in range(k):
-                L.append(ind + "yp[%d] -= sL.get(%d) * y[%d];" % (i, Lidx(k, i), k))
+                L.append(ind + "yp[%d] -= sL.get(%d) * yp[%d];" % (i, Lidx(k, i), k))
                 nfma += 1
+        L.append(ind + "#pragma unroll")
+        L.append(ind + "for (int i = 0; i < %d; ++i) y[i] = yp[i];" % M)
+        L.append(ind + "return res;")
         self.solve_fma = nfma
         return L
 
@@ -490,36 +532,67 @@ class Generator:
         return used
 
     def emit(self, struct_name, display_name):
-        ev = self.gen_evaluate()
+        groups = self.spec.get("warp_groups") or [list(range(len(self.tasks)))]
+        if sorted(t for g in groups for t in g) != list(range(len(self.tasks))):
+            raise ValueError("warp_groups must partition the task list")
+        solver = int(self.spec.get("solver_warp", 0))
+        evs = [self.gen_evaluate(g) for g in groups]
         dq = self.gen_dq()
         integ = self.gen_integrate()
         rows, nslot = self.rows, len(self.slots)
         solve = self.gen_solve(int(self.spec.get("block_width", 4)))
         used = self.signature()
+        nfact = max(rows * (rows + 1) // 2, rows + self.nv)  # the factor strip also carries e (M) and dq (NV)
         out = []
         out.append("// GENERATED by tools/gen_kernel.py -- do not edit.  Specialisation: %s" % display_name)
-        out.append("// rows=%d nv=%d nq=%d non-zero Jacobian entries=%d solve FMAs=%d" % (rows, self.nv, self.nq, nslot, self.solve_fma))
+        out.append("// rows=%d nv=%d nq=%d non-zero Jacobian entries=%d solve FMAs=%d warp roles=%d" %
+                   (rows, self.nv, self.nq, nslot, self.solve_fma, len(groups)))
         out.append("#pragma once")
         out.append('#include "../se3_math.cuh"')
         out.append('#include "../spec_common.hpp"')
         out.append("namespace ikb {")
         out.append("struct %s {" % struct_name)
         out.append("    static constexpr int NQ = %d, NV = %d, M = %d, M0 = %d, TSZ = %d, NSLOT = %d, NFACT = %d;" %
-                   (self.nq, self.nv, rows, self.rows_p0, self.tsz, nslot, rows * (rows + 1) // 2))
+                   (self.nq, self.nv, rows, self.rows_p0, self.tsz, nslot, nfact))
+        out.append("    // warp roles: the tasks are split over NWARPS warps that evaluate concurrently; role SOLVER solves")
+        out.append("    static constexpr int NWARPS = %d, SOLVER = %d;" % (len(groups), solver))
         out.append('    static const char *name() { return "%s"; }' % display_name)
-        out.append("    // FK + task errors + weighted task Jacobian (non-zero entries -> strip sJ)")
-        out.append("    template <typename T, typename JS, typename TGT>")
-        out.append("    static IKB_HD void evaluate(const T (&q)[NQ], const TGT &tg, const SpecConsts<T, NQ, M> &c, JS &sJ, T (&e)[M]) {")
-        out.extend(ev)
+        for k, (g, ev) in enumerate(zip(groups, evs)):
+            names = ", ".join("%s %s" % (self.tasks[t]["name"], ["Position", "Orientation", "Full"][self.tasks[t]["ktype"]]) for t in g)
+            out.append("    // ---- role %d: %s ----" % (k, names))
+            out.append("    // copy this role's target poses into the strip sT")
+            out.append("    template <typename T, typename S>")
+            out.append("    static IKB_HD void load_targets_w%d(const T *tg, long long es, const S &sT) {" % k)
+            for t in g:
+                toff = self.tasks[t]["toff"]
+                out.append("#pragma unroll 4")
+                out.append("        for (int k = %d; k < %d; ++k) sT.set(k, tg[k * es]);" % (toff, toff + 12))
+            out.append("    }")
+            out.append("    // FK + task errors (-> sE) + weighted task Jacobian non-zeros (-> sJ)")
+            out.append("    template <typename T, typename S>")
+            out.append("    static IKB_HD void evaluate_w%d(const T (&q)[NQ], const S &tg, const SpecConsts<T, NQ, M> &c, const S &sJ, const S &sE) {" % k)
+            out.extend(ev)
+            out.append("    }")
+        out.append("    // role dispatch (warp-uniform)")
+        out.append("    template <typename T, typename S>")
+        out.append("    static IKB_HD void load_targets(int role, const T *tg, long long es, const S &sT) {")
+        for k in range(len(groups)):
+            out.append("        if (role == %d) load_targets_w%d(tg, es, sT);" % (k, k))
         out.append("    }")
-        out.append("    // y = (J J^T + damping^2 I)^-1 e: fused Gram + blocked LDL^T (factor -> strip sL) + substitutions")
-        out.append("    template <typename T, typename JS, typename LS>")
-        out.append("    static IKB_HD void solve(const JS &sJ, LS &sL, T damping2, const T (&e)[M], T (&y)[M]) {")
+        out.append("    template <typename T, typename S>")
+        out.append("    static IKB_HD void evaluate(int role, const T (&q)[NQ], const S &tg, const SpecConsts<T, NQ, M> &c, const S &sJ, const S &sE) {")
+        for k in range(len(groups)):
+            out.append("        if (role == %d) evaluate_w%d(q, tg, c, sJ, sE);" % (k, k))
+        out.append("    }")
+        out.append("    // y = (J J^T + damping^2 I)^-1 e: fused Gram + blocked LDL^T (factor -> strip sL) + substitutions.")
+        out.append("    // Reads e from sE (may alias the start of sL), returns ||e[0..M0)||^2 (the stop-test quantity, visitor.hpp:19).")
+        out.append("    template <typename T, typename S>")
+        out.append("    static IKB_HD T solve(const S &sJ, const S &sL, const S &sE, T damping2, T (&y)[M]) {")
         out.extend(solve)
         out.append("    }")
         out.append("    // dq = -J^T y from the strip (dls.cpp:52)")
-        out.append("    template <typename T, typename JS>")
-        out.append("    static IKB_HD void step_direction(const JS &sJ, const T (&y)[M], T (&dq)[NV]) {")
+        out.append("    template <typename T, typename S>")
+        out.append("    static IKB_HD void step_direction(const S &sJ, const T (&y)[M], T (&dq)[NV]) {")
         out.extend(dq)
         out.append("    }")
         out.append("    // q <- clamp(integrate(q, step*dq))")
