@@ -1,0 +1,18 @@
+// Specialised solve kernel: 32-DoF free-flyer humanoid with torso pose + four end-effector poses, all Full frame
+// tasks in `universe` (BASELINE.json config 4: 30 task rows).  Five warp roles: torso (+ the 30x30 solve) and one per
+// limb.  The per-problem strips (303 J non-zeros + 465 factor + 60 target scalars) allow one 32-problem group per SM in
+// FP64, so both launch variants are the one-group configuration.
+#include "dls_spec.cuh"
+#include "gen/humanoid_limbs.cuh"
+
+namespace ikb {
+namespace {
+using S = SpecHumanoidLimbs;
+template <typename T> int launch(const SpecHostConsts &hc, const SolveArgs<T> &a, int variant, long long n, int sms, cudaStream_t s) {
+    return variant == SPEC_TAIL ? launch_spec_tail<S, T>(hc, a, n, sms, s) : launch_spec_bulk<S, T>(hc, a, n, sms, s);
+}
+int l64(const SpecHostConsts &hc, const SolveArgs<double> &a, int v, long long n, int sms, cudaStream_t s) { return launch<double>(hc, a, v, n, sms, s); }
+int l32(const SpecHostConsts &hc, const SolveArgs<float> &a, int v, long long n, int sms, cudaStream_t s) { return launch<float>(hc, a, v, n, sms, s); }
+}  // namespace
+extern const SpecializedKernel kSpecHumanoidLimbs = {S::name(), spec_matches<S>, l64, l32};
+}  // namespace ikb

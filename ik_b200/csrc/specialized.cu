@@ -9,9 +9,10 @@ namespace ikb {
 
 extern const SpecializedKernel kSpecCassieFeetPelvis;
 extern const SpecializedKernel kSpecManipulatorTool;
+extern const SpecializedKernel kSpecHumanoidLimbs;
 
 namespace {
-const SpecializedKernel *const kRegistry[] = {&kSpecCassieFeetPelvis, &kSpecManipulatorTool, nullptr};
+const SpecializedKernel *const kRegistry[] = {&kSpecCassieFeetPelvis, &kSpecManipulatorTool, &kSpecHumanoidLimbs, nullptr};
 }
 
 const SpecializedKernel *const *specialized_registry() { return kRegistry; }

@@ -112,7 +112,8 @@ def _spec_solve(lib, name, dtype, pb, q0, tg, prm):
 CASES = [("cassie_feet_pelvis", "cassie", True, W.cassie_feet_pelvis_problem, W.CASSIE_STANDING),      # 3 warp roles
          ("cassie_feet_pelvis_w1", "cassie", True, W.cassie_feet_pelvis_problem, W.CASSIE_STANDING),   # 1 role, legs interleaved
          ("cassie_feet_pelvis_w2", "cassie", True, W.cassie_feet_pelvis_problem, W.CASSIE_STANDING),   # 2 roles
-         ("manipulator_tool", "manipulator", False, W.manipulator_problem, "near")]
+         ("manipulator_tool", "manipulator", False, W.manipulator_problem, "near"),
+         ("humanoid_limbs", "humanoid", True, W.humanoid_problem, "near")]                              # 5 roles, 30 rows
 
 
 def _workload(pb, om, B, standing):
@@ -128,7 +129,7 @@ def test_generated_body_f64_matches_oracle(spec_lib, name, robot, ff, make, stan
     pb = make()
     om = oracle_model(robot, ff)
     opb = oracle_problem_like(pb, om)
-    B = 200
+    B = 200 if robot != "humanoid" else 60
     q0, tg, _ = _workload(pb, om, B, standing)
     prm = O.params() if params == "defaults" else O.params(200, 1e-1, 1e-1)
     q_ref, ok_ref, it_ref, res_ref = O.dls_batch(opb, q0, tg, prm)
@@ -161,7 +162,8 @@ def test_specialisation_matching_is_exact():
     """ikb_problem_specialisation (host only): the compiled fast paths are picked for exactly their (tree, task list)."""
     assert W.cassie_feet_pelvis_problem().specialisation() == "cassie_feet_pelvis"
     assert W.manipulator_problem().specialisation() == "manipulator_tool"
-    assert W.humanoid_problem().specialisation() is None
+    assert W.humanoid_problem().specialisation() == "humanoid_limbs"
+    assert W.humanoid_problem(root_task=False).specialisation() is None
     m = W.cassie_model()
     # different task type / frame / reference frame / order -> generic kernel
     pb = ik.InverseKinematicsProblem(m, 0)

@@ -190,9 +190,10 @@ def test_host_path_layouts_agree():
     assert np.array_equal(a["resid"], d[3])
 
 
-def test_humanoid_f64():
+def test_humanoid_f64(kernel_path):
     """BASELINE config 4 (warm-started: W.near_start)."""
     pb = W.humanoid_problem()
+    _check_path(pb, kernel_path, "humanoid_limbs")
     om = oracle_model("humanoid")
     opb = oracle_problem_like(pb, om)
     q0, tg, _ = make_workload(pb, om, 512, seed=5, start="near")
