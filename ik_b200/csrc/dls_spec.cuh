@@ -52,7 +52,7 @@ template <class Spec, typename T, int GROUPS, int MINB>
 __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
     dls_spec_kernel(const __grid_constant__ SpecConsts<T, Spec::NQ, Spec::M> c, const __grid_constant__ SolveArgs<T> a) {
     constexpr int NQ = Spec::NQ, NV = Spec::NV, M = Spec::M, NW = Spec::NWARPS, SLOTS = GROUPS * 32;
-    static_assert(Spec::NFACT >= M + NV, "factor strip must also hold e and dq");
+    static_assert(Spec::NFACT >= M + NQ, "factor strip must also hold e and the stepped q");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group = warp / NW, role = warp % NW;
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
     const S sJ{sm};                                         // weighted task Jacobian, non-zeros only
     const S sL{sm + Spec::NSLOT * SLOTS};                   // LDL^T factor
     const S sE = sL;                                        //   ... whose first M slots carry e until the solve starts
-    const S sD{sm + (Spec::NSLOT + M) * SLOTS};             //   ... and whose next NV slots carry dq after it
+    const S sD{sm + (Spec::NSLOT + M) * SLOTS};             //   ... and whose next NQ slots carry the stepped q after it
     const S sT{sm + (Spec::NSLOT + Spec::NFACT) * SLOTS};   // target poses
     T *sRes = sm + (Spec::NSLOT + Spec::NFACT + Spec::TSZ) * SLOTS;  // ||e[0]||^2 of the current evaluation
     long long *sNext = reinterpret_cast<long long *>(smem_raw + (size_t)(Spec::NSLOT + Spec::NFACT + Spec::TSZ + 1) * SLOTS * sizeof(T)) + slot;
@@ -101,6 +101,21 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
         }
         if (have) Spec::load_targets(role, a.targets + b * a.tg_bs, a.tg_es, sT);
     };
+    // SOLVER role, after the solve: dq = -J^T y, the manifold step and the clamp on ITS copy of q, which it then publishes
+    // in the (dead) factor strip -- the other roles only copy it (no second and third integrate on the critical path).
+    auto step_and_publish = [&](const T(&y)[M], T sres) {
+        if (!(abs_(sres) < a.tolerance)) {                           // dls.cpp:61-64: a converged iterate is returned as is
+            T dq[NV];
+            Spec::step_direction(sJ, y, dq);                         // dls.cpp:52
+            Spec::integrate(q, dq, a.step_length, c);                // dls.cpp:67-71
+            if constexpr (NW > 1) {
+#pragma unroll
+                for (int k = 0; k < NQ; ++k) sD.set(k, q[k]);
+            }
+        }
+        *sRes = sres;
+    };
+
     // first ticket of every slot (the SOLVER role owns the ticket counter)
     if (role == Spec::SOLVER) *sNext = (long long)atomicAdd(a.ticket, 1ULL);
     group_sync();
@@ -114,6 +129,7 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
     while (__syncthreads_or(have)) {
         if (have) Spec::evaluate(role, q, sT, c, sJ, sE);  // data.cpp:25-58, this role's tasks
         group_sync();                                       // J and e of all roles visible
+        T sres_mine = T(0);
         if (role == Spec::SOLVER && have) {
             // The stop-test quantity first: a slot that is about to finish (converged, or on its last iteration) pulls
             // its next ticket NOW, so the atomic's latency hides behind the solve and no slot ever hoards a ticket.
@@ -130,12 +146,21 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
             if (it + 1 >= a.it_cap && !(res < a.tolerance) && it + 1 < a.max_iterations)
                 susp = *(volatile unsigned long long *)a.ticket >= (unsigned long long)a.B;
             if (res < a.tolerance || it + 1 >= a.max_iterations || susp) *sNext = (long long)atomicAdd(a.ticket, 1ULL);
-            T y[M], dq[NV];
-            Spec::solve(sJ, sL, sE, a.damping2, y);                 // dls.cpp:39-41,53
-            Spec::step_direction(sJ, y, dq);                        // dls.cpp:52
-            *sRes = susp ? -res : res;
-#pragma unroll
-            for (int k = 0; k < NV; ++k) sD.set(k, dq[k]);
+            sres_mine = susp ? -res : res;
+        }
+        if constexpr (NW > 1 && Spec::PSOLVE) {
+            // dls.cpp:39-41,53 distributed over the roles (cyclic row ownership, two barriers per block column).  Every
+            // lane of every warp takes part in the barriers, also lanes without a problem (their arithmetic is garbage
+            // that nobody reads).
+            T y[M];
+            Spec::psolve(role, sJ, sL, sE, a.damping2, y, group_sync);
+            if (role == Spec::SOLVER && have) step_and_publish(y, sres_mine);
+        } else {
+            if (role == Spec::SOLVER && have) {
+                T y[M];
+                Spec::solve(sJ, sL, sE, a.damping2, y);             // dls.cpp:39-41,53
+                step_and_publish(y, sres_mine);
+            }
         }
         group_sync();                                       // ||e||^2, dq (and the next ticket) visible; J, e, factor dead
         if (have) {
@@ -145,10 +170,12 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
             const bool converged = res < a.tolerance;       // visitor.hpp:19
             bool finished = converged;                      // dls.cpp:61-64: the un-stepped iterate is returned
             if (!converged) {
-                T dq[NV];
+                if constexpr (NW > 1) {
+                    if (role != Spec::SOLVER) {             // the stepped, clamped iterate (dls.cpp:67-71) from the solver
 #pragma unroll
-                for (int k = 0; k < NV; ++k) dq[k] = sD.get(k);
-                Spec::integrate(q, dq, a.step_length, c);   // dls.cpp:67-71
+                        for (int k = 0; k < NQ; ++k) q[k] = sD.get(k);
+                    }
+                }
                 ++it;
                 finished = it >= a.max_iterations;          // dls.cpp:14,76-77
             }

@@ -30,10 +30,10 @@ template <typename T> int launch(const SpecHostConsts &hc, const SolveArgs<T> &a
     }
 }
 int l64(const SpecHostConsts &hc, const SolveArgs<double> &a, int v, long long n, int sms, cudaStream_t s) {
-    return launch<double>(hc, a, v, n, sms, s, 2);
+    return launch<double>(hc, a, v, n, sms, s, 3);
 }
 int l32(const SpecHostConsts &hc, const SolveArgs<float> &a, int v, long long n, int sms, cudaStream_t s) {
-    return launch<float>(hc, a, v, n, sms, s, 3);
+    return launch<float>(hc, a, v, n, sms, s, 1);
 }
 }  // namespace
 extern const SpecializedKernel kSpecCassieFeetPelvis = {S3::name(), spec_matches<S3>, l64, l32};

@@ -2,6 +2,8 @@
 // dls_spec.cuh instantiates) with g++ and drives them with the same loop as the kernel, so the generated arithmetic
 // can be checked against the oracle on the GPU-less build box.  Never linked into libikb200.so; the product has no
 // CPU path.
+#include <barrier>
+#include <thread>
 #include <vector>
 
 #include "../../ik_b200/csrc/gen/cassie_feet_pelvis.cuh"
@@ -15,7 +17,7 @@ using namespace ikb;
 template <class Spec, typename T>
 static int spec_solve(const double *lower, const double *upper, const double *weight, const double *q0, const double *targets,
                       int max_it, double step, double damping, double tol, double *q_out, int *iters, double *resid,
-                      double *e_first) {
+                      double *e_first, bool parallel = false) {
     constexpr int NQ = Spec::NQ, NV = Spec::NV, M = Spec::M;
     SpecConsts<T, NQ, M> c;
     for (int k = 0; k < NQ; ++k) { c.lower[k] = (T)lower[k]; c.upper[k] = (T)upper[k]; }
@@ -32,7 +34,23 @@ static int spec_solve(const double *lower, const double *upper, const double *we
         for (int role = 0; role < Spec::NWARPS; ++role) Spec::evaluate(role, q, sT, c, sJ, sE);  // the warp roles, in turn
         if (it == 0 && e_first) for (int i = 0; i < M; ++i) e_first[i] = (double)sE.get(i);
         T y[M], dq[NV];
-        res = Spec::solve(sJ, sL, sE, (T)(damping * damping), y);
+        if (parallel && Spec::NWARPS > 1) {
+            // the role-distributed solve: one host thread per warp role, a std::barrier as the group barrier
+            res = 0;
+            for (int i = 0; i < Spec::M0; ++i) res += sE.get(i) * sE.get(i);
+            std::barrier<> bar(Spec::NWARPS);
+            std::vector<std::thread> th;
+            for (int role = 0; role < Spec::NWARPS; ++role)
+                th.emplace_back([&, role]() {
+                    T yl[M];
+                    auto sync = [&]() { bar.arrive_and_wait(); };
+                    Spec::psolve(role, sJ, sL, sE, (T)(damping * damping), yl, sync);
+                    if (role == Spec::SOLVER) for (int i = 0; i < M; ++i) y[i] = yl[i];
+                });
+            for (auto &t : th) t.join();
+        } else {
+            res = Spec::solve(sJ, sL, sE, (T)(damping * damping), y);
+        }
         if (res < (T)tol) { success = 1; break; }
         Spec::step_direction(sJ, y, dq);
         Spec::integrate(q, dq, (T)step, c);
@@ -68,6 +86,10 @@ static void spec_eval(const double *weight, const double *q0, const double *targ
     extern "C" int fn##_f(const double *lo, const double *hi, const double *w, const double *q0, const double *tg, int mi, \
                           double st, double da, double tol, double *q, int *it, double *res, double *e0) {               \
         return spec_solve<Spec, float>(lo, hi, w, q0, tg, mi, st, da, tol, q, it, res, e0);                              \
+    }                                                                                                                    \
+    extern "C" int fn##_pd(const double *lo, const double *hi, const double *w, const double *q0, const double *tg, int mi, \
+                           double st, double da, double tol, double *q, int *it, double *res, double *e0) {              \
+        return spec_solve<Spec, double>(lo, hi, w, q0, tg, mi, st, da, tol, q, it, res, e0, true);                       \
     }                                                                                                                    \
     extern "C" void fn##_eval(const double *w, const double *q0, const double *tg, double *e, double *J) {               \
         spec_eval<Spec>(w, q0, tg, e, J);                                                                                \

@@ -30,7 +30,8 @@ def _build(name):
     so = os.path.join(OUT, "lib" + name + ".so")
     deps = [src] + [os.path.join(dp, f) for dp, _, fs in os.walk(os.path.join(ROOT, "ik_b200", "csrc")) for f in fs]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-ffp-contract=off", "-o", so, src])
+        subprocess.check_call(["g++", "-O1", "-std=c++20", "-fPIC", "-shared", "-pthread", "-x", "c++", "-ffp-contract=off",
+                               "-o", so, src])
     return C.CDLL(so)
 
 
@@ -89,7 +90,7 @@ def test_device_integrate_freeflyer_matches_oracle(math_lib):
 
 def _spec_solve(lib, name, dtype, pb, q0, tg, prm):
     m = pb.model()
-    fn = getattr(lib, "h_spec_%s_%s" % (name, "d" if dtype == "f64" else "f"))
+    fn = getattr(lib, "h_spec_%s_%s" % (name, {"f64": "d", "f32": "f", "f64p": "pd"}[dtype]))
     fn.argtypes = [_dp, _dp, _dp, _dp, _dp, C.c_int, C.c_double, C.c_double, C.c_double, _dp, C.POINTER(C.c_int), _dp, _dp]
     lo, hi = np.ascontiguousarray(m.lowerPositionLimit), np.ascontiguousarray(m.upperPositionLimit)
     w = np.ascontiguousarray(np.concatenate([t.weighting() for _, t, _ in pb._tasks]))
@@ -216,3 +217,19 @@ def test_branch_free_sincos_and_atan2(math_lib):
                              np.array([1.0, -1.0, 0.0, 0.5, -0.5, 0.5000001, 1 - 1e-16])]):
         ref = np.arccos(x)
         assert abs(math_lib.h_acos_d(float(x)) - ref) <= 4e-16 * max(ref, 1e-8) + 1e-300, x
+
+
+@pytest.mark.parametrize("name,robot,ff,make,standing", [c for c in CASES if c[0] in ("cassie_feet_pelvis", "cassie_feet_pelvis_w2",
+                                                                                     "humanoid_limbs")])
+def test_role_distributed_solve_matches_oracle(spec_lib, name, robot, ff, make, standing):
+    """psolve_w<k>: the factorisation split over the warp roles (one host thread per role, std::barrier = group barrier)
+    gives the oracle's trajectory too."""
+    pb = make()
+    om = oracle_model(robot, ff)
+    opb = oracle_problem_like(pb, om)
+    B = 40 if robot != "humanoid" else 12
+    q0, tg, _ = _workload(pb, om, B, standing)
+    q_ref, ok_ref, it_ref, res_ref = O.dls_batch(opb, q0, tg)
+    q, ok, it, res, _ = _spec_solve(spec_lib, name, "f64p", pb, q0, tg, O.params())
+    assert (ok == ok_ref.astype(bool)).all() and (it == it_ref).all()
+    assert np.abs(q - q_ref).max() < 1e-8

@@ -492,6 +492,132 @@ class Generator:
         self.solve_fma = nfma
         return L
 
+    def gen_solve_parallel(self, W, R, solver):
+        """The same factorisation as gen_solve, distributed over the R warp roles of a group (one code list per role).
+
+        Block column kb (columns j0..j1-1): the rows of the diagonal block belong to role kb % R for this column, the rows
+        below it to role (i % R) (cyclic), the right-hand-side row to role `solver`.
+          phase 1  every role accumulates Gram + left-looking updates for its rows; the diagonal owner factorises the W x W
+                   block in registers and publishes it (L entries, pivots d) in the strip              -> sync
+          phase 2  every role eliminates its sub-diagonal rows against the published block (W(W-1)/2 + W loads), writes
+                   its L entries; the solver role does the same for the rhs row (forward substitution)   -> sync
+        After the last block column the solver role back-substitutes (serial) -- y ends in its registers.
+        All roles execute the same sequence of sync() calls."""
+        M = self.rows
+        ind = "        "
+        nstrict = M * (M - 1) // 2
+
+        def Lidx(i, k):
+            return i * (i - 1) // 2 + k
+
+        col_rows = {}
+        for (r, c) in self.slots:
+            col_rows.setdefault(c, []).append(r)
+        for c in col_rows:
+            col_rows[c].sort()
+        codes = [[] for _ in range(R)]
+        nfma = [0] * R
+        for role in range(R):
+            L = codes[role]
+            if role == solver:
+                L.append(ind + "T e[%d], yp[%d];" % (M, M))
+                L.append(ind + "#pragma unroll")
+                L.append(ind + "for (int i = 0; i < %d; ++i) e[i] = sE.get(i);" % M)
+            L.append(ind + "sync();  // e is in the solver's registers: the strip slots it aliased may be overwritten now")
+        nblk = (M + W - 1) // W
+        for kb in range(nblk):
+            j0, j1 = kb * W, min(kb * W + W, M)
+            blk = list(range(j0, j1))
+            downer = kb % R
+            for role in range(R):
+                L = codes[role]
+                own = [i for i in range(j1, M) if i % R == role]
+                rows = (blk if role == downer else []) + own  # matrix rows this role accumulates in this block column
+                has_e = role == solver
+                L.append(ind + "// ---- block column %d..%d: rows %s%s ----" % (j0, j1 - 1, rows, " + rhs" if has_e else ""))
+                L.append(ind + "IKB_PHASE_FENCE();")
+                pairs = [(i, j) for j in blk for i in rows if i >= j]
+                for (i, j) in pairs:
+                    L.append(ind + "T g_%d_%d = %s;" % (i, j, "damping2" if i == j else "T(0)"))
+                if has_e:
+                    for j in blk:
+                        L.append(ind + "T g_e_%d = e[%d];" % (j, j))
+                # Gram part
+                for c in sorted(col_rows):
+                    rs = col_rows[c]
+                    bj = [j for j in rs if j0 <= j < j1]
+                    mine = [i for i in rs if i in rows]
+                    use = [(i, j) for j in bj for i in mine if i >= j]
+                    if not use:
+                        continue
+                    need = sorted(set([i for i, _ in use] + [j for _, j in use]))
+                    L.append(ind + "{  // J column %d" % c)
+                    for i in need:
+                        L.append(ind + "    const T a%d = sJ.get(%d);" % (i, self.slots[(i, c)]))
+                    for (i, j) in use:
+                        L.append(ind + "    g_%d_%d += a%d * a%d;" % (i, j, i, j))
+                        nfma[role] += 1
+                    L.append(ind + "}")
+                # left-looking update from factor columns k < j0
+                if rows or has_e:
+                    for k in range(j0):
+                        L.append(ind + "{  // minus column %d of the factor" % k)
+                        L.append(ind + "    const T dk = sL.get(%d);" % (nstrict + k))
+                        for i in sorted(set(rows) | set(blk)):
+                            L.append(ind + "    const T l%d = sL.get(%d);" % (i, Lidx(i, k)))
+                        for j in blk:
+                            L.append(ind + "    const T v%d = l%d * dk;" % (j, j))
+                        for (i, j) in pairs:
+                            L.append(ind + "    g_%d_%d -= l%d * v%d;" % (i, j, i, j))
+                            nfma[role] += 1
+                        if has_e:
+                            for j in blk:
+                                L.append(ind + "    g_e_%d -= yp[%d] * v%d;" % (j, k, j))
+                        L.append(ind + "}")
+                if role == downer:
+                    # factorise the diagonal block in registers and publish it
+                    for j in blk:
+                        L.append(ind + "sL.set(%d, g_%d_%d);" % (nstrict + j, j, j))
+                        L.append(ind + "const T inv_%d = rcp_(g_%d_%d);" % (j, j, j))
+                        for i in range(j + 1, j1):
+                            L.append(ind + "const T l_%d_%d = g_%d_%d * inv_%d;" % (i, j, i, j, j))
+                            L.append(ind + "sL.set(%d, l_%d_%d);" % (Lidx(i, j), i, j))
+                        for j2 in range(j + 1, j1):
+                            for i in range(j2, j1):
+                                L.append(ind + "g_%d_%d -= l_%d_%d * g_%d_%d;" % (i, j2, i, j, j2, j))
+                                nfma[role] += 1
+                L.append(ind + "sync();  // diagonal block %d..%d published" % (j0, j1 - 1))
+                # phase 2: sub-diagonal rows (and the rhs row) against the published block
+                if own or has_e:
+                    L.append(ind + "{")
+                    for j in blk:
+                        L.append(ind + "    const T pd%d = sL.get(%d), pinv%d = rcp_(pd%d);" % (j, nstrict + j, j, j))
+                        for j2 in range(j + 1, j1):
+                            L.append(ind + "    const T pv_%d_%d = sL.get(%d) * pd%d;  // L[%d][%d] d[%d]" % (j2, j, Lidx(j2, j), j, j2, j, j))
+                    for j in blk:
+                        for i in own:
+                            L.append(ind + "    const T l_%d_%d = g_%d_%d * pinv%d;" % (i, j, i, j, j))
+                            L.append(ind + "    sL.set(%d, l_%d_%d);" % (Lidx(i, j), i, j))
+                            for j2 in range(j + 1, j1):
+                                L.append(ind + "    g_%d_%d -= l_%d_%d * pv_%d_%d;" % (i, j2, i, j, j2, j))
+                                nfma[role] += 1
+                        if has_e:
+                            L.append(ind + "    yp[%d] = g_e_%d * pinv%d;" % (j, j, j))
+                            for j2 in range(j + 1, j1):
+                                L.append(ind + "    g_e_%d -= yp[%d] * pv_%d_%d;" % (j2, j, j2, j))
+                    L.append(ind + "}")
+                L.append(ind + "sync();  // block column %d..%d of the factor complete" % (j0, j1 - 1))
+        L = codes[solver]
+        L.append(ind + "// ---- back substitution (solver role) ----")
+        for k in range(M - 1, -1, -1):
+            for i in range(k):
+                L.append(ind + "yp[%d] -= sL.get(%d) * yp[%d];" % (i, Lidx(k, i), k))
+                nfma[solver] += 1
+        L.append(ind + "#pragma unroll")
+        L.append(ind + "for (int i = 0; i < %d; ++i) y[i] = yp[i];" % M)
+        self.psolve_fma = nfma
+        return codes
+
     def gen_dq(self):
         L = []
         ind = "        "
@@ -542,7 +668,7 @@ class Generator:
         rows, nslot = self.rows, len(self.slots)
         solve = self.gen_solve(int(self.spec.get("block_width", 4)))
         used = self.signature()
-        nfact = max(rows * (rows + 1) // 2, rows + self.nv)  # the factor strip also carries e (M) and dq (NV)
+        nfact = max(rows * (rows + 1) // 2, rows + self.nq)  # the factor strip also carries e (M) and the stepped q (NQ)
         out = []
         out.append("// GENERATED by tools/gen_kernel.py -- do not edit.  Specialisation: %s" % display_name)
         out.append("// rows=%d nv=%d nq=%d non-zero Jacobian entries=%d solve FMAs=%d warp roles=%d" %
@@ -556,6 +682,9 @@ class Generator:
                    (self.nq, self.nv, rows, self.rows_p0, self.tsz, nslot, nfact))
         out.append("    // warp roles: the tasks are split over NWARPS warps that evaluate concurrently; role SOLVER solves")
         out.append("    static constexpr int NWARPS = %d, SOLVER = %d;" % (len(groups), solver))
+        out.append("    // PSOLVE: distribute the factorisation over the roles (pays off for large M; for M = 12 the ~7 extra group")
+        out.append("    // barriers cost more than the shorter critical path saves -- measured, DESIGN.md 4.1)")
+        out.append("    static constexpr bool PSOLVE = %s;" % ("true" if self.spec.get("parallel_solve") and len(groups) > 1 else "false"))
         out.append('    static const char *name() { return "%s"; }' % display_name)
         for k, (g, ev) in enumerate(zip(groups, evs)):
             names = ", ".join("%s %s" % (self.tasks[t]["name"], ["Position", "Orientation", "Full"][self.tasks[t]["ktype"]]) for t in g)
@@ -589,6 +718,20 @@ class Generator:
         out.append("    template <typename T, typename S>")
         out.append("    static IKB_HD T solve(const S &sJ, const S &sL, const S &sE, T damping2, T (&y)[M]) {")
         out.extend(solve)
+        out.append("    }")
+        psolve = self.gen_solve_parallel(int(self.spec.get("parallel_block_width", self.spec.get("block_width", 4))), len(groups), solver)
+        out.append("    // The same solve distributed over the warp roles (cyclic row ownership; see gen_solve_parallel): every role")
+        out.append("    // calls psolve(role, ...) with a group barrier `sync`; y is produced in the SOLVER role's registers only.")
+        out.append("    // FMAs per role: %s" % self.psolve_fma)
+        for k, code in enumerate(psolve):
+            out.append("    template <typename T, typename S, typename SYNC>")
+            out.append("    static IKB_HD void psolve_w%d(const S &sJ, const S &sL, const S &sE, T damping2, T (&y)[M], SYNC &sync) {" % k)
+            out.extend(code)
+            out.append("    }")
+        out.append("    template <typename T, typename S, typename SYNC>")
+        out.append("    static IKB_HD void psolve(int role, const S &sJ, const S &sL, const S &sE, T damping2, T (&y)[M], SYNC &sync) {")
+        for k in range(len(groups)):
+            out.append("        if (role == %d) psolve_w%d(sJ, sL, sE, damping2, y, sync);" % (k, k))
         out.append("    }")
         out.append("    // dq = -J^T y from the strip (dls.cpp:52)")
         out.append("    template <typename T, typename S>")
