@@ -7,11 +7,14 @@ Workload (config.workload): Cassie feet+pelvis IK (pelvis Full + LeftFootFront/R
 frame), library-default solver parameters (max_iterations 100, damping 1e-2, step 1.0), batch 65,536 seeded random
 reachable targets PER GPU (weak scaling: rank r solves problem indices [r*B, (r+1)*B)), FP64.
 
-A "step" = one batched ik::dls over one batch = ONE kernel launch.  `value` = converged solves of all ranks /
-max-over-ranks device time with inputs already resident in HBM.  `e2e` = the same metric through the host-buffer
+A "step" = one batched ik::dls over one batch = TWO kernel launches (ikb_dls_solve_batch: the BULK launch suspends the
+few stragglers still unfinished when the ticket queue runs dry, the TAIL launch continues them in the latency
+configuration).  `value` = converged solves of all ranks / max-over-ranks device time with inputs already
+resident in HBM.  `e2e` = the same metric through the host-buffer
 C-ABI call (ikb_dls_solve_batch_host): pinned host inputs copied H2D, solve, results copied D2H, every step.
-`roofline` is the compute roofline of the solve kernel: algorithmic FLOPs (F_iter = 9,360 per
-evaluation, (iterations+1) evaluations per problem) / event-timed kernel duration, against the FP64 (FP32) FMA-pipe
+`roofline` is the compute roofline of the solve (both launches of a step together -- they are one pass of the path):
+algorithmic FLOPs (F_iter = 9,360 per evaluation, (iterations+1) evaluations per problem) / event-timed
+duration of the step, against the FP64 (FP32) FMA-pipe
 peak measured in this run by ikb_measure_fma_peak (MEASURED_PEAKS.json carries no vector-pipe figure; the nominal
 37.2 / 74.4 TFLOP/s is printed beside it).  `cpu_baseline` = the restated reference CPU path (oracle/, "port":
 Pinocchio/Eigen are unavailable so the reference itself cannot be built) on this box's host cores, bounded sample.
@@ -33,6 +36,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 F_ITER_CASSIE = 9360.0  # SURVEY.md 8d, algorithmic FLOPs of one evaluate+solve+step for the Cassie problem
+# dram__bytes_read.sum + dram__bytes_write.sum of the two launches of one FP64 step, from the committed ncu --set full
+# capture profiles/r1_final_full.txt (bulk 31.55 + 0.75 MB, tail 21.40 + 0.00 MB); algorithmic bytes are 43.8 MB.
+NCU_TRAFFIC_BYTES_F64 = 53.7e6
 METRIC = "converged IK solves/sec (Cassie, batch 65,536)"
 UNIT = "solves/s"
 NOMINAL_TFLOPS = {"f64": 37.2, "f32": 74.4}
@@ -327,7 +333,11 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64_fma_pipe" if args.dtype == "f64" else "fp32_fma_pipe",
                          "achieved": achieved_tf, "peak": peak.value, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak.value if peak.value else None, "traffic": None,
+                         "frac": achieved_tf / peak.value if peak.value else None,
+                         "traffic": NCU_TRAFFIC_BYTES_F64 if (args.dtype == "f64" and B == 65536) else None,
+                         "traffic_source": "ncu --set full, profiles/r1_final_full.txt (DRAM bytes of both launches of a step)",
+                         "kernels": "2 launches per step: BULK %s + TAIL (3 warp roles, 1 group/CTA); ncu durations "
+                                    "0.39 + 0.61 ms, profiles/r1_final_full.txt" % pb.kernel_name(args.dtype),
                          "peak_source": "measured in this run (ikb_measure_fma_peak); nominal %.1f"
                                         % NOMINAL_TFLOPS[args.dtype],
                          "frac_of_nominal": achieved_tf / NOMINAL_TFLOPS[args.dtype],
