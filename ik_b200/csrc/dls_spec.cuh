@@ -271,7 +271,8 @@ template <class Spec, typename T> int launch_spec_bulk(const SpecHostConsts &hc,
 // Latency configuration: one 32-problem group per CTA, at most 2 CTAs per SM (full register budget per thread).
 template <class Spec, typename T> int launch_spec_tail(const SpecHostConsts &hc, const SolveArgs<T> &a, long long n, int sm_count, cudaStream_t s) {
     using L = SpecLaunch<Spec, T>;
-    constexpr int kPerSm = (2 * (L::smem_bytes(1) + 1024) <= 228 * 1024) ? 2 : 1;  // shared memory may allow only one
+    // two CTAs per SM only if shared memory allows it and every thread still gets the full 255-register budget
+    constexpr int kPerSm = (2 * (L::smem_bytes(1) + 1024) <= 228 * 1024 && 2 * Spec::NWARPS * 32 * 255 <= 65536) ? 2 : 1;
     long long ctas = (n + 31) / 32;
     if (ctas > (long long)kPerSm * sm_count) ctas = (long long)kPerSm * sm_count;
     return launch_spec_cfg<Spec, T, 1, kPerSm>(hc, a, ctas, s);

@@ -233,3 +233,85 @@ def test_role_distributed_solve_matches_oracle(spec_lib, name, robot, ff, make, 
     q, ok, it, res, _ = _spec_solve(spec_lib, name, "f64p", pb, q0, tg, O.params())
     assert (ok == ok_ref.astype(bool)).all() and (it == it_ref).all()
     assert np.abs(q - q_ref).max() < 1e-8
+
+
+# ---- team-per-problem iteration (dls_team.cuh): 16 host threads = the 16 lanes of a team ----------------------
+@pytest.fixture(scope="module")
+def team_lib():
+    return _build("team_harness")
+
+
+def _team_tree(m):
+    """PR[2][7][9], Pp[2][7][3], FR[2][9], Fp[2][3] of Cassie's two leg chains, from the product's flattened model."""
+    chains = []
+    for fname in ("LeftFootFront", "RightFootFront"):
+        f = m.getFrameId(fname)
+        j, ch = int(m.frame_parents[f]), []
+        while j > 1:
+            ch.append(j)
+            j = int(m.parents[j])
+        chains.append((ch[::-1], m.framePlacements[f]))
+    out = []
+    out += [x for ch, _ in chains for j in ch for x in m.jointPlacements[j][:9]]
+    out += [x for ch, _ in chains for j in ch for x in m.jointPlacements[j][9:]]
+    out += [x for _, fp in chains for x in fp[:9]]
+    out += [x for _, fp in chains for x in fp[9:]]
+    return np.ascontiguousarray(out, dtype=np.float64)
+
+
+def _team_solve(lib, dtype, pb, q0, tg, prm):
+    m = pb.model()
+    fn = getattr(lib, "h_team_cassie_" + dtype)
+    fn.argtypes = [_dp, _dp, _dp, _dp, _dp, _dp, C.c_int, C.c_double, C.c_double, C.c_double, _dp, C.POINTER(C.c_int), _dp, _dp, _dp]
+    tree = _team_tree(m)
+    lo, hi = np.ascontiguousarray(m.lowerPositionLimit), np.ascontiguousarray(m.upperPositionLimit)
+    w = np.ascontiguousarray(np.concatenate([t.weighting() for _, t, _ in pb._tasks]))
+    B = q0.shape[0]
+    q, ok, it, res = np.zeros((B, m.nq)), np.zeros(B, dtype=bool), np.zeros(B, dtype=np.int32), np.zeros(B)
+    e0, J0 = np.zeros((B, 12)), np.zeros((B, 12, 13))
+    for b in range(B):
+        itc, r = C.c_int(0), C.c_double(0)
+        ok[b] = fn(_pd(tree), _pd(lo), _pd(hi), _pd(w), _pd(np.ascontiguousarray(q0[b])), _pd(np.ascontiguousarray(tg[b])),
+                   prm.max_iterations, prm.step_length, prm.damping, prm.tolerance, _pd(q[b]), C.byref(itc), C.byref(r),
+                   _pd(e0[b]), _pd(J0[b]))
+        it[b], res[b] = itc.value, r.value
+    return q, ok, it, res, e0, J0
+
+
+@pytest.mark.parametrize("params", ["defaults", "demo"])
+def test_team_iteration_f64_matches_oracle(team_lib, params):
+    """The 16-lane SPMD decomposition of ik::dls (FK by rows, LDL^T by rows, ...) follows the oracle's trajectory."""
+    pb = W.cassie_feet_pelvis_problem()
+    om = oracle_model("cassie")
+    opb = oracle_problem_like(pb, om)
+    B = 120
+    q0, tg, _ = make_workload(pb, om, B, standing=W.CASSIE_STANDING)
+    prm = O.params() if params == "defaults" else O.params(200, 1e-1, 1e-1)
+    q_ref, ok_ref, it_ref, res_ref = O.dls_batch(opb, q0, tg, prm)
+    q, ok, it, res, e0, J0 = _team_solve(team_lib, "d", pb, q0, tg, prm)
+    # first evaluation: error and the dense task Jacobian (team slots 0-5 = free-flyer columns, 6-12 = the limb's chain)
+    for b in range(0, B, 10):
+        e_ref, J_ref = opb.evaluate(q0[b], tg[b])[:2]
+        assert np.abs(e0[b] - e_ref).max() < 1e-12
+        J = np.zeros((12, 22))
+        J[:, :6] = J0[b][:, :6]
+        J[6:9, [6, 7, 8, 9, 10, 11, 13]] = J0[b][6:9, 6:13]
+        J[9:12, [14, 15, 16, 17, 18, 19, 21]] = J0[b][9:12, 6:13]
+        assert np.abs(J - np.asarray(J_ref).reshape(12, 22)).max() < 1e-11
+    assert (ok == ok_ref.astype(bool)).all()
+    assert (it == it_ref).all()
+    assert np.abs(q - q_ref).max() < 1e-8
+    assert np.abs(res - res_ref).max() < 1e-10
+
+
+def test_team_iteration_f32_is_close(team_lib):
+    pb = W.cassie_feet_pelvis_problem()
+    om = oracle_model("cassie")
+    opb = oracle_problem_like(pb, om)
+    B = 100
+    q0, tg, _ = make_workload(pb, om, B, standing=W.CASSIE_STANDING)
+    q_ref, ok_ref, it_ref, _ = O.dls_batch(opb, q0, tg)
+    q, ok, it, res, _, _ = _team_solve(team_lib, "f", pb, q0, tg, O.params())
+    same = (it == it_ref) & ok & ok_ref.astype(bool)
+    assert same.mean() > 0.9
+    assert (ok == ok_ref.astype(bool)).mean() > 0.98
