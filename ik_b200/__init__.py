@@ -5,9 +5,9 @@ The package is a thin host-side mirror of the reference's task/solver API over l
 """
 from . import _capi  # noqa: F401  (fails loudly if the CUDA library is missing)
 from .api import (AlignAxisTask, AlignAxisType, FrameTask, InverseKinematicsProblem, KinematicType, Model,
-                  PostureTask, dls, dls_batch, dls_batch_host, dls_data, dls_parameters, fk_batch,
+                  PostureTask, SolveQueue, dls, dls_batch, dls_batch_host, dls_data, dls_parameters, fk_batch,
                   inverse_kinematics_visitor, kernel_launch_count)
 
 __all__ = ["AlignAxisTask", "AlignAxisType", "FrameTask", "InverseKinematicsProblem", "KinematicType", "Model",
-           "PostureTask", "dls", "dls_batch", "dls_batch_host", "dls_data", "dls_parameters", "fk_batch",
+           "PostureTask", "SolveQueue", "dls", "dls_batch", "dls_batch_host", "dls_data", "dls_parameters", "fk_batch",
            "inverse_kinematics_visitor", "kernel_launch_count"]

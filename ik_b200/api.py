@@ -402,6 +402,100 @@ def dls_batch(problem, q0, targets, p=None, out=None, stream=None):
     return dict(q=q, success=success, iters=iters, resid=resid)
 
 
+class SolveQueue:
+    """Pipelined stream of batches (ikb_queue_*, include/ikb200.h): up to ``depth`` batches in flight, the straggler
+    launch of one batch beside the bulk launch of the next, host-buffer copies beside both.  Results are those of
+    dls_batch / dls_batch_host, bit for bit.
+
+        queue = ik.SolveQueue(problem, depth=3)
+        tickets = [queue.submit(q0_k, targets_k, out=out_k) for ...]     # device tensors (torch, SoA)
+        queue.wait(tickets[0]); ... ; queue.drain()
+    """
+
+    def __init__(self, problem, depth=3, device=0):
+        problem.finalize(problem._device if problem._device is not None else device)
+        self._problem = problem
+        self._h = C.c_void_p()
+        capi.check(capi.lib.ikb_queue_create(problem._h, depth, C.byref(self._h)), "ikb_queue_create")
+        self._keep = {}  # ticket -> buffers that must outlive the batch
+
+    def __del__(self):
+        if getattr(self, "_h", None) and capi is not None and getattr(capi, "lib", None) is not None:
+            capi.lib.ikb_queue_free(self._h)
+            self._h = None
+
+    def submit(self, q0, targets, p=None, out=None, in_stream=None):
+        """Device tensors q0 [nq, B], targets [tsz, B]; inputs must be ready in ``in_stream`` order (default: torch's
+        current stream).  Returns (ticket, dict(q, success, iters, resid)); the outputs are valid after wait(ticket)."""
+        import torch
+
+        problem = self._problem
+        p = p or dls_parameters()
+        nq, tsz = problem.model().nq, problem.target_size
+        dtype = "f64" if q0.dtype == torch.float64 else "f32"
+        B = q0.shape[1]
+        assert q0.is_cuda and targets.is_cuda and q0.dtype == targets.dtype
+        assert q0.shape == (nq, B) and targets.shape == (tsz, B) and q0.is_contiguous() and targets.is_contiguous()
+        out = out or {}
+        q = out.get("q") if out.get("q") is not None else torch.empty((nq, B), dtype=q0.dtype, device=q0.device)
+        success = out.get("success") if out.get("success") is not None else torch.empty(B, dtype=torch.uint8, device=q0.device)
+        iters = out.get("iters") if out.get("iters") is not None else torch.empty(B, dtype=torch.int32, device=q0.device)
+        resid = out.get("resid") if out.get("resid") is not None else torch.empty(B, dtype=q0.dtype, device=q0.device)
+        io = capi.BatchIO(q0.data_ptr(), B, 1, targets.data_ptr(), B, 1, q.data_ptr(), B, 1, success.data_ptr(),
+                          iters.data_ptr(), resid.data_ptr())
+        s = in_stream if in_stream is not None else torch.cuda.current_stream(q0.device).cuda_stream
+        prm = p.c()
+        t = capi.check_index(capi.lib.ikb_queue_submit(self._h, _DT[dtype][0], C.byref(prm), B, C.byref(io), C.c_void_p(s)),
+                             "ikb_queue_submit")
+        res = dict(q=q, success=success, iters=iters, resid=resid)
+        self._keep[t] = (q0, targets, res)
+        return t, res
+
+    def submit_host(self, q0, targets, p=None, dtype="f64", layout="soa", out=None):
+        """Host arrays (numpy; pinned -- ikb_host_alloc -- for the copies to overlap), layouts as dls_batch_host."""
+        problem = self._problem
+        p = p or dls_parameters()
+        code, npdt = _DT[dtype]
+        nq, tsz = problem.model().nq, problem.target_size
+        assert q0.dtype == npdt and targets.dtype == npdt and q0.flags.c_contiguous and targets.flags.c_contiguous
+        if layout == "soa":
+            B = q0.shape[1]
+            assert q0.shape == (nq, B) and targets.shape == (tsz, B)
+            strides = lambda k: (B, 1)
+            qshape = (nq, B)
+        else:
+            B = q0.shape[0]
+            assert q0.shape == (B, nq) and targets.shape == (B, tsz)
+            strides = lambda k: (1, k)
+            qshape = (B, nq)
+        out = out or {}
+        q = out.get("q") if out.get("q") is not None else np.empty(qshape, dtype=npdt)
+        success = out.get("success") if out.get("success") is not None else np.empty(B, dtype=np.uint8)
+        iters = out.get("iters") if out.get("iters") is not None else np.empty(B, dtype=np.int32)
+        resid = out.get("resid") if out.get("resid") is not None else np.empty(B, dtype=npdt)
+        io = capi.BatchIO(q0.ctypes.data, *strides(nq), targets.ctypes.data, *strides(tsz), q.ctypes.data, *strides(nq),
+                          success.ctypes.data, iters.ctypes.data, resid.ctypes.data)
+        prm = p.c()
+        t = capi.check_index(capi.lib.ikb_queue_submit_host(self._h, code, C.byref(prm), B, C.byref(io)), "ikb_queue_submit_host")
+        res = dict(q=q, success=success, iters=iters, resid=resid)
+        self._keep[t] = (q0, targets, res)
+        return t, res
+
+    def wait(self, ticket):
+        capi.check(capi.lib.ikb_queue_wait(self._h, ticket), "ikb_queue_wait")
+        return self._keep.pop(ticket, (None, None, None))[2]
+
+    def wait_on_stream(self, ticket, stream=None):
+        import torch
+
+        s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        capi.check(capi.lib.ikb_queue_wait_on_stream(self._h, ticket, C.c_void_p(s)), "ikb_queue_wait_on_stream")
+
+    def drain(self):
+        capi.check(capi.lib.ikb_queue_drain(self._h), "ikb_queue_drain")
+        self._keep.clear()
+
+
 def fk_batch(problem, q, frames, out=None, stream=None):
     """Batched framesForwardKinematics (data.cpp:28-29) on device tensors: q [nq, B] -> [len(frames)*12, B]."""
     import torch

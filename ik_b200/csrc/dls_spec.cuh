@@ -48,8 +48,10 @@ template <class Spec, typename T> struct SpecLaunch {
     static constexpr int smem_bytes(int groups) { return groups * 32 * kBytesPerProblem; }
 };
 
-template <class Spec, typename T, int GROUPS, int MINB>
-__global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
+// LBT = the thread count the register allocation is bounded for (>= the block size): a SHARED-residency variant keeps
+// the register budget of a bigger CTA so that a second kernel's CTAs fit on the SM beside it (pipelined queue).
+template <class Spec, typename T, int GROUPS, int MINB, int LBT = GROUPS * Spec::NWARPS * 32>
+__global__ void __launch_bounds__(LBT, MINB)
     dls_spec_kernel(const __grid_constant__ SpecConsts<T, Spec::NQ, Spec::M> c, const __grid_constant__ SolveArgs<T> a) {
     constexpr int NQ = Spec::NQ, NV = Spec::NV, M = Spec::M, NW = Spec::NWARPS, SLOTS = GROUPS * 32;
     static_assert(Spec::NFACT >= M + NQ, "factor strip must also hold e and the stepped q");
@@ -239,12 +241,12 @@ template <class Spec> bool spec_matches(const HostProblem &hp) {
 // GROUPS = 32-problem groups per CTA, MINB = CTAs per SM the register allocation must allow.  The throughput
 // configuration is one big CTA per SM (GROUPS = SpecLaunch::GROUPS); the latency configuration is GROUPS = 1, so that
 // few problems spread over all SMs and every group has its schedulers to itself.
-template <class Spec, typename T, int GROUPS, int MINB>
+template <class Spec, typename T, int GROUPS, int MINB, int LBT = GROUPS * Spec::NWARPS * 32>
 int launch_spec_cfg(const SpecHostConsts &hc, const SolveArgs<T> &a, long long ctas, cudaStream_t s) {
     using L = SpecLaunch<Spec, T>;
     static_assert(L::kFits && GROUPS <= L::GROUPS, "per-problem strips do not fit in shared memory for this scalar type");
     constexpr int kSmem = L::smem_bytes(GROUPS);
-    auto fn = dls_spec_kernel<Spec, T, GROUPS, MINB>;
+    auto fn = dls_spec_kernel<Spec, T, GROUPS, MINB, LBT>;
     static bool attr_set = false;  // per instantiation
     if (!attr_set) {
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess) return 1;
@@ -267,6 +269,13 @@ template <class Spec, typename T> int launch_spec_bulk(const SpecHostConsts &hc,
     long long ctas = (n + L::GROUPS * 32 - 1) / (L::GROUPS * 32);
     if (ctas > sm_count) ctas = sm_count;
     return launch_spec_cfg<Spec, T, L::GROUPS, 1>(hc, a, ctas, s);
+}
+// Latency configuration with G groups per CTA (G = 2: half as many SMs are tied up, each trip a little slower -- the
+// better trade when the TAIL launch shares the GPU with the BULK launch of the next batch).
+template <class Spec, typename T, int G> int launch_spec_tail_g(const SpecHostConsts &hc, const SolveArgs<T> &a, long long n, int sm_count, cudaStream_t s) {
+    long long ctas = (n + 32 * G - 1) / (32 * G);
+    if (ctas > sm_count) ctas = sm_count;
+    return launch_spec_cfg<Spec, T, G, 1>(hc, a, ctas, s);
 }
 // Latency configuration: one 32-problem group per CTA, at most 2 CTAs per SM (full register budget per thread).
 template <class Spec, typename T> int launch_spec_tail(const SpecHostConsts &hc, const SolveArgs<T> &a, long long n, int sm_count, cudaStream_t s) {

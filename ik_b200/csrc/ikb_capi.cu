@@ -67,8 +67,9 @@ struct ikb_problem {
     const SpecializedKernel *spec = nullptr;
     std::vector<double> weight_stacked;  // Task::weighting() rows in stacked order (constants of the specialised kernels)
     std::string kernel_name[2];
-    // host-path staging (ikb_dls_solve_batch_host)
-    cudaStream_t stream = nullptr;
+    // host-path staging (ikb_dls_solve_batch_host): main stream + the pipelined path's copy-in and second compute stream
+    cudaStream_t stream = nullptr, stream_in = nullptr, stream_aux = nullptr;
+    cudaEvent_t ev_in[8] = {}, ev_aux = nullptr, ev_main = nullptr;
     Staging<double> st64;
     Staging<float> st32;
     unsigned char *st_success = nullptr;
@@ -190,8 +191,39 @@ template <typename T> DevProblem<T> *dev_blob(const ikb_problem *p);
 template <> DevProblem<double> *dev_blob<double>(const ikb_problem *p) { return p->d64; }
 template <> DevProblem<float> *dev_blob<float>(const ikb_problem *p) { return p->d32; }
 
+// Pipelined host path (solve_host): the inputs of batch slice [begin[c], begin[c + 1]) are on the device once `ready[c]`
+// has happened.  The BULK launch is issued per slice, alternating between the caller's stream and `aux`, so that it
+// overlaps the host-to-device copy of the next slices; the TAIL launch continues the stragglers of all slices at once.
+struct ChunkPlan {
+    int n = 0;
+    long long begin[9] = {};
+    cudaEvent_t ready[8] = {};
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_aux = nullptr, ev_main = nullptr;
+};
+__global__ void set_ticket_kernel(unsigned long long *t, unsigned long long v) { *t = v; }
+
+// Is this solve going to take the two-launch (BULK + TAIL) path?  (the only one that can be pipelined by slices)
+bool two_phase(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, int *cap_out = nullptr) {
+    const char *cap_env = std::getenv("IKB_BULK_CAP");
+    const int cap = cap_env ? std::atoi(cap_env) : 16;
+    if (cap_out) *cap_out = cap;
+    return p->spec && B > 2LL * 32 * p->sm_count && cap > 0 && prm->max_iterations > cap;
+}
+
+// Pipelined queue (ikb_queue_*): the TAIL launch goes to its own stream, so that it runs beside the BULK launch of the
+// next batch (the stragglers' 100-step latency chain then costs SM space, not wall time).
+struct SplitStreams {
+    cudaStream_t tail;
+    cudaEvent_t ev_bulk;
+    cudaEvent_t ev_go;      // recorded on `tail` right before the TAIL launch (the next BULK launch is held until then)
+    bool *went;             // set when ev_go was recorded
+};
+__global__ void marker_kernel() {}
+
 template <typename T>
-int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io, cudaStream_t s) {
+int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io, cudaStream_t s,
+                 const ChunkPlan *plan = nullptr, const SplitStreams *split = nullptr) {
     SolveArgs<T> a;
     a.q0 = (const T *)io->q0; a.q0_es = io->q0_elem_stride; a.q0_bs = io->q0_batch_stride;
     a.targets = (const T *)io->targets; a.tg_es = io->targets_elem_stride; a.tg_bs = io->targets_batch_stride;
@@ -229,9 +261,10 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
         // and a TAIL launch continues all of them at once, each group of 32 with an SM's schedulers to itself, instead
         // of letting them trickle out of the bulk kernel one 100-step straggler at a time.
         const long long wave = 2LL * 32 * p->sm_count;
-        const char *cap_env = std::getenv("IKB_BULK_CAP");
-        const int cap = cap_env ? std::atoi(cap_env) : 16;
+        int cap;
+        const bool two = two_phase(p, prm, B, &cap);
         int rc;
+        if (plan && !two) return fail(IKB_ERR_INVALID_ARG, "internal: slice plan on a single-launch solve");
         if (B <= wave) {
             rc = launch_specialized<T>(*p->spec, hc, a, SPEC_TAIL, B, p->sm_count, s);
             if (rc == IKB_OK) g_launches.fetch_add(1);
@@ -264,17 +297,57 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
             a.list = sc->list;
             a.list_count = a.ticket + 2;
             a.iters_ws = io->iters ? io->iters : sc->iters;
-            rc = launch_specialized<T>(*p->spec, hc, a, SPEC_BULK, B, p->sm_count, s);
+            if (!plan) {
+                rc = launch_specialized<T>(*p->spec, hc, a, SPEC_BULK, B, p->sm_count, s);
+                if (rc == IKB_OK) g_launches.fetch_add(1);
+            } else {
+                // one BULK launch per slice: its tickets run from begin[c] to begin[c + 1] (own counter, words 3.. of the slot)
+                rc = IKB_OK;
+                IKB_CUDA(cudaEventRecord(plan->ev_main, s));  // counters zeroed
+                IKB_CUDA(cudaStreamWaitEvent(plan->aux, plan->ev_main, 0));
+                for (int c = 0; c < plan->n && rc == IKB_OK; ++c) {
+                    cudaStream_t cs = (c & 1) ? plan->aux : s;
+                    IKB_CUDA(cudaStreamWaitEvent(cs, plan->ready[c], 0));
+                    SolveArgs<T> ac = a;
+                    ac.ticket = a.ticket + 3 + c;
+                    ac.B = plan->begin[c + 1];
+                    set_ticket_kernel<<<1, 1, 0, cs>>>(ac.ticket, (unsigned long long)plan->begin[c]);
+                    rc = launch_specialized<T>(*p->spec, hc, ac, SPEC_BULK, plan->begin[c + 1] - plan->begin[c], p->sm_count, cs);
+                    if (rc == IKB_OK) g_launches.fetch_add(2);
+                }
+                IKB_CUDA(cudaEventRecord(plan->ev_aux, plan->aux));
+                IKB_CUDA(cudaStreamWaitEvent(s, plan->ev_aux, 0));
+            }
+            cudaStream_t ts = s;
+            if (split) {
+                ts = split->tail;
+                IKB_CUDA(cudaEventRecord(split->ev_bulk, s));
+                IKB_CUDA(cudaStreamWaitEvent(ts, split->ev_bulk, 0));
+                // ev_go completes when the tail stream has reached this point, i.e. when the BULK launch is over: the next
+                // BULK launch waits for it and so becomes runnable together with (not before) this TAIL launch, which has
+                // the higher stream priority and gets its SMs first.
+                marker_kernel<<<1, 1, 0, ts>>>();
+                IKB_CUDA(cudaEventRecord(split->ev_go, ts));
+                *split->went = true;
+            }
             if (rc == IKB_OK) {
-                g_launches.fetch_add(1);
                 SolveArgs<T> t = a;
                 t.resume = 1;
                 t.it_cap = INT_MAX;
                 t.ticket = a.ticket + 1;
-                rc = launch_specialized<T>(*p->spec, hc, t, SPEC_TAIL, B, p->sm_count, s);
+                // Queue mode: the TAIL launch shares the GPU with the next BULK launch, whose persistent CTAs need whole SMs.
+                // Its grid is sized for the expected number of stragglers (slots refill from the list, so any number
+                // works) instead of spreading them thinly over every SM.
+                long long n_tail = B;
+                if (split) {
+                    const char *fe = std::getenv("IKB_TAIL_DIV");
+                    const int div = fe ? std::max(1, std::atoi(fe)) : 14;
+                    n_tail = std::max<long long>(B / div, 1024);
+                }
+                rc = launch_specialized<T>(*p->spec, hc, t, split ? SPEC_TAIL_SHARED : SPEC_TAIL, n_tail, p->sm_count, ts);
                 if (rc == IKB_OK) g_launches.fetch_add(1);
             }
-            IKB_CUDA(cudaEventRecord(sc->ev, s));
+            IKB_CUDA(cudaEventRecord(sc->ev, ts));
         }
         if (rc != IKB_OK) return cuda_fail(cudaGetLastError(), "specialised kernel launch");
         return IKB_OK;
@@ -312,6 +385,58 @@ template <typename T> Staging<T> &staging(ikb_problem *p);
 template <> Staging<double> &staging<double>(ikb_problem *p) { return p->st64; }
 template <> Staging<float> &staging<float>(ikb_problem *p) { return p->st32; }
 
+// A strided [n_elem][B] view of a host array (include/ikb200.h: element k of problem b at base[k * es + b * bs]).
+struct View {
+    const void *base;
+    long long es, bs;
+    int n_elem;
+    // can batch slices be copied on their own?  SoA rows (bs == 1), dense AoS (es == 1, bs == n_elem), broadcast (bs == 0)
+    bool sliceable(long long B) const {
+        if (n_elem <= 0 || bs == 0) return true;
+        if (bs == 1) return es >= B;
+        return es == 1 && bs == n_elem;
+    }
+};
+// Host-to-device copy of batch slice [b0, b1) of `v` into the staging buffer `dst` (same strides as the view).
+template <typename T> int copy_in_slice(T *dst, const View &v, long long B, long long b0, long long b1, bool first, cudaStream_t s) {
+    if (v.n_elem <= 0) return IKB_OK;
+    const T *src = (const T *)v.base;
+    if (v.bs == 0) {
+        if (first) IKB_CUDA(cudaMemcpyAsync(dst, src, view_extent(v.n_elem, v.es, 0, 1) * sizeof(T), cudaMemcpyHostToDevice, s));
+    } else if (v.bs == 1) {
+        IKB_CUDA(cudaMemcpy2DAsync(dst + b0, (size_t)v.es * sizeof(T), src + b0, (size_t)v.es * sizeof(T), (size_t)(b1 - b0) * sizeof(T),
+                                   (size_t)v.n_elem, cudaMemcpyHostToDevice, s));
+    } else {
+        IKB_CUDA(cudaMemcpyAsync(dst + b0 * v.bs, src + b0 * v.bs, (size_t)(b1 - b0) * v.bs * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    return IKB_OK;
+}
+
+// IKB_HOST_TRACE=1: print the device-side timeline of one host-path solve (debug aid for the e2e numbers in DESIGN.md)
+struct HostTrace {
+    bool on = false;
+    std::vector<std::pair<const char *, cudaEvent_t>> ev;
+    HostTrace() { const char *e = std::getenv("IKB_HOST_TRACE"); on = e && e[0] == '1'; }
+    void mark(const char *name, cudaStream_t s) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        ev.emplace_back(name, e);
+    }
+    void dump() {
+        if (!on || ev.empty()) return;
+        for (auto &x : ev) {
+            float ms = 0;
+            cudaEventSynchronize(x.second);
+            cudaEventElapsedTime(&ms, ev[0].second, x.second);
+            std::fprintf(stderr, "[ikb host trace] %-14s %8.3f ms\n", x.first, ms);
+            }
+        for (auto &x : ev) cudaEventDestroy(x.second);
+        ev.clear();
+    }
+};
+
 template <typename T>
 int solve_host(ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io) {
     const int nq = p->hp.model.nq, tsz = p->hp.target_size();
@@ -332,8 +457,8 @@ int solve_host(ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_b
         p->st_flag_cap = (size_t)B;
     }
     cudaStream_t s = p->stream;
-    IKB_CUDA(cudaMemcpyAsync(st.q0, io->q0, n_q0 * sizeof(T), cudaMemcpyHostToDevice, s));
-    if (n_tg) IKB_CUDA(cudaMemcpyAsync(st.targets, io->targets, n_tg * sizeof(T), cudaMemcpyHostToDevice, s));
+    HostTrace tr;
+    tr.mark("start", s);
     ikb_batch_io dio = *io;
     dio.q0 = st.q0;
     dio.targets = st.targets;
@@ -341,12 +466,136 @@ int solve_host(ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_b
     dio.success = p->st_success;
     dio.iters = p->st_iters;
     dio.resid = st.resid;
-    if ((rc = launch_solve<T>(p, prm, B, &dio, s))) return rc;
+    // A two-launch solve whose input views can be cut into batch slices is pipelined: slice c + 1 crosses PCIe while the
+    // BULK launch of slice c runs (the staging buffers keep the caller's strides, so a slice is a 2-D or a dense copy).
+    const View vq{io->q0, (long long)io->q0_elem_stride, (long long)io->q0_batch_stride, nq};
+    const View vt{io->targets, (long long)io->targets_elem_stride, (long long)io->targets_batch_stride, tsz};
+    const char *slices_env = std::getenv("IKB_HOST_SLICES");
+    const int nslice = (int)std::min<int64_t>(slices_env ? std::max(1, std::min(8, std::atoi(slices_env))) : 4, B / 8192);
+    const char *pipe_env = std::getenv("IKB_HOST_PIPELINE");
+    if (two_phase(p, prm, B) && nslice >= 2 && vq.sliceable(B) && vt.sliceable(B) && !(pipe_env && pipe_env[0] == '0')) {
+        ChunkPlan plan;
+        plan.n = nslice;
+        plan.aux = p->stream_aux;
+        plan.ev_aux = p->ev_aux;
+        plan.ev_main = p->ev_main;
+        for (int c = 0; c <= nslice; ++c) plan.begin[c] = c == nslice ? B : (B / nslice * c) / 32 * 32;
+        for (int c = 0; c < nslice; ++c) {
+            if ((rc = copy_in_slice<T>(st.q0, vq, B, plan.begin[c], plan.begin[c + 1], c == 0, p->stream_in)) ||
+                (rc = copy_in_slice<T>(st.targets, vt, B, plan.begin[c], plan.begin[c + 1], c == 0, p->stream_in)))
+                return rc;
+            plan.ready[c] = p->ev_in[c];
+            IKB_CUDA(cudaEventRecord(plan.ready[c], p->stream_in));
+            tr.mark("h2d slice", p->stream_in);
+        }
+        if ((rc = launch_solve<T>(p, prm, B, &dio, s, &plan))) return rc;
+    } else {
+        IKB_CUDA(cudaMemcpyAsync(st.q0, io->q0, n_q0 * sizeof(T), cudaMemcpyHostToDevice, s));
+        if (n_tg) IKB_CUDA(cudaMemcpyAsync(st.targets, io->targets, n_tg * sizeof(T), cudaMemcpyHostToDevice, s));
+        tr.mark("h2d", s);
+        if ((rc = launch_solve<T>(p, prm, B, &dio, s))) return rc;
+    }
+    tr.mark("solve", s);
     IKB_CUDA(cudaMemcpyAsync(io->q, st.q, n_q * sizeof(T), cudaMemcpyDeviceToHost, s));
     if (io->success) IKB_CUDA(cudaMemcpyAsync(io->success, p->st_success, (size_t)B, cudaMemcpyDeviceToHost, s));
     if (io->iters) IKB_CUDA(cudaMemcpyAsync(io->iters, p->st_iters, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, s));
     if (io->resid) IKB_CUDA(cudaMemcpyAsync(io->resid, st.resid, (size_t)B * sizeof(T), cudaMemcpyDeviceToHost, s));
+    tr.mark("d2h", s);
     IKB_CUDA(cudaStreamSynchronize(s));
+    tr.dump();
+    return IKB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pipelined queue: batches in flight on four streams (copy-in, BULK, TAIL, copy-out)
+// ---------------------------------------------------------------------------------------------------
+}  // namespace
+struct ikb_queue {
+    struct Slot {
+        cudaEvent_t ev_in = nullptr, ev_bulk = nullptr, ev_mid = nullptr, ev_done = nullptr, ev_go = nullptr;
+        bool busy = false;
+        int64_t ticket = -1;  // the batch occupying the slot
+        // host-mode staging (per scalar type, grown on demand)
+        Staging<double> st64;
+        Staging<float> st32;
+        unsigned char *success = nullptr;
+        int *iters = nullptr;
+        size_t flag_cap = 0;
+    };
+    ikb_problem *p = nullptr;
+    int depth = 0;
+    std::vector<Slot> slots;
+    cudaStream_t s_in = nullptr, s_bulk = nullptr, s_tail = nullptr, s_out = nullptr;
+    cudaEvent_t ev_user = nullptr;
+    cudaEvent_t ev_go_last = nullptr;  // of the last two-launch batch submitted (not owned)
+    int64_t next = 0;
+    std::vector<std::pair<std::string, cudaEvent_t>> trace;  // IKB_QUEUE_TRACE=1: device timeline, printed by drain
+    bool tracing = false;
+    void mark(const std::string &name, cudaStream_t s) {
+        if (!tracing) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        trace.emplace_back(name, e);
+    }
+};
+namespace {
+template <typename T> Staging<T> &slot_staging(ikb_queue::Slot &sl);
+template <> Staging<double> &slot_staging<double>(ikb_queue::Slot &sl) { return sl.st64; }
+template <> Staging<float> &slot_staging<float>(ikb_queue::Slot &sl) { return sl.st32; }
+
+// Enqueue the solve of one batch whose device inputs are ready in s_bulk order; the slot's ev_done fires when the outputs
+// are complete on s_tail.
+template <typename T> int queue_solve(ikb_queue *q, ikb_queue::Slot &sl, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *dio) {
+    bool went = false;
+    const SplitStreams split{q->s_tail, sl.ev_bulk, sl.ev_go, &went};
+    if (q->ev_go_last) IKB_CUDA(cudaStreamWaitEvent(q->s_bulk, q->ev_go_last, 0));
+    q->mark("bulk begin " + std::to_string(q->next), q->s_bulk);
+    int rc = launch_solve<T>(q->p, prm, B, dio, q->s_bulk, nullptr, &split);
+    if (rc) return rc;
+    if (went) q->ev_go_last = sl.ev_go;
+    q->mark("bulk end   " + std::to_string(q->next), q->s_bulk);
+    q->mark("tail end   " + std::to_string(q->next), q->s_tail);
+    // single-launch solves ran on s_bulk only: s_tail picks that up, so that "done" always means "everything"
+    IKB_CUDA(cudaEventRecord(sl.ev_mid, q->s_bulk));
+    IKB_CUDA(cudaStreamWaitEvent(q->s_tail, sl.ev_mid, 0));
+    return IKB_OK;
+}
+
+template <typename T> int queue_submit_host(ikb_queue *q, ikb_queue::Slot &sl, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io) {
+    ikb_problem *p = q->p;
+    const int nq = p->hp.model.nq, tsz = p->hp.target_size();
+    Staging<T> &st = slot_staging<T>(sl);
+    const size_t n_q0 = view_extent(nq, io->q0_elem_stride, io->q0_batch_stride, B);
+    const size_t n_tg = tsz > 0 ? view_extent(tsz, io->targets_elem_stride, io->targets_batch_stride, B) : 0;
+    const size_t n_q = view_extent(nq, io->q_elem_stride, io->q_batch_stride, B);
+    int rc;
+    if ((rc = ensure(st.q0, st.q0_cap, n_q0)) || (rc = ensure(st.targets, st.tg_cap, std::max<size_t>(n_tg, 1))) ||
+        (rc = ensure(st.q, st.q_cap, n_q)) || (rc = ensure(st.resid, st.b_cap, (size_t)B)))
+        return rc;
+    if ((size_t)B > sl.flag_cap) {
+        if (sl.success) cudaFree(sl.success);
+        if (sl.iters) cudaFree(sl.iters);
+        sl.success = nullptr; sl.iters = nullptr; sl.flag_cap = 0;
+        IKB_CUDA(cudaMalloc(&sl.success, (size_t)B));
+        IKB_CUDA(cudaMalloc(&sl.iters, (size_t)B * sizeof(int)));
+        sl.flag_cap = (size_t)B;
+    }
+    IKB_CUDA(cudaMemcpyAsync(st.q0, io->q0, n_q0 * sizeof(T), cudaMemcpyHostToDevice, q->s_in));
+    if (n_tg) IKB_CUDA(cudaMemcpyAsync(st.targets, io->targets, n_tg * sizeof(T), cudaMemcpyHostToDevice, q->s_in));
+    IKB_CUDA(cudaEventRecord(sl.ev_in, q->s_in));
+    IKB_CUDA(cudaStreamWaitEvent(q->s_bulk, sl.ev_in, 0));
+    ikb_batch_io dio = *io;
+    dio.q0 = st.q0; dio.targets = st.targets; dio.q = st.q;
+    dio.success = sl.success; dio.iters = sl.iters; dio.resid = st.resid;
+    if ((rc = queue_solve<T>(q, sl, prm, B, &dio))) return rc;
+    IKB_CUDA(cudaEventRecord(sl.ev_mid, q->s_tail));
+    IKB_CUDA(cudaStreamWaitEvent(q->s_out, sl.ev_mid, 0));
+    IKB_CUDA(cudaMemcpyAsync(io->q, st.q, n_q * sizeof(T), cudaMemcpyDeviceToHost, q->s_out));
+    if (io->success) IKB_CUDA(cudaMemcpyAsync(io->success, sl.success, (size_t)B, cudaMemcpyDeviceToHost, q->s_out));
+    if (io->iters) IKB_CUDA(cudaMemcpyAsync(io->iters, sl.iters, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, q->s_out));
+    if (io->resid) IKB_CUDA(cudaMemcpyAsync(io->resid, st.resid, (size_t)B * sizeof(T), cudaMemcpyDeviceToHost, q->s_out));
+    IKB_CUDA(cudaEventRecord(sl.ev_done, q->s_out));
     return IKB_OK;
 }
 
@@ -595,6 +844,11 @@ void ikb_problem_free(ikb_problem *p) {
             if (sc.ev) cudaEventDestroy(sc.ev);
         }
         if (p->stream) cudaStreamDestroy(p->stream);
+        if (p->stream_in) cudaStreamDestroy(p->stream_in);
+        if (p->stream_aux) cudaStreamDestroy(p->stream_aux);
+        for (auto e : p->ev_in) if (e) cudaEventDestroy(e);
+        if (p->ev_aux) cudaEventDestroy(p->ev_aux);
+        if (p->ev_main) cudaEventDestroy(p->ev_main);
     }
     delete p;
 }
@@ -734,6 +988,11 @@ int ikb_problem_finalize(ikb_problem *p, int device) {
     IKB_CUDA(cudaMalloc(&p->d_tickets, kTicketSlots * 16 * sizeof(unsigned long long)));
     IKB_CUDA(cudaMemset(p->d_tickets, 0, kTicketSlots * 16 * sizeof(unsigned long long)));
     IKB_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    IKB_CUDA(cudaStreamCreateWithFlags(&p->stream_in, cudaStreamNonBlocking));
+    IKB_CUDA(cudaStreamCreateWithFlags(&p->stream_aux, cudaStreamNonBlocking));
+    for (auto &e : p->ev_in) IKB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    IKB_CUDA(cudaEventCreateWithFlags(&p->ev_aux, cudaEventDisableTiming));
+    IKB_CUDA(cudaEventCreateWithFlags(&p->ev_main, cudaEventDisableTiming));
 
     p->size_class = cls;
     p->device = device;
@@ -786,6 +1045,137 @@ int ikb_dls_solve_batch_host(ikb_problem *p, int dtype, const ikb_dls_params *pr
     if (B == 0) return IKB_OK;
     DeviceGuard g(p->device);
     return dtype == IKB_F64 ? solve_host<double>(p, prm, B, io) : solve_host<float>(p, prm, B, io);
+}
+
+/* ---- pipelined queue ---- */
+int ikb_queue_create(ikb_problem *p, int depth, ikb_queue **out) {
+    if (!p || !out) return fail(IKB_ERR_INVALID_ARG, "null argument");
+    if (!p->finalized) return fail(IKB_ERR_NOT_FINALIZED, "call ikb_problem_finalize first");
+    if (depth < 1 || depth > kScratchSlots) return fail(IKB_ERR_INVALID_ARG, "queue depth must be between 1 and 8");
+    DeviceGuard g(p->device);
+    ikb_queue *q = new ikb_queue;
+    q->p = p;
+    q->depth = depth;
+    q->slots.resize(depth);
+    *out = q;  // the caller frees it also when creation fails half-way
+    {
+        const char *e = std::getenv("IKB_QUEUE_TRACE");
+        q->tracing = e && e[0] == '1';
+    }
+    // The TAIL stream outranks the BULK stream: when a bulk launch ends, the stragglers' CTAs (few, latency-bound) are
+    // placed first and the next bulk launch (persistent CTAs that take whole SMs) fills what is left -- the other way
+    // round the stragglers would wait for a free SM until the queue runs empty.
+    int prio_lo = 0, prio_hi = 0;
+    IKB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    IKB_CUDA(cudaStreamCreateWithFlags(&q->s_in, cudaStreamNonBlocking));
+    IKB_CUDA(cudaStreamCreateWithFlags(&q->s_out, cudaStreamNonBlocking));
+    IKB_CUDA(cudaStreamCreateWithPriority(&q->s_bulk, cudaStreamNonBlocking, prio_lo));
+    IKB_CUDA(cudaStreamCreateWithPriority(&q->s_tail, cudaStreamNonBlocking, prio_hi));
+    IKB_CUDA(cudaEventCreateWithFlags(&q->ev_user, cudaEventDisableTiming));
+    for (auto &sl : q->slots)
+        for (cudaEvent_t *e : {&sl.ev_in, &sl.ev_bulk, &sl.ev_mid, &sl.ev_done, &sl.ev_go}) IKB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    return IKB_OK;
+}
+
+void ikb_queue_free(ikb_queue *q) {
+    if (!q) return;
+    DeviceGuard g(q->p->device);
+    for (cudaStream_t s : {q->s_in, q->s_bulk, q->s_tail, q->s_out})
+        if (s) {
+            cudaStreamSynchronize(s);
+            cudaStreamDestroy(s);
+        }
+    if (q->ev_user) cudaEventDestroy(q->ev_user);
+    for (auto &sl : q->slots) {
+        for (cudaEvent_t e : {sl.ev_in, sl.ev_bulk, sl.ev_mid, sl.ev_done, sl.ev_go})
+            if (e) cudaEventDestroy(e);
+        cudaFree(sl.st64.q0); cudaFree(sl.st64.targets); cudaFree(sl.st64.q); cudaFree(sl.st64.resid);
+        cudaFree(sl.st32.q0); cudaFree(sl.st32.targets); cudaFree(sl.st32.q); cudaFree(sl.st32.resid);
+        cudaFree(sl.success); cudaFree(sl.iters);
+    }
+    delete q;
+}
+
+static int queue_slot(ikb_queue *q, ikb_queue::Slot **sl) {
+    *sl = &q->slots[q->next % q->depth];
+    if ((*sl)->busy) {  // back-pressure: the slot's previous batch must have left the pipeline
+        IKB_CUDA(cudaEventSynchronize((*sl)->ev_done));
+        (*sl)->busy = false;
+    }
+    return IKB_OK;
+}
+
+int64_t ikb_queue_submit(ikb_queue *q, int dtype, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io, void *in_stream) {
+    if (!q) return -fail(IKB_ERR_INVALID_ARG, "null queue");
+    int rc = check_solve_args(q->p, dtype, prm, B, io);
+    if (rc) return -rc;
+    DeviceGuard g(q->p->device);
+    ikb_queue::Slot *sl;
+    if ((rc = queue_slot(q, &sl))) return -rc;
+    // the inputs are ready in `in_stream` order (NULL = the legacy default stream) at this point
+    if (cudaEventRecord(q->ev_user, (cudaStream_t)in_stream) != cudaSuccess || cudaStreamWaitEvent(q->s_bulk, q->ev_user, 0) != cudaSuccess)
+        return -cuda_fail(cudaGetLastError(), "queue input dependency");
+    if (B > 0) {
+        rc = dtype == IKB_F64 ? queue_solve<double>(q, *sl, prm, B, io) : queue_solve<float>(q, *sl, prm, B, io);
+        if (rc) return -rc;
+    }
+    if (cudaEventRecord(sl->ev_done, q->s_tail) != cudaSuccess) return -cuda_fail(cudaGetLastError(), "cudaEventRecord");
+    sl->busy = true;
+    sl->ticket = q->next;
+    return q->next++;
+}
+
+int64_t ikb_queue_submit_host(ikb_queue *q, int dtype, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io) {
+    if (!q) return -fail(IKB_ERR_INVALID_ARG, "null queue");
+    int rc = check_solve_args(q->p, dtype, prm, B, io);
+    if (rc) return -rc;
+    DeviceGuard g(q->p->device);
+    ikb_queue::Slot *sl;
+    if ((rc = queue_slot(q, &sl))) return -rc;
+    if (B > 0) {
+        rc = dtype == IKB_F64 ? queue_submit_host<double>(q, *sl, prm, B, io) : queue_submit_host<float>(q, *sl, prm, B, io);
+        if (rc) return -rc;
+    } else if (cudaEventRecord(sl->ev_done, q->s_out) != cudaSuccess) {
+        return -cuda_fail(cudaGetLastError(), "cudaEventRecord");
+    }
+    sl->busy = true;
+    sl->ticket = q->next;
+    return q->next++;
+}
+
+int ikb_queue_wait(ikb_queue *q, int64_t ticket) {
+    if (!q || ticket < 0 || ticket >= q->next) return fail(IKB_ERR_INVALID_ARG, "unknown queue ticket");
+    ikb_queue::Slot &sl = q->slots[ticket % q->depth];
+    if (sl.ticket != ticket) return IKB_OK;  // its slot has been reused: it left the pipeline long ago
+    DeviceGuard g(q->p->device);
+    IKB_CUDA(cudaEventSynchronize(sl.ev_done));
+    sl.busy = false;
+    return IKB_OK;
+}
+
+int ikb_queue_wait_on_stream(ikb_queue *q, int64_t ticket, void *cuda_stream) {
+    if (!q || ticket < 0 || ticket >= q->next) return fail(IKB_ERR_INVALID_ARG, "unknown queue ticket");
+    if (q->slots[ticket % q->depth].ticket != ticket) return IKB_OK;
+    DeviceGuard g(q->p->device);
+    IKB_CUDA(cudaStreamWaitEvent((cudaStream_t)cuda_stream, q->slots[ticket % q->depth].ev_done, 0));
+    return IKB_OK;
+}
+
+int ikb_queue_drain(ikb_queue *q) {
+    if (!q) return fail(IKB_ERR_INVALID_ARG, "null queue");
+    DeviceGuard g(q->p->device);
+    for (cudaStream_t s : {q->s_in, q->s_bulk, q->s_tail, q->s_out}) IKB_CUDA(cudaStreamSynchronize(s));
+    for (auto &sl : q->slots) sl.busy = false;
+    if (!q->trace.empty()) {
+        for (auto &x : q->trace) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, q->trace[0].second, x.second);
+            std::fprintf(stderr, "[ikb queue trace] %-16s %8.3f ms\n", x.first.c_str(), ms);
+            }
+        for (auto &x : q->trace) cudaEventDestroy(x.second);
+        q->trace.clear();
+    }
+    return IKB_OK;
 }
 
 int ikb_dls_solve(ikb_problem *p, const ikb_dls_params *prm, const double *q0, const double *targets, double *q_out,

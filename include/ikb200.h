@@ -164,6 +164,30 @@ int ikb_dls_solve_batch_host(ikb_problem *p, int dtype, const ikb_dls_params *pa
 int ikb_dls_solve(ikb_problem *p, const ikb_dls_params *params, const double *q0, const double *targets,
                   double *q_out, int *success, int *iters, double *resid);
 
+/* ---- pipelined queue --------------------------------------------------------------------------------
+ * The reference's only caller runs ik::dls once per control tick, one call after the other
+ * (ik_ros/src/cassie.cpp:112-113 inside CassieIK::loop, :146-171).  A stream of BATCHES has the same shape, and one
+ * batch alone cannot keep the GPU busy: the few problems that never converge run all max_iterations steps
+ * (dls.cpp:14), a serial chain of ~0.7 ms during which most SMs idle.  A queue keeps `depth` batches in flight on
+ * four internal streams (copy-in, BULK launch, TAIL launch, copy-out), so the straggler launch of batch k runs beside
+ * the bulk launch of batch k+1 and -- with host buffers -- beside the PCIe copies of its neighbours.  Results are
+ * those of ikb_dls_solve_batch, bit for bit.  One thread drives a queue; a problem may have several queues. */
+typedef struct ikb_queue ikb_queue;
+int ikb_queue_create(ikb_problem *p, int depth /* 1..8 batches in flight */, ikb_queue **out);
+void ikb_queue_free(ikb_queue *q);
+/* DEVICE buffers (as ikb_dls_solve_batch).  The inputs must be complete in `in_stream` order at the time of the
+ * call; the buffers of a batch must stay untouched until its ticket has been waited for.  Returns the batch's
+ * ticket (>= 0) or minus an ikb_status.  Blocks only when all `depth` slots are still in flight. */
+int64_t ikb_queue_submit(ikb_queue *q, int dtype, const ikb_dls_params *params, int64_t B, const ikb_batch_io *io,
+                         void *in_stream);
+/* HOST buffers (as ikb_dls_solve_batch_host; pinned memory -- ikb_host_alloc -- for the copies to overlap). */
+int64_t ikb_queue_submit_host(ikb_queue *q, int dtype, const ikb_dls_params *params, int64_t B,
+                              const ikb_batch_io *io);
+/* Block the host until the outputs of `ticket` are complete / make `cuda_stream` wait for them / wait for all. */
+int ikb_queue_wait(ikb_queue *q, int64_t ticket);
+int ikb_queue_wait_on_stream(ikb_queue *q, int64_t ticket, void *cuda_stream);
+int ikb_queue_drain(ikb_queue *q);
+
 /* pinocchio::framesForwardKinematics (reference data.cpp:28-29) for a batch: placements of `nf` frames.
  * q: device, strided as above; out: device SoA [nf*12][B] (frame-major, then the 12 SE3 scalars). */
 int ikb_fk_batch(const ikb_problem *p, int dtype, int64_t B, const void *q, int64_t q_elem_stride,

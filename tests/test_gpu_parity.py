@@ -304,3 +304,12 @@ def test_two_phase_scheduling_matches_oracle(params):
     out = ik.dls_batch_host(pb, q0[:20000], tg[:20000], prm, "f64", "aos")
     assert np.array_equal(out["success"].astype(bool), ref[1][:20000].astype(bool))
     assert np.abs(out["q"] - ref[0][:20000]).max() < 1e-6
+    # the host path cuts a two-launch batch into slices (H2D of slice c + 1 under the BULK launch of slice c): same
+    # arithmetic per problem, so bit-identical to the unsliced call -- SoA (2-D slice copies) and AoS (dense slices)
+    for layout, a, b in (("soa", q0.T.copy(), tg.T.copy()), ("aos", q0, tg)):
+        os.environ["IKB_HOST_PIPELINE"] = "0"
+        plain = ik.dls_batch_host(pb, a, b, prm, "f64", layout)
+        del os.environ["IKB_HOST_PIPELINE"]
+        piped = ik.dls_batch_host(pb, a, b, prm, "f64", layout)
+        for k in ("q", "success", "iters", "resid"):
+            assert np.array_equal(plain[k], piped[k]), (layout, k)
