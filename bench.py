@@ -146,6 +146,8 @@ def main():
     ap.add_argument("--batch", type=int, default=65536, help="problems per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--merge", type=int, default=4, help="consecutive batches per kernel pair in the pipelined queue (1 = off)")
+    ap.add_argument("--depth", type=int, default=8, help="batches in flight in the pipelined queue")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -222,6 +224,10 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident arm ----
+    # A step = one batch of B problems through the solver.  The timed K steps are submitted to the pipelined queue
+    # (ikb_queue_*, the API for a stream of batches): `--merge` consecutive batches share one BULK + TAIL kernel pair, so
+    # the straggler chain (problems that never converge run all 100 steps, ~0.7 ms of mostly idle SMs) is paid once per
+    # group.  The same K steps through the plain per-batch call (ikb_dls_solve_batch) are timed too: `isolated`.
     sampler = ClockSampler(local_rank)
     sampler.start()
     sampler.ready.wait(10.0)
@@ -229,19 +235,40 @@ def main():
         q0_d, tg_d, out, _ = sets[w % nsets]
         ik.dls_batch(pb, q0_d, tg_d, prm, out)
     barrier()
-    sampler.armed.set()
-    launches0 = ik.kernel_launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    ev[0].record()
+    iso = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    iso[0].record()
     for k in range(args.steps):
         q0_d, tg_d, out, _ = sets[k % nsets]
         ik.dls_batch(pb, q0_d, tg_d, prm, out)
-        ev[k + 1].record()
+    iso[1].record()
     barrier()
+    isolated_ms = iso[0].elapsed_time(iso[1]) / args.steps
+
+    depth = max(args.depth, args.merge)
+    queue = ik.SolveQueue(pb, depth, args.merge, local_rank)
+    for w in range(max(args.warmup, args.merge)):
+        q0_d, tg_d, out, _ = sets[w % nsets]
+        queue.submit(q0_d, tg_d, prm, out)
+    queue.drain()
+    barrier()
+    sampler.armed.set()
+    launches0 = ik.kernel_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()                       # the queue's compute stream waits for this point of the current stream
+    last = None
+    for k in range(args.steps):
+        q0_d, tg_d, out, _ = sets[k % nsets]
+        last, _ = queue.submit(q0_d, tg_d, prm, out)
+    queue.flush()
+    for t in range(max(0, last - depth + 1), last + 1):
+        queue.wait_on_stream(t)          # ... and the current stream waits for every batch still in flight
+    ev[1].record()
+    barrier()
+    queue.drain()
     launches = ik.kernel_launch_count() - launches0
-    elapsed_ms = ev[0].elapsed_time(ev[-1])
+    elapsed_ms = ev[0].elapsed_time(ev[1])
     sampler.armed.clear()
-    kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    kernel_ms = [elapsed_ms / args.steps]
 
     conv = 0
     evals = 0
@@ -254,24 +281,47 @@ def main():
         # evaluations: a converged problem evaluated (iters+1) times, a failed one `iters` times
         evals += int((it + out["success"].to(torch.int64)).sum().item())
 
-    # ---- e2e arm: host buffers through the C-ABI host entry point ----
-    h_q0 = pinned_array((nq, B), npdt)
-    h_tg = pinned_array((tsz, B), npdt)
-    h_out = {"q": pinned_array((nq, B), npdt), "success": pinned_array((B,), np.uint8),
-             "iters": pinned_array((B,), np.int32), "resid": pinned_array((B,), npdt)}
-    h_q0[:] = q0_np.T
-    e2e_steps = max(3, min(args.steps, 10))
+    # ---- e2e arm: HOST buffers.  Every step copies that step's inputs from pinned host memory and reads its results back
+    # (q, success, iters, resid); the steps go through the queue's host entry point (ikb_queue_submit_host / ikb_queue_wait),
+    # so the copies of one group of batches run beside the kernels of its neighbours. ----
+    nbuf = depth
+    h_in = [(pinned_array((nq, B), npdt), pinned_array((tsz, B), npdt)) for _ in range(nbuf)]
+    h_outs = [{"q": pinned_array((nq, B), npdt), "success": pinned_array((B,), np.uint8),
+               "iters": pinned_array((B,), np.int32), "resid": pinned_array((B,), npdt)} for _ in range(nbuf)]
     host_sets = [np.ascontiguousarray(sets[s][3].T, dtype=npdt) for s in range(min(nsets, 3))]
-    for w in range(2):
-        h_tg[:] = host_sets[w % len(host_sets)]
-        ik.dls_batch_host(pb, h_q0, h_tg, prm, args.dtype, "soa", h_out)
+    for i, (hq, ht) in enumerate(h_in):
+        hq[:] = q0_np.T
+        ht[:] = host_sets[i % len(host_sets)]
+    e2e_steps = max(3, min(args.steps, 20))
+    lag = max(1, depth - 1)              # results of step k are consumed after step k + lag has been submitted: the
+                                         # next group is fully in flight before the host blocks on the previous one
+
+    def e2e_run(nsteps):
+        got = 0
+        tickets = []
+        for k in range(nsteps):
+            t, _ = queue.submit_host(h_in[k % nbuf][0], h_in[k % nbuf][1], prm, args.dtype, "soa", h_outs[k % nbuf])
+            tickets.append(t)
+            if k >= lag:
+                queue.wait(tickets[k - lag])
+                got += int(h_outs[(k - lag) % nbuf]["success"].sum())
+        for k in range(max(0, nsteps - lag), nsteps):
+            queue.wait(tickets[k])
+            got += int(h_outs[k % nbuf]["success"].sum())
+        return got
+
+    e2e_run(nbuf + args.merge)           # every slot's staging buffers exist before the timed region
+    # the same steps through the blocking per-batch host call, for reference
+    for k in range(2):
+        ik.dls_batch_host(pb, h_in[0][0], h_in[0][1], prm, args.dtype, "soa", h_outs[0])
+    t0 = time.perf_counter()
+    for k in range(3):
+        ik.dls_batch_host(pb, h_in[0][0], h_in[0][1], prm, args.dtype, "soa", h_outs[0])
+    e2e_isolated_ms = (time.perf_counter() - t0) / 3 * 1e3
     barrier()
     sampler.armed.set()  # the clocks record covers both timed regions (device-resident steps and e2e steps)
     t0 = time.perf_counter()
-    e2e_conv = 0
-    for k in range(e2e_steps):
-        ik.dls_batch_host(pb, h_q0, h_tg, prm, args.dtype, "soa", h_out)
-        e2e_conv += int(h_out["success"].sum())
+    e2e_conv = e2e_run(e2e_steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     sampler.armed.clear()
@@ -325,19 +375,24 @@ def main():
                        "kernel": pb.kernel_name(args.dtype),
                        "l2": "inputs/outputs rotate over %d distinct batches (%.0f MB > 126 MB L2)"
                              % (nsets, nsets * per_set / 1e6),
+                       "pipeline": "ikb_queue, depth %d, %d consecutive batches per BULK+TAIL kernel pair" % (depth, args.merge),
+                       "isolated_ms_per_batch": isolated_ms,
+                       "isolated_value": conv * world / args.steps / (isolated_ms * 1e-3),
                        "converged_fraction": conv_all / (B * world * args.steps),
                        "mean_iterations": it_all / (B * world * args.steps)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * (nq + tsz) * itemsize),
                     "d2h_bytes_per_step": int(B * ((nq + 1) * itemsize + 5)), "steps": e2e_steps,
-                    "api": "ikb_dls_solve_batch_host (pinned host buffers, H2D + solve + D2H per step)"},
+                    "api": "ikb_queue_submit_host + ikb_queue_wait (pinned host buffers; H2D, solve, D2H of every step)",
+                    "isolated_ms_per_batch": e2e_isolated_ms,
+                    "isolated_api": "ikb_dls_solve_batch_host (blocking, one batch at a time)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64_fma_pipe" if args.dtype == "f64" else "fp32_fma_pipe",
                          "achieved": achieved_tf, "peak": peak.value, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak.value if peak.value else None,
                          "traffic": NCU_TRAFFIC_BYTES_F64 if (args.dtype == "f64" and B == 65536) else None,
                          "traffic_source": "ncu --set full, profiles/r1_final_full.txt (DRAM bytes of both launches of a step)",
-                         "kernels": "2 launches per step: BULK %s + TAIL (3 warp roles, 1 group/CTA); ncu durations "
-                                    "0.39 + 0.61 ms, profiles/r1_final_full.txt" % pb.kernel_name(args.dtype),
+                         "kernels": "BULK %s + TAIL per group of %d steps; kernel_ms = device time of the timed region / steps"
+                                    % (pb.kernel_name(args.dtype), args.merge),
                          "peak_source": "measured in this run (ikb_measure_fma_peak); nominal %.1f"
                                         % NOMINAL_TFLOPS[args.dtype],
                          "frac_of_nominal": achieved_tf / NOMINAL_TFLOPS[args.dtype],

@@ -84,7 +84,8 @@ SIGNATURES = {
     "ikb_dls_solve_batch": (C.c_int, [_vp, C.c_int, C.POINTER(DlsParams), C.c_int64, C.POINTER(BatchIO), _vp]),
     "ikb_dls_solve_batch_host": (C.c_int, [_vp, C.c_int, C.POINTER(DlsParams), C.c_int64, C.POINTER(BatchIO)]),
     "ikb_dls_solve": (C.c_int, [_vp, C.POINTER(DlsParams), _dp, _dp, _dp, C.POINTER(C.c_int), C.POINTER(C.c_int), _dp]),
-    "ikb_queue_create": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
+    "ikb_queue_create": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "ikb_queue_flush": (C.c_int, [_vp]),
     "ikb_queue_free": (None, [_vp]),
     "ikb_queue_submit": (C.c_int64, [_vp, C.c_int, C.POINTER(DlsParams), C.c_int64, C.POINTER(BatchIO), _vp]),
     "ikb_queue_submit_host": (C.c_int64, [_vp, C.c_int, C.POINTER(DlsParams), C.c_int64, C.POINTER(BatchIO)]),

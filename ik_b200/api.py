@@ -403,20 +403,20 @@ def dls_batch(problem, q0, targets, p=None, out=None, stream=None):
 
 
 class SolveQueue:
-    """Pipelined stream of batches (ikb_queue_*, include/ikb200.h): up to ``depth`` batches in flight, the straggler
-    launch of one batch beside the bulk launch of the next, host-buffer copies beside both.  Results are those of
-    dls_batch / dls_batch_host, bit for bit.
+    """Pipelined stream of batches (ikb_queue_*, include/ikb200.h): up to ``depth`` batches in flight, ``merge``
+    consecutive batches per kernel pair (the ~0.7 ms straggler chain is paid once per group), host-buffer copies of one
+    group beside the kernels of its neighbours.  Results are those of dls_batch / dls_batch_host, bit for bit.
 
-        queue = ik.SolveQueue(problem, depth=3)
+        queue = ik.SolveQueue(problem, depth=8, merge=4)
         tickets = [queue.submit(q0_k, targets_k, out=out_k) for ...]     # device tensors (torch, SoA)
         queue.wait(tickets[0]); ... ; queue.drain()
     """
 
-    def __init__(self, problem, depth=3, device=0):
+    def __init__(self, problem, depth=8, merge=4, device=0):
         problem.finalize(problem._device if problem._device is not None else device)
         self._problem = problem
         self._h = C.c_void_p()
-        capi.check(capi.lib.ikb_queue_create(problem._h, depth, C.byref(self._h)), "ikb_queue_create")
+        capi.check(capi.lib.ikb_queue_create(problem._h, depth, merge, C.byref(self._h)), "ikb_queue_create")
         self._keep = {}  # ticket -> buffers that must outlive the batch
 
     def __del__(self):
@@ -490,6 +490,9 @@ class SolveQueue:
 
         s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
         capi.check(capi.lib.ikb_queue_wait_on_stream(self._h, ticket, C.c_void_p(s)), "ikb_queue_wait_on_stream")
+
+    def flush(self):
+        capi.check(capi.lib.ikb_queue_flush(self._h), "ikb_queue_flush")
 
     def drain(self):
         capi.check(capi.lib.ikb_queue_drain(self._h), "ikb_queue_drain")

@@ -48,10 +48,9 @@ template <class Spec, typename T> struct SpecLaunch {
     static constexpr int smem_bytes(int groups) { return groups * 32 * kBytesPerProblem; }
 };
 
-// LBT = the thread count the register allocation is bounded for (>= the block size): a SHARED-residency variant keeps
-// the register budget of a bigger CTA so that a second kernel's CTAs fit on the SM beside it (pipelined queue).
-template <class Spec, typename T, int GROUPS, int MINB, int LBT = GROUPS * Spec::NWARPS * 32>
-__global__ void __launch_bounds__(LBT, MINB)
+// SEG: merged launch of the pipelined queue (several batches, each with its own buffers: SolveArgs::seg).
+template <class Spec, typename T, int GROUPS, int MINB, bool SEG>
+__global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
     dls_spec_kernel(const __grid_constant__ SpecConsts<T, Spec::NQ, Spec::M> c, const __grid_constant__ SolveArgs<T> a) {
     constexpr int NQ = Spec::NQ, NV = Spec::NV, M = Spec::M, NW = Spec::NWARPS, SLOTS = GROUPS * 32;
     static_assert(Spec::NFACT >= M + NQ, "factor strip must also hold e and the stepped q");
@@ -86,22 +85,21 @@ __global__ void __launch_bounds__(LBT, MINB)
         it = 0;
         if (!a.resume) {
             have = b < a.B;
-            if (have) {
-                const T *q0 = a.q0 + b * a.q0_bs;
-#pragma unroll
-                for (int k = 0; k < NQ; ++k) q[k] = __ldg(q0 + k * a.q0_es);
-            }
         } else {
             have = b < (long long)*a.list_count;
             if (have) {
                 b = a.list[b];
                 it = a.iters_ws[b];
-                const T *qs = a.q + b * a.q_bs;
-#pragma unroll
-                for (int k = 0; k < NQ; ++k) q[k] = qs[k * a.q_es];
             }
         }
-        if (have) Spec::load_targets(role, a.targets + b * a.tg_bs, a.tg_es, sT);
+        if (have) {
+            const ProblemIO<T> io = problem_io<SEG>(a, b);
+            const T *src = a.resume ? io.q : io.q0;       // a suspended problem continues from its saved iterate
+            const long long es = a.resume ? io.q_es : io.q0_es;
+#pragma unroll
+            for (int k = 0; k < NQ; ++k) q[k] = src[k * es];
+            Spec::load_targets(role, io.targets, io.tg_es, sT);
+        }
     };
     // SOLVER role, after the solve: dq = -J^T y, the manifold step and the clamp on ITS copy of q, which it then publishes
     // in the (dead) factor strip -- the other roles only copy it (no second and third integrate on the critical path).
@@ -183,16 +181,16 @@ __global__ void __launch_bounds__(LBT, MINB)
             }
             if (finished || suspend) {
                 if (role == Spec::SOLVER) {
-                    T *qo = a.q + b * a.q_bs;
+                    const ProblemIO<T> io = problem_io<SEG>(a, b);
 #pragma unroll
-                    for (int k = 0; k < NQ; ++k) qo[k * a.q_es] = q[k];
+                    for (int k = 0; k < NQ; ++k) io.q[k * io.q_es] = q[k];
                     if (suspend) {
                         a.iters_ws[b] = it;
                         a.list[atomicAdd(a.list_count, 1ULL)] = (unsigned int)b;
                     } else {
-                        if (a.success) a.success[b] = converged ? 1 : 0;
-                        if (a.iters) a.iters[b] = it;
-                        if (a.resid) a.resid[b] = res;
+                        if (io.success) *io.success = converged ? 1 : 0;
+                        if (io.iters) *io.iters = it;
+                        if (io.resid) *io.resid = res;
                     }
                 }
                 b = *sNext;
@@ -241,12 +239,12 @@ template <class Spec> bool spec_matches(const HostProblem &hp) {
 // GROUPS = 32-problem groups per CTA, MINB = CTAs per SM the register allocation must allow.  The throughput
 // configuration is one big CTA per SM (GROUPS = SpecLaunch::GROUPS); the latency configuration is GROUPS = 1, so that
 // few problems spread over all SMs and every group has its schedulers to itself.
-template <class Spec, typename T, int GROUPS, int MINB, int LBT = GROUPS * Spec::NWARPS * 32>
-int launch_spec_cfg(const SpecHostConsts &hc, const SolveArgs<T> &a, long long ctas, cudaStream_t s) {
+template <class Spec, typename T, int GROUPS, int MINB, bool SEG>
+int launch_spec_cfg_seg(const SpecHostConsts &hc, const SolveArgs<T> &a, long long ctas, cudaStream_t s) {
     using L = SpecLaunch<Spec, T>;
     static_assert(L::kFits && GROUPS <= L::GROUPS, "per-problem strips do not fit in shared memory for this scalar type");
     constexpr int kSmem = L::smem_bytes(GROUPS);
-    auto fn = dls_spec_kernel<Spec, T, GROUPS, MINB, LBT>;
+    auto fn = dls_spec_kernel<Spec, T, GROUPS, MINB, SEG>;
     static bool attr_set = false;  // per instantiation
     if (!attr_set) {
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess) return 1;
@@ -263,19 +261,18 @@ int launch_spec_cfg(const SpecHostConsts &hc, const SolveArgs<T> &a, long long c
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
+template <class Spec, typename T, int GROUPS, int MINB>
+int launch_spec_cfg(const SpecHostConsts &hc, const SolveArgs<T> &a, long long ctas, cudaStream_t s) {
+    return a.seg ? launch_spec_cfg_seg<Spec, T, GROUPS, MINB, true>(hc, a, ctas, s)
+                 : launch_spec_cfg_seg<Spec, T, GROUPS, MINB, false>(hc, a, ctas, s);
+}
+
 // Throughput configuration: persistent, one CTA per SM.
 template <class Spec, typename T> int launch_spec_bulk(const SpecHostConsts &hc, const SolveArgs<T> &a, long long n, int sm_count, cudaStream_t s) {
     using L = SpecLaunch<Spec, T>;
     long long ctas = (n + L::GROUPS * 32 - 1) / (L::GROUPS * 32);
     if (ctas > sm_count) ctas = sm_count;
     return launch_spec_cfg<Spec, T, L::GROUPS, 1>(hc, a, ctas, s);
-}
-// Latency configuration with G groups per CTA (G = 2: half as many SMs are tied up, each trip a little slower -- the
-// better trade when the TAIL launch shares the GPU with the BULK launch of the next batch).
-template <class Spec, typename T, int G> int launch_spec_tail_g(const SpecHostConsts &hc, const SolveArgs<T> &a, long long n, int sm_count, cudaStream_t s) {
-    long long ctas = (n + 32 * G - 1) / (32 * G);
-    if (ctas > sm_count) ctas = sm_count;
-    return launch_spec_cfg<Spec, T, G, 1>(hc, a, ctas, s);
 }
 // Latency configuration: one 32-problem group per CTA, at most 2 CTAs per SM (full register budget per thread).
 template <class Spec, typename T> int launch_spec_tail(const SpecHostConsts &hc, const SolveArgs<T> &a, long long n, int sm_count, cudaStream_t s) {

@@ -314,7 +314,7 @@ template <typename T> struct TeamLaunch {
     static constexpr size_t kSmem = kConstBytes + kTeamsPerCta * sizeof(TeamScratch<T>);
 };
 
-template <typename T>
+template <typename T, bool SEG>
 __global__ void __launch_bounds__(TeamLaunch<T>::kTeamsPerCta *kTeamLanes, TeamLaunch<T>::kCtasPerSm)
     dls_team_kernel(const __grid_constant__ TeamConsts<T> gc, const __grid_constant__ SolveArgs<T> a) {
     extern __shared__ __align__(16) unsigned char team_smem[];
@@ -348,28 +348,25 @@ __global__ void __launch_bounds__(TeamLaunch<T>::kTeamsPerCta *kTeamLanes, TeamL
         if (need && lane == 0) t = atomicAdd(a.ticket, 1ULL);
         t = __shfl_sync(0xffffffffu, t, 0, kTeamLanes);
         if (need) {
-            const T *qs;
-            long long es, bs;
             it = 0;
             if (!a.resume) {
                 have = (long long)t < a.B;
                 b = (long long)t;
-                qs = a.q0; es = a.q0_es; bs = a.q0_bs;
             } else {
                 have = t < *a.list_count;
                 if (have) {
                     b = a.list[t];
                     it = a.iters_ws[b];
                 }
-                qs = a.q; es = a.q_es; bs = a.q_bs;
             }
             if (have) {
-                const T *qb = qs + b * bs;
+                const ProblemIO<T> io = problem_io<SEG>(a, b);
+                const T *qb = a.resume ? io.q : io.q0;
+                const long long es = a.resume ? io.q_es : io.q0_es;
 #pragma unroll
                 for (int k = 0; k < 7; ++k) st.qff[k] = qb[k * es];
                 st.qr = qb[(7 + lane) * es];
-                const T *tb = a.targets + b * a.tg_bs;
-                for (int i = lane; i < 36; i += kTeamLanes) S.tg[i] = tb[i * a.tg_es];
+                for (int i = lane; i < 36; i += kTeamLanes) S.tg[i] = io.targets[i * io.tg_es];
             }
             need = false;
         }
@@ -381,15 +378,15 @@ __global__ void __launch_bounds__(TeamLaunch<T>::kTeamsPerCta *kTeamLanes, TeamL
             const bool converged = res < a.tolerance;      // visitor.hpp:19
             if (!converged) ++it;                           // team_iteration has stepped q
             if (converged || it >= a.max_iterations) {      // dls.cpp:61-64 / 14,76-77
-                T *qo = a.q + b * a.q_bs;
+                const ProblemIO<T> io = problem_io<SEG>(a, b);
 #pragma unroll
                 for (int k = 0; k < 7; ++k)
-                    if (lane == k) qo[k * a.q_es] = st.qff[k];
-                qo[(7 + lane) * a.q_es] = st.qr;
+                    if (lane == k) io.q[k * io.q_es] = st.qff[k];
+                io.q[(7 + lane) * io.q_es] = st.qr;
                 if (lane == 0) {
-                    if (a.success) a.success[b] = converged ? 1 : 0;
-                    if (a.iters) a.iters[b] = it;
-                    if (a.resid) a.resid[b] = res;
+                    if (io.success) *io.success = converged ? 1 : 0;
+                    if (io.iters) *io.iters = it;
+                    if (io.resid) *io.resid = res;
                 }
                 need = true;
                 have = false;
@@ -398,9 +395,9 @@ __global__ void __launch_bounds__(TeamLaunch<T>::kTeamsPerCta *kTeamLanes, TeamL
     }
 }
 
-template <typename T> int launch_team(const TeamConsts<T> &c, const SolveArgs<T> &a, long long n, int sm_count, cudaStream_t s) {
+template <typename T, bool SEG> int launch_team_seg(const TeamConsts<T> &c, const SolveArgs<T> &a, long long n, int sm_count, cudaStream_t s) {
     using L = TeamLaunch<T>;
-    auto fn = dls_team_kernel<T>;
+    auto fn = dls_team_kernel<T, SEG>;
     static bool attr_set = false;  // per instantiation
     if (!attr_set) {
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kSmem) != cudaSuccess) return 1;
@@ -411,6 +408,9 @@ template <typename T> int launch_team(const TeamConsts<T> &c, const SolveArgs<T>
     if (ctas < 1) ctas = 1;
     fn<<<(unsigned)ctas, L::kTeamsPerCta * kTeamLanes, L::kSmem, s>>>(c, a);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+template <typename T> int launch_team(const TeamConsts<T> &c, const SolveArgs<T> &a, long long n, int sm_count, cudaStream_t s) {
+    return a.seg ? launch_team_seg<T, true>(c, a, n, sm_count, s) : launch_team_seg<T, false>(c, a, n, sm_count, s);
 }
 #endif  // __CUDACC__
 

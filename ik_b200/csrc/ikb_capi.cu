@@ -211,26 +211,30 @@ bool two_phase(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, int *
     return p->spec && B > 2LL * 32 * p->sm_count && cap > 0 && prm->max_iterations > cap;
 }
 
-// Pipelined queue (ikb_queue_*): the TAIL launch goes to its own stream, so that it runs beside the BULK launch of the
-// next batch (the stragglers' 100-step latency chain then costs SM space, not wall time).
-struct SplitStreams {
-    cudaStream_t tail;
-    cudaEvent_t ev_bulk;
-    cudaEvent_t ev_go;      // recorded on `tail` right before the TAIL launch (the next BULK launch is held until then)
-    bool *went;             // set when ev_go was recorded
+// Merged launch of the pipelined queue (ikb_queue_*): `nseg` batches described by a device-resident table.
+template <typename T> struct Merged {
+    const BatchSeg<T> *d_seg;
+    int nseg;
 };
-__global__ void marker_kernel() {}
 
 template <typename T>
 int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io, cudaStream_t s,
-                 const ChunkPlan *plan = nullptr, const SplitStreams *split = nullptr) {
-    SolveArgs<T> a;
-    a.q0 = (const T *)io->q0; a.q0_es = io->q0_elem_stride; a.q0_bs = io->q0_batch_stride;
-    a.targets = (const T *)io->targets; a.tg_es = io->targets_elem_stride; a.tg_bs = io->targets_batch_stride;
-    a.q = (T *)io->q; a.q_es = io->q_elem_stride; a.q_bs = io->q_batch_stride;
-    a.success = io->success;
-    a.iters = io->iters;
-    a.resid = (T *)io->resid;
+                 const ChunkPlan *plan = nullptr, const Merged<T> *merged = nullptr) {
+    SolveArgs<T> a{};
+    if (!merged) {
+        a.q0 = (const T *)io->q0; a.q0_es = io->q0_elem_stride; a.q0_bs = io->q0_batch_stride;
+        a.targets = (const T *)io->targets; a.tg_es = io->targets_elem_stride; a.tg_bs = io->targets_batch_stride;
+        a.q = (T *)io->q; a.q_es = io->q_elem_stride; a.q_bs = io->q_batch_stride;
+        a.success = io->success;
+        a.iters = io->iters;
+        a.resid = (T *)io->resid;
+        a.seg = nullptr;
+        a.nseg = 0;
+    } else {
+        if (!p->spec || prm->max_iterations <= 0) return fail(IKB_ERR_INVALID_ARG, "internal: merged launch on a problem without a specialised kernel");
+        a.seg = merged->d_seg;
+        a.nseg = merged->nseg;
+    }
     a.B = B;
     a.max_iterations = prm->max_iterations;
     a.step_length = (T)prm->step_length;
@@ -252,7 +256,7 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
     a.resume = 0;
     a.list = nullptr;
     a.list_count = nullptr;
-    a.iters_ws = io->iters;
+    a.iters_ws = merged ? nullptr : io->iters;
     if (p->spec) {
         const SpecHostConsts hc{p->hp.model.lower.data(), p->hp.model.upper.data(), p->weight_stacked.data()};
         // Scheduling.  A batch that the latency configuration keeps resident in one wave runs there
@@ -296,7 +300,7 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
             a.it_cap = cap;
             a.list = sc->list;
             a.list_count = a.ticket + 2;
-            a.iters_ws = io->iters ? io->iters : sc->iters;
+            a.iters_ws = (!merged && io->iters) ? io->iters : sc->iters;
             if (!plan) {
                 rc = launch_specialized<T>(*p->spec, hc, a, SPEC_BULK, B, p->sm_count, s);
                 if (rc == IKB_OK) g_launches.fetch_add(1);
@@ -318,36 +322,15 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
                 IKB_CUDA(cudaEventRecord(plan->ev_aux, plan->aux));
                 IKB_CUDA(cudaStreamWaitEvent(s, plan->ev_aux, 0));
             }
-            cudaStream_t ts = s;
-            if (split) {
-                ts = split->tail;
-                IKB_CUDA(cudaEventRecord(split->ev_bulk, s));
-                IKB_CUDA(cudaStreamWaitEvent(ts, split->ev_bulk, 0));
-                // ev_go completes when the tail stream has reached this point, i.e. when the BULK launch is over: the next
-                // BULK launch waits for it and so becomes runnable together with (not before) this TAIL launch, which has
-                // the higher stream priority and gets its SMs first.
-                marker_kernel<<<1, 1, 0, ts>>>();
-                IKB_CUDA(cudaEventRecord(split->ev_go, ts));
-                *split->went = true;
-            }
             if (rc == IKB_OK) {
                 SolveArgs<T> t = a;
                 t.resume = 1;
                 t.it_cap = INT_MAX;
                 t.ticket = a.ticket + 1;
-                // Queue mode: the TAIL launch shares the GPU with the next BULK launch, whose persistent CTAs need whole SMs.
-                // Its grid is sized for the expected number of stragglers (slots refill from the list, so any number
-                // works) instead of spreading them thinly over every SM.
-                long long n_tail = B;
-                if (split) {
-                    const char *fe = std::getenv("IKB_TAIL_DIV");
-                    const int div = fe ? std::max(1, std::atoi(fe)) : 14;
-                    n_tail = std::max<long long>(B / div, 1024);
-                }
-                rc = launch_specialized<T>(*p->spec, hc, t, split ? SPEC_TAIL_SHARED : SPEC_TAIL, n_tail, p->sm_count, ts);
+                rc = launch_specialized<T>(*p->spec, hc, t, SPEC_TAIL, B, p->sm_count, s);
                 if (rc == IKB_OK) g_launches.fetch_add(1);
             }
-            IKB_CUDA(cudaEventRecord(sc->ev, ts));
+            IKB_CUDA(cudaEventRecord(sc->ev, s));
         }
         if (rc != IKB_OK) return cuda_fail(cudaGetLastError(), "specialised kernel launch");
         return IKB_OK;
@@ -507,14 +490,18 @@ int solve_host(ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_b
 }
 
 // ---------------------------------------------------------------------------------------------------
-// pipelined queue: batches in flight on four streams (copy-in, BULK, TAIL, copy-out)
+// pipelined queue: batches in flight on three streams (copy-in, compute, copy-out); consecutive batches are MERGED
+// into one BULK + TAIL launch pair (the straggler chain of ~0.7 ms is paid once per group instead of once per batch)
 // ---------------------------------------------------------------------------------------------------
 }  // namespace
 struct ikb_queue {
     struct Slot {
-        cudaEvent_t ev_in = nullptr, ev_bulk = nullptr, ev_mid = nullptr, ev_done = nullptr, ev_go = nullptr;
-        bool busy = false;
+        cudaEvent_t ev_in = nullptr, ev_done = nullptr;
+        bool busy = false, pending = false, host = false;
         int64_t ticket = -1;  // the batch occupying the slot
+        int64_t B = 0;
+        ikb_batch_io dio{};   // device view of the batch
+        ikb_batch_io hio{};   // host mode: the caller's buffers (copy-out targets)
         // host-mode staging (per scalar type, grown on demand)
         Staging<double> st64;
         Staging<float> st32;
@@ -523,46 +510,125 @@ struct ikb_queue {
         size_t flag_cap = 0;
     };
     ikb_problem *p = nullptr;
-    int depth = 0;
+    int depth = 0, merge = 1;
     std::vector<Slot> slots;
-    cudaStream_t s_in = nullptr, s_bulk = nullptr, s_tail = nullptr, s_out = nullptr;
-    cudaEvent_t ev_user = nullptr;
-    cudaEvent_t ev_go_last = nullptr;  // of the last two-launch batch submitted (not owned)
+    std::vector<int> open;        // slots of the group that has not been launched yet
+    ikb_dls_params open_prm{};
+    int open_dtype = -1;
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    cudaEvent_t ev_user = nullptr, ev_comp = nullptr;
+    void *d_seg = nullptr;        // segment table of the merged launch in flight (reused in s_comp order)
     int64_t next = 0;
-    std::vector<std::pair<std::string, cudaEvent_t>> trace;  // IKB_QUEUE_TRACE=1: device timeline, printed by drain
-    bool tracing = false;
-    void mark(const std::string &name, cudaStream_t s) {
-        if (!tracing) return;
-        cudaEvent_t e;
-        cudaEventCreate(&e);
-        cudaEventRecord(e, s);
-        trace.emplace_back(name, e);
-    }
 };
 namespace {
+constexpr int kMaxMerge = 8;
+template <typename T> struct SegTable {
+    BatchSeg<T> e[kMaxMerge];
+};
+template <typename T> __global__ void upload_seg_kernel(const __grid_constant__ SegTable<T> t, BatchSeg<T> *dst, int n) {
+    if ((int)threadIdx.x < n) dst[threadIdx.x] = t.e[threadIdx.x];
+}
+
 template <typename T> Staging<T> &slot_staging(ikb_queue::Slot &sl);
 template <> Staging<double> &slot_staging<double>(ikb_queue::Slot &sl) { return sl.st64; }
 template <> Staging<float> &slot_staging<float>(ikb_queue::Slot &sl) { return sl.st32; }
 
-// Enqueue the solve of one batch whose device inputs are ready in s_bulk order; the slot's ev_done fires when the outputs
-// are complete on s_tail.
-template <typename T> int queue_solve(ikb_queue *q, ikb_queue::Slot &sl, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *dio) {
-    bool went = false;
-    const SplitStreams split{q->s_tail, sl.ev_bulk, sl.ev_go, &went};
-    if (q->ev_go_last) IKB_CUDA(cudaStreamWaitEvent(q->s_bulk, q->ev_go_last, 0));
-    q->mark("bulk begin " + std::to_string(q->next), q->s_bulk);
-    int rc = launch_solve<T>(q->p, prm, B, dio, q->s_bulk, nullptr, &split);
-    if (rc) return rc;
-    if (went) q->ev_go_last = sl.ev_go;
-    q->mark("bulk end   " + std::to_string(q->next), q->s_bulk);
-    q->mark("tail end   " + std::to_string(q->next), q->s_tail);
-    // single-launch solves ran on s_bulk only: s_tail picks that up, so that "done" always means "everything"
-    IKB_CUDA(cudaEventRecord(sl.ev_mid, q->s_bulk));
-    IKB_CUDA(cudaStreamWaitEvent(q->s_tail, sl.ev_mid, 0));
+bool same_params(const ikb_dls_params &a, const ikb_dls_params &b) {
+    return a.max_iterations == b.max_iterations && a.step_length == b.step_length && a.damping == b.damping && a.tolerance == b.tolerance;
+}
+
+template <typename T> int queue_copy_out(ikb_queue *q, ikb_queue::Slot &sl) {
+    const int nq = q->p->hp.model.nq;
+    const ikb_batch_io &io = sl.hio;
+    Staging<T> &st = slot_staging<T>(sl);
+    const size_t n_q = view_extent(nq, io.q_elem_stride, io.q_batch_stride, sl.B);
+    IKB_CUDA(cudaMemcpyAsync(io.q, st.q, n_q * sizeof(T), cudaMemcpyDeviceToHost, q->s_out));
+    if (io.success) IKB_CUDA(cudaMemcpyAsync(io.success, sl.success, (size_t)sl.B, cudaMemcpyDeviceToHost, q->s_out));
+    if (io.iters) IKB_CUDA(cudaMemcpyAsync(io.iters, sl.iters, (size_t)sl.B * sizeof(int), cudaMemcpyDeviceToHost, q->s_out));
+    if (io.resid) IKB_CUDA(cudaMemcpyAsync(io.resid, st.resid, (size_t)sl.B * sizeof(T), cudaMemcpyDeviceToHost, q->s_out));
     return IKB_OK;
 }
 
-template <typename T> int queue_submit_host(ikb_queue *q, ikb_queue::Slot &sl, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io) {
+// Launch the open group: one merged BULK + TAIL pair when the problem has a specialised kernel, else batch by batch.
+template <typename T> int queue_flush_t(ikb_queue *q) {
+    const int n = (int)q->open.size();
+    int rc;
+    for (int i : q->open)
+        if (q->slots[i].host) IKB_CUDA(cudaStreamWaitEvent(q->s_comp, q->slots[i].ev_in, 0));
+    if (n >= 2 && q->p->spec && q->open_prm.max_iterations > 0) {
+        SegTable<T> tab{};
+        long long total = 0;
+        for (int k = 0; k < n; ++k) {
+            const ikb_queue::Slot &sl = q->slots[q->open[k]];
+            const ikb_batch_io &d = sl.dio;
+            tab.e[k] = BatchSeg<T>{(const T *)d.q0, d.q0_elem_stride, d.q0_batch_stride, (const T *)d.targets, d.targets_elem_stride,
+                                   d.targets_batch_stride, (T *)d.q, d.q_elem_stride, d.q_batch_stride, d.success, d.iters,
+                                   (T *)d.resid, total};
+            total += sl.B;
+        }
+        upload_seg_kernel<T><<<1, kMaxMerge, 0, q->s_comp>>>(tab, (BatchSeg<T> *)q->d_seg, n);
+        const Merged<T> m{(const BatchSeg<T> *)q->d_seg, n};
+        if ((rc = launch_solve<T>(q->p, &q->open_prm, total, nullptr, q->s_comp, nullptr, &m))) return rc;
+        g_launches.fetch_add(1);
+    } else {
+        for (int i : q->open) {
+            ikb_queue::Slot &sl = q->slots[i];
+            if (sl.B > 0 && (rc = launch_solve<T>(q->p, &q->open_prm, sl.B, &sl.dio, q->s_comp))) return rc;
+        }
+    }
+    bool any_host = false;
+    for (int i : q->open) any_host |= q->slots[i].host;
+    if (any_host) {
+        IKB_CUDA(cudaEventRecord(q->ev_comp, q->s_comp));
+        IKB_CUDA(cudaStreamWaitEvent(q->s_out, q->ev_comp, 0));
+    }
+    for (int i : q->open) {
+        ikb_queue::Slot &sl = q->slots[i];
+        if (sl.host) {
+            if (sl.B > 0 && (rc = queue_copy_out<T>(q, sl))) return rc;
+            IKB_CUDA(cudaEventRecord(sl.ev_done, q->s_out));
+        } else {
+            IKB_CUDA(cudaEventRecord(sl.ev_done, q->s_comp));
+        }
+        sl.pending = false;
+    }
+    q->open.clear();
+    return IKB_OK;
+}
+int queue_flush(ikb_queue *q) {
+    if (q->open.empty()) return IKB_OK;
+    return q->open_dtype == IKB_F64 ? queue_flush_t<double>(q) : queue_flush_t<float>(q);
+}
+
+// The slot of the next batch, free of its previous occupant (back-pressure: blocks while that batch is in flight).
+int queue_acquire(ikb_queue *q, int dtype, const ikb_dls_params *prm, ikb_queue::Slot **out) {
+    int rc;
+    ikb_queue::Slot *sl = &q->slots[q->next % q->depth];
+    if (sl->pending && (rc = queue_flush(q))) return rc;
+    if (sl->busy) {
+        IKB_CUDA(cudaEventSynchronize(sl->ev_done));
+        sl->busy = false;
+    }
+    // a group shares one launch: same scalar type, same solver parameters
+    if (!q->open.empty() && (q->open_dtype != dtype || !same_params(q->open_prm, *prm)) && (rc = queue_flush(q))) return rc;
+    q->open_dtype = dtype;
+    q->open_prm = *prm;
+    *out = sl;
+    return IKB_OK;
+}
+int64_t queue_commit(ikb_queue *q, ikb_queue::Slot *sl) {
+    sl->busy = true;
+    sl->pending = true;
+    sl->ticket = q->next;
+    q->open.push_back((int)(q->next % q->depth));
+    if ((int)q->open.size() >= q->merge) {
+        int rc = queue_flush(q);
+        if (rc) return -rc;
+    }
+    return q->next++;
+}
+
+template <typename T> int queue_stage_host(ikb_queue *q, ikb_queue::Slot &sl, int64_t B, const ikb_batch_io *io) {
     ikb_problem *p = q->p;
     const int nq = p->hp.model.nq, tsz = p->hp.target_size();
     Staging<T> &st = slot_staging<T>(sl);
@@ -584,18 +650,10 @@ template <typename T> int queue_submit_host(ikb_queue *q, ikb_queue::Slot &sl, c
     IKB_CUDA(cudaMemcpyAsync(st.q0, io->q0, n_q0 * sizeof(T), cudaMemcpyHostToDevice, q->s_in));
     if (n_tg) IKB_CUDA(cudaMemcpyAsync(st.targets, io->targets, n_tg * sizeof(T), cudaMemcpyHostToDevice, q->s_in));
     IKB_CUDA(cudaEventRecord(sl.ev_in, q->s_in));
-    IKB_CUDA(cudaStreamWaitEvent(q->s_bulk, sl.ev_in, 0));
-    ikb_batch_io dio = *io;
-    dio.q0 = st.q0; dio.targets = st.targets; dio.q = st.q;
-    dio.success = sl.success; dio.iters = sl.iters; dio.resid = st.resid;
-    if ((rc = queue_solve<T>(q, sl, prm, B, &dio))) return rc;
-    IKB_CUDA(cudaEventRecord(sl.ev_mid, q->s_tail));
-    IKB_CUDA(cudaStreamWaitEvent(q->s_out, sl.ev_mid, 0));
-    IKB_CUDA(cudaMemcpyAsync(io->q, st.q, n_q * sizeof(T), cudaMemcpyDeviceToHost, q->s_out));
-    if (io->success) IKB_CUDA(cudaMemcpyAsync(io->success, sl.success, (size_t)B, cudaMemcpyDeviceToHost, q->s_out));
-    if (io->iters) IKB_CUDA(cudaMemcpyAsync(io->iters, sl.iters, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, q->s_out));
-    if (io->resid) IKB_CUDA(cudaMemcpyAsync(io->resid, st.resid, (size_t)B * sizeof(T), cudaMemcpyDeviceToHost, q->s_out));
-    IKB_CUDA(cudaEventRecord(sl.ev_done, q->s_out));
+    sl.hio = *io;
+    sl.dio = *io;
+    sl.dio.q0 = st.q0; sl.dio.targets = st.targets; sl.dio.q = st.q;
+    sl.dio.success = sl.success; sl.dio.iters = sl.iters; sl.dio.resid = st.resid;
     return IKB_OK;
 }
 
@@ -1048,46 +1106,41 @@ int ikb_dls_solve_batch_host(ikb_problem *p, int dtype, const ikb_dls_params *pr
 }
 
 /* ---- pipelined queue ---- */
-int ikb_queue_create(ikb_problem *p, int depth, ikb_queue **out) {
+int ikb_queue_create(ikb_problem *p, int depth, int merge, ikb_queue **out) {
     if (!p || !out) return fail(IKB_ERR_INVALID_ARG, "null argument");
     if (!p->finalized) return fail(IKB_ERR_NOT_FINALIZED, "call ikb_problem_finalize first");
-    if (depth < 1 || depth > kScratchSlots) return fail(IKB_ERR_INVALID_ARG, "queue depth must be between 1 and 8");
+    if (depth < 1 || depth > 16) return fail(IKB_ERR_INVALID_ARG, "queue depth must be between 1 and 16");
+    if (merge < 1 || merge > kMaxMerge || merge > depth) return fail(IKB_ERR_INVALID_ARG, "merge must be between 1 and min(depth, 8)");
     DeviceGuard g(p->device);
     ikb_queue *q = new ikb_queue;
     q->p = p;
     q->depth = depth;
+    q->merge = merge;
     q->slots.resize(depth);
     *out = q;  // the caller frees it also when creation fails half-way
-    {
-        const char *e = std::getenv("IKB_QUEUE_TRACE");
-        q->tracing = e && e[0] == '1';
-    }
-    // The TAIL stream outranks the BULK stream: when a bulk launch ends, the stragglers' CTAs (few, latency-bound) are
-    // placed first and the next bulk launch (persistent CTAs that take whole SMs) fills what is left -- the other way
-    // round the stragglers would wait for a free SM until the queue runs empty.
-    int prio_lo = 0, prio_hi = 0;
-    IKB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    IKB_CUDA(cudaStreamCreateWithFlags(&q->s_in, cudaStreamNonBlocking));
-    IKB_CUDA(cudaStreamCreateWithFlags(&q->s_out, cudaStreamNonBlocking));
-    IKB_CUDA(cudaStreamCreateWithPriority(&q->s_bulk, cudaStreamNonBlocking, prio_lo));
-    IKB_CUDA(cudaStreamCreateWithPriority(&q->s_tail, cudaStreamNonBlocking, prio_hi));
+    for (cudaStream_t *s : {&q->s_in, &q->s_comp, &q->s_out}) IKB_CUDA(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking));
     IKB_CUDA(cudaEventCreateWithFlags(&q->ev_user, cudaEventDisableTiming));
+    IKB_CUDA(cudaEventCreateWithFlags(&q->ev_comp, cudaEventDisableTiming));
+    IKB_CUDA(cudaMalloc(&q->d_seg, sizeof(SegTable<double>)));
     for (auto &sl : q->slots)
-        for (cudaEvent_t *e : {&sl.ev_in, &sl.ev_bulk, &sl.ev_mid, &sl.ev_done, &sl.ev_go}) IKB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        for (cudaEvent_t *e : {&sl.ev_in, &sl.ev_done}) IKB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     return IKB_OK;
 }
 
 void ikb_queue_free(ikb_queue *q) {
     if (!q) return;
     DeviceGuard g(q->p->device);
-    for (cudaStream_t s : {q->s_in, q->s_bulk, q->s_tail, q->s_out})
+    queue_flush(q);
+    for (cudaStream_t s : {q->s_in, q->s_comp, q->s_out})
         if (s) {
             cudaStreamSynchronize(s);
             cudaStreamDestroy(s);
         }
     if (q->ev_user) cudaEventDestroy(q->ev_user);
+    if (q->ev_comp) cudaEventDestroy(q->ev_comp);
+    cudaFree(q->d_seg);
     for (auto &sl : q->slots) {
-        for (cudaEvent_t e : {sl.ev_in, sl.ev_bulk, sl.ev_mid, sl.ev_done, sl.ev_go})
+        for (cudaEvent_t e : {sl.ev_in, sl.ev_done})
             if (e) cudaEventDestroy(e);
         cudaFree(sl.st64.q0); cudaFree(sl.st64.targets); cudaFree(sl.st64.q); cudaFree(sl.st64.resid);
         cudaFree(sl.st32.q0); cudaFree(sl.st32.targets); cudaFree(sl.st32.q); cudaFree(sl.st32.resid);
@@ -1096,33 +1149,20 @@ void ikb_queue_free(ikb_queue *q) {
     delete q;
 }
 
-static int queue_slot(ikb_queue *q, ikb_queue::Slot **sl) {
-    *sl = &q->slots[q->next % q->depth];
-    if ((*sl)->busy) {  // back-pressure: the slot's previous batch must have left the pipeline
-        IKB_CUDA(cudaEventSynchronize((*sl)->ev_done));
-        (*sl)->busy = false;
-    }
-    return IKB_OK;
-}
-
 int64_t ikb_queue_submit(ikb_queue *q, int dtype, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io, void *in_stream) {
     if (!q) return -fail(IKB_ERR_INVALID_ARG, "null queue");
     int rc = check_solve_args(q->p, dtype, prm, B, io);
     if (rc) return -rc;
     DeviceGuard g(q->p->device);
     ikb_queue::Slot *sl;
-    if ((rc = queue_slot(q, &sl))) return -rc;
+    if ((rc = queue_acquire(q, dtype, prm, &sl))) return -rc;
     // the inputs are ready in `in_stream` order (NULL = the legacy default stream) at this point
-    if (cudaEventRecord(q->ev_user, (cudaStream_t)in_stream) != cudaSuccess || cudaStreamWaitEvent(q->s_bulk, q->ev_user, 0) != cudaSuccess)
+    if (cudaEventRecord(q->ev_user, (cudaStream_t)in_stream) != cudaSuccess || cudaStreamWaitEvent(q->s_comp, q->ev_user, 0) != cudaSuccess)
         return -cuda_fail(cudaGetLastError(), "queue input dependency");
-    if (B > 0) {
-        rc = dtype == IKB_F64 ? queue_solve<double>(q, *sl, prm, B, io) : queue_solve<float>(q, *sl, prm, B, io);
-        if (rc) return -rc;
-    }
-    if (cudaEventRecord(sl->ev_done, q->s_tail) != cudaSuccess) return -cuda_fail(cudaGetLastError(), "cudaEventRecord");
-    sl->busy = true;
-    sl->ticket = q->next;
-    return q->next++;
+    sl->host = false;
+    sl->B = B;
+    sl->dio = *io;
+    return queue_commit(q, sl);
 }
 
 int64_t ikb_queue_submit_host(ikb_queue *q, int dtype, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io) {
@@ -1131,16 +1171,22 @@ int64_t ikb_queue_submit_host(ikb_queue *q, int dtype, const ikb_dls_params *prm
     if (rc) return -rc;
     DeviceGuard g(q->p->device);
     ikb_queue::Slot *sl;
-    if ((rc = queue_slot(q, &sl))) return -rc;
+    if ((rc = queue_acquire(q, dtype, prm, &sl))) return -rc;
+    sl->host = true;
+    sl->B = B;
     if (B > 0) {
-        rc = dtype == IKB_F64 ? queue_submit_host<double>(q, *sl, prm, B, io) : queue_submit_host<float>(q, *sl, prm, B, io);
+        rc = dtype == IKB_F64 ? queue_stage_host<double>(q, *sl, B, io) : queue_stage_host<float>(q, *sl, B, io);
         if (rc) return -rc;
-    } else if (cudaEventRecord(sl->ev_done, q->s_out) != cudaSuccess) {
+    } else if (cudaEventRecord(sl->ev_in, q->s_in) != cudaSuccess) {
         return -cuda_fail(cudaGetLastError(), "cudaEventRecord");
     }
-    sl->busy = true;
-    sl->ticket = q->next;
-    return q->next++;
+    return queue_commit(q, sl);
+}
+
+int ikb_queue_flush(ikb_queue *q) {
+    if (!q) return fail(IKB_ERR_INVALID_ARG, "null queue");
+    DeviceGuard g(q->p->device);
+    return queue_flush(q);
 }
 
 int ikb_queue_wait(ikb_queue *q, int64_t ticket) {
@@ -1148,6 +1194,8 @@ int ikb_queue_wait(ikb_queue *q, int64_t ticket) {
     ikb_queue::Slot &sl = q->slots[ticket % q->depth];
     if (sl.ticket != ticket) return IKB_OK;  // its slot has been reused: it left the pipeline long ago
     DeviceGuard g(q->p->device);
+    int rc;
+    if (sl.pending && (rc = queue_flush(q))) return rc;
     IKB_CUDA(cudaEventSynchronize(sl.ev_done));
     sl.busy = false;
     return IKB_OK;
@@ -1155,26 +1203,22 @@ int ikb_queue_wait(ikb_queue *q, int64_t ticket) {
 
 int ikb_queue_wait_on_stream(ikb_queue *q, int64_t ticket, void *cuda_stream) {
     if (!q || ticket < 0 || ticket >= q->next) return fail(IKB_ERR_INVALID_ARG, "unknown queue ticket");
-    if (q->slots[ticket % q->depth].ticket != ticket) return IKB_OK;
+    ikb_queue::Slot &sl = q->slots[ticket % q->depth];
+    if (sl.ticket != ticket) return IKB_OK;
     DeviceGuard g(q->p->device);
-    IKB_CUDA(cudaStreamWaitEvent((cudaStream_t)cuda_stream, q->slots[ticket % q->depth].ev_done, 0));
+    int rc;
+    if (sl.pending && (rc = queue_flush(q))) return rc;
+    IKB_CUDA(cudaStreamWaitEvent((cudaStream_t)cuda_stream, sl.ev_done, 0));
     return IKB_OK;
 }
 
 int ikb_queue_drain(ikb_queue *q) {
     if (!q) return fail(IKB_ERR_INVALID_ARG, "null queue");
     DeviceGuard g(q->p->device);
-    for (cudaStream_t s : {q->s_in, q->s_bulk, q->s_tail, q->s_out}) IKB_CUDA(cudaStreamSynchronize(s));
+    int rc = queue_flush(q);
+    if (rc) return rc;
+    for (cudaStream_t s : {q->s_in, q->s_comp, q->s_out}) IKB_CUDA(cudaStreamSynchronize(s));
     for (auto &sl : q->slots) sl.busy = false;
-    if (!q->trace.empty()) {
-        for (auto &x : q->trace) {
-            float ms = 0;
-            cudaEventElapsedTime(&ms, q->trace[0].second, x.second);
-            std::fprintf(stderr, "[ikb queue trace] %-16s %8.3f ms\n", x.first.c_str(), ms);
-            }
-        for (auto &x : q->trace) cudaEventDestroy(x.second);
-        q->trace.clear();
-    }
     return IKB_OK;
 }
 

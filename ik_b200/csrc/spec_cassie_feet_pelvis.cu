@@ -91,12 +91,7 @@ bool use_team(bool is_f64, bool resume) {
 
 template <typename T> int launch(const SpecHostConsts &hc, const SolveArgs<T> &a, int variant, long long n, int sms, cudaStream_t s,
                                  int bulk_roles) {
-    if (variant == SPEC_TAIL_SHARED && sizeof(T) == 8) {
-        const char *g = std::getenv("IKB_TAIL_GROUPS");
-        if (g && g[0] == '1') return launch_spec_tail<S3, T>(hc, a, n, sms, s);
-        return launch_spec_tail_g<S3, T, 2>(hc, a, n, sms, s);
-    }
-    if (variant == SPEC_TAIL || variant == SPEC_TAIL_SHARED) {
+    if (variant == SPEC_TAIL) {
         if (use_team(sizeof(T) == 8, a.resume != 0)) return launch_team<T>(team_consts<T>(hc), a, n, sms, s);
         return launch_spec_tail<S3, T>(hc, a, n, sms, s);
     }

@@ -17,9 +17,7 @@ struct SpecHostConsts {
 
 // BULK: throughput configuration (persistent, one CTA per SM).  TAIL: latency configuration (one 32-problem group per
 // CTA, more warp roles) -- used for the stragglers a BULK launch suspends and for batches too small to fill the GPU.
-// SPEC_TAIL_SHARED: the TAIL launch of the pipelined queue, which runs beside the next batch's BULK launch: packed onto as
-// few SMs as the latency allows (n = expected number of stragglers) instead of one group per SM.
-enum SpecVariant { SPEC_BULK = 0, SPEC_TAIL = 1, SPEC_TAIL_SHARED = 3 };
+enum SpecVariant { SPEC_BULK = 0, SPEC_TAIL = 1 };
 
 struct SpecializedKernel {
     const char *name;

@@ -168,22 +168,27 @@ int ikb_dls_solve(ikb_problem *p, const ikb_dls_params *params, const double *q0
  * The reference's only caller runs ik::dls once per control tick, one call after the other
  * (ik_ros/src/cassie.cpp:112-113 inside CassieIK::loop, :146-171).  A stream of BATCHES has the same shape, and one
  * batch alone cannot keep the GPU busy: the few problems that never converge run all max_iterations steps
- * (dls.cpp:14), a serial chain of ~0.7 ms during which most SMs idle.  A queue keeps `depth` batches in flight on
- * four internal streams (copy-in, BULK launch, TAIL launch, copy-out), so the straggler launch of batch k runs beside
- * the bulk launch of batch k+1 and -- with host buffers -- beside the PCIe copies of its neighbours.  Results are
- * those of ikb_dls_solve_batch, bit for bit.  One thread drives a queue; a problem may have several queues. */
+ * (dls.cpp:14), a serial chain of ~0.7 ms during which most SMs idle.  A queue keeps up to `depth` batches in flight
+ * on three internal streams (copy-in, compute, copy-out) and launches `merge` consecutive batches as ONE kernel pair,
+ * so the straggler chain is paid once per group and -- with host buffers -- the PCIe copies of one group run beside
+ * the kernels of its neighbours.  Batches of a group must share dtype and solver parameters (a change starts a new
+ * group).  Results are those of ikb_dls_solve_batch, bit for bit.  One thread drives a queue. */
 typedef struct ikb_queue ikb_queue;
-int ikb_queue_create(ikb_problem *p, int depth /* 1..8 batches in flight */, ikb_queue **out);
+int ikb_queue_create(ikb_problem *p, int depth /* 1..16 batches in flight */, int merge /* 1..min(depth, 8) */,
+                     ikb_queue **out);
 void ikb_queue_free(ikb_queue *q);
 /* DEVICE buffers (as ikb_dls_solve_batch).  The inputs must be complete in `in_stream` order at the time of the
  * call; the buffers of a batch must stay untouched until its ticket has been waited for.  Returns the batch's
- * ticket (>= 0) or minus an ikb_status.  Blocks only when all `depth` slots are still in flight. */
+ * ticket (>= 0) or minus an ikb_status.  Blocks only while the slot's previous batch is still in flight. */
 int64_t ikb_queue_submit(ikb_queue *q, int dtype, const ikb_dls_params *params, int64_t B, const ikb_batch_io *io,
                          void *in_stream);
 /* HOST buffers (as ikb_dls_solve_batch_host; pinned memory -- ikb_host_alloc -- for the copies to overlap). */
 int64_t ikb_queue_submit_host(ikb_queue *q, int dtype, const ikb_dls_params *params, int64_t B,
                               const ikb_batch_io *io);
-/* Block the host until the outputs of `ticket` are complete / make `cuda_stream` wait for them / wait for all. */
+/* Launch the batches submitted so far even if their group is not full. */
+int ikb_queue_flush(ikb_queue *q);
+/* Block the host until the outputs of `ticket` are complete / make `cuda_stream` wait for them / wait for all.
+ * Waiting for a batch whose group is still open launches the group first. */
 int ikb_queue_wait(ikb_queue *q, int64_t ticket);
 int ikb_queue_wait_on_stream(ikb_queue *q, int64_t ticket, void *cuda_stream);
 int ikb_queue_drain(ikb_queue *q);

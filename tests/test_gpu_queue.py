@@ -1,0 +1,134 @@
+"""GPU tests of the pipelined queue (ikb_queue_*): merged launches must give the results of the per-batch calls."""
+import numpy as np
+import pytest
+
+import ik_b200 as ik
+from ik_b200 import workloads as W
+from oracle import oracle as O
+from tests.common import make_workload, oracle_model, oracle_problem_like
+
+pytestmark = pytest.mark.gpu
+NT = 8
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    return torch
+
+
+@pytest.fixture(scope="module")
+def cassie():
+    pb = W.cassie_feet_pelvis_problem()
+    om = oracle_model("cassie")
+    return pb, om, oracle_problem_like(pb, om)
+
+
+def _dev(torch, a, dtype=None):
+    return torch.tensor(np.ascontiguousarray(a.T), device="cuda:0", dtype=dtype)
+
+
+def test_merged_large_batches_are_bit_identical_f64(cassie):
+    """Four two-launch batches of different sizes in one kernel pair: FP64 BULK and TAIL share their arithmetic, so the
+    merged launch reproduces ik.dls_batch bit for bit (and therefore the oracle to the parity bar)."""
+    torch = _torch()
+    pb, om, opb = cassie
+    pb.finalize(0)
+    sizes = [12000, 20000, 9600, 15000]
+    data = [make_workload(pb, om, B, seed=100 + i, standing=W.CASSIE_STANDING) for i, B in enumerate(sizes)]
+    dev = [(_dev(torch, q0), _dev(torch, tg)) for q0, tg, _ in data]
+    ref = [ik.dls_batch(pb, a, b) for a, b in dev]
+    torch.cuda.synchronize()
+    queue = ik.SolveQueue(pb, depth=8, merge=4)
+    got = [queue.submit(a, b) for a, b in dev]
+    for t, _ in got:
+        queue.wait(t)
+    for (t, out), r in zip(got, ref):
+        for k in ("q", "success", "iters", "resid"):
+            assert torch.equal(out[k], r[k]), k
+    # ... and the oracle, on the first batch
+    q_ref, ok_ref, it_ref, _ = O.dls_batch(opb, data[0][0], data[0][1], nthreads=NT)
+    ok = got[0][1]["success"].cpu().numpy().astype(bool)
+    assert np.array_equal(ok, ok_ref.astype(bool)) and np.array_equal(got[0][1]["iters"].cpu().numpy(), it_ref)
+    assert np.abs(got[0][1]["q"].cpu().numpy().T - q_ref)[ok].max() < 1e-6
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_merged_small_batches_match_per_batch_calls(cassie, dtype):
+    """Small batches: the merged group may take other kernels than a lone batch (team-per-problem vs thread-per-problem),
+    so flags and step counts are equal and q agrees to rounding (FP64) / to the FP32 bar."""
+    torch = _torch()
+    pb, om, opb = cassie
+    pb.finalize(0)
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    sizes = [700, 33, 4096, 1]
+    data = [make_workload(pb, om, B, seed=200 + i, standing=W.CASSIE_STANDING) for i, B in enumerate(sizes)]
+    dev = [(_dev(torch, q0, tdt), _dev(torch, tg, tdt)) for q0, tg, _ in data]
+    ref = [ik.dls_batch(pb, a, b) for a, b in dev]
+    torch.cuda.synchronize()
+    queue = ik.SolveQueue(pb, depth=4, merge=4)
+    got = [queue.submit(a, b) for a, b in dev]
+    queue.drain()
+    for (t, out), r in zip(got, ref):
+        ok = r["success"].bool()
+        if dtype == "f64":
+            assert torch.equal(out["success"], r["success"]) and torch.equal(out["iters"], r["iters"])
+            assert (out["q"] - r["q"]).abs()[:, ok].max() < 1e-9
+        else:
+            same = (out["success"] == r["success"]) & (out["iters"] == r["iters"])
+            assert same.float().mean() > 0.97
+            assert (out["q"] - r["q"]).abs()[:, ok & same].max() < 3e-3
+
+
+def test_host_mode_and_parameter_change(cassie):
+    """Host buffers (SoA and AoS), a parameter change in the middle of the stream (starts a new group), waiting for
+    tickets in any order, re-using a slot."""
+    torch = _torch()
+    pb, om, opb = cassie
+    pb.finalize(0)
+    B = 11000
+    q0, tg, _ = make_workload(pb, om, B, seed=300, standing=W.CASSIE_STANDING)
+    demo = ik.dls_parameters(max_iterations=200, step_length=0.1, damping=0.1)
+    ref_default = ik.dls_batch_host(pb, q0, tg, None, "f64", "aos")
+    ref_demo = ik.dls_batch_host(pb, q0, tg, demo, "f64", "aos")
+    queue = ik.SolveQueue(pb, depth=3, merge=3)
+    soa = (np.ascontiguousarray(q0.T), np.ascontiguousarray(tg.T))
+    jobs = []
+    for k in range(7):  # more batches than slots: submit blocks on the slot's previous occupant
+        prm = demo if k in (2, 3) else None
+        if k % 2:
+            jobs.append((queue.submit_host(soa[0], soa[1], prm, "f64", "soa"), "soa", prm))
+        else:
+            jobs.append((queue.submit_host(q0, tg, prm, "f64", "aos"), "aos", prm))
+    for (t, out), layout, prm in reversed(jobs):
+        queue.wait(t)
+        r = ref_demo if prm is not None else ref_default
+        q = out["q"].T if layout == "soa" else out["q"]
+        assert np.array_equal(q, r["q"]) and np.array_equal(out["success"], r["success"])
+        assert np.array_equal(out["iters"], r["iters"]) and np.array_equal(out["resid"], r["resid"])
+
+
+def test_queue_with_generic_kernel_and_empty_batch():
+    """A problem without a specialised kernel goes through the queue batch by batch (no merged launch); B = 0 is legal."""
+    torch = _torch()
+    m = ik.Model.builtin("ur5", free_flyer=False)
+    pb = ik.InverseKinematicsProblem(m)
+    pb.add_frame_task("tool", ik.FrameTask(m, "tool0", ik.KinematicType.Full))
+    pb.finalize(0)
+    assert pb.specialisation() is None
+    om = oracle_model("ur5", free_flyer=False)
+    q0, tg, _ = make_workload(pb, om, 300, seed=3, start="near")
+    a, b = _dev(torch, q0), _dev(torch, tg)
+    ref = ik.dls_batch(pb, a, b)
+    torch.cuda.synchronize()
+    queue = ik.SolveQueue(pb, depth=4, merge=2)
+    t0, o0 = queue.submit(a, b)
+    t1, o1 = queue.submit(a[:, :0].contiguous(), b[:, :0].contiguous())
+    t2, o2 = queue.submit(a, b)
+    queue.drain()
+    for o in (o0, o2):
+        for k in ("q", "success", "iters", "resid"):
+            assert torch.equal(o[k], ref[k])
+    assert o1["q"].shape[1] == 0
