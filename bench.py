@@ -7,17 +7,23 @@ Workload (config.workload): Cassie feet+pelvis IK (pelvis Full + LeftFootFront/R
 frame), library-default solver parameters (max_iterations 100, damping 1e-2, step 1.0), batch 65,536 seeded random
 reachable targets PER GPU (weak scaling: rank r solves problem indices [r*B, (r+1)*B)), FP64.
 
-A "step" = one batched ik::dls over one batch = TWO kernel launches (ikb_dls_solve_batch: the BULK launch suspends the
-few stragglers still unfinished when the ticket queue runs dry, the TAIL launch continues them in the latency
-configuration).  `value` = converged solves of all ranks / max-over-ranks device time with inputs already
-resident in HBM.  `e2e` = the same metric through the host-buffer
-C-ABI call (ikb_dls_solve_batch_host): pinned host inputs copied H2D, solve, results copied D2H, every step.
-`roofline` is the compute roofline of the solve (both launches of a step together -- they are one pass of the path):
-algorithmic FLOPs (F_iter = 9,360 per evaluation, (iterations+1) evaluations per problem) / event-timed
-duration of the step, against the FP64 (FP32) FMA-pipe
-peak measured in this run by ikb_measure_fma_peak (MEASURED_PEAKS.json carries no vector-pipe figure; the nominal
-37.2 / 74.4 TFLOP/s is printed beside it).  `cpu_baseline` = the restated reference CPU path (oracle/, "port":
-Pinocchio/Eigen are unavailable so the reference itself cannot be built) on this box's host cores, bounded sample.
+A "step" = one batched ik::dls over one batch of B problems.  The K timed steps go through the pipelined queue
+(ikb_queue_*, include/ikb200.h -- the API for a stream of batches): `--merge` consecutive batches (default 4), each with
+its own buffers, share ONE kernel pair -- the BULK launch suspends the few stragglers still unfinished when the ticket
+queue runs dry, the TAIL launch continues them in the latency configuration -- so the stragglers'
+serial chain (a problem that never converges runs all 100 steps, ~0.7 ms of mostly idle SMs) is paid once per group.
+`value` = converged solves of all ranks / max-over-ranks device time (CUDA events) with inputs already resident in HBM;
+`config.isolated_ms_per_batch` is the same K steps through the plain per-batch call (ikb_dls_solve_batch), one kernel
+pair per batch.  `e2e` = the same metric with HOST buffers through the queue's host entry point
+(ikb_queue_submit_host / ikb_queue_wait): every step's inputs are copied from pinned host memory, every step's results
+(q, success, iters, resid) are copied back and read; the copies of one group run beside the kernels of its neighbours.
+`e2e.isolated_ms_per_batch` is the blocking per-batch host call (ikb_dls_solve_batch_host).
+`roofline` is the compute roofline of the solve (all launches of the timed region -- they are one pass of the path per
+step): algorithmic FLOPs (F_iter = 9,360 per evaluation, (iterations+1) evaluations per problem) / event-
+timed device time per step, against the FP64 (FP32) FMA-pipe peak measured in this run by ikb_measure_fma_peak
+(MEASURED_PEAKS.json carries no vector-pipe figure; the nominal 37.2 / 74.4 TFLOP/s is printed beside it).
+`cpu_baseline` = the restated reference CPU path (oracle/, "port": Pinocchio/Eigen are unavailable so the reference
+itself cannot be built) on this box's host cores, bounded sample.
 
 --impl reference times that CPU path alone (rank 0 only under torchrun).
 """

@@ -32,6 +32,8 @@ template <typename T> struct alignas(16) DevProblem {
     int32_t pad_[4];     // keeps sizeof a multiple of 16 for the bulk copy
 };
 
+constexpr int kMaxSegments = 8;
+
 // One batch of a MERGED launch (pipelined queue, ikb_queue_*): problems [begin, begin + its B) of the launch live in
 // these buffers (same meaning as the fields of SolveArgs / ikb_batch_io).
 template <typename T> struct BatchSeg {
@@ -64,10 +66,11 @@ template <typename T> struct SolveArgs {
     unsigned int *list;               // suspended problem indices
     unsigned long long *list_count;   // number of entries in `list` (zeroed before the BULK launch)
     int *iters_ws;                    // step counts of suspended problems (the caller's `iters` or scratch)
-    // Merged launch: `nseg` batches, sorted by `begin`, B = their total size; q0 ... resid above are then unused and
-    // iters_ws / list are indexed by the launch-wide problem index.  nullptr: one batch, described by the fields above.
-    const BatchSeg<T> *seg;
+    // Merged launch: `nseg` > 0 batches, sorted by `begin`, B = their total size; q0 ... resid above are then unused and
+    // iters_ws / list are indexed by the launch-wide problem index.  Unused entries have begin = LLONG_MAX.  The table
+    // travels in the kernel parameters: the lookup is a handful of constant-bank compares, no memory traffic.
     int nseg;
+    BatchSeg<T> seg[kMaxSegments];
 };
 
 // Buffers of ONE problem, resolved from its launch-wide index (all pointers already point at the problem).
@@ -80,21 +83,17 @@ template <typename T> struct ProblemIO {
     T *resid;
 };
 #if defined(__CUDACC__)
-// SEG = false: one batch, plain pointer arithmetic on the launch arguments (inlined).
-// SEG = true : merged launch, segment lookup.  Out of line on purpose: it runs once per problem load / store, and the
-// solver bodies are instruction-fetch bound (their straight-line code is streamed from L2 every iteration).
-template <typename T> __device__ __noinline__ ProblemIO<T> problem_io_seg(const SolveArgs<T> &a, long long b) {
-    int s = 0;
-    for (int i = 1; i < a.nseg; ++i)
-        if (b >= a.seg[i].begin) s = i;
-    const BatchSeg<T> &g = a.seg[s];
-    const long long l = b - g.begin;
-    return {g.q0 + l * g.q0_bs, g.q0_es, g.targets + l * g.tg_bs, g.tg_es, g.q + l * g.q_bs, g.q_es,
-            g.success ? g.success + l : nullptr, g.iters ? g.iters + l : nullptr, g.resid ? g.resid + l : nullptr};
-}
+// SEG = false: one batch, plain pointer arithmetic on the launch arguments.
+// SEG = true : merged launch, segment lookup in the (constant-bank) kernel parameters.
 template <bool SEG, typename T> __device__ __forceinline__ ProblemIO<T> problem_io(const SolveArgs<T> &a, long long b) {
     if constexpr (SEG) {
-        return problem_io_seg(a, b);
+        int s = 0;
+#pragma unroll
+        for (int i = 1; i < kMaxSegments; ++i) s += b >= a.seg[i].begin ? 1 : 0;
+        const BatchSeg<T> &g = a.seg[s];
+        const long long l = b - g.begin;
+        return {g.q0 + l * g.q0_bs, g.q0_es, g.targets + l * g.tg_bs, g.tg_es, g.q + l * g.q_bs, g.q_es,
+                g.success ? g.success + l : nullptr, g.iters ? g.iters + l : nullptr, g.resid ? g.resid + l : nullptr};
     } else {
         return {a.q0 + b * a.q0_bs, a.q0_es, a.targets + b * a.tg_bs, a.tg_es, a.q + b * a.q_bs, a.q_es,
                 a.success ? a.success + b : nullptr, a.iters ? a.iters + b : nullptr, a.resid ? a.resid + b : nullptr};

@@ -263,7 +263,7 @@ int launch_spec_cfg_seg(const SpecHostConsts &hc, const SolveArgs<T> &a, long lo
 
 template <class Spec, typename T, int GROUPS, int MINB>
 int launch_spec_cfg(const SpecHostConsts &hc, const SolveArgs<T> &a, long long ctas, cudaStream_t s) {
-    return a.seg ? launch_spec_cfg_seg<Spec, T, GROUPS, MINB, true>(hc, a, ctas, s)
+    return a.nseg > 0 ? launch_spec_cfg_seg<Spec, T, GROUPS, MINB, true>(hc, a, ctas, s)
                  : launch_spec_cfg_seg<Spec, T, GROUPS, MINB, false>(hc, a, ctas, s);
 }
 

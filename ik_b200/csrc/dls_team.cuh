@@ -410,7 +410,7 @@ template <typename T, bool SEG> int launch_team_seg(const TeamConsts<T> &c, cons
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 template <typename T> int launch_team(const TeamConsts<T> &c, const SolveArgs<T> &a, long long n, int sm_count, cudaStream_t s) {
-    return a.seg ? launch_team_seg<T, true>(c, a, n, sm_count, s) : launch_team_seg<T, false>(c, a, n, sm_count, s);
+    return a.nseg > 0 ? launch_team_seg<T, true>(c, a, n, sm_count, s) : launch_team_seg<T, false>(c, a, n, sm_count, s);
 }
 #endif  // __CUDACC__
 

@@ -213,7 +213,7 @@ bool two_phase(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, int *
 
 // Merged launch of the pipelined queue (ikb_queue_*): `nseg` batches described by a device-resident table.
 template <typename T> struct Merged {
-    const BatchSeg<T> *d_seg;
+    const BatchSeg<T> *seg;  // host array, `nseg` entries sorted by begin
     int nseg;
 };
 
@@ -228,12 +228,14 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
         a.success = io->success;
         a.iters = io->iters;
         a.resid = (T *)io->resid;
-        a.seg = nullptr;
         a.nseg = 0;
     } else {
         if (!p->spec || prm->max_iterations <= 0) return fail(IKB_ERR_INVALID_ARG, "internal: merged launch on a problem without a specialised kernel");
-        a.seg = merged->d_seg;
         a.nseg = merged->nseg;
+        for (int i = 0; i < kMaxSegments; ++i) {
+            if (i < merged->nseg) a.seg[i] = merged->seg[i];
+            else a.seg[i].begin = LLONG_MAX;
+        }
     }
     a.B = B;
     a.max_iterations = prm->max_iterations;
@@ -517,17 +519,10 @@ struct ikb_queue {
     int open_dtype = -1;
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
     cudaEvent_t ev_user = nullptr, ev_comp = nullptr;
-    void *d_seg = nullptr;        // segment table of the merged launch in flight (reused in s_comp order)
     int64_t next = 0;
 };
 namespace {
-constexpr int kMaxMerge = 8;
-template <typename T> struct SegTable {
-    BatchSeg<T> e[kMaxMerge];
-};
-template <typename T> __global__ void upload_seg_kernel(const __grid_constant__ SegTable<T> t, BatchSeg<T> *dst, int n) {
-    if ((int)threadIdx.x < n) dst[threadIdx.x] = t.e[threadIdx.x];
-}
+constexpr int kMaxMerge = kMaxSegments;
 
 template <typename T> Staging<T> &slot_staging(ikb_queue::Slot &sl);
 template <> Staging<double> &slot_staging<double>(ikb_queue::Slot &sl) { return sl.st64; }
@@ -556,20 +551,18 @@ template <typename T> int queue_flush_t(ikb_queue *q) {
     for (int i : q->open)
         if (q->slots[i].host) IKB_CUDA(cudaStreamWaitEvent(q->s_comp, q->slots[i].ev_in, 0));
     if (n >= 2 && q->p->spec && q->open_prm.max_iterations > 0) {
-        SegTable<T> tab{};
+        BatchSeg<T> tab[kMaxSegments];
         long long total = 0;
         for (int k = 0; k < n; ++k) {
             const ikb_queue::Slot &sl = q->slots[q->open[k]];
             const ikb_batch_io &d = sl.dio;
-            tab.e[k] = BatchSeg<T>{(const T *)d.q0, d.q0_elem_stride, d.q0_batch_stride, (const T *)d.targets, d.targets_elem_stride,
+            tab[k] = BatchSeg<T>{(const T *)d.q0, d.q0_elem_stride, d.q0_batch_stride, (const T *)d.targets, d.targets_elem_stride,
                                    d.targets_batch_stride, (T *)d.q, d.q_elem_stride, d.q_batch_stride, d.success, d.iters,
                                    (T *)d.resid, total};
             total += sl.B;
         }
-        upload_seg_kernel<T><<<1, kMaxMerge, 0, q->s_comp>>>(tab, (BatchSeg<T> *)q->d_seg, n);
-        const Merged<T> m{(const BatchSeg<T> *)q->d_seg, n};
+        const Merged<T> m{tab, n};
         if ((rc = launch_solve<T>(q->p, &q->open_prm, total, nullptr, q->s_comp, nullptr, &m))) return rc;
-        g_launches.fetch_add(1);
     } else {
         for (int i : q->open) {
             ikb_queue::Slot &sl = q->slots[i];
@@ -1121,7 +1114,6 @@ int ikb_queue_create(ikb_problem *p, int depth, int merge, ikb_queue **out) {
     for (cudaStream_t *s : {&q->s_in, &q->s_comp, &q->s_out}) IKB_CUDA(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking));
     IKB_CUDA(cudaEventCreateWithFlags(&q->ev_user, cudaEventDisableTiming));
     IKB_CUDA(cudaEventCreateWithFlags(&q->ev_comp, cudaEventDisableTiming));
-    IKB_CUDA(cudaMalloc(&q->d_seg, sizeof(SegTable<double>)));
     for (auto &sl : q->slots)
         for (cudaEvent_t *e : {&sl.ev_in, &sl.ev_done}) IKB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     return IKB_OK;
@@ -1138,7 +1130,6 @@ void ikb_queue_free(ikb_queue *q) {
         }
     if (q->ev_user) cudaEventDestroy(q->ev_user);
     if (q->ev_comp) cudaEventDestroy(q->ev_comp);
-    cudaFree(q->d_seg);
     for (auto &sl : q->slots) {
         for (cudaEvent_t e : {sl.ev_in, sl.ev_done})
             if (e) cudaEventDestroy(e);
