@@ -222,14 +222,14 @@ template <class Spec> bool spec_matches(const HostProblem &hp) {
             if (!same_values(m.axis[j].data(), pl + 15 * j + 12, 3)) return false;
     }
     // tasks must already be in stacked order (the generated code has no notion of insertion order)
-    const SE3d ident = se3_identity();
     for (int t = 0; t < Spec::NTASKS; ++t) {
         const HostTask &ht = hp.tasks[t];
-        if (ht.kind != IKB_TASK_FRAME || ht.type != Spec::sig_task_type()[t] || ht.priority != Spec::sig_task_priority()[t])
-            return false;
+        if (ht.kind != (Spec::sig_task_kind()[t] ? IKB_TASK_ALIGN_AXIS : IKB_TASK_FRAME)) return false;
+        if (ht.type != Spec::sig_task_type()[t] || ht.priority != Spec::sig_task_priority()[t]) return false;  // kinematic type / axis
         if (t > 0 && ht.priority < hp.tasks[t - 1].priority) return false;
-        // reference frame must coincide with `universe`
-        if (m.frame_parent[ht.ref] != 0 || m.frame_placement[ht.ref] != ident) return false;
+        // the reference frame (`universe` or a moving frame) and the task frame must sit where the generator saw them
+        if (m.frame_parent[ht.ref] != Spec::sig_task_ref_joint()[t]) return false;
+        if (!same_values(m.frame_placement[ht.ref].data(), Spec::sig_task_ref_placement() + 12 * t, 12)) return false;
         if (m.frame_parent[ht.frame] != Spec::sig_task_joint()[t]) return false;
         if (!same_values(m.frame_placement[ht.frame].data(), Spec::sig_task_placement() + 12 * t, 12)) return false;
     }

@@ -10,9 +10,10 @@ namespace ikb {
 extern const SpecializedKernel kSpecCassieFeetPelvis;
 extern const SpecializedKernel kSpecManipulatorTool;
 extern const SpecializedKernel kSpecHumanoidLimbs;
+extern const SpecializedKernel kSpecCassieDemo;
 
 namespace {
-const SpecializedKernel *const kRegistry[] = {&kSpecCassieFeetPelvis, &kSpecManipulatorTool, &kSpecHumanoidLimbs, nullptr};
+const SpecializedKernel *const kRegistry[] = {&kSpecCassieFeetPelvis, &kSpecManipulatorTool, &kSpecHumanoidLimbs, &kSpecCassieDemo, nullptr};
 }
 
 const SpecializedKernel *const *specialized_registry() { return kRegistry; }

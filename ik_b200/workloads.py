@@ -9,7 +9,7 @@ translation (ik_ros/src/cassie.cpp:95-96).  The initial guess is the SRDF standi
 """
 import numpy as np
 
-from .api import FrameTask, InverseKinematicsProblem, KinematicType, Model
+from .api import AlignAxisTask, AlignAxisType, FrameTask, InverseKinematicsProblem, KinematicType, Model
 
 # cassie-description/srdf/cassie.srdf:22-39 (group_state "default"), in model joint order
 CASSIE_STANDING = [0.0045, 0.0, 0.4973, -1.1997, 0.0, 1.4267, 0.0, -1.5968,
@@ -122,30 +122,59 @@ def manipulator_problem(model=None):
     return pb
 
 
+def cassie_demo_problem(model=None):
+    """The task set of the reference's own demo (ik_ros/src/cassie.cpp:43-81): LeftFootFront Position relative to the
+    moving ``pelvis`` frame, pelvis Full in ``universe``, AlignAxisTask on the foot's y axis.  10 task rows."""
+    model = model or cassie_model()
+    pb = InverseKinematicsProblem(model, 1)
+    pb.add_frame_task("fl", FrameTask(model, "LeftFootFront", KinematicType.Position, "pelvis"))
+    pb.add_frame_task("pelvis", FrameTask(model, "pelvis", KinematicType.Full))
+    pb.add_align_axis_task("align", AlignAxisTask(model, "LeftFootFront", AlignAxisType.AxisY))
+    return pb
+
+
 def frame_task_list(problem):
     return [(t, problem.target_offset(t)) for _, t, _ in problem._tasks if isinstance(t, FrameTask)]
 
 
+def _rel(Mr, Mf):
+    """Mr^-1 * Mf for [B, 12] placements (R row-major 9 + p 3)."""
+    Rr, Rf = Mr[:, :9].reshape(-1, 3, 3), Mf[:, :9].reshape(-1, 3, 3)
+    R = np.einsum("bji,bjk->bik", Rr, Rf)
+    p = np.einsum("bji,bj->bi", Rr, Mf[:, 9:12] - Mr[:, 9:12])
+    return np.concatenate([R.reshape(-1, 9), p], axis=1)
+
+
 def targets_from_frame_poses(problem, poses):
-    """poses: dict frame name -> [B, 12] world placements at q*.  Returns targets [B, tsz] (AoS)."""
+    """poses: dict frame name -> [B, 12] world placements at q* (task frames and their reference frames).  Returns targets
+    [B, tsz] (AoS) that q* satisfies exactly: frame tasks get the frame's placement relative to the reference frame,
+    align-axis tasks the frame's own axis (scaled by 2: the task normalises it, frame.hpp:264)."""
     B = next(iter(poses.values())).shape[0]
     tg = np.zeros((B, problem.target_size))
-    for t, off in frame_task_list(problem):
-        M = poses[t.frame]
-        if t.type == KinematicType.Full:
-            tg[:, off:off + 12] = M
-        else:
-            tg[:, off:off + 9] = np.eye(3).reshape(-1)
-            if t.type == KinematicType.Position:
-                tg[:, off + 9:off + 12] = M[:, 9:12]
+    for _, t, _ in problem._tasks:
+        off = problem.target_offset(t)
+        if isinstance(t, FrameTask):
+            M = poses[t.frame] if t.reference_frame == "universe" else _rel(poses[t.reference_frame], poses[t.frame])
+            if t.type == KinematicType.Full:
+                tg[:, off:off + 12] = M
             else:
-                tg[:, off:off + 9] = M[:, :9]
+                tg[:, off:off + 9] = np.eye(3).reshape(-1)
+                if t.type == KinematicType.Position:
+                    tg[:, off + 9:off + 12] = M[:, 9:12]
+                else:
+                    tg[:, off:off + 9] = M[:, :9]
+        elif isinstance(t, AlignAxisTask):
+            M = poses[t.frame] if t.reference_frame == "universe" else _rel(poses[t.reference_frame], poses[t.frame])
+            tg[:, off:off + 3] = 2.0 * M[:, :9].reshape(-1, 3, 3)[:, :, int(t.axis)]
     return tg
 
 
 def task_frames(problem):
+    """Frames whose placements targets_from_frame_poses needs."""
     names = []
-    for t, _ in frame_task_list(problem):
-        if t.frame not in names:
-            names.append(t.frame)
+    for _, t, _ in problem._tasks:
+        if isinstance(t, (FrameTask, AlignAxisTask)):
+            for n in (t.frame, t.reference_frame):
+                if n != "universe" and n not in names:
+                    names.append(n)
     return names

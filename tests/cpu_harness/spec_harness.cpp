@@ -11,6 +11,7 @@
 #include "../../ik_b200/csrc/gen/cassie_feet_pelvis_w2.cuh"
 #include "../../ik_b200/csrc/gen/humanoid_limbs.cuh"
 #include "../../ik_b200/csrc/gen/manipulator_tool.cuh"
+#include "../../ik_b200/csrc/gen/cassie_demo.cuh"
 
 using namespace ikb;
 
@@ -100,3 +101,4 @@ IKB_SPEC_EXPORT(h_spec_cassie_feet_pelvis_w1, SpecCassieFeetPelvisW1)
 IKB_SPEC_EXPORT(h_spec_cassie_feet_pelvis_w2, SpecCassieFeetPelvisW2)
 IKB_SPEC_EXPORT(h_spec_manipulator_tool, SpecManipulatorTool)
 IKB_SPEC_EXPORT(h_spec_humanoid_limbs, SpecHumanoidLimbs)
+IKB_SPEC_EXPORT(h_spec_cassie_demo, SpecCassieDemo)

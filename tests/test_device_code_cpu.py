@@ -114,7 +114,8 @@ CASES = [("cassie_feet_pelvis", "cassie", True, W.cassie_feet_pelvis_problem, W.
          ("cassie_feet_pelvis_w1", "cassie", True, W.cassie_feet_pelvis_problem, W.CASSIE_STANDING),   # 1 role, legs interleaved
          ("cassie_feet_pelvis_w2", "cassie", True, W.cassie_feet_pelvis_problem, W.CASSIE_STANDING),   # 2 roles
          ("manipulator_tool", "manipulator", False, W.manipulator_problem, "near"),
-         ("humanoid_limbs", "humanoid", True, W.humanoid_problem, "near")]                              # 5 roles, 30 rows
+         ("humanoid_limbs", "humanoid", True, W.humanoid_problem, "near"),                              # 5 roles, 30 rows
+         ("cassie_demo", "cassie", True, W.cassie_demo_problem, W.CASSIE_STANDING)]   # moving reference frame + align-axis task
 
 
 def _workload(pb, om, B, standing):
@@ -186,6 +187,19 @@ def test_specialisation_matching_is_exact():
     pb = W.cassie_feet_pelvis_problem()
     pb.get_frame_task("fl").weighting()[:] = [2.0, 1.0, 0.5]
     assert pb.specialisation() == "cassie_feet_pelvis"
+    # the reference demo's task set (moving reference frame + align-axis task) has its own fast path ...
+    assert W.cassie_demo_problem().specialisation() == "cassie_demo"
+    # ... for exactly that reference frame and axis
+    pb = ik.InverseKinematicsProblem(m, 1)
+    pb.add_frame_task("fl", ik.FrameTask(m, "LeftFootFront", ik.KinematicType.Position, "pelvis"))
+    pb.add_frame_task("pelvis", ik.FrameTask(m, "pelvis", ik.KinematicType.Full))
+    pb.add_align_axis_task("align", ik.AlignAxisTask(m, "LeftFootFront", ik.AlignAxisType.AxisZ))
+    assert pb.specialisation() is None
+    pb = ik.InverseKinematicsProblem(m, 1)
+    pb.add_frame_task("fl", ik.FrameTask(m, "LeftFootFront", ik.KinematicType.Position, "VectorNav"))
+    pb.add_frame_task("pelvis", ik.FrameTask(m, "pelvis", ik.KinematicType.Full))
+    pb.add_align_axis_task("align", ik.AlignAxisTask(m, "LeftFootFront", ik.AlignAxisType.AxisY))
+    assert pb.specialisation() is None
     # the fixed-base Cassie is a different tree
     mf = ik.Model.builtin("cassie", free_flyer=False)
     pb = ik.InverseKinematicsProblem(mf, 0)

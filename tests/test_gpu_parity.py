@@ -144,6 +144,38 @@ def test_cassie_f64_demo_params(kernel_path):
     _compare("cassie f64 demo params", _solve_gpu(pb, q0, tg, prm), ref, 1e-6)
 
 
+@pytest.mark.parametrize("params", ["defaults", "demo"])
+@pytest.mark.parametrize("B", [1, 700, 24000])
+def test_cassie_demo_task_set(B, params, kernel_path):
+    """the reference demo's own task set (cassie.cpp:43-81) -- foot Position relative to the MOVING
+    pelvis frame (whose motion compute_jacobian does not differentiate, frame.hpp:169-181), pelvis Full, AlignAxisTask --
+    on its specialised kernel (one launch and, for 24 000, BULK + TAIL) and on the generic one."""
+    pb = W.cassie_demo_problem()
+    _check_path(pb, kernel_path, "cassie_demo")
+    if kernel_path == "generic" and B > 1000:
+        pytest.skip("generic kernel: covered at the smaller sizes")
+    om = oracle_model("cassie")
+    opb = oracle_problem_like(pb, om)
+    q0, tg, _ = make_workload(pb, om, B, seed=31, standing=W.CASSIE_STANDING)
+    if params == "defaults":
+        prm, oprm = None, O.params()
+    else:
+        prm, oprm = ik.dls_parameters(max_iterations=200, step_length=0.1, damping=0.1), O.params(200, 0.1, 0.1)
+    ref = O.dls_batch(opb, q0, tg, oprm, nthreads=NT)
+    gpu = _solve_gpu(pb, q0, tg, prm)
+    # Flags and step counts exactly.  q: 1e-6 rad on every problem that converges within half the iteration budget.  The
+    # few that need 70-100 steps crawl along an ill-conditioned valley (the moving reference frame is not differentiated,
+    # so the iteration is not a Gauss-Newton step there) and amplify rounding: the generic and the specialised kernel and
+    # the oracle differ pairwise by up to 1e-5 rad on the same ~0.1 % of problems (tools/demo_diff.py) -- bar 1e-4.
+    _compare("cassie demo tasks %s B=%d" % (params, B), gpu, ref, 1e-4, min_same_frac=0.95,  # ~3 % never converge
+             converged_only=True)
+    q, ok, it, _ = gpu
+    q_ref, ok_ref, it_ref, _ = ref
+    fast = ok & (it_ref <= oprm.max_iterations // 2)
+    assert np.abs(q[fast] - q_ref[fast]).max() < 1e-6
+    assert (np.abs(q[ok] - q_ref[ok]).max(axis=1) < 1e-6).mean() > 0.998
+
+
 def test_cassie_f32_defaults():
     """FP32 instantiation against the FP64 oracle.  The discrete stop decision may differ on a few problems (SURVEY 7
     'FP32 parity of the discrete stop decision'); where it agrees the bar is 1e-4 rad.  Measured: median 2e-6, 99th

@@ -166,20 +166,31 @@ class Generator:
             raise ValueError("spec tasks must be listed in stacked (priority) order")
         for t in spec["tasks"]:
             f = self.frames[t["frame"]]
-            ktype = {"position": POSITION, "orientation": ORIENTATION, "full": FULL}[t["type"]]
-            dim = 6 if ktype == FULL else 3
+            kind = t.get("kind", "frame")
+            if kind == "frame":
+                ktype = {"position": POSITION, "orientation": ORIENTATION, "full": FULL}[t["type"]]
+                dim = 6 if ktype == FULL else 3
+                tsize = 12
+            elif kind == "align":  # AlignAxisTask (frame.hpp:210-319): one row, target = the axis to align with (3 scalars)
+                ktype = {"x": 0, "y": 1, "z": 2}[t["axis"]]
+                dim = 1
+                tsize = 3
+            else:
+                raise ValueError("unsupported task kind %r (PostureTask runs on the generic kernel)" % kind)
+            ref = self.frames[t.get("reference", "universe")]
             chain = []
             j = f["parent"]
             while j > 0:
                 chain.append(j)
                 j = self.joints[j]["parent"]
             chain.reverse()
-            self.tasks.append(dict(frame=f, ktype=ktype, dim=dim, row=row, toff=toff, chain=chain, name=t["frame"],
+            self.tasks.append(dict(frame=f, kind=kind, ktype=ktype, dim=dim, row=row, toff=toff, tsize=tsize, chain=chain,
+                                   name=t["frame"], ref=ref, ref_name=t.get("reference", "universe"),
                                    priority=int(t.get("priority", 0))))
             if int(t.get("priority", 0)) == 0:
                 self.rows_p0 += dim
             row += dim
-            toff += 12
+            toff += tsize
         self.rows = row
         self.tsz = toff
         self.slots = {}  # (row, col) -> slot index
@@ -293,28 +304,48 @@ class Generator:
                 world.update(wk)
         return E.lines
 
+    def frame_world(self, E, f, world, hint):
+        """World placement (R[9], p[3]) of model frame f = placement of its parent joint times the frame placement."""
+        jf = f["parent"]
+        if jf > 0:
+            w = self.fk_joint(E, jf, world)
+            jR, jp = w["R"], w["p"]
+        else:
+            jR, jp = [1.0, 0, 0, 0, 1.0, 0, 0, 0, 1.0], [0.0, 0.0, 0.0]
+        FP = f["placement"]
+        return matmul(E, jR, FP[:9], "R" + hint), matvec(E, jR, FP[9:], "p" + hint, add=jp)
+
+    def is_universe(self, f):
+        return f["parent"] == 0 and f["placement"] == [1.0, 0, 0, 0, 1.0, 0, 0, 0, 1.0, 0, 0, 0]
+
     def gen_task(self, E, ti, world):
         """Error rows and Jacobian non-zeros of task ti (FK of its chain memoised in `world`)."""
+        if self.tasks[ti]["kind"] == "align":
+            return self.gen_align_task(E, ti, world)
         if True:
             task = self.tasks[ti]
             f = task["frame"]
-            E.comment("==== task %d: frame %s, %s ====" % (ti, task["name"], ["Position", "Orientation", "Full"][task["ktype"]]))
-            jf = f["parent"]
-            if jf > 0:
-                w = self.fk_joint(E, jf, world)
-                # make sure every joint of the chain is emitted (memoised)
-                jR, jp = w["R"], w["p"]
-            else:
-                jR, jp = [1.0, 0, 0, 0, 1.0, 0, 0, 0, 1.0], [0.0, 0.0, 0.0]
+            E.comment("==== task %d: frame %s, %s, reference %s ====" % (ti, task["name"], ["Position", "Orientation", "Full"][task["ktype"]],
+                                                                        task["ref_name"]))
             FP = f["placement"]
             ident = FP == [1.0, 0, 0, 0, 1.0, 0, 0, 0, 1.0, 0, 0, 0]
-            Rf = matmul(E, jR, FP[:9], "Rf")
-            pf = matvec(E, jR, FP[9:], "pf", add=jp)
+            Rf, pf = self.frame_world(E, f, world, "f")
             n = ti
             toff = task["toff"]
             E.raw("T Rt%d[9], pt%d[3];" % (n, n))
-            E.raw("for (int k = 0; k < 9; ++k) Rt%d[k] = tg[%d + k];" % (n, toff))
-            E.raw("for (int k = 0; k < 3; ++k) pt%d[k] = tg[%d + k];" % (n, toff + 9))
+            if self.is_universe(task["ref"]):
+                E.raw("for (int k = 0; k < 9; ++k) Rt%d[k] = tg[%d + k];" % (n, toff))
+                E.raw("for (int k = 0; k < 3; ++k) pt%d[k] = tg[%d + k];" % (n, toff + 9))
+            else:
+                # oMt = oMr * target (frame.hpp:46-47).  The reference frame moves with q but compute_jacobian does not
+                # differentiate it (frame.hpp:169-181, SURVEY 8a note) -- neither does this code.
+                Rr, pr = self.frame_world(E, task["ref"], world, "r")
+                arr(E, "Rr%d" % n, Rr)
+                arr(E, "pr%d" % n, pr)
+                E.raw("T Rg%d[9], pg%d[3];" % (n, n))
+                E.raw("for (int k = 0; k < 9; ++k) Rg%d[k] = tg[%d + k];" % (n, toff))
+                E.raw("for (int k = 0; k < 3; ++k) pg%d[k] = tg[%d + k];" % (n, toff + 9))
+                E.raw("se3_mul(Rr%d, pr%d, Rg%d, pg%d, Rt%d, pt%d);" % (n, n, n, n, n, n))
             arr(E, "Rf%d" % n, Rf)
             arr(E, "pf%d" % n, pf)
             # fMt = oMf^-1 * oMt  (frame.hpp:48-50, universe reference => oMt = target)
@@ -401,6 +432,47 @@ class Generator:
                         m1z = matvec(E, M1, w["z"], "m1z")
                         for i in range(3):
                             store(row + i, iv, neg(E, m1z[i]))
+
+    def gen_align_task(self, E, ti, world):
+        """AlignAxisTask (frame.hpp:246-299): e = 1 - r . t^,  J = -(r x t^)^T R_rMf Jf_LOCAL.bottomRows(3), with r the
+        aligned axis of the frame expressed in the reference frame and t^ the normalised target."""
+        task = self.tasks[ti]
+        f = task["frame"]
+        n, toff, row, ax = ti, task["toff"], task["row"], task["ktype"]
+        E.comment("==== task %d: align axis %s of frame %s, reference %s ====" % (ti, "xyz"[ax], task["name"], task["ref_name"]))
+        Rf, pf = self.frame_world(E, f, world, "f")
+        arr(E, "Rf%d" % n, Rf)
+        if self.is_universe(task["ref"]):
+            E.raw("T Rm%d[9];" % n)
+            E.raw("for (int k = 0; k < 9; ++k) Rm%d[k] = Rf%d[k];" % (n, n))
+        else:
+            Rr, _ = self.frame_world(E, task["ref"], world, "r")
+            arr(E, "Rr%d" % n, Rr)
+            E.raw("T Rm%d[9];" % n)
+            E.raw("mat3T_mul(Rr%d, Rf%d, Rm%d);  // rotation of rMf = oMr^-1 oMf" % (n, n, n))
+        E.raw("const T rv%d[3] = {Rm%d[%d], Rm%d[%d], Rm%d[%d]};" % (n, n, ax, n, 3 + ax, n, 6 + ax))
+        E.raw("T tn%d[3] = {tg[%d], tg[%d], tg[%d]};" % (n, toff, toff + 1, toff + 2))
+        E.raw("const T nn%d = sqrt_(dot3(tn%d, tn%d));" % (n, n, n))
+        E.raw("for (int k = 0; k < 3; ++k) tn%d[k] = tn%d[k] / nn%d;  // target.normalized()" % (n, n, n))
+        E.raw("sE.set(%d, c.weight[%d] * (T(1) - dot3(rv%d, tn%d)));" % (row, row, n, n))
+        E.raw("T rxt%d[3], r3%d[3], u%d[3];" % (n, n, n))
+        E.raw("cross3(rv%d, tn%d, rxt%d);" % (n, n, n))
+        E.raw("rotT_vec(Rm%d, rxt%d, r3%d);   // (r x t)^T R_rMf" % (n, n, n))
+        E.raw("rot_vec(Rf%d, r3%d, u%d);      // ... times Rf^T w_j for every column: (Rf r3) . w_j" % (n, n, n))
+        u = ["u%d[%d]" % (n, k) for k in range(3)]
+        for j in task["chain"]:
+            w = world[j] if j in world else self.fk_joint(E, j, world)
+            jt = self.joints[j]
+            iv = jt["idx_v"]
+            if jt["type"] == J_FF:
+                for k in range(3):  # angular columns only: world column [p x R e_k; R e_k]
+                    rk = [w["R"][k], w["R"][3 + k], w["R"][6 + k]]
+                    d = sop(E, [(u[i], rk[i]) for i in range(3)], "al")
+                    E.raw("sJ.set(%d, c.weight[%d] * -(%s));  // J[%d][%d]" % (self.slot(row, iv + 3 + k), row, lit(d), row, iv + 3 + k))
+            elif jt["type"] in (J_RX, J_RY, J_RZ, J_RU):
+                d = sop(E, [(u[i], w["z"][i]) for i in range(3)], "al")
+                E.raw("sJ.set(%d, c.weight[%d] * -(%s));  // J[%d][%d]" % (self.slot(row, iv), row, lit(d), row, iv))
+            # prismatic joints have no angular part
 
     def gen_solve(self, W):
         """y = (J J^T + damping^2 I)^-1 e  (dls.cpp:39-41,53) -- fused Gram / blocked left-looking LDL^T / substitutions.
@@ -687,7 +759,8 @@ class Generator:
         out.append("    static constexpr bool PSOLVE = %s;" % ("true" if self.spec.get("parallel_solve") and len(groups) > 1 else "false"))
         out.append('    static const char *name() { return "%s"; }' % display_name)
         for k, (g, ev) in enumerate(zip(groups, evs)):
-            names = ", ".join("%s %s" % (self.tasks[t]["name"], ["Position", "Orientation", "Full"][self.tasks[t]["ktype"]]) for t in g)
+            names = ", ".join("%s %s" % (self.tasks[t]["name"], ("align-" + "xyz"[self.tasks[t]["ktype"]]) if self.tasks[t]["kind"] == "align"
+                                         else ["Position", "Orientation", "Full"][self.tasks[t]["ktype"]]) for t in g)
             out.append("    // ---- role %d: %s ----" % (k, names))
             out.append("    // copy this role's target poses into the strip sT")
             out.append("    template <typename T, typename S>")
@@ -695,7 +768,7 @@ class Generator:
             for t in g:
                 toff = self.tasks[t]["toff"]
                 out.append("#pragma unroll 4")
-                out.append("        for (int k = %d; k < %d; ++k) sT.set(k, tg[k * es]);" % (toff, toff + 12))
+                out.append("        for (int k = %d; k < %d; ++k) sT.set(k, tg[k * es]);" % (toff, toff + self.tasks[t]["tsize"]))
             out.append("    }")
             out.append("    // FK + task errors (-> sE) + weighted task Jacobian non-zeros (-> sJ)")
             out.append("    template <typename T, typename S>")
@@ -763,6 +836,16 @@ class Generator:
                    ", ".join("%d, %d" % rc for rc, _ in inv))
         out.append("    static const int *sig_task_type() { static const int v[] = {%s}; return v; }" %
                    ", ".join(str(t["ktype"]) for t in self.tasks))
+        out.append("    // task kind (0 frame, 1 align-axis; for align tasks sig_task_type is the axis) and reference frame")
+        out.append("    static const int *sig_task_kind() { static const int v[] = {%s}; return v; }" %
+                   ", ".join("1" if t["kind"] == "align" else "0" for t in self.tasks))
+        out.append("    static const int *sig_task_ref_joint() { static const int v[] = {%s}; return v; }" %
+                   ", ".join(str(t["ref"]["parent"]) for t in self.tasks))
+        rpl = []
+        for t in self.tasks:
+            rpl.extend(t["ref"]["placement"])
+        out.append("    static const double *sig_task_ref_placement() { static const double v[] = {%s}; return v; }" %
+                   ", ".join(repr(float(x)) for x in rpl))
         out.append("    static const int *sig_task_priority() { static const int v[] = {%s}; return v; }" %
                    ", ".join(str(t["priority"]) for t in self.tasks))
         out.append("    static const int *sig_task_joint() { static const int v[] = {%s}; return v; }" %
