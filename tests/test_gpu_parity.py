@@ -317,6 +317,77 @@ def test_full_size_properties():
     assert np.all(q[moved][:, 7:] >= lo[7:] - 1e-15) and np.all(q[moved][:, 7:] <= hi[7:] + 1e-15)
 
 
+def _full_size_case(make, B, start, dtype, chunk=65536):
+    """Seeded workload of B problems built on the GPU (FK of sampled configurations), solved in one call."""
+    torch = _torch()
+    pb = make()
+    pb.finalize(0)
+    m = pb.model()
+    dev = torch.device("cuda:0")
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    names = W.task_frames(pb)
+    qstar = W.sample_configurations(m, B)
+    poses_t = torch.cat([ik.fk_batch(pb, torch.tensor(qstar[i:i + chunk].T.copy(), device=dev), names)
+                         for i in range(0, B, chunk)], dim=1)
+    poses = {n: poses_t[12 * i:12 * i + 12].T.cpu().numpy() for i, n in enumerate(names)}
+    tg = W.targets_from_frame_poses(pb, poses)
+    q0 = (np.tile(W.standing_configuration(m, W.CASSIE_STANDING), (B, 1)) if start == "standing" else W.near_start(m, qstar))
+    out = ik.dls_batch(pb, torch.tensor(q0.T.copy(), dtype=tdt, device=dev), torch.tensor(tg.T.copy(), dtype=tdt, device=dev))
+    torch.cuda.synchronize()
+    return pb, names, poses, q0, tg, out
+
+
+@pytest.mark.parametrize("name,make,B,start,min_conv", [("humanoid", W.humanoid_problem, 262144, "near", 0.9),
+                                                        ("manipulator", W.manipulator_problem, 1048576, "near", 0.99)])
+def test_full_size_properties_other_configs(name, make, B, start, min_conv):
+    """BASELINE configs 4 and 5 at their full batch sizes (262,144 / 1,048,576): size-independent properties -- every
+    converged problem reaches its targets when the frames are recomputed by GPU FK from the returned q, failed problems
+    used the whole iteration budget, joint limits hold, and a slice of the batch equals a separate smaller solve."""
+    torch = _torch()
+    pb, names, poses, q0, tg, out = _full_size_case(make, B, start, "f64")
+    m = pb.model()
+    ok = out["success"].bool()
+    it = out["iters"]
+    assert ok.float().mean().item() > min_conv
+    assert (out["resid"][ok] < 1e-4).all() and (it[~ok] == 100).all() and (it[ok] < 100).all()
+    got = torch.cat([ik.fk_batch(pb, out["q"][:, i:i + 65536].contiguous(), names) for i in range(0, B, 65536)], dim=1)
+    want = torch.tensor(np.concatenate([poses[n] for n in names], axis=1).T.copy(), device=got.device)
+    perr = (got - want).reshape(len(names), 12, B)[:, 9:12].norm(dim=1).max(dim=0).values  # worst frame position error
+    assert (perr[ok] < 2e-2).all()                                                       # ||e||^2 < 1e-4 bounds it by 1e-2
+    lo = torch.tensor(m.lowerPositionLimit, device=got.device)[:, None]
+    hi = torch.tensor(m.upperPositionLimit, device=got.device)[:, None]
+    moved = it > 0
+    assert ((out["q"] >= lo - 1e-15) & (out["q"] <= hi + 1e-15))[:, moved].all()
+    n2 = 20000
+    dev = got.device
+    out2 = ik.dls_batch(pb, torch.tensor(q0[:n2].T.copy(), device=dev), torch.tensor(tg[:n2].T.copy(), device=dev))
+    torch.cuda.synchronize()
+    assert torch.equal(out2["success"], out["success"][:n2]) and torch.equal(out2["iters"], out["iters"][:n2])
+    assert (out2["q"] - out["q"][:, :n2]).abs().max().item() < 1e-9
+
+
+def test_full_size_f32_cassie():
+    """BASELINE config 3 in FP32 at 65,536: converged fraction, residuals and reached targets; against the FP64 solve of
+    the same batch: flags equal on >= 99 %, q within 1e-4 rad on >= 99 % of the problems both converge on."""
+    torch = _torch()
+    pb, names, poses, q0, tg, o32 = _full_size_case(W.cassie_feet_pelvis_problem, 65536, "standing", "f32")
+    dev = o32["q"].device
+    o64 = ik.dls_batch(pb, torch.tensor(q0.T.copy(), device=dev), torch.tensor(tg.T.copy(), device=dev))
+    torch.cuda.synchronize()
+    ok32, ok64 = o32["success"].bool(), o64["success"].bool()
+    assert ok32.float().mean().item() > 0.97 and (o32["resid"][ok32] < 1e-4).all()
+    assert (ok32 == ok64).float().mean().item() > 0.99
+    both = ok32 & ok64 & (o32["iters"] == o64["iters"])
+    err = (o32["q"].double() - o64["q"]).abs().max(dim=0).values[both]
+    q = torch.quantile(err, torch.tensor([0.5, 0.99, 0.999], dtype=err.dtype, device=err.device)).tolist()
+    print("cassie f32 vs f64 at 65536: flags equal %.4f, same steps %.4f, |dq| median %.2e p99 %.2e p99.9 %.2e max %.2e"
+          % ((ok32 == ok64).float().mean().item(), both.float().mean().item(), q[0], q[1], q[2], err.max().item()))
+    assert both.float().mean().item() > 0.95
+    # the foot-pitch direction is barely observed by the two foot POSITION tasks: FP32 rounding of FK is amplified by
+    # ~1/damping there, so the tail of 65 536 samples reaches a few 1e-2 rad (DESIGN.md 2) -- the bar is on quantiles
+    assert (err < 1e-4).float().mean().item() > 0.99 and (err < 3e-3).float().mean().item() > 0.998 and err.max().item() < 0.2
+
+
 @pytest.mark.parametrize("params", ["defaults", "demo"])
 def test_two_phase_scheduling_matches_oracle(params):
     """A batch larger than one resident wave runs BULK (with suspension of stragglers once the ticket queue is dry) +
