@@ -64,6 +64,17 @@ int main(int argc, char **argv) {
         const ik::dls_batch_result r = ik::dls_batch(problem, B, q0.data(), tg.data(), ik::inverse_kinematics_visitor(), p);
         for (int b = 0; b < B; ++b)
             std::printf("batch %d success %d iterations %d resid %.12e\n", b, (int)r.success[b], r.iterations[b], r.residual[b]);
+        // stream of batches: three copies of that batch through the pipelined queue, merged into one kernel pair
+        ik::dls_batch_queue queue(problem, /*depth=*/4, /*merge=*/3);
+        ik::dls_batch_result rq[3];
+        ik::dls_batch_queue::ticket_t tk[3];
+        for (int k = 0; k < 3; ++k) tk[k] = queue.submit(B, q0.data(), tg.data(), rq[k], ik::inverse_kinematics_visitor(), p);
+        int same = 0;
+        for (int k = 0; k < 3; ++k) {
+            queue.wait(tk[k]);
+            same += rq[k].q == r.q && rq[k].iterations == r.iterations && rq[k].success == r.success;
+        }
+        std::printf("queue: %d of 3 merged batches identical to ik::dls_batch\n", same);
     } catch (const std::exception &e) {
         std::fprintf(stderr, "error: %s\n", e.what());
         return 1;

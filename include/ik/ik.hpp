@@ -19,7 +19,7 @@
 //   ik::inverse_kinematics_visitor                       ik/ik/visitor.hpp:7-24         default stop test; `tolerance` member
 //   ik::dls_parameters, ik::dls_data, ik::dls_info       ik/ik/dls.hpp:24-74            same (+ iterations / residual filled)
 //   ik::vector_t ik::dls(problem, q0, data, visitor, p)  ik/ik/dls.hpp:111-114          same signature
-//   -- extension the reference lacks --                                                 ik::dls_batch (host arrays)
+//   -- extension the reference lacks --                                                 ik::dls_batch (host arrays), ik::dls_batch_queue
 //
 // Not provided (outside the hot path): pik, FrameConstraint, CentreOfMassTask.  Eigen is not a
 // dependency: vector_t / se3_t are minimal value types with the accessors the reference's callers use.
@@ -389,5 +389,51 @@ inline dls_batch_result dls_batch(InverseKinematicsProblem &problem, std::size_t
     check(ikb_dls_solve_batch_host(h, IKB_F64, &c, (int64_t)B, &io), "ikb_dls_solve_batch_host");
     return r;
 }
+
+// Stream of batches (extension, ikb_queue_*): keeps several batches in flight and launches `merge` consecutive ones as
+// one kernel pair; host-buffer copies of one group run beside the kernels of its neighbours.  The batched analogue of the
+// reference's per-tick loop (ik_ros/src/cassie.cpp:112-113, 146-171).
+//
+//     ik::dls_batch_queue queue(problem, /*depth=*/8, /*merge=*/4);
+//     auto t = queue.submit(B, q0, targets, result);   // returns at once; `result` must outlive the batch
+//     ...                                               // submit more batches
+//     queue.wait(t);                                    // `result` is complete
+class dls_batch_queue {
+   public:
+    using ticket_t = std::int64_t;
+    dls_batch_queue(InverseKinematicsProblem &problem, int depth = 8, int merge = 4) : problem_(problem) {
+        check(ikb_queue_create(problem.handle(), depth, merge, &q_), "ikb_queue_create");
+    }
+    ~dls_batch_queue() { ikb_queue_free(q_); }
+    dls_batch_queue(const dls_batch_queue &) = delete;
+    dls_batch_queue &operator=(const dls_batch_queue &) = delete;
+
+    // host arrays as in ik::dls_batch; `out` is resized here and filled when the batch completes
+    ticket_t submit(std::size_t B, const number_t *q0, const number_t *targets, dls_batch_result &out,
+                    const inverse_kinematics_visitor &visitor = inverse_kinematics_visitor(), const dls_parameters &p = dls_parameters()) {
+        ikb_problem *h = problem_.handle();
+        const int nq = problem_.model().nq, tsz = ikb_problem_target_size(h);
+        out.q.resize(B * nq);
+        out.success.resize(B);
+        out.iterations.resize(B);
+        out.residual.resize(B);
+        const ikb_dls_params c = to_c(p, visitor);
+        ikb_batch_io io;
+        io.q0 = q0; io.q0_elem_stride = 1; io.q0_batch_stride = nq;
+        io.targets = targets; io.targets_elem_stride = 1; io.targets_batch_stride = tsz;
+        io.q = out.q.data(); io.q_elem_stride = 1; io.q_batch_stride = nq;
+        io.success = out.success.data(); io.iters = out.iterations.data(); io.resid = out.residual.data();
+        const ticket_t t = ikb_queue_submit_host(q_, IKB_F64, &c, (int64_t)B, &io);
+        if (t < 0) check((int)-t, "ikb_queue_submit_host");
+        return t;
+    }
+    void wait(ticket_t t) { check(ikb_queue_wait(q_, t), "ikb_queue_wait"); }
+    void flush() { check(ikb_queue_flush(q_), "ikb_queue_flush"); }
+    void drain() { check(ikb_queue_drain(q_), "ikb_queue_drain"); }
+
+   private:
+    InverseKinematicsProblem &problem_;
+    ikb_queue *q_ = nullptr;
+};
 
 }  // namespace ik

@@ -122,3 +122,4 @@ def test_cpp_facade_demo_matches_oracle():
         assert abs(float(l[7]) - res) < 1e-9
         assert np.abs(np.array([float(x) for x in l[9:13]]) - q[7:11]).max() < 1e-6
     assert len([l for l in r.stdout.splitlines() if l.startswith("batch")]) == 4
+    assert "queue: 3 of 3 merged batches identical" in r.stdout
