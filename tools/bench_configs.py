@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0, help="scale the batch sizes (smoke runs)")
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=8)
     args = ap.parse_args()
     import torch
 
@@ -26,7 +26,8 @@ def main():
     from ik_b200 import workloads as W
 
     dev = torch.device("cuda:0")
-    cases = [("cassie feet+pelvis B=4096", W.cassie_feet_pelvis_problem, 4096, "standing", ("f64",)),
+    cases = [("cassie feet+pelvis B=4096", W.cassie_feet_pelvis_problem, 4096, "standing", ("f64", "f32")),
+             ("cassie demo task set (cassie.cpp:43-81) B=65536", W.cassie_demo_problem, 65536, "standing", ("f64", "f32")),
              ("cassie feet+pelvis B=65536", W.cassie_feet_pelvis_problem, 65536, "standing", ("f64", "f32")),
              ("humanoid 5 Full tasks B=262144", W.humanoid_problem, 262144, "near", ("f64", "f32")),
              ("manipulator 1 Full task B=1048576", W.manipulator_problem, 1048576, "near", ("f64", "f32"))]
@@ -57,9 +58,28 @@ def main():
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / args.steps
             ok = out["success"].sum().item()
+            # the same batches as a stream through the pipelined queue (4 per kernel pair)
+            queue = ik.SolveQueue(pb, 8, 4)
+            outs = [None] * 4
+            for k in range(4):
+                _, outs[k] = queue.submit(q0_d, tg_d, None, outs[k])
+            queue.drain()
+            nq_steps = max(4, args.steps // 4 * 4)
+            e0.record()
+            last = None
+            for k in range(nq_steps):
+                last, outs[k % 4] = queue.submit(q0_d, tg_d, None, outs[k % 4])
+            queue.flush()
+            queue.wait_on_stream(last)
+            e1.record()
+            torch.cuda.synchronize()
+            queue.drain()
+            qms = e0.elapsed_time(e1) / nq_steps
             print(json.dumps({"config": name, "dtype": dt, "kernel": pb.kernel_name(dt), "batch": B, "ms_per_batch": ms,
-                              "converged_solves_per_s": ok / (ms * 1e-3), "converged_fraction": ok / B,
+                              "converged_solves_per_s": ok / (ms * 1e-3), "queue_ms_per_batch": qms,
+                              "queue_converged_solves_per_s": ok / (qms * 1e-3), "converged_fraction": ok / B,
                               "mean_iterations": out["iters"].float().mean().item()}))
+            del queue
 
 
 if __name__ == "__main__":
