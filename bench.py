@@ -42,9 +42,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 F_ITER_CASSIE = 9360.0  # SURVEY.md 8d, algorithmic FLOPs of one evaluate+solve+step for the Cassie problem
-# dram__bytes_read.sum + dram__bytes_write.sum of the two launches of one FP64 step, from the committed ncu --set full
-# capture profiles/r1_final_full.txt (bulk 31.55 + 0.75 MB, tail 21.40 + 0.00 MB); algorithmic bytes are 43.8 MB.
-NCU_TRAFFIC_BYTES_F64 = 53.7e6
+# dram__bytes_read.sum + dram__bytes_write.sum per FP64 step, from the committed ncu --set full capture
+# profiles/r1_queue_full.txt: the BULK + TAIL launches of a group of 4 steps move 132.8 + 45.1 and 47.9 + 0.3 MB -> 56.5 MB
+# per step (a lone step: 53.7 MB, profiles/r1_final_full.txt); algorithmic bytes are 43.8 MB.
+NCU_TRAFFIC_BYTES_F64 = 56.5e6
 METRIC = "converged IK solves/sec (Cassie, batch 65,536)"
 UNIT = "solves/s"
 NOMINAL_TFLOPS = {"f64": 37.2, "f32": 74.4}
@@ -396,7 +397,7 @@ def main():
                          "achieved": achieved_tf, "peak": peak.value, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak.value if peak.value else None,
                          "traffic": NCU_TRAFFIC_BYTES_F64 if (args.dtype == "f64" and B == 65536) else None,
-                         "traffic_source": "ncu --set full, profiles/r1_final_full.txt (DRAM bytes of both launches of a step)",
+                         "traffic_source": "ncu --set full, profiles/r1_queue_full.txt: DRAM bytes of the BULK + TAIL launches of a group of 4 steps (177.9 + 48.2 MB) / 4; algorithmic 43.8 MB",
                          "kernels": "BULK %s + TAIL per group of %d steps; kernel_ms = device time of the timed region / steps"
                                     % (pb.kernel_name(args.dtype), args.merge),
                          "peak_source": "measured in this run (ikb_measure_fma_peak); nominal %.1f"
