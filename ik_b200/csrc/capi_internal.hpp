@@ -1,0 +1,147 @@
+// Internals shared by the translation units of the C ABI (ikb_capi.cu: models, problems, FK, utilities; ikb_solve.cu:
+// the solve launcher and the host-buffer path; ikb_queue.cu: the pipelined queue).  Not installed; include/ikb200.h is
+// the public contract.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <climits>
+#include <cstdint>
+#include <cstdlib>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ikb200.h"
+#include "dev_problem.hpp"
+#include "model.hpp"
+#include "specialized.hpp"
+
+namespace ikb {
+namespace capi {
+constexpr int kTicketSlots = 64;
+constexpr int kScratchSlots = 8;
+
+// Device scratch of one in-flight two-phase solve: the suspended-problem list and (when the caller passes no `iters`)
+// the step counts the tail launch resumes from.  Slots rotate; `ev` marks the end of the slot's last user.
+struct SolveScratch {
+    unsigned int *list = nullptr;
+    int *iters = nullptr;
+    size_t cap = 0;
+    cudaEvent_t ev = nullptr;
+};
+
+// Device staging buffers of one host-buffer batch (same strides as the caller's views).
+template <typename T> struct Staging {
+    T *q0 = nullptr, *targets = nullptr, *q = nullptr, *resid = nullptr;
+    size_t q0_cap = 0, tg_cap = 0, q_cap = 0, b_cap = 0;
+};
+}  // namespace capi
+}  // namespace ikb
+
+struct ikb_model {
+    ikb::HostModel m;
+};
+
+struct ikb_problem {
+    ikb::HostProblem hp;
+    bool finalized = false;
+    int device = -1;
+    int size_class = -1;
+    int sm_count = 0;
+    ikb::DevProblem<double> *d64 = nullptr;
+    ikb::DevProblem<float> *d32 = nullptr;
+    int *d_frame_parent = nullptr;  // all model frames (for ikb_fk_batch)
+    double *d_frame_pl64 = nullptr;
+    float *d_frame_pl32 = nullptr;
+    unsigned long long *d_tickets = nullptr;
+    std::atomic<unsigned> ticket_next{0};
+    ikb::capi::SolveScratch scratch[ikb::capi::kScratchSlots];
+    std::mutex scratch_mu;
+    const ikb::SpecializedKernel *spec = nullptr;
+    std::vector<double> weight_stacked;  // Task::weighting() rows in stacked order (constants of the specialised kernels)
+    std::string kernel_name[2];
+    // host-path staging (ikb_dls_solve_batch_host): main stream + the pipelined path's copy-in and second compute stream
+    cudaStream_t stream = nullptr, stream_in = nullptr, stream_aux = nullptr;
+    cudaEvent_t ev_in[8] = {}, ev_aux = nullptr, ev_main = nullptr;
+    ikb::capi::Staging<double> st64;
+    ikb::capi::Staging<float> st32;
+    unsigned char *st_success = nullptr;
+    int *st_iters = nullptr;
+    size_t st_flag_cap = 0;
+};
+
+namespace ikb {
+namespace capi {
+
+// ---- error reporting (ikb_last_error is per thread) ----
+std::string &last_error();
+extern std::atomic<long long> g_launches;
+int fail(int code, const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what);
+#define IKB_CUDA(call)                                                  \
+    do {                                                                \
+        cudaError_t e_ = (call);                                        \
+        if (e_ != cudaSuccess) return ::ikb::capi::cuda_fail(e_, #call); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int check_solve_args(const ikb_problem *p, int dtype, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io);
+
+// ---- buffers ----
+inline size_t view_extent(int64_t n_elem, int64_t es, int64_t bs, int64_t B) {
+    return (size_t)((n_elem - 1) * es + (B - 1) * bs + 1);
+}
+template <typename T> int ensure(T *&ptr, size_t &cap, size_t need) {
+    if (need <= cap) return IKB_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    size_t want = std::max(need, (size_t)1024);
+    IKB_CUDA(cudaMalloc(&ptr, want * sizeof(T)));
+    cap = want;
+    return IKB_OK;
+}
+
+// ---- the solve launcher (ikb_solve.cu) ----
+// Pipelined host path (solve_host): the inputs of batch slice [begin[c], begin[c + 1]) are on the device once `ready[c]`
+// has happened.  The BULK launch is issued per slice, alternating between the caller's stream and `aux`, so that it
+// overlaps the host-to-device copy of the next slices; the TAIL launch continues the stragglers of all slices at once.
+struct ChunkPlan {
+    int n = 0;
+    long long begin[9] = {};
+    cudaEvent_t ready[8] = {};
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_aux = nullptr, ev_main = nullptr;
+};
+
+// Merged launch of the pipelined queue (ikb_queue_*): `nseg` batches, each with its own buffers (host array of segment
+// descriptors sorted by `begin`; launch_solve copies them into the kernel parameters).
+template <typename T> struct Merged {
+    const BatchSeg<T> *seg;
+    int nseg;
+};
+
+// Is this solve going to take the two-launch (BULK + TAIL) path?  (the only one that can be pipelined by slices)
+bool two_phase(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, int *cap_out = nullptr);
+
+// Enqueue ik::dls for B problems on stream `s`: picks the kernels (specialised BULK + TAIL pair, latency configuration,
+// team kernel, generic kernel) and the scratch.  `io` holds DEVICE pointers (nullptr for a merged launch).
+template <typename T>
+int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io, cudaStream_t s,
+                 const ChunkPlan *plan = nullptr, const Merged<T> *merged = nullptr);
+
+}  // namespace capi
+}  // namespace ikb

@@ -1,0 +1,287 @@
+// The pipelined queue of the C ABI (include/ikb200.h, ikb_queue_*).
+#include <utility>
+
+#include "capi_internal.hpp"
+
+using namespace ikb;
+using namespace ikb::capi;
+
+
+// ---------------------------------------------------------------------------------------------------
+// pipelined queue: batches in flight on three streams (copy-in, compute, copy-out); consecutive batches are MERGED
+// into one BULK + TAIL launch pair (the straggler chain of ~0.7 ms is paid once per group instead of once per batch)
+// ---------------------------------------------------------------------------------------------------
+
+struct ikb_queue {
+    struct Slot {
+        cudaEvent_t ev_in = nullptr, ev_done = nullptr;
+        bool busy = false, pending = false, host = false;
+        int64_t ticket = -1;  // the batch occupying the slot
+        int64_t B = 0;
+        ikb_batch_io dio{};   // device view of the batch
+        ikb_batch_io hio{};   // host mode: the caller's buffers (copy-out targets)
+        // host-mode staging (per scalar type, grown on demand)
+        Staging<double> st64;
+        Staging<float> st32;
+        unsigned char *success = nullptr;
+        int *iters = nullptr;
+        size_t flag_cap = 0;
+    };
+    ikb_problem *p = nullptr;
+    int depth = 0, merge = 1;
+    std::vector<Slot> slots;
+    std::vector<int> open;        // slots of the group that has not been launched yet
+    ikb_dls_params open_prm{};
+    int open_dtype = -1;
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    cudaEvent_t ev_user = nullptr, ev_comp = nullptr;
+    int64_t next = 0;
+};
+
+namespace {
+constexpr int kMaxMerge = kMaxSegments;
+
+template <typename T> Staging<T> &slot_staging(ikb_queue::Slot &sl);
+template <> Staging<double> &slot_staging<double>(ikb_queue::Slot &sl) { return sl.st64; }
+template <> Staging<float> &slot_staging<float>(ikb_queue::Slot &sl) { return sl.st32; }
+
+bool same_params(const ikb_dls_params &a, const ikb_dls_params &b) {
+    return a.max_iterations == b.max_iterations && a.step_length == b.step_length && a.damping == b.damping && a.tolerance == b.tolerance;
+}
+
+template <typename T> int queue_copy_out(ikb_queue *q, ikb_queue::Slot &sl) {
+    const int nq = q->p->hp.model.nq;
+    const ikb_batch_io &io = sl.hio;
+    Staging<T> &st = slot_staging<T>(sl);
+    const size_t n_q = view_extent(nq, io.q_elem_stride, io.q_batch_stride, sl.B);
+    IKB_CUDA(cudaMemcpyAsync(io.q, st.q, n_q * sizeof(T), cudaMemcpyDeviceToHost, q->s_out));
+    if (io.success) IKB_CUDA(cudaMemcpyAsync(io.success, sl.success, (size_t)sl.B, cudaMemcpyDeviceToHost, q->s_out));
+    if (io.iters) IKB_CUDA(cudaMemcpyAsync(io.iters, sl.iters, (size_t)sl.B * sizeof(int), cudaMemcpyDeviceToHost, q->s_out));
+    if (io.resid) IKB_CUDA(cudaMemcpyAsync(io.resid, st.resid, (size_t)sl.B * sizeof(T), cudaMemcpyDeviceToHost, q->s_out));
+    return IKB_OK;
+}
+
+// Launch the open group: one merged BULK + TAIL pair when the problem has a specialised kernel, else batch by batch.
+template <typename T> int queue_flush_t(ikb_queue *q) {
+    const int n = (int)q->open.size();
+    int rc;
+    for (int i : q->open)
+        if (q->slots[i].host) IKB_CUDA(cudaStreamWaitEvent(q->s_comp, q->slots[i].ev_in, 0));
+    if (n >= 2 && q->p->spec && q->open_prm.max_iterations > 0) {
+        BatchSeg<T> tab[kMaxSegments];
+        long long total = 0;
+        for (int k = 0; k < n; ++k) {
+            const ikb_queue::Slot &sl = q->slots[q->open[k]];
+            const ikb_batch_io &d = sl.dio;
+            tab[k] = BatchSeg<T>{(const T *)d.q0, d.q0_elem_stride, d.q0_batch_stride, (const T *)d.targets, d.targets_elem_stride,
+                                   d.targets_batch_stride, (T *)d.q, d.q_elem_stride, d.q_batch_stride, d.success, d.iters,
+                                   (T *)d.resid, total};
+            total += sl.B;
+        }
+        const Merged<T> m{tab, n};
+        if ((rc = launch_solve<T>(q->p, &q->open_prm, total, nullptr, q->s_comp, nullptr, &m))) return rc;
+    } else {
+        for (int i : q->open) {
+            ikb_queue::Slot &sl = q->slots[i];
+            if (sl.B > 0 && (rc = launch_solve<T>(q->p, &q->open_prm, sl.B, &sl.dio, q->s_comp))) return rc;
+        }
+    }
+    bool any_host = false;
+    for (int i : q->open) any_host |= q->slots[i].host;
+    if (any_host) {
+        IKB_CUDA(cudaEventRecord(q->ev_comp, q->s_comp));
+        IKB_CUDA(cudaStreamWaitEvent(q->s_out, q->ev_comp, 0));
+    }
+    for (int i : q->open) {
+        ikb_queue::Slot &sl = q->slots[i];
+        if (sl.host) {
+            if (sl.B > 0 && (rc = queue_copy_out<T>(q, sl))) return rc;
+            IKB_CUDA(cudaEventRecord(sl.ev_done, q->s_out));
+        } else {
+            IKB_CUDA(cudaEventRecord(sl.ev_done, q->s_comp));
+        }
+        sl.pending = false;
+    }
+    q->open.clear();
+    return IKB_OK;
+}
+int queue_flush(ikb_queue *q) {
+    if (q->open.empty()) return IKB_OK;
+    return q->open_dtype == IKB_F64 ? queue_flush_t<double>(q) : queue_flush_t<float>(q);
+}
+
+// The slot of the next batch, free of its previous occupant (back-pressure: blocks while that batch is in flight).
+int queue_acquire(ikb_queue *q, int dtype, const ikb_dls_params *prm, ikb_queue::Slot **out) {
+    int rc;
+    ikb_queue::Slot *sl = &q->slots[q->next % q->depth];
+    if (sl->pending && (rc = queue_flush(q))) return rc;
+    if (sl->busy) {
+        IKB_CUDA(cudaEventSynchronize(sl->ev_done));
+        sl->busy = false;
+    }
+    // a group shares one launch: same scalar type, same solver parameters
+    if (!q->open.empty() && (q->open_dtype != dtype || !same_params(q->open_prm, *prm)) && (rc = queue_flush(q))) return rc;
+    q->open_dtype = dtype;
+    q->open_prm = *prm;
+    *out = sl;
+    return IKB_OK;
+}
+int64_t queue_commit(ikb_queue *q, ikb_queue::Slot *sl) {
+    sl->busy = true;
+    sl->pending = true;
+    sl->ticket = q->next;
+    q->open.push_back((int)(q->next % q->depth));
+    if ((int)q->open.size() >= q->merge) {
+        int rc = queue_flush(q);
+        if (rc) return -rc;
+    }
+    return q->next++;
+}
+
+template <typename T> int queue_stage_host(ikb_queue *q, ikb_queue::Slot &sl, int64_t B, const ikb_batch_io *io) {
+    ikb_problem *p = q->p;
+    const int nq = p->hp.model.nq, tsz = p->hp.target_size();
+    Staging<T> &st = slot_staging<T>(sl);
+    const size_t n_q0 = view_extent(nq, io->q0_elem_stride, io->q0_batch_stride, B);
+    const size_t n_tg = tsz > 0 ? view_extent(tsz, io->targets_elem_stride, io->targets_batch_stride, B) : 0;
+    const size_t n_q = view_extent(nq, io->q_elem_stride, io->q_batch_stride, B);
+    int rc;
+    if ((rc = ensure(st.q0, st.q0_cap, n_q0)) || (rc = ensure(st.targets, st.tg_cap, std::max<size_t>(n_tg, 1))) ||
+        (rc = ensure(st.q, st.q_cap, n_q)) || (rc = ensure(st.resid, st.b_cap, (size_t)B)))
+        return rc;
+    if ((size_t)B > sl.flag_cap) {
+        if (sl.success) cudaFree(sl.success);
+        if (sl.iters) cudaFree(sl.iters);
+        sl.success = nullptr; sl.iters = nullptr; sl.flag_cap = 0;
+        IKB_CUDA(cudaMalloc(&sl.success, (size_t)B));
+        IKB_CUDA(cudaMalloc(&sl.iters, (size_t)B * sizeof(int)));
+        sl.flag_cap = (size_t)B;
+    }
+    IKB_CUDA(cudaMemcpyAsync(st.q0, io->q0, n_q0 * sizeof(T), cudaMemcpyHostToDevice, q->s_in));
+    if (n_tg) IKB_CUDA(cudaMemcpyAsync(st.targets, io->targets, n_tg * sizeof(T), cudaMemcpyHostToDevice, q->s_in));
+    IKB_CUDA(cudaEventRecord(sl.ev_in, q->s_in));
+    sl.hio = *io;
+    sl.dio = *io;
+    sl.dio.q0 = st.q0; sl.dio.targets = st.targets; sl.dio.q = st.q;
+    sl.dio.success = sl.success; sl.dio.iters = sl.iters; sl.dio.resid = st.resid;
+    return IKB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int ikb_queue_create(ikb_problem *p, int depth, int merge, ikb_queue **out) {
+    if (!p || !out) return fail(IKB_ERR_INVALID_ARG, "null argument");
+    if (!p->finalized) return fail(IKB_ERR_NOT_FINALIZED, "call ikb_problem_finalize first");
+    if (depth < 1 || depth > 16) return fail(IKB_ERR_INVALID_ARG, "queue depth must be between 1 and 16");
+    if (merge < 1 || merge > kMaxMerge || merge > depth) return fail(IKB_ERR_INVALID_ARG, "merge must be between 1 and min(depth, 8)");
+    DeviceGuard g(p->device);
+    ikb_queue *q = new ikb_queue;
+    q->p = p;
+    q->depth = depth;
+    q->merge = merge;
+    q->slots.resize(depth);
+    *out = q;  // the caller frees it also when creation fails half-way
+    for (cudaStream_t *s : {&q->s_in, &q->s_comp, &q->s_out}) IKB_CUDA(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking));
+    IKB_CUDA(cudaEventCreateWithFlags(&q->ev_user, cudaEventDisableTiming));
+    IKB_CUDA(cudaEventCreateWithFlags(&q->ev_comp, cudaEventDisableTiming));
+    for (auto &sl : q->slots)
+        for (cudaEvent_t *e : {&sl.ev_in, &sl.ev_done}) IKB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    return IKB_OK;
+}
+
+void ikb_queue_free(ikb_queue *q) {
+    if (!q) return;
+    DeviceGuard g(q->p->device);
+    queue_flush(q);
+    for (cudaStream_t s : {q->s_in, q->s_comp, q->s_out})
+        if (s) {
+            cudaStreamSynchronize(s);
+            cudaStreamDestroy(s);
+        }
+    if (q->ev_user) cudaEventDestroy(q->ev_user);
+    if (q->ev_comp) cudaEventDestroy(q->ev_comp);
+    for (auto &sl : q->slots) {
+        for (cudaEvent_t e : {sl.ev_in, sl.ev_done})
+            if (e) cudaEventDestroy(e);
+        cudaFree(sl.st64.q0); cudaFree(sl.st64.targets); cudaFree(sl.st64.q); cudaFree(sl.st64.resid);
+        cudaFree(sl.st32.q0); cudaFree(sl.st32.targets); cudaFree(sl.st32.q); cudaFree(sl.st32.resid);
+        cudaFree(sl.success); cudaFree(sl.iters);
+    }
+    delete q;
+}
+
+int64_t ikb_queue_submit(ikb_queue *q, int dtype, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io, void *in_stream) {
+    if (!q) return -fail(IKB_ERR_INVALID_ARG, "null queue");
+    int rc = check_solve_args(q->p, dtype, prm, B, io);
+    if (rc) return -rc;
+    DeviceGuard g(q->p->device);
+    ikb_queue::Slot *sl;
+    if ((rc = queue_acquire(q, dtype, prm, &sl))) return -rc;
+    // the inputs are ready in `in_stream` order (NULL = the legacy default stream) at this point
+    if (cudaEventRecord(q->ev_user, (cudaStream_t)in_stream) != cudaSuccess || cudaStreamWaitEvent(q->s_comp, q->ev_user, 0) != cudaSuccess)
+        return -cuda_fail(cudaGetLastError(), "queue input dependency");
+    sl->host = false;
+    sl->B = B;
+    sl->dio = *io;
+    return queue_commit(q, sl);
+}
+
+int64_t ikb_queue_submit_host(ikb_queue *q, int dtype, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io) {
+    if (!q) return -fail(IKB_ERR_INVALID_ARG, "null queue");
+    int rc = check_solve_args(q->p, dtype, prm, B, io);
+    if (rc) return -rc;
+    DeviceGuard g(q->p->device);
+    ikb_queue::Slot *sl;
+    if ((rc = queue_acquire(q, dtype, prm, &sl))) return -rc;
+    sl->host = true;
+    sl->B = B;
+    if (B > 0) {
+        rc = dtype == IKB_F64 ? queue_stage_host<double>(q, *sl, B, io) : queue_stage_host<float>(q, *sl, B, io);
+        if (rc) return -rc;
+    } else if (cudaEventRecord(sl->ev_in, q->s_in) != cudaSuccess) {
+        return -cuda_fail(cudaGetLastError(), "cudaEventRecord");
+    }
+    return queue_commit(q, sl);
+}
+
+int ikb_queue_flush(ikb_queue *q) {
+    if (!q) return fail(IKB_ERR_INVALID_ARG, "null queue");
+    DeviceGuard g(q->p->device);
+    return queue_flush(q);
+}
+
+int ikb_queue_wait(ikb_queue *q, int64_t ticket) {
+    if (!q || ticket < 0 || ticket >= q->next) return fail(IKB_ERR_INVALID_ARG, "unknown queue ticket");
+    ikb_queue::Slot &sl = q->slots[ticket % q->depth];
+    if (sl.ticket != ticket) return IKB_OK;  // its slot has been reused: it left the pipeline long ago
+    DeviceGuard g(q->p->device);
+    int rc;
+    if (sl.pending && (rc = queue_flush(q))) return rc;
+    IKB_CUDA(cudaEventSynchronize(sl.ev_done));
+    sl.busy = false;
+    return IKB_OK;
+}
+
+int ikb_queue_wait_on_stream(ikb_queue *q, int64_t ticket, void *cuda_stream) {
+    if (!q || ticket < 0 || ticket >= q->next) return fail(IKB_ERR_INVALID_ARG, "unknown queue ticket");
+    ikb_queue::Slot &sl = q->slots[ticket % q->depth];
+    if (sl.ticket != ticket) return IKB_OK;
+    DeviceGuard g(q->p->device);
+    int rc;
+    if (sl.pending && (rc = queue_flush(q))) return rc;
+    IKB_CUDA(cudaStreamWaitEvent((cudaStream_t)cuda_stream, sl.ev_done, 0));
+    return IKB_OK;
+}
+
+int ikb_queue_drain(ikb_queue *q) {
+    if (!q) return fail(IKB_ERR_INVALID_ARG, "null queue");
+    DeviceGuard g(q->p->device);
+    int rc = queue_flush(q);
+    if (rc) return rc;
+    for (cudaStream_t s : {q->s_in, q->s_comp, q->s_out}) IKB_CUDA(cudaStreamSynchronize(s));
+    for (auto &sl : q->slots) sl.busy = false;
+    return IKB_OK;
+}
+
+}  // extern "C"
