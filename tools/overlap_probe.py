@@ -1,5 +1,7 @@
-"""Steady-state throughput of back-to-back batches when consecutive solves alternate between two streams (the TAIL
-launch of batch k can then run beside the BULK launch of batch k+1 if the SHARED-residency variants are selected)."""
+"""Steady-state throughput of back-to-back batches when consecutive solves alternate between 1 / 2 / 3 user streams
+(ikb_dls_solve_batch): the experiment behind DESIGN.md 4.1 "overlapping the TAIL launch with the next batch's BULK launch"
+(two streams: 0.77 ms per batch instead of 1.07 -- two TAIL launches run side by side -- which is what led to merging the
+batches of a stream into one kernel pair, the pipelined queue)."""
 import os, sys, time, numpy as np
 sys.path.insert(0, os.getcwd())
 import torch
@@ -31,20 +33,5 @@ for nstreams in (1, 2, 3):
                 ik.dls_batch(pb, q0, tg, None, outs[k % 5], stream=streams[k % nstreams].cuda_stream)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / K
-    print("IKB_SHARED=%s streams=%d  %.4f ms/batch  %.1f M problems/s" % (os.environ.get("IKB_SHARED", "0"), nstreams, dt * 1e3, B / dt / 1e6))
+    print("streams=%d  %.4f ms/batch  %.1f M problems/s" % (nstreams, dt * 1e3, B / dt / 1e6))
 
-# ---- the pipelined queue ----
-for depth in (2, 3, 4):
-    queue = ik.SolveQueue(pb, depth)
-    for rep in range(2):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        K = 40
-        for k in range(K):
-            q0, tg, _ = sets[k % 5]
-            queue.submit(q0, tg, None, outs[k % 5])
-        queue.drain()
-        dt = (time.perf_counter() - t0) / K
-    print("queue depth=%d  %.4f ms/batch  %.1f M problems/s" % (depth, dt * 1e3, B / dt / 1e6))
-    ref = ik.dls_batch(pb, sets[4][0], sets[4][1]); torch.cuda.synchronize()
-    print("  bit-identical to dls_batch:", all(torch.equal(ref[k], outs[4][k]) for k in ("q", "success", "iters", "resid")))
