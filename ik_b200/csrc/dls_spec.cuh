@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
     using S = Strip<T, SLOTS>;
     const S sJ{sm};                                         // weighted task Jacobian, non-zeros only
     const S sL{sm + Spec::NSLOT * SLOTS};                   // LDL^T factor
-    const S sE = sL;                                        //   ... whose first M slots carry e until the solve starts
+    const S sE{sm + (Spec::NSLOT + Spec::EOFF) * SLOTS};    //   ... M of whose slots carry e until the solve starts
     const S sD{sm + (Spec::NSLOT + M) * SLOTS};             //   ... and whose next NQ slots carry the stepped q after it
     const S sT{sm + (Spec::NSLOT + Spec::NFACT) * SLOTS};   // target poses
     T *sRes = sm + (Spec::NSLOT + Spec::NFACT + Spec::TSZ) * SLOTS;  // ||e[0]||^2 of the current evaluation
@@ -127,7 +127,13 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
     // stay in step (same instruction count whatever their lanes do) and share each fetched line; left alone they drift
     // apart and each pulls its own copy (ncu: no_instruction stalls 0.4 -> 1.1 per issue).
     while (__syncthreads_or(have)) {
-        if (have) Spec::evaluate(role, q, sT, c, sJ, sE);  // data.cpp:25-58, this role's tasks
+        if (have) {
+            Spec::evaluate(role, q, sT, c, sJ, sE);         // data.cpp:25-58, this role's tasks
+            // The solver role's own tasks are the cheap ones: while the others still evaluate, it factorises the leading
+            // block of the normal equations, which involves its rows only (off the critical path, no extra barrier).
+            if constexpr (Spec::PRE > 0)
+                if (role == Spec::SOLVER) Spec::presolve(sJ, sL, sE, a.damping2);
+        }
         group_sync();                                       // J and e of all roles visible
         T sres_mine = T(0);
         if (role == Spec::SOLVER && have) {

@@ -25,7 +25,7 @@ static int spec_solve(const double *lower, const double *upper, const double *we
     for (int i = 0; i < M; ++i) c.weight[i] = (T)weight[i];
     std::vector<T> bufJ(Spec::NSLOT), bufL(Spec::NFACT), bufT(Spec::TSZ), tgt(targets, targets + Spec::TSZ);
     const Strip<T, 1> sJ{bufJ.data()}, sL{bufL.data()}, sT{bufT.data()};
-    const Strip<T, 1> sE = sL;  // e aliases the start of the factor strip, as in the kernel
+    const Strip<T, 1> sE{bufL.data() + Spec::EOFF};  // e aliases part of the factor strip, as in the kernel
     for (int role = 0; role < Spec::NWARPS; ++role) Spec::load_targets(role, tgt.data(), 1LL, sT);
     T q[NQ];
     for (int k = 0; k < NQ; ++k) q[k] = (T)q0[k];
@@ -33,6 +33,7 @@ static int spec_solve(const double *lower, const double *upper, const double *we
     T res = 0;
     while (it < max_it) {
         for (int role = 0; role < Spec::NWARPS; ++role) Spec::evaluate(role, q, sT, c, sJ, sE);  // the warp roles, in turn
+        if (Spec::PRE > 0) Spec::presolve(sJ, sL, sE, (T)(damping * damping));                      // solver role, before the barrier
         if (it == 0 && e_first) for (int i = 0; i < M; ++i) e_first[i] = (double)sE.get(i);
         T y[M], dq[NV];
         if (parallel && Spec::NWARPS > 1) {

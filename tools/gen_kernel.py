@@ -474,10 +474,64 @@ class Generator:
                 E.raw("sJ.set(%d, c.weight[%d] * -(%s));  // J[%d][%d]" % (self.slot(row, iv), row, lit(d), row, iv))
             # prismatic joints have no angular part
 
-    def gen_solve(self, W):
+    def gen_presolve(self, P):
+        """The leading P x P block of the factorisation, which involves only the task rows of the SOLVER role itself: Gram
+        entries, LDL^T of the block and the first P entries of D^-1 L^-1 e.  The solver role runs this right after its own
+        evaluate, while the other roles are still evaluating theirs (its tasks are cheaper), i.e. off the critical path.
+        Results go to the factor strip (L, d at their usual slots; yp at slot YOFF + j)."""
+        M = self.rows
+        ind = "        "
+        L = []
+        nstrict = M * (M - 1) // 2
+
+        def Lidx(i, k):
+            return i * (i - 1) // 2 + k
+
+        col_rows = {}
+        for (r, c) in self.slots:
+            if r < P:
+                col_rows.setdefault(c, []).append(r)
+        for c in col_rows:
+            col_rows[c].sort()
+        nfma = 0
+        L.append(ind + "IKB_PHASE_FENCE();  // the J / e entries below were written by this very thread")
+        for j in range(P):
+            for i in range(j, P):
+                L.append(ind + "T g_%d_%d = %s;" % (i, j, "damping2" if i == j else "T(0)"))
+            L.append(ind + "T g_e_%d = sE.get(%d);" % (j, j))
+        for c in sorted(col_rows):
+            rs = col_rows[c]
+            L.append(ind + "{  // J column %d" % c)
+            for i in rs:
+                L.append(ind + "    const T a%d = sJ.get(%d);" % (i, self.slots[(i, c)]))
+            for j in rs:
+                for i in rs:
+                    if i >= j:
+                        L.append(ind + "    g_%d_%d += a%d * a%d;" % (i, j, i, j))
+                        nfma += 1
+            L.append(ind + "}")
+        for j in range(P):
+            L.append(ind + "sL.set(%d, g_%d_%d);" % (nstrict + j, j, j))
+            L.append(ind + "const T inv_%d = rcp_(g_%d_%d);" % (j, j, j))
+            for i in range(j + 1, P):
+                L.append(ind + "const T l_%d_%d = g_%d_%d * inv_%d;" % (i, j, i, j, j))
+                L.append(ind + "sL.set(%d, l_%d_%d);" % (Lidx(i, j), i, j))
+            L.append(ind + "sL.set(%d, g_e_%d * inv_%d);  // yp[%d]" % (self.yoff + j, j, j, j))
+            for j2 in range(j + 1, P):
+                for i in range(j2, P):
+                    L.append(ind + "g_%d_%d -= l_%d_%d * g_%d_%d;" % (i, j2, i, j, j2, j))
+                    nfma += 1
+                L.append(ind + "g_e_%d -= (g_e_%d * inv_%d) * g_%d_%d;" % (j2, j, j, j2, j))
+        L.append(ind + "IKB_PHASE_FENCE();")
+        self.presolve_fma = nfma
+        return L
+
+    def gen_solve(self, W, P=0):
         """y = (J J^T + damping^2 I)^-1 e  (dls.cpp:39-41,53) -- fused Gram / blocked left-looking LDL^T / substitutions.
 
-        Strip sL layout: strictly-lower L[i][k] at i*(i-1)/2 + k, then d[k] at M*(M-1)/2 + k."""
+        Strip sL layout: strictly-lower L[i][k] at i*(i-1)/2 + k, then d[k] at M*(M-1)/2 + k.
+        P > 0: the leading P x P block (and yp[0..P)) has been produced by gen_presolve; the first block column is then
+        columns 0..P-1 restricted to the rows below the block."""
         M = self.rows
         ind = "        "
         L = []
@@ -499,7 +553,43 @@ class Generator:
         L.append(ind + "#pragma unroll")
         L.append(ind + "for (int i = 0; i < %d; ++i) res += e[i] * e[i];  // visitor.hpp:19 (priority-0 rows)" % self.rows_p0)
         L.append(ind + "IKB_PHASE_FENCE();  // sE may alias the factor strip: every e is in a register from here on")
-        for j0 in range(0, M, W):
+        if P > 0:
+            # ---- block column 0..P-1, rows P..M-1, against the pre-factorised P x P block ----
+            L.append(ind + "#pragma unroll")
+            L.append(ind + "for (int j = 0; j < %d; ++j) yp[j] = sL.get(%d + j);  // from presolve" % (P, self.yoff))
+            L.append(ind + "IKB_PHASE_FENCE();")
+            L.append(ind + "// ---- block column 0..%d (rows %d..%d; the diagonal block comes from presolve) ----" % (P - 1, P, M - 1))
+            for j in range(P):
+                for i in range(P, M):
+                    L.append(ind + "T g_%d_%d = T(0);" % (i, j))
+            for c in sorted(col_rows):
+                rs = col_rows[c]
+                bj = [j for j in rs if j < P]
+                lo = [i for i in rs if i >= P]
+                if not bj or not lo:
+                    continue
+                L.append(ind + "{  // J column %d" % c)
+                for i in bj + lo:
+                    L.append(ind + "    const T a%d = sJ.get(%d);" % (i, self.slots[(i, c)]))
+                for j in bj:
+                    for i in lo:
+                        L.append(ind + "    g_%d_%d += a%d * a%d;" % (i, j, i, j))
+                        nfma += 1
+                L.append(ind + "}")
+            for j in range(P):
+                L.append(ind + "{  // column %d" % j)
+                L.append(ind + "    const T d%d = sL.get(%d), pinv%d = rcp_(d%d);" % (j, nstrict + j, j, j))
+                for i in range(P, M):
+                    L.append(ind + "    const T l_%d_%d = g_%d_%d * pinv%d;" % (i, j, i, j, j))
+                    L.append(ind + "    sL.set(%d, l_%d_%d);" % (Lidx(i, j), i, j))
+                for j2 in range(j + 1, P):
+                    L.append(ind + "    const T pv_%d_%d = sL.get(%d) * d%d;  // L[%d][%d] d[%d]" % (j2, j, Lidx(j2, j), j, j2, j, j))
+                    for i in range(P, M):
+                        L.append(ind + "    g_%d_%d -= l_%d_%d * pv_%d_%d;" % (i, j2, i, j, j2, j))
+                        nfma += 1
+                L.append(ind + "}")
+        starts = list(range(P, M, W)) if P > 0 else list(range(0, M, W))
+        for j0 in starts:
             j1 = min(j0 + W, M)
             blk = list(range(j0, j1))
             L.append(ind + "IKB_PHASE_FENCE();")
@@ -738,7 +828,19 @@ class Generator:
         dq = self.gen_dq()
         integ = self.gen_integrate()
         rows, nslot = self.rows, len(self.slots)
-        solve = self.gen_solve(int(self.spec.get("block_width", 4)))
+        # presolve: the solver role factorises the leading block of its own task rows before the first barrier
+        P = 0
+        if self.spec.get("presolve") and len(groups) > 1 and not self.spec.get("parallel_solve"):
+            own = sorted(groups[solver])
+            if own == list(range(len(own))):  # its tasks are the first ones of the stacked order: rows 0..P-1
+                P = sum(self.tasks[t]["dim"] for t in own)
+        nstrict = rows * (rows - 1) // 2
+        self.eoff = P * (P - 1) // 2 if P else 0          # e lives where rows >= P of L will go (written after e was read)
+        self.yoff = self.eoff + rows                        # yp[0..P) of presolve
+        if P and self.yoff + P > nstrict:
+            raise ValueError("presolve: the factor strip cannot hold e and yp beside the leading block")
+        presolve = self.gen_presolve(P) if P else []
+        solve = self.gen_solve(int(self.spec.get("block_width", 4)), P)
         used = self.signature()
         nfact = max(rows * (rows + 1) // 2, rows + self.nq)  # the factor strip also carries e (M) and the stepped q (NQ)
         out = []
@@ -757,6 +859,9 @@ class Generator:
         out.append("    // PSOLVE: distribute the factorisation over the roles (pays off for large M; for M = 12 the ~7 extra group")
         out.append("    // barriers cost more than the shorter critical path saves -- measured, DESIGN.md 4.1)")
         out.append("    static constexpr bool PSOLVE = %s;" % ("true" if self.spec.get("parallel_solve") and len(groups) > 1 else "false"))
+        out.append("    // PRE: leading rows whose P x P factor block the SOLVER role computes in presolve(), before the first barrier;")
+        out.append("    // EOFF: slot of the factor strip where e starts (rows >= PRE of L, written only after e has been read)")
+        out.append("    static constexpr int PRE = %d, EOFF = %d;" % (P, self.eoff))
         out.append('    static const char *name() { return "%s"; }' % display_name)
         for k, (g, ev) in enumerate(zip(groups, evs)):
             names = ", ".join("%s %s" % (self.tasks[t]["name"], ("align-" + "xyz"[self.tasks[t]["ktype"]]) if self.tasks[t]["kind"] == "align"
@@ -785,6 +890,11 @@ class Generator:
         out.append("    static IKB_HD void evaluate(int role, const T (&q)[NQ], const S &tg, const SpecConsts<T, NQ, M> &c, const S &sJ, const S &sE) {")
         for k in range(len(groups)):
             out.append("        if (role == %d) evaluate_w%d(q, tg, c, sJ, sE);" % (k, k))
+        out.append("    }")
+        out.append("    // leading PRE x PRE block of the factorisation (solver role, right after its own evaluate)")
+        out.append("    template <typename T, typename S>")
+        out.append("    static IKB_HD void presolve(const S &sJ, const S &sL, const S &sE, T damping2) {")
+        out.extend(presolve)
         out.append("    }")
         out.append("    // y = (J J^T + damping^2 I)^-1 e: fused Gram + blocked LDL^T (factor -> strip sL) + substitutions.")
         out.append("    // Reads e from sE (may alias the start of sL), returns ||e[0..M0)||^2 (the stop-test quantity, visitor.hpp:19).")
