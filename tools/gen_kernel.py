@@ -487,10 +487,11 @@ class Generator:
         def Lidx(i, k):
             return i * (i - 1) // 2 + k
 
+        order, pos = self.order, self.pos  # elimination order: position -> task row, and back
         col_rows = {}
         for (r, c) in self.slots:
-            if r < P:
-                col_rows.setdefault(c, []).append(r)
+            if pos[r] < P:
+                col_rows.setdefault(c, []).append(pos[r])
         for c in col_rows:
             col_rows[c].sort()
         nfma = 0
@@ -498,12 +499,12 @@ class Generator:
         for j in range(P):
             for i in range(j, P):
                 L.append(ind + "T g_%d_%d = %s;" % (i, j, "damping2" if i == j else "T(0)"))
-            L.append(ind + "T g_e_%d = sE.get(%d);" % (j, j))
+            L.append(ind + "T g_e_%d = sE.get(%d);" % (j, order[j]))
         for c in sorted(col_rows):
             rs = col_rows[c]
             L.append(ind + "{  // J column %d" % c)
             for i in rs:
-                L.append(ind + "    const T a%d = sJ.get(%d);" % (i, self.slots[(i, c)]))
+                L.append(ind + "    const T a%d = sJ.get(%d);" % (i, self.slots[(order[i], c)]))
             for j in rs:
                 for i in rs:
                     if i >= j:
@@ -540,18 +541,24 @@ class Generator:
         def Lidx(i, k):
             return i * (i - 1) // 2 + k
 
-        col_rows = {}
+        order, pos = self.order, self.pos  # elimination order (the SOLVER role's rows first when it presolves): every
+        col_rows = {}                       # index below is a POSITION in that order; order[i] is the task row
         for (r, c) in self.slots:
-            col_rows.setdefault(c, []).append(r)
+            col_rows.setdefault(c, []).append(pos[r])
         for c in col_rows:
             col_rows[c].sort()
         nfma = 0
         L.append(ind + "T e[%d], yp[%d];  // yp = D^-1 L^-1 e, produced as the extra row of the factorisation" % (M, M))
         L.append(ind + "#pragma unroll")
-        L.append(ind + "for (int i = 0; i < %d; ++i) e[i] = sE.get(i);" % M)
+        if order == list(range(M)):
+            L.append(ind + "for (int i = 0; i < %d; ++i) e[i] = sE.get(i);" % M)
+        else:
+            L.pop()  # the #pragma unroll
+            for i in range(M):
+                L.append(ind + "e[%d] = sE.get(%d);" % (i, order[i]))
         L.append(ind + "T res = T(0);")
-        L.append(ind + "#pragma unroll")
-        L.append(ind + "for (int i = 0; i < %d; ++i) res += e[i] * e[i];  // visitor.hpp:19 (priority-0 rows)" % self.rows_p0)
+        for r in range(self.rows_p0):
+            L.append(ind + "res += e[%d] * e[%d];  // visitor.hpp:19 (priority-0 rows, in task-row order)" % (pos[r], pos[r]))
         L.append(ind + "IKB_PHASE_FENCE();  // sE may alias the factor strip: every e is in a register from here on")
         if P > 0:
             # ---- block column 0..P-1, rows P..M-1, against the pre-factorised P x P block ----
@@ -570,7 +577,7 @@ class Generator:
                     continue
                 L.append(ind + "{  // J column %d" % c)
                 for i in bj + lo:
-                    L.append(ind + "    const T a%d = sJ.get(%d);" % (i, self.slots[(i, c)]))
+                    L.append(ind + "    const T a%d = sJ.get(%d);" % (i, self.slots[(order[i], c)]))
                 for j in bj:
                     for i in lo:
                         L.append(ind + "    g_%d_%d += a%d * a%d;" % (i, j, i, j))
@@ -607,7 +614,7 @@ class Generator:
                 need = [i for i in rs if i >= bj[0]]
                 L.append(ind + "{  // J column %d" % c)
                 for i in need:
-                    L.append(ind + "    const T a%d = sJ.get(%d);" % (i, self.slots[(i, c)]))
+                    L.append(ind + "    const T a%d = sJ.get(%d);" % (i, self.slots[(order[i], c)]))
                 for j in bj:
                     for i in need:
                         if i >= j:
@@ -648,8 +655,8 @@ class Generator:
             for i in range(k):
                 L.append(ind + "yp[%d] -= sL.get(%d) * yp[%d];" % (i, Lidx(k, i), k))
                 nfma += 1
-        L.append(ind + "#pragma unroll")
-        L.append(ind + "for (int i = 0; i < %d; ++i) y[i] = yp[i];" % M)
+        for i in range(M):
+            L.append(ind + "y[%d] = yp[%d];" % (order[i], i))
         L.append(ind + "return res;")
         self.solve_fma = nfma
         return L
@@ -830,10 +837,14 @@ class Generator:
         rows, nslot = self.rows, len(self.slots)
         # presolve: the solver role factorises the leading block of its own task rows before the first barrier
         P = 0
+        self.order = list(range(rows))
+        self.pos = list(range(rows))
         if self.spec.get("presolve") and len(groups) > 1 and not self.spec.get("parallel_solve"):
-            own = sorted(groups[solver])
-            if own == list(range(len(own))):  # its tasks are the first ones of the stacked order: rows 0..P-1
-                P = sum(self.tasks[t]["dim"] for t in own)
+            own_rows = [self.tasks[t]["row"] + i for t in sorted(groups[solver]) for i in range(self.tasks[t]["dim"])]
+            P = len(own_rows)
+            # the solver role's rows are eliminated first (a symmetric permutation of the normal equations)
+            self.order = own_rows + [r for r in range(rows) if r not in own_rows]
+            self.pos = [self.order.index(r) for r in range(rows)]
         nstrict = rows * (rows - 1) // 2
         self.eoff = P * (P - 1) // 2 if P else 0          # e lives where rows >= P of L will go (written after e was read)
         self.yoff = self.eoff + rows                        # yp[0..P) of presolve
