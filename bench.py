@@ -277,6 +277,9 @@ def main():
     sampler.armed.clear()
     kernel_ms = [elapsed_ms / args.steps]
 
+    it_last = sets[(args.steps - 1) % nsets][2]["iters"].float()
+    it_hist = {"p50": it_last.quantile(0.5).item(), "p90": it_last.quantile(0.9).item(), "p95": it_last.quantile(0.95).item(),
+               "p99": it_last.quantile(0.99).item(), "at_max_iterations": (it_last >= 100).float().mean().item()}
     conv = 0
     evals = 0
     it_sum = 0
@@ -370,7 +373,8 @@ def main():
             probe, _, _, _ = cpu_reference_arm(min(sample, 4096), 1, 1, cores)
             passes = int(min(50, max(1, np.ceil(10.0 * probe / sample))))
             v, ms, cf, mi = cpu_reference_arm(sample, passes, 1, cores)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+            v1, _, _, _ = cpu_reference_arm(min(sample, 4096), 1, 0, 1)   # one thread, small sample (both)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "single_thread_value": v1,
                    "sample": "%d problems x %d passes of the same seeded workload (%.1f s); restated reference CPU path "
                              "(Pinocchio/Eigen unavailable), pthreads over all %d host cores"
                              % (sample, passes, passes * ms / 1e3, cores)}
@@ -386,7 +390,7 @@ def main():
                        "isolated_ms_per_batch": isolated_ms,
                        "isolated_value": conv * world / args.steps / (isolated_ms * 1e-3),
                        "converged_fraction": conv_all / (B * world * args.steps),
-                       "mean_iterations": it_all / (B * world * args.steps)},
+                       "mean_iterations": it_all / (B * world * args.steps), "iterations": it_hist},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * (nq + tsz) * itemsize),
                     "d2h_bytes_per_step": int(B * ((nq + 1) * itemsize + 5)), "steps": e2e_steps,
                     "api": "ikb_queue_submit_host + ikb_queue_wait (pinned host buffers; H2D, solve, D2H of every step)",

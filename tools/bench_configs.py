@@ -26,12 +26,16 @@ def main():
     from ik_b200 import workloads as W
 
     dev = torch.device("cuda:0")
+    demo = ik.dls_parameters(max_iterations=200, step_length=0.1, damping=0.1)  # cassie.cpp:107-109 (secondary set)
     cases = [("cassie feet+pelvis B=4096", W.cassie_feet_pelvis_problem, 4096, "standing", ("f64", "f32")),
+             ("cassie feet+pelvis B=65536, demo parameters (200 / 0.1 / 0.1)", W.cassie_feet_pelvis_problem, 65536, "standing", ("f64",), demo),
              ("cassie demo task set (cassie.cpp:43-81) B=65536", W.cassie_demo_problem, 65536, "standing", ("f64", "f32")),
              ("cassie feet+pelvis B=65536", W.cassie_feet_pelvis_problem, 65536, "standing", ("f64", "f32")),
              ("humanoid 5 Full tasks B=262144", W.humanoid_problem, 262144, "near", ("f64", "f32")),
              ("manipulator 1 Full task B=1048576", W.manipulator_problem, 1048576, "near", ("f64", "f32"))]
-    for name, make, B, start, dtypes in cases:
+    for case in cases:
+        name, make, B, start, dtypes = case[:5]
+        prm = case[5] if len(case) > 5 else None
         B = max(64, int(B * args.scale))
         pb = make()
         pb.finalize(0)
@@ -48,12 +52,12 @@ def main():
             tdt = torch.float64 if dt == "f64" else torch.float32
             q0_d = torch.tensor(q0.T.copy(), dtype=tdt, device=dev)
             tg_d = torch.tensor(tg.T.copy(), dtype=tdt, device=dev)
-            out = ik.dls_batch(pb, q0_d, tg_d)
+            out = ik.dls_batch(pb, q0_d, tg_d, prm)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(args.steps):
-                out = ik.dls_batch(pb, q0_d, tg_d, None, out)
+                out = ik.dls_batch(pb, q0_d, tg_d, prm, out)
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / args.steps
@@ -62,13 +66,13 @@ def main():
             queue = ik.SolveQueue(pb, 8, 4)
             outs = [None] * 4
             for k in range(4):
-                _, outs[k] = queue.submit(q0_d, tg_d, None, outs[k])
+                _, outs[k] = queue.submit(q0_d, tg_d, prm, outs[k])
             queue.drain()
             nq_steps = max(4, args.steps // 4 * 4)
             e0.record()
             last = None
             for k in range(nq_steps):
-                last, outs[k % 4] = queue.submit(q0_d, tg_d, None, outs[k % 4])
+                last, outs[k % 4] = queue.submit(q0_d, tg_d, prm, outs[k % 4])
             queue.flush()
             queue.wait_on_stream(last)
             e1.record()
