@@ -132,3 +132,60 @@ def test_queue_with_generic_kernel_and_empty_batch():
         for k in ("q", "success", "iters", "resid"):
             assert torch.equal(o[k], ref[k])
     assert o1["q"].shape[1] == 0
+
+
+def test_merged_large_batches_f32_and_stream_wait(cassie):
+    """FP32 two-launch batches merged (BULK thread-per-problem + TAIL team-per-problem, both with the segment table):
+    the step at which a straggler changes arithmetic depends on scheduling, so the comparison with the per-batch calls is
+    to the FP32 bar, not bit for bit.  Also: depth = merge = 1 degenerates to the plain call; wait_on_stream chains a
+    consumer stream instead of blocking the host."""
+    torch = _torch()
+    pb, om, opb = cassie
+    pb.finalize(0)
+    sizes = [11000, 16000, 12000]
+    data = [make_workload(pb, om, B, seed=400 + i, standing=W.CASSIE_STANDING) for i, B in enumerate(sizes)]
+    dev = [(_dev(torch, q0, torch.float32), _dev(torch, tg, torch.float32)) for q0, tg, _ in data]
+    ref = [ik.dls_batch(pb, a, b) for a, b in dev]
+    torch.cuda.synchronize()
+    queue = ik.SolveQueue(pb, depth=4, merge=3)
+    got = [queue.submit(a, b) for a, b in dev]
+    consumer = torch.cuda.Stream()
+    sums = []
+    with torch.cuda.stream(consumer):
+        for t, out in got:
+            queue.wait_on_stream(t, consumer.cuda_stream)
+            sums.append(out["success"].sum())          # enqueued on the consumer stream, after the batch
+    consumer.synchronize()
+    for (t, out), r, n in zip(got, ref, sums):
+        assert int(n.item()) == int(out["success"].sum().item())
+        same = (out["success"] == r["success"]) & (out["iters"] == r["iters"])
+        ok = r["success"].bool() & same
+        assert same.float().mean().item() > 0.97
+        assert (out["q"] - r["q"]).abs()[:, ok].max().item() < 3e-3
+    queue.drain()
+    # degenerate queue: one slot, no merging -> exactly the plain FP64 call
+    a64, b64 = _dev(torch, data[0][0]), _dev(torch, data[0][1])
+    r64 = ik.dls_batch(pb, a64, b64)
+    torch.cuda.synchronize()
+    q1 = ik.SolveQueue(pb, depth=1, merge=1)
+    for _ in range(3):  # the single slot is reused: submit blocks on the previous batch
+        t, o = q1.submit(a64, b64)
+    q1.wait(t)
+    for k in ("q", "success", "iters", "resid"):
+        assert torch.equal(o[k], r64[k])
+
+
+def test_queue_argument_errors(cassie):
+    from ik_b200 import _capi as capi
+
+    torch = _torch()
+    pb, _, _ = cassie
+    pb.finalize(0)
+    h = capi.C.c_void_p()
+    assert capi.lib.ikb_queue_create(pb._h, 0, 1, capi.C.byref(h)) == 1      # IKB_ERR_INVALID_ARG: depth
+    assert capi.lib.ikb_queue_create(pb._h, 4, 5, capi.C.byref(h)) == 1      # merge > depth
+    assert capi.lib.ikb_queue_create(pb._h, 16, 9, capi.C.byref(h)) == 1     # merge > 8
+    queue = ik.SolveQueue(pb, 2, 2)
+    assert capi.lib.ikb_queue_wait(queue._h, 0) == 1                          # no such ticket yet
+    assert capi.lib.ikb_queue_wait(queue._h, -1) == 1
+    queue.drain()                                                             # draining an empty queue is fine
