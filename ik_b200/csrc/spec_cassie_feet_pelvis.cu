@@ -3,7 +3,7 @@
 //
 // BULK (throughput): thread-per-problem, generated arithmetic; three decompositions are compiled
 // (ik_b200/specs/cassie_feet_pelvis*.json): one warp role (W1), two (pelvis+left | right+solve, W2) and three
-// (pelvis+solve | left | right, W3); the measured-best one per scalar type is the default, IKB_CASSIE_ROLES=1|2|3
+// (pelvis+solve | left | right, W3, with presolve); W3 is the measured-best one for both scalar types, IKB_CASSIE_ROLES=1|2|3
 // overrides it (tools/bench_variants.sh).
 // TAIL (latency): the team-per-problem kernel of dls_team.cuh -- 16 lanes share one problem -- for the stragglers a BULK
 // launch suspends and for batches too small to fill the GPU.  IKB_CASSIE_TAIL=0 selects the previous latency
@@ -105,7 +105,7 @@ int l64(const SpecHostConsts &hc, const SolveArgs<double> &a, int v, long long n
     return launch<double>(hc, a, v, n, sms, s, 3);
 }
 int l32(const SpecHostConsts &hc, const SolveArgs<float> &a, int v, long long n, int sms, cudaStream_t s) {
-    return launch<float>(hc, a, v, n, sms, s, 1);
+    return launch<float>(hc, a, v, n, sms, s, 3);  // with presolve the 3-role split wins in FP32 too (156 vs 145 M solves/s merged)
 }
 }  // namespace
 extern const SpecializedKernel kSpecCassieFeetPelvis = {S3::name(), spec_matches<S3>, l64, l32};
