@@ -277,6 +277,21 @@ def main():
     sampler.armed.clear()
     kernel_ms = [elapsed_ms / args.steps]
 
+    # optional final result gather: not part of the solve, timed and reported separately
+    gather_ms = None
+    if world > 1:
+        from ik_b200.sharding import gather_results
+
+        last_out = sets[(args.steps - 1) % nsets][2]
+        loc = {k: last_out[k] for k in ("q", "success", "iters")}
+        gather_results(loc, B * world, dist)      # warm-up (NCCL communicator set-up)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        gather_results(loc, B * world, dist)
+        g1.record()
+        barrier()
+        gather_ms = g0.elapsed_time(g1)
     it_last = sets[(args.steps - 1) % nsets][2]["iters"].float()
     it_hist = {"p50": it_last.quantile(0.5).item(), "p90": it_last.quantile(0.9).item(), "p95": it_last.quantile(0.95).item(),
                "p99": it_last.quantile(0.99).item(), "at_max_iterations": (it_last >= 100).float().mean().item()}
@@ -390,7 +405,8 @@ def main():
                        "isolated_ms_per_batch": isolated_ms,
                        "isolated_value": conv * world / args.steps / (isolated_ms * 1e-3),
                        "converged_fraction": conv_all / (B * world * args.steps),
-                       "mean_iterations": it_all / (B * world * args.steps), "iterations": it_hist},
+                       "mean_iterations": it_all / (B * world * args.steps), "iterations": it_hist,
+                       "result_gather_ms": gather_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * (nq + tsz) * itemsize),
                     "d2h_bytes_per_step": int(B * ((nq + 1) * itemsize + 5)), "steps": e2e_steps,
                     "api": "ikb_queue_submit_host + ikb_queue_wait (pinned host buffers; H2D, solve, D2H of every step)",
