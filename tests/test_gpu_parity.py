@@ -176,6 +176,34 @@ def test_cassie_demo_task_set(B, params, kernel_path):
     assert (np.abs(q[ok] - q_ref[ok]).max(axis=1) < 1e-6).mean() > 0.998
 
 
+@pytest.mark.parametrize("params", ["defaults", "demo"])
+def test_cassie_demo_with_posture_task(params):
+    """The demo's full declared task set (cassie.cpp:43-81 with the commented-out lines enabled): the three priority-0
+    tasks plus a PostureTask (posture.hpp:17-86; masked, weighted) on priority level 1 -- 26 stacked rows, stop test on the
+    priority-0 rows only (visitor.hpp:19).  No compiled specialisation: the table-driven kernel."""
+    m = W.cassie_model()
+    pb = W.cassie_demo_problem(m)
+    posture = ik.PostureTask(m, m.nq - 7)
+    posture.mask[:] = np.r_[np.ones(6), 0.0, np.ones(7), 0.0, 1.0]   # the two spring joints are left alone
+    posture.weighting()[:] = 0.05
+    pb.add_posture_task("posture", posture, 1)
+    pb.finalize(0)
+    assert pb.kernel_name().startswith("generic<")
+    om = oracle_model("cassie")
+    opb = oracle_problem_like(pb, om)
+    B = 600
+    q0, tg, qstar = make_workload(pb, om, B, seed=57, standing=W.CASSIE_STANDING)
+    off = pb.target_offset(posture)
+    tg[:, off:off + 16] = qstar[:, 7:]      # the posture the targets were generated from
+    if params == "defaults":
+        prm, oprm = None, O.params()
+    else:
+        prm, oprm = ik.dls_parameters(max_iterations=200, step_length=0.1, damping=0.1), O.params(200, 0.1, 0.1)
+    ref = O.dls_batch(opb, q0, tg, oprm, nthreads=NT)
+    _compare("cassie demo + posture %s" % params, _solve_gpu(pb, q0, tg, prm), ref, 1e-6, min_same_frac=0.9,
+             converged_only=True)
+
+
 def test_cassie_f32_defaults():
     """FP32 instantiation against the FP64 oracle.  The discrete stop decision may differ on a few problems (SURVEY 7
     'FP32 parity of the discrete stop decision'); where it agrees the bar is 1e-4 rad.  Measured: median 2e-6, 99th
