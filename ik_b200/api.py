@@ -405,7 +405,8 @@ def dls_batch(problem, q0, targets, p=None, out=None, stream=None):
 class SolveQueue:
     """Pipelined stream of batches (ikb_queue_*, include/ikb200.h): up to ``depth`` batches in flight, ``merge``
     consecutive batches per kernel pair (the ~0.7 ms straggler chain is paid once per group), host-buffer copies of one
-    group beside the kernels of its neighbours.  Results are those of dls_batch / dls_batch_host, bit for bit.
+    group beside the kernels of its neighbours.  Results are those of dls_batch / dls_batch_host (bit for bit in FP64 when
+    both take the same kernels, to rounding otherwise; see include/ikb200.h).
 
         queue = ik.SolveQueue(problem, depth=8, merge=4)
         tickets = [queue.submit(q0_k, targets_k, out=out_k) for ...]     # device tensors (torch, SoA)

@@ -172,7 +172,10 @@ int ikb_dls_solve(ikb_problem *p, const ikb_dls_params *params, const double *q0
  * on three internal streams (copy-in, compute, copy-out) and launches `merge` consecutive batches as ONE kernel pair,
  * so the straggler chain is paid once per group and -- with host buffers -- the PCIe copies of one group run beside
  * the kernels of its neighbours.  Batches of a group must share dtype and solver parameters (a change starts a new
- * group).  Results are those of ikb_dls_solve_batch, bit for bit.  One thread drives a queue. */
+ * group).  Results are those of ikb_dls_solve_batch: bit for bit in FP64 whenever both take the same kernels (always
+ * for batches larger than the latency configuration holds), to rounding otherwise -- a merged group of small batches
+ * may run the thread-per-problem kernels where a lone small batch runs the team-per-problem one, and in FP32 the step
+ * at which a straggler changes kernels depends on scheduling.  One thread drives a queue. */
 typedef struct ikb_queue ikb_queue;
 int ikb_queue_create(ikb_problem *p, int depth /* 1..16 batches in flight */, int merge /* 1..min(depth, 8) */,
                      ikb_queue **out);
