@@ -22,6 +22,7 @@ template <typename T, int NQ, int M> struct SpecConsts {
 // A thread-private strip of shared memory: element k of thread t lives at base0[k * STRIDE + t], i.e. consecutive
 // lanes touch consecutive words (conflict-free for 4- and 8-byte scalars).  STRIDE = 1 gives a plain array (CPU).
 template <typename T, int STRIDE> struct Strip {
+    static constexpr int kStride = STRIDE;
     T *base;
     IKB_HD void set(int k, T v) const { base[k * STRIDE] = v; }
     IKB_HD T get(int k) const { return base[k * STRIDE]; }

@@ -194,6 +194,9 @@ class Generator:
         self.rows = row
         self.tsz = toff
         self.slots = {}  # (row, col) -> slot index
+        # mirror mode (gen_evaluate_mirrored): while the body of task A is emitted for the pair (A, B), quantities that
+        # differ between the two sides are emitted as side-dependent variables
+        self.mir = None
 
     def slot(self, row, col):
         key = (row, col)
@@ -208,7 +211,7 @@ class Generator:
             return world[j]
         jt = self.joints[j]
         par = jt["parent"]
-        P = jt["placement"]
+        P = self.mirror_placement(E, j, jt["placement"])
         PR, Pp = P[:9], P[9:]
         if par > 0:
             pw = self.fk_joint(E, par, world)
@@ -229,7 +232,7 @@ class Generator:
             w = dict(R=R, p=p, z=None, type=t)
         elif t in (J_RX, J_RY, J_RZ, J_RU):
             E.raw("T s%d, c%d;" % (j, j))
-            E.raw("sincos_(q[%d], &s%d, &c%d);" % (iq, j, j))
+            E.raw("sincos_(%s, &s%d, &c%d);" % (self.qref(j, iq), j, j))
             s, c = "s%d" % j, "c%d" % j
             if t == J_RU:
                 a = jt["axis"]
@@ -256,12 +259,82 @@ class Generator:
         elif t in (J_PX, J_PY, J_PZ, J_PU):
             a = jt["axis"] if t == J_PU else [1.0 if i == t - J_PX else 0.0 for i in range(3)]
             z = matvec(E, A, a, "z%d" % j)
-            p = [sop(E, [(z[i], "q[%d]" % iq)], "p%d" % j, p[i]) for i in range(3)]
+            p = [sop(E, [(z[i], self.qref(j, iq))], "p%d" % j, p[i]) for i in range(3)]
             w = dict(R=A, p=p, z=z, type=t)
         else:
             raise ValueError("unsupported joint type %d" % t)
         world[j] = w
         return w
+
+    # ---- mirrored tasks ----
+    def qref(self, j, iq):
+        """Expression of the configuration scalar of (revolute / prismatic) joint j."""
+        if self.mir and j in self.mir["jmap"]:
+            return "qm%d" % j
+        return "q[%d]" % iq
+
+    def mirror_placement(self, E, j, P):
+        """Placement of joint j; in mirror mode entries that differ on the other side become side-dependent variables."""
+        if not (self.mir and j in self.mir["jmap"]):
+            return P
+        PB = self.joints[self.mir["jmap"][j]]["placement"]
+        out = []
+        for i, (a, b) in enumerate(zip(P, PB)):
+            if a == b:
+                out.append(a)
+            else:
+                if (a == 0) != (b == 0) or abs(a) == 1.0 or abs(b) == 1.0:
+                    raise ValueError("mirror: joint %d placement entry %d has a different structure on the two sides" % (j, i))
+                out.append(E.var("side ? %s : %s" % (lit(b), lit(a)), "pm%d_" % j))
+        return out
+
+    def gen_evaluate_mirrored(self, ta, tb):
+        """ONE evaluate body for two tasks that are mirror images of each other (Cassie's feet): same chain structure, same
+        task type, placements equal up to a few entries.  `side` = 0 evaluates task ta, 1 task tb: the entries that differ
+        are side-dependent variables, the joint coordinates are selected once, and the row / slot / target offsets of the
+        other side are folded into the base pointers of the strips.  Both warp roles then run the SAME instructions -- in
+        lock step they share every instruction line they fetch (the kernels are instruction-fetch bound)."""
+        A, B = self.tasks[ta], self.tasks[tb]
+        if (A["kind"], A["ktype"], A["dim"], A["tsize"], len(A["chain"]), A["ref_name"]) != \
+                (B["kind"], B["ktype"], B["dim"], B["tsize"], len(B["chain"]), B["ref_name"]):
+            raise ValueError("mirror: tasks %d and %d differ in shape" % (ta, tb))
+        if A["frame"]["placement"] != B["frame"]["placement"] or not self.is_universe(A["ref"]):
+            raise ValueError("mirror: frame placements differ / moving reference frame")
+        jmap = {}
+        for ja, jb in zip(A["chain"], B["chain"]):
+            if ja != jb:
+                if self.joints[ja]["type"] != self.joints[jb]["type"] or self.joints[ja]["type"] in (J_RU, J_PU, J_FF):
+                    raise ValueError("mirror: joints %d / %d differ in type" % (ja, jb))
+                pa, pb = self.joints[ja]["parent"], self.joints[jb]["parent"]
+                if not (pa == pb or jmap.get(pa) == pb):
+                    raise ValueError("mirror: joints %d / %d hang off different parents" % (ja, jb))
+                jmap[ja] = jb
+        E = Emitter()
+        E.comment("side 0: task %d (%s), side 1: task %d (%s)" % (ta, A["name"], tb, B["name"]))
+        for ja, jb in jmap.items():
+            E.raw("const T qm%d = side ? q[%d] : q[%d];" % (ja, self.joints[jb]["idx_q"], self.joints[ja]["idx_q"]))
+        for i in range(A["dim"]):
+            E.raw("const T wm%d = side ? c.weight[%d] : c.weight[%d];" % (i, B["row"] + i, A["row"] + i))
+        s0 = len(self.slots)
+        self.mir = dict(jmap=jmap, row=A["row"], toff=A["toff"])
+        body = Emitter()
+        self.gen_task(body, ta, {})
+        self.mir = None
+        nA = len(self.slots) - s0
+        # the other side's Jacobian entries take the same slots, nA further on
+        for (r, cidx), k in list(self.slots.items()):
+            if k >= s0:
+                if cidx < 6 and self.joints[A["chain"][0]]["type"] == J_FF:
+                    cb = cidx  # free-flyer columns are shared
+                else:
+                    ja = next(j for j in A["chain"] if self.joints[j]["idx_v"] == cidx)
+                    cb = self.joints[jmap.get(ja, ja)]["idx_v"]
+                self.slots[(r - A["row"] + B["row"], cb)] = k + nA
+        E.raw("const S sJm{sJ.base + side * (%d * S::kStride)};  // the other side's slots" % nA)
+        E.raw("const S sEm{sE.base + side * (%d * S::kStride)};  // ... rows" % (B["row"] - A["row"]))
+        E.raw("const S tgm{tg.base + side * (%d * S::kStride)};  // ... target pose" % (B["toff"] - A["toff"]))
+        E.lines.extend(body.lines)
+        return E.lines
 
     def gen_evaluate(self, task_ids):
         """evaluate_w<k>(): FK of the joints supporting the tasks of one warp role, their weighted error rows (-> strip sE)
@@ -333,9 +406,11 @@ class Generator:
             n = ti
             toff = task["toff"]
             E.raw("T Rt%d[9], pt%d[3];" % (n, n))
+            tgn, sEn, sJn = ("tgm", "sEm", "sJm") if self.mir else ("tg", "sE", "sJ")
+            wexpr = (lambda r: "wm%d" % (r - task["row"])) if self.mir else (lambda r: "c.weight[%d]" % r)
             if self.is_universe(task["ref"]):
-                E.raw("for (int k = 0; k < 9; ++k) Rt%d[k] = tg[%d + k];" % (n, toff))
-                E.raw("for (int k = 0; k < 3; ++k) pt%d[k] = tg[%d + k];" % (n, toff + 9))
+                E.raw("for (int k = 0; k < 9; ++k) Rt%d[k] = %s[%d + k];" % (n, tgn, toff))
+                E.raw("for (int k = 0; k < 3; ++k) pt%d[k] = %s[%d + k];" % (n, tgn, toff + 9))
             else:
                 # oMt = oMr * target (frame.hpp:46-47).  The reference frame moves with q but compute_jacobian does not
                 # differentiate it (frame.hpp:169-181, SURVEY 8a note) -- neither does this code.
@@ -366,7 +441,7 @@ class Generator:
             src = {POSITION: ["lin%d[%d]" % (n, i) for i in range(3)], ORIENTATION: ["w%d[%d]" % (n, i) for i in range(3)],
                    FULL: ["lin%d[%d]" % (n, i) for i in range(3)] + ["w%d[%d]" % (n, i) for i in range(3)]}[kt]
             for i, s in enumerate(src):
-                E.raw("sE.set(%d, c.weight[%d] * %s);" % (row + i, row + i, s))
+                E.raw("%s.set(%d, %s * %s);" % (sEn, row + i, wexpr(row + i), s))
             top = kt in (POSITION, FULL)
             bot = kt in (ORIENTATION, FULL)
             brow = row + (3 if kt == FULL else 0)
@@ -375,7 +450,7 @@ class Generator:
 
             def store(r, col, val):
                 k = self.slot(r, col)
-                E.raw("sJ.set(%d, c.weight[%d] * %s);  // J[%d][%d]" % (k, r, lit(val), r, col))
+                E.raw("%s.set(%d, %s * %s);  // J[%d][%d]" % (sJn, k, wexpr(r), lit(val), r, col))
 
             chain = task["chain"]
             ff_self = ident and len(chain) == 1 and self.joints[chain[0]]["type"] == J_FF
@@ -831,7 +906,26 @@ class Generator:
         if sorted(t for g in groups for t in g) != list(range(len(self.tasks))):
             raise ValueError("warp_groups must partition the task list")
         solver = int(self.spec.get("solver_warp", 0))
-        evs = [self.gen_evaluate(g) for g in groups]
+        # mirrored task pairs (each alone in its warp role) share ONE evaluate body
+        mirrors = {}   # role index -> (shared body id, side)
+        shared = []    # bodies
+        for pair in self.spec.get("mirror", []):
+            ta, tb = pair
+            ra = next(k for k, g in enumerate(groups) if g == [ta])
+            rb = next(k for k, g in enumerate(groups) if g == [tb])
+            mirrors[ra] = (len(shared), 0)
+            mirrors[rb] = (len(shared), 1)
+            shared.append(None)
+        evs = []
+        for k, g in enumerate(groups):
+            if k in mirrors:
+                bid, side = mirrors[k]
+                if side == 0:
+                    pair = self.spec["mirror"][bid]
+                    shared[bid] = self.gen_evaluate_mirrored(pair[0], pair[1])
+                evs.append(None)
+            else:
+                evs.append(self.gen_evaluate(g))
         dq = self.gen_dq()
         integ = self.gen_integrate()
         rows, nslot = self.rows, len(self.slots)
@@ -886,10 +980,18 @@ class Generator:
                 out.append("#pragma unroll 4")
                 out.append("        for (int k = %d; k < %d; ++k) sT.set(k, tg[k * es]);" % (toff, toff + self.tasks[t]["tsize"]))
             out.append("    }")
+            if ev is None:
+                continue
             out.append("    // FK + task errors (-> sE) + weighted task Jacobian non-zeros (-> sJ)")
             out.append("    template <typename T, typename S>")
             out.append("    static IKB_HD void evaluate_w%d(const T (&q)[NQ], const S &tg, const SpecConsts<T, NQ, M> &c, const S &sJ, const S &sE) {" % k)
             out.extend(ev)
+            out.append("    }")
+        for bid, body in enumerate(shared):
+            out.append("    // ---- shared by the roles of the mirrored tasks %s (side = 0 / 1) ----" % (self.spec["mirror"][bid],))
+            out.append("    template <typename T, typename S>")
+            out.append("    static IKB_HD void evaluate_m%d(const int side, const T (&q)[NQ], const S &tg, const SpecConsts<T, NQ, M> &c, const S &sJ, const S &sE) {" % bid)
+            out.extend(body)
             out.append("    }")
         out.append("    // role dispatch (warp-uniform)")
         out.append("    template <typename T, typename S>")
@@ -900,7 +1002,11 @@ class Generator:
         out.append("    template <typename T, typename S>")
         out.append("    static IKB_HD void evaluate(int role, const T (&q)[NQ], const S &tg, const SpecConsts<T, NQ, M> &c, const S &sJ, const S &sE) {")
         for k in range(len(groups)):
-            out.append("        if (role == %d) evaluate_w%d(q, tg, c, sJ, sE);" % (k, k))
+            if k not in mirrors:
+                out.append("        if (role == %d) evaluate_w%d(q, tg, c, sJ, sE);" % (k, k))
+        for bid in range(len(shared)):
+            ra, rb = [k for k, v in sorted(mirrors.items()) if v[0] == bid]
+            out.append("        if (role == %d || role == %d) evaluate_m%d(role == %d ? 1 : 0, q, tg, c, sJ, sE);  // one copy of the code for both" % (ra, rb, bid, rb))
         out.append("    }")
         out.append("    // leading PRE x PRE block of the factorisation (solver role, right after its own evaluate)")
         out.append("    template <typename T, typename S>")
