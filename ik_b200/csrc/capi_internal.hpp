@@ -61,6 +61,7 @@ struct ikb_problem {
     std::mutex scratch_mu;
     const ikb::SpecializedKernel *spec = nullptr;
     std::vector<double> weight_stacked;  // Task::weighting() rows in stacked order (constants of the specialised kernels)
+    std::vector<double> mask_stacked;    // posture masks per row, 1 for the rows of other tasks
     std::string kernel_name[2];
     // host-path staging (ikb_dls_solve_batch_host): main stream + the pipelined path's copy-in and second compute stream
     cudaStream_t stream = nullptr, stream_in = nullptr, stream_aux = nullptr;

@@ -230,9 +230,11 @@ template <class Spec> bool spec_matches(const HostProblem &hp) {
     // tasks must already be in stacked order (the generated code has no notion of insertion order)
     for (int t = 0; t < Spec::NTASKS; ++t) {
         const HostTask &ht = hp.tasks[t];
-        if (ht.kind != (Spec::sig_task_kind()[t] ? IKB_TASK_ALIGN_AXIS : IKB_TASK_FRAME)) return false;
-        if (ht.type != Spec::sig_task_type()[t] || ht.priority != Spec::sig_task_priority()[t]) return false;  // kinematic type / axis
+        const int kinds[3] = {IKB_TASK_FRAME, IKB_TASK_ALIGN_AXIS, IKB_TASK_POSTURE};
+        if (ht.kind != kinds[Spec::sig_task_kind()[t]]) return false;
+        if (ht.type != Spec::sig_task_type()[t] || ht.priority != Spec::sig_task_priority()[t]) return false;  // type / axis / nj
         if (t > 0 && ht.priority < hp.tasks[t - 1].priority) return false;
+        if (ht.kind == IKB_TASK_POSTURE) continue;  // no frames
         // the reference frame (`universe` or a moving frame) and the task frame must sit where the generator saw them
         if (m.frame_parent[ht.ref] != Spec::sig_task_ref_joint()[t]) return false;
         if (!same_values(m.frame_placement[ht.ref].data(), Spec::sig_task_ref_placement() + 12 * t, 12)) return false;
@@ -261,7 +263,10 @@ int launch_spec_cfg_seg(const SpecHostConsts &hc, const SolveArgs<T> &a, long lo
         c.lower[k] = (T)hc.lower[k];
         c.upper[k] = (T)hc.upper[k];
     }
-    for (int i = 0; i < Spec::M; ++i) c.weight[i] = (T)hc.weight[i];
+    for (int i = 0; i < Spec::M; ++i) {
+        c.weight[i] = (T)hc.weight[i];
+        c.mask[i] = (T)hc.mask[i];
+    }
     if (ctas < 1) ctas = 1;
     fn<<<(unsigned)ctas, GROUPS * Spec::NWARPS * 32, kSmem, s>>>(c, a);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;

@@ -501,8 +501,12 @@ int ikb_problem_finalize(ikb_problem *p, int device) {
     p->size_class = cls;
     p->device = device;
     p->weight_stacked.clear();
-    for (int t : order)
+    p->mask_stacked.clear();
+    for (int t : order) {
         for (double w : hp.tasks[t].weight) p->weight_stacked.push_back(w);
+        for (int i = 0; i < hp.tasks[t].dim; ++i)
+            p->mask_stacked.push_back(hp.tasks[t].kind == IKB_TASK_POSTURE ? hp.tasks[t].mask[i] : 1.0);
+    }
     p->spec = select_specialized(hp);
     char buf[96];
     std::snprintf(buf, sizeof buf, "generic<NJ=%d,NV=%d,M=%d>", kClasses[cls].nj, kClasses[cls].nv, kClasses[cls].m);

@@ -104,7 +104,7 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
     a.list_count = nullptr;
     a.iters_ws = merged ? nullptr : io->iters;
     if (p->spec) {
-        const SpecHostConsts hc{p->hp.model.lower.data(), p->hp.model.upper.data(), p->weight_stacked.data()};
+        const SpecHostConsts hc{p->hp.model.lower.data(), p->hp.model.upper.data(), p->weight_stacked.data(), p->mask_stacked.data()};
         // Scheduling.  A batch that the latency configuration keeps resident in one wave runs there
         // directly.  A larger batch runs BULK (throughput configuration) with a step cap: the few problems still
         // unfinished after `cap` steps -- the reference lets them run to max_iterations, 100 by default -- are suspended

@@ -17,6 +17,7 @@ namespace ikb {
 template <typename T, int NQ, int M> struct SpecConsts {
     T lower[NQ], upper[NQ];  // model.lowerPositionLimit / upperPositionLimit (common.hpp:54-55)
     T weight[M];             // Task::weighting() rows in stacked order (task.hpp:40, data.cpp:49-50)
+    T mask[M];               // PostureTask::mask per row (posture.hpp:52), 1 for the rows of other tasks
 };
 
 // A thread-private strip of shared memory: element k of thread t lives at base0[k * STRIDE + t], i.e. consecutive

@@ -11,9 +11,10 @@ extern const SpecializedKernel kSpecCassieFeetPelvis;
 extern const SpecializedKernel kSpecManipulatorTool;
 extern const SpecializedKernel kSpecHumanoidLimbs;
 extern const SpecializedKernel kSpecCassieDemo;
+extern const SpecializedKernel kSpecCassieDemoPosture;
 
 namespace {
-const SpecializedKernel *const kRegistry[] = {&kSpecCassieFeetPelvis, &kSpecManipulatorTool, &kSpecHumanoidLimbs, &kSpecCassieDemo, nullptr};
+const SpecializedKernel *const kRegistry[] = {&kSpecCassieFeetPelvis, &kSpecManipulatorTool, &kSpecHumanoidLimbs, &kSpecCassieDemo, &kSpecCassieDemoPosture, nullptr};
 }
 
 const SpecializedKernel *const *specialized_registry() { return kRegistry; }

@@ -13,6 +13,7 @@ namespace ikb {
 struct SpecHostConsts {
     const double *lower, *upper;  // [nq]
     const double *weight;         // [rows], stacked order
+    const double *mask;           // [rows]: posture masks, 1 elsewhere
 };
 
 // BULK: throughput configuration (persistent, one CTA per SM).  TAIL: latency configuration (one 32-problem group per

@@ -9,7 +9,8 @@ translation (ik_ros/src/cassie.cpp:95-96).  The initial guess is the SRDF standi
 """
 import numpy as np
 
-from .api import AlignAxisTask, AlignAxisType, FrameTask, InverseKinematicsProblem, KinematicType, Model
+from .api import (AlignAxisTask, AlignAxisType, FrameTask, InverseKinematicsProblem, KinematicType, Model,
+                  PostureTask)
 
 # cassie-description/srdf/cassie.srdf:22-39 (group_state "default"), in model joint order
 CASSIE_STANDING = [0.0045, 0.0, 0.4973, -1.1997, 0.0, 1.4267, 0.0, -1.5968,
@@ -133,6 +134,18 @@ def cassie_demo_problem(model=None):
     return pb
 
 
+def cassie_demo_posture_problem(model=None):
+    """The demo's full declared task set (cassie.cpp:43-81 with the commented-out posture line enabled): cassie_demo_problem
+    plus a PostureTask on the 16 revolutes at priority level 1, spring joints masked out, weight 0.05.  26 task rows."""
+    model = model or cassie_model()
+    pb = cassie_demo_problem(model)
+    posture = PostureTask(model, model.nq - 7)
+    posture.mask[:] = [1, 1, 1, 1, 1, 1, 0, 1, 1, 1, 1, 1, 1, 1, 0, 1]
+    posture.weighting()[:] = 0.05
+    pb.add_posture_task("posture", posture, 1)
+    return pb
+
+
 def frame_task_list(problem):
     return [(t, problem.target_offset(t)) for _, t, _ in problem._tasks if isinstance(t, FrameTask)]
 
@@ -145,7 +158,7 @@ def _rel(Mr, Mf):
     return np.concatenate([R.reshape(-1, 9), p], axis=1)
 
 
-def targets_from_frame_poses(problem, poses):
+def targets_from_frame_poses(problem, poses, qstar=None):
     """poses: dict frame name -> [B, 12] world placements at q* (task frames and their reference frames).  Returns targets
     [B, tsz] (AoS) that q* satisfies exactly: frame tasks get the frame's placement relative to the reference frame,
     align-axis tasks the frame's own axis (scaled by 2: the task normalises it, frame.hpp:264)."""
@@ -166,6 +179,8 @@ def targets_from_frame_poses(problem, poses):
         elif isinstance(t, AlignAxisTask):
             M = poses[t.frame] if t.reference_frame == "universe" else _rel(poses[t.reference_frame], poses[t.frame])
             tg[:, off:off + 3] = 2.0 * M[:, :9].reshape(-1, 3, 3)[:, :, int(t.axis)]
+        elif isinstance(t, PostureTask) and qstar is not None:
+            tg[:, off:off + t.nj] = qstar[:, problem.model().nq - t.nj:]   # the posture the other targets come from
     return tg
 
 

@@ -49,7 +49,7 @@ def make_workload(problem, omodel, B, seed=12345, standing=None, b0=0, start="st
     m = problem.model()
     qstar = W.sample_configurations(m, B, seed, b0)
     poses = oracle_frame_poses(omodel, qstar, W.task_frames(problem))
-    targets = W.targets_from_frame_poses(problem, poses)
+    targets = W.targets_from_frame_poses(problem, poses, qstar)
     if start == "near":
         q0 = W.near_start(m, qstar, seed, b0)
     else:

@@ -12,17 +12,21 @@
 #include "../../ik_b200/csrc/gen/humanoid_limbs.cuh"
 #include "../../ik_b200/csrc/gen/manipulator_tool.cuh"
 #include "../../ik_b200/csrc/gen/cassie_demo.cuh"
+#include "../../ik_b200/csrc/gen/cassie_demo_posture.cuh"
 
 using namespace ikb;
 
 template <class Spec, typename T>
-static int spec_solve(const double *lower, const double *upper, const double *weight, const double *q0, const double *targets,
-                      int max_it, double step, double damping, double tol, double *q_out, int *iters, double *resid,
-                      double *e_first, bool parallel = false) {
+static int spec_solve(const double *lower, const double *upper, const double *weight, const double *mask, const double *q0,
+                      const double *targets, int max_it, double step, double damping, double tol, double *q_out, int *iters,
+                      double *resid, double *e_first, bool parallel = false) {
     constexpr int NQ = Spec::NQ, NV = Spec::NV, M = Spec::M;
     SpecConsts<T, NQ, M> c;
     for (int k = 0; k < NQ; ++k) { c.lower[k] = (T)lower[k]; c.upper[k] = (T)upper[k]; }
-    for (int i = 0; i < M; ++i) c.weight[i] = (T)weight[i];
+    for (int i = 0; i < M; ++i) {
+        c.weight[i] = (T)weight[i];
+        c.mask[i] = mask ? (T)mask[i] : T(1);
+    }
     std::vector<T> bufJ(Spec::NSLOT), bufL(Spec::NFACT), bufT(Spec::TSZ), tgt(targets, targets + Spec::TSZ);
     const Strip<T, 1> sJ{bufJ.data()}, sL{bufL.data()}, sT{bufT.data()};
     const Strip<T, 1> sE{bufL.data() + Spec::EOFF};  // e aliases part of the factor strip, as in the kernel
@@ -69,7 +73,10 @@ template <class Spec>
 static void spec_eval(const double *weight, const double *q0, const double *targets, double *e_out, double *J_out) {
     constexpr int NQ = Spec::NQ, NV = Spec::NV, M = Spec::M;
     SpecConsts<double, NQ, M> c{};
-    for (int i = 0; i < M; ++i) c.weight[i] = weight[i];
+    for (int i = 0; i < M; ++i) {
+        c.weight[i] = weight[i];
+        c.mask[i] = 1.0;
+    }
     std::vector<double> bufJ(Spec::NSLOT), bufT(targets, targets + Spec::TSZ), bufE(M);
     const Strip<double, 1> sJ{bufJ.data()}, sT{bufT.data()}, sE{bufE.data()};
     double q[NQ];
@@ -81,17 +88,20 @@ static void spec_eval(const double *weight, const double *q0, const double *targ
 }
 
 #define IKB_SPEC_EXPORT(fn, Spec)                                                                                        \
-    extern "C" int fn##_d(const double *lo, const double *hi, const double *w, const double *q0, const double *tg, int mi, \
-                          double st, double da, double tol, double *q, int *it, double *res, double *e0) {               \
-        return spec_solve<Spec, double>(lo, hi, w, q0, tg, mi, st, da, tol, q, it, res, e0);                             \
+    extern "C" int fn##_d(const double *lo, const double *hi, const double *w, const double *mk, const double *q0,       \
+                          const double *tg, int mi, double st, double da, double tol, double *q, int *it, double *res,  \
+                          double *e0) {                                                                                  \
+        return spec_solve<Spec, double>(lo, hi, w, mk, q0, tg, mi, st, da, tol, q, it, res, e0);                         \
     }                                                                                                                    \
-    extern "C" int fn##_f(const double *lo, const double *hi, const double *w, const double *q0, const double *tg, int mi, \
-                          double st, double da, double tol, double *q, int *it, double *res, double *e0) {               \
-        return spec_solve<Spec, float>(lo, hi, w, q0, tg, mi, st, da, tol, q, it, res, e0);                              \
+    extern "C" int fn##_f(const double *lo, const double *hi, const double *w, const double *mk, const double *q0,       \
+                          const double *tg, int mi, double st, double da, double tol, double *q, int *it, double *res,  \
+                          double *e0) {                                                                                  \
+        return spec_solve<Spec, float>(lo, hi, w, mk, q0, tg, mi, st, da, tol, q, it, res, e0);                          \
     }                                                                                                                    \
-    extern "C" int fn##_pd(const double *lo, const double *hi, const double *w, const double *q0, const double *tg, int mi, \
-                           double st, double da, double tol, double *q, int *it, double *res, double *e0) {              \
-        return spec_solve<Spec, double>(lo, hi, w, q0, tg, mi, st, da, tol, q, it, res, e0, true);                       \
+    extern "C" int fn##_pd(const double *lo, const double *hi, const double *w, const double *mk, const double *q0,      \
+                           const double *tg, int mi, double st, double da, double tol, double *q, int *it, double *res, \
+                           double *e0) {                                                                                 \
+        return spec_solve<Spec, double>(lo, hi, w, mk, q0, tg, mi, st, da, tol, q, it, res, e0, true);                   \
     }                                                                                                                    \
     extern "C" void fn##_eval(const double *w, const double *q0, const double *tg, double *e, double *J) {               \
         spec_eval<Spec>(w, q0, tg, e, J);                                                                                \
@@ -103,3 +113,4 @@ IKB_SPEC_EXPORT(h_spec_cassie_feet_pelvis_w2, SpecCassieFeetPelvisW2)
 IKB_SPEC_EXPORT(h_spec_manipulator_tool, SpecManipulatorTool)
 IKB_SPEC_EXPORT(h_spec_humanoid_limbs, SpecHumanoidLimbs)
 IKB_SPEC_EXPORT(h_spec_cassie_demo, SpecCassieDemo)
+IKB_SPEC_EXPORT(h_spec_cassie_demo_posture, SpecCassieDemoPosture)

@@ -91,9 +91,11 @@ def test_device_integrate_freeflyer_matches_oracle(math_lib):
 def _spec_solve(lib, name, dtype, pb, q0, tg, prm):
     m = pb.model()
     fn = getattr(lib, "h_spec_%s_%s" % (name, {"f64": "d", "f32": "f", "f64p": "pd"}[dtype]))
-    fn.argtypes = [_dp, _dp, _dp, _dp, _dp, C.c_int, C.c_double, C.c_double, C.c_double, _dp, C.POINTER(C.c_int), _dp, _dp]
+    fn.argtypes = [_dp, _dp, _dp, _dp, _dp, _dp, C.c_int, C.c_double, C.c_double, C.c_double, _dp, C.POINTER(C.c_int), _dp, _dp]
     lo, hi = np.ascontiguousarray(m.lowerPositionLimit), np.ascontiguousarray(m.upperPositionLimit)
     w = np.ascontiguousarray(np.concatenate([t.weighting() for _, t, _ in pb._tasks]))
+    mk = np.ascontiguousarray(np.concatenate([t.mask if isinstance(t, ik.PostureTask) else np.ones(t.dimension())
+                                              for _, t, _ in pb._tasks]))
     B = q0.shape[0]
     q = np.zeros((B, m.nq))
     ok = np.zeros(B, dtype=bool)
@@ -103,7 +105,7 @@ def _spec_solve(lib, name, dtype, pb, q0, tg, prm):
     for b in range(B):
         itc = C.c_int(0)
         r = C.c_double(0)
-        ok[b] = fn(_pd(lo), _pd(hi), _pd(w), _pd(np.ascontiguousarray(q0[b])), _pd(np.ascontiguousarray(tg[b])),
+        ok[b] = fn(_pd(lo), _pd(hi), _pd(w), _pd(mk), _pd(np.ascontiguousarray(q0[b])), _pd(np.ascontiguousarray(tg[b])),
                    prm.max_iterations, prm.step_length, prm.damping, prm.tolerance, _pd(q[b]), C.byref(itc), C.byref(r),
                    _pd(e0[b]))
         it[b], res[b] = itc.value, r.value
@@ -115,7 +117,8 @@ CASES = [("cassie_feet_pelvis", "cassie", True, W.cassie_feet_pelvis_problem, W.
          ("cassie_feet_pelvis_w2", "cassie", True, W.cassie_feet_pelvis_problem, W.CASSIE_STANDING),   # 2 roles
          ("manipulator_tool", "manipulator", False, W.manipulator_problem, "near"),
          ("humanoid_limbs", "humanoid", True, W.humanoid_problem, "near"),                              # 5 roles, 30 rows
-         ("cassie_demo", "cassie", True, W.cassie_demo_problem, W.CASSIE_STANDING)]   # moving reference frame + align-axis task
+         ("cassie_demo", "cassie", True, W.cassie_demo_problem, W.CASSIE_STANDING),   # moving reference frame + align-axis task
+         ("cassie_demo_posture", "cassie", True, W.cassie_demo_posture_problem, W.CASSIE_STANDING)]  # + masked posture, level 1
 
 
 def _workload(pb, om, B, standing):
@@ -189,6 +192,10 @@ def test_specialisation_matching_is_exact():
     assert pb.specialisation() == "cassie_feet_pelvis"
     # the reference demo's task set (moving reference frame + align-axis task) has its own fast path ...
     assert W.cassie_demo_problem().specialisation() == "cassie_demo"
+    assert W.cassie_demo_posture_problem().specialisation() == "cassie_demo_posture"
+    pb = W.cassie_demo_problem(m)
+    pb.add_posture_task("posture", ik.PostureTask(m, 8), 1)      # another number of coordinates: no fast path
+    assert pb.specialisation() is None
     # ... for exactly that reference frame and axis
     pb = ik.InverseKinematicsProblem(m, 1)
     pb.add_frame_task("fl", ik.FrameTask(m, "LeftFootFront", ik.KinematicType.Position, "pelvis"))

@@ -177,24 +177,18 @@ def test_cassie_demo_task_set(B, params, kernel_path):
 
 
 @pytest.mark.parametrize("params", ["defaults", "demo"])
-def test_cassie_demo_with_posture_task(params):
+def test_cassie_demo_with_posture_task(params, kernel_path):
     """The demo's full declared task set (cassie.cpp:43-81 with the commented-out lines enabled): the three priority-0
     tasks plus a PostureTask (posture.hpp:17-86; masked, weighted) on priority level 1 -- 26 stacked rows, stop test on the
-    priority-0 rows only (visitor.hpp:19).  No compiled specialisation: the table-driven kernel."""
-    m = W.cassie_model()
-    pb = W.cassie_demo_problem(m)
-    posture = ik.PostureTask(m, m.nq - 7)
-    posture.mask[:] = np.r_[np.ones(6), 0.0, np.ones(7), 0.0, 1.0]   # the two spring joints are left alone
-    posture.weighting()[:] = 0.05
-    pb.add_posture_task("posture", posture, 1)
-    pb.finalize(0)
-    assert pb.kernel_name().startswith("generic<")
+    priority-0 rows only (visitor.hpp:19).  Specialised kernel `cassie_demo_posture` and the table-driven one."""
+    pb = W.cassie_demo_posture_problem()
+    _check_path(pb, kernel_path, "cassie_demo_posture")
     om = oracle_model("cassie")
     opb = oracle_problem_like(pb, om)
-    B = 600
+    B = 600 if kernel_path == "generic" else 12000    # 12 000: BULK + TAIL
     q0, tg, qstar = make_workload(pb, om, B, seed=57, standing=W.CASSIE_STANDING)
-    off = pb.target_offset(posture)
-    tg[:, off:off + 16] = qstar[:, 7:]      # the posture the targets were generated from
+    off = pb.target_offset(pb.get_posture_task("posture"))
+    assert np.array_equal(tg[:, off:off + 16], qstar[:, 7:])      # the posture the other targets were generated from
     if params == "defaults":
         prm, oprm = None, O.params()
     else:

@@ -165,8 +165,18 @@ class Generator:
         if prios != sorted(prios):
             raise ValueError("spec tasks must be listed in stacked (priority) order")
         for t in spec["tasks"]:
-            f = self.frames[t["frame"]]
             kind = t.get("kind", "frame")
+            if kind == "posture":  # PostureTask (posture.hpp:17-86): the last nj coordinates, no frame
+                nj = int(t["nj"])
+                universe = self.frames["universe"]
+                self.tasks.append(dict(frame=universe, kind=kind, ktype=nj, dim=nj, row=row, toff=toff, tsize=nj, chain=[],
+                                       name="posture(%d)" % nj, ref=universe, ref_name="universe", priority=int(t.get("priority", 0))))
+                if int(t.get("priority", 0)) == 0:
+                    self.rows_p0 += nj
+                row += nj
+                toff += nj
+                continue
+            f = self.frames[t["frame"]]
             if kind == "frame":
                 ktype = {"position": POSITION, "orientation": ORIENTATION, "full": FULL}[t["type"]]
                 dim = 6 if ktype == FULL else 3
@@ -395,6 +405,8 @@ class Generator:
         """Error rows and Jacobian non-zeros of task ti (FK of its chain memoised in `world`)."""
         if self.tasks[ti]["kind"] == "align":
             return self.gen_align_task(E, ti, world)
+        if self.tasks[ti]["kind"] == "posture":
+            return self.gen_posture_task(E, ti)
         if True:
             task = self.tasks[ti]
             f = task["frame"]
@@ -507,6 +519,16 @@ class Generator:
                         m1z = matvec(E, M1, w["z"], "m1z")
                         for i in range(3):
                             store(row + i, iv, neg(E, m1z[i]))
+
+    def gen_posture_task(self, E, ti):
+        """PostureTask (posture.hpp:47-66): e = (q.bottomRows(nj) - target) .* mask, J.rightCols(nj) = I (the reference does
+        not apply the mask to J); both weighted by the task's row weights (data.cpp:49-50)."""
+        task = self.tasks[ti]
+        nj, row, toff = task["dim"], task["row"], task["toff"]
+        E.comment("==== task %d: posture of the last %d coordinates ====" % (ti, nj))
+        for i in range(nj):
+            E.raw("sE.set(%d, c.weight[%d] * ((q[%d] - tg[%d]) * c.mask[%d]));" % (row + i, row + i, self.nq - nj + i, toff + i, row + i))
+            E.raw("sJ.set(%d, c.weight[%d]);  // J[%d][%d]" % (self.slot(row + i, self.nv - nj + i), row + i, row + i, self.nv - nj + i))
 
     def gen_align_task(self, E, ti, world):
         """AlignAxisTask (frame.hpp:246-299): e = 1 - r . t^,  J = -(r x t^)^T R_rMf Jf_LOCAL.bottomRows(3), with r the
@@ -970,6 +992,7 @@ class Generator:
         out.append('    static const char *name() { return "%s"; }' % display_name)
         for k, (g, ev) in enumerate(zip(groups, evs)):
             names = ", ".join("%s %s" % (self.tasks[t]["name"], ("align-" + "xyz"[self.tasks[t]["ktype"]]) if self.tasks[t]["kind"] == "align"
+                                         else "" if self.tasks[t]["kind"] == "posture"
                                          else ["Position", "Orientation", "Full"][self.tasks[t]["ktype"]]) for t in g)
             out.append("    // ---- role %d: %s ----" % (k, names))
             out.append("    // copy this role's target poses into the strip sT")
@@ -1063,9 +1086,9 @@ class Generator:
                    ", ".join("%d, %d" % rc for rc, _ in inv))
         out.append("    static const int *sig_task_type() { static const int v[] = {%s}; return v; }" %
                    ", ".join(str(t["ktype"]) for t in self.tasks))
-        out.append("    // task kind (0 frame, 1 align-axis; for align tasks sig_task_type is the axis) and reference frame")
+        out.append("    // task kind (0 frame, 1 align-axis, 2 posture; sig_task_type is the axis / the number of coordinates for those)")
         out.append("    static const int *sig_task_kind() { static const int v[] = {%s}; return v; }" %
-                   ", ".join("1" if t["kind"] == "align" else "0" for t in self.tasks))
+                   ", ".join({"frame": "0", "align": "1", "posture": "2"}[t["kind"]] for t in self.tasks))
         out.append("    static const int *sig_task_ref_joint() { static const int v[] = {%s}; return v; }" %
                    ", ".join(str(t["ref"]["parent"]) for t in self.tasks))
         rpl = []
