@@ -642,3 +642,240 @@ void iko_dls_batch(const iko_model *m, const iko_problem *pb, const iko_params *
         for (int t = 0; t < nthreads; ++t) pthread_join(th[t], 0);
     free(th); free(jobs);
 }
+
+/* ======================================================================================================
+ * ik::pik -- priority-based IK (reference ik/ik/pik.cpp:5-96, pik.hpp:13-57).  SURVEY 8f rank 2.
+ * ====================================================================================================== */
+
+/* Thin SVD of A (m x n, row-major, m <= n) by one-sided Jacobi on the rows: A = U diag(s) V^T with U m x m, V n x m.
+ * (Eigen::JacobiSVD, pik.cpp:8-9, is a two-sided Jacobi; singular triplets are unique up to sign / order for distinct
+ * values, and damp_pseudoinverse sums over all of them, so any converged SVD gives the same matrix.) */
+static void svd_rows(int m, int n, const double *A, double *U, double *s, double *V) {
+    double *W = (double *)malloc(sizeof(double) * m * n); /* rows become s_i * v_i^T */
+    memcpy(W, A, sizeof(double) * m * n);
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) U[i * m + j] = (i == j);
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0;
+        for (int p = 0; p < m - 1; ++p)
+            for (int q = p + 1; q < m; ++q) {
+                double a = 0, b = 0, c = 0;
+                for (int k = 0; k < n; ++k) {
+                    a += W[p * n + k] * W[p * n + k];
+                    b += W[q * n + k] * W[q * n + k];
+                    c += W[p * n + k] * W[q * n + k];
+                }
+                if (fabs(c) <= 1e-300 || fabs(c) <= 1e-17 * sqrt(a * b)) continue;
+                off += fabs(c) / sqrt(a * b + 1e-300);
+                const double zeta = (b - a) / (2 * c);
+                const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1 + zeta * zeta));
+                const double cs = 1 / sqrt(1 + t * t), sn = cs * t;
+                for (int k = 0; k < n; ++k) {
+                    const double wp = W[p * n + k], wq = W[q * n + k];
+                    W[p * n + k] = cs * wp - sn * wq;
+                    W[q * n + k] = sn * wp + cs * wq;
+                }
+                for (int k = 0; k < m; ++k) { /* A = U W: rows of W rotated => columns of U rotated */
+                    const double up = U[k * m + p], uq = U[k * m + q];
+                    U[k * m + p] = cs * up - sn * uq;
+                    U[k * m + q] = sn * up + cs * uq;
+                }
+            }
+        if (off < 1e-15) break;
+    }
+    for (int i = 0; i < m; ++i) {
+        double nrm = 0;
+        for (int k = 0; k < n; ++k) nrm += W[i * n + k] * W[i * n + k];
+        nrm = sqrt(nrm);
+        s[i] = nrm;
+        for (int k = 0; k < n; ++k) V[k * m + i] = nrm > 0 ? W[i * n + k] / nrm : 0.0;
+    }
+    free(W);
+}
+
+/* damp_pseudoinverse(M, lambda) (pik.cpp:5-21): sum_i sigma_i / (lambda^2 + sigma_i^2) v_i u_i^T, n x m row-major */
+void iko_damp_pseudoinverse(int m, int n, const double *M, double lambda, double *out) {
+    double *U = (double *)malloc(sizeof(double) * m * m), *s = (double *)malloc(sizeof(double) * m);
+    double *V = (double *)malloc(sizeof(double) * n * m);
+    svd_rows(m, n, M, U, s, V);
+    memset(out, 0, sizeof(double) * n * m);
+    for (int i = 0; i < m; ++i) {
+        const double f = s[i] / (lambda * lambda + s[i] * s[i]);
+        for (int r = 0; r < n; ++r)
+            for (int c = 0; c < m; ++c) out[r * m + c] += f * V[r * m + i] * U[c * m + i];
+    }
+    free(U); free(s); free(V);
+}
+
+/* M.completeOrthogonalDecomposition().pseudoInverse() * M (pik.cpp:59-61): the orthogonal projector onto the row space of
+ * the numerically rank-r part of M (m x n).  Eigen's COD = Householder QR with column pivoting, rank r = number of pivots
+ * with |R_kk| > eps * min(m, n) * max_k |R_kk|, then the trailing block is zeroed from the right; pinv(M) M projects onto
+ * the span of the first r rows of Q^T M.  Those rows are orthonormalised here (modified Gram-Schmidt, twice) and the
+ * projector summed.  Returns r; proj is n x n row-major. */
+int iko_rowspace_projector(int m, int n, const double *M, double *proj) {
+    double *R = (double *)malloc(sizeof(double) * m * n);
+    int *perm = (int *)malloc(sizeof(int) * n);
+    memcpy(R, M, sizeof(double) * m * n);
+    for (int c = 0; c < n; ++c) perm[c] = c;
+    const int steps = m < n ? m : n;
+    double maxpiv = 0;
+    double *diag = (double *)malloc(sizeof(double) * steps);
+    for (int k = 0; k < steps; ++k) {
+        /* pivot: the remaining column with the largest norm below row k */
+        int best = k;
+        double bn = -1;
+        for (int c = k; c < n; ++c) {
+            double s = 0;
+            for (int r = k; r < m; ++r) s += R[r * n + c] * R[r * n + c];
+            if (s > bn) { bn = s; best = c; }
+        }
+        if (best != k) {
+            for (int r = 0; r < m; ++r) { double t = R[r * n + k]; R[r * n + k] = R[r * n + best]; R[r * n + best] = t; }
+            int t = perm[k]; perm[k] = perm[best]; perm[best] = t;
+        }
+        /* Householder on column k, rows k.. */
+        double nrm = sqrt(bn > 0 ? bn : 0);
+        if (nrm == 0) { diag[k] = 0; continue; }
+        const double alpha = R[k * n + k] >= 0 ? -nrm : nrm;
+        double *v = (double *)malloc(sizeof(double) * m);
+        double vn = 0;
+        for (int r = k; r < m; ++r) { v[r] = R[r * n + k]; }
+        v[k] -= alpha;
+        for (int r = k; r < m; ++r) vn += v[r] * v[r];
+        if (vn > 0)
+            for (int c = k; c < n; ++c) {
+                double s = 0;
+                for (int r = k; r < m; ++r) s += v[r] * R[r * n + c];
+                s = 2 * s / vn;
+                for (int r = k; r < m; ++r) R[r * n + c] -= s * v[r];
+            }
+        free(v);
+        diag[k] = fabs(R[k * n + k]);
+        if (diag[k] > maxpiv) maxpiv = diag[k];
+    }
+    int rank = 0;
+    const double thr = 2.220446049250313e-16 * (double)steps * maxpiv;
+    for (int k = 0; k < steps; ++k)
+        if (diag[k] > thr) ++rank;
+    /* rows 0..rank-1 of R, columns back in their original order */
+    double *W = (double *)malloc(sizeof(double) * (rank > 0 ? rank : 1) * n);
+    for (int r = 0; r < rank; ++r)
+        for (int c = 0; c < n; ++c) W[r * n + perm[c]] = (c >= r) ? R[r * n + c] : 0.0;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int r = 0; r < rank; ++r) {
+            for (int p = 0; p < r; ++p) {
+                double s = 0;
+                for (int c = 0; c < n; ++c) s += W[r * n + c] * W[p * n + c];
+                for (int c = 0; c < n; ++c) W[r * n + c] -= s * W[p * n + c];
+            }
+            double nr = 0;
+            for (int c = 0; c < n; ++c) nr += W[r * n + c] * W[r * n + c];
+            nr = sqrt(nr);
+            for (int c = 0; c < n; ++c) W[r * n + c] /= nr;
+        }
+    memset(proj, 0, sizeof(double) * n * n);
+    for (int r = 0; r < rank; ++r)
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) proj[i * n + j] += W[r * n + i] * W[r * n + j];
+    free(R); free(perm); free(diag); free(W);
+    return rank;
+}
+
+int iko_pik(const iko_model *m, const iko_problem *pb, const iko_pik_params *prm, const double *q0, const double *targets,
+            double *q_out, int *iters, double *resid, double *dq_out) {
+    const int nq = m->nq, nv = m->nv, rows = iko_total_rows(pb), r0 = iko_e_size(pb, 0);
+    double *q = (double *)malloc(sizeof(double) * nq), *qn = (double *)malloc(sizeof(double) * nq);
+    double *e = (double *)malloc(sizeof(double) * (rows + 1)), *J = (double *)malloc(sizeof(double) * (rows * nv + 1));
+    double *P = (double *)malloc(sizeof(double) * nv * nv), *Pj = (double *)malloc(sizeof(double) * nv * nv);
+    double *Jbar = (double *)malloc(sizeof(double) * (rows * nv + 1)), *dp = (double *)malloc(sizeof(double) * (rows * nv + 1));
+    double *de = (double *)malloc(sizeof(double) * (rows + 1));
+    double *dq = (double *)malloc(sizeof(double) * nv), *sdq = (double *)malloc(sizeof(double) * nv);
+    memcpy(q, q0, sizeof(double) * nq);                                      /* pik.cpp:34 */
+    int success = 0, it = 0;
+    double res = 0;
+    for (it = 0; it < prm->max_iterations; ++it) {                            /* pik.cpp:39 */
+        iko_evaluate(m, pb, q, targets, e, J);                                /* pik.cpp:41 */
+        for (int i = 0; i < nv * nv; ++i) P[i] = 0;                           /* pik.cpp:44-45 */
+        for (int i = 0; i < nv; ++i) { P[i * nv + i] = 1; dq[i] = 0; }
+        int row = 0;
+        for (int lvl = 0; lvl <= pb->max_priority_level; ++lvl) {             /* pik.cpp:47 */
+            const int mi = iko_e_size(pb, lvl);
+            const double *Ji = J + row * nv, *ei = e + row;
+            if (mi > 0) {
+                for (int r = 0; r < mi; ++r) {                                 /* de_bar = e_i - J_i dq (pik.cpp:49) */
+                    double s = 0;
+                    for (int c = 0; c < nv; ++c) s += Ji[r * nv + c] * dq[c];
+                    de[r] = ei[r] - s;
+                }
+                for (int r = 0; r < mi; ++r)                                   /* Jbar = J_i P (pik.cpp:51) */
+                    for (int c = 0; c < nv; ++c) {
+                        double s = 0;
+                        for (int k = 0; k < nv; ++k) s += Ji[r * nv + k] * P[k * nv + c];
+                        Jbar[r * nv + c] = s;
+                    }
+                iko_damp_pseudoinverse(mi, nv, Jbar, prm->lambda[lvl], dp);    /* pik.cpp:54-55 */
+                for (int c = 0; c < nv; ++c) {
+                    double s = 0;
+                    for (int r = 0; r < mi; ++r) s += dp[c * mi + r] * de[r];
+                    dq[c] -= s;
+                }
+                iko_rowspace_projector(mi, nv, Jbar, Pj);                      /* pik.cpp:58-61 */
+                for (int i = 0; i < nv * nv; ++i) P[i] -= Pj[i];
+            }
+            row += mi;
+        }
+        /* dq += P * da with da = 0 (pik.cpp:65, pik.hpp:39) */
+        res = 0;                                                              /* visitor.hpp:19 */
+        for (int i = 0; i < r0; ++i) res += e[i] * e[i];
+        if (res < prm->tolerance) { success = 1; break; }                     /* pik.cpp:67-70 */
+        for (int c = 0; c < nv; ++c) sdq[c] = prm->step_length * dq[c];
+        iko_integrate(m, q, sdq, qn);                                         /* pik.cpp:73-74 */
+        memcpy(q, qn, sizeof(double) * nq);
+        iko_clip(m, q);                                                       /* pik.cpp:77 */
+    }
+    memcpy(q_out, q, sizeof(double) * nq);
+    if (iters) *iters = it;
+    if (resid) *resid = res;
+    if (dq_out) memcpy(dq_out, dq, sizeof(double) * nv);
+    free(q); free(qn); free(e); free(J); free(P); free(Pj); free(Jbar); free(dp); free(de); free(dq); free(sdq);
+    return success;
+}
+
+typedef struct {
+    const iko_model *m; const iko_problem *pb; const iko_pik_params *prm;
+    int b0, b1;
+    const double *q0, *targets;
+    double *q_out; unsigned char *success; int *iters; double *resid;
+} pik_job;
+
+static void *pik_worker(void *arg) {
+    pik_job *j = (pik_job *)arg;
+    const int nq = j->m->nq, tsz = iko_target_size(j->pb);
+    for (int b = j->b0; b < j->b1; ++b) {
+        int it; double r;
+        int ok = iko_pik(j->m, j->pb, j->prm, j->q0 + (size_t)b * nq, j->targets + (size_t)b * tsz,
+                         j->q_out + (size_t)b * nq, &it, &r, 0);
+        j->success[b] = (unsigned char)ok;
+        if (j->iters) j->iters[b] = it;
+        if (j->resid) j->resid[b] = r;
+    }
+    return 0;
+}
+
+void iko_pik_batch(const iko_model *m, const iko_problem *pb, const iko_pik_params *prm, int B, const double *q0,
+                   const double *targets, double *q_out, unsigned char *success, int *iters, double *resid, int nthreads) {
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > B) nthreads = B > 0 ? B : 1;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
+    pik_job *jobs = (pik_job *)malloc(sizeof(pik_job) * nthreads);
+    for (int t = 0; t < nthreads; ++t) {
+        pik_job jb = {m, pb, prm, (int)((long long)B * t / nthreads), (int)((long long)B * (t + 1) / nthreads),
+                      q0, targets, q_out, success, iters, resid};
+        jobs[t] = jb;
+        if (nthreads == 1) pik_worker(&jobs[t]);
+        else pthread_create(&th[t], 0, pik_worker, &jobs[t]);
+    }
+    if (nthreads > 1)
+        for (int t = 0; t < nthreads; ++t) pthread_join(th[t], 0);
+    free(th); free(jobs);
+}

@@ -113,6 +113,24 @@ void iko_dls_batch(const iko_model *m, const iko_problem *pb, const iko_params *
                    const double *q0, const double *targets, double *q_out, unsigned char *success,
                    int *iters, double *resid, int nthreads);
 
+/* ---- ik::pik, priority-based IK (pik.cpp:5-96, pik.hpp:13-57) ---- */
+#define IKO_MAX_LEVELS 8
+typedef struct {
+    int max_iterations;              /* pik.hpp:14 (default 100) */
+    double step_length;              /* pik.hpp:16 (default 1.0) */
+    double tolerance;                /* visitor.hpp:19 */
+    double lambda[IKO_MAX_LEVELS];   /* pik_data::lambda, damping per priority level (pik.hpp:31: 1.0) */
+} iko_pik_params;
+/* damp_pseudoinverse(M, lambda) (pik.cpp:5-21): M m x n row-major (m <= n) -> out n x m */
+void iko_damp_pseudoinverse(int m, int n, const double *M, double lambda, double *out);
+/* M.completeOrthogonalDecomposition().pseudoInverse() * M (pik.cpp:59-61) -> proj n x n; returns the numerical rank */
+int iko_rowspace_projector(int m, int n, const double *M, double *proj);
+int iko_pik(const iko_model *m, const iko_problem *pb, const iko_pik_params *prm, const double *q0,
+            const double *targets, double *q_out, int *iters, double *resid, double *dq_out);
+void iko_pik_batch(const iko_model *m, const iko_problem *pb, const iko_pik_params *prm, int B, const double *q0,
+                   const double *targets, double *q_out, unsigned char *success, int *iters, double *resid,
+                   int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

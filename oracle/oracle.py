@@ -227,6 +227,68 @@ def dls_batch(problem, q0, targets, prm=None, nthreads=1):
     return q, ok.astype(bool), it, res
 
 
+class _CPikParams(C.Structure):
+    _fields_ = [("max_iterations", C.c_int), ("step_length", C.c_double), ("tolerance", C.c_double),
+                ("lam", C.c_double * 8)]
+
+
+def pik_params(max_iterations=100, step_length=1.0, lambdas=None, tolerance=1e-4):
+    """pik.hpp:13-18 and pik_data::lambda (pik.hpp:31: 1.0 per priority level)."""
+    lam = (C.c_double * 8)(*([1.0] * 8))
+    for i, v in enumerate(lambdas or []):
+        lam[i] = float(v)
+    return _CPikParams(max_iterations, step_length, tolerance, lam)
+
+
+def pik(problem, q0, targets, prm=None):
+    """ik::pik (pik.cpp:31-96) on one problem.  Returns q, success, iterations, resid, dq."""
+    prm = prm or pik_params()
+    m = problem.model
+    q = np.zeros(m.nq)
+    dq = np.zeros(m.nv)
+    it = C.c_int(0)
+    res = C.c_double(0)
+    ok = lib().iko_pik(C.byref(m.c), C.byref(problem.c), C.byref(prm), _pd(_d(q0)), _pd(_d(targets)), _pd(q),
+                       C.byref(it), C.byref(res), _pd(dq))
+    return q, bool(ok), it.value, res.value, dq
+
+
+def pik_batch(problem, q0, targets, prm=None, nthreads=1):
+    """Loop of ik::pik over a batch.  q0 [B, nq], targets [B, target_size] (AoS)."""
+    prm = prm or pik_params()
+    m = problem.model
+    q0 = _d(q0)
+    targets = _d(targets)
+    B = q0.shape[0]
+    assert q0.shape == (B, m.nq) and targets.shape == (B, problem.target_size)
+    q = np.zeros((B, m.nq))
+    ok = np.zeros(B, dtype=np.uint8)
+    it = np.zeros(B, dtype=np.int32)
+    res = np.zeros(B)
+    lib().iko_pik_batch(C.byref(m.c), C.byref(problem.c), C.byref(prm), C.c_int(B), _pd(q0), _pd(targets), _pd(q),
+                        ok.ctypes.data_as(C.POINTER(C.c_ubyte)), _pi(it), _pd(res), C.c_int(nthreads))
+    return q, ok.astype(bool), it, res
+
+
+def damp_pseudoinverse(M, lam):
+    """damp_pseudoinverse (pik.cpp:5-21): M [m, n] -> [n, m]."""
+    M = _d(M)
+    m, n = M.shape
+    out = np.zeros((n, m))
+    lib().iko_damp_pseudoinverse(C.c_int(m), C.c_int(n), _pd(M), C.c_double(lam), _pd(out))
+    return out
+
+
+def rowspace_projector(M):
+    """pinv(M) @ M through the restated complete orthogonal decomposition (pik.cpp:59-61).  Returns (P [n, n], rank)."""
+    M = _d(M)
+    m, n = M.shape
+    out = np.zeros((n, n))
+    lib().iko_rowspace_projector.restype = C.c_int
+    r = lib().iko_rowspace_projector(C.c_int(m), C.c_int(n), _pd(M), _pd(out))
+    return out, int(r)
+
+
 def ldlt_solve(A, b):
     A = _d(A).copy()
     n = A.shape[0]
