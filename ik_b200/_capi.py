@@ -35,6 +35,11 @@ class BatchIO(C.Structure):
                 ("success", C.c_void_p), ("iters", C.c_void_p), ("resid", C.c_void_p)]
 
 
+class PikParams(C.Structure):
+    _fields_ = [("max_iterations", C.c_int32), ("step_length", C.c_double), ("tolerance", C.c_double),
+                ("lam", C.c_double * 7)]
+
+
 class ModelDesc(C.Structure):
     _fields_ = [("njoints", C.c_int32), ("parent", C.POINTER(C.c_int32)), ("jtype", C.POINTER(C.c_int32)),
                 ("placement", C.POINTER(C.c_double)), ("axis", C.POINTER(C.c_double)),
@@ -84,6 +89,9 @@ SIGNATURES = {
     "ikb_dls_solve_batch": (C.c_int, [_vp, C.c_int, C.POINTER(DlsParams), C.c_int64, C.POINTER(BatchIO), _vp]),
     "ikb_dls_solve_batch_host": (C.c_int, [_vp, C.c_int, C.POINTER(DlsParams), C.c_int64, C.POINTER(BatchIO)]),
     "ikb_dls_solve": (C.c_int, [_vp, C.POINTER(DlsParams), _dp, _dp, _dp, C.POINTER(C.c_int), C.POINTER(C.c_int), _dp]),
+    "ikb_pik_params_default": (None, [C.POINTER(PikParams)]),
+    "ikb_pik_solve_batch": (C.c_int, [_vp, C.c_int, C.POINTER(PikParams), C.c_int64, C.POINTER(BatchIO), _vp]),
+    "ikb_pik_solve_batch_host": (C.c_int, [_vp, C.c_int, C.POINTER(PikParams), C.c_int64, C.POINTER(BatchIO)]),
     "ikb_queue_create": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
     "ikb_queue_flush": (C.c_int, [_vp]),
     "ikb_queue_free": (None, [_vp]),

@@ -178,6 +178,26 @@ class dls_parameters:  # dls.hpp:24-28 + common.hpp:59-66
                               self.damping, self.tolerance)
 
 
+class pik_parameters:  # pik.hpp:13-18 + pik_data::lambda (pik.hpp:31)
+    def __init__(self, max_iterations=100, damping=1e-2, step_length=1.0, max_time=1.0, lambdas=None, tolerance=1e-4):
+        self.max_iterations = max_iterations
+        self.damping = damping          # declared by the reference, never read (pik.cpp uses pik_data::lambda)
+        self.step_length = step_length
+        self.max_time = max_time
+        self.lambdas = list(lambdas) if lambdas is not None else []   # per priority level; missing levels: 1.0
+        self.tolerance = tolerance
+
+    def c(self):
+        p = capi.PikParams()
+        capi.lib.ikb_pik_params_default(C.byref(p))
+        p.max_iterations = int(self.max_iterations)
+        p.step_length = float(self.step_length)
+        p.tolerance = float(self.tolerance)
+        for i, v in enumerate(self.lambdas[:7]):
+            p.lam[i] = float(v)
+        return p
+
+
 class inverse_kinematics_visitor:  # visitor.hpp:7-24 -- the stop test itself runs in the kernel
     tolerance = 1e-4
 
@@ -400,6 +420,68 @@ def dls_batch(problem, q0, targets, p=None, out=None, stream=None):
     capi.check(capi.lib.ikb_dls_solve_batch(problem._h, _DT[dtype][0], C.byref(prm), B, C.byref(io), C.c_void_p(s)),
                "ikb_dls_solve_batch")
     return dict(q=q, success=success, iters=iters, resid=resid)
+
+
+def pik_batch(problem, q0, targets, p=None, out=None, stream=None):
+    """Batched ik::pik (pik.cpp:31-96) on DEVICE tensors; arguments and results as dls_batch."""
+    import torch
+
+    p = p or pik_parameters()
+    nq, tsz = problem.model().nq, problem.target_size
+    assert q0.is_cuda and targets.is_cuda and q0.dtype == targets.dtype
+    problem.finalize(q0.device.index or 0)
+    dtype = "f64" if q0.dtype == torch.float64 else "f32"
+    B = q0.shape[1]
+    assert q0.shape == (nq, B) and targets.shape == (tsz, B) and q0.is_contiguous() and targets.is_contiguous()
+    out = out or {}
+    q = out.get("q") if out.get("q") is not None else torch.empty((nq, B), dtype=q0.dtype, device=q0.device)
+    success = out.get("success") if out.get("success") is not None else torch.empty(B, dtype=torch.uint8, device=q0.device)
+    iters = out.get("iters") if out.get("iters") is not None else torch.empty(B, dtype=torch.int32, device=q0.device)
+    resid = out.get("resid") if out.get("resid") is not None else torch.empty(B, dtype=q0.dtype, device=q0.device)
+    io = capi.BatchIO(q0.data_ptr(), B, 1, targets.data_ptr(), B, 1, q.data_ptr(), B, 1, success.data_ptr(),
+                      iters.data_ptr(), resid.data_ptr())
+    s = stream if stream is not None else torch.cuda.current_stream(q0.device).cuda_stream
+    prm = p.c()
+    capi.check(capi.lib.ikb_pik_solve_batch(problem._h, _DT[dtype][0], C.byref(prm), B, C.byref(io), C.c_void_p(s)),
+               "ikb_pik_solve_batch")
+    return dict(q=q, success=success, iters=iters, resid=resid)
+
+
+def pik_batch_host(problem, q0, targets, p=None, dtype="f64"):
+    """Batched ik::pik on HOST arrays, AoS: q0 [B, nq], targets [B, tsz]."""
+    problem.finalize(problem._device or 0)
+    p = p or pik_parameters()
+    code, npdt = _DT[dtype]
+    nq, tsz = problem.model().nq, problem.target_size
+    q0 = np.ascontiguousarray(q0, dtype=npdt)
+    targets = np.ascontiguousarray(targets, dtype=npdt)
+    B = q0.shape[0]
+    assert q0.shape == (B, nq) and targets.shape == (B, tsz)
+    q = np.empty((B, nq), dtype=npdt)
+    success, iters, resid = np.empty(B, dtype=np.uint8), np.empty(B, dtype=np.int32), np.empty(B, dtype=npdt)
+    io = capi.BatchIO(q0.ctypes.data, 1, nq, targets.ctypes.data, 1, tsz, q.ctypes.data, 1, nq, success.ctypes.data,
+                      iters.ctypes.data, resid.ctypes.data)
+    prm = p.c()
+    capi.check(capi.lib.ikb_pik_solve_batch_host(problem._h, code, C.byref(prm), B, C.byref(io)), "ikb_pik_solve_batch_host")
+    return dict(q=q, success=success, iters=iters, resid=resid)
+
+
+class pik_data(dls_data):  # pik.hpp:27-49: the user-owned per-solve record (P, da, lambda live in the kernel / parameters)
+    pass
+
+
+def pik(problem, q0, data=None, visitor=None, p=None):
+    """vector_t ik::pik(problem, q0, data, visitor, p) (pik.hpp:51-54): one problem, targets from the tasks' `target` members."""
+    p = p or pik_parameters()
+    if visitor is not None:
+        p.tolerance = visitor.tolerance
+    out = pik_batch_host(problem, np.asarray(q0, dtype=np.float64)[None, :], problem.gather_targets()[None, :], p)
+    if data is not None:
+        data.success = bool(out["success"][0])
+        data.iterations = int(out["iters"][0])
+        data.residual = float(out["resid"][0])
+        data.q = out["q"][0].copy()
+    return out["q"][0].copy()
 
 
 class SolveQueue:

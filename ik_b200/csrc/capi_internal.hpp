@@ -142,7 +142,8 @@ bool two_phase(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, int *
 // team kernel, generic kernel) and the scratch.  `io` holds DEVICE pointers (nullptr for a merged launch).
 template <typename T>
 int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io, cudaStream_t s,
-                 const ChunkPlan *plan = nullptr, const Merged<T> *merged = nullptr);
+                 const ChunkPlan *plan = nullptr, const Merged<T> *merged = nullptr, const double *pik_lambda = nullptr);
+// (pik_lambda != nullptr: ik::pik instead of ik::dls -- per-level damping, table-driven kernel only)
 
 }  // namespace capi
 }  // namespace ikb

@@ -29,7 +29,9 @@ template <typename T> struct alignas(16) DevProblem {
     int32_t t_row[kMaxTasks], t_dim[kMaxTasks], t_toff[kMaxTasks], t_moff[kMaxTasks];
     T weight[kMaxRows];  // stacked row order
     T mask[kMaxNq];      // posture masks, concatenated in stacked order
-    int32_t pad_[4];     // keeps sizeof a multiple of 16 for the bulk copy
+    int32_t nlevels;           // priority levels (max_priority_level + 1)
+    int32_t level_rows[7];     // rows of priority level l (stacked order = level by level); ik::pik walks them
+    int32_t pad_[4];           // keeps sizeof a multiple of 16 for the bulk copy
 };
 
 constexpr int kMaxSegments = 8;
@@ -66,6 +68,8 @@ template <typename T> struct SolveArgs {
     unsigned int *list;               // suspended problem indices
     unsigned long long *list_count;   // number of entries in `list` (zeroed before the BULK launch)
     int *iters_ws;                    // step counts of suspended problems (the caller's `iters` or scratch)
+    // ik::pik (generic kernel only): squared damping of every priority level (pik_data::lambda, pik.hpp:31)
+    T pik_lambda2[7];
     // Merged launch: `nseg` > 0 batches, sorted by `begin`, B = their total size; q0 ... resid above are then unused and
     // iters_ws / list are indexed by the launch-wide problem index.  Unused entries have begin = LLONG_MAX.  The table
     // travels in the kernel parameters: the lookup is a handful of constant-bank compares, no memory traffic.

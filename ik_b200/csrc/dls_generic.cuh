@@ -116,7 +116,9 @@ __device__ __forceinline__ void fk_all(const DevProblem<T> &P, const T *q, T (*o
     }
 }
 
-template <typename T, int NJ, int NV, int M>
+// PIK = false: ik::dls (dls.cpp:5-78).  PIK = true: ik::pik (pik.cpp:31-96) -- same evaluate / stop test / integrate, the
+// step comes from the priority recursion below instead of one damped solve of the stacked system.
+template <typename T, int NJ, int NV, int M, bool PIK = false>
 __global__ void __launch_bounds__(128) dls_generic_kernel(const DevProblem<T> *__restrict__ gP, SolveArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DevProblem<T> &P = *reinterpret_cast<DevProblem<T> *>(smem_raw);
@@ -263,44 +265,176 @@ __global__ void __launch_bounds__(128) dls_generic_kernel(const DevProblem<T> *_
                     for (int c = 0; c < nv; ++c) J[row + i][c] *= wgt;
                 }
             }
-            // ---- Gram matrix + damping (dls.cpp:39-41), packed lower triangle ----
-            for (int i = 0; i < rows; ++i)
-                for (int j = 0; j <= i; ++j) {
+            if constexpr (PIK) {
+                // ---- ik::pik step (pik.cpp:43-65): dq = 0, P = I; for every priority level i:
+                //        de = e_i - J_i dq;  Jb = J_i P;  dq -= damp_pinv(Jb, lambda_i) de;  P -= pinv(Jb) Jb
+                //      damp_pinv(Jb, l) = sum s/(l^2+s^2) v u^T (pik.cpp:5-21) == Jb^T (Jb Jb^T + l^2 I)^-1, so the damped
+                //      step is one LDL^T solve; pinv(Jb) Jb (Eigen COD, pik.cpp:59-61) is the projector onto the row space
+                //      of the numerically rank-r part of Jb: Householder QR with column pivoting, rank from Eigen's
+                //      threshold eps * min(m, n) * max pivot, rows orthonormalised (modified Gram-Schmidt, twice). ----
+                T Pm[NV][NV];
+                for (int i = 0; i < nv; ++i) {
+                    for (int j = 0; j < nv; ++j) Pm[i][j] = (i == j) ? T(1) : T(0);
+                    dq[i] = T(0);
+                }
+                int row0 = 0;
+                for (int lvl = 0; lvl < P.nlevels; ++lvl) {
+                    const int mi = P.level_rows[lvl];
+                    if (mi == 0) continue;
+                    T Jb[M][NV];
+                    for (int r = 0; r < mi; ++r) {
+                        T s = T(0);
+                        for (int c = 0; c < nv; ++c) s += J[row0 + r][c] * dq[c];
+                        y[r] = e[row0 + r] - s;                                  // de_bar (pik.cpp:49)
+                        for (int c = 0; c < nv; ++c) {
+                            T t = T(0);
+                            for (int k = 0; k < nv; ++k) t += J[row0 + r][k] * Pm[k][c];
+                            Jb[r][c] = t;                                        // Jbar = J_i P (pik.cpp:51)
+                        }
+                    }
+                    // (Jb Jb^T + lambda^2 I) z = de, LDL^T, packed lower triangle
+                    for (int i = 0; i < mi; ++i)
+                        for (int j = 0; j <= i; ++j) {
+                            T s = T(0);
+                            for (int c = 0; c < nv; ++c) s += Jb[i][c] * Jb[j][c];
+                            G[i * (i + 1) / 2 + j] = s + (i == j ? a.pik_lambda2[lvl] : T(0));
+                        }
+                    for (int j = 0; j < mi; ++j) {
+                        T d = G[j * (j + 1) / 2 + j];
+                        for (int k = 0; k < j; ++k) {
+                            const T l = G[j * (j + 1) / 2 + k];
+                            d -= l * l * G[k * (k + 1) / 2 + k];
+                        }
+                        G[j * (j + 1) / 2 + j] = d;
+                        const T inv = rcp_(d);
+                        for (int i = j + 1; i < mi; ++i) {
+                            T s = G[i * (i + 1) / 2 + j];
+                            for (int k = 0; k < j; ++k) s -= G[i * (i + 1) / 2 + k] * G[j * (j + 1) / 2 + k] * G[k * (k + 1) / 2 + k];
+                            G[i * (i + 1) / 2 + j] = s * inv;
+                        }
+                    }
+                    for (int i = 0; i < mi; ++i) {
+                        T s = y[i];
+                        for (int k = 0; k < i; ++k) s -= G[i * (i + 1) / 2 + k] * y[k];
+                        y[i] = s;
+                    }
+                    for (int i = 0; i < mi; ++i) y[i] *= rcp_(G[i * (i + 1) / 2 + i]);
+                    for (int i = mi - 1; i >= 0; --i) {
+                        T s = y[i];
+                        for (int k = i + 1; k < mi; ++k) s -= G[k * (k + 1) / 2 + i] * y[k];
+                        y[i] = s;
+                    }
+                    for (int c = 0; c < nv; ++c) {                              // dq -= Jb^T z (pik.cpp:54-55)
+                        T s = T(0);
+                        for (int i = 0; i < mi; ++i) s += Jb[i][c] * y[i];
+                        dq[c] -= s;
+                    }
+                    // projector update (pik.cpp:58-61): Householder QR with column pivoting on Jb, in place
+                    int perm[NV];
+                    for (int c = 0; c < nv; ++c) perm[c] = c;
+                    const int steps = mi < nv ? mi : nv;
+                    T maxpiv = T(0);
+                    T *diag = y;  // |R_kk|
+                    for (int k = 0; k < steps; ++k) {
+                        int best = k;
+                        T bn = T(-1);
+                        for (int c = k; c < nv; ++c) {
+                            T s = T(0);
+                            for (int r = k; r < mi; ++r) s += Jb[r][c] * Jb[r][c];
+                            if (s > bn) { bn = s; best = c; }
+                        }
+                        if (best != k) {
+                            for (int r = 0; r < mi; ++r) { const T t = Jb[r][k]; Jb[r][k] = Jb[r][best]; Jb[r][best] = t; }
+                            const int t = perm[k]; perm[k] = perm[best]; perm[best] = t;
+                        }
+                        const T nrm = sqrt_(max_(bn, T(0)));
+                        if (!(nrm > T(0))) { diag[k] = T(0); continue; }
+                        const T alpha = Jb[k][k] >= T(0) ? -nrm : nrm;
+                        T v[M];
+                        T vn = T(0);
+                        for (int r = k; r < mi; ++r) v[r] = Jb[r][k];
+                        v[k] -= alpha;
+                        for (int r = k; r < mi; ++r) vn += v[r] * v[r];
+                        if (vn > T(0)) {
+                            const T two_over = T(2) / vn;
+                            for (int c = k; c < nv; ++c) {
+                                T s = T(0);
+                                for (int r = k; r < mi; ++r) s += v[r] * Jb[r][c];
+                                s *= two_over;
+                                for (int r = k; r < mi; ++r) Jb[r][c] -= s * v[r];
+                            }
+                        }
+                        diag[k] = abs_(Jb[k][k]);
+                        maxpiv = max_(maxpiv, diag[k]);
+                    }
+                    const T eps = sizeof(T) == 8 ? T(2.220446049250313e-16) : T(1.1920929e-7);
+                    const T thr = eps * T(steps) * maxpiv;
+                    int rank = 0;
+                    for (int k = 0; k < steps; ++k) rank += diag[k] > thr ? 1 : 0;
+                    // W = rows 0..rank-1 of R with the columns back in place, orthonormalised; P -= sum w w^T
+                    T Wm[M][NV];
+                    for (int r = 0; r < rank; ++r)
+                        for (int c = 0; c < nv; ++c) Wm[r][perm[c]] = c >= r ? Jb[r][c] : T(0);
+                    for (int pass = 0; pass < 2; ++pass)
+                        for (int r = 0; r < rank; ++r) {
+                            for (int p2 = 0; p2 < r; ++p2) {
+                                T s = T(0);
+                                for (int c = 0; c < nv; ++c) s += Wm[r][c] * Wm[p2][c];
+                                for (int c = 0; c < nv; ++c) Wm[r][c] -= s * Wm[p2][c];
+                            }
+                            T nr = T(0);
+                            for (int c = 0; c < nv; ++c) nr += Wm[r][c] * Wm[r][c];
+                            const T inr = T(1) / sqrt_(nr);
+                            for (int c = 0; c < nv; ++c) Wm[r][c] *= inr;
+                        }
+                    for (int r = 0; r < rank; ++r)
+                        for (int i = 0; i < nv; ++i) {
+                            const T wi = Wm[r][i];
+                            for (int j = 0; j < nv; ++j) Pm[i][j] -= wi * Wm[r][j];
+                        }
+                    row0 += mi;
+                }
+                // dq += P da with da = 0 (pik.cpp:65, pik.hpp:39)
+            } else {
+                // ---- Gram matrix + damping (dls.cpp:39-41), packed lower triangle ----
+                for (int i = 0; i < rows; ++i)
+                    for (int j = 0; j <= i; ++j) {
+                        T s = T(0);
+                        for (int c = 0; c < nv; ++c) s += J[i][c] * J[j][c];
+                        G[i * (i + 1) / 2 + j] = s + (i == j ? a.damping2 : T(0));
+                    }
+                // ---- LDL^T (G is SPD thanks to the damping, so no pivoting is needed; SURVEY 8a notes) ----
+                for (int j = 0; j < rows; ++j) {
+                    T d = G[j * (j + 1) / 2 + j];
+                    for (int k = 0; k < j; ++k) {
+                        const T l = G[j * (j + 1) / 2 + k];
+                        d -= l * l * G[k * (k + 1) / 2 + k];
+                    }
+                    G[j * (j + 1) / 2 + j] = d;
+                    const T inv = rcp_(d);
+                    for (int i = j + 1; i < rows; ++i) {
+                        T s = G[i * (i + 1) / 2 + j];
+                        for (int k = 0; k < j; ++k) s -= G[i * (i + 1) / 2 + k] * G[j * (j + 1) / 2 + k] * G[k * (k + 1) / 2 + k];
+                        G[i * (i + 1) / 2 + j] = s * inv;
+                    }
+                }
+                for (int i = 0; i < rows; ++i) {
+                    T s = e[i];
+                    for (int k = 0; k < i; ++k) s -= G[i * (i + 1) / 2 + k] * y[k];
+                    y[i] = s;
+                }
+                for (int i = 0; i < rows; ++i) y[i] *= rcp_(G[i * (i + 1) / 2 + i]);
+                for (int i = rows - 1; i >= 0; --i) {
+                    T s = y[i];
+                    for (int k = i + 1; k < rows; ++k) s -= G[k * (k + 1) / 2 + i] * y[k];
+                    y[i] = s;
+                }
+                // ---- dq = -J^T y (dls.cpp:52) and the stop test on priority 0 (visitor.hpp:19) ----
+                for (int c = 0; c < nv; ++c) {
                     T s = T(0);
-                    for (int c = 0; c < nv; ++c) s += J[i][c] * J[j][c];
-                    G[i * (i + 1) / 2 + j] = s + (i == j ? a.damping2 : T(0));
+                    for (int i = 0; i < rows; ++i) s += J[i][c] * y[i];
+                    dq[c] = -s;
                 }
-            // ---- LDL^T (G is SPD thanks to the damping, so no pivoting is needed; SURVEY 8a notes) ----
-            for (int j = 0; j < rows; ++j) {
-                T d = G[j * (j + 1) / 2 + j];
-                for (int k = 0; k < j; ++k) {
-                    const T l = G[j * (j + 1) / 2 + k];
-                    d -= l * l * G[k * (k + 1) / 2 + k];
-                }
-                G[j * (j + 1) / 2 + j] = d;
-                const T inv = rcp_(d);
-                for (int i = j + 1; i < rows; ++i) {
-                    T s = G[i * (i + 1) / 2 + j];
-                    for (int k = 0; k < j; ++k) s -= G[i * (i + 1) / 2 + k] * G[j * (j + 1) / 2 + k] * G[k * (k + 1) / 2 + k];
-                    G[i * (i + 1) / 2 + j] = s * inv;
-                }
-            }
-            for (int i = 0; i < rows; ++i) {
-                T s = e[i];
-                for (int k = 0; k < i; ++k) s -= G[i * (i + 1) / 2 + k] * y[k];
-                y[i] = s;
-            }
-            for (int i = 0; i < rows; ++i) y[i] *= rcp_(G[i * (i + 1) / 2 + i]);
-            for (int i = rows - 1; i >= 0; --i) {
-                T s = y[i];
-                for (int k = i + 1; k < rows; ++k) s -= G[k * (k + 1) / 2 + i] * y[k];
-                y[i] = s;
-            }
-            // ---- dq = -J^T y (dls.cpp:52) and the stop test on priority 0 (visitor.hpp:19) ----
-            for (int c = 0; c < nv; ++c) {
-                T s = T(0);
-                for (int i = 0; i < rows; ++i) s += J[i][c] * y[i];
-                dq[c] = -s;
             }
             T res = T(0);
             for (int i = 0; i < P.rows_p0; ++i) res += e[i] * e[i];

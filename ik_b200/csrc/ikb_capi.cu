@@ -58,6 +58,8 @@ void fill_dev_problem(const HostProblem &hp, const std::vector<int> &order, cons
     P.ntasks = (int)hp.tasks.size();
     P.rows = hp.rows();
     P.rows_p0 = hp.e_size(0);
+    P.nlevels = hp.max_priority_level + 1;
+    for (int l = 0; l < 7; ++l) P.level_rows[l] = l < P.nlevels ? hp.e_size(l) : 0;
     P.tsz = hp.target_size();
     for (int j = 0; j < m.njoints(); ++j) {
         P.parent[j] = m.parent[j];

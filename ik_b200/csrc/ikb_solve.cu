@@ -21,6 +21,13 @@ template <typename T> struct KernelTable {
             default: return dls_generic_kernel<T, 32, 36, 30>;
         }
     }
+    static Fn pik(int cls) {  // ik::pik (pik.cpp:31-96)
+        switch (cls) {
+            case 0: return dls_generic_kernel<T, 10, 8, 6, true>;
+            case 1: return dls_generic_kernel<T, 20, 24, 12, true>;
+            default: return dls_generic_kernel<T, 32, 36, 30, true>;
+        }
+    }
 };
 
 // max_iterations <= 0: the reference returns q0 untouched, success = false, nothing evaluated
@@ -63,7 +70,7 @@ bool two_phase(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, int *
 
 template <typename T>
 int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io, cudaStream_t s,
-                 const ChunkPlan *plan, const Merged<T> *merged) {
+                 const ChunkPlan *plan, const Merged<T> *merged, const double *pik_lambda) {
     SolveArgs<T> a{};
     if (!merged) {
         a.q0 = (const T *)io->q0; a.q0_es = io->q0_elem_stride; a.q0_bs = io->q0_batch_stride;
@@ -103,7 +110,8 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
     a.list = nullptr;
     a.list_count = nullptr;
     a.iters_ws = merged ? nullptr : io->iters;
-    if (p->spec) {
+    for (int l = 0; l < 7; ++l) a.pik_lambda2[l] = pik_lambda ? (T)(pik_lambda[l] * pik_lambda[l]) : T(0);
+    if (p->spec && !pik_lambda) {
         const SpecHostConsts hc{p->hp.model.lower.data(), p->hp.model.upper.data(), p->weight_stacked.data(), p->mask_stacked.data()};
         // Scheduling.  A batch that the latency configuration keeps resident in one wave runs there
         // directly.  A larger batch runs BULK (throughput configuration) with a step cap: the few problems still
@@ -181,7 +189,8 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
         if (rc != IKB_OK) return cuda_fail(cudaGetLastError(), "specialised kernel launch");
         return IKB_OK;
     }
-    auto fn = KernelTable<T>::dls(p->size_class);
+    if (merged) return fail(IKB_ERR_INVALID_ARG, "internal: merged launch on the table-driven kernel");
+    auto fn = pik_lambda ? KernelTable<T>::pik(p->size_class) : KernelTable<T>::dls(p->size_class);
     const int threads = 128;
     const size_t smem = sizeof(DevProblem<T>) + 16;
     int per_sm = 0;
@@ -196,9 +205,9 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
 }
 
 template int launch_solve<double>(const ikb_problem *, const ikb_dls_params *, int64_t, const ikb_batch_io *, cudaStream_t,
-                                  const ChunkPlan *, const Merged<double> *);
+                                  const ChunkPlan *, const Merged<double> *, const double *);
 template int launch_solve<float>(const ikb_problem *, const ikb_dls_params *, int64_t, const ikb_batch_io *, cudaStream_t,
-                                 const ChunkPlan *, const Merged<float> *);
+                                 const ChunkPlan *, const Merged<float> *, const double *);
 
 }  // namespace capi
 }  // namespace ikb
@@ -261,7 +270,7 @@ struct HostTrace {
 };
 
 template <typename T>
-int solve_host(ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io) {
+int solve_host(ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io, const double *pik_lambda = nullptr) {
     const int nq = p->hp.model.nq, tsz = p->hp.target_size();
     Staging<T> &st = staging<T>(p);
     const size_t n_q0 = view_extent(nq, io->q0_elem_stride, io->q0_batch_stride, B);
@@ -296,7 +305,7 @@ int solve_host(ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_b
     const char *slices_env = std::getenv("IKB_HOST_SLICES");
     const int nslice = (int)std::min<int64_t>(slices_env ? std::max(1, std::min(8, std::atoi(slices_env))) : 4, B / 8192);
     const char *pipe_env = std::getenv("IKB_HOST_PIPELINE");
-    if (two_phase(p, prm, B) && nslice >= 2 && vq.sliceable(B) && vt.sliceable(B) && !(pipe_env && pipe_env[0] == '0')) {
+    if (!pik_lambda && two_phase(p, prm, B) && nslice >= 2 && vq.sliceable(B) && vt.sliceable(B) && !(pipe_env && pipe_env[0] == '0')) {
         ChunkPlan plan;
         plan.n = nslice;
         plan.aux = p->stream_aux;
@@ -316,7 +325,7 @@ int solve_host(ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_b
         IKB_CUDA(cudaMemcpyAsync(st.q0, io->q0, n_q0 * sizeof(T), cudaMemcpyHostToDevice, s));
         if (n_tg) IKB_CUDA(cudaMemcpyAsync(st.targets, io->targets, n_tg * sizeof(T), cudaMemcpyHostToDevice, s));
         tr.mark("h2d", s);
-        if ((rc = launch_solve<T>(p, prm, B, &dio, s))) return rc;
+        if ((rc = launch_solve<T>(p, prm, B, &dio, s, nullptr, nullptr, pik_lambda))) return rc;
     }
     tr.mark("solve", s);
     IKB_CUDA(cudaMemcpyAsync(io->q, st.q, n_q * sizeof(T), cudaMemcpyDeviceToHost, s));
@@ -348,6 +357,45 @@ int ikb_dls_solve_batch_host(ikb_problem *p, int dtype, const ikb_dls_params *pr
     if (B == 0) return IKB_OK;
     DeviceGuard g(p->device);
     return dtype == IKB_F64 ? solve_host<double>(p, prm, B, io) : solve_host<float>(p, prm, B, io);
+}
+
+/* ---- ik::pik ---- */
+void ikb_pik_params_default(ikb_pik_params *p) {
+    if (!p) return;
+    p->max_iterations = 100;  // pik.hpp:14
+    p->step_length = 1.0;     // pik.hpp:16
+    p->tolerance = 1e-4;      // visitor.hpp:19
+    for (double &l : p->lambda) l = 1.0;  // pik_data::lambda (pik.hpp:31)
+}
+
+static int pik_to_dls(const ikb_problem *p, const ikb_pik_params *prm, ikb_dls_params *out) {
+    if (!p || !prm) return fail(IKB_ERR_INVALID_ARG, "null argument");
+    if (p->hp.max_priority_level + 1 > 7) return fail(IKB_ERR_UNSUPPORTED, "ik::pik supports at most 7 priority levels");
+    ikb_dls_params_default(out);
+    out->max_iterations = prm->max_iterations;
+    out->step_length = prm->step_length;
+    out->tolerance = prm->tolerance;
+    return IKB_OK;
+}
+
+int ikb_pik_solve_batch(const ikb_problem *p, int dtype, const ikb_pik_params *prm, int64_t B, const ikb_batch_io *io, void *cuda_stream) {
+    ikb_dls_params d;
+    int rc = pik_to_dls(p, prm, &d);
+    if (rc || (rc = check_solve_args(p, dtype, &d, B, io))) return rc;
+    if (B == 0) return IKB_OK;
+    DeviceGuard g(p->device);
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    return dtype == IKB_F64 ? launch_solve<double>(p, &d, B, io, s, nullptr, nullptr, prm->lambda)
+                            : launch_solve<float>(p, &d, B, io, s, nullptr, nullptr, prm->lambda);
+}
+
+int ikb_pik_solve_batch_host(ikb_problem *p, int dtype, const ikb_pik_params *prm, int64_t B, const ikb_batch_io *io) {
+    ikb_dls_params d;
+    int rc = pik_to_dls(p, prm, &d);
+    if (rc || (rc = check_solve_args(p, dtype, &d, B, io))) return rc;
+    if (B == 0) return IKB_OK;
+    DeviceGuard g(p->device);
+    return dtype == IKB_F64 ? solve_host<double>(p, &d, B, io, prm->lambda) : solve_host<float>(p, &d, B, io, prm->lambda);
 }
 
 int ikb_dls_solve(ikb_problem *p, const ikb_dls_params *prm, const double *q0, const double *targets, double *q_out,

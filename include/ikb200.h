@@ -164,6 +164,24 @@ int ikb_dls_solve_batch_host(ikb_problem *p, int dtype, const ikb_dls_params *pa
 int ikb_dls_solve(ikb_problem *p, const ikb_dls_params *params, const double *q0, const double *targets,
                   double *q_out, int *success, int *iters, double *resid);
 
+/* ---- ik::pik: priority-based IK (reference ik/ik/pik.cpp:31-96, pik.hpp:13-57) ----------------
+ * Per iteration: dq = 0, P = I; for every priority level i: de = e_i - J_i dq, Jb = J_i P,
+ * dq -= damp_pseudoinverse(Jb, lambda_i) de, P -= Jb.completeOrthogonalDecomposition().pseudoInverse() Jb; then the
+ * stop test, integrate and clamp of ik::dls.  (pik_data::da, the null-space bias, is zero in the reference and not
+ * exposed.)  Runs on the table-driven kernel for any tree / task mix; at most 7 priority levels. */
+typedef struct {
+    int32_t max_iterations; /* 100 (pik.hpp:14) */
+    double step_length;     /* 1.0 (pik.hpp:16) */
+    double tolerance;       /* 1e-4 (visitor.hpp:19) */
+    double lambda[7];       /* pik_data::lambda, damping of every priority level: 1.0 (pik.hpp:31) */
+} ikb_pik_params;
+void ikb_pik_params_default(ikb_pik_params *p);
+/* as ikb_dls_solve_batch / ikb_dls_solve_batch_host */
+int ikb_pik_solve_batch(const ikb_problem *p, int dtype, const ikb_pik_params *params, int64_t B,
+                        const ikb_batch_io *io, void *cuda_stream);
+int ikb_pik_solve_batch_host(ikb_problem *p, int dtype, const ikb_pik_params *params, int64_t B,
+                             const ikb_batch_io *io);
+
 /* ---- pipelined queue --------------------------------------------------------------------------------
  * The reference's only caller runs ik::dls once per control tick, one call after the other
  * (ik_ros/src/cassie.cpp:112-113 inside CassieIK::loop, :146-171).  A stream of BATCHES has the same shape, and one
