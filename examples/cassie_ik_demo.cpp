@@ -14,6 +14,7 @@
 
 #include "ik/dls.hpp"
 #include "ik/frame.hpp"
+#include "ik/pik.hpp"
 #include "ik/problem.hpp"
 
 int main(int argc, char **argv) {
@@ -75,6 +76,16 @@ int main(int argc, char **argv) {
             same += rq[k].q == r.q && rq[k].iterations == r.iterations && rq[k].success == r.success;
         }
         std::printf("queue: %d of 3 merged batches identical to ik::dls_batch\n", same);
+        // the demo's other solver (IKMethod::PIK, cassie.cpp:114-124): one tick with ik::pik and the demo's parameters
+        ik::pik_data pdata(problem);  // lambda = 1.0 per priority level (pik.hpp:31)
+        ik::pik_parameters pp;
+        pp.damping = 1e-2;
+        pp.max_iterations = 200;
+        pp.step_length = 1e0;
+        problem.get_frame_task("fl")->target.translation() = {0.0, 0.1, -0.6};
+        const ik::vector_t qp = ik::pik(problem, model.neutral(), pdata, ik::inverse_kinematics_visitor(), pp);
+        std::printf("pik success %d iterations %d resid %.12e q7..10 %.12e %.12e %.12e %.12e\n", (int)pdata.success,
+                    pdata.info.iterations, pdata.residual, qp[7], qp[8], qp[9], qp[10]);
     } catch (const std::exception &e) {
         std::fprintf(stderr, "error: %s\n", e.what());
         return 1;

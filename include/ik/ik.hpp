@@ -19,7 +19,7 @@
 //   ik::inverse_kinematics_visitor                       ik/ik/visitor.hpp:7-24         default stop test; `tolerance` member
 //   ik::dls_parameters, ik::dls_data, ik::dls_info       ik/ik/dls.hpp:24-74            same (+ iterations / residual filled)
 //   ik::vector_t ik::dls(problem, q0, data, visitor, p)  ik/ik/dls.hpp:111-114          same signature
-//   -- extension the reference lacks --                                                 ik::dls_batch (host arrays), ik::dls_batch_queue
+//   -- extension the reference lacks --                                                 ik::dls_batch (host arrays), ik::dls_batch_queue;  ik::pik / pik_data / pik_parameters (pik.hpp)
 //
 // Not provided (outside the hot path): pik, FrameConstraint, CentreOfMassTask.  Eigen is not a
 // dependency: vector_t / se3_t are minimal value types with the accessors the reference's callers use.
@@ -388,6 +388,55 @@ inline dls_batch_result dls_batch(InverseKinematicsProblem &problem, std::size_t
     io.success = r.success.data(); io.iters = r.iterations.data(); io.resid = r.residual.data();
     check(ikb_dls_solve_batch_host(h, IKB_F64, &c, (int64_t)B, &io), "ikb_dls_solve_batch_host");
     return r;
+}
+
+// ---- ik::pik: priority-based IK (ik/ik/pik.hpp:13-57, pik.cpp:31-96) ----
+struct pik_parameters {  // pik.hpp:13-18
+    int max_iterations = 100;
+    double damping = 1e-2;  // declared by the reference, never read: pik.cpp uses pik_data::lambda
+    double step_length = 1.0;
+    double max_time = 1.0;
+};
+
+class pik_data {  // pik.hpp:27-49 + data.hpp:8-28 (P and da live in the kernel; da is zero in the reference)
+   public:
+    explicit pik_data(const InverseKinematicsProblem &problem)
+        : q(problem.model().nq, 0.0), dq(problem.model().nv, 0.0), lambda(problem.max_priority_level() + 1, 1.0) {}
+    bool success = false;
+    vector_t q;
+    vector_t dq;
+    std::vector<double> lambda;  // damping factor of every priority level (pik.hpp:31: 1.0)
+    dls_info info;
+    number_t residual = 0;
+};
+
+// vector_t ik::pik(problem, q0, data, visitor, p) -- reference pik.hpp:51-54
+inline vector_t pik(InverseKinematicsProblem &problem, const vector_t &q0, pik_data &data,
+                    const inverse_kinematics_visitor &visitor = inverse_kinematics_visitor(),
+                    const pik_parameters &p = pik_parameters()) {
+    if ((int)q0.size() != problem.model().nq) throw std::invalid_argument("pik: q0 has the wrong size");
+    ikb_problem *h = problem.handle();
+    const int nq = problem.model().nq, tsz = ikb_problem_target_size(h);
+    ikb_pik_params c;
+    ikb_pik_params_default(&c);
+    c.max_iterations = p.max_iterations;
+    c.step_length = p.step_length;
+    c.tolerance = visitor.tolerance;
+    for (std::size_t l = 0; l < data.lambda.size() && l < 7; ++l) c.lambda[l] = data.lambda[l];
+    const vector_t targets = problem.gather_targets();
+    std::uint8_t ok = 0;
+    std::int32_t it = 0;
+    data.q.assign(q0.size(), 0.0);
+    ikb_batch_io io;
+    io.q0 = q0.data(); io.q0_elem_stride = 1; io.q0_batch_stride = nq;
+    io.targets = targets.data(); io.targets_elem_stride = 1; io.targets_batch_stride = tsz;
+    io.q = data.q.data(); io.q_elem_stride = 1; io.q_batch_stride = nq;
+    io.success = &ok; io.iters = &it; io.resid = &data.residual;
+    check(ikb_pik_solve_batch_host(h, IKB_F64, &c, 1, &io), "ikb_pik_solve_batch_host");
+    data.success = ok != 0;
+    data.info.success = data.success;
+    data.info.iterations = it;
+    return data.q;
 }
 
 // Stream of batches (extension, ikb_queue_*): keeps several batches in flight and launches `merge` consecutive ones as

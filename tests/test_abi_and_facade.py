@@ -123,3 +123,9 @@ def test_cpp_facade_demo_matches_oracle():
         assert np.abs(np.array([float(x) for x in l[9:13]]) - q[7:11]).max() < 1e-6
     assert len([l for l in r.stdout.splitlines() if l.startswith("batch")]) == 4
     assert "queue: 3 of 3 merged batches identical" in r.stdout
+    # ik::pik through the facade (cassie.cpp:114-124): same problem, demo parameters, lambda = 1 per level
+    pl = [l.split() for l in r.stdout.splitlines() if l.startswith("pik ")][0]
+    tgp = np.concatenate([np.eye(3).reshape(-1), [0.0, 0.1, -0.6], np.eye(3).reshape(-1), np.zeros(3), [1.0, 0.0, 0.0]])
+    qp, okp, itp, resp, _ = O.pik(opb, om.neutral(), tgp, O.pik_params(max_iterations=200, step_length=1.0, lambdas=[1.0, 1.0]))
+    assert int(pl[2]) == int(okp) and int(pl[4]) == itp and abs(float(pl[6]) - resp) < 1e-9
+    assert np.abs(np.array([float(x) for x in pl[8:12]]) - qp[7:11]).max() < 1e-6
