@@ -86,6 +86,18 @@ int main(int argc, char **argv) {
         const ik::vector_t qp = ik::pik(problem, model.neutral(), pdata, ik::inverse_kinematics_visitor(), pp);
         std::printf("pik success %d iterations %d resid %.12e q7..10 %.12e %.12e %.12e %.12e\n", (int)pdata.success,
                     pdata.info.iterations, pdata.residual, qp[7], qp[8], qp[9], qp[10]);
+        // the demo's commented-out contact constraint (cassie.cpp:49-51,75: "keep the foot in place"): right foot pinned
+        ik::InverseKinematicsProblem pinned(model, 0);
+        auto pel = ik::FrameTask::create(model, "pelvis", ik::KinematicType::Full);
+        pel->target.translation() = {0.0, 0.01, -0.02};
+        pinned.add_frame_task("pelvis", pel);
+        pinned.add_frame_constraint("fr", ik::FrameConstraint::create(model, "RightFootFront", ik::KinematicType::Full));
+        ik::dls_data cdata(pinned);
+        ik::dls_parameters cp;
+        cp.step_length = 0.5;
+        const ik::vector_t qc = ik::dls(pinned, model.neutral(), cdata, ik::inverse_kinematics_visitor(), cp);
+        std::printf("constraint c_size %d success %d iterations %d resid %.12e q7..10 %.12e %.12e %.12e %.12e\n", (int)pinned.c_size(),
+                    (int)cdata.success, cdata.info.iterations, cdata.residual, qc[7], qc[8], qc[9], qc[10]);
     } catch (const std::exception &e) {
         std::fprintf(stderr, "error: %s\n", e.what());
         return 1;

@@ -77,6 +77,8 @@ SIGNATURES = {
     "ikb_problem_add_frame_task": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp]),
     "ikb_problem_add_align_axis_task": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp]),
     "ikb_problem_add_posture_task": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp]),
+    "ikb_problem_add_frame_constraint": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
+    "ikb_problem_c_size": (C.c_int, [_vp]),
     "ikb_problem_num_tasks": (C.c_int, [_vp]),
     "ikb_problem_task_dim": (C.c_int, [_vp, C.c_int]),
     "ikb_problem_e_size": (C.c_int, [_vp, C.c_int]),

@@ -137,6 +137,20 @@ class FrameTask(Task):  # frame.hpp:78-200
     target_size = 12
 
 
+class FrameConstraint:  # frame.hpp:333-465 -- hard constraint: ik::dls keeps `frame` at rest relative to `reference_frame`
+    def __init__(self, model, frame, type=KinematicType.Full, reference_frame="universe"):
+        self.type = KinematicType(type)
+        self._dim = 6 if self.type == KinematicType.Full else 3
+        self.frame = frame
+        self.reference_frame = reference_frame
+        self.target = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], dtype=np.float64)  # declared, not read by ik::dls
+
+    create = classmethod(lambda cls, *a, **k: cls(*a, **k))
+
+    def dimension(self):
+        return self._dim
+
+
 class AlignAxisTask(Task):  # frame.hpp:210-319
     def __init__(self, model, frame, axis, reference_frame="universe"):
         super().__init__(1)
@@ -207,6 +221,7 @@ class InverseKinematicsProblem:  # problem.hpp:9-206
         self._model = model
         self._max_priority_level = max_priority_level
         self._tasks = []  # (name, task, priority) in insertion order
+        self._constraints = []  # (name, FrameConstraint) in insertion order
         self._h = None
         self._device = None
 
@@ -228,6 +243,15 @@ class InverseKinematicsProblem:  # problem.hpp:9-206
             raise IndexError("Maximum priority level exceeded!")  # problem.hpp:162-163
         self._tasks.append((name, task, priority))
         return task
+
+    def add_frame_constraint(self, name, constraint):  # problem.hpp:107-118
+        if self._h is not None:
+            raise RuntimeError("problem already finalized (device constants are immutable)")
+        self._constraints.append((name, constraint))
+        return constraint
+
+    def get_all_constraints(self):  # problem.hpp:167-169
+        return [c for _, c in self._constraints]
 
     def add_frame_task(self, name, task, priority=0):  # problem.hpp:55-66
         return self._add(name, task, priority)
@@ -261,8 +285,8 @@ class InverseKinematicsProblem:  # problem.hpp:9-206
     def e_size(self, priority):  # problem.hpp:34-40
         return sum(t.dimension() for t in self.get_all_tasks(priority))
 
-    def c_size(self):  # problem.hpp:47-53 -- constraints are out of scope
-        return 0
+    def c_size(self):  # problem.hpp:47-53
+        return sum(c.dimension() for _, c in self._constraints)
 
     @property
     def target_size(self):
@@ -304,6 +328,11 @@ class InverseKinematicsProblem:  # problem.hpp:9-206
                 else:
                     capi.check_index(lib.ikb_problem_add_align_axis_task(h, f, int(t.axis), r, prio, _dptr(w)),
                                      "ikb_problem_add_align_axis_task")
+            for name, c in self._constraints:
+                f, r = m.getFrameId(c.frame), m.getFrameId(c.reference_frame)
+                if f >= m.nframes or r >= m.nframes:
+                    raise KeyError("constraint %r: unknown frame %r / %r" % (name, c.frame, c.reference_frame))
+                capi.check_index(lib.ikb_problem_add_frame_constraint(h, f, int(c.type), r), "ikb_problem_add_frame_constraint")
             if device is not None:
                 capi.check(lib.ikb_problem_finalize(h, device), "ikb_problem_finalize")
         except Exception:

@@ -15,6 +15,8 @@ constexpr int kMaxNq = 64;
 constexpr int kMaxTasks = 16;
 constexpr int kMaxFrames = 32;  // frames referenced by tasks (task frames + reference frames)
 constexpr int kMaxRows = 48;
+constexpr int kMaxConstraints = 4;   // FrameConstraints
+constexpr int kMaxConstraintRows = 12;
 
 template <typename T> struct alignas(16) DevProblem {
     int32_t njoints, nq, nv, nframes, ntasks, rows, rows_p0, tsz;
@@ -29,6 +31,9 @@ template <typename T> struct alignas(16) DevProblem {
     int32_t t_row[kMaxTasks], t_dim[kMaxTasks], t_toff[kMaxTasks], t_moff[kMaxTasks];
     T weight[kMaxRows];  // stacked row order
     T mask[kMaxNq];      // posture masks, concatenated in stacked order
+    // FrameConstraints (frame.hpp:333-465): frame / reference frame (indices into f_parent / f_placement) and KinematicType
+    int32_t nconstraints, crows;
+    int32_t c_frame[kMaxConstraints], c_ref[kMaxConstraints], c_type[kMaxConstraints], c_pad_[2];
     int32_t nlevels;           // priority levels (max_priority_level + 1)
     int32_t level_rows[7];     // rows of priority level l (stacked order = level by level); ik::pik walks them
     int32_t pad_[4];           // keeps sizeof a multiple of 16 for the bulk copy

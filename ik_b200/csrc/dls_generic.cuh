@@ -116,6 +116,87 @@ __device__ __forceinline__ void fk_all(const DevProblem<T> &P, const T *q, T (*o
     }
 }
 
+// Orthonormal basis W (rank rows) of the row space of the numerically rank-r part of A (mi x nv, destroyed): what
+// A.completeOrthogonalDecomposition().pseudoInverse() * A projects onto (pik.cpp:59-61, dls.cpp:44-49).  Householder QR with
+// column pivoting in place, r from Eigen's threshold eps * min(m, n) * max pivot, the first r rows of R (columns back in
+// place) orthonormalised by modified Gram-Schmidt, twice.  `diag` is scratch for mi scalars.
+template <typename T, int NV, int MR>
+__device__ __forceinline__ int rowspace_basis(T (*A)[NV], int mi, int nv, T (*W)[NV], T *diag) {
+    int perm[NV];
+    for (int c = 0; c < nv; ++c) perm[c] = c;
+    const int steps = mi < nv ? mi : nv;
+    T maxpiv = T(0);
+    for (int k = 0; k < steps; ++k) {
+        int best = k;
+        T bn = T(-1);
+        for (int c = k; c < nv; ++c) {
+            T s = T(0);
+            for (int r = k; r < mi; ++r) s += A[r][c] * A[r][c];
+            if (s > bn) { bn = s; best = c; }
+        }
+        if (best != k) {
+            for (int r = 0; r < mi; ++r) { const T t = A[r][k]; A[r][k] = A[r][best]; A[r][best] = t; }
+            const int t = perm[k]; perm[k] = perm[best]; perm[best] = t;
+        }
+        const T nrm = sqrt_(max_(bn, T(0)));
+        if (!(nrm > T(0))) { diag[k] = T(0); continue; }
+        const T alpha = A[k][k] >= T(0) ? -nrm : nrm;
+        T v[MR];
+        T vn = T(0);
+        for (int r = k; r < mi; ++r) v[r] = A[r][k];
+        v[k] -= alpha;
+        for (int r = k; r < mi; ++r) vn += v[r] * v[r];
+        if (vn > T(0)) {
+            const T two_over = T(2) / vn;
+            for (int c = k; c < nv; ++c) {
+                T s = T(0);
+                for (int r = k; r < mi; ++r) s += v[r] * A[r][c];
+                s *= two_over;
+                for (int r = k; r < mi; ++r) A[r][c] -= s * v[r];
+            }
+        }
+        diag[k] = abs_(A[k][k]);
+        maxpiv = max_(maxpiv, diag[k]);
+    }
+    const T eps = sizeof(T) == 8 ? T(2.220446049250313e-16) : T(1.1920929e-7);
+    const T thr = eps * T(steps) * maxpiv;
+    int rank = 0;
+    for (int k = 0; k < steps; ++k) rank += diag[k] > thr ? 1 : 0;
+    for (int r = 0; r < rank; ++r)
+        for (int c = 0; c < nv; ++c) W[r][perm[c]] = c >= r ? A[r][c] : T(0);
+    for (int pass = 0; pass < 2; ++pass)
+        for (int r = 0; r < rank; ++r) {
+            for (int p2 = 0; p2 < r; ++p2) {
+                T s = T(0);
+                for (int c = 0; c < nv; ++c) s += W[r][c] * W[p2][c];
+                for (int c = 0; c < nv; ++c) W[r][c] -= s * W[p2][c];
+            }
+            T nr = T(0);
+            for (int c = 0; c < nv; ++c) nr += W[r][c] * W[r][c];
+            const T inr = T(1) / sqrt_(nr);
+            for (int c = 0; c < nv; ++c) W[r][c] *= inr;
+        }
+    return rank;
+}
+
+// World column (linear v, angular w) of velocity coordinate cc of joint j (data.cpp:30: oMi.act(S_i)).
+template <typename T, int NJ>
+__device__ __forceinline__ void world_column(const DevProblem<T> &P, int j, int cc, const T (*oR)[9], const T (*op)[3], T *v, T *ww) {
+    const int jt = P.jtype[j];
+    if (jt == IKB_J_FREEFLYER) {
+        const int ax = cc % 3;
+        const T rc[3] = {oR[j][ax], oR[j][3 + ax], oR[j][6 + ax]};
+        if (cc < 3) { v[0] = rc[0]; v[1] = rc[1]; v[2] = rc[2]; ww[0] = ww[1] = ww[2] = T(0); }
+        else { cross3(op[j], rc, v); ww[0] = rc[0]; ww[1] = rc[1]; ww[2] = rc[2]; }
+    } else {
+        T al[3], z[3];
+        joint_axis_local(P, j, al);
+        rot_vec(oR[j], al, z);
+        if (jt <= IKB_J_REV_UNALIGNED) { cross3(op[j], z, v); ww[0] = z[0]; ww[1] = z[1]; ww[2] = z[2]; }
+        else { v[0] = z[0]; v[1] = z[1]; v[2] = z[2]; ww[0] = ww[1] = ww[2] = T(0); }
+    }
+}
+
 // PIK = false: ik::dls (dls.cpp:5-78).  PIK = true: ik::pik (pik.cpp:31-96) -- same evaluate / stop test / integrate, the
 // step comes from the priority recursion below instead of one damped solve of the stacked system.
 template <typename T, int NJ, int NV, int M, bool PIK = false>
@@ -329,64 +410,9 @@ __global__ void __launch_bounds__(128) dls_generic_kernel(const DevProblem<T> *_
                         for (int i = 0; i < mi; ++i) s += Jb[i][c] * y[i];
                         dq[c] -= s;
                     }
-                    // projector update (pik.cpp:58-61): Householder QR with column pivoting on Jb, in place
-                    int perm[NV];
-                    for (int c = 0; c < nv; ++c) perm[c] = c;
-                    const int steps = mi < nv ? mi : nv;
-                    T maxpiv = T(0);
-                    T *diag = y;  // |R_kk|
-                    for (int k = 0; k < steps; ++k) {
-                        int best = k;
-                        T bn = T(-1);
-                        for (int c = k; c < nv; ++c) {
-                            T s = T(0);
-                            for (int r = k; r < mi; ++r) s += Jb[r][c] * Jb[r][c];
-                            if (s > bn) { bn = s; best = c; }
-                        }
-                        if (best != k) {
-                            for (int r = 0; r < mi; ++r) { const T t = Jb[r][k]; Jb[r][k] = Jb[r][best]; Jb[r][best] = t; }
-                            const int t = perm[k]; perm[k] = perm[best]; perm[best] = t;
-                        }
-                        const T nrm = sqrt_(max_(bn, T(0)));
-                        if (!(nrm > T(0))) { diag[k] = T(0); continue; }
-                        const T alpha = Jb[k][k] >= T(0) ? -nrm : nrm;
-                        T v[M];
-                        T vn = T(0);
-                        for (int r = k; r < mi; ++r) v[r] = Jb[r][k];
-                        v[k] -= alpha;
-                        for (int r = k; r < mi; ++r) vn += v[r] * v[r];
-                        if (vn > T(0)) {
-                            const T two_over = T(2) / vn;
-                            for (int c = k; c < nv; ++c) {
-                                T s = T(0);
-                                for (int r = k; r < mi; ++r) s += v[r] * Jb[r][c];
-                                s *= two_over;
-                                for (int r = k; r < mi; ++r) Jb[r][c] -= s * v[r];
-                            }
-                        }
-                        diag[k] = abs_(Jb[k][k]);
-                        maxpiv = max_(maxpiv, diag[k]);
-                    }
-                    const T eps = sizeof(T) == 8 ? T(2.220446049250313e-16) : T(1.1920929e-7);
-                    const T thr = eps * T(steps) * maxpiv;
-                    int rank = 0;
-                    for (int k = 0; k < steps; ++k) rank += diag[k] > thr ? 1 : 0;
-                    // W = rows 0..rank-1 of R with the columns back in place, orthonormalised; P -= sum w w^T
+                    // projector update (pik.cpp:58-61)
                     T Wm[M][NV];
-                    for (int r = 0; r < rank; ++r)
-                        for (int c = 0; c < nv; ++c) Wm[r][perm[c]] = c >= r ? Jb[r][c] : T(0);
-                    for (int pass = 0; pass < 2; ++pass)
-                        for (int r = 0; r < rank; ++r) {
-                            for (int p2 = 0; p2 < r; ++p2) {
-                                T s = T(0);
-                                for (int c = 0; c < nv; ++c) s += Wm[r][c] * Wm[p2][c];
-                                for (int c = 0; c < nv; ++c) Wm[r][c] -= s * Wm[p2][c];
-                            }
-                            T nr = T(0);
-                            for (int c = 0; c < nv; ++c) nr += Wm[r][c] * Wm[r][c];
-                            const T inr = T(1) / sqrt_(nr);
-                            for (int c = 0; c < nv; ++c) Wm[r][c] *= inr;
-                        }
+                    const int rank = rowspace_basis<T, NV, M>(Jb, mi, nv, Wm, y);
                     for (int r = 0; r < rank; ++r)
                         for (int i = 0; i < nv; ++i) {
                             const T wi = Wm[r][i];
@@ -434,6 +460,58 @@ __global__ void __launch_bounds__(128) dls_generic_kernel(const DevProblem<T> *_
                     T s = T(0);
                     for (int i = 0; i < rows; ++i) s += J[i][c] * y[i];
                     dq[c] = -s;
+                }
+                // ---- FrameConstraints (dls.cpp:26-34,44-52): dq <- (I - Jc^+ Jc) dq ----
+                if (P.nconstraints > 0) {
+                    T Jc[kMaxConstraintRows][NV], Wc[kMaxConstraintRows][NV], dscr[kMaxConstraintRows];
+                    for (int r = 0; r < P.crows; ++r)
+                        for (int c = 0; c < nv; ++c) Jc[r][c] = T(0);
+                    int crow = 0;
+                    for (int k = 0; k < P.nconstraints; ++k) {
+                        const int f = P.c_frame[k], r = P.c_ref[k], fj = P.f_parent[f], rj = P.f_parent[r];
+                        const int full = P.c_type[k] == IKB_FULL, r0 = P.c_type[k] == IKB_ORIENTATION ? 3 : 0, dim = full ? 6 : 3;
+                        T Rf[9], pf[3], Rr[9], pr[3], Rm[9], pm[3];
+                        se3_mul(oR[fj], op[fj], P.f_placement[f], P.f_placement[f] + 9, Rf, pf);
+                        se3_mul(oR[rj], op[rj], P.f_placement[r], P.f_placement[r] + 9, Rr, pr);
+                        se3_actinv(Rr, pr, Rf, pf, Rm, pm);  // rMf (frame.hpp:407)
+                        // + frame Jacobian, LOCAL (frame.hpp:410-411)
+                        for (int j = fj; j > 0; j = P.parent[j]) {
+                            const int ncol = P.jtype[j] == IKB_J_FREEFLYER ? 6 : 1;
+                            for (int cc = 0; cc < ncol; ++cc) {
+                                T v[3], ww[3], pxw[3], d[3], col[6];
+                                world_column<T, NJ>(P, j, cc, oR, op, v, ww);
+                                cross3(pf, ww, pxw);
+                                d[0] = v[0] - pxw[0]; d[1] = v[1] - pxw[1]; d[2] = v[2] - pxw[2];
+                                rotT_vec(Rf, d, col);
+                                rotT_vec(Rf, ww, col + 3);
+                                for (int i = 0; i < dim; ++i) Jc[crow + i][P.idx_v[j] + cc] += col[r0 + i];
+                            }
+                        }
+                        // - rMf.toActionMatrixInverse() * reference frame Jacobian, LOCAL (frame.hpp:414-436)
+                        for (int j = rj; j > 0; j = P.parent[j]) {
+                            const int ncol = P.jtype[j] == IKB_J_FREEFLYER ? 6 : 1;
+                            for (int cc = 0; cc < ncol; ++cc) {
+                                T v[3], ww[3], pxw[3], d[3], lv[3], lw[3], col[6];
+                                world_column<T, NJ>(P, j, cc, oR, op, v, ww);
+                                cross3(pr, ww, pxw);
+                                d[0] = v[0] - pxw[0]; d[1] = v[1] - pxw[1]; d[2] = v[2] - pxw[2];
+                                rotT_vec(Rr, d, lv);
+                                rotT_vec(Rr, ww, lw);
+                                cross3(pm, lw, pxw);
+                                d[0] = lv[0] - pxw[0]; d[1] = lv[1] - pxw[1]; d[2] = lv[2] - pxw[2];
+                                rotT_vec(Rm, d, col);
+                                rotT_vec(Rm, lw, col + 3);
+                                for (int i = 0; i < dim; ++i) Jc[crow + i][P.idx_v[j] + cc] -= col[r0 + i];
+                            }
+                        }
+                        crow += dim;
+                    }
+                    const int rank = rowspace_basis<T, NV, kMaxConstraintRows>(Jc, P.crows, nv, Wc, dscr);
+                    for (int r = 0; r < rank; ++r) {
+                        T s = T(0);
+                        for (int c = 0; c < nv; ++c) s += Wc[r][c] * dq[c];
+                        for (int c = 0; c < nv; ++c) dq[c] -= s * Wc[r][c];
+                    }
                 }
             }
             T res = T(0);

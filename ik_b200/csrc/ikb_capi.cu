@@ -58,6 +58,14 @@ void fill_dev_problem(const HostProblem &hp, const std::vector<int> &order, cons
     P.ntasks = (int)hp.tasks.size();
     P.rows = hp.rows();
     P.rows_p0 = hp.e_size(0);
+    P.nconstraints = (int)hp.constraints.size();
+    P.crows = hp.c_size();
+    for (size_t k = 0; k < hp.constraints.size(); ++k) {
+        auto lf = [&](int fid) { return (int)(std::find(used_frames.begin(), used_frames.end(), fid) - used_frames.begin()); };
+        P.c_frame[k] = lf(hp.constraints[k].frame);
+        P.c_ref[k] = lf(hp.constraints[k].ref);
+        P.c_type[k] = hp.constraints[k].type;
+    }
     P.nlevels = hp.max_priority_level + 1;
     for (int l = 0; l < 7; ++l) P.level_rows[l] = l < P.nlevels ? hp.e_size(l) : 0;
     P.tsz = hp.target_size();
@@ -157,6 +165,7 @@ int launch_fk(const ikb_problem *p, int64_t B, const void *q, int64_t es, int64_
 // The specialised bodies lay targets out in stacked order, the ABI in insertion order: only problems whose tasks
 // were added in non-decreasing priority (stacked order == insertion order) can take the fast path.
 const SpecializedKernel *select_specialized(const HostProblem &hp) {
+    if (!hp.constraints.empty()) return nullptr;  // the null-space projection lives in the table-driven kernel
     for (size_t i = 1; i < hp.tasks.size(); ++i)
         if (hp.tasks[i].priority < hp.tasks[i - 1].priority) return nullptr;
     return find_specialized(hp);
@@ -412,6 +421,23 @@ int ikb_problem_add_posture_task(ikb_problem *p, int nj, int priority, const dou
     return add_task_common(p, t, priority, weights);
 }
 
+int ikb_problem_add_frame_constraint(ikb_problem *p, int frame, int ktype, int ref) {
+    if (!p) return -fail(IKB_ERR_INVALID_ARG, "null problem");
+    if (p->finalized) return -fail(IKB_ERR_INVALID_ARG, "problem is finalized (immutable)");
+    const int nf = p->hp.model.nframes();
+    if (frame < 0 || frame >= nf || ref < 0 || ref >= nf) return -fail(IKB_ERR_UNKNOWN_FRAME, "frame index out of range");
+    if (ktype != IKB_POSITION && ktype != IKB_ORIENTATION && ktype != IKB_FULL)
+        return -fail(IKB_ERR_INVALID_ARG, "kinematic type must be IKB_POSITION, IKB_ORIENTATION or IKB_FULL");
+    HostConstraint c;
+    c.frame = frame;
+    c.ref = ref;
+    c.type = ktype;
+    c.dim = ktype == IKB_FULL ? 6 : 3;
+    p->hp.constraints.push_back(c);
+    return (int)p->hp.constraints.size() - 1;
+}
+int ikb_problem_c_size(const ikb_problem *p) { return p ? p->hp.c_size() : -IKB_ERR_INVALID_ARG; }
+
 int ikb_problem_num_tasks(const ikb_problem *p) { return p ? (int)p->hp.tasks.size() : -IKB_ERR_INVALID_ARG; }
 int ikb_problem_task_dim(const ikb_problem *p, int t) {
     return (p && t >= 0 && t < (int)p->hp.tasks.size()) ? p->hp.tasks[t].dim : -IKB_ERR_INVALID_ARG;
@@ -438,7 +464,12 @@ int ikb_problem_finalize(ikb_problem *p, int device) {
         if (t.kind != IKB_TASK_POSTURE)
             for (int f : {t.frame, t.ref})
                 if (std::find(used.begin(), used.end(), f) == used.end()) used.push_back(f);
+    for (const auto &c : hp.constraints)
+        for (int f : {c.frame, c.ref})
+            if (std::find(used.begin(), used.end(), f) == used.end()) used.push_back(f);
     if (used.empty()) used.push_back(0);
+    if ((int)hp.constraints.size() > kMaxConstraints || hp.c_size() > kMaxConstraintRows)
+        return fail(IKB_ERR_UNSUPPORTED, "at most 4 frame constraints / 12 constraint rows");
     if (m.njoints() > kMaxJoints || m.nq > kMaxNq || (int)hp.tasks.size() > kMaxTasks || (int)used.size() > kMaxFrames ||
         hp.rows() > kMaxRows)
         return fail(IKB_ERR_UNSUPPORTED, "problem exceeds the compiled capacities of the constant blob");

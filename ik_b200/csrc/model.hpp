@@ -57,10 +57,23 @@ struct HostTask {
     std::vector<double> mask;    // posture only
 };
 
+// FrameConstraint (frame.hpp:333-465): ik::dls projects its step into the null space of the stacked constraint Jacobian
+struct HostConstraint {
+    int frame = 0, ref = 0;
+    int type = IKB_FULL;
+    int dim = 6;
+};
+
 struct HostProblem {
     HostModel model;  // by value, like the reference (problem.hpp:183)
     int max_priority_level = 0;
     std::vector<HostTask> tasks;  // insertion order
+    std::vector<HostConstraint> constraints;  // insertion order
+    int c_size() const {  // problem.hpp:47-53
+        int n = 0;
+        for (const auto &c : constraints) n += c.dim;
+        return n;
+    }
 
     int rows() const;
     int e_size(int priority) const;

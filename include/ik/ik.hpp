@@ -166,6 +166,26 @@ class AlignAxisTask : public Task {  // ik/ik/frame.hpp:210-319
     std::string frame, reference_frame;
 };
 
+// ik/ik/frame.hpp:333-465: a hard constraint -- ik::dls projects its step into the null space of the stacked constraint
+// Jacobian (dls.cpp:26-34,44-52), i.e. keeps `frame` at rest relative to `reference_frame`.
+class FrameConstraint {
+   public:
+    FrameConstraint(const model_t &model, const std::string &frame, const KinematicType &type = KinematicType::Full,
+                    const std::string &reference_frame = "universe")
+        : type(type), frame(frame), reference_frame(reference_frame) {
+        (void)model;
+    }
+    static std::shared_ptr<FrameConstraint> create(const model_t &model, const std::string &frame,
+                                                   const KinematicType &type = KinematicType::Full,
+                                                   const std::string &reference_frame = "universe") {
+        return std::make_shared<FrameConstraint>(model, frame, type, reference_frame);
+    }
+    index_t dimension() const { return type == KinematicType::Full ? 6 : 3; }
+    se3_t target = se3_t::Identity();  // declared by the reference, not read by ik::dls
+    KinematicType type;
+    std::string frame, reference_frame;
+};
+
 class PostureTask : public Task {  // ik/ik/posture.hpp:17-86
    public:
     PostureTask(const model_t &model, const index_t &nj) : Task(nj), target(nj, 0.0), mask(nj, 1.0), nj(nj) { (void)model; }
@@ -191,7 +211,19 @@ class InverseKinematicsProblem {  // ik/ik/problem.hpp:9-206
         for (const auto &task : get_all_tasks(priority)) sz += task->dimension();
         return sz;
     }
-    std::size_t c_size() const { return 0; }  // no constraints on the hot path (dls.cpp:44-45: N = I)
+    std::size_t c_size() const {  // problem.hpp:47-53
+        std::size_t sz = 0;
+        for (const auto &c : constraints_) sz += c->dimension();
+        return sz;
+    }
+    std::shared_ptr<FrameConstraint> add_frame_constraint(const std::string &name, const std::shared_ptr<FrameConstraint> &c) {
+        constraints_map_.insert({name, constraints_.size()});  // problem.hpp:107-118
+        constraints_.push_back(c);
+        release();
+        return constraints_.back();
+    }
+    std::shared_ptr<FrameConstraint> get_frame_constraint(const std::string &name) { return constraints_.at(constraints_map_.at(name)); }
+    const std::vector<std::shared_ptr<FrameConstraint>> &get_all_constraints() const { return constraints_; }
 
     std::shared_ptr<FrameTask> add_frame_task(const std::string &name, const std::shared_ptr<FrameTask> &task,
                                               const std::size_t &priority = 0) {
@@ -244,6 +276,12 @@ class InverseKinematicsProblem {  // ik/ik/problem.hpp:9-206
                 throw std::runtime_error("InverseKinematicsProblem: " + msg);
             }
         }
+        for (const auto &c : constraints_)
+            if (ikb_problem_add_frame_constraint(h_, frame_id(c->frame), (int)c->type, frame_id(c->reference_frame)) < 0) {
+                const std::string msg = ikb_last_error();
+                release();
+                throw std::runtime_error("InverseKinematicsProblem: " + msg);
+            }
         check(ikb_problem_finalize(h_, device), "ikb_problem_finalize");
         baked_weights_ = w;
         device_ = device;
@@ -300,6 +338,8 @@ class InverseKinematicsProblem {  // ik/ik/problem.hpp:9-206
     std::unordered_map<string_t, std::size_t> frame_tasks_map_;
     std::vector<std::shared_ptr<AlignAxisTask>> axis_tasks_;
     std::unordered_map<string_t, std::size_t> axis_tasks_map_;
+    std::vector<std::shared_ptr<FrameConstraint>> constraints_;
+    std::unordered_map<string_t, std::size_t> constraints_map_;
     ikb_problem *h_ = nullptr;
     vector_t baked_weights_;
     int device_ = 0;

@@ -122,6 +122,12 @@ int ikb_problem_add_align_axis_task(ikb_problem *p, int frame, int axis, int ref
                                     const double *weights);
 /* PostureTask(model, nj) + add_posture_task: posture.hpp:17-86, problem.hpp:134-145.  mask: nj entries or NULL */
 int ikb_problem_add_posture_task(ikb_problem *p, int nj, int priority, const double *weights, const double *mask);
+/* FrameConstraint (reference frame.hpp:333-465; problem.hpp add_frame_constraint): ik::dls projects its step into the null
+ * space of the stacked constraint Jacobian, N = I - Jc.completeOrthogonalDecomposition().pseudoInverse() Jc
+ * (dls.cpp:26-34,44-52), i.e. keeps `frame` at rest relative to `ref`.  Returns the constraint index or minus an
+ * ikb_status.  At most 4 constraints / 12 rows; problems with constraints run on the table-driven kernel. */
+int ikb_problem_add_frame_constraint(ikb_problem *p, int frame, int ktype, int ref);
+int ikb_problem_c_size(const ikb_problem *p); /* InverseKinematicsProblem::c_size(), problem.hpp:47-53 */
 int ikb_problem_num_tasks(const ikb_problem *p);
 int ikb_problem_task_dim(const ikb_problem *p, int task);            /* Task::dimension(), task.hpp:38 */
 int ikb_problem_e_size(const ikb_problem *p, int priority);          /* problem.hpp:34-40 */

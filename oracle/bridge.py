@@ -31,6 +31,8 @@ def oracle_problem_like(problem, omodel):
             opb.add_align_axis_task(t.frame, int(t.axis), t.reference_frame, prio, t.weighting())
         else:
             opb.add_posture_task(t.nj, prio, t.weighting(), t.mask)
+    for c in problem.get_all_constraints():
+        opb.add_frame_constraint(c.frame, int(c.type), c.reference_frame)
     return opb
 
 

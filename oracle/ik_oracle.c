@@ -518,6 +518,46 @@ void iko_evaluate(const iko_model *m, const iko_problem *pb, const double *q, co
  * pivoting on the largest remaining diagonal entry, A = P^T L D L^T P; solve uses D's pseudo-inverse.
  * Reference call site: dls.cpp:53  data.JJ.ldlt().solve(data.et).
  * ---------------------------------------------------------------------------------------------- */
+int iko_c_size(const iko_problem *pb) {
+    int n = 0;
+    for (int k = 0; k < pb->nconstraints; ++k) n += pb->c_type[k] == IKO_FULL ? 6 : 3;
+    return n;
+}
+
+/* FrameConstraint::compute_jacobian (frame.hpp:399-437) for every constraint, stacked in insertion order (dls.cpp:26-34) */
+void iko_constraint_jacobian(const iko_model *m, const iko_problem *pb, const double *q, double *Jc) {
+    const int nv = m->nv;
+    double *oMi = (double *)malloc(sizeof(double) * 12 * m->njoints);
+    double *Jw = (double *)malloc(sizeof(double) * 6 * nv);
+    double *Jf = (double *)malloc(sizeof(double) * 6 * nv), *Jr = (double *)malloc(sizeof(double) * 6 * nv);
+    iko_fk(m, q, oMi);
+    iko_joint_jacobians(m, oMi, Jw);
+    int row = 0;
+    for (int k = 0; k < pb->nconstraints; ++k) {
+        double oMf[12], oMr[12], rMf[12];
+        iko_frame_placement(m, oMi, pb->c_frame[k], oMf);
+        iko_frame_placement(m, oMi, pb->c_ref[k], oMr);
+        iko_se3_actinv(oMr, oMf, rMf);                                      /* frame.hpp:407 */
+        iko_frame_jacobian_local(m, oMi, Jw, pb->c_frame[k], Jf);           /* frame.hpp:410-411 */
+        iko_frame_jacobian_local(m, oMi, Jw, pb->c_ref[k], Jr);             /* frame.hpp:414-416 */
+        /* rMf.toActionMatrixInverse() = [[R^T, -R^T p^], [0, R^T]] for rMf = (R, p): (v, w) -> (R^T (v - p x w), R^T w) */
+        const double *R = rMf, *p = rMf + 9;
+        const int full = pb->c_type[k] == IKO_FULL, r0 = pb->c_type[k] == IKO_ORIENTATION ? 3 : 0, dim = full ? 6 : 3;
+        for (int c = 0; c < nv; ++c) {
+            double v[3] = {Jr[c], Jr[nv + c], Jr[2 * nv + c]}, w[3] = {Jr[3 * nv + c], Jr[4 * nv + c], Jr[5 * nv + c]};
+            double pxw[3], d[3], lv[3], lw[3], col[6];
+            cross3(p, w, pxw);
+            for (int i = 0; i < 3; ++i) d[i] = v[i] - pxw[i];
+            matTvec3(R, d, lv);
+            matTvec3(R, w, lw);
+            for (int i = 0; i < 3; ++i) { col[i] = Jf[i * nv + c] - lv[i]; col[3 + i] = Jf[(3 + i) * nv + c] - lw[i]; }
+            for (int i = 0; i < dim; ++i) Jc[(row + i) * nv + c] = col[r0 + i];     /* frame.hpp:420-436 */
+        }
+        row += dim;
+    }
+    free(oMi); free(Jw); free(Jf); free(Jr);
+}
+
 void iko_ldlt_solve(int n, double *A, const double *b, double *x) {
     int *tr = (int *)malloc(sizeof(int) * (n > 0 ? n : 1));
     double *tmp = (double *)malloc(sizeof(double) * (n > 0 ? n : 1));
@@ -572,6 +612,8 @@ int iko_dls(const iko_model *m, const iko_problem *pb, const iko_params *prm, co
     memcpy(q, q0, sizeof(double) * nq);                                     /* dls.cpp:8 */
     int success = 0, it = 0;
     double res = 0;
+    const int crows = iko_c_size(pb);
+    double *Jc = (double *)malloc(sizeof(double) * (crows * nv + 1)), *N = (double *)malloc(sizeof(double) * nv * nv);
     for (it = 0; it < prm->max_iterations; ++it) {                           /* dls.cpp:14 */
         iko_evaluate(m, pb, q, targets, e, J);                               /* dls.cpp:16-24 */
         for (int i = 0; i < rows; ++i)                                       /* dls.cpp:39 */
@@ -587,6 +629,16 @@ int iko_dls(const iko_model *m, const iko_problem *pb, const iko_params *prm, co
             for (int i = 0; i < rows; ++i) s += J[i * nv + c] * y[i];
             dq[c] = -s;
         }
+        if (crows > 0) {                                                     /* dls.cpp:26-34,44-52: dq = -N (J^T y) */
+            iko_constraint_jacobian(m, pb, q, Jc);
+            iko_rowspace_projector(crows, nv, Jc, N);                        /* Jc.cod().pseudoInverse() * Jc */
+            for (int c = 0; c < nv; ++c) {
+                double s = 0;
+                for (int k = 0; k < nv; ++k) s += N[c * nv + k] * dq[k];
+                sdq[c] = dq[c] - s;                                          /* (I - Jc^+ Jc) dq */
+            }
+            memcpy(dq, sdq, sizeof(double) * nv);
+        }
         res = 0;                                                             /* visitor.hpp:19 */
         for (int i = 0; i < r0; ++i) res += e[i] * e[i];
         if (res < prm->tolerance) { success = 1; break; }                    /* dls.cpp:61-64 */
@@ -599,7 +651,7 @@ int iko_dls(const iko_model *m, const iko_problem *pb, const iko_params *prm, co
     if (iters) *iters = it;
     if (resid) *resid = res;
     if (dq_out) memcpy(dq_out, dq, sizeof(double) * nv);
-    free(q); free(qn); free(e); free(J); free(JJ); free(y); free(dq); free(sdq);
+    free(q); free(qn); free(e); free(J); free(JJ); free(y); free(dq); free(sdq); free(Jc); free(N);
     return success;
 }
 

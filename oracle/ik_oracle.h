@@ -59,6 +59,12 @@ typedef struct {
     const int *priority; /* [ntasks] */
     const double *weight; /* concatenated per-row weights, task insertion order */
     const double *mask;   /* concatenated posture masks (POSTURE tasks only, insertion order) */
+    /* FrameConstraints (frame.hpp:333-465, problem.hpp add_frame_constraint): ik::dls projects its step into the null
+     * space of their stacked Jacobian (dls.cpp:26-34,44-49) */
+    int nconstraints;
+    const int *c_frame;  /* [nconstraints] */
+    const int *c_ref;    /* [nconstraints] reference frame */
+    const int *c_type;   /* [nconstraints] IKO_POSITION / ORIENTATION / FULL */
 } iko_problem;
 
 typedef struct {
@@ -99,6 +105,11 @@ void iko_clip(const iko_model *m, double *q);
 /* one evaluate_problem_data() (data.cpp:25-58): stacked e [rows] and J [rows][nv] */
 void iko_evaluate(const iko_model *m, const iko_problem *pb, const double *q, const double *targets,
                   double *e, double *J);
+
+/* rows of all FrameConstraints and their stacked Jacobian Jc [crows][nv] (FrameConstraint::compute_jacobian,
+ * frame.hpp:399-437: frame Jacobian minus the reference frame's, both LOCAL, the latter moved by rMf^-1) */
+int iko_c_size(const iko_problem *pb);
+void iko_constraint_jacobian(const iko_model *m, const iko_problem *pb, const double *q, double *Jc);
 
 /* Eigen LDLT (pivoted, lower, unblocked) restated: solves A x = b, A n x n row-major (destroyed) */
 void iko_ldlt_solve(int n, double *A, const double *b, double *x);

@@ -29,7 +29,8 @@ class _CModel(C.Structure):
 
 class _CProblem(C.Structure):
     _fields_ = [("ntasks", C.c_int), ("max_priority_level", C.c_int), ("kind", _ip), ("frame", _ip), ("ref", _ip),
-                ("type", _ip), ("priority", _ip), ("weight", _dp), ("mask", _dp)]
+                ("type", _ip), ("priority", _ip), ("weight", _dp), ("mask", _dp),
+                ("nconstraints", C.c_int), ("c_frame", _ip), ("c_ref", _ip), ("c_type", _ip)]
 
 
 class _CParams(C.Structure):
@@ -128,7 +129,23 @@ class Problem:
         self.model = model
         self.max_priority_level = max_priority_level
         self.tasks = []
+        self.constraints = []
         self._c = None
+
+    def add_frame_constraint(self, frame, ktype=FULL, ref="universe"):
+        """FrameConstraint (frame.hpp:333-465): ik::dls keeps the frame's velocity relative to `ref` at zero."""
+        self.constraints.append(dict(frame=self._fid(frame), ref=self._fid(ref), type=ktype, dim=6 if ktype == FULL else 3))
+        self._c = None
+        return len(self.constraints) - 1
+
+    @property
+    def c_size(self):
+        return sum(x["dim"] for x in self.constraints)
+
+    def constraint_jacobian(self, q):
+        Jc = np.zeros((max(self.c_size, 1), self.model.nv))
+        lib().iko_constraint_jacobian(C.byref(self.model.c), C.byref(self.c), _pd(_d(q)), _pd(Jc))
+        return Jc[:self.c_size]
 
     def add_frame_task(self, frame, ktype=FULL, ref="universe", priority=0, weight=None):
         f, r = self._fid(frame), self._fid(ref)
@@ -170,8 +187,12 @@ class Problem:
                               weight=_d(np.concatenate([x["weight"] for x in t]) if t else np.zeros(0)),
                               mask=_d(np.concatenate([x["mask"] for x in t] + [np.zeros(1)])))
             k = self._keep
+            cs = self.constraints
+            carr = lambda key: np.array([x[key] for x in cs] + [0], dtype=np.int32)
+            k.update(c_frame=carr("frame"), c_ref=carr("ref"), c_type=carr("type"))
             self._c = _CProblem(len(t), self.max_priority_level, _pi(k["kind"]), _pi(k["frame"]), _pi(k["ref"]),
-                                _pi(k["type"]), _pi(k["priority"]), _pd(k["weight"]), _pd(k["mask"]))
+                                _pi(k["type"]), _pi(k["priority"]), _pd(k["weight"]), _pd(k["mask"]),
+                                len(cs), _pi(k["c_frame"]), _pi(k["c_ref"]), _pi(k["c_type"]))
         return self._c
 
     @property

@@ -129,3 +129,11 @@ def test_cpp_facade_demo_matches_oracle():
     qp, okp, itp, resp, _ = O.pik(opb, om.neutral(), tgp, O.pik_params(max_iterations=200, step_length=1.0, lambdas=[1.0, 1.0]))
     assert int(pl[2]) == int(okp) and int(pl[4]) == itp and abs(float(pl[6]) - resp) < 1e-9
     assert np.abs(np.array([float(x) for x in pl[8:12]]) - qp[7:11]).max() < 1e-6
+    # ik::dls with a FrameConstraint through the facade (frame.hpp:333-465, dls.cpp:26-34,44-52)
+    cl = [l.split() for l in r.stdout.splitlines() if l.startswith("constraint ")][0]
+    opc = O.Problem(om, 0)
+    opc.add_frame_task("pelvis", O.FULL, "universe", 0)
+    opc.add_frame_constraint("RightFootFront", O.FULL, "universe")
+    qc, okc, itc, resc, _ = O.dls(opc, om.neutral(), O.se3(p=[0.0, 0.01, -0.02]), O.params(step_length=0.5))
+    assert int(cl[2]) == 6 and int(cl[4]) == int(okc) and int(cl[6]) == itc and abs(float(cl[8]) - resc) < 1e-9
+    assert np.abs(np.array([float(x) for x in cl[10:14]]) - qc[7:11]).max() < 1e-6

@@ -438,3 +438,41 @@ def test_two_phase_scheduling_matches_oracle(params):
         piped = ik.dls_batch_host(pb, a, b, prm, "f64", layout)
         for k in ("q", "success", "iters", "resid"):
             assert np.array_equal(plain[k], piped[k]), (layout, k)
+
+
+@pytest.mark.parametrize("ref", ["universe", "pelvis"])
+@pytest.mark.parametrize("ktype", ["Full", "Position"])
+def test_frame_constraint_null_space_projection(ktype, ref):
+    """FrameConstraint (frame.hpp:333-465) in ik::dls (dls.cpp:26-34,44-52): the right foot is pinned (relative to the world
+    or to the moving pelvis frame) while pelvis pose and left foot are tracked.  Table-driven kernel vs the oracle: flags,
+    step counts, q; and the pinned frame really stays put."""
+    m = W.cassie_model()
+    pb = ik.InverseKinematicsProblem(m, 0)
+    pb.add_frame_task("pelvis", ik.FrameTask(m, "pelvis", ik.KinematicType.Full))
+    pb.add_frame_task("fl", ik.FrameTask(m, "LeftFootFront", ik.KinematicType.Position))
+    pb.add_frame_constraint("fr", ik.FrameConstraint(m, "RightFootFront", getattr(ik.KinematicType, ktype), ref))
+    assert pb.c_size() == (6 if ktype == "Full" else 3) and pb.specialisation() is None
+    om = oracle_model("cassie")
+    opb = oracle_problem_like(pb, om)
+    B = 500
+    q0, tg, _ = make_workload(pb, om, B, seed=91, standing=W.CASSIE_STANDING)
+    # modest targets around the standing pose, so that a pinned foot is compatible with them
+    s0 = W.standing_configuration(m, W.CASSIE_STANDING)
+    lf = om.frame_placement(s0, om.frame_id("LeftFootFront"))[9:]
+    rng = np.random.default_rng(3)
+    tg[:, :9] = np.eye(3).reshape(-1)
+    tg[:, 9:12] = rng.uniform(-0.03, 0.03, (B, 3))
+    tg[:, 21:24] = lf + rng.uniform(-0.05, 0.05, (B, 3))
+    prm, oprm = ik.dls_parameters(max_iterations=60, step_length=0.5), O.params(max_iterations=60, step_length=0.5)
+    ref_out = O.dls_batch(opb, q0, tg, oprm, nthreads=NT)
+    gpu = _solve_gpu(pb, q0, tg, prm)
+    q, ok, it, res = gpu
+    q_ref, ok_ref, it_ref, res_ref = ref_out
+    assert (ok == ok_ref).all() and (it == it_ref).all()
+    assert np.abs(q - q_ref).max() < 1e-6 and np.abs(res - res_ref).max() < 1e-9
+    # the constrained frame has not moved relative to its reference frame (to first order along the path)
+    f, r = om.frame_id("RightFootFront"), om.frame_id(ref)
+    for b in range(0, B, 50):
+        rel = lambda qq: O.se3_actinv(om.frame_placement(qq, r), om.frame_placement(qq, f))
+        d = rel(q[b]) - rel(q0[b])
+        assert np.abs(d[9:]).max() < 2e-3 and (ktype == "Position" or np.abs(d[:9]).max() < 2e-3)

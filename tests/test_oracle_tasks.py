@@ -203,3 +203,46 @@ def test_align_axis_and_posture_tasks():
         ep, _ = pb.evaluate(m.integrate(q0, v), tg)
         em, _ = pb.evaluate(m.integrate(q0, -v), tg)
         assert abs((ep[0] - em[0]) / (2 * h) - J[0, c]) < 1e-8
+
+
+def test_frame_constraint_jacobian_and_null_space_projection():
+    """FrameConstraint (frame.hpp:333-465) and its use in ik::dls (dls.cpp:26-34,44-52), from first principles: Jc v is the
+    velocity of the frame relative to the reference frame, expressed in the frame (checked by differencing rMf along
+    q (+) eps v, for `universe` and for a moving reference frame and every KinematicType), the projected step satisfies
+    Jc dq = 0, and a solve with the right foot pinned leaves it where it was."""
+    m, q0 = cassie()
+    rng = np.random.default_rng(5)
+    q = m.integrate(q0, 0.3 * rng.standard_normal(m.nv))
+    for ref in ("universe", "pelvis"):
+        for ktype, rows in ((O.POSITION, slice(0, 3)), (O.ORIENTATION, slice(3, 6)), (O.FULL, slice(0, 6))):
+            pb = O.Problem(m)
+            pb.add_frame_constraint("RightFootFront", ktype, ref)
+            Jc = pb.constraint_jacobian(q)
+            f, r = m.frame_id("RightFootFront"), m.frame_id(ref)
+            rel = lambda qq: O.se3_actinv(m.frame_placement(qq, r), m.frame_placement(qq, f))
+            h = 1e-6
+            for _ in range(4):
+                v = rng.standard_normal(m.nv)
+                fd = (O.log6(O.se3_actinv(rel(q), rel(m.integrate(q, h * v)))) - O.log6(O.se3_actinv(rel(q), rel(m.integrate(q, -h * v))))) / (2 * h)
+                assert np.abs(Jc @ v - fd[rows]).max() < 1e-7, (ref, ktype)
+    # ik::dls with the right foot pinned (Full) while the left foot and the pelvis are asked to move
+    pb = O.Problem(m)
+    pb.add_frame_task("pelvis", O.FULL)
+    pb.add_frame_task("LeftFootFront", O.POSITION)
+    pb.add_frame_constraint("RightFootFront", O.FULL)
+    lf = m.frame_placement(q0, m.frame_id("LeftFootFront"))[9:]
+    tg = np.concatenate([O.se3(p=[0.0, 0.02, -0.03]), O.se3(p=lf + np.array([0.03, 0.0, 0.05]))])
+    q1, ok, it, res, dq = O.dls(pb, q0, tg, O.params(max_iterations=1))
+    assert np.abs(pb.constraint_jacobian(q0) @ dq).max() < 1e-12            # the step lies in the null space of Jc
+    qf, ok, it, res, _ = O.dls(pb, q0, tg, O.params(step_length=0.25, max_iterations=200))
+    rf0 = m.frame_placement(q0, m.frame_id("RightFootFront"))
+    rff = m.frame_placement(qf, m.frame_id("RightFootFront"))
+    # pinned along the whole path; the projected step (dls.cpp:52 projects AFTER the damped solve) stalls short of the
+    # tolerance here, like the reference would -- the error still drops from 4.7e-3 to 1e-3
+    assert np.abs(rff - rf0).max() < 1e-4 and res < 4.7e-3 / 3
+    # without the constraint the right foot is dragged along by the pelvis
+    pb2 = O.Problem(m)
+    pb2.add_frame_task("pelvis", O.FULL)
+    pb2.add_frame_task("LeftFootFront", O.POSITION)
+    qu = O.dls(pb2, q0, tg, O.params(step_length=0.25, max_iterations=200))[0]
+    assert np.abs(m.frame_placement(qu, m.frame_id("RightFootFront")) - rf0).max() > 1e-2
