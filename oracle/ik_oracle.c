@@ -407,14 +407,60 @@ void iko_clip(const iko_model *m, double *q) {
 /* ------------------------------------------------------------------------------------------------
  * problem bookkeeping (reference problem.hpp:34-40, frame.hpp:100-107, posture.hpp:27-33)
  * ---------------------------------------------------------------------------------------------- */
+/* pinocchio::jacobianCenterOfMass(model, data, q, false) (data.cpp:31-34): backward pass over the tree accumulating the
+ * mass and first moment of every subtree; the column of a joint coordinate is the velocity it gives its subtree's centre
+ * of mass, scaled by the subtree's share of the total mass.  Bodies attached to `universe` are not counted (Pinocchio's
+ * loops start at joint 1). */
+void iko_center_of_mass(const iko_model *m, const double *q, double com[3], double *Jcom) {
+    const int nj = m->njoints, nv = m->nv;
+    double *oMi = (double *)malloc(sizeof(double) * 12 * nj), *Jw = (double *)malloc(sizeof(double) * 6 * nv);
+    double *ms = (double *)calloc(nj, sizeof(double)), *mc = (double *)calloc(3 * nj, sizeof(double));
+    iko_fk(m, q, oMi);
+    iko_joint_jacobians(m, oMi, Jw);
+    for (int j = 1; j < nj; ++j) {
+        double cw[3];
+        matvec3(oMi + 12 * j, m->com + 3 * j, cw);
+        ms[j] = m->mass[j];
+        for (int i = 0; i < 3; ++i) mc[3 * j + i] = m->mass[j] * (cw[i] + oMi[12 * j + 9 + i]);
+    }
+    double M = 0, tot[3] = {0, 0, 0};
+    for (int j = nj - 1; j >= 1; --j) {
+        const int p = m->parent[j];
+        if (p > 0) {
+            ms[p] += ms[j];
+            for (int i = 0; i < 3; ++i) mc[3 * p + i] += mc[3 * j + i];
+        } else {
+            M += ms[j];
+            for (int i = 0; i < 3; ++i) tot[i] += mc[3 * j + i];
+        }
+    }
+    for (int i = 0; i < 3; ++i) com[i] = tot[i] / M;
+    if (Jcom) {
+        memset(Jcom, 0, sizeof(double) * 3 * nv);
+        for (int j = 1; j < nj; ++j) {
+            if (!(ms[j] > 0)) continue;
+            const double cs[3] = {mc[3 * j] / ms[j], mc[3 * j + 1] / ms[j], mc[3 * j + 2] / ms[j]};
+            for (int c = m->idx_v[j]; c < m->idx_v[j] + joint_nv(m, j); ++c) {
+                const double v[3] = {Jw[c], Jw[nv + c], Jw[2 * nv + c]}, w[3] = {Jw[3 * nv + c], Jw[4 * nv + c], Jw[5 * nv + c]};
+                double wxc[3];
+                cross3(w, cs, wxc);
+                for (int i = 0; i < 3; ++i) Jcom[i * nv + c] = ms[j] / M * (v[i] + wxc[i]);
+            }
+        }
+    }
+    free(oMi); free(Jw); free(ms); free(mc);
+}
+
 int iko_task_dim(const iko_problem *pb, int t) {
     if (pb->kind[t] == IKO_TASK_FRAME) return pb->type[t] == IKO_FULL ? 6 : 3;
     if (pb->kind[t] == IKO_TASK_ALIGN_AXIS) return 1;
+    if (pb->kind[t] == IKO_TASK_COM) return 3;
     return pb->type[t]; /* posture: nj */
 }
 int iko_task_target_size(const iko_problem *pb, int t) {
     if (pb->kind[t] == IKO_TASK_FRAME) return 12;
     if (pb->kind[t] == IKO_TASK_ALIGN_AXIS) return 3;
+    if (pb->kind[t] == IKO_TASK_COM) return 3;
     return pb->type[t];
 }
 int iko_target_size(const iko_problem *pb) {
@@ -490,6 +536,22 @@ void iko_evaluate(const iko_model *m, const iko_problem *pb, const double *q, co
                     iko_frame_jacobian_local(m, oMi, Jw, pb->frame[t], Jf);
                     for (int c = 0; c < nv; ++c)
                         Jt[c] = -(row3[0] * Jf[3 * nv + c] + row3[1] * Jf[4 * nv + c] + row3[2] * Jf[5 * nv + c]);
+                } else if (pb->kind[t] == IKO_TASK_COM) {
+                    /* CentreOfMassTask, centre_of_mass.hpp:24-38: e = oMr^-1 com - target; J = R_r^T Jcom (the reference frame
+                     * is not differentiated, like everywhere else in the reference) */
+                    double com[3], oMr[12], d[3];
+                    double *Jcom = (double *)malloc(sizeof(double) * 3 * nv);
+                    iko_center_of_mass(m, q, com, Jcom);
+                    iko_frame_placement(m, oMi, pb->ref[t], oMr);
+                    for (int i = 0; i < 3; ++i) d[i] = com[i] - oMr[9 + i];
+                    matTvec3(oMr, d, et);
+                    for (int i = 0; i < 3; ++i) et[i] -= tg[i];
+                    for (int c = 0; c < nv; ++c) {
+                        double col[3] = {Jcom[c], Jcom[nv + c], Jcom[2 * nv + c]}, lc[3];
+                        matTvec3(oMr, col, lc);
+                        for (int i = 0; i < 3; ++i) Jt[i * nv + c] = lc[i];
+                    }
+                    free(Jcom);
                 } else {
                     /* PostureTask, posture.hpp:50-67: e = (q.tail(nj) - target) o mask; J.rightCols(nj) = I */
                     const int nj = pb->type[t];

@@ -30,7 +30,7 @@ extern "C" {
 enum { IKO_J_UNIVERSE = 0, IKO_J_FREEFLYER = 1, IKO_J_RX = 2, IKO_J_RY = 3, IKO_J_RZ = 4,
        IKO_J_REV_UNALIGNED = 5, IKO_J_PX = 6, IKO_J_PY = 7, IKO_J_PZ = 8, IKO_J_PRIS_UNALIGNED = 9 };
 
-enum { IKO_TASK_FRAME = 0, IKO_TASK_ALIGN_AXIS = 1, IKO_TASK_POSTURE = 2 };
+enum { IKO_TASK_FRAME = 0, IKO_TASK_ALIGN_AXIS = 1, IKO_TASK_POSTURE = 2, IKO_TASK_COM = 3 };
 enum { IKO_POSITION = 0, IKO_ORIENTATION = 1, IKO_FULL = 2 };
 
 typedef struct {
@@ -47,6 +47,10 @@ typedef struct {
     int nframes;
     const int *frame_parent;       /* [nframes] supporting joint */
     const double *frame_placement; /* [nframes][12] */
+    /* per joint: total mass of the bodies it supports and their centre of mass in the joint frame (Pinocchio
+     * model.inertias[j].mass() / .lever(); CentreOfMassTask, centre_of_mass.hpp:14-52) */
+    const double *mass;            /* [njoints] */
+    const double *com;             /* [njoints][3] */
 } iko_model;
 
 typedef struct {
@@ -105,6 +109,9 @@ void iko_clip(const iko_model *m, double *q);
 /* one evaluate_problem_data() (data.cpp:25-58): stacked e [rows] and J [rows][nv] */
 void iko_evaluate(const iko_model *m, const iko_problem *pb, const double *q, const double *targets,
                   double *e, double *J);
+
+/* pinocchio::centerOfMass / jacobianCenterOfMass (data.cpp:31-34): com [3] and Jcom [3][nv] in the world frame */
+void iko_center_of_mass(const iko_model *m, const double *q, double com[3], double *Jcom);
 
 /* rows of all FrameConstraints and their stacked Jacobian Jc [crows][nv] (FrameConstraint::compute_jacobian,
  * frame.hpp:399-437: frame Jacobian minus the reference frame's, both LOCAL, the latter moved by rMf^-1) */

@@ -14,7 +14,7 @@ from . import urdf_flatten
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-TASK_FRAME, TASK_ALIGN_AXIS, TASK_POSTURE = 0, 1, 2
+TASK_FRAME, TASK_ALIGN_AXIS, TASK_POSTURE, TASK_COM = 0, 1, 2, 3
 POSITION, ORIENTATION, FULL = 0, 1, 2
 
 _dp = C.POINTER(C.c_double)
@@ -24,7 +24,7 @@ _ip = C.POINTER(C.c_int)
 class _CModel(C.Structure):
     _fields_ = [("njoints", C.c_int), ("nq", C.c_int), ("nv", C.c_int), ("parent", _ip), ("jtype", _ip),
                 ("idx_q", _ip), ("idx_v", _ip), ("placement", _dp), ("axis", _dp), ("lower", _dp), ("upper", _dp),
-                ("nframes", C.c_int), ("frame_parent", _ip), ("frame_placement", _dp)]
+                ("nframes", C.c_int), ("frame_parent", _ip), ("frame_placement", _dp), ("mass", _dp), ("com", _dp)]
 
 
 class _CProblem(C.Structure):
@@ -70,13 +70,17 @@ class Model:
     def __init__(self, flat):
         self.flat = flat
         self.nq, self.nv, self.njoints, self.nframes = flat["nq"], flat["nv"], flat["njoints"], flat["nframes"]
+        flat.setdefault("mass", np.zeros(self.njoints))
+        flat.setdefault("com", np.zeros((self.njoints, 3)))
         self._keep = {k: np.ascontiguousarray(flat[k]) for k in
                       ("parent", "jtype", "idx_q", "idx_v", "placement", "axis", "lower", "upper", "frame_parent",
                        "frame_placement")}
+        self._keep["mass"] = np.ascontiguousarray(flat["mass"], dtype=np.float64)
+        self._keep["com"] = np.ascontiguousarray(flat["com"], dtype=np.float64)
         k = self._keep
         self.c = _CModel(self.njoints, self.nq, self.nv, _pi(k["parent"]), _pi(k["jtype"]), _pi(k["idx_q"]),
                          _pi(k["idx_v"]), _pd(k["placement"]), _pd(k["axis"]), _pd(k["lower"]), _pd(k["upper"]),
-                         self.nframes, _pi(k["frame_parent"]), _pd(k["frame_placement"]))
+                         self.nframes, _pi(k["frame_parent"]), _pd(k["frame_placement"]), _pd(k["mass"]), _pd(k["com"]))
 
     @classmethod
     def from_urdf(cls, xml_text, free_flyer=True):
@@ -110,6 +114,13 @@ class Model:
         lib().iko_joint_jacobians(C.byref(self.c), _pd(oMi), _pd(Jw))
         lib().iko_frame_jacobian_local(C.byref(self.c), _pd(oMi), _pd(Jw), C.c_int(frame), _pd(Jf))
         return Jf
+
+    def center_of_mass(self, q):
+        """pinocchio::jacobianCenterOfMass: (com [3], Jcom [3, nv]) in the world frame."""
+        com = np.zeros(3)
+        J = np.zeros((3, self.nv))
+        lib().iko_center_of_mass(C.byref(self.c), _pd(_d(q)), _pd(com), _pd(J))
+        return com, J
 
     def integrate(self, q, v):
         out = np.zeros(self.nq)
@@ -166,6 +177,13 @@ class Problem:
         self.tasks.append(dict(kind=TASK_POSTURE, frame=0, ref=0, type=nj, priority=priority, dim=nj, tsz=nj,
                                weight=np.ones(nj) if weight is None else _d(weight),
                                mask=np.ones(nj) if mask is None else _d(mask)))
+        self._c = None
+        return len(self.tasks) - 1
+
+    def add_com_task(self, ref="universe", priority=0, weight=None):
+        """CentreOfMassTask (centre_of_mass.hpp:14-52): the centre of mass expressed in frame `ref` tracks a 3-vector."""
+        self.tasks.append(dict(kind=TASK_COM, frame=0, ref=self._fid(ref), type=0, priority=priority, dim=3, tsz=3,
+                               weight=np.ones(3) if weight is None else _d(weight), mask=np.zeros(0)))
         self._c = None
         return len(self.tasks) - 1
 

@@ -69,6 +69,15 @@ IDENTITY = [1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0]
 def flatten_urdf(xml_text, free_flyer=True):
     root = ET.fromstring(xml_text)
     links = [l.get("name") for l in root.findall("link")]
+    # <inertial>: mass and centre of mass of every link in its own frame (the rotational inertia is irrelevant for IK)
+    inertials = {}
+    for l in root.findall("link"):
+        ine = l.find("inertial")
+        if ine is None or ine.find("mass") is None:
+            continue
+        origin = ine.find("origin")
+        inertials[l.get("name")] = (float(ine.find("mass").get("value")),
+                                    _floats(origin.get("xyz") if origin is not None else None, 3, (0, 0, 0)))
     joints = {}
     for j in root.findall("joint"):
         name = j.get("name")
@@ -164,7 +173,23 @@ def flatten_urdf(xml_text, free_flyer=True):
     for jt in children[root_link]:
         visit(jt)
 
+    # Pinocchio appends the inertia of every body to its supporting joint (bodies behind fixed joints included):
+    # per joint the total mass and the centre of mass in the joint frame
+    nj = len(m["names"])
+    mass = np.zeros(nj)
+    moment = np.zeros((nj, 3))
+    for link, (ml, c) in inertials.items():
+        if link not in body_frame:
+            continue
+        f = body_frame[link]
+        pl = m["frame_placement"][f]
+        cj = [pl[9 + i] + sum(pl[3 * i + k] * c[k] for k in range(3)) for i in range(3)]
+        mass[m["frame_parent"][f]] += ml
+        moment[m["frame_parent"][f]] += ml * np.array(cj)
+    com = np.where(mass[:, None] > 0, moment / np.maximum(mass[:, None], 1e-300), 0.0)
+
     out = dict(
+        mass=mass, com=com,
         names=m["names"], frame_names=m["frame_names"], njoints=len(m["names"]), nq=nq, nv=nv,
         parent=np.array(m["parent"], dtype=np.int32), jtype=np.array(m["jtype"], dtype=np.int32),
         idx_q=np.array(m["idx_q"], dtype=np.int32), idx_v=np.array(m["idx_v"], dtype=np.int32),

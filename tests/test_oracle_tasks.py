@@ -246,3 +246,43 @@ def test_frame_constraint_jacobian_and_null_space_projection():
     pb2.add_frame_task("LeftFootFront", O.POSITION)
     qu = O.dls(pb2, q0, tg, O.params(step_length=0.25, max_iterations=200))[0]
     assert np.abs(m.frame_placement(qu, m.frame_id("RightFootFront")) - rf0).max() > 1e-2
+
+
+def test_centre_of_mass_task_from_first_principles():
+    """CentreOfMassTask (centre_of_mass.hpp:14-52, data.cpp:31-34): the oracle's centre of mass against a brute-force sum over
+    the bodies, its Jacobian against central differences, the task error / Jacobian in a moving reference frame (which
+    the reference does not differentiate: J = R_r^T Jcom), and the masses read from the URDF."""
+    m, q0 = cassie()
+    assert abs(m.flat["mass"].sum() - 34.676752) < 1e-9 and m.flat["mass"][1] == 10.33   # cassie.urdf <inertial><mass>
+    rng = np.random.default_rng(8)
+    q = m.integrate(q0, 0.4 * rng.standard_normal(m.nv))
+    com, Jcom = m.center_of_mass(q)
+    oMi = m.fk(q).reshape(-1, 12)
+    brute = sum(m.flat["mass"][j] * (oMi[j][:9].reshape(3, 3) @ m.flat["com"][j] + oMi[j][9:]) for j in range(1, m.njoints))
+    assert np.abs(com - brute / m.flat["mass"].sum()).max() < 1e-14
+    h = 1e-6
+    for c in range(m.nv):
+        v = np.zeros(m.nv)
+        v[c] = h
+        fd = (m.center_of_mass(m.integrate(q, v))[0] - m.center_of_mass(m.integrate(q, -v))[0]) / (2 * h)
+        assert np.abs(Jcom[:, c] - fd).max() < 1e-8, c
+    for ref in ("universe", "pelvis"):
+        pb = O.Problem(m)
+        pb.add_com_task(ref, weight=[1.0, 2.0, 0.5])
+        tg = np.array([0.01, -0.02, -0.5])
+        e, J = pb.evaluate(q, tg)
+        M = m.frame_placement(q, m.frame_id(ref))
+        R, p = M[:9].reshape(3, 3), M[9:]
+        assert np.abs(e - np.array([1.0, 2.0, 0.5]) * (R.T @ (com - p) - tg)).max() < 1e-14
+        assert np.abs(np.asarray(J).reshape(3, m.nv) - np.diag([1.0, 2.0, 0.5]) @ R.T @ Jcom).max() < 1e-14
+    # a solve: shift the centre of mass 3 cm sideways and 2 cm down, feet pinned by position tasks
+    pb = O.Problem(m)
+    pb.add_com_task("universe")
+    pb.add_frame_task("LeftFootFront", O.POSITION)
+    pb.add_frame_task("RightFootFront", O.POSITION)
+    c0 = m.center_of_mass(q0)[0]
+    lf = m.frame_placement(q0, m.frame_id("LeftFootFront"))[9:]
+    rf = m.frame_placement(q0, m.frame_id("RightFootFront"))[9:]
+    tg = np.concatenate([c0 + [0.0, 0.03, -0.02], O.se3(p=lf), O.se3(p=rf)])
+    qf, ok, it, res, _ = O.dls(pb, q0, tg)
+    assert ok and np.abs(m.center_of_mass(qf)[0] - (c0 + [0.0, 0.03, -0.02])).max() < 1e-2
