@@ -14,6 +14,7 @@
 
 #include "ik/dls.hpp"
 #include "ik/frame.hpp"
+#include "ik/centre_of_mass.hpp"
 #include "ik/pik.hpp"
 #include "ik/problem.hpp"
 
@@ -98,6 +99,16 @@ int main(int argc, char **argv) {
         const ik::vector_t qc = ik::dls(pinned, model.neutral(), cdata, ik::inverse_kinematics_visitor(), cp);
         std::printf("constraint c_size %d success %d iterations %d resid %.12e q7..10 %.12e %.12e %.12e %.12e\n", (int)pinned.c_size(),
                     (int)cdata.success, cdata.info.iterations, cdata.residual, qc[7], qc[8], qc[9], qc[10]);
+        // CentreOfMassTask (centre_of_mass.hpp:14-52): shift the centre of mass, keep the pelvis upright
+        ik::InverseKinematicsProblem balance(model, 0);
+        auto com = ik::CentreOfMassTask::create(model);
+        com->target = {0.02, 0.01, -0.25};
+        balance.add_centre_of_mass_task(com);
+        balance.add_frame_task("pelvis", ik::FrameTask::create(model, "pelvis", ik::KinematicType::Orientation));
+        ik::dls_data bdata(balance);
+        const ik::vector_t qb = ik::dls(balance, model.neutral(), bdata, ik::inverse_kinematics_visitor(), cp);
+        std::printf("com e_size %d success %d iterations %d resid %.12e q0..3 %.12e %.12e %.12e %.12e\n", (int)balance.e_size(0),
+                    (int)bdata.success, bdata.info.iterations, bdata.residual, qb[0], qb[1], qb[2], qb[7]);
     } catch (const std::exception &e) {
         std::fprintf(stderr, "error: %s\n", e.what());
         return 1;

@@ -77,6 +77,9 @@ SIGNATURES = {
     "ikb_problem_add_frame_task": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp]),
     "ikb_problem_add_align_axis_task": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp]),
     "ikb_problem_add_posture_task": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp]),
+    "ikb_problem_add_com_task": (C.c_int, [_vp, C.c_int, C.c_int, _dp]),
+    "ikb_model_get_inertias": (C.c_int, [_vp, _dp, _dp]),
+    "ikb_model_set_inertias": (C.c_int, [_vp, _dp, _dp]),
     "ikb_problem_add_frame_constraint": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
     "ikb_problem_c_size": (C.c_int, [_vp]),
     "ikb_problem_num_tasks": (C.c_int, [_vp]),

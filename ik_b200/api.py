@@ -107,6 +107,18 @@ class Model:
         capi.check(capi.lib.ikb_model_set_limits(self._h, _dptr(lo) if lo is not None else None,
                                                  _dptr(hi) if hi is not None else None), "ikb_model_set_limits")
 
+    def inertias(self):
+        """(mass [njoints], centre of mass in the joint frame [njoints, 3]) of the bodies each joint supports."""
+        mass, com = np.zeros(self.njoints), np.zeros((self.njoints, 3))
+        capi.check(capi.lib.ikb_model_get_inertias(self._h, _dptr(mass), _dptr(com)), "ikb_model_get_inertias")
+        return mass, com
+
+    def set_inertias(self, mass, com):
+        mass, com = _as_f64(mass), _as_f64(com)
+        if mass.shape != (self.njoints,) or com.shape != (self.njoints, 3):
+            raise ValueError("inertias: expected mass [%d] and com [%d, 3]" % (self.njoints, self.njoints))
+        capi.check(capi.lib.ikb_model_set_inertias(self._h, _dptr(mass), _dptr(com)), "ikb_model_set_inertias")
+
     def neutral(self):
         q = np.zeros(self.nq)
         capi.check(capi.lib.ikb_model_neutral(self._h, _dptr(q)), "ikb_model_neutral")
@@ -175,6 +187,16 @@ class PostureTask(Task):  # posture.hpp:17-86
     @property
     def target_size(self):
         return self.nj
+
+
+class CentreOfMassTask(Task):  # centre_of_mass.hpp:14-52
+    def __init__(self, model, reference_frame="universe"):
+        super().__init__(3)
+        self.reference_frame = reference_frame
+        self.target = np.zeros(3)  # centre of mass expressed in the reference frame
+
+    create = classmethod(lambda cls, *a, **k: cls(*a, **k))
+    target_size = 3
 
 
 class dls_parameters:  # dls.hpp:24-28 + common.hpp:59-66
@@ -262,6 +284,13 @@ class InverseKinematicsProblem:  # problem.hpp:9-206
     def add_posture_task(self, name, task, priority=0):  # problem.hpp:134-145
         return self._add(name, task, priority)
 
+    def add_centre_of_mass_task(self, task, priority=0):  # problem.hpp:121-128 (one per problem, no name)
+        self._com_task = self._add("centre_of_mass", task, priority)
+        return task
+
+    def get_centre_of_mass_task(self):  # problem.hpp:130-132
+        return getattr(self, "_com_task", None)
+
     def _get(self, name, cls):
         for n, t, _ in self._tasks:
             if n == name and isinstance(t, cls):
@@ -318,6 +347,12 @@ class InverseKinematicsProblem:  # problem.hpp:9-206
                     mask = _as_f64(t.mask)
                     capi.check_index(lib.ikb_problem_add_posture_task(h, t.nj, prio, _dptr(w), _dptr(mask)),
                                      "ikb_problem_add_posture_task")
+                    continue
+                if isinstance(t, CentreOfMassTask):
+                    r = m.getFrameId(t.reference_frame)
+                    if r >= m.nframes:
+                        raise KeyError("centre of mass task: unknown frame %r" % (t.reference_frame,))
+                    capi.check_index(lib.ikb_problem_add_com_task(h, r, prio, _dptr(w)), "ikb_problem_add_com_task")
                     continue
                 f, r = m.getFrameId(t.frame), m.getFrameId(t.reference_frame)
                 if f >= m.nframes or r >= m.nframes:

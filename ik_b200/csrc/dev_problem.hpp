@@ -24,6 +24,9 @@ template <typename T> struct alignas(16) DevProblem {
     T placement[kMaxJoints][12];
     T axis[kMaxJoints][3];
     T lower[kMaxNq], upper[kMaxNq];
+    T mass[kMaxJoints];        // per joint: mass of the bodies it supports, their centre of mass in the joint frame
+    T com[kMaxJoints][3];      //   (CentreOfMassTask, centre_of_mass.hpp:14-52); total_mass = sum over joints >= 1
+    T total_mass, tm_pad_;
     int32_t f_parent[kMaxFrames];
     T f_placement[kMaxFrames][12];
     // tasks, stacked order

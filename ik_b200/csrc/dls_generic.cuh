@@ -235,6 +235,49 @@ __global__ void __launch_bounds__(128) dls_generic_kernel(const DevProblem<T> *_
                         e[row + i] = (q[nq - nj + i] - tg[(toff + i) * es]) * P.mask[P.t_moff[t] + i];
                         J[row + i][nv - nj + i] = T(1);
                     }
+                } else if (kind == IKB_TASK_COM) {
+                    // CentreOfMassTask (centre_of_mass.hpp:24-38, data.cpp:31-34): backward pass accumulating the mass and
+                    // first moment of every subtree (joints are stored parents first), e = oMr^-1 com - target, and per
+                    // velocity coordinate the velocity it gives its subtree's centre of mass, weighted by the subtree's
+                    // share of the total mass, rotated into the reference frame (which the reference does not differentiate).
+                    T ms[NJ], mc[NJ][3];
+                    for (int j = 1; j < P.njoints; ++j) {
+                        T cw[3];
+                        rot_vec(oR[j], P.com[j], cw);
+                        ms[j] = P.mass[j];
+                        for (int i = 0; i < 3; ++i) mc[j][i] = P.mass[j] * (cw[i] + op[j][i]);
+                    }
+                    T tot[3] = {T(0), T(0), T(0)};
+                    for (int j = P.njoints - 1; j >= 1; --j) {
+                        const int par = P.parent[j];
+                        if (par > 0) {
+                            ms[par] += ms[j];
+                            for (int i = 0; i < 3; ++i) mc[par][i] += mc[j][i];
+                        } else {
+                            for (int i = 0; i < 3; ++i) tot[i] += mc[j][i];
+                        }
+                    }
+                    const T inv_m = T(1) / P.total_mass;
+                    const int r = P.t_ref[t], rj = P.f_parent[r];
+                    T Rr[9], pr[3], d[3], lc[3];
+                    se3_mul(oR[rj], op[rj], P.f_placement[r], P.f_placement[r] + 9, Rr, pr);
+                    for (int i = 0; i < 3; ++i) d[i] = tot[i] * inv_m - pr[i];
+                    rotT_vec(Rr, d, lc);
+                    for (int i = 0; i < 3; ++i) e[row + i] = lc[i] - tg[(toff + i) * es];
+                    for (int j = 1; j < P.njoints; ++j) {
+                        if (!(ms[j] > T(0))) continue;
+                        const T share = ms[j] * inv_m, ims = T(1) / ms[j];
+                        const T cs[3] = {mc[j][0] * ims, mc[j][1] * ims, mc[j][2] * ims};
+                        const int ncol = P.jtype[j] == IKB_J_FREEFLYER ? 6 : 1;
+                        for (int cc = 0; cc < ncol; ++cc) {
+                            T v[3], ww[3], wxc[3], vel[3];
+                            world_column<T, NJ>(P, j, cc, oR, op, v, ww);
+                            cross3(ww, cs, wxc);
+                            for (int i = 0; i < 3; ++i) vel[i] = share * (v[i] + wxc[i]);
+                            rotT_vec(Rr, vel, lc);
+                            for (int i = 0; i < 3; ++i) J[row + i][P.idx_v[j] + cc] = lc[i];
+                        }
+                    }
                 } else {
                     const int f = P.t_frame[t], r = P.t_ref[t];
                     const int fj = P.f_parent[f], rj = P.f_parent[r];

@@ -77,6 +77,13 @@ void fill_dev_problem(const HostProblem &hp, const std::vector<int> &order, cons
         for (int k = 0; k < 12; ++k) P.placement[j][k] = (T)m.placement[j][k];
         for (int k = 0; k < 3; ++k) P.axis[j][k] = (T)m.axis[j][k];
     }
+    double tm = 0;
+    for (int j = 0; j < m.njoints(); ++j) {
+        P.mass[j] = (T)m.mass[j];
+        for (int k = 0; k < 3; ++k) P.com[j][k] = (T)m.com[j][k];
+        if (j >= 1) tm += m.mass[j];
+    }
+    P.total_mass = (T)tm;
     const double big = (double)std::numeric_limits<T>::max();
     for (int k = 0; k < m.nq; ++k) {
         P.lower[k] = (T)std::max(m.lower[k], -big);
@@ -93,7 +100,7 @@ void fill_dev_problem(const HostProblem &hp, const std::vector<int> &order, cons
     for (size_t s = 0; s < order.size(); ++s) {
         const HostTask &t = hp.tasks[order[s]];
         P.t_kind[s] = t.kind;
-        P.t_frame[s] = t.kind == IKB_TASK_POSTURE ? 0 : local_frame(t.frame);
+        P.t_frame[s] = (t.kind == IKB_TASK_POSTURE || t.kind == IKB_TASK_COM) ? 0 : local_frame(t.frame);
         P.t_ref[s] = t.kind == IKB_TASK_POSTURE ? 0 : local_frame(t.ref);
         P.t_type[s] = t.type;
         P.t_row[s] = row;
@@ -421,6 +428,41 @@ int ikb_problem_add_posture_task(ikb_problem *p, int nj, int priority, const dou
     return add_task_common(p, t, priority, weights);
 }
 
+int ikb_problem_add_com_task(ikb_problem *p, int ref, int priority, const double *weights) {
+    if (!p) return -fail(IKB_ERR_INVALID_ARG, "null problem");
+    if (ref < 0 || ref >= p->hp.model.nframes()) return -fail(IKB_ERR_UNKNOWN_FRAME, "frame index out of range");
+    double tm = 0;
+    for (int j = 1; j < p->hp.model.njoints(); ++j) tm += p->hp.model.mass[j];
+    if (!(tm > 0)) return -fail(IKB_ERR_INVALID_ARG, "the model carries no mass (no <inertial> in the URDF / ikb_model_set_inertias)");
+    HostTask t;
+    t.kind = IKB_TASK_COM;
+    t.frame = ref;
+    t.ref = ref;
+    t.type = 0;
+    t.dim = 3;
+    t.target_size = 3;
+    return add_task_common(p, t, priority, weights);
+}
+
+int ikb_model_get_inertias(const ikb_model *m, double *mass, double *com) {
+    if (!m) return fail(IKB_ERR_INVALID_ARG, "null model");
+    for (int j = 0; j < m->m.njoints(); ++j) {
+        if (mass) mass[j] = m->m.mass[j];
+        if (com)
+            for (int k = 0; k < 3; ++k) com[3 * j + k] = m->m.com[j][k];
+    }
+    return IKB_OK;
+}
+int ikb_model_set_inertias(ikb_model *m, const double *mass, const double *com) {
+    if (!m || !mass || !com) return fail(IKB_ERR_INVALID_ARG, "null argument");
+    for (int j = 0; j < m->m.njoints(); ++j) {
+        if (!(mass[j] >= 0)) return fail(IKB_ERR_INVALID_ARG, "negative mass");
+        m->m.mass[j] = mass[j];
+        for (int k = 0; k < 3; ++k) m->m.com[j][k] = com[3 * j + k];
+    }
+    return IKB_OK;
+}
+
 int ikb_problem_add_frame_constraint(ikb_problem *p, int frame, int ktype, int ref) {
     if (!p) return -fail(IKB_ERR_INVALID_ARG, "null problem");
     if (p->finalized) return -fail(IKB_ERR_INVALID_ARG, "problem is finalized (immutable)");
@@ -462,7 +504,7 @@ int ikb_problem_finalize(ikb_problem *p, int device) {
     std::vector<int> used;
     for (const auto &t : hp.tasks)
         if (t.kind != IKB_TASK_POSTURE)
-            for (int f : {t.frame, t.ref})
+            for (int f : {t.kind == IKB_TASK_COM ? t.ref : t.frame, t.ref})
                 if (std::find(used.begin(), used.end(), f) == used.end()) used.push_back(f);
     for (const auto &c : hp.constraints)
         for (int f : {c.frame, c.ref})

@@ -27,6 +27,10 @@ struct HostModel {
     std::vector<SE3d> placement;
     std::vector<std::array<double, 3>> axis;
     std::vector<double> lower, upper;
+    // per joint: total mass of the bodies it supports (bodies behind fixed joints included) and their centre of mass in
+    // the joint frame -- Pinocchio's model.inertias[j].mass() / .lever(), read by CentreOfMassTask only
+    std::vector<double> mass;
+    std::vector<std::array<double, 3>> com;
     std::vector<std::string> frame_names;
     std::vector<int32_t> frame_parent, frame_type;
     std::vector<SE3d> frame_placement;

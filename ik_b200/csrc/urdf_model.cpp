@@ -44,6 +44,8 @@ int HostModel::add_joint(const std::string &name, int type, int parent_joint, co
     idx_v.push_back(nv);
     placement.push_back(pl);
     axis.push_back(ax);
+    mass.push_back(0.0);
+    com.push_back({0.0, 0.0, 0.0});
     lower.insert(lower.end(), lo.begin(), lo.end());
     upper.insert(upper.end(), hi.begin(), hi.end());
     nq += joint_nq(type);
@@ -319,12 +321,19 @@ HostModel model_from_urdf(const std::string &xml, bool free_flyer) {
     if (root->name != "robot") throw std::runtime_error("URDF: root element is <" + root->name + ">, expected <robot>");
 
     std::vector<std::string> links;
+    std::map<std::string, std::array<double, 4>> inertials;  // link -> mass, centre of mass in the link frame
     std::map<std::string, UrdfJoint> joints;  // std::map: byte-wise name order, as in urdfdom
     for (const auto &c : root->children) {
         if (c->name == "link") {
             const std::string *n = c->attr("name");
             if (!n) throw std::runtime_error("URDF: <link> without a name");
             links.push_back(*n);
+            if (const XmlNode *ine = c->child("inertial"))
+                if (const XmlNode *ms = ine->child("mass")) {
+                    const XmlNode *o = ine->child("origin");
+                    const auto xyz = parse_floats(o ? o->attr("xyz") : nullptr, 3, {0, 0, 0}, "inertial xyz");
+                    inertials[*n] = {parse_floats(ms->attr("value"), 1, {0}, "mass value")[0], xyz[0], xyz[1], xyz[2]};
+                }
         } else if (c->name == "joint") {
             UrdfJoint j;
             const std::string *n = c->attr("name"), *t = c->attr("type");
@@ -380,6 +389,21 @@ HostModel model_from_urdf(const std::string &xml, bool free_flyer) {
     auto it = b.children.find(root_link);
     if (it != b.children.end())
         for (const UrdfJoint *c : it->second) b.visit(*c);
+    // Pinocchio appends every body's inertia to its supporting joint: mass and first moment in the joint frame
+    std::vector<std::array<double, 3>> moment(m.njoints(), {0.0, 0.0, 0.0});
+    for (const auto &kv : inertials) {
+        auto bf = b.body_frame.find(kv.first);
+        if (bf == b.body_frame.end()) continue;
+        const SE3d &pl = m.frame_placement[bf->second];
+        const int j = m.frame_parent[bf->second];
+        const double ml = kv.second[0];
+        m.mass[j] += ml;
+        for (int i = 0; i < 3; ++i)
+            moment[j][i] += ml * (pl[9 + i] + pl[3 * i] * kv.second[1] + pl[3 * i + 1] * kv.second[2] + pl[3 * i + 2] * kv.second[3]);
+    }
+    for (int j = 0; j < m.njoints(); ++j)
+        if (m.mass[j] > 0)
+            for (int i = 0; i < 3; ++i) m.com[j][i] = moment[j][i] / m.mass[j];
     return std::move(b.m);
 }
 

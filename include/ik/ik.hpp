@@ -15,6 +15,7 @@
 //   ik::KinematicType, ik::FrameTask (+ ::create, target) ik/ik/frame.hpp:20,78-200     same
 //   ik::AlignAxisType, ik::AlignAxisTask                 ik/ik/frame.hpp:202-319        same
 //   ik::PostureTask                                      ik/ik/posture.hpp:17-86        same
+//   ik::CentreOfMassTask                                 ik/ik/centre_of_mass.hpp:14-52 same (add_/get_centre_of_mass_task)
 //   ik::InverseKinematicsProblem                         ik/ik/problem.hpp:9-206        same members (frame/axis/posture tasks)
 //   ik::inverse_kinematics_visitor                       ik/ik/visitor.hpp:7-24         default stop test; `tolerance` member
 //   ik::dls_parameters, ik::dls_data, ik::dls_info       ik/ik/dls.hpp:24-74            same (+ iterations / residual filled)
@@ -106,7 +107,7 @@ struct default_solver_parameters {  // ik/ik/common.hpp:59-66
 
 class Task {  // ik/ik/task.hpp:19-57
    public:
-    enum class Kind { Frame, AlignAxis, Posture };
+    enum class Kind { Frame, AlignAxis, Posture, CentreOfMass };
     Task() : dimension_(0) {}
     explicit Task(const index_t &dimension) { set_dimension(dimension); }
     virtual ~Task() = default;
@@ -197,6 +198,19 @@ class PostureTask : public Task {  // ik/ik/posture.hpp:17-86
     index_t nj;
 };
 
+class CentreOfMassTask : public Task {  // ik/ik/centre_of_mass.hpp:14-52
+   public:
+    CentreOfMassTask(const model_t &model, const std::string &reference_frame) : Task(3), reference_frame(reference_frame) {
+        (void)model;
+    }
+    static std::shared_ptr<CentreOfMassTask> create(const model_t &model, const std::string &reference_frame = "universe") {
+        return std::make_shared<CentreOfMassTask>(model, reference_frame);
+    }
+    Kind kind() const override { return Kind::CentreOfMass; }
+    std::array<number_t, 3> target{{0, 0, 0}};  // centre of mass in the task's reference frame
+    std::string reference_frame;         // (private in the reference; the bridge to the C ABI reads it)
+};
+
 class InverseKinematicsProblem {  // ik/ik/problem.hpp:9-206
    public:
     InverseKinematicsProblem(const model_t &model, const std::size_t &max_priority_level = 0)
@@ -241,6 +255,16 @@ class InverseKinematicsProblem {  // ik/ik/problem.hpp:9-206
         return add(posture_tasks_map_, posture_tasks_, name, task, priority);
     }
     std::shared_ptr<PostureTask> get_posture_task(const std::string &name) { return posture_tasks_.at(posture_tasks_map_.at(name)); }
+    std::shared_ptr<CentreOfMassTask> add_centre_of_mass_task(const std::shared_ptr<CentreOfMassTask> &task,
+                                                              const std::size_t &priority = 0) {  // problem.hpp:121-128
+        if (priority > max_priority_level_) throw std::out_of_range("Maximum priority level exceeded!");
+        com_task_ = task;
+        tasks_[priority].push_back(task);
+        ordered_.emplace_back(task, priority);
+        release();
+        return com_task_;
+    }
+    std::shared_ptr<CentreOfMassTask> get_centre_of_mass_task() { return com_task_; }
     const std::vector<std::shared_ptr<Task>> &get_all_tasks(const std::size_t &priority) const { return tasks_.at(priority); }
     const model_t &model() const { return model_; }
 
@@ -266,6 +290,9 @@ class InverseKinematicsProblem {  // ik/ik/problem.hpp:9-206
                 const auto &a = static_cast<const AlignAxisTask &>(t);
                 rc = ikb_problem_add_align_axis_task(h_, frame_id(a.frame), (int)a.axis, frame_id(a.reference_frame),
                                                      (int)tp.second, t.weighting().data());
+            } else if (t.kind() == Task::Kind::CentreOfMass) {
+                const auto &c = static_cast<const CentreOfMassTask &>(t);
+                rc = ikb_problem_add_com_task(h_, frame_id(c.reference_frame), (int)tp.second, t.weighting().data());
             } else {
                 const auto &p = static_cast<const PostureTask &>(t);
                 rc = ikb_problem_add_posture_task(h_, (int)p.nj, (int)tp.second, t.weighting().data(), p.mask.data());
@@ -299,6 +326,9 @@ class InverseKinematicsProblem {  // ik/ik/problem.hpp:9-206
             } else if (k.kind() == Task::Kind::AlignAxis) {
                 const auto &a = static_cast<const AlignAxisTask &>(k);
                 t.insert(t.end(), a.target.begin(), a.target.end());
+            } else if (k.kind() == Task::Kind::CentreOfMass) {
+                const auto &c = static_cast<const CentreOfMassTask &>(k);
+                t.insert(t.end(), c.target.begin(), c.target.end());
             } else {
                 const auto &p = static_cast<const PostureTask &>(k);
                 t.insert(t.end(), p.target.begin(), p.target.end());
@@ -338,6 +368,7 @@ class InverseKinematicsProblem {  // ik/ik/problem.hpp:9-206
     std::unordered_map<string_t, std::size_t> frame_tasks_map_;
     std::vector<std::shared_ptr<AlignAxisTask>> axis_tasks_;
     std::unordered_map<string_t, std::size_t> axis_tasks_map_;
+    std::shared_ptr<CentreOfMassTask> com_task_ = nullptr;
     std::vector<std::shared_ptr<FrameConstraint>> constraints_;
     std::unordered_map<string_t, std::size_t> constraints_map_;
     ikb_problem *h_ = nullptr;

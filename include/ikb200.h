@@ -51,7 +51,7 @@ typedef enum {
 typedef enum { IKB_POSITION = 0, IKB_ORIENTATION = 1, IKB_FULL = 2 } ikb_kinematic_type;
 /* ik::AlignAxisType, reference ik/ik/frame.hpp:202 */
 typedef enum { IKB_AXIS_X = 0, IKB_AXIS_Y = 1, IKB_AXIS_Z = 2 } ikb_axis;
-typedef enum { IKB_TASK_FRAME = 0, IKB_TASK_ALIGN_AXIS = 1, IKB_TASK_POSTURE = 2 } ikb_task_kind;
+typedef enum { IKB_TASK_FRAME = 0, IKB_TASK_ALIGN_AXIS = 1, IKB_TASK_POSTURE = 2, IKB_TASK_COM = 3 } ikb_task_kind;
 typedef enum { IKB_F64 = 0, IKB_F32 = 1 } ikb_dtype;
 
 typedef struct ikb_model ikb_model;     /* replaces ik::model_t = pinocchio::Model (common.hpp:17) */
@@ -122,6 +122,14 @@ int ikb_problem_add_align_axis_task(ikb_problem *p, int frame, int axis, int ref
                                     const double *weights);
 /* PostureTask(model, nj) + add_posture_task: posture.hpp:17-86, problem.hpp:134-145.  mask: nj entries or NULL */
 int ikb_problem_add_posture_task(ikb_problem *p, int nj, int priority, const double *weights, const double *mask);
+/* CentreOfMassTask (reference centre_of_mass.hpp:14-52, problem.hpp add_centre_of_mass_task, data.cpp:31-34):
+ * e = oMr^-1 com(q) - target, J = R_r^T Jcom; 3 rows, target = 3 scalars.  Needs link masses: models from URDF read
+ * <inertial><mass>/<origin xyz>; ikb_model_set_inertias supplies them for models built from flat arrays.  Runs on
+ * the table-driven kernel.  Returns the task index (insertion order) or minus an ikb_status. */
+int ikb_problem_add_com_task(ikb_problem *p, int ref, int priority, const double *weights /* 3 or NULL */);
+/* per joint: mass of the bodies it supports and their centre of mass in the joint frame (Pinocchio inertias[j]) */
+int ikb_model_get_inertias(const ikb_model *m, double *mass /* [njoints] */, double *com /* [njoints][3] */);
+int ikb_model_set_inertias(ikb_model *m, const double *mass, const double *com);
 /* FrameConstraint (reference frame.hpp:333-465; problem.hpp add_frame_constraint): ik::dls projects its step into the null
  * space of the stacked constraint Jacobian, N = I - Jc.completeOrthogonalDecomposition().pseudoInverse() Jc
  * (dls.cpp:26-34,44-52), i.e. keeps `frame` at rest relative to `ref`.  Returns the constraint index or minus an

@@ -29,6 +29,8 @@ def oracle_problem_like(problem, omodel):
             opb.add_frame_task(t.frame, int(t.type), t.reference_frame, prio, t.weighting())
         elif isinstance(t, ik.AlignAxisTask):
             opb.add_align_axis_task(t.frame, int(t.axis), t.reference_frame, prio, t.weighting())
+        elif isinstance(t, ik.CentreOfMassTask):
+            opb.add_com_task(t.reference_frame, prio, t.weighting())
         else:
             opb.add_posture_task(t.nj, prio, t.weighting(), t.mask)
     for c in problem.get_all_constraints():

@@ -71,6 +71,29 @@ def test_problem_sizes_follow_the_reference():
         capi.lib.ikb_problem_free(h)
 
 
+def test_model_inertias_follow_the_urdf_and_the_oracle():
+    """CentreOfMassTask needs Pinocchio's model.inertias: per joint, the mass / centre of mass of the bodies it carries
+    (links behind fixed joints folded into their supporting joint).  The product's URDF parser against the oracle's."""
+    from tests.common import oracle_model
+    for name, ff in (("cassie", True), ("ur5", False)):
+        m = ik.Model.builtin(name, free_flyer=ff)
+        om = oracle_model(name, ff)
+        mass, com = m.inertias()
+        assert mass.shape == (m.njoints,) and np.allclose(mass, om.flat["mass"], rtol=0, atol=1e-12)
+        assert np.allclose(com, np.reshape(om.flat["com"], (-1, 3)), rtol=0, atol=1e-12)
+    m = W.cassie_model()
+    mass, com = m.inertias()
+    assert abs(mass[1:].sum() - 34.676752) < 1e-9  # sum of the <mass value=...> entries of the fixture
+    # a model without mass cannot carry the task (hard error, not a division by zero on the device)
+    m.set_inertias(np.zeros_like(mass), com)
+    pb = ik.InverseKinematicsProblem(m, 0)
+    pb.add_centre_of_mass_task(ik.CentreOfMassTask(m))
+    with pytest.raises(RuntimeError, match="mass"):
+        pb.specialisation()
+    m.set_inertias(mass, com)
+    assert pb.specialisation() is None and pb.get_centre_of_mass_task().dimension() == 3 and pb.target_size == 3
+
+
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
 def test_solve_fails_loudly_without_a_gpu():
     pb = W.cassie_feet_pelvis_problem()
@@ -137,3 +160,11 @@ def test_cpp_facade_demo_matches_oracle():
     qc, okc, itc, resc, _ = O.dls(opc, om.neutral(), O.se3(p=[0.0, 0.01, -0.02]), O.params(step_length=0.5))
     assert int(cl[2]) == 6 and int(cl[4]) == int(okc) and int(cl[6]) == itc and abs(float(cl[8]) - resc) < 1e-9
     assert np.abs(np.array([float(x) for x in cl[10:14]]) - qc[7:11]).max() < 1e-6
+    # CentreOfMassTask through the facade (centre_of_mass.hpp:14-52)
+    bl = [l.split() for l in r.stdout.splitlines() if l.startswith("com ")][0]
+    opm = O.Problem(om, 0)
+    opm.add_com_task("universe", 0)
+    opm.add_frame_task("pelvis", O.ORIENTATION, "universe", 0)
+    qb, okb, itb, resb, _ = O.dls(opm, om.neutral(), np.concatenate([[0.02, 0.01, -0.25], O.se3()]), O.params(step_length=0.5))
+    assert int(bl[2]) == 6 and int(bl[4]) == int(okb) and int(bl[6]) == itb and abs(float(bl[8]) - resb) < 1e-9
+    assert np.abs(np.array([float(x) for x in bl[10:14]]) - qb[[0, 1, 2, 7]]).max() < 1e-6

@@ -476,3 +476,47 @@ def test_frame_constraint_null_space_projection(ktype, ref):
         rel = lambda qq: O.se3_actinv(om.frame_placement(qq, r), om.frame_placement(qq, f))
         d = rel(q[b]) - rel(q0[b])
         assert np.abs(d[9:]).max() < 2e-3 and (ktype == "Position" or np.abs(d[:9]).max() < 2e-3)
+
+
+@pytest.mark.parametrize("ref", ["universe", "LeftFootFront"])
+def test_centre_of_mass_task(ref):
+    """CentreOfMassTask (centre_of_mass.hpp:14-52; data.cpp:31-34 jacobianCenterOfMass): the centre of mass -- in the
+    world, or relative to the moving stance foot -- is steered together with both foot positions and the pelvis
+    orientation.  Table-driven kernel vs the oracle: flags, step counts, q, residuals; and converged solutions really put
+    the centre of mass (computed independently from the URDF masses) on the target."""
+    m = W.cassie_model()
+    pb = ik.InverseKinematicsProblem(m, 0)
+    pb.add_frame_task("fl", ik.FrameTask(m, "LeftFootFront", ik.KinematicType.Position))
+    com = pb.add_centre_of_mass_task(ik.CentreOfMassTask(m, ref))
+    pb.add_frame_task("fr", ik.FrameTask(m, "RightFootFront", ik.KinematicType.Position))
+    pb.add_frame_task("pelvis", ik.FrameTask(m, "pelvis", ik.KinematicType.Orientation))
+    com.weighting()[:] = [2.0, 2.0, 0.5]
+    assert pb.e_size(0) == 12 and pb.specialisation() is None and pb.get_centre_of_mass_task() is com
+    om = oracle_model("cassie")
+    opb = oracle_problem_like(pb, om)
+    B = 600
+    q0, tg, qstar = make_workload(pb, om, B, seed=17, standing=W.CASSIE_STANDING)
+    off, r = pb.target_offset(com), om.frame_id(ref)
+    for b in range(B):
+        oMr = om.frame_placement(qstar[b], r)
+        tg[b, off:off + 3] = oMr[:9].reshape(3, 3).T @ (om.center_of_mass(qstar[b])[0] - oMr[9:])
+    # Relative to a moving frame the task's Jacobian is inexact -- the reference does not differentiate the reference
+    # frame's own motion -- so almost nothing converges and the iteration wanders off chaotically: there the first 6
+    # steps of the trajectory are compared instead of its end.
+    mi = 100 if ref == "universe" else 6
+    q_ref, ok_ref, it_ref, res_ref = O.dls_batch(opb, q0, tg, O.params(mi), nthreads=NT)
+    q, ok, it, res = _solve_gpu(pb, q0, tg, ik.dls_parameters(max_iterations=mi))
+    assert (ok == ok_ref).all() and (it == it_ref).all() and (ok.mean() > 0.9 or ref != "universe")
+    assert np.abs(q - q_ref)[ok].max(initial=0) < 1e-6 and np.abs(res - res_ref)[ok].max(initial=0) < 1e-9
+    err = np.abs(q - q_ref).max(axis=1)
+    print("com", ref, "converged", ok.mean(), "q err max", err.max(), "p99", np.percentile(err, 99))
+    assert np.percentile(err, 99) < 1e-6 and err.max() < 1e-4
+    for b in np.flatnonzero(ok)[:20]:
+        oMr = om.frame_placement(q[b], r)
+        c = oMr[:9].reshape(3, 3).T @ (om.center_of_mass(q[b])[0] - oMr[9:])
+        assert np.abs(c - tg[b, off:off + 3]).max() < 2e-3  # stop test: |J^T e| < 1e-4, not |e|
+    # FP32 build of the same kernel
+    if ref == "universe":
+        q32, ok32, _, _ = _solve_gpu(pb, q0, tg, dtype="f32")
+        both = ok & ok32
+        assert (ok32 == ok).mean() > 0.97 and np.percentile(np.abs(q32 - q)[both].max(axis=1), 99) < 1e-3
