@@ -8,7 +8,7 @@ frame), library-default solver parameters (max_iterations 100, damping 1e-2, ste
 reachable targets PER GPU (weak scaling: rank r solves problem indices [r*B, (r+1)*B)), FP64.
 
 A "step" = one batched ik::dls over one batch of B problems.  The K timed steps go through the pipelined queue
-(ikb_queue_*, include/ikb200.h -- the API for a stream of batches): `--merge` consecutive batches (default 4), each with
+(ikb_queue_*, include/ikb200.h -- the API for a stream of batches): `--merge` consecutive batches (default 8 of 16 in flight), each with
 its own buffers, share ONE kernel pair -- the BULK launch suspends the few stragglers still unfinished when the ticket
 queue runs dry, the TAIL launch continues them in the latency configuration -- so the stragglers'
 serial chain (a problem that never converges runs all 100 steps, ~0.7 ms of mostly idle SMs) is paid once per group.
@@ -16,7 +16,8 @@ serial chain (a problem that never converges runs all 100 steps, ~0.7 ms of most
 `config.isolated_ms_per_batch` is the same K steps through the plain per-batch call (ikb_dls_solve_batch), one kernel
 pair per batch.  `e2e` = the same metric with HOST buffers through the queue's host entry point
 (ikb_queue_submit_host / ikb_queue_wait): every step's inputs are copied from pinned host memory, every step's results
-(q, success, iters, resid) are copied back and read; the copies of one group run beside the kernels of its neighbours.
+(q, success, iters, resid) are copied back and read; the copies of one group run beside the kernels of its neighbours
+(`--e2e-merge` 4 of `--e2e-depth` 8 in flight: this arm is bound by the PCIe link, smaller groups shorten its fill and drain).
 `e2e.isolated_ms_per_batch` is the blocking per-batch host call (ikb_dls_solve_batch_host).
 `roofline` is the compute roofline of the solve (all launches of the timed region -- they are one pass of the path per
 step): algorithmic FLOPs (F_iter = 9,360 per evaluation, (iterations+1) evaluations per problem) / event-
@@ -146,15 +147,18 @@ def cpu_reference_arm(B_sample, steps, warmup, cores):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=48)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--batch", type=int, default=65536, help="problems per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--merge", type=int, default=4, help="consecutive batches per kernel pair in the pipelined queue (1 = off)")
-    ap.add_argument("--depth", type=int, default=8, help="batches in flight in the pipelined queue")
+    ap.add_argument("--merge", type=int, default=8, help="consecutive batches per kernel pair in the pipelined queue (1 = off)")
+    ap.add_argument("--depth", type=int, default=16, help="batches in flight in the pipelined queue")
+    ap.add_argument("--e2e-merge", type=int, default=4, help="the same for the host-buffer (e2e) arm: smaller groups keep the "
+                    "PCIe pipeline's fill / drain short")
+    ap.add_argument("--e2e-depth", type=int, default=8)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -211,7 +215,7 @@ def main():
     # Distinct input/output sets, rotated every step, so the per-step inputs are not L2 hits left by the previous
     # step: NSETS * (inputs+outputs) > 126 MB of L2.
     per_set = B * hbm_bytes_per_solve(nq, tsz, np.dtype(npdt).itemsize)
-    nsets = max(2, int(np.ceil(160e6 / per_set)) + 1)
+    nsets = max(2, int(np.ceil(160e6 / per_set)) + 1, args.depth)  # ... and no set twice among the batches in flight
     sets = []
     for s in range(nsets):
         qstar = W.sample_configurations(m, B, seed=12345 + s, b0=rank * B)
@@ -309,7 +313,9 @@ def main():
     # ---- e2e arm: HOST buffers.  Every step copies that step's inputs from pinned host memory and reads its results back
     # (q, success, iters, resid); the steps go through the queue's host entry point (ikb_queue_submit_host / ikb_queue_wait),
     # so the copies of one group of batches run beside the kernels of its neighbours. ----
-    nbuf = depth
+    e2e_depth = max(args.e2e_depth, args.e2e_merge)
+    queue_h = ik.SolveQueue(pb, e2e_depth, args.e2e_merge, local_rank)
+    nbuf = e2e_depth
     h_in = [(pinned_array((nq, B), npdt), pinned_array((tsz, B), npdt)) for _ in range(nbuf)]
     h_outs = [{"q": pinned_array((nq, B), npdt), "success": pinned_array((B,), np.uint8),
                "iters": pinned_array((B,), np.int32), "resid": pinned_array((B,), npdt)} for _ in range(nbuf)]
@@ -317,25 +323,25 @@ def main():
     for i, (hq, ht) in enumerate(h_in):
         hq[:] = q0_np.T
         ht[:] = host_sets[i % len(host_sets)]
-    e2e_steps = max(3, min(args.steps, 20))
-    lag = max(1, depth - 1)              # results of step k are consumed after step k + lag has been submitted: the
+    e2e_steps = args.steps
+    lag = max(1, e2e_depth - 1)              # results of step k are consumed after step k + lag has been submitted: the
                                          # next group is fully in flight before the host blocks on the previous one
 
     def e2e_run(nsteps):
         got = 0
         tickets = []
         for k in range(nsteps):
-            t, _ = queue.submit_host(h_in[k % nbuf][0], h_in[k % nbuf][1], prm, args.dtype, "soa", h_outs[k % nbuf])
+            t, _ = queue_h.submit_host(h_in[k % nbuf][0], h_in[k % nbuf][1], prm, args.dtype, "soa", h_outs[k % nbuf])
             tickets.append(t)
             if k >= lag:
-                queue.wait(tickets[k - lag])
+                queue_h.wait(tickets[k - lag])
                 got += int(h_outs[(k - lag) % nbuf]["success"].sum())
         for k in range(max(0, nsteps - lag), nsteps):
-            queue.wait(tickets[k])
+            queue_h.wait(tickets[k])
             got += int(h_outs[k % nbuf]["success"].sum())
         return got
 
-    e2e_run(nbuf + args.merge)           # every slot's staging buffers exist before the timed region
+    e2e_run(nbuf + args.e2e_merge)           # every slot's staging buffers exist before the timed region
     # the same steps through the blocking per-batch host call, for reference
     for k in range(2):
         ik.dls_batch_host(pb, h_in[0][0], h_in[0][1], prm, args.dtype, "soa", h_outs[0])
@@ -410,6 +416,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * (nq + tsz) * itemsize),
                     "d2h_bytes_per_step": int(B * ((nq + 1) * itemsize + 5)), "steps": e2e_steps,
                     "api": "ikb_queue_submit_host + ikb_queue_wait (pinned host buffers; H2D, solve, D2H of every step)",
+                    "pipeline": "ikb_queue, depth %d, %d consecutive batches per BULK+TAIL kernel pair" % (e2e_depth, args.e2e_merge),
                     "isolated_ms_per_batch": e2e_isolated_ms,
                     "isolated_api": "ikb_dls_solve_batch_host (blocking, one batch at a time)"},
             "gpu_launches": int(launches),

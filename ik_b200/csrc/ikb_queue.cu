@@ -1,4 +1,6 @@
 // The pipelined queue of the C ABI (include/ikb200.h, ikb_queue_*).
+#include <chrono>
+#include <cstdio>
 #include <utility>
 
 #include "capi_internal.hpp"
@@ -15,6 +17,8 @@ using namespace ikb::capi;
 struct ikb_queue {
     struct Slot {
         cudaEvent_t ev_in = nullptr, ev_done = nullptr;
+        cudaEvent_t tr_in0 = nullptr, tr_c0 = nullptr, tr_c1 = nullptr;  // IKB_QUEUE_TRACE only
+        double tr_submit_ms = 0;
         bool busy = false, pending = false, host = false;
         int64_t ticket = -1;  // the batch occupying the slot
         int64_t B = 0;
@@ -36,6 +40,10 @@ struct ikb_queue {
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
     cudaEvent_t ev_user = nullptr, ev_comp = nullptr;
     int64_t next = 0;
+    // IKB_QUEUE_TRACE=1: device timeline of every host batch on stderr (printed by ikb_queue_wait)
+    bool trace = false, tr_started = false;
+    cudaEvent_t tr_ref = nullptr;
+    std::chrono::steady_clock::time_point tr_host_ref;
 };
 
 namespace {
@@ -67,6 +75,8 @@ template <typename T> int queue_flush_t(ikb_queue *q) {
     int rc;
     for (int i : q->open)
         if (q->slots[i].host) IKB_CUDA(cudaStreamWaitEvent(q->s_comp, q->slots[i].ev_in, 0));
+    if (q->trace)
+        for (int i : q->open) IKB_CUDA(cudaEventRecord(q->slots[i].tr_c0, q->s_comp));
     if (n >= 2 && q->p->spec && q->open_prm.max_iterations > 0) {
         BatchSeg<T> tab[kMaxSegments];
         long long total = 0;
@@ -88,6 +98,8 @@ template <typename T> int queue_flush_t(ikb_queue *q) {
     }
     bool any_host = false;
     for (int i : q->open) any_host |= q->slots[i].host;
+    if (q->trace)
+        for (int i : q->open) IKB_CUDA(cudaEventRecord(q->slots[i].tr_c1, q->s_comp));
     if (any_host) {
         IKB_CUDA(cudaEventRecord(q->ev_comp, q->s_comp));
         IKB_CUDA(cudaStreamWaitEvent(q->s_out, q->ev_comp, 0));
@@ -157,6 +169,15 @@ template <typename T> int queue_stage_host(ikb_queue *q, ikb_queue::Slot &sl, in
         IKB_CUDA(cudaMalloc(&sl.iters, (size_t)B * sizeof(int)));
         sl.flag_cap = (size_t)B;
     }
+    if (q->trace) {
+        if (!q->tr_started) {
+            IKB_CUDA(cudaEventRecord(q->tr_ref, q->s_in));
+            q->tr_host_ref = std::chrono::steady_clock::now();
+            q->tr_started = true;
+        }
+        sl.tr_submit_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - q->tr_host_ref).count();
+        IKB_CUDA(cudaEventRecord(sl.tr_in0, q->s_in));
+    }
     IKB_CUDA(cudaMemcpyAsync(st.q0, io->q0, n_q0 * sizeof(T), cudaMemcpyHostToDevice, q->s_in));
     if (n_tg) IKB_CUDA(cudaMemcpyAsync(st.targets, io->targets, n_tg * sizeof(T), cudaMemcpyHostToDevice, q->s_in));
     IKB_CUDA(cudaEventRecord(sl.ev_in, q->s_in));
@@ -183,10 +204,18 @@ int ikb_queue_create(ikb_problem *p, int depth, int merge, ikb_queue **out) {
     q->slots.resize(depth);
     *out = q;  // the caller frees it also when creation fails half-way
     for (cudaStream_t *s : {&q->s_in, &q->s_comp, &q->s_out}) IKB_CUDA(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking));
+    const char *tr = std::getenv("IKB_QUEUE_TRACE");
+    q->trace = tr && tr[0] == '1';
+    const unsigned evf = q->trace ? cudaEventDefault : cudaEventDisableTiming;
     IKB_CUDA(cudaEventCreateWithFlags(&q->ev_user, cudaEventDisableTiming));
     IKB_CUDA(cudaEventCreateWithFlags(&q->ev_comp, cudaEventDisableTiming));
     for (auto &sl : q->slots)
-        for (cudaEvent_t *e : {&sl.ev_in, &sl.ev_done}) IKB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        for (cudaEvent_t *e : {&sl.ev_in, &sl.ev_done}) IKB_CUDA(cudaEventCreateWithFlags(e, evf));
+    if (q->trace) {
+        IKB_CUDA(cudaEventCreate(&q->tr_ref));
+        for (auto &sl : q->slots)
+            for (cudaEvent_t *e : {&sl.tr_in0, &sl.tr_c0, &sl.tr_c1}) IKB_CUDA(cudaEventCreate(e));
+    }
     return IKB_OK;
 }
 
@@ -201,8 +230,9 @@ void ikb_queue_free(ikb_queue *q) {
         }
     if (q->ev_user) cudaEventDestroy(q->ev_user);
     if (q->ev_comp) cudaEventDestroy(q->ev_comp);
+    if (q->tr_ref) cudaEventDestroy(q->tr_ref);
     for (auto &sl : q->slots) {
-        for (cudaEvent_t e : {sl.ev_in, sl.ev_done})
+        for (cudaEvent_t e : {sl.ev_in, sl.ev_done, sl.tr_in0, sl.tr_c0, sl.tr_c1})
             if (e) cudaEventDestroy(e);
         cudaFree(sl.st64.q0); cudaFree(sl.st64.targets); cudaFree(sl.st64.q); cudaFree(sl.st64.resid);
         cudaFree(sl.st32.q0); cudaFree(sl.st32.targets); cudaFree(sl.st32.q); cudaFree(sl.st32.resid);
@@ -259,6 +289,17 @@ int ikb_queue_wait(ikb_queue *q, int64_t ticket) {
     int rc;
     if (sl.pending && (rc = queue_flush(q))) return rc;
     IKB_CUDA(cudaEventSynchronize(sl.ev_done));
+    if (q->trace && sl.host && sl.busy) {
+        float a = 0, b = 0, c = 0, d = 0, e = 0;
+        cudaEventElapsedTime(&a, q->tr_ref, sl.tr_in0);
+        cudaEventElapsedTime(&b, q->tr_ref, sl.ev_in);
+        cudaEventElapsedTime(&c, q->tr_ref, sl.tr_c0);
+        cudaEventElapsedTime(&d, q->tr_ref, sl.tr_c1);
+        cudaEventElapsedTime(&e, q->tr_ref, sl.ev_done);
+        const double now = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - q->tr_host_ref).count();
+        std::fprintf(stderr, "[ikb queue] ticket %lld: submit %.3f | copy-in %.3f-%.3f | solve %.3f-%.3f | results on host %.3f | wait returns %.3f ms\n",
+                     (long long)ticket, sl.tr_submit_ms, a, b, c, d, e, now);
+    }
     sl.busy = false;
     return IKB_OK;
 }
