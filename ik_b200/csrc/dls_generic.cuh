@@ -212,11 +212,30 @@ __global__ void __launch_bounds__(128) dls_generic_kernel(const DevProblem<T> *_
     T J[M][NV], e[M], y[M], G[M * (M + 1) / 2], dq[NV];
 
     const int nq = P.nq, nv = P.nv, rows = P.rows;
-    long long b = (long long)atomicAdd(a.ticket, 1ULL);
-    bool have = b < a.B;
+    // Work fetch.  First launch: tickets are problem indices.  Second launch of a two-phase solve (a.resume): tickets
+    // index the list of problems the first one suspended after a.it_cap steps; they continue from their saved iterate.
+    // (Why two launches: a straggler alone in its warp touches one 4-byte word per 128-byte line of local memory, so
+    // its ~8 KB of scratch occupy a whole L1; compacted 32 to a warp the stragglers run from L1 -- DESIGN.md 4.2.)
+    long long b = 0;
+    bool have = false;
     int it = 0;
-    if (have)
-        for (int k = 0; k < nq; ++k) q[k] = a.q0[k * a.q0_es + b * a.q0_bs];
+    auto fetch = [&]() {
+        b = (long long)atomicAdd(a.ticket, 1ULL);
+        if (!a.resume) {
+            have = b < a.B;
+            it = 0;
+            if (have)
+                for (int k = 0; k < nq; ++k) q[k] = a.q0[k * a.q0_es + b * a.q0_bs];
+        } else {
+            have = b < (long long)*a.list_count;
+            if (have) {
+                b = a.list[b];
+                it = a.iters_ws[b];
+                for (int k = 0; k < nq; ++k) q[k] = a.q[k * a.q_es + b * a.q_bs];
+            }
+        }
+    };
+    fetch();
 
     while (__any_sync(0xffffffffu, have)) {
         if (have) {
@@ -584,11 +603,13 @@ __global__ void __launch_bounds__(128) dls_generic_kernel(const DevProblem<T> *_
                 if (a.success) a.success[b] = converged ? 1 : 0;
                 if (a.iters) a.iters[b] = it;
                 if (a.resid) a.resid[b] = res;
-                b = (long long)atomicAdd(a.ticket, 1ULL);
-                have = b < a.B;
-                it = 0;
-                if (have)
-                    for (int k = 0; k < nq; ++k) q[k] = a.q0[k * a.q0_es + b * a.q0_bs];
+                fetch();
+            } else if (it >= a.it_cap) {
+                // straggler: park it for the second launch
+                for (int k = 0; k < nq; ++k) a.q[k * a.q_es + b * a.q_bs] = q[k];
+                a.iters_ws[b] = it;
+                a.list[atomicAdd(a.list_count, 1ULL)] = (unsigned int)b;
+                fetch();
             }
         }
     }

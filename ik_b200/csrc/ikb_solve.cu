@@ -68,6 +68,29 @@ bool two_phase(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, int *
     return p->spec && B > 2LL * 32 * p->sm_count && cap > 0 && prm->max_iterations > cap;
 }
 
+// Scratch of a two-launch solve (suspended-problem list, step counts): slot `slot` of the problem's ring, grown to B
+// entries; stream `s` waits for the slot's previous user.
+static int acquire_scratch(const ikb_problem *p, unsigned slot, int64_t B, cudaStream_t s, SolveScratch **out) {
+    ikb_problem *mp = const_cast<ikb_problem *>(p);
+    std::lock_guard<std::mutex> lk(mp->scratch_mu);
+    if (mp->scratch[0].cap < (size_t)B) {
+        // grow every slot at once (one synchronisation, on the first large batch only)
+        IKB_CUDA(cudaDeviceSynchronize());
+        for (auto &x : mp->scratch) {
+            if (x.list) cudaFree(x.list);
+            if (x.iters) cudaFree(x.iters);
+            x.list = nullptr; x.iters = nullptr; x.cap = 0;
+            IKB_CUDA(cudaMalloc(&x.list, (size_t)B * sizeof(unsigned int)));
+            IKB_CUDA(cudaMalloc(&x.iters, (size_t)B * sizeof(int)));
+            x.cap = (size_t)B;
+            if (!x.ev) IKB_CUDA(cudaEventCreateWithFlags(&x.ev, cudaEventDisableTiming));
+        }
+    }
+    *out = &mp->scratch[slot % kScratchSlots];
+    IKB_CUDA(cudaStreamWaitEvent(s, (*out)->ev, 0));  // the slot's previous user (any stream) must be done
+    return IKB_OK;
+}
+
 template <typename T>
 int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io, cudaStream_t s,
                  const ChunkPlan *plan, const Merged<T> *merged, const double *pik_lambda) {
@@ -130,26 +153,8 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
             rc = launch_specialized<T>(*p->spec, hc, a, SPEC_BULK, B, p->sm_count, s);
             if (rc == IKB_OK) g_launches.fetch_add(1);
         } else {
-            ikb_problem *mp = const_cast<ikb_problem *>(p);
             SolveScratch *sc;
-            {
-                std::lock_guard<std::mutex> lk(mp->scratch_mu);
-                if (mp->scratch[0].cap < (size_t)B) {
-                    // grow every slot at once (one synchronisation, on the first large batch only)
-                    IKB_CUDA(cudaDeviceSynchronize());
-                    for (auto &x : mp->scratch) {
-                        if (x.list) cudaFree(x.list);
-                        if (x.iters) cudaFree(x.iters);
-                        x.list = nullptr; x.iters = nullptr; x.cap = 0;
-                        IKB_CUDA(cudaMalloc(&x.list, (size_t)B * sizeof(unsigned int)));
-                        IKB_CUDA(cudaMalloc(&x.iters, (size_t)B * sizeof(int)));
-                        x.cap = (size_t)B;
-                        if (!x.ev) IKB_CUDA(cudaEventCreateWithFlags(&x.ev, cudaEventDisableTiming));
-                    }
-                }
-                sc = &mp->scratch[slot % kScratchSlots];
-                IKB_CUDA(cudaStreamWaitEvent(s, sc->ev, 0));  // the slot's previous user (any stream) must be done
-            }
+            if ((rc = acquire_scratch(p, slot, B, s, &sc))) return rc;
             IKB_CUDA(cudaMemsetAsync(a.ticket, 0, 3 * sizeof(unsigned long long), s));  // bulk ticket, tail ticket, list count
             a.it_cap = cap;
             a.list = sc->list;
@@ -191,13 +196,44 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
     }
     if (merged) return fail(IKB_ERR_INVALID_ARG, "internal: merged launch on the table-driven kernel");
     auto fn = pik_lambda ? KernelTable<T>::pik(p->size_class) : KernelTable<T>::dls(p->size_class);
-    const int threads = 128;
+    const char *thr_env = std::getenv("IKB_GENERIC_THREADS"), *bps_env = std::getenv("IKB_GENERIC_BLOCKS_PER_SM");
+    const int threads = thr_env ? std::max(32, std::min(128, std::atoi(thr_env) / 32 * 32)) : 128;
     const size_t smem = sizeof(DevProblem<T>) + 16;
     int per_sm = 0;
     IKB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
     if (per_sm < 1) per_sm = 1;
+    if (bps_env && std::atoi(bps_env) > 0) per_sm = std::min(per_sm, std::atoi(bps_env));
     long long blocks = (B + threads - 1) / threads;
     blocks = std::min<long long>(blocks, (long long)per_sm * p->sm_count);
+    // Two launches for a batch that more than fills the GPU: problems unfinished after `cap` steps are
+    // parked and a second launch continues them, 32 to a warp and one warp per CTA, so that a straggler's local-memory
+    // scratch shares its cache lines with 31 others and stays in L1 instead of thrashing it from a mostly idle warp.
+    const char *cap_env = std::getenv("IKB_GENERIC_CAP");
+    const int cap = cap_env ? std::atoi(cap_env) : 16;
+    if (cap > 0 && prm->max_iterations > cap && B > 2048) {
+        SolveScratch *sc;
+        int rc;
+        if ((rc = acquire_scratch(p, slot, B, s, &sc))) return rc;
+        IKB_CUDA(cudaMemsetAsync(a.ticket, 0, 3 * sizeof(unsigned long long), s));  // first ticket, second ticket, list count
+        a.it_cap = cap;
+        a.list = sc->list;
+        a.list_count = a.ticket + 2;
+        a.iters_ws = io->iters ? io->iters : sc->iters;
+        fn<<<(unsigned)blocks, threads, smem, s>>>(dev_blob<T>(p), a);
+        IKB_CUDA(cudaGetLastError());
+        SolveArgs<T> t = a;
+        t.resume = 1;
+        t.it_cap = INT_MAX;
+        t.ticket = a.ticket + 1;
+        int per_sm1 = 0;
+        IKB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, fn, 32, smem));
+        const long long blocks1 = std::min<long long>((B + 31) / 32, (long long)std::max(per_sm1, 1) * p->sm_count);
+        fn<<<(unsigned)blocks1, 32, smem, s>>>(dev_blob<T>(p), t);
+        IKB_CUDA(cudaGetLastError());
+        IKB_CUDA(cudaEventRecord(sc->ev, s));
+        g_launches.fetch_add(2);
+        return IKB_OK;
+    }
     fn<<<(unsigned)blocks, threads, smem, s>>>(dev_blob<T>(p), a);
     IKB_CUDA(cudaGetLastError());
     g_launches.fetch_add(1);

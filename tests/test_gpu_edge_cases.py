@@ -138,3 +138,49 @@ def test_tight_iteration_budgets(cassie):
         q, ok, it, _ = _gpu(pb, q0, tg, ik.dls_parameters(max_iterations=mi))
         assert np.array_equal(ok, ok_ref.astype(bool)) and np.array_equal(it, it_ref)
         assert np.abs(q - q_ref).max() < 1e-6
+
+
+def test_table_driven_kernel_two_launch_schedule(monkeypatch):
+    """Above 2 048 problems the table-driven kernel parks problems unfinished after 16 steps and continues them in a
+    second launch.  Same answers as the single launch (bit for bit) and as the oracle -- with the caller's
+    `iters` buffer and without it (internal scratch), for ik::dls and ik::pik."""
+    torch = _torch()
+    m = W.cassie_model()
+    pb = ik.InverseKinematicsProblem(m, 1)
+    pb.add_frame_task("pelvis", ik.FrameTask(m, "pelvis", ik.KinematicType.Full))
+    pb.add_frame_task("fl", ik.FrameTask(m, "LeftFootFront", ik.KinematicType.Position))
+    pb.add_frame_task("fr", ik.FrameTask(m, "RightFootFront", ik.KinematicType.Orientation), 1)
+    assert pb.specialisation() is None
+    pb.finalize(0)
+    om = oracle_model("cassie")
+    opb = oracle_problem_like(pb, om)
+    B = 3000
+    q0, tg, _ = make_workload(pb, om, B, seed=4242, standing=W.CASSIE_STANDING)
+    dq0, dtg = torch.tensor(q0.T.copy(), device="cuda:0"), torch.tensor(tg.T.copy(), device="cuda:0")
+    monkeypatch.setenv("IKB_GENERIC_CAP", "0")
+    one = ik.dls_batch(pb, dq0, dtg)
+    one_p = ik.pik_batch(pb, dq0, dtg, ik.pik_parameters(lambdas=[1e-2, 1e-1]))
+    torch.cuda.synchronize()
+    launches = ik.kernel_launch_count()
+    monkeypatch.delenv("IKB_GENERIC_CAP")
+    two = ik.dls_batch(pb, dq0, dtg)
+    torch.cuda.synchronize()
+    assert ik.kernel_launch_count() - launches == 2
+    two_p = ik.pik_batch(pb, dq0, dtg, ik.pik_parameters(lambdas=[1e-2, 1e-1]))
+    torch.cuda.synchronize()
+    for a, b in ((one, two), (one_p, two_p)):
+        for k in ("q", "success", "iters", "resid"):
+            assert torch.equal(a[k], b[k]), k
+    assert (one["iters"] > 16).sum().item() > 0  # some problems did change launches
+    # optional outputs absent: the step counts of parked problems live in internal scratch
+    dq = torch.empty_like(dq0)
+    io = capi.BatchIO(dq0.data_ptr(), B, 1, dtg.data_ptr(), B, 1, dq.data_ptr(), B, 1, None, None, None)
+    prm = ik.dls_parameters().c()
+    capi.check(capi.lib.ikb_dls_solve_batch(pb._h, capi.F64, C.byref(prm), B, C.byref(io), None), "solve")
+    torch.cuda.synchronize()
+    assert torch.equal(dq, one["q"])
+    q_ref, ok_ref, it_ref, _ = O.dls_batch(opb, q0, tg, nthreads=NT)
+    assert np.array_equal(two["success"].cpu().numpy().astype(bool), ok_ref.astype(bool))
+    assert np.array_equal(two["iters"].cpu().numpy(), it_ref)
+    err = np.abs(two["q"].cpu().numpy().T - q_ref).max(axis=1)
+    assert err[ok_ref.astype(bool)].max() < 1e-6 and np.percentile(err, 99) < 1e-6
