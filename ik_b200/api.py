@@ -606,21 +606,25 @@ class SolveQueue:
         nq, tsz = problem.model().nq, problem.target_size
         assert q0.dtype == npdt and targets.dtype == npdt and q0.flags.c_contiguous and targets.flags.c_contiguous
         if layout == "soa":
-            B = q0.shape[1]
-            assert q0.shape == (nq, B) and targets.shape == (tsz, B)
+            B = targets.shape[1]
+            assert targets.shape == (tsz, B)
             strides = lambda k: (B, 1)
             qshape = (nq, B)
         else:
-            B = q0.shape[0]
-            assert q0.shape == (B, nq) and targets.shape == (B, tsz)
+            B = targets.shape[0]
+            assert targets.shape == (B, tsz)
             strides = lambda k: (1, k)
             qshape = (B, nq)
+        # q0 of shape (nq,): ONE initial guess for the whole batch (batch_stride = 0, include/ikb200.h) -- nq values cross
+        # the host link instead of B * nq
+        q0_strides = (1, 0) if q0.ndim == 1 else strides(nq)
+        assert q0.shape == ((nq,) if q0.ndim == 1 else qshape)
         out = out or {}
         q = out.get("q") if out.get("q") is not None else np.empty(qshape, dtype=npdt)
         success = out.get("success") if out.get("success") is not None else np.empty(B, dtype=np.uint8)
         iters = out.get("iters") if out.get("iters") is not None else np.empty(B, dtype=np.int32)
         resid = out.get("resid") if out.get("resid") is not None else np.empty(B, dtype=npdt)
-        io = capi.BatchIO(q0.ctypes.data, *strides(nq), targets.ctypes.data, *strides(tsz), q.ctypes.data, *strides(nq),
+        io = capi.BatchIO(q0.ctypes.data, *q0_strides, targets.ctypes.data, *strides(tsz), q.ctypes.data, *strides(nq),
                           success.ctypes.data, iters.ctypes.data, resid.ctypes.data)
         prm = p.c()
         t = capi.check_index(capi.lib.ikb_queue_submit_host(self._h, code, C.byref(prm), B, C.byref(io)), "ikb_queue_submit_host")

@@ -110,6 +110,28 @@ def test_host_mode_and_parameter_change(cassie):
         assert np.array_equal(out["iters"], r["iters"]) and np.array_equal(out["resid"], r["resid"])
 
 
+def test_host_mode_broadcast_initial_guess(cassie):
+    """One initial guess for the whole batch (q0 of shape (nq,), batch_stride = 0): 23 values cross the host link
+    instead of B x 23; results equal those of the tiled q0, SoA and AoS, merged and alone."""
+    _torch()
+    pb, om, opb = cassie
+    pb.finalize(0)
+    B = 10000
+    q0, tg, _ = make_workload(pb, om, B, seed=301, standing=W.CASSIE_STANDING)
+    assert (q0 == q0[0]).all()
+    ref = ik.dls_batch_host(pb, q0, tg, None, "f64", "aos")
+    queue = ik.SolveQueue(pb, depth=4, merge=2)
+    one = np.ascontiguousarray(q0[0])
+    jobs = [queue.submit_host(one, np.ascontiguousarray(tg.T), None, "f64", "soa"),
+            queue.submit_host(one, tg, None, "f64", "aos"),
+            queue.submit_host(one, tg, None, "f64", "aos")]
+    for k, (t, out) in enumerate(jobs):
+        queue.wait(t)
+        q = out["q"].T if k == 0 else out["q"]
+        assert np.array_equal(q, ref["q"]) and np.array_equal(out["success"], ref["success"])
+        assert np.array_equal(out["iters"], ref["iters"])
+
+
 def test_queue_with_generic_kernel_and_empty_batch():
     """A problem without a specialised kernel goes through the queue batch by batch (no merged launch); B = 0 is legal."""
     torch = _torch()
