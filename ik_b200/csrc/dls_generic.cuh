@@ -415,11 +415,15 @@ __global__ void __launch_bounds__(128) dls_generic_kernel(const DevProblem<T> *_
                 //      step is one LDL^T solve; pinv(Jb) Jb (Eigen COD, pik.cpp:59-61) is the projector onto the row space
                 //      of the numerically rank-r part of Jb: Householder QR with column pivoting, rank from Eigen's
                 //      threshold eps * min(m, n) * max pivot, rows orthonormalised (modified Gram-Schmidt, twice). ----
-                T Pm[NV][NV];
-                for (int i = 0; i < nv; ++i) {
-                    for (int j = 0; j < nv; ++j) Pm[i][j] = (i == j) ? T(1) : T(0);
-                    dq[i] = T(0);
-                }
+                // The projector is kept factored, P = I - sum_k w_k w_k^T, with the orthonormal row-space bases w of the
+                // levels done so far (each level's Jb = J_i P lies in range(P), so its basis is orthogonal to the earlier
+                // ones): Jb = J_i - (J_i W^T) W costs rows x basis x nv instead of rows x nv x nv, the first level (P = I) is
+                // free, the last level's update is never read, and the nv x nv matrix leaves the per-thread scratch.
+                T Wall[M][NV];
+                int nb = 0, last_lvl = 0;
+                for (int i = 0; i < nv; ++i) dq[i] = T(0);
+                for (int lvl = 0; lvl < P.nlevels; ++lvl)
+                    if (P.level_rows[lvl] > 0) last_lvl = lvl;
                 int row0 = 0;
                 for (int lvl = 0; lvl < P.nlevels; ++lvl) {
                     const int mi = P.level_rows[lvl];
@@ -427,12 +431,16 @@ __global__ void __launch_bounds__(128) dls_generic_kernel(const DevProblem<T> *_
                     T Jb[M][NV];
                     for (int r = 0; r < mi; ++r) {
                         T s = T(0);
-                        for (int c = 0; c < nv; ++c) s += J[row0 + r][c] * dq[c];
-                        y[r] = e[row0 + r] - s;                                  // de_bar (pik.cpp:49)
                         for (int c = 0; c < nv; ++c) {
+                            const T jrc = J[row0 + r][c];
+                            s += jrc * dq[c];
+                            Jb[r][c] = jrc;
+                        }
+                        y[r] = e[row0 + r] - s;                                  // de_bar (pik.cpp:49)
+                        for (int k = 0; k < nb; ++k) {                           // Jbar = J_i P (pik.cpp:51)
                             T t = T(0);
-                            for (int k = 0; k < nv; ++k) t += J[row0 + r][k] * Pm[k][c];
-                            Jb[r][c] = t;                                        // Jbar = J_i P (pik.cpp:51)
+                            for (int c = 0; c < nv; ++c) t += J[row0 + r][c] * Wall[k][c];
+                            for (int c = 0; c < nv; ++c) Jb[r][c] -= t * Wall[k][c];
                         }
                     }
                     // (Jb Jb^T + lambda^2 I) z = de, LDL^T, packed lower triangle
@@ -472,14 +480,8 @@ __global__ void __launch_bounds__(128) dls_generic_kernel(const DevProblem<T> *_
                         for (int i = 0; i < mi; ++i) s += Jb[i][c] * y[i];
                         dq[c] -= s;
                     }
-                    // projector update (pik.cpp:58-61)
-                    T Wm[M][NV];
-                    const int rank = rowspace_basis<T, NV, M>(Jb, mi, nv, Wm, y);
-                    for (int r = 0; r < rank; ++r)
-                        for (int i = 0; i < nv; ++i) {
-                            const T wi = Wm[r][i];
-                            for (int j = 0; j < nv; ++j) Pm[i][j] -= wi * Wm[r][j];
-                        }
+                    // projector update (pik.cpp:58-61): append this level's row-space basis
+                    if (lvl != last_lvl) nb += rowspace_basis<T, NV, M>(Jb, mi, nv, Wall + nb, y);
                     row0 += mi;
                 }
                 // dq += P da with da = 0 (pik.cpp:65, pik.hpp:39)
