@@ -68,7 +68,7 @@ class Model:
                                             _dptr(self.framePlacements)), "ikb_model_get_frames")
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and capi is not None and getattr(capi, "lib", None) is not None:  # (None at interpreter exit)
             capi.lib.ikb_model_free(self._h)
             self._h = None
 
@@ -248,7 +248,7 @@ class InverseKinematicsProblem:  # problem.hpp:9-206
         self._device = None
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and capi is not None and getattr(capi, "lib", None) is not None:
             capi.lib.ikb_problem_free(self._h)
             self._h = None
 

@@ -40,6 +40,11 @@ template <typename T> struct alignas(16) DevProblem {
     int32_t nlevels;           // priority levels (max_priority_level + 1)
     int32_t level_rows[7];     // rows of priority level l (stacked order = level by level); ik::pik walks them
     int32_t pad_[4];           // keeps sizeof a multiple of 16 for the bulk copy
+    // Sparsity of the stacked task Jacobian, known when the problem is finalized (a frame task only touches the columns of
+    // the joints between the root and its frame; SURVEY 8a: the reference's dense products ignore 60 % zeros): bit c of
+    // row_cols[r] = column c of row r may be non-zero, bit r of col_rows[c] likewise (supersets; nv, rows <= 64).
+    uint64_t row_cols[kMaxRows];
+    uint64_t col_rows[kMaxNq];
 };
 
 constexpr int kMaxSegments = 8;

@@ -404,8 +404,10 @@ __global__ void __launch_bounds__(128) dls_generic_kernel(const DevProblem<T> *_
                 // weighting (data.cpp:49-50)
                 for (int i = 0; i < dim; ++i) {
                     const T wgt = P.weight[row + i];
-                    e[row + i] *= wgt;
-                    for (int c = 0; c < nv; ++c) J[row + i][c] *= wgt;
+                    if (wgt != T(1)) {  // Task::weighting() defaults to ones (task.hpp:48-51)
+                        e[row + i] *= wgt;
+                        for (int c = 0; c < nv; ++c) J[row + i][c] *= wgt;
+                    }
                 }
             }
             if constexpr (PIK) {
@@ -486,31 +488,45 @@ __global__ void __launch_bounds__(128) dls_generic_kernel(const DevProblem<T> *_
                 }
                 // dq += P da with da = 0 (pik.cpp:65, pik.hpp:39)
             } else {
-                // ---- Gram matrix + damping (dls.cpp:39-41), packed lower triangle ----
-                for (int i = 0; i < rows; ++i)
+                // ---- Gram matrix + damping (dls.cpp:39-41), packed lower triangle.  Only the columns both rows can touch
+                //      (the bounding range of P.row_cols[i] & P.row_cols[j], known at finalize) enter a dot product, in
+                //      ascending order -- the skipped terms are exact zeros, so the sums equal the dense ones. ----
+                for (int i = 0; i < rows; ++i) {
+                    T *Gi = G + i * (i + 1) / 2;
+                    const uint64_t mi = P.row_cols[i];
                     for (int j = 0; j <= i; ++j) {
                         T s = T(0);
-                        for (int c = 0; c < nv; ++c) s += J[i][c] * J[j][c];
-                        G[i * (i + 1) / 2 + j] = s + (i == j ? a.damping2 : T(0));
+                        const uint64_t mm = mi & P.row_cols[j];
+                        if (mm) {  // the bounding range of the common columns: a plain loop the compiler can pipeline
+                            const int c1 = 64 - __clzll((long long)mm);
+                            for (int c = __ffsll((long long)mm) - 1; c < c1; ++c) s += J[i][c] * J[j][c];
+                        }
+                        Gi[j] = s + (i == j ? a.damping2 : T(0));
                     }
-                // ---- LDL^T (G is SPD thanks to the damping, so no pivoting is needed; SURVEY 8a notes) ----
+                }
+                // ---- LDL^T (G is SPD thanks to the damping, so no pivoting is needed; SURVEY 8a notes); column j:
+                //      v_k = L_jk D_k once, then one FMA per term ----
                 for (int j = 0; j < rows; ++j) {
-                    T d = G[j * (j + 1) / 2 + j];
+                    T *Gj = G + j * (j + 1) / 2;
+                    T d = Gj[j];
                     for (int k = 0; k < j; ++k) {
-                        const T l = G[j * (j + 1) / 2 + k];
-                        d -= l * l * G[k * (k + 1) / 2 + k];
+                        const T v = Gj[k] * G[k * (k + 1) / 2 + k];
+                        y[k] = v;
+                        d -= Gj[k] * v;
                     }
-                    G[j * (j + 1) / 2 + j] = d;
+                    Gj[j] = d;
                     const T inv = rcp_(d);
                     for (int i = j + 1; i < rows; ++i) {
-                        T s = G[i * (i + 1) / 2 + j];
-                        for (int k = 0; k < j; ++k) s -= G[i * (i + 1) / 2 + k] * G[j * (j + 1) / 2 + k] * G[k * (k + 1) / 2 + k];
-                        G[i * (i + 1) / 2 + j] = s * inv;
+                        T *Gi = G + i * (i + 1) / 2;
+                        T s = Gi[j];
+                        for (int k = 0; k < j; ++k) s -= Gi[k] * y[k];
+                        Gi[j] = s * inv;
                     }
                 }
                 for (int i = 0; i < rows; ++i) {
+                    const T *Gi = G + i * (i + 1) / 2;
                     T s = e[i];
-                    for (int k = 0; k < i; ++k) s -= G[i * (i + 1) / 2 + k] * y[k];
+                    for (int k = 0; k < i; ++k) s -= Gi[k] * y[k];
                     y[i] = s;
                 }
                 for (int i = 0; i < rows; ++i) y[i] *= rcp_(G[i * (i + 1) / 2 + i]);
@@ -519,10 +535,14 @@ __global__ void __launch_bounds__(128) dls_generic_kernel(const DevProblem<T> *_
                     for (int k = i + 1; k < rows; ++k) s -= G[k * (k + 1) / 2 + i] * y[k];
                     y[i] = s;
                 }
-                // ---- dq = -J^T y (dls.cpp:52) and the stop test on priority 0 (visitor.hpp:19) ----
+                // ---- dq = -J^T y (dls.cpp:52), rows that can touch column c only ----
                 for (int c = 0; c < nv; ++c) {
                     T s = T(0);
-                    for (int i = 0; i < rows; ++i) s += J[i][c] * y[i];
+                    const uint64_t mm = P.col_rows[c];
+                    if (mm) {
+                        const int i1 = 64 - __clzll((long long)mm);
+                        for (int i = __ffsll((long long)mm) - 1; i < i1; ++i) s += J[i][c] * y[i];
+                    }
                     dq[c] = -s;
                 }
                 // ---- FrameConstraints (dls.cpp:26-34,44-52): dq <- (I - Jc^+ Jc) dq ----

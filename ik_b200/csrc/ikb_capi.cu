@@ -96,9 +96,26 @@ void fill_dev_problem(const HostProblem &hp, const std::vector<int> &order, cons
     auto local_frame = [&](int fid) {
         return (int)(std::find(used_frames.begin(), used_frames.end(), fid) - used_frames.begin());
     };
+    for (auto &x : P.row_cols) x = 0;
+    for (auto &x : P.col_rows) x = 0;
     int row = 0, moff = 0;
     for (size_t s = 0; s < order.size(); ++s) {
         const HostTask &t = hp.tasks[order[s]];
+        // columns this task's Jacobian rows can touch
+        uint64_t cols = 0;
+        if (t.kind == IKB_TASK_POSTURE) {
+            for (int i = 0; i < t.type; ++i) cols |= 1ULL << (m.nv - t.type + i);
+        } else if (t.kind == IKB_TASK_COM) {
+            cols = m.nv >= 64 ? ~0ULL : ((1ULL << m.nv) - 1);
+        } else {
+            for (int j = m.frame_parent[t.frame]; j > 0; j = m.parent[j])
+                for (int k = 0; k < HostModel::joint_nv(m.jtype[j]); ++k) cols |= 1ULL << (m.idx_v[j] + k);
+        }
+        for (int i = 0; i < t.dim; ++i) {
+            P.row_cols[row + i] = cols;
+            for (int c = 0; c < m.nv; ++c)
+                if (cols >> c & 1) P.col_rows[c] |= 1ULL << (row + i);
+        }
         P.t_kind[s] = t.kind;
         P.t_frame[s] = (t.kind == IKB_TASK_POSTURE || t.kind == IKB_TASK_COM) ? 0 : local_frame(t.frame);
         P.t_ref[s] = t.kind == IKB_TASK_POSTURE ? 0 : local_frame(t.ref);

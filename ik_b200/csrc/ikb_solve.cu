@@ -209,7 +209,7 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
     // parked and a second launch continues them, 32 to a warp and one warp per CTA, so that a straggler's local-memory
     // scratch shares its cache lines with 31 others and stays in L1 instead of thrashing it from a mostly idle warp.
     const char *cap_env = std::getenv("IKB_GENERIC_CAP");
-    const int cap = cap_env ? std::atoi(cap_env) : 16;
+    const int cap = cap_env ? std::atoi(cap_env) : 32;  // measured: profiles/r1_generic_two_launch.txt (16 suits quick problems, 32 never loses to one launch)
     if (cap > 0 && prm->max_iterations > cap && B > 2048) {
         SolveScratch *sc;
         int rc;

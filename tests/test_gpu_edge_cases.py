@@ -141,7 +141,7 @@ def test_tight_iteration_budgets(cassie):
 
 
 def test_table_driven_kernel_two_launch_schedule(monkeypatch):
-    """Above 2 048 problems the table-driven kernel parks problems unfinished after 16 steps and continues them in a
+    """Above 2 048 problems the table-driven kernel parks problems unfinished after 32 steps and continues them in a
     second launch.  Same answers as the single launch (bit for bit) and as the oracle -- with the caller's
     `iters` buffer and without it (internal scratch), for ik::dls and ik::pik."""
     torch = _torch()
@@ -171,7 +171,7 @@ def test_table_driven_kernel_two_launch_schedule(monkeypatch):
     for a, b in ((one, two), (one_p, two_p)):
         for k in ("q", "success", "iters", "resid"):
             assert torch.equal(a[k], b[k]), k
-    assert (one["iters"] > 16).sum().item() > 0  # some problems did change launches
+    assert (one["iters"] > 32).sum().item() > 0  # some problems did change launches
     # optional outputs absent: the step counts of parked problems live in internal scratch
     dq = torch.empty_like(dq0)
     io = capi.BatchIO(dq0.data_ptr(), B, 1, dtg.data_ptr(), B, 1, dq.data_ptr(), B, 1, None, None, None)

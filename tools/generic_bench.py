@@ -9,6 +9,7 @@ import ik_b200 as ik
 from ik_b200 import workloads as W
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+CAPS = sys.argv[2].split(",") if len(sys.argv) > 2 else ["0", "16"]
 dev = torch.device("cuda:0")
 m = W.cassie_model()
 
@@ -25,7 +26,7 @@ def run(name, pb, solve, tg):
     q0 = torch.tensor(np.tile(W.standing_configuration(m, W.CASSIE_STANDING), (B, 1)).T.copy(), device=dev)
     tg = torch.tensor(tg.T.copy(), device=dev)
     res = {}
-    for cap in ("0", "16"):
+    for cap in CAPS:
         os.environ["IKB_GENERIC_CAP"] = cap
         out = solve(pb, q0, tg)
         torch.cuda.synchronize()
@@ -38,7 +39,7 @@ def run(name, pb, solve, tg):
         print("%-28s cap %2s  %8.2f ms  %6.2f M solves/s  converged %.4f  mean iters %.2f" % (
             name, cap, dt * 1e3, out["success"].sum().item() / dt / 1e6, out["success"].float().mean().item(),
             out["iters"].float().mean().item()), flush=True)
-    same = all(torch.equal(res["0"][k], res["16"][k]) for k in ("q", "success", "iters"))
+    same = all(torch.equal(res[CAPS[0]][k], res[c][k]) for k in ("q", "success", "iters") for c in CAPS[1:])
     print("%-28s two-launch results identical to single launch: %s" % (name, same), flush=True)
 
 
