@@ -783,6 +783,7 @@ class Generator:
             col_rows[c].sort()
         codes = [[] for _ in range(R)]
         nfma = [0] * R
+        rolled = int(self.spec.get("rolled_update", 0))  # 0 = unrolled; n = `#pragma unroll n` on the loop over factor columns
         for role in range(R):
             L = codes[role]
             if role == solver:
@@ -825,7 +826,28 @@ class Generator:
                         nfma[role] += 1
                     L.append(ind + "}")
                 # left-looking update from factor columns k < j0
-                if rows or has_e:
+                if (rows or has_e) and rolled and j0 > 0:
+                    # ONE loop body for all factor columns k < j0 (run-time k: the strip addresses advance by a stride, the
+                    # accumulators keep their registers); same operations in the same order as the unrolled form below, so
+                    # the results are bit-identical -- only the code is j0 times smaller.  yp[k] comes from the strip (the
+                    # solver role publishes it there in phase 2), because a register array cannot take a run-time index.
+                    L.append(ind + "#pragma unroll %d" % rolled)
+                    L.append(ind + "for (int k = 0; k < %d; ++k) {  // minus column k of the factor" % j0)
+                    L.append(ind + "    const S sK{sL.base + k * S::kStride};")
+                    L.append(ind + "    const T dk = sK.get(%d);" % nstrict)
+                    for i in sorted(set(rows) | set(blk)):
+                        L.append(ind + "    const T l%d = sK.get(%d);" % (i, Lidx(i, 0)))
+                    for j in blk:
+                        L.append(ind + "    const T v%d = l%d * dk;" % (j, j))
+                    for (i, j) in pairs:
+                        L.append(ind + "    g_%d_%d -= l%d * v%d;" % (i, j, i, j))
+                        nfma[role] += j0
+                    if has_e:
+                        L.append(ind + "    const T ypk = sK.get(%d);" % (nstrict + M))
+                        for j in blk:
+                            L.append(ind + "    g_e_%d -= ypk * v%d;" % (j, j))
+                    L.append(ind + "}")
+                elif rows or has_e:
                     for k in range(j0):
                         L.append(ind + "{  // minus column %d of the factor" % k)
                         L.append(ind + "    const T dk = sL.get(%d);" % (nstrict + k))
@@ -869,6 +891,8 @@ class Generator:
                                 nfma[role] += 1
                         if has_e:
                             L.append(ind + "    yp[%d] = g_e_%d * pinv%d;" % (j, j, j))
+                            if rolled:
+                                L.append(ind + "    sL.set(%d, yp[%d]);" % (nstrict + M + j, j))
                             for j2 in range(j + 1, j1):
                                 L.append(ind + "    g_e_%d -= yp[%d] * pv_%d_%d;" % (j2, j, j2, j))
                     L.append(ind + "}")
@@ -970,6 +994,8 @@ class Generator:
         solve = self.gen_solve(int(self.spec.get("block_width", 4)), P)
         used = self.signature()
         nfact = max(rows * (rows + 1) // 2, rows + self.nq)  # the factor strip also carries e (M) and the stepped q (NQ)
+        if self.spec.get("rolled_update") and self.spec.get("parallel_solve") and len(groups) > 1:
+            nfact += rows                                     # ... and yp for the rolled left-looking loops (gen_solve_parallel)
         out = []
         out.append("// GENERATED by tools/gen_kernel.py -- do not edit.  Specialisation: %s" % display_name)
         out.append("// rows=%d nv=%d nq=%d non-zero Jacobian entries=%d solve FMAs=%d warp roles=%d" %
