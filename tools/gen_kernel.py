@@ -908,6 +908,169 @@ class Generator:
         self.psolve_fma = nfma
         return codes
 
+    def gen_solve_uniform(self, R, solver):
+        """The distributed factorisation with ONE body for all R warp roles (spec "uniform_solve").
+
+        The fetch of the role-specific bodies of gen_solve_parallel is what bounds the humanoid kernel (ncu: no_instruction
+        is the top stall): here every role runs the SAME instructions on rows picked by its run-time role index r, so the
+        warps of a group -- kept in step by the barriers -- share every fetched line.
+          phase 0  (role-specific, small) Gram: role r accumulates the task blocks {r,r}, {r,r+1}, {r,r+2} (indices mod R; the
+                   R(R-1)/2 off-diagonal blocks are exactly the pairs at cyclic distance 1 and 2 for R = 5) of
+                   G = J J^T + damping^2 I into the factor strip: strictly-lower entries in place, the diagonal in its own
+                   M slots (DI), e in the right-hand-side slots (RHS; Spec::EOFF points there)            -> sync
+          block column kb = 0..M/R-1 (width R, columns j0..j0+R-1), every role:
+                   rows r+R*m, m > kb, are its own; the R x R diagonal block is computed redundantly by everybody (same
+                   instructions on the same values: identical bits), so there is no publish/consume barrier inside a
+                   block column.  Left-looking loop over the finished factor columns k < j0 (run-time k), the diagonal block
+                   factorised in registers, own rows eliminated against it and stored; the solver role also carries the
+                   rhs row, the pivots d and -- AFTER the barrier, because everybody reads the block's Gram entries from
+                   those very slots -- the L entries inside the diagonal block                                -> sync
+        One barrier per block column (M/R + 1 in all) instead of two per 2 columns.  Back substitution: solver role."""
+        M = self.rows
+        if M % R or len(self.tasks) != R or any(t["dim"] != M // R for t in self.tasks):
+            raise ValueError("uniform_solve needs R tasks of M/R rows each")
+        ind = "        "
+        nstrict = M * (M - 1) // 2
+        DF, RHS, DI = nstrict, nstrict + M, nstrict + 2 * M
+        NB, W = M // R, R
+        TD = M // R  # rows per task
+
+        def Lidx(i, k):
+            return i * (i - 1) // 2 + k
+
+        row_cols = {}
+        for (r, c) in self.slots:
+            row_cols.setdefault(r, set()).add(c)
+        # ---- phase 0: Gram, per role ----
+        grams = []
+        nf_gram = [0] * R
+        for role in range(R):
+            L = []
+            blocks = [(role, role)]
+            for d in (1, 2):
+                o = (role + d) % R
+                if o != role and (max(role, o), min(role, o)) not in blocks:
+                    blocks.append((max(role, o), min(role, o)))
+            if R != 5:
+                raise ValueError("uniform_solve: the Gram block assignment is written for 5 roles")
+            for (ta, tb) in blocks:
+                ra = list(range(self.tasks[ta]["row"], self.tasks[ta]["row"] + TD))
+                rb = list(range(self.tasks[tb]["row"], self.tasks[tb]["row"] + TD))
+                pairs = [(i, j) for i in ra for j in rb if i >= j]
+                L.append(ind + "{  // Gram block (task %d, task %d)" % (ta, tb))
+                for (i, j) in pairs:
+                    L.append(ind + "    T g_%d_%d = %s;" % (i, j, "damping2" if i == j else "T(0)"))
+                cols = sorted(set().union(*[row_cols.get(i, set()) for i in ra]) & set().union(*[row_cols.get(j, set()) for j in rb]))
+                for c in cols:
+                    use = [(i, j) for (i, j) in pairs if c in row_cols.get(i, ()) and c in row_cols.get(j, ())]
+                    if not use:
+                        continue
+                    need = sorted(set([i for i, _ in use] + [j for _, j in use]))
+                    L.append(ind + "    {  // J column %d" % c)
+                    for i in need:
+                        L.append(ind + "        const T a%d = sJ.get(%d);" % (i, self.slots[(i, c)]))
+                    for (i, j) in use:
+                        L.append(ind + "        g_%d_%d += a%d * a%d;" % (i, j, i, j))
+                        nf_gram[role] += 1
+                    L.append(ind + "    }")
+                for (i, j) in pairs:
+                    L.append(ind + "    sL.set(%d, g_%d_%d);" % (DI + i if i == j else Lidx(i, j), i, j))
+                L.append(ind + "}")
+            grams.append(L)
+        # ---- block columns: one body, run-time role r ----
+        L = []
+        nf = 0
+        L.append(ind + "const int r = role;")
+        for m in range(1, NB):
+            L.append(ind + "const S sO%d{sL.base + ((r + %d) * (r + %d) / 2) * S::kStride};  // own row r + %d: L[r + %d][.]" %
+                     (m, R * m, R * m - 1, R * m, R * m))
+        for kb in range(NB):
+            j0 = kb * W
+            own = list(range(kb + 1, NB))
+            tri = [(a, b) for b in range(W) for a in range(b, W)]
+            L.append(ind + "// ---- block column %d..%d ----" % (j0, j0 + W - 1))
+            L.append(ind + "IKB_PHASE_FENCE();")
+            for (a, b) in tri:
+                L.append(ind + "T d%d_%d_%d = sL.get(%d);" % (kb, a, b, DI + j0 + a if a == b else Lidx(j0 + a, j0 + b)))
+            for m in own:
+                for b in range(W):
+                    L.append(ind + "T o%d_%d_%d = sO%d.get(%d);" % (kb, m, b, m, j0 + b))
+            for b in range(W):
+                L.append(ind + "T e%d_%d = T(0);" % (kb, b))
+            L.append(ind + "if (r == %d) {" % solver)
+            for b in range(W):
+                L.append(ind + "    e%d_%d = sL.get(%d);" % (kb, b, RHS + j0 + b))
+            L.append(ind + "}")
+            if j0 > 0:
+                L.append(ind + "#pragma unroll %d" % int(self.spec.get("rolled_update", 2) or 2))
+                L.append(ind + "for (int k = 0; k < %d; ++k) {  // minus column k of the factor" % j0)
+                L.append(ind + "    const S sK{sL.base + k * S::kStride};")
+                L.append(ind + "    const T dk = sK.get(%d);" % DF)
+                for a in range(W):
+                    L.append(ind + "    const T l%d = sK.get(%d);" % (a, Lidx(j0 + a, 0)))
+                for b in range(W):
+                    L.append(ind + "    const T v%d = l%d * dk;" % (b, b))
+                for (a, b) in tri:
+                    L.append(ind + "    d%d_%d_%d -= l%d * v%d;" % (kb, a, b, a, b))
+                nf += j0 * len(tri)
+                for m in own:
+                    L.append(ind + "    const T lo%d = sO%d.get(k);" % (m, m))
+                    for b in range(W):
+                        L.append(ind + "    o%d_%d_%d -= lo%d * v%d;" % (kb, m, b, m, b))
+                    nf += j0 * W
+                L.append(ind + "    if (r == %d) {" % solver)
+                L.append(ind + "        const T le = sK.get(%d);" % RHS)
+                for b in range(W):
+                    L.append(ind + "        e%d_%d -= le * v%d;" % (kb, b, b))
+                L.append(ind + "    }")
+                L.append(ind + "}")
+            # the diagonal block, in registers (every role: identical bits)
+            for b in range(W):
+                L.append(ind + "const T inv%d_%d = rcp_(d%d_%d_%d);" % (kb, b, kb, b, b))
+                for a in range(b + 1, W):
+                    L.append(ind + "const T l%d_%d_%d = d%d_%d_%d * inv%d_%d;" % (kb, a, b, kb, a, b, kb, b))
+                for b2 in range(b + 1, W):
+                    for a in range(b2, W):
+                        L.append(ind + "d%d_%d_%d -= l%d_%d_%d * d%d_%d_%d;" % (kb, a, b2, kb, a, b, kb, b2, b))
+                        nf += 1
+            # own rows against the block
+            for m in own:
+                for b in range(W):
+                    L.append(ind + "{ const T lo = o%d_%d_%d * inv%d_%d; sO%d.set(%d, lo);" % (kb, m, b, kb, b, m, j0 + b))
+                    for b2 in range(b + 1, W):
+                        L.append(ind + "  o%d_%d_%d -= lo * d%d_%d_%d;" % (kb, m, b2, kb, b2, b))
+                        nf += 1
+                    L.append(ind + "}")
+            L.append(ind + "if (r == %d) {  // pivots and the rhs row (forward substitution rides along)" % solver)
+            for b in range(W):
+                L.append(ind + "    sL.set(%d, d%d_%d_%d);" % (DF + j0 + b, kb, b, b))
+            for b in range(W):
+                L.append(ind + "    { const T yb = e%d_%d * inv%d_%d; sL.set(%d, yb);" % (kb, b, kb, b, RHS + j0 + b))
+                for b2 in range(b + 1, W):
+                    L.append(ind + "      e%d_%d -= yb * d%d_%d_%d;" % (kb, b2, kb, b2, b))
+                L.append(ind + "    }")
+            L.append(ind + "}")
+            if kb < NB - 1:
+                L.append(ind + "sync();  // block column %d..%d of the factor complete; everybody has read the block's Gram entries" % (j0, j0 + W - 1))
+            L.append(ind + "if (r == %d) {" % solver)
+            for b in range(W):
+                for a in range(b + 1, W):
+                    L.append(ind + "    sL.set(%d, l%d_%d_%d);" % (Lidx(j0 + a, j0 + b), kb, a, b))
+            L.append(ind + "}")
+        L.append(ind + "if (r == %d) {  // ---- back substitution (solver role) ----" % solver)
+        L.append(ind + "    T yp[%d];" % M)
+        L.append(ind + "    #pragma unroll")
+        L.append(ind + "    for (int i = 0; i < %d; ++i) yp[i] = sL.get(%d + i);" % (M, RHS))
+        for k in range(M - 1, -1, -1):
+            for i in range(k):
+                L.append(ind + "    yp[%d] -= sL.get(%d) * yp[%d];" % (i, Lidx(k, i), k))
+                nf += 1
+        L.append(ind + "    #pragma unroll")
+        L.append(ind + "    for (int i = 0; i < %d; ++i) y[i] = yp[i];" % M)
+        L.append(ind + "}")
+        self.usolve_fma = (nf_gram, nf)
+        return grams, L
+
     def gen_dq(self):
         L = []
         ind = "        "
@@ -994,7 +1157,11 @@ class Generator:
         solve = self.gen_solve(int(self.spec.get("block_width", 4)), P)
         used = self.signature()
         nfact = max(rows * (rows + 1) // 2, rows + self.nq)  # the factor strip also carries e (M) and the stepped q (NQ)
-        if self.spec.get("rolled_update") and self.spec.get("parallel_solve") and len(groups) > 1:
+        uniform = bool(self.spec.get("uniform_solve")) and bool(self.spec.get("parallel_solve")) and len(groups) > 1
+        if uniform:
+            nfact = nstrict + 3 * rows                        # L | d | rhs (e, then yp) | Gram diagonal (gen_solve_uniform)
+            self.eoff = nstrict + rows
+        elif self.spec.get("rolled_update") and self.spec.get("parallel_solve") and len(groups) > 1:
             nfact += rows                                     # ... and yp for the rolled left-looking loops (gen_solve_parallel)
         out = []
         out.append("// GENERATED by tools/gen_kernel.py -- do not edit.  Specialisation: %s" % display_name)
@@ -1068,20 +1235,38 @@ class Generator:
         out.append("    static IKB_HD T solve(const S &sJ, const S &sL, const S &sE, T damping2, T (&y)[M]) {")
         out.extend(solve)
         out.append("    }")
-        psolve = self.gen_solve_parallel(int(self.spec.get("parallel_block_width", self.spec.get("block_width", 4))), len(groups), solver)
+        if uniform:
+            grams, ubody = self.gen_solve_uniform(len(groups), solver)
+            out.append("    // The same solve distributed over the warp roles with ONE factorisation body (see gen_solve_uniform).")
+            out.append("    // FMAs: Gram per role %s, factorisation + back substitution %d" % self.usolve_fma)
+            for k, code in enumerate(grams):
+                out.append("    template <typename T, typename S>")
+                out.append("    static IKB_HD void ugram_w%d(const S &sJ, const S &sL, T damping2) {" % k)
+                out.extend(code)
+                out.append("    }")
+            out.append("    template <typename T, typename S, typename SYNC>")
+            out.append("    static IKB_HD void psolve(int role, const S &sJ, const S &sL, const S &sE, T damping2, T (&y)[M], SYNC &sync) {")
+            for k in range(len(groups)):
+                out.append("        if (role == %d) ugram_w%d(sJ, sL, damping2);" % (k, k))
+            out.append("        sync();  // the normal equations are in the strip")
+            out.extend(ubody)
+            out.append("    }")
+        psolve = [] if uniform else self.gen_solve_parallel(int(self.spec.get("parallel_block_width", self.spec.get("block_width", 4))), len(groups), solver)
         out.append("    // The same solve distributed over the warp roles (cyclic row ownership; see gen_solve_parallel): every role")
         out.append("    // calls psolve(role, ...) with a group barrier `sync`; y is produced in the SOLVER role's registers only.")
-        out.append("    // FMAs per role: %s" % self.psolve_fma)
+        if not uniform:
+            out.append("    // FMAs per role: %s" % self.psolve_fma)
         for k, code in enumerate(psolve):
             out.append("    template <typename T, typename S, typename SYNC>")
             out.append("    static IKB_HD void psolve_w%d(const S &sJ, const S &sL, const S &sE, T damping2, T (&y)[M], SYNC &sync) {" % k)
             out.extend(code)
             out.append("    }")
-        out.append("    template <typename T, typename S, typename SYNC>")
-        out.append("    static IKB_HD void psolve(int role, const S &sJ, const S &sL, const S &sE, T damping2, T (&y)[M], SYNC &sync) {")
-        for k in range(len(groups)):
-            out.append("        if (role == %d) psolve_w%d(sJ, sL, sE, damping2, y, sync);" % (k, k))
-        out.append("    }")
+        if not uniform:
+            out.append("    template <typename T, typename S, typename SYNC>")
+            out.append("    static IKB_HD void psolve(int role, const S &sJ, const S &sL, const S &sE, T damping2, T (&y)[M], SYNC &sync) {")
+            for k in range(len(groups)):
+                out.append("        if (role == %d) psolve_w%d(sJ, sL, sE, damping2, y, sync);" % (k, k))
+            out.append("    }")
         out.append("    // dq = -J^T y from the strip (dls.cpp:52)")
         out.append("    template <typename T, typename S>")
         out.append("    static IKB_HD void step_direction(const S &sJ, const T (&y)[M], T (&dq)[NV]) {")
