@@ -160,7 +160,17 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
             // that nobody reads).
             T y[M];
             Spec::psolve(role, sJ, sL, sE, a.damping2, y, group_sync);
-            if (role == Spec::SOLVER && have) step_and_publish(y, sres_mine);
+            if constexpr (Spec::DSTEP) {
+                // Distributed step: y is in the strip; every role takes dq = -J^T y and the manifold step on the
+                // coordinates its own evaluate reads (the free-flyer redundantly, with the same instructions), so the
+                // solver role's serial tail -- 40 % of a humanoid iteration in the ncu profile -- shrinks to the back
+                // substitution.  One more barrier: y and ||e||^2 visible.
+                if (role == Spec::SOLVER && have) *sRes = sres_mine;
+                group_sync();
+                if (have && !(abs_(*sRes) < a.tolerance)) Spec::step_role(role, sJ, sL, q, a.step_length, c);  // dls.cpp:52,61-71
+            } else {
+                if (role == Spec::SOLVER && have) step_and_publish(y, sres_mine);
+            }
         } else {
             if (role == Spec::SOLVER && have) {
                 T y[M];
@@ -176,7 +186,7 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
             const bool converged = res < a.tolerance;       // visitor.hpp:19
             bool finished = converged;                      // dls.cpp:61-64: the un-stepped iterate is returned
             if (!converged) {
-                if constexpr (NW > 1) {
+                if constexpr (NW > 1 && !Spec::DSTEP) {
                     if (role != Spec::SOLVER) {             // the stepped, clamped iterate (dls.cpp:67-71) from the solver
 #pragma unroll
                         for (int k = 0; k < NQ; ++k) q[k] = sD.get(k);
@@ -186,10 +196,16 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
                 finished = it >= a.max_iterations;          // dls.cpp:14,76-77
             }
             if (finished || suspend) {
+                if constexpr (Spec::DSTEP) {                // every role holds (and writes) its own coordinates
+                    const ProblemIO<T> io = problem_io<SEG>(a, b);
+                    Spec::store_q(role, q, io.q, io.q_es);
+                }
                 if (role == Spec::SOLVER) {
                     const ProblemIO<T> io = problem_io<SEG>(a, b);
+                    if constexpr (!Spec::DSTEP) {
 #pragma unroll
-                    for (int k = 0; k < NQ; ++k) io.q[k * io.q_es] = q[k];
+                        for (int k = 0; k < NQ; ++k) io.q[k * io.q_es] = q[k];
+                    }
                     if (suspend) {
                         a.iters_ws[b] = it;
                         a.list[atomicAdd(a.list_count, 1ULL)] = (unsigned int)b;

@@ -33,10 +33,16 @@ static int spec_solve(const double *lower, const double *upper, const double *we
     for (int role = 0; role < Spec::NWARPS; ++role) Spec::load_targets(role, tgt.data(), 1LL, sT);
     T q[NQ];
     for (int k = 0; k < NQ; ++k) q[k] = (T)q0[k];
+    // distributed step (Spec::DSTEP): every role keeps its own copy of q and steps only the coordinates it owns, as in the kernel
+    const bool dstep = parallel && Spec::NWARPS > 1 && Spec::DSTEP;
+    std::vector<T> qr_buf((size_t)Spec::NWARPS * NQ);
+    auto qr = [&](int role) -> T(&)[NQ] { return *reinterpret_cast<T(*)[NQ]>(qr_buf.data() + (size_t)role * NQ); };
+    for (int role = 0; role < Spec::NWARPS; ++role)
+        for (int k = 0; k < NQ; ++k) qr(role)[k] = q[k];
     int it = 0, success = 0;
     T res = 0;
     while (it < max_it) {
-        for (int role = 0; role < Spec::NWARPS; ++role) Spec::evaluate(role, q, sT, c, sJ, sE);  // the warp roles, in turn
+        for (int role = 0; role < Spec::NWARPS; ++role) Spec::evaluate(role, dstep ? qr(role) : q, sT, c, sJ, sE);  // the warp roles, in turn
         if (Spec::PRE > 0) Spec::presolve(sJ, sL, sE, (T)(damping * damping));                      // solver role, before the barrier
         if (it == 0 && e_first) for (int i = 0; i < M; ++i) e_first[i] = (double)sE.get(i);
         T y[M], dq[NV];
@@ -58,9 +64,20 @@ static int spec_solve(const double *lower, const double *upper, const double *we
             res = Spec::solve(sJ, sL, sE, (T)(damping * damping), y);
         }
         if (res < (T)tol) { success = 1; break; }
+        if constexpr (Spec::DSTEP) {
+            if (dstep) {
+                for (int role = 0; role < Spec::NWARPS; ++role) Spec::step_role(role, sJ, sL, qr(role), (T)step, c);
+                ++it;
+                continue;
+            }
+        }
         Spec::step_direction(sJ, y, dq);
         Spec::integrate(q, dq, (T)step, c);
         ++it;
+    }
+    if constexpr (Spec::DSTEP) {
+        if (dstep)
+            for (int role = 0; role < Spec::NWARPS; ++role) Spec::store_q(role, qr(role), q, 1LL);  // the result, assembled as the kernel does
     }
     for (int k = 0; k < NQ; ++k) q_out[k] = (double)q[k];
     *iters = it;

@@ -1066,16 +1066,18 @@ class Generator:
                 L.append(ind + "    yp[%d] -= sL.get(%d) * yp[%d];" % (i, Lidx(k, i), k))
                 nf += 1
         L.append(ind + "    #pragma unroll")
+        L.append(ind + "    for (int i = 0; i < %d; ++i) sL.set(%d + i, yp[i]);  // y for step_role() of every role" % (M, RHS))
+        L.append(ind + "    #pragma unroll")
         L.append(ind + "    for (int i = 0; i < %d; ++i) y[i] = yp[i];" % M)
         L.append(ind + "}")
         self.usolve_fma = (nf_gram, nf)
+        self.rhs_off = RHS
         return grams, L
 
-    def gen_dq(self):
+    def gen_dq(self, cols=None, ind="        "):
         L = []
-        ind = "        "
         L.append(ind + "IKB_PHASE_FENCE();")
-        for c in range(self.nv):
+        for c in (range(self.nv) if cols is None else cols):
             rs = sorted(r for (r, cc) in self.slots if cc == c)
             if not rs:
                 L.append(ind + "dq[%d] = T(0);" % c)
@@ -1084,12 +1086,41 @@ class Generator:
             L.append(ind + "dq[%d] = -(%s);" % (c, expr))
         return L
 
-    def gen_integrate(self):
+    def joint_cols(self, joints):
+        """velocity columns / configuration entries of a set of joints"""
+        cols, qs = [], []
+        for j in joints:
+            jt = self.joints[j]
+            nvj, nqj = (6, 7) if jt["type"] == J_FF else (1, 1)
+            cols.extend(range(jt["idx_v"], jt["idx_v"] + nvj))
+            qs.extend(range(jt["idx_q"], jt["idx_q"] + nqj))
+        return cols, qs
+
+    def gen_step_roles(self, groups, solver):
+        """Distributed step (spec "uniform_solve"): after the solve every role takes dq = -J^T y and the manifold step
+        (dls.cpp:52,67-71) on the coordinates ITS evaluate reads -- the joints common to all roles (the free-flyer) by
+        everybody, redundantly and with the same instructions; the rest of its chains by the role alone -- instead of the
+        solver role doing all of it while the others wait.  Returns (common code, per-role code, per-role q entries)."""
+        chains = [sorted(set(j for t in g for j in self.tasks[t]["chain"])) for g in groups]
+        common = sorted(set.intersection(*[set(ch) for ch in chains]))
+        covered = set(j for ch in chains for j in ch)
+        loose = [j for j, jt in enumerate(self.joints) if jt["type"] != J_UNIVERSE and j not in covered]
+        ind = "        "
+        ccols, cqs = self.joint_cols(common)
+        C = self.gen_dq(ccols, ind) + self.gen_integrate(common, ind)
+        roles, qsets = [], []
+        for k, ch in enumerate(chains):
+            own = [j for j in ch if j not in common] + (loose if k == solver else [])
+            cols, qs = self.joint_cols(own)
+            roles.append(self.gen_dq(cols, ind + "    ") + self.gen_integrate(own, ind + "    "))
+            qsets.append(qs + (cqs if k == solver else []))
+        return C, roles, qsets
+
+    def gen_integrate(self, joints=None, ind="        "):
         """pinocchio::integrate (dls.cpp:67-68) + clamp (common.hpp:53-56), joint by joint."""
         L = []
-        ind = "        "
         for j, jt in enumerate(self.joints):
-            if jt["type"] == J_UNIVERSE:
+            if jt["type"] == J_UNIVERSE or (joints is not None and j not in joints):
                 continue
             iq, iv = jt["idx_q"], jt["idx_v"]
             if jt["type"] == J_FF:
@@ -1101,6 +1132,10 @@ class Generator:
                 L.append(ind + "}")
             else:
                 L.append(ind + "q[%d] += step * dq[%d];" % (iq, iv))
+        if joints is not None:
+            for k in self.joint_cols(joints)[1]:
+                L.append(ind + "q[%d] = min_(c.upper[%d], max_(q[%d], c.lower[%d]));" % (k, k, k, k))
+            return L
         L.append(ind + "#pragma unroll")
         L.append(ind + "for (int k = 0; k < %d; ++k) q[k] = min_(c.upper[k], max_(q[k], c.lower[k]));" % self.nq)
         return L
@@ -1179,6 +1214,8 @@ class Generator:
         out.append("    // PSOLVE: distribute the factorisation over the roles (pays off for large M; for M = 12 the ~7 extra group")
         out.append("    // barriers cost more than the shorter critical path saves -- measured, DESIGN.md 4.1)")
         out.append("    static constexpr bool PSOLVE = %s;" % ("true" if self.spec.get("parallel_solve") and len(groups) > 1 else "false"))
+        out.append("    // DSTEP: after psolve() y sits in the strip and every role steps its own coordinates (step_role / store_q)")
+        out.append("    static constexpr bool DSTEP = %s;" % ("true" if uniform else "false"))
         out.append("    // PRE: leading rows whose P x P factor block the SOLVER role computes in presolve(), before the first barrier;")
         out.append("    // EOFF: slot of the factor strip where e starts (rows >= PRE of L, written only after e has been read)")
         out.append("    static constexpr int PRE = %d, EOFF = %d;" % (P, self.eoff))
@@ -1277,6 +1314,29 @@ class Generator:
         out.append("    static IKB_HD void integrate(T (&q)[NQ], const T (&dq)[NV], T step, const SpecConsts<T, NQ, M> &c) {")
         out.extend(integ)
         out.append("    }")
+        if uniform:
+            C, roles, qsets = self.gen_step_roles(groups, solver)
+            out.append("    // Distributed step (see gen_step_roles): y from the strip; common joints by every role, the others by their role.")
+            out.append("    template <typename T, typename S>")
+            out.append("    static IKB_HD void step_role(int role, const S &sJ, const S &sL, T (&q)[NQ], T step, const SpecConsts<T, NQ, M> &c) {")
+            out.append("        T y[M], dq[NV];")
+            out.append("        #pragma unroll")
+            out.append("        for (int i = 0; i < M; ++i) y[i] = sL.get(%d + i);" % self.rhs_off)
+            out.extend(C)
+            for k, code in enumerate(roles):
+                out.append("        if (role == %d) {" % k)
+                out.extend(code)
+                out.append("        }")
+            out.append("    }")
+            out.append("    // the entries of q a role owns (its step_role keeps exactly these current), written to the result")
+            out.append("    template <typename T>")
+            out.append("    static IKB_HD void store_q(int role, const T (&q)[NQ], T *dst, long long es) {")
+            for k, qs in enumerate(qsets):
+                out.append("        if (role == %d) {" % k)
+                for iq in sorted(qs):
+                    out.append("            dst[%d * es] = q[%d];" % (iq, iq))
+                out.append("        }")
+            out.append("    }")
         # signature data for matches()
         out.append("    // ---- signature (host): the tree and task list this code was generated for ----")
         out.append("    static constexpr int NJOINTS = %d, NTASKS = %d;" % (len(self.joints), len(self.tasks)))
