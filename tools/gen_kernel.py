@@ -942,6 +942,7 @@ class Generator:
         for (r, c) in self.slots:
             row_cols.setdefault(r, set()).add(c)
         # ---- phase 0: Gram, per role ----
+        roll_gram = bool(self.spec.get("rolled_gram", True))
         grams = []
         nf_gram = [0] * R
         for role in range(R):
@@ -961,17 +962,49 @@ class Generator:
                 for (i, j) in pairs:
                     L.append(ind + "    T g_%d_%d = %s;" % (i, j, "damping2" if i == j else "T(0)"))
                 cols = sorted(set().union(*[row_cols.get(i, set()) for i in ra]) & set().union(*[row_cols.get(j, set()) for j in rb]))
-                for c in cols:
-                    use = [(i, j) for (i, j) in pairs if c in row_cols.get(i, ()) and c in row_cols.get(j, ())]
+                # Runs of consecutive columns that involve the same rows, with slots affine in the column, become ONE rolled
+                # loop (run-time column, one shifted strip per distinct slot stride): the same FMAs in the same order,
+                # a third of the code -- the Gram phase is instruction-fetch bound.
+                def col_use(c):
+                    return [(i, j) for (i, j) in pairs if c in row_cols.get(i, ()) and c in row_cols.get(j, ())]
+                runs, k0 = [], 0
+                while k0 < len(cols):
+                    c0 = cols[k0]
+                    use0 = col_use(c0)
+                    need0 = sorted(set([i for i, _ in use0] + [j for _, j in use0]))
+                    k1 = k0 + 1
+                    stride = None
+                    while roll_gram and k1 < len(cols) and cols[k1] == cols[k1 - 1] + 1 and col_use(cols[k1]) == use0:
+                        st = {i: self.slots[(i, cols[k1])] - self.slots[(i, cols[k1 - 1])] for i in need0}
+                        if stride is None:
+                            stride = st
+                        if st != stride:
+                            break
+                        k1 += 1
+                    runs.append((cols[k0:k1], use0, need0, stride))
+                    k0 = k1
+                for (rc, use, need, stride) in runs:
                     if not use:
                         continue
-                    need = sorted(set([i for i, _ in use] + [j for _, j in use]))
-                    L.append(ind + "    {  // J column %d" % c)
+                    if len(rc) == 1:
+                        c = rc[0]
+                        L.append(ind + "    {  // J column %d" % c)
+                        for i in need:
+                            L.append(ind + "        const T a%d = sJ.get(%d);" % (i, self.slots[(i, c)]))
+                        for (i, j) in use:
+                            L.append(ind + "        g_%d_%d += a%d * a%d;" % (i, j, i, j))
+                            nf_gram[role] += 1
+                        L.append(ind + "    }")
+                        continue
+                    L.append(ind + "    #pragma unroll 1")
+                    L.append(ind + "    for (int k = 0; k < %d; ++k) {  // J columns %d..%d" % (len(rc), rc[0], rc[-1]))
+                    for st in sorted(set(stride.values())):
+                        L.append(ind + "        const S sC%d{sJ.base + k * %d * S::kStride};" % (st, st))
                     for i in need:
-                        L.append(ind + "        const T a%d = sJ.get(%d);" % (i, self.slots[(i, c)]))
+                        L.append(ind + "        const T a%d = sC%d.get(%d);" % (i, stride[i], self.slots[(i, rc[0])]))
                     for (i, j) in use:
                         L.append(ind + "        g_%d_%d += a%d * a%d;" % (i, j, i, j))
-                        nf_gram[role] += 1
+                        nf_gram[role] += len(rc)
                     L.append(ind + "    }")
                 for (i, j) in pairs:
                     L.append(ind + "    sL.set(%d, g_%d_%d);" % (DI + i if i == j else Lidx(i, j), i, j))
