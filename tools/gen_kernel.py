@@ -1023,6 +1023,8 @@ class Generator:
             tri = [(a, b) for b in range(W) for a in range(b, W)]
             L.append(ind + "// ---- block column %d..%d ----" % (j0, j0 + W - 1))
             L.append(ind + "IKB_PHASE_FENCE();")
+            if kb == NB - 1:
+                L.append(ind + "if (r == %d) {  // nobody owns rows below the last block: the solver role alone" % solver)
             for (a, b) in tri:
                 L.append(ind + "T d%d_%d_%d = sL.get(%d);" % (kb, a, b, DI + j0 + a if a == b else Lidx(j0 + a, j0 + b)))
             for m in own:
@@ -1090,6 +1092,8 @@ class Generator:
                 for a in range(b + 1, W):
                     L.append(ind + "    sL.set(%d, l%d_%d_%d);" % (Lidx(j0 + a, j0 + b), kb, a, b))
             L.append(ind + "}")
+            if kb == NB - 1:
+                L.append(ind + "}")
         L.append(ind + "if (r == %d) {  // ---- back substitution (solver role) ----" % solver)
         L.append(ind + "    T yp[%d];" % M)
         L.append(ind + "    #pragma unroll")
