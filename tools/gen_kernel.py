@@ -943,17 +943,20 @@ class Generator:
             row_cols.setdefault(r, set()).add(c)
         # ---- phase 0: Gram, per role ----
         roll_gram = bool(self.spec.get("rolled_gram", True))
-        grams = []
+        grams, grams_blocks = [], []
         nf_gram = [0] * R
         for role in range(R):
             L = []
             blocks = [(role, role)]
-            for d in (1, 2):
-                o = (role + d) % R
-                if o != role and (max(role, o), min(role, o)) not in blocks:
-                    blocks.append((max(role, o), min(role, o)))
-            if R != 5:
-                raise ValueError("uniform_solve: the Gram block assignment is written for 5 roles")
+            if self.spec.get("gram_blocks"):  # explicit (balanced) assignment of the off-diagonal task blocks: [[ta, tb], ...] per role
+                blocks += [(max(a, b), min(a, b)) for a, b in self.spec["gram_blocks"][role]]
+            else:
+                for d in (1, 2):
+                    o = (role + d) % R
+                    if o != role and (max(role, o), min(role, o)) not in blocks:
+                        blocks.append((max(role, o), min(role, o)))
+                if R != 5:
+                    raise ValueError("uniform_solve: the default Gram block assignment is written for 5 roles")
             for (ta, tb) in blocks:
                 ra = list(range(self.tasks[ta]["row"], self.tasks[ta]["row"] + TD))
                 rb = list(range(self.tasks[tb]["row"], self.tasks[tb]["row"] + TD))
@@ -1010,6 +1013,10 @@ class Generator:
                     L.append(ind + "    sL.set(%d, g_%d_%d);" % (DI + i if i == j else Lidx(i, j), i, j))
                 L.append(ind + "}")
             grams.append(L)
+            grams_blocks.append(blocks)
+        owned = sorted(b for role in range(R) for b in grams_blocks[role])
+        if owned != sorted((a, b) for a in range(R) for b in range(a + 1)):
+            raise ValueError("uniform_solve: the Gram blocks must be assigned exactly once each")
         # ---- block columns: one body, run-time role r ----
         L = []
         nf = 0
