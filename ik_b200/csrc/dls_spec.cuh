@@ -10,7 +10,9 @@
 //     the other roles do theirs (Cassie: pelvis pose | left foot | right foot).  Role SOLVER then runs the fused
 //     Gram + blocked LDL^T + substitutions and the step dq = -J^T y; every role integrates its own register copy of q
 //     (bit-identical, same code and inputs), so no role ever waits for q.  Two named barriers per iteration
-//     (bar.sync id, NWARPS*32): after evaluate (J, e visible) and after solve (dq, ||e||^2 visible).
+//     (bar.sync id, NWARPS*32): after evaluate (J, e visible) and after solve (dq, ||e||^2 visible).  Large systems
+//     (Spec::PSOLVE, the humanoid) run the factorisation on all roles (Spec::psolve takes the group barrier as an
+//     argument) and, with Spec::DSTEP, every role steps and writes the coordinates of q its own evaluate reads.
 //   * per-problem state lives in strips of shared memory (element k of slot s at base[k * SLOTS + s]:
 //     conflict-free): weighted J non-zeros, the LDL^T factor (whose storage first carries e and finally dq), the
 //     target poses; plus ||e||^2 and a prefetched ticket per slot.  Cassie FP64: 219 doubles + 16 B = 1768 B per

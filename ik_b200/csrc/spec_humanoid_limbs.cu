@@ -1,7 +1,9 @@
 // Specialised solve kernel: 32-DoF free-flyer humanoid with torso pose + four end-effector poses, all Full frame
-// tasks in `universe` (BASELINE.json config 4: 30 task rows).  Five warp roles: torso (+ the 30x30 solve) and one per
-// limb.  The per-problem strips (303 J non-zeros + 465 factor + 60 target scalars) allow one 32-problem group per SM in
-// FP64, so both launch variants are the one-group configuration.
+// tasks in `universe` (BASELINE.json config 4: 30 task rows).  Five warp roles: torso (+ back substitution) and one per
+// limb; the factorisation runs on all five with ONE body (rows r + 5m by run-time role index, tools/gen_kernel.py
+// gen_solve_uniform) and every role steps the coordinates its own evaluate reads (Spec::DSTEP).  The per-problem strips
+// (303 J non-zeros + 525 factor / rhs / Gram-diagonal + 60 target scalars) allow one 32-problem group per SM in FP64
+// (two in FP32), so both launch variants are the one-group configuration.
 #include "dls_spec.cuh"
 #include "gen/humanoid_limbs.cuh"
 
