@@ -555,6 +555,10 @@ int ikb_problem_finalize(ikb_problem *p, int device) {
     if (prop.major < 10)
         return fail(IKB_ERR_NO_DEVICE, std::string("device ") + prop.name + " is not Blackwell-class (sm_100a code only)");
     p->sm_count = prop.multiProcessorCount;
+    if (const char *e = std::getenv("IKB_SM_LIMIT")) {  // measurement knob: persistent grids sized for fewer SMs (read at finalize)
+        const int lim = std::atoi(e);
+        if (lim >= 1 && lim < p->sm_count) p->sm_count = lim;
+    }
 
     auto *h64 = new DevProblem<double>();
     auto *h32 = new DevProblem<float>();
