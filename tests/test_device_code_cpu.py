@@ -248,7 +248,7 @@ def test_role_distributed_solve_matches_oracle(spec_lib, name, robot, ff, make, 
     pb = make()
     om = oracle_model(robot, ff)
     opb = oracle_problem_like(pb, om)
-    B = 40 if robot != "humanoid" else 12
+    B = 60
     q0, tg, _ = _workload(pb, om, B, standing)
     q_ref, ok_ref, it_ref, res_ref = O.dls_batch(opb, q0, tg)
     q, ok, it, res, _ = _spec_solve(spec_lib, name, "f64p", pb, q0, tg, O.params())
