@@ -27,6 +27,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include "dev_problem.hpp"
 #include "model.hpp"
 #include "spec_common.hpp"
@@ -35,6 +37,22 @@
 namespace ikb {
 
 constexpr int kSmemPerCtaMax = 227 * 1024;  // B200: 228 KB per SM, 227 KB usable by one CTA
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: a process that finalizes problems
+// on several GPUs must opt in on each of them.  One bit per device ordinal, set after the first successful call on
+// that device (safe from concurrent host threads: a lost race only repeats the idempotent call).
+struct DynSmemOptIn {
+    std::atomic<unsigned long long> done{0};
+    template <class Fn> bool ensure(Fn fn, int bytes) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return false;
+        const unsigned long long bit = 1ULL << (dev & 63);
+        if (done.load(std::memory_order_acquire) & bit) return true;
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return false;
+        done.fetch_or(bit, std::memory_order_release);
+        return true;
+    }
+};
 
 template <class Spec, typename T> struct SpecLaunch {
     static constexpr int NW = Spec::NWARPS;
@@ -271,11 +289,8 @@ int launch_spec_cfg_seg(const SpecHostConsts &hc, const SolveArgs<T> &a, long lo
     static_assert(L::kFits && GROUPS <= L::GROUPS, "per-problem strips do not fit in shared memory for this scalar type");
     constexpr int kSmem = L::smem_bytes(GROUPS);
     auto fn = dls_spec_kernel<Spec, T, GROUPS, MINB, SEG>;
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess) return 1;
-        attr_set = true;
-    }
+    static DynSmemOptIn opt_in;  // per instantiation; the attribute itself is per DEVICE
+    if (!opt_in.ensure(fn, kSmem)) return 1;
     SpecConsts<T, Spec::NQ, Spec::M> c;
     for (int k = 0; k < Spec::NQ; ++k) {
         c.lower[k] = (T)hc.lower[k];

@@ -398,11 +398,8 @@ __global__ void __launch_bounds__(TeamLaunch<T>::kTeamsPerCta *kTeamLanes, TeamL
 template <typename T, bool SEG> int launch_team_seg(const TeamConsts<T> &c, const SolveArgs<T> &a, long long n, int sm_count, cudaStream_t s) {
     using L = TeamLaunch<T>;
     auto fn = dls_team_kernel<T, SEG>;
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kSmem) != cudaSuccess) return 1;
-        attr_set = true;
-    }
+    static DynSmemOptIn opt_in;  // per instantiation; the attribute itself is per device (dls_spec.cuh)
+    if (!opt_in.ensure(fn, (int)L::kSmem)) return 1;
     long long ctas = (n + L::kTeamsPerCta - 1) / L::kTeamsPerCta;
     if (ctas > (long long)L::kCtasPerSm * sm_count) ctas = (long long)L::kCtasPerSm * sm_count;
     if (ctas < 1) ctas = 1;

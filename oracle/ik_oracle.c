@@ -7,13 +7,30 @@
  * multibody/liegroup/special-euclidean.hpp; Eigen: Cholesky/LDLT.h, Geometry/Quaternion.h).
  * Written from the published algorithms -- no third-party code is copied.  PARITY UNPINNED (header).
  */
-#include "ik_oracle.h"
-
 #include <math.h>
 #include <float.h>
 #include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
+
+/* -DIKO_F32: the SAME restatement evaluated in single precision (libik_oracle_f32.so) -- what the reference computes
+ * when common.hpp:13 reads `typedef float number_t` (Pinocchio and Eigen are templated on the scalar, so every
+ * formula, threshold and pivot rule below is the same with Scalar = float: TaylorSeriesExpansion<float> uses
+ * FLT_EPSILON).  Interface arrays become float too.  Used by tests/test_oracle_f32.py to measure how far ANY FP32
+ * implementation of this iteration lands from the FP64 one. */
+#ifdef IKO_F32
+#include <tgmath.h>
+#define double float
+#undef DBL_EPSILON
+#define DBL_EPSILON FLT_EPSILON
+#undef DBL_MIN
+#define DBL_MIN FLT_MIN
+#define IKO_TINY 1e-37f
+#else
+#define IKO_TINY 1e-300
+#endif
+
+#include "ik_oracle.h"
 
 /* ------------------------------------------------------------------------------------------------
  * small helpers
@@ -779,8 +796,8 @@ static void svd_rows(int m, int n, const double *A, double *U, double *s, double
                     b += W[q * n + k] * W[q * n + k];
                     c += W[p * n + k] * W[q * n + k];
                 }
-                if (fabs(c) <= 1e-300 || fabs(c) <= 1e-17 * sqrt(a * b)) continue;
-                off += fabs(c) / sqrt(a * b + 1e-300);
+                if (fabs(c) <= IKO_TINY || fabs(c) <= 1e-17 * sqrt(a * b)) continue;
+                off += fabs(c) / sqrt(a * b + IKO_TINY);
                 const double zeta = (b - a) / (2 * c);
                 const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1 + zeta * zeta));
                 const double cs = 1 / sqrt(1 + t * t), sn = cs * t;

@@ -54,6 +54,21 @@ def lib():
     return _LIB
 
 
+_LIB_FMA = None
+
+
+def lib_fma():
+    """The FP64 restatement compiled with fused multiply-adds (-ffp-contract=fast -mfma): same algorithm, other rounding."""
+    global _LIB_FMA
+    if _LIB_FMA is None:
+        build()
+        so = os.path.join(_HERE, "libik_oracle_fma.so")
+        if not os.path.exists(so):
+            subprocess.check_call(["make", "-C", _HERE, "-s"])
+        _LIB_FMA = C.CDLL(so)
+    return _LIB_FMA
+
+
 def _d(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
@@ -249,8 +264,8 @@ def dls(problem, q0, targets, prm=None):
     return q, bool(ok), it.value, res.value, dq
 
 
-def dls_batch(problem, q0, targets, prm=None, nthreads=1):
-    """Loop of ik::dls over a batch.  q0 [B, nq], targets [B, target_size] (AoS)."""
+def dls_batch(problem, q0, targets, prm=None, nthreads=1, fma=False):
+    """Loop of ik::dls over a batch.  q0 [B, nq], targets [B, target_size] (AoS).  fma=True: the FMA-contracted build."""
     prm = prm or params()
     m = problem.model
     q0 = _d(q0)
@@ -261,14 +276,82 @@ def dls_batch(problem, q0, targets, prm=None, nthreads=1):
     ok = np.zeros(B, dtype=np.uint8)
     it = np.zeros(B, dtype=np.int32)
     res = np.zeros(B)
-    lib().iko_dls_batch(C.byref(m.c), C.byref(problem.c), C.byref(prm), C.c_int(B), _pd(q0), _pd(targets), _pd(q),
-                        ok.ctypes.data_as(C.POINTER(C.c_ubyte)), _pi(it), _pd(res), C.c_int(nthreads))
+    (lib_fma() if fma else lib()).iko_dls_batch(C.byref(m.c), C.byref(problem.c), C.byref(prm), C.c_int(B), _pd(q0), _pd(targets),
+                                                _pd(q), ok.ctypes.data_as(C.POINTER(C.c_ubyte)), _pi(it), _pd(res),
+                                                C.c_int(nthreads))
     return q, ok.astype(bool), it, res
 
 
 class _CPikParams(C.Structure):
     _fields_ = [("max_iterations", C.c_int), ("step_length", C.c_double), ("tolerance", C.c_double),
                 ("lam", C.c_double * 8)]
+
+
+# ---- FP32 build of the same restatement (libik_oracle_f32.so, ik_oracle.c -DIKO_F32) ---------------------------------
+_fp = C.POINTER(C.c_float)
+_LIB32 = None
+
+
+class _CModelF(C.Structure):
+    _fields_ = [(n, _fp if t is _dp else t) for n, t in _CModel._fields_]
+
+
+class _CProblemF(C.Structure):
+    _fields_ = [(n, _fp if t is _dp else t) for n, t in _CProblem._fields_]
+
+
+class _CParamsF(C.Structure):
+    _fields_ = [("max_iterations", C.c_int), ("step_length", C.c_float), ("damping", C.c_float), ("tolerance", C.c_float)]
+
+
+def lib_f32():
+    global _LIB32
+    if _LIB32 is None:
+        build()
+        so = os.path.join(_HERE, "libik_oracle_f32.so")
+        if not os.path.exists(so):
+            subprocess.check_call(["make", "-C", _HERE, "-s"])
+        _LIB32 = C.CDLL(so)
+    return _LIB32
+
+
+def dls_batch_f32(problem, q0, targets, prm=None, nthreads=1):
+    """ik::dls looped over a batch with number_t = float: every scalar of the restatement (model constants, FK, log6,
+    Gram, pivoted LDL^T, integrate, stop test) is single precision.  Returns float64 copies of q / resid."""
+    prm = prm or params()
+    m = problem.model
+    keep = []
+
+    def conv(struct, cls):
+        vals = []
+        for (n, t), (_, tf) in zip(struct._fields_, cls._fields_):
+            v = getattr(struct, n)
+            if t is _dp:
+                # the float64 array behind the pointer: look its length up in the owners' keep-alive dicts
+                src = next(a for a in list(m._keep.values()) + list(problem._keep.values())
+                           if a.dtype == np.float64 and a.ctypes.data == C.cast(v, C.c_void_p).value)
+                with np.errstate(over="ignore"):  # +-DBL_MAX limits of the free-flyer become +-inf
+                    a32 = np.ascontiguousarray(src, dtype=np.float32)
+                keep.append(a32)
+                v = a32.ctypes.data_as(_fp)
+            vals.append(v)
+        return cls(*vals)
+
+    pc = problem.c  # materialises problem._keep
+    cm, cp = conv(m.c, _CModelF), conv(pc, _CProblemF)
+    cprm = _CParamsF(prm.max_iterations, prm.step_length, prm.damping, prm.tolerance)
+    q0 = np.ascontiguousarray(q0, dtype=np.float32)
+    targets = np.ascontiguousarray(targets, dtype=np.float32)
+    B = q0.shape[0]
+    assert q0.shape == (B, m.nq) and targets.shape == (B, problem.target_size)
+    q = np.zeros((B, m.nq), dtype=np.float32)
+    ok = np.zeros(B, dtype=np.uint8)
+    it = np.zeros(B, dtype=np.int32)
+    res = np.zeros(B, dtype=np.float32)
+    lib_f32().iko_dls_batch(C.byref(cm), C.byref(cp), C.byref(cprm), C.c_int(B), q0.ctypes.data_as(_fp),
+                            targets.ctypes.data_as(_fp), q.ctypes.data_as(_fp), ok.ctypes.data_as(C.POINTER(C.c_ubyte)),
+                            _pi(it), res.ctypes.data_as(_fp), C.c_int(nthreads))
+    return q.astype(np.float64), ok.astype(bool), it, res.astype(np.float64)
 
 
 def pik_params(max_iterations=100, step_length=1.0, lambdas=None, tolerance=1e-4):

@@ -35,26 +35,55 @@ def _solve_gpu(pb, q0, tg, params=None, dtype="f64"):
             out["iters"].cpu().numpy(), out["resid"].cpu().numpy().astype(np.float64))
 
 
-def _compare(name, gpu, ref, qtol, flag_mismatch_allowed=0, min_same_frac=0.99, converged_only=False):
-    """converged_only: compare q on converged problems only -- a FAILED solve of a 6R arm bounces between joint limits
+PARITY_LOG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_r2.txt")
+
+
+def _log(line):
+    """Measured agreement of every parity case: printed (-s) and appended to gpurun_out/parity_r2.txt, which is copied to
+    profiles/ after a GPU run (keep the measured same-iteration numbers)."""
+    print(line)
+    try:
+        os.makedirs(os.path.dirname(PARITY_LOG), exist_ok=True)
+        with open(PARITY_LOG, "a") as f:
+            f.write(line + "\n")
+    except OSError:
+        pass
+
+
+def _compare(name, gpu, ref, qtol, expect_agree=1.0, flag_mismatch_allowed=0, converged_only=False, q_frac=1.0):
+    """`agree` = problems whose converged flag AND iteration count equal the oracle's.  expect_agree = 1.0 asserts
+    agree.all() (the FP64 bar: flags and iteration counts identical); where less than 100 % is real (chaotic failed
+    trajectories of serial arms) the MEASURED fraction is pinned to +-0.5 %.
+    converged_only: compare q on converged problems only -- a FAILED solve of a 6R arm bounces between joint limits
     for 100 iterations (chaotic: two FP64 implementations end at different limits), unlike Cassie's failures, which
     stagnate at a fixed point and are compared too."""
     q, ok, it, res = gpu
     q_ref, ok_ref, it_ref, res_ref = ref
+    ok_ref = ok_ref.astype(bool)
     B = len(ok)
     flag_mismatch = int((ok != ok_ref).sum())
-    same = (it == it_ref) & (ok == ok_ref)
-    if converged_only:
-        same &= ok.astype(bool)
-    qerr = float(np.abs(q[same] - q_ref[same]).max()) if same.any() else 0.0
-    conv = same & ok
+    agree = (it == it_ref) & (ok == ok_ref)
+    same = agree & ok if converged_only else agree
+    qerrs = np.abs(q[same] - q_ref[same]).max(axis=1) if same.any() else np.zeros(1)
+    qerr = float(qerrs.max())
+    within = float((qerrs < qtol).mean())
+    conv = agree & ok
     rerr = float(np.abs(res[conv] - res_ref[conv]).max()) if conv.any() else 0.0
-    print("%s: B=%d converged gpu/ref=%d/%d flag mismatches=%d same-iteration=%d (%.4f) max|q-q_ref|=%.3e "
-          "max|resid diff|=%.3e mean iters=%.2f" % (name, B, ok.sum(), ok_ref.sum(), flag_mismatch, same.sum(),
-                                                    same.mean(), qerr, rerr, it_ref.mean()))
+    _log("%s: B=%d converged gpu/ref=%d/%d flag mismatches=%d agree(flags+iterations)=%d (%.6f) max|q-q_ref|=%.3e "
+         "(within %.0e: %.6f, p99.9 %.2e) max|resid diff|=%.3e mean iters=%.2f"
+         % (name, B, ok.sum(), ok_ref.sum(), flag_mismatch, agree.sum(), agree.mean(), qerr, qtol, within,
+            np.percentile(qerrs, 99.9), rerr, it_ref.mean()))
     assert flag_mismatch <= flag_mismatch_allowed
-    assert same.mean() >= min_same_frac
-    assert qerr < qtol
+    if expect_agree is None:          # not pinned yet: floor only
+        assert agree.mean() >= 0.9
+    elif expect_agree >= 1.0:
+        assert agree.all(), "%d of %d problems differ in flag or iteration count" % (B - agree.sum(), B)
+    else:
+        assert abs(agree.mean() - expect_agree) <= 0.005, "measured agreement %.4f, pinned %.4f" % (agree.mean(), expect_agree)
+    if q_frac >= 1.0:
+        assert qerr < qtol
+    else:                              # chaotic outliers: the measured fraction within qtol is pinned (+-0.5 %)
+        assert abs(within - q_frac) <= 0.005 and within >= q_frac - 1e-4, "within %.6f, pinned %.6f" % (within, q_frac)
     return qerr
 
 
@@ -167,7 +196,7 @@ def test_cassie_demo_task_set(B, params, kernel_path):
     # few that need 70-100 steps crawl along an ill-conditioned valley (the moving reference frame is not differentiated,
     # so the iteration is not a Gauss-Newton step there) and amplify rounding: the generic and the specialised kernel and
     # the oracle differ pairwise by up to 1e-5 rad on the same ~0.1 % of problems (tools/demo_diff.py) -- bar 1e-4.
-    _compare("cassie demo tasks %s B=%d" % (params, B), gpu, ref, 1e-4, min_same_frac=0.95,  # ~3 % never converge
+    _compare("cassie demo tasks %s B=%d" % (params, B), gpu, ref, 1e-4,
              converged_only=True)
     q, ok, it, _ = gpu
     q_ref, ok_ref, it_ref, _ = ref
@@ -194,7 +223,7 @@ def test_cassie_demo_with_posture_task(params, kernel_path):
     else:
         prm, oprm = ik.dls_parameters(max_iterations=200, step_length=0.1, damping=0.1), O.params(200, 0.1, 0.1)
     ref = O.dls_batch(opb, q0, tg, oprm, nthreads=NT)
-    _compare("cassie demo + posture %s" % params, _solve_gpu(pb, q0, tg, prm), ref, 1e-6, min_same_frac=0.9,
+    _compare("cassie demo + posture %s" % params, _solve_gpu(pb, q0, tg, prm), ref, 1e-6,
              converged_only=True)
 
 
@@ -252,7 +281,7 @@ def test_humanoid_f64(kernel_path):
     opb = oracle_problem_like(pb, om)
     q0, tg, _ = make_workload(pb, om, 512, seed=5, start="near")
     ref = O.dls_batch(opb, q0, tg, nthreads=NT)
-    _compare("humanoid f64", _solve_gpu(pb, q0, tg), ref, 1e-6, min_same_frac=0.97)
+    _compare("humanoid f64", _solve_gpu(pb, q0, tg), ref, 1e-6)
 
 
 def test_manipulator_f64(kernel_path):
@@ -263,7 +292,7 @@ def test_manipulator_f64(kernel_path):
     opb = oracle_problem_like(pb, om)
     q0, tg, _ = make_workload(pb, om, 2048, seed=11, start="near")
     ref = O.dls_batch(opb, q0, tg, nthreads=NT)
-    _compare("manipulator f64", _solve_gpu(pb, q0, tg), ref, 1e-6, min_same_frac=0.97)
+    _compare("manipulator f64", _solve_gpu(pb, q0, tg), ref, 1e-6)
 
 
 def test_zero_iterations_returns_q0():
@@ -296,7 +325,7 @@ def test_ur5_orientation_and_weights():
     opb = oracle_problem_like(pb, om)
     q0, tg, _ = make_workload(pb, om, B, seed=21, start="near")  # warm start: far starts are chaotic for a 6R arm
     ref = O.dls_batch(opb, q0, tg, nthreads=NT)
-    _compare("ur5 mixed tasks", _solve_gpu(pb, q0, tg), ref, 1e-6, min_same_frac=0.97, converged_only=True)
+    _compare("ur5 mixed tasks", _solve_gpu(pb, q0, tg), ref, 1e-6, converged_only=True)
 
 
 def test_full_size_properties():
@@ -408,6 +437,77 @@ def test_full_size_f32_cassie():
     # the foot-pitch direction is barely observed by the two foot POSITION tasks: FP32 rounding of FK is amplified by
     # ~1/damping there, so the tail of 65 536 samples reaches a few 1e-2 rad -- the bar is on quantiles
     assert (err < 1e-4).float().mean().item() > 0.99 and (err < 3e-3).float().mean().item() > 0.998 and err.max().item() < 0.2
+
+
+@pytest.mark.parametrize("name,make,oname,ff,B,start,expect", [
+    ("cassie", W.cassie_feet_pelvis_problem, "cassie", True, 65536, "standing", 1.0),
+    ("humanoid", W.humanoid_problem, "humanoid", True, 262144, "near", None),
+    ("manipulator", W.manipulator_problem, "manipulator", False, 1048576, "near", None)])
+def test_full_size_oracle_parity(name, make, oname, ff, B, start, expect):
+    """every BASELINE config against the ORACLE at its FULL batch size (65,536 / 262,144 /
+    1,048,576), all problems: converged flags exact, iteration counts as pinned, |q - q_oracle| < 1e-6 rad wherever flag
+    and iteration count agree, residuals within 1e-9.  The oracle loop is threaded over all host cores."""
+    pb, names, poses, q0, tg, out = _full_size_case(make, B, start, "f64")
+    om = oracle_model(oname, free_flyer=ff)
+    opb = oracle_problem_like(pb, om)
+    ref = O.dls_batch(opb, q0, tg, nthreads=NT)
+    gpu = (out["q"].cpu().numpy().T.astype(np.float64), out["success"].cpu().numpy().astype(bool),
+           out["iters"].cpu().numpy(), out["resid"].cpu().numpy().astype(np.float64))
+    if name == "cassie":
+        # failures stagnate at a fixed point and are compared too: every one of the 65,536 problems, exact flags and
+        # iteration counts, q within 1e-6 rad (measured 6.0e-7 on the slowest stragglers, 6e-12 on 4,096)
+        _compare("FULL SIZE %s f64 (%s)" % (name, pb.kernel_name()), gpu, ref, 1e-6)
+        return
+    # Serial chains started 0.3 rad away with full steps: a handful of problems per 100,000 follow chaotic trajectories
+    # (failed solves bounce between joint limits; some converging ones pass near a singularity), on which ANY two FP64
+    # evaluations drift apart.  The yardstick is the oracle itself compiled with fused multiply-adds (same algorithm,
+    # other rounding): the kernel must agree with the oracle as well as the oracle's two builds agree with each other.
+    ref_fma = O.dls_batch(opb, q0, tg, nthreads=NT, fma=True)
+
+    def stats(x):
+        agree = (x[2] == ref[2]) & (x[1] == ref[1].astype(bool))
+        same = agree & x[1]
+        err = np.abs(x[0][same] - ref[0][same]).max(axis=1)
+        return dict(flags=int((x[1] != ref[1].astype(bool)).sum()), agree=float(agree.mean()), within=float((err < 1e-6).mean()),
+                    p999=float(np.percentile(err, 99.9)), max=float(err.max()))
+
+    g, o = stats(gpu), stats(ref_fma)
+    for label, st in (("kernel %s" % pb.kernel_name(), g), ("oracle built with FMA", o)):
+        _log("FULL SIZE %s f64, %s vs oracle: B=%d flag mismatches=%d agree(flags+iterations)=%.6f |dq|<1e-6 on %.6f of the "
+             "converged agreeing problems, p99.9 %.2e, max %.2e" % (name, label, B, st["flags"], st["agree"], st["within"],
+                                                                   st["p999"], st["max"]))
+    assert g["flags"] <= max(3 * o["flags"], B // 20000) and g["agree"] >= min(o["agree"], 0.9999) - 1e-4
+    assert g["within"] >= min(o["within"], 0.9999) - 1e-4 and g["p999"] < 1e-6
+
+
+def test_f32_spread_is_inherent_to_single_precision():
+    """VERDICT r1 item 1c / north_star 'within 1e-4 rad (FP32)'.  The oracle built with every scalar a float
+    (libik_oracle_f32.so: number_t = float, common.hpp:13) is the yardstick: FP32-oracle vs FP64-oracle and FP32-KERNEL
+    vs FP64-oracle must have the same |dq| distribution on the full 65,536 batch.  Measured on the CPU alone
+    (tests/test_oracle_f32.py): median 2.1e-6, p99 6.0e-5, p99.9 3.9e-4, max 4.0e-2 rad -- 0.55 % of the problems
+    exceed 1e-4 rad in ANY single-precision evaluation of this iteration (the foot-pitch direction is observed by the
+    foot-position tasks only through a 4 cm lever, so FK rounding is amplified by ~1/damping^2 there)."""
+    pb, names, poses, q0, tg, o32 = _full_size_case(W.cassie_feet_pelvis_problem, 65536, "standing", "f32")
+    om = oracle_model("cassie")
+    opb = oracle_problem_like(pb, om)
+    q64, ok64, it64, _ = O.dls_batch(opb, q0, tg, nthreads=NT)
+    stats = {}
+    for label, (q, ok, it) in (("oracle f32", O.dls_batch_f32(opb, q0, tg, nthreads=NT)[:3]),
+                               ("kernel f32", (o32["q"].cpu().numpy().T.astype(np.float64),
+                                               o32["success"].cpu().numpy().astype(bool), o32["iters"].cpu().numpy()))):
+        both = ok & ok64 & (it == it64)
+        err = np.abs(q - q64).max(axis=1)[both]
+        st = dict(flags=(ok == ok64).mean(), both=both.mean(), med=np.median(err), p99=np.percentile(err, 99),
+                  p999=np.percentile(err, 99.9), max=err.max(), within=(err < 1e-4).mean())
+        stats[label] = st
+        _log("FP32 study, %s vs oracle f64 (B=65536): flags equal %.5f same steps %.5f |dq| median %.2e p99 %.2e p99.9 %.2e "
+             "max %.2e within 1e-4: %.5f" % (label, st["flags"], st["both"], st["med"], st["p99"], st["p999"], st["max"], st["within"]))
+    o, k = stats["oracle f32"], stats["kernel f32"]
+    # the kernel is as close to the FP64 answer as the reference's own arithmetic in float is (within 1.5x on every
+    # quantile), and both meet the 1e-4 bar on the same >= 99.4 % of the problems
+    assert k["med"] < 1.5 * o["med"] and k["p99"] < 1.5 * o["p99"] and k["p999"] < 1.5 * o["p999"] and k["max"] < 3 * o["max"]
+    assert k["within"] > 0.99 and abs(k["within"] - o["within"]) < 0.003
+    assert k["flags"] > 0.9995 and k["both"] > 0.97
 
 
 @pytest.mark.parametrize("params", ["defaults", "demo"])
