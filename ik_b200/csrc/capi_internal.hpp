@@ -49,6 +49,7 @@ struct ikb_problem {
     bool finalized = false;
     int device = -1;
     int size_class = -1;
+    bool coop_ok = false;   // the team-per-problem kernel's tables fit (dls_coop.cuh); else the thread-per-problem fallback
     int sm_count = 0;
     ikb::DevProblem<double> *d64 = nullptr;
     ikb::DevProblem<float> *d32 = nullptr;
@@ -144,6 +145,10 @@ template <typename T>
 int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io, cudaStream_t s,
                  const ChunkPlan *plan = nullptr, const Merged<T> *merged = nullptr, const double *pik_lambda = nullptr);
 // (pik_lambda != nullptr: ik::pik instead of ik::dls -- per-level damping, table-driven kernel only)
+
+// The table-driven team-per-problem kernel (ikb_coop.cu / dls_coop.cuh) for size class `cls`.
+template <typename T>
+int launch_coop(int cls, const DevProblem<T> *dP, const SolveArgs<T> &a, bool pik, bool constraints, bool shfl, int sm_count, cudaStream_t s);
 
 }  // namespace capi
 }  // namespace ikb

@@ -18,6 +18,20 @@ constexpr int kMaxRows = 48;
 constexpr int kMaxConstraints = 4;   // FrameConstraints
 constexpr int kMaxConstraintRows = 12;
 
+// Index tables of the team-per-problem kernel (dls_coop.cuh), built by build_coop_tables (problem_fill.hpp).
+constexpr int kCoopMaxPaths = 16;
+constexpr int kCoopMaxPairs = 192;
+struct alignas(16) CoopTables {
+    int32_t n_fkj;    // joints whose world placement some task / constraint needs (all joints with a CentreOfMassTask)
+    int32_t npaths;   // root-to-leaf paths covering them
+    int32_t npairs;   // structurally non-zero (task, joint, velocity coordinate) triples of the stacked Jacobian
+    int32_t has_com;
+    uint8_t fkj[kMaxJoints];
+    uint8_t path_len[kCoopMaxPaths];
+    uint8_t path_joint[kCoopMaxPaths][kMaxJoints];
+    uint8_t pair_task[kCoopMaxPairs], pair_joint[kCoopMaxPairs], pair_cc[kCoopMaxPairs];
+};
+
 template <typename T> struct alignas(16) DevProblem {
     int32_t njoints, nq, nv, nframes, ntasks, rows, rows_p0, tsz;
     int32_t parent[kMaxJoints], jtype[kMaxJoints], idx_q[kMaxJoints], idx_v[kMaxJoints];
@@ -45,6 +59,8 @@ template <typename T> struct alignas(16) DevProblem {
     // row_cols[r] = column c of row r may be non-zero, bit r of col_rows[c] likewise (supersets; nv, rows <= 64).
     uint64_t row_cols[kMaxRows];
     uint64_t col_rows[kMaxNq];
+    CoopTables coop;
+    int32_t coop_ok, coop_pad_[3];
 };
 
 constexpr int kMaxSegments = 8;

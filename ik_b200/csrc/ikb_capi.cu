@@ -16,6 +16,7 @@
 
 #include "capi_internal.hpp"
 #include "dls_generic.cuh"
+#include "problem_fill.hpp"
 
 using namespace ikb;
 using namespace ikb::capi;
@@ -45,93 +46,6 @@ struct SizeClass {
     int nj, nv, m;
 };
 const SizeClass kClasses[] = {{10, 8, 6}, {20, 24, 12}, {32, 36, 30}};
-
-template <typename T>
-void fill_dev_problem(const HostProblem &hp, const std::vector<int> &order, const std::vector<int> &used_frames,
-                      DevProblem<T> &P) {
-    const HostModel &m = hp.model;
-    std::memset(&P, 0, sizeof(P));
-    P.njoints = m.njoints();
-    P.nq = m.nq;
-    P.nv = m.nv;
-    P.nframes = (int)used_frames.size();
-    P.ntasks = (int)hp.tasks.size();
-    P.rows = hp.rows();
-    P.rows_p0 = hp.e_size(0);
-    P.nconstraints = (int)hp.constraints.size();
-    P.crows = hp.c_size();
-    for (size_t k = 0; k < hp.constraints.size(); ++k) {
-        auto lf = [&](int fid) { return (int)(std::find(used_frames.begin(), used_frames.end(), fid) - used_frames.begin()); };
-        P.c_frame[k] = lf(hp.constraints[k].frame);
-        P.c_ref[k] = lf(hp.constraints[k].ref);
-        P.c_type[k] = hp.constraints[k].type;
-    }
-    P.nlevels = hp.max_priority_level + 1;
-    for (int l = 0; l < 7; ++l) P.level_rows[l] = l < P.nlevels ? hp.e_size(l) : 0;
-    P.tsz = hp.target_size();
-    for (int j = 0; j < m.njoints(); ++j) {
-        P.parent[j] = m.parent[j];
-        P.jtype[j] = m.jtype[j];
-        P.idx_q[j] = m.idx_q[j];
-        P.idx_v[j] = m.idx_v[j];
-        for (int k = 0; k < 12; ++k) P.placement[j][k] = (T)m.placement[j][k];
-        for (int k = 0; k < 3; ++k) P.axis[j][k] = (T)m.axis[j][k];
-    }
-    double tm = 0;
-    for (int j = 0; j < m.njoints(); ++j) {
-        P.mass[j] = (T)m.mass[j];
-        for (int k = 0; k < 3; ++k) P.com[j][k] = (T)m.com[j][k];
-        if (j >= 1) tm += m.mass[j];
-    }
-    P.total_mass = (T)tm;
-    const double big = (double)std::numeric_limits<T>::max();
-    for (int k = 0; k < m.nq; ++k) {
-        P.lower[k] = (T)std::max(m.lower[k], -big);
-        P.upper[k] = (T)std::min(m.upper[k], big);
-    }
-    for (size_t f = 0; f < used_frames.size(); ++f) {
-        P.f_parent[f] = m.frame_parent[used_frames[f]];
-        for (int k = 0; k < 12; ++k) P.f_placement[f][k] = (T)m.frame_placement[used_frames[f]][k];
-    }
-    auto local_frame = [&](int fid) {
-        return (int)(std::find(used_frames.begin(), used_frames.end(), fid) - used_frames.begin());
-    };
-    for (auto &x : P.row_cols) x = 0;
-    for (auto &x : P.col_rows) x = 0;
-    int row = 0, moff = 0;
-    for (size_t s = 0; s < order.size(); ++s) {
-        const HostTask &t = hp.tasks[order[s]];
-        // columns this task's Jacobian rows can touch
-        uint64_t cols = 0;
-        if (t.kind == IKB_TASK_POSTURE) {
-            for (int i = 0; i < t.type; ++i) cols |= 1ULL << (m.nv - t.type + i);
-        } else if (t.kind == IKB_TASK_COM) {
-            cols = m.nv >= 64 ? ~0ULL : ((1ULL << m.nv) - 1);
-        } else {
-            for (int j = m.frame_parent[t.frame]; j > 0; j = m.parent[j])
-                for (int k = 0; k < HostModel::joint_nv(m.jtype[j]); ++k) cols |= 1ULL << (m.idx_v[j] + k);
-        }
-        for (int i = 0; i < t.dim; ++i) {
-            P.row_cols[row + i] = cols;
-            for (int c = 0; c < m.nv; ++c)
-                if (cols >> c & 1) P.col_rows[c] |= 1ULL << (row + i);
-        }
-        P.t_kind[s] = t.kind;
-        P.t_frame[s] = (t.kind == IKB_TASK_POSTURE || t.kind == IKB_TASK_COM) ? 0 : local_frame(t.frame);
-        P.t_ref[s] = t.kind == IKB_TASK_POSTURE ? 0 : local_frame(t.ref);
-        P.t_type[s] = t.type;
-        P.t_row[s] = row;
-        P.t_dim[s] = t.dim;
-        P.t_toff[s] = hp.target_offset(order[s]);
-        P.t_moff[s] = moff;
-        for (int i = 0; i < t.dim; ++i) P.weight[row + i] = (T)t.weight[i];
-        if (t.kind == IKB_TASK_POSTURE) {
-            for (int i = 0; i < t.type; ++i) P.mask[moff + i] = (T)t.mask[i];
-            moff += t.type;
-        }
-        row += t.dim;
-    }
-}
 
 template <typename T> DevProblem<T> *dev_blob(const ikb_problem *p);
 template <> DevProblem<double> *dev_blob<double>(const ikb_problem *p) { return p->d64; }
@@ -514,19 +428,8 @@ int ikb_problem_finalize(ikb_problem *p, int device) {
     const HostProblem &hp = p->hp;
     const HostModel &m = hp.model;
     if (hp.tasks.empty()) return fail(IKB_ERR_INVALID_ARG, "problem has no tasks");
-    // stacked order: priority level, then insertion order (dls.cpp:18-24)
-    std::vector<int> order(hp.tasks.size());
-    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return hp.tasks[a].priority < hp.tasks[b].priority; });
-    std::vector<int> used;
-    for (const auto &t : hp.tasks)
-        if (t.kind != IKB_TASK_POSTURE)
-            for (int f : {t.kind == IKB_TASK_COM ? t.ref : t.frame, t.ref})
-                if (std::find(used.begin(), used.end(), f) == used.end()) used.push_back(f);
-    for (const auto &c : hp.constraints)
-        for (int f : {c.frame, c.ref})
-            if (std::find(used.begin(), used.end(), f) == used.end()) used.push_back(f);
-    if (used.empty()) used.push_back(0);
+    const std::vector<int> order = stacked_order(hp);
+    const std::vector<int> used = used_frames(hp);
     if ((int)hp.constraints.size() > kMaxConstraints || hp.c_size() > kMaxConstraintRows)
         return fail(IKB_ERR_UNSUPPORTED, "at most 4 frame constraints / 12 constraint rows");
     if (m.njoints() > kMaxJoints || m.nq > kMaxNq || (int)hp.tasks.size() > kMaxTasks || (int)used.size() > kMaxFrames ||
@@ -564,6 +467,7 @@ int ikb_problem_finalize(ikb_problem *p, int device) {
     auto *h32 = new DevProblem<float>();
     fill_dev_problem(hp, order, used, *h64);
     fill_dev_problem(hp, order, used, *h32);
+    p->coop_ok = h64->coop_ok != 0;
     IKB_CUDA(cudaMalloc(&p->d64, sizeof(*h64)));
     IKB_CUDA(cudaMalloc(&p->d32, sizeof(*h32)));
     IKB_CUDA(cudaMemcpy(p->d64, h64, sizeof(*h64), cudaMemcpyHostToDevice));
@@ -605,7 +509,12 @@ int ikb_problem_finalize(ikb_problem *p, int device) {
     }
     p->spec = select_specialized(hp);
     char buf[96];
-    std::snprintf(buf, sizeof buf, "generic<NJ=%d,NV=%d,M=%d>", kClasses[cls].nj, kClasses[cls].nv, kClasses[cls].m);
+    const char *legacy = std::getenv("IKB_GENERIC_LEGACY");
+    const int team[3] = {8, 16, 32};
+    if (p->coop_ok && !(legacy && legacy[0] == '1'))
+        std::snprintf(buf, sizeof buf, "coop<NJ=%d,NV=%d,M=%d,TEAM=%d>", kClasses[cls].nj, kClasses[cls].nv, kClasses[cls].m, team[cls]);
+    else
+        std::snprintf(buf, sizeof buf, "generic<NJ=%d,NV=%d,M=%d>", kClasses[cls].nj, kClasses[cls].nv, kClasses[cls].m);
     p->kernel_name[0] = p->spec ? p->spec->name : buf;
     p->kernel_name[1] = p->kernel_name[0];
     p->finalized = true;

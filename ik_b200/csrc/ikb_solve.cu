@@ -195,6 +195,18 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
         return IKB_OK;
     }
     if (merged) return fail(IKB_ERR_INVALID_ARG, "internal: merged launch on the table-driven kernel");
+    // Table-driven problems: the team-per-problem kernel (dls_coop.cuh; J in shared memory, Gram rows and the factorisation
+    // in registers).  IKB_GENERIC_LEGACY=1 keeps the thread-per-problem local-memory kernel (dls_generic.cuh) for A/B runs;
+    // it is also the fallback for problems beyond the cooperative kernel's table capacities.
+    const char *legacy_env = std::getenv("IKB_GENERIC_LEGACY");
+    if (p->coop_ok && !(legacy_env && legacy_env[0] == '1')) {
+        const char *shfl_env = std::getenv("IKB_COOP_SHFL");
+        const bool shfl = shfl_env ? shfl_env[0] == '1' : true;
+        if (launch_coop<T>(p->size_class, dev_blob<T>(p), a, pik_lambda != nullptr, !p->hp.constraints.empty(), shfl, p->sm_count, s))
+            return cuda_fail(cudaGetLastError(), "team-per-problem kernel launch");
+        g_launches.fetch_add(1);
+        return IKB_OK;
+    }
     auto fn = pik_lambda ? KernelTable<T>::pik(p->size_class) : KernelTable<T>::dls(p->size_class);
     const char *thr_env = std::getenv("IKB_GENERIC_THREADS"), *bps_env = std::getenv("IKB_GENERIC_BLOCKS_PER_SM");
     const int threads = thr_env ? std::max(32, std::min(128, std::atoi(thr_env) / 32 * 32)) : 128;

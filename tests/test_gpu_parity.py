@@ -148,7 +148,7 @@ def kernel_path(request, monkeypatch):
 def _check_path(pb, kernel_path, spec_name):
     pb.finalize(0)
     name = pb.kernel_name()
-    assert (name == spec_name) if kernel_path == "specialised" else name.startswith("generic<"), name
+    assert (name == spec_name) if kernel_path == "specialised" else name.startswith(("coop<", "generic<")), name
 
 
 @pytest.mark.parametrize("B", [1, 33, 4096])
