@@ -7,6 +7,7 @@
 //   build/cassie_ik_demo ik_b200/data/cassie.urdf [ticks]
 //
 // Prints one line per tick: tick, success, iterations, ||e||^2, q[7..10]; and a final "batch" line from ik::dls_batch.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <fstream>
@@ -77,6 +78,33 @@ int main(int argc, char **argv) {
             same += rq[k].q == r.q && rq[k].iterations == r.iterations && rq[k].success == r.success;
         }
         std::printf("queue: %d of 3 merged batches identical to ik::dls_batch\n", same);
+        // several GPUs behind the same call (ikb_multi_*): the batch is cut into one slice per listed device.  With one GPU
+        // in the box the two slices share it -- the sharding logic is the same.
+        const int ndev = ikb_device_count();
+        const ik::dls_batch_result rm = ik::dls_batch(problem, B, q0.data(), tg.data(), std::vector<int>{0, ndev > 1 ? 1 : 0},
+                                                      ik::inverse_kinematics_visitor(), p);
+        std::printf("multi: devices %d sharded batch identical %d\n", ndev, (int)(rm.q == r.q && rm.iterations == r.iterations && rm.success == r.success));
+        // dls_data after a solve (data.hpp:15-28): dq, e, J of the last evaluation; and a visitor that overrides should_stop
+        {
+            struct step_visitor : ik::inverse_kinematics_visitor {   // stop when the step is small instead of the error
+                bool should_stop(const ik::InverseKinematicsProblem &, const std::vector<ik::vector_t> &, const ik::vector_t &dq) const override {
+                    double m = 0;
+                    for (double x : dq) m = std::max(m, std::fabs(x));
+                    return m < 5e-2;
+                }
+                bool is_default_test() const override { return false; }
+            };
+            ik::dls_data d1(problem), d2(problem);
+            problem.get_frame_task("fl")->target.translation() = {0.0, 0.1, -0.6};
+            ik::dls(problem, model.neutral(), d1, ik::inverse_kinematics_visitor(), p);
+            ik::dls(problem, model.neutral(), d2, step_visitor(), p);
+            double e2 = 0, dqmax = 0;
+            for (double x : d1.e[0]) e2 += x * x;
+            for (double x : d2.dq) dqmax = std::max(dqmax, std::fabs(x));
+            std::printf("data: e_rows %d J_entries %d |e|^2-resid %.3e iterations %d | custom stop: success %d iterations %d max|dq| %.6e\n",
+                        (int)d1.e[0].size(), (int)d1.J[0].size(), std::fabs(e2 - d1.residual), d1.info.iterations, (int)d2.success,
+                        d2.info.iterations, dqmax);
+        }
         // the demo's other solver (IKMethod::PIK, cassie.cpp:114-124): one tick with ik::pik and the demo's parameters
         ik::pik_data pdata(problem);  // lambda = 1.0 per priority level (pik.hpp:31)
         ik::pik_parameters pp;

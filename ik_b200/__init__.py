@@ -5,12 +5,12 @@ The package is a thin host-side mirror of the reference's task/solver API over l
 """
 from . import _capi  # noqa: F401  (fails loudly if the CUDA library is missing)
 from .api import (AlignAxisTask, AlignAxisType, CentreOfMassTask, FrameConstraint, FrameTask,
-                  InverseKinematicsProblem, KinematicType, Model,
+                  InverseKinematicsProblem, KinematicType, Model, MultiGPU,
                   PostureTask, SolveQueue, dls, dls_batch, dls_batch_host, dls_data, dls_parameters, fk_batch,
                   inverse_kinematics_visitor, kernel_launch_count, pik, pik_batch, pik_batch_host, pik_data,
                   pik_parameters)
 
-__all__ = ["AlignAxisTask", "AlignAxisType", "CentreOfMassTask", "FrameConstraint", "FrameTask", "InverseKinematicsProblem", "KinematicType", "Model",
+__all__ = ["AlignAxisTask", "AlignAxisType", "CentreOfMassTask", "FrameConstraint", "FrameTask", "InverseKinematicsProblem", "KinematicType", "Model", "MultiGPU",
            "PostureTask", "SolveQueue", "dls", "dls_batch", "dls_batch_host", "dls_data", "dls_parameters", "fk_batch",
            "inverse_kinematics_visitor", "kernel_launch_count", "pik", "pik_batch", "pik_batch_host", "pik_data",
            "pik_parameters"]

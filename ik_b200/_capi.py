@@ -15,6 +15,7 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 
 OK = 0
+ERR_INVALID_ARG = 1
 F64, F32 = 0, 1
 POSITION, ORIENTATION, FULL = 0, 1, 2
 TASK_FRAME, TASK_ALIGN_AXIS, TASK_POSTURE = 0, 1, 2
@@ -32,7 +33,11 @@ class BatchIO(C.Structure):
     _fields_ = [("q0", C.c_void_p), ("q0_elem_stride", C.c_int64), ("q0_batch_stride", C.c_int64),
                 ("targets", C.c_void_p), ("targets_elem_stride", C.c_int64), ("targets_batch_stride", C.c_int64),
                 ("q", C.c_void_p), ("q_elem_stride", C.c_int64), ("q_batch_stride", C.c_int64),
-                ("success", C.c_void_p), ("iters", C.c_void_p), ("resid", C.c_void_p)]
+                ("success", C.c_void_p), ("iters", C.c_void_p), ("resid", C.c_void_p),
+                ("targets_format", C.c_int32), ("reserved_", C.c_int32)]
+
+
+TARGETS_SE3, TARGETS_COMPACT = 0, 1
 
 
 class PikParams(C.Structure):
@@ -94,6 +99,20 @@ SIGNATURES = {
     "ikb_dls_solve_batch": (C.c_int, [_vp, C.c_int, C.POINTER(DlsParams), C.c_int64, C.POINTER(BatchIO), _vp]),
     "ikb_dls_solve_batch_host": (C.c_int, [_vp, C.c_int, C.POINTER(DlsParams), C.c_int64, C.POINTER(BatchIO)]),
     "ikb_dls_solve": (C.c_int, [_vp, C.POINTER(DlsParams), _dp, _dp, _dp, C.POINTER(C.c_int), C.POINTER(C.c_int), _dp]),
+    "ikb_dls_solve_ex": (C.c_int, [_vp, C.POINTER(DlsParams), _dp, _dp, _dp, C.POINTER(C.c_int), C.POINTER(C.c_int), _dp, _dp, _dp, _dp]),
+    "ikb_pik_solve_ex": (C.c_int, [_vp, C.POINTER(PikParams), _dp, _dp, _dp, C.POINTER(C.c_int), C.POINTER(C.c_int), _dp, _dp, _dp, _dp]),
+    "ikb_problem_status_string": (C.c_char_p, [_vp]),
+    "ikb_problem_compact_target_size": (C.c_int, [_vp]),
+    "ikb_problem_task_compact_target_offset": (C.c_int, [_vp, C.c_int]),
+    "ikb_multi_create": (C.c_int, [_vp, _i32p, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "ikb_multi_free": (None, [_vp]),
+    "ikb_multi_device_count": (C.c_int, [_vp]),
+    "ikb_multi_problem": (_vp, [_vp, C.c_int]),
+    "ikb_multi_submit_host": (C.c_int64, [_vp, C.c_int, C.POINTER(DlsParams), C.c_int64, C.POINTER(BatchIO)]),
+    "ikb_multi_wait": (C.c_int, [_vp, C.c_int64]),
+    "ikb_multi_drain": (C.c_int, [_vp]),
+    "ikb_multi_dls_solve_batch_host": (C.c_int, [_vp, C.c_int, C.POINTER(DlsParams), C.c_int64, C.POINTER(BatchIO)]),
+    "ikb_multi_gather_device": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_int64, C.c_int, C.c_int, _vp]),
     "ikb_pik_params_default": (None, [C.POINTER(PikParams)]),
     "ikb_pik_solve_batch": (C.c_int, [_vp, C.c_int, C.POINTER(PikParams), C.c_int64, C.POINTER(BatchIO), _vp]),
     "ikb_pik_solve_batch_host": (C.c_int, [_vp, C.c_int, C.POINTER(PikParams), C.c_int64, C.POINTER(BatchIO)]),

@@ -234,8 +234,14 @@ class pik_parameters:  # pik.hpp:13-18 + pik_data::lambda (pik.hpp:31)
         return p
 
 
-class inverse_kinematics_visitor:  # visitor.hpp:7-24 -- the stop test itself runs in the kernel
+class inverse_kinematics_visitor:  # visitor.hpp:7-24
+    """The stock stop test runs in the kernel (`tolerance` is its squared-norm threshold).  A subclass that overrides
+    should_stop is honoured by dls() / pik(): the iteration loop then runs on the host, one device iteration per step."""
     tolerance = 1e-4
+
+    def should_stop(self, problem, e, dq):
+        """visitor.hpp:15-21: e = list of the weighted error vectors per priority level; true when ||e[0]||^2 < 1e-4."""
+        return float(np.dot(e[0], e[0])) < self.tolerance
 
 
 class InverseKinematicsProblem:  # problem.hpp:9-206
@@ -387,10 +393,53 @@ class InverseKinematicsProblem:  # problem.hpp:9-206
     # ---- device side ----
     def finalize(self, device=0):
         if self._h is not None:
+            if device is not None and self._device is not None and device != self._device:
+                raise ValueError("problem is finalized on cuda:%d; its buffers / tensors must live there (got cuda:%d)"
+                                 % (self._device, device))
             return self
         self._h = self._build_handle(device)
         self._device = device
         return self
+
+    def status_string(self):
+        """Note on the kernel selection (ikb_problem_status_string): why a near-miss of a compiled specialisation fell back
+        to the table-driven kernel; "" when there is nothing to say."""
+        s = capi.lib.ikb_problem_status_string(self._h) if self._h is not None else b""
+        return s.decode() if s else ""
+
+    @property
+    def compact_target_size(self):
+        """Scalars per problem of the compact wire format of the targets (IKB_TARGETS_COMPACT, include/ikb200.h)."""
+        h = self._h if self._h is not None else self._build_handle(None)
+        try:
+            return int(capi.lib.ikb_problem_compact_target_size(h))
+        finally:
+            if h is not self._h:
+                capi.lib.ikb_problem_free(h)
+
+    def compact_targets(self, targets):
+        """SE3 target records [B, tsz] (AoS) -> compact records [B, csz]: per FrameTask Full = unit quaternion (x, y, z, w)
+        + translation, Position = translation (the rotation must be the identity, FrameTask's default target),
+        Orientation = quaternion; other tasks unchanged."""
+        targets = np.asarray(targets, dtype=np.float64)
+        parts, off = [], 0
+        for _, t, _ in self._tasks:
+            n = int(np.asarray(t.target).size)
+            blk = targets[:, off:off + n]
+            off += n
+            if isinstance(t, FrameTask):
+                R, tr = blk[:, :9].reshape(-1, 3, 3), blk[:, 9:12]
+                if t.type == KinematicType.Position:
+                    if not np.allclose(R, np.eye(3)[None], atol=0):
+                        raise ValueError("compact Position targets carry no rotation: the SE3 target's rotation must be the identity")
+                    parts.append(tr)
+                elif t.type == KinematicType.Orientation:
+                    parts.append(_rot_to_quat(R))
+                else:
+                    parts.append(np.concatenate([_rot_to_quat(R), tr], axis=1))
+            else:
+                parts.append(blk)
+        return np.ascontiguousarray(np.concatenate(parts, axis=1))
 
     def kernel_name(self, dtype="f64"):
         n = capi.lib.ikb_problem_kernel_name(self._h, _DT[dtype][0])
@@ -400,62 +449,166 @@ class InverseKinematicsProblem:  # problem.hpp:9-206
 _DT = {"f64": (capi.F64, np.float64), "f32": (capi.F32, np.float32)}
 
 
+def _rot_to_quat(R):
+    """Rotation matrices [B, 3, 3] -> unit quaternions [B, 4] (x, y, z, w), w >= 0 (Shepperd's method, vectorised)."""
+    R = np.asarray(R, dtype=np.float64)
+    B = R.shape[0]
+    q = np.zeros((B, 4))
+    tr = R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2]
+    cand = np.stack([R[:, 0, 0], R[:, 1, 1], R[:, 2, 2], tr], axis=1)
+    k = cand.argmax(axis=1)
+    for i in range(3):
+        m = k == i
+        if not m.any():
+            continue
+        j, l = (i + 1) % 3, (i + 2) % 3
+        s_ = np.sqrt(np.maximum(1.0 + R[m, i, i] - R[m, j, j] - R[m, l, l], 0)) * 2
+        q[m, i] = 0.25 * s_
+        q[m, j] = (R[m, j, i] + R[m, i, j]) / s_
+        q[m, l] = (R[m, l, i] + R[m, i, l]) / s_
+        q[m, 3] = (R[m, l, j] - R[m, j, l]) / s_
+    m = k == 3
+    if m.any():
+        s_ = np.sqrt(np.maximum(tr[m] + 1.0, 0)) * 2
+        q[m, 3] = 0.25 * s_
+        q[m, 0] = (R[m, 2, 1] - R[m, 1, 2]) / s_
+        q[m, 1] = (R[m, 0, 2] - R[m, 2, 0]) / s_
+        q[m, 2] = (R[m, 1, 0] - R[m, 0, 1]) / s_
+    q *= np.where(q[:, 3:4] < 0, -1.0, 1.0)
+    return q / np.linalg.norm(q, axis=1, keepdims=True)
+
+
+def _host_io(problem, q0, targets, dtype, layout, out, compact=False, outputs=("q", "success", "iters", "resid")):
+    """ikb_batch_io over HOST arrays.  layout "soa": q0 [nq, B], targets [tsz, B]; "aos": q0 [B, nq], targets [B, tsz]; a
+    q0 of shape (nq,) is ONE initial guess for the whole batch (batch_stride = 0).  compact: `targets` holds the compact
+    wire format (csz scalars per problem).  outputs: which of success / iters / resid come back (q always does).
+    Returns (io, B, result dict, keep-alive tuple)."""
+    code, npdt = _DT[dtype]
+    nq = problem.model().nq
+    tsz = problem.compact_target_size if compact else problem.target_size
+    assert q0.dtype == npdt and targets.dtype == npdt and q0.flags.c_contiguous and targets.flags.c_contiguous
+    if layout == "soa":
+        B = targets.shape[1]
+        assert targets.shape == (tsz, B)
+        strides = lambda k: (B, 1)
+        qshape = (nq, B)
+    else:
+        B = targets.shape[0]
+        assert targets.shape == (B, tsz)
+        strides = lambda k: (1, k)
+        qshape = (B, nq)
+    q0_strides = (1, 0) if q0.ndim == 1 else strides(nq)
+    assert q0.shape == ((nq,) if q0.ndim == 1 else qshape)
+    out = out or {}
+
+    def buf(key, shape, dt):
+        if key != "q" and key not in outputs:
+            return None
+        a = out.get(key)
+        if a is None:
+            a = np.empty(shape, dtype=dt)
+        assert a.shape == shape and a.dtype == dt and a.flags.c_contiguous, "output %r: wrong shape / dtype / layout" % key
+        return a
+
+    q = buf("q", qshape, npdt)
+    success, iters, resid = buf("success", (B,), np.uint8), buf("iters", (B,), np.int32), buf("resid", (B,), npdt)
+    ptr = lambda a: a.ctypes.data if a is not None else None
+    io = capi.BatchIO(q0.ctypes.data, *q0_strides, targets.ctypes.data, *strides(tsz), q.ctypes.data, *strides(nq),
+                      ptr(success), ptr(iters), ptr(resid), capi.TARGETS_COMPACT if compact else capi.TARGETS_SE3, 0)
+    res = dict(q=q, success=success, iters=iters, resid=resid)
+    return io, B, res, (q0, targets, res)
+
+
 class dls_data:  # dls.hpp:34-65 / data.hpp:8-28
     def __init__(self, problem):
+        m = problem.model()
+        rows = sum(int(t.dimension()) for _, t, _ in problem._tasks)
         self.success = False
-        self.q = np.zeros(problem.model().nq)
+        self.q = np.zeros(m.nq)
+        self.dq = np.zeros(m.nv)            # problem_data::dq: the last step direction computed (dls.cpp:52)
+        self.e = np.zeros(rows)             # stacked weighted task errors of the last evaluation (data.hpp:24, dls.cpp:18-24)
+        self.J = np.zeros((rows, m.nv))     # stacked weighted task Jacobian of the last evaluation
         self.iterations = 0  # dls_info::iterations (dls.hpp:71-74), never filled by the reference
         self.residual = 0.0
 
 
-def dls(problem, q0, data=None, visitor=None, p=None):
-    """vector_t ik::dls(problem, q0, data, visitor, p) (dls.hpp:111-114): one FP64 solve on the GPU."""
-    problem.finalize(problem._device or 0)
-    p = p or dls_parameters()
-    data = data if data is not None else dls_data(problem)
+def _solve_one(problem, q0, prm, pik_prm=None, want=True):
+    m = problem.model()
+    rows = sum(int(t.dimension()) for _, t, _ in problem._tasks)
     q0 = _as_f64(q0)
     tg = _as_f64(problem.gather_targets())
-    q = np.zeros(problem.model().nq)
+    q, dq, e, J = np.zeros(m.nq), np.zeros(m.nv), np.zeros(rows), np.zeros((rows, m.nv))
     ok, it, res = C.c_int(0), C.c_int(0), C.c_double(0)
-    prm = p.c()
-    capi.check(capi.lib.ikb_dls_solve(problem._h, C.byref(prm), _dptr(q0), _dptr(tg), _dptr(q), C.byref(ok),
-                                      C.byref(it), C.byref(res)), "ikb_dls_solve")
-    data.q, data.success, data.iterations, data.residual = q, bool(ok.value), it.value, res.value
+    aux = (_dptr(dq), _dptr(e), _dptr(J)) if want else (None, None, None)
+    if pik_prm is None:
+        capi.check(capi.lib.ikb_dls_solve_ex(problem._h, C.byref(prm), _dptr(q0), _dptr(tg), _dptr(q), C.byref(ok), C.byref(it),
+                                             C.byref(res), *aux), "ikb_dls_solve_ex")
+    else:
+        capi.check(capi.lib.ikb_pik_solve_ex(problem._h, C.byref(pik_prm), _dptr(q0), _dptr(tg), _dptr(q), C.byref(ok), C.byref(it),
+                                             C.byref(res), *aux), "ikb_pik_solve_ex")
+    return q, bool(ok.value), it.value, res.value, dq, e, J
+
+
+def _stepped(problem, q0, data, visitor, p, pik):
+    """A visitor that OVERRIDES should_stop (visitor.hpp:15-21 is virtual-by-convention in the reference): the loop of
+    dls.cpp:14-74 runs on the host, one device iteration (evaluate, dq, integrate, clamp) per step, and the user's stop
+    test sees e and dq exactly where the reference calls it (dls.cpp:61)."""
+    q = _as_f64(q0).copy()
+    data.success = False
+    levels = problem.max_priority_level() + 1
+    row_level = np.concatenate([np.full(int(t.dimension()), prio) for _, t, prio in sorted(problem._tasks, key=lambda x: x[2])])
+    for it in range(p.max_iterations):
+        if pik:
+            one = pik_parameters(max_iterations=1, step_length=p.step_length, lambdas=p.lambdas, tolerance=-1.0)
+            qn, _, _, res, dq, e, J = _solve_one(problem, q, None, one.c())
+        else:
+            one = dls_parameters(max_iterations=1, step_length=p.step_length, damping=p.damping, tolerance=-1.0)
+            qn, _, _, res, dq, e, J = _solve_one(problem, q, one.c())
+        data.dq, data.e, data.J, data.residual, data.iterations = dq, e, J, res, it
+        if visitor.should_stop(problem, [e[row_level == l] for l in range(levels)], dq):   # dls.cpp:61-64
+            data.success = True
+            data.q = q
+            return q
+        q = qn
+    data.iterations = p.max_iterations
+    data.q = q
     return q
 
 
-def dls_batch_host(problem, q0, targets, p=None, dtype="f64", layout="soa", out=None):
+def dls(problem, q0, data=None, visitor=None, p=None):
+    """vector_t ik::dls(problem, q0, data, visitor, p) (dls.hpp:111-114): one FP64 solve on the GPU.  `data` receives what
+    the reference leaves in dls_data: success, q, dq, e, J (data.hpp:15-28).  A visitor whose class overrides should_stop
+    is honoured (host-stepped loop); the stock visitor's test runs in the kernel with its `tolerance`."""
+    problem.finalize(problem._device if problem._device is not None else 0)
+    p = p or dls_parameters()
+    data = data if data is not None else dls_data(problem)
+    if visitor is not None and type(visitor).should_stop is not inverse_kinematics_visitor.should_stop:
+        return _stepped(problem, q0, data, visitor, p, False)
+    if visitor is not None:
+        p = dls_parameters(max_iterations=p.max_iterations, step_length=p.step_length, damping=p.damping, tolerance=visitor.tolerance)
+    q, ok, it, res, dq, e, J = _solve_one(problem, q0, p.c())
+    data.q, data.success, data.iterations, data.residual, data.dq, data.e, data.J = q, ok, it, res, dq, e, J
+    return q
+
+
+def dls_batch_host(problem, q0, targets, p=None, dtype="f64", layout="soa", out=None, compact=False,
+                   outputs=("q", "success", "iters", "resid")):
     """Batched ik::dls on HOST arrays (numpy, ideally pinned): H2D + solve + D2H inside the call.
 
-    layout "soa": q0 [nq, B], targets [tsz, B]; "aos": q0 [B, nq], targets [B, tsz].  Returns dict(q, success,
-    iters, resid) in the same layout.  ``out`` may hold preallocated result arrays."""
-    problem.finalize(problem._device or 0)
+    layout "soa": q0 [nq, B], targets [tsz, B]; "aos": q0 [B, nq], targets [B, tsz]; q0 of shape (nq,) = one initial guess
+    for the whole batch.  compact=True: `targets` is the compact wire format (InverseKinematicsProblem.compact_targets).
+    Returns dict(q, success, iters, resid) in the same layout (None for outputs not asked for).  ``out`` may hold
+    preallocated result arrays."""
+    problem.finalize(problem._device if problem._device is not None else 0)
     p = p or dls_parameters()
     code, npdt = _DT[dtype]
-    nq, tsz = problem.model().nq, problem.target_size
     q0 = np.ascontiguousarray(q0, dtype=npdt)
     targets = np.ascontiguousarray(targets, dtype=npdt)
-    if layout == "soa":
-        B = q0.shape[1]
-        assert q0.shape == (nq, B) and targets.shape == (tsz, B)
-        strides = lambda k: (B, 1)
-        qshape = (nq, B)
-    else:
-        B = q0.shape[0]
-        assert q0.shape == (B, nq) and targets.shape == (B, tsz)
-        strides = lambda k: (1, k)
-        qshape = (B, nq)
-    out = out or {}
-    q = out.get("q") if out.get("q") is not None else np.empty(qshape, dtype=npdt)
-    success = out.get("success") if out.get("success") is not None else np.empty(B, dtype=np.uint8)
-    iters = out.get("iters") if out.get("iters") is not None else np.empty(B, dtype=np.int32)
-    resid = out.get("resid") if out.get("resid") is not None else np.empty(B, dtype=npdt)
-    io = capi.BatchIO(q0.ctypes.data, *strides(nq), targets.ctypes.data, *strides(tsz), q.ctypes.data, *strides(nq),
-                      success.ctypes.data, iters.ctypes.data, resid.ctypes.data)
+    io, B, res, _ = _host_io(problem, q0, targets, dtype, layout, out, compact, outputs)
     prm = p.c()
     capi.check(capi.lib.ikb_dls_solve_batch_host(problem._h, code, C.byref(prm), B, C.byref(io)),
                "ikb_dls_solve_batch_host")
-    return dict(q=q, success=success, iters=iters, resid=resid)
+    return res
 
 
 def dls_batch(problem, q0, targets, p=None, out=None, stream=None):
@@ -467,12 +620,16 @@ def dls_batch(problem, q0, targets, p=None, out=None, stream=None):
 
     p = p or dls_parameters()
     nq, tsz = problem.model().nq, problem.target_size
-    assert q0.is_cuda and targets.is_cuda and q0.dtype == targets.dtype
-    problem.finalize(q0.device.index or 0)
+    assert q0.is_cuda and targets.is_cuda and q0.dtype == targets.dtype and q0.device == targets.device
+    problem.finalize(q0.device.index or 0)   # raises when the problem lives on another device
     dtype = "f64" if q0.dtype == torch.float64 else "f32"
     B = q0.shape[1]
     assert q0.shape == (nq, B) and targets.shape == (tsz, B) and q0.is_contiguous() and targets.is_contiguous()
     out = out or {}
+    for k, shape, dt in (("q", (nq, B), q0.dtype), ("success", (B,), torch.uint8), ("iters", (B,), torch.int32), ("resid", (B,), q0.dtype)):
+        o = out.get(k)
+        if o is not None and not (o.device == q0.device and tuple(o.shape) == shape and o.dtype == dt and o.is_contiguous()):
+            raise ValueError("out[%r] must be a contiguous %s tensor of shape %s on %s" % (k, dt, shape, q0.device))
     q = out.get("q") if out.get("q") is not None else torch.empty((nq, B), dtype=q0.dtype, device=q0.device)
     success = out.get("success") if out.get("success") is not None else torch.empty(B, dtype=torch.uint8, device=q0.device)
     iters = out.get("iters") if out.get("iters") is not None else torch.empty(B, dtype=torch.int32, device=q0.device)
@@ -535,17 +692,18 @@ class pik_data(dls_data):  # pik.hpp:27-49: the user-owned per-solve record (P, 
 
 
 def pik(problem, q0, data=None, visitor=None, p=None):
-    """vector_t ik::pik(problem, q0, data, visitor, p) (pik.hpp:51-54): one problem, targets from the tasks' `target` members."""
+    """vector_t ik::pik(problem, q0, data, visitor, p) (pik.hpp:51-54): one problem, targets from the tasks' `target`
+    members; `data` receives success, q, dq, e, J like dls()."""
+    problem.finalize(problem._device if problem._device is not None else 0)
     p = p or pik_parameters()
+    data = data if data is not None else pik_data(problem)
+    if visitor is not None and type(visitor).should_stop is not inverse_kinematics_visitor.should_stop:
+        return _stepped(problem, q0, data, visitor, p, True)
     if visitor is not None:
-        p.tolerance = visitor.tolerance
-    out = pik_batch_host(problem, np.asarray(q0, dtype=np.float64)[None, :], problem.gather_targets()[None, :], p)
-    if data is not None:
-        data.success = bool(out["success"][0])
-        data.iterations = int(out["iters"][0])
-        data.residual = float(out["resid"][0])
-        data.q = out["q"][0].copy()
-    return out["q"][0].copy()
+        p = pik_parameters(max_iterations=p.max_iterations, step_length=p.step_length, lambdas=p.lambdas, tolerance=visitor.tolerance)
+    q, ok, it, res, dq, e, J = _solve_one(problem, q0, None, p.c())
+    data.q, data.success, data.iterations, data.residual, data.dq, data.e, data.J = q, ok, it, res, dq, e, J
+    return q
 
 
 class SolveQueue:
@@ -596,41 +754,24 @@ class SolveQueue:
                              "ikb_queue_submit")
         res = dict(q=q, success=success, iters=iters, resid=resid)
         self._keep[t] = (q0, targets, res)
+        self._prune(t)
         return t, res
 
-    def submit_host(self, q0, targets, p=None, dtype="f64", layout="soa", out=None):
-        """Host arrays (numpy; pinned -- ikb_host_alloc -- for the copies to overlap), layouts as dls_batch_host."""
-        problem = self._problem
+    def submit_host(self, q0, targets, p=None, dtype="f64", layout="soa", out=None, compact=False,
+                    outputs=("q", "success", "iters", "resid")):
+        """Host arrays (numpy; pinned -- ikb_host_alloc -- for the copies to overlap), arguments as dls_batch_host."""
         p = p or dls_parameters()
-        code, npdt = _DT[dtype]
-        nq, tsz = problem.model().nq, problem.target_size
-        assert q0.dtype == npdt and targets.dtype == npdt and q0.flags.c_contiguous and targets.flags.c_contiguous
-        if layout == "soa":
-            B = targets.shape[1]
-            assert targets.shape == (tsz, B)
-            strides = lambda k: (B, 1)
-            qshape = (nq, B)
-        else:
-            B = targets.shape[0]
-            assert targets.shape == (B, tsz)
-            strides = lambda k: (1, k)
-            qshape = (B, nq)
-        # q0 of shape (nq,): ONE initial guess for the whole batch (batch_stride = 0, include/ikb200.h) -- nq values cross
-        # the host link instead of B * nq
-        q0_strides = (1, 0) if q0.ndim == 1 else strides(nq)
-        assert q0.shape == ((nq,) if q0.ndim == 1 else qshape)
-        out = out or {}
-        q = out.get("q") if out.get("q") is not None else np.empty(qshape, dtype=npdt)
-        success = out.get("success") if out.get("success") is not None else np.empty(B, dtype=np.uint8)
-        iters = out.get("iters") if out.get("iters") is not None else np.empty(B, dtype=np.int32)
-        resid = out.get("resid") if out.get("resid") is not None else np.empty(B, dtype=npdt)
-        io = capi.BatchIO(q0.ctypes.data, *q0_strides, targets.ctypes.data, *strides(tsz), q.ctypes.data, *strides(nq),
-                          success.ctypes.data, iters.ctypes.data, resid.ctypes.data)
+        io, B, res, keep = _host_io(self._problem, q0, targets, dtype, layout, out, compact, outputs)
         prm = p.c()
-        t = capi.check_index(capi.lib.ikb_queue_submit_host(self._h, code, C.byref(prm), B, C.byref(io)), "ikb_queue_submit_host")
-        res = dict(q=q, success=success, iters=iters, resid=resid)
-        self._keep[t] = (q0, targets, res)
+        t = capi.check_index(capi.lib.ikb_queue_submit_host(self._h, _DT[dtype][0], C.byref(prm), B, C.byref(io)), "ikb_queue_submit_host")
+        self._keep[t] = keep
+        self._prune(t)
         return t, res
+
+    def _prune(self, t):
+        # buffers of batches that left the pipeline long ago (callers that only use wait_on_stream never pop them)
+        for old in [k for k in self._keep if k < t - 64]:
+            del self._keep[old]
 
     def wait(self, ticket):
         capi.check(capi.lib.ikb_queue_wait(self._h, ticket), "ikb_queue_wait")
@@ -648,6 +789,72 @@ class SolveQueue:
     def drain(self):
         capi.check(capi.lib.ikb_queue_drain(self._h), "ikb_queue_drain")
         self._keep.clear()
+
+
+class MultiGPU:
+    """Several GPUs behind one handle (ikb_multi_*, include/ikb200.h): a HOST batch is cut into contiguous slices
+    [r B / G, (r + 1) B / G), slice r is staged, solved and read back on device r -- all devices concurrently
+    under the calling thread -- and the results land in the caller's arrays: no gather, no collective.
+
+        multi = ik.MultiGPU(problem, devices=[0, 1, 2, 3])
+        out = multi.dls_batch_host(q0, targets)                  # blocking
+        t, out = multi.submit_host(q0_k, targets_k); ...; multi.wait(t)   # pipelined, as SolveQueue
+    """
+
+    def __init__(self, problem, devices=None, depth=4, merge=1):
+        if devices is None:
+            devices = list(range(capi.lib.ikb_device_count()))
+        self._problem = problem
+        self.devices = list(devices)
+        h = problem._h if problem._h is not None else problem._build_handle(None)
+        self._h = C.c_void_p()
+        dev = np.asarray(self.devices, dtype=np.int32)
+        try:
+            rc = capi.lib.ikb_multi_create(h, dev.ctypes.data_as(C.POINTER(C.c_int32)), len(dev), depth, merge, C.byref(self._h))
+            if rc != capi.OK:
+                capi.lib.ikb_multi_free(self._h)
+                self._h = None
+                capi.check(rc, "ikb_multi_create")
+        finally:
+            if h is not problem._h:
+                capi.lib.ikb_problem_free(h)
+        self._keep = {}
+
+    def __del__(self):
+        if getattr(self, "_h", None) and capi is not None and getattr(capi, "lib", None) is not None:
+            capi.lib.ikb_multi_free(self._h)
+            self._h = None
+
+    def kernel_name(self, index=0, dtype="f64"):
+        n = capi.lib.ikb_problem_kernel_name(capi.lib.ikb_multi_problem(self._h, index), _DT[dtype][0])
+        return n.decode() if n else None
+
+    def submit_host(self, q0, targets, p=None, dtype="f64", layout="soa", out=None, compact=False,
+                    outputs=("q", "success", "iters", "resid")):
+        p = p or dls_parameters()
+        io, B, res, keep = _host_io(self._problem, q0, targets, dtype, layout, out, compact, outputs)
+        prm = p.c()
+        t = capi.check_index(capi.lib.ikb_multi_submit_host(self._h, _DT[dtype][0], C.byref(prm), B, C.byref(io)), "ikb_multi_submit_host")
+        self._keep[t] = keep
+        for old in [k for k in self._keep if k < t - 64]:
+            del self._keep[old]
+        return t, res
+
+    def wait(self, ticket):
+        capi.check(capi.lib.ikb_multi_wait(self._h, ticket), "ikb_multi_wait")
+        return self._keep.pop(ticket, (None, None, None))[2]
+
+    def drain(self):
+        capi.check(capi.lib.ikb_multi_drain(self._h), "ikb_multi_drain")
+        self._keep.clear()
+
+    def dls_batch_host(self, q0, targets, p=None, dtype="f64", layout="soa", out=None, compact=False,
+                       outputs=("q", "success", "iters", "resid")):
+        npdt = _DT[dtype][1]
+        t, res = self.submit_host(np.ascontiguousarray(q0, dtype=npdt), np.ascontiguousarray(targets, dtype=npdt), p, dtype, layout,
+                                  out, compact, outputs)
+        self.wait(t)
+        return res
 
 
 def fk_batch(problem, q, frames, out=None, stream=None):

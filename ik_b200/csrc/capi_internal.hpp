@@ -36,6 +36,18 @@ struct SolveScratch {
 template <typename T> struct Staging {
     T *q0 = nullptr, *targets = nullptr, *q = nullptr, *resid = nullptr;
     size_t q0_cap = 0, tg_cap = 0, q_cap = 0, b_cap = 0;
+    T *compact = nullptr;  // IKB_TARGETS_COMPACT: the wire-format targets as copied in; `targets` receives the SE3 expansion
+    size_t compact_cap = 0;
+};
+
+// Compact wire format of the targets (include/ikb200.h): per task (insertion order) what to expand and where.
+struct ExpandTable {
+    int ntasks = 0;
+    int mode[kMaxTasks] = {};   // 0: copy `n` scalars; 1: quaternion + translation -> SE3; 2: translation -> (I, p); 3: quaternion -> (R, 0)
+    int n[kMaxTasks] = {};
+    int coff[kMaxTasks] = {};   // offset in the compact record
+    int toff[kMaxTasks] = {};   // offset in the SE3 record
+    int csz = 0, tsz = 0;
 };
 }  // namespace capi
 }  // namespace ikb
@@ -58,8 +70,12 @@ struct ikb_problem {
     float *d_frame_pl32 = nullptr;
     unsigned long long *d_tickets = nullptr;
     std::atomic<unsigned> ticket_next{0};
+    cudaEvent_t ticket_ev[ikb::capi::kTicketSlots] = {};  // end of the last launch that used the slot's counters (any stream)
     ikb::capi::SolveScratch scratch[ikb::capi::kScratchSlots];
+    std::vector<void *> retired;   // scratch buffers replaced by larger ones: freed with the handle, never while in flight
     std::mutex scratch_mu;
+    ikb::capi::ExpandTable expand;
+    std::string status;            // ikb_problem_status_string
     const ikb::SpecializedKernel *spec = nullptr;
     std::vector<double> weight_stacked;  // Task::weighting() rows in stacked order (constants of the specialised kernels)
     std::vector<double> mask_stacked;    // posture masks per row, 1 for the rows of other tasks
@@ -106,6 +122,74 @@ int check_solve_args(const ikb_problem *p, int dtype, const ikb_dls_params *prm,
 inline size_t view_extent(int64_t n_elem, int64_t es, int64_t bs, int64_t B) {
     return (size_t)((n_elem - 1) * es + (B - 1) * bs + 1);
 }
+
+// HOST views (include/ikb200.h): SoA rows, AoS records or a broadcast.  The device staging copy is always DENSE in the
+// same orientation -- only the payload crosses PCIe, whatever gaps the caller's view has.
+enum ViewKind { VIEW_SOA = 0, VIEW_AOS = 1, VIEW_BCAST = 2, VIEW_BAD = 3 };
+struct HostView {
+    const void *base = nullptr;
+    long long es = 0, bs = 0;
+    int n = 0;
+    ViewKind kind = VIEW_BAD;
+    // strides of the dense device copy
+    long long dev_es(long long B) const { return kind == VIEW_SOA ? B : 1; }
+    long long dev_bs() const { return kind == VIEW_SOA ? 1 : (kind == VIEW_AOS ? n : 0); }
+    size_t dev_count(long long B) const { return kind == VIEW_BCAST ? (size_t)n : (size_t)n * (size_t)B; }
+};
+inline HostView host_view(const void *base, long long es, long long bs, int n, long long B, bool input) {
+    HostView v;
+    v.base = base; v.es = es; v.bs = bs; v.n = n;
+    if (n <= 0) v.kind = VIEW_AOS;
+    else if (bs == 0) v.kind = (input && es >= 1) ? VIEW_BCAST : VIEW_BAD;
+    else if (es == 1 && bs >= n) v.kind = VIEW_AOS;
+    else if (bs == 1 && es >= B) v.kind = VIEW_SOA;
+    else v.kind = VIEW_BAD;
+    return v;
+}
+// Host -> device copy of batch slice [b0, b1) of `v` into its dense staging copy `dst` (`first`: broadcasts travel once).
+template <typename T> int copy_view_in(T *dst, const HostView &v, long long B, long long b0, long long b1, bool first, cudaStream_t s) {
+    if (v.n <= 0 || b1 <= b0) return IKB_OK;
+    const T *src = (const T *)v.base;
+    if (v.kind == VIEW_BCAST) {
+        if (!first) return IKB_OK;
+        if (v.es == 1) IKB_CUDA(cudaMemcpyAsync(dst, src, (size_t)v.n * sizeof(T), cudaMemcpyHostToDevice, s));
+        else IKB_CUDA(cudaMemcpy2DAsync(dst, sizeof(T), src, (size_t)v.es * sizeof(T), sizeof(T), (size_t)v.n, cudaMemcpyHostToDevice, s));
+    } else if (v.kind == VIEW_SOA) {
+        if (v.es == B && b0 == 0 && b1 == B) IKB_CUDA(cudaMemcpyAsync(dst, src, (size_t)v.n * (size_t)B * sizeof(T), cudaMemcpyHostToDevice, s));
+        else IKB_CUDA(cudaMemcpy2DAsync(dst + b0, (size_t)B * sizeof(T), src + b0, (size_t)v.es * sizeof(T), (size_t)(b1 - b0) * sizeof(T),
+                                        (size_t)v.n, cudaMemcpyHostToDevice, s));
+    } else {
+        if (v.bs == v.n) IKB_CUDA(cudaMemcpyAsync(dst + b0 * v.n, src + b0 * v.n, (size_t)(b1 - b0) * v.n * sizeof(T), cudaMemcpyHostToDevice, s));
+        else IKB_CUDA(cudaMemcpy2DAsync(dst + b0 * v.n, (size_t)v.n * sizeof(T), src + b0 * v.bs, (size_t)v.bs * sizeof(T), (size_t)v.n * sizeof(T),
+                                        (size_t)(b1 - b0), cudaMemcpyHostToDevice, s));
+    }
+    return IKB_OK;
+}
+// Device -> host copy of the dense staging copy `src` into the caller's view.
+template <typename T> int copy_view_out(const HostView &v, const T *src, long long B, cudaStream_t s) {
+    if (v.n <= 0 || B <= 0) return IKB_OK;
+    T *dst = (T *)v.base;
+    if (v.kind == VIEW_SOA) {
+        if (v.es == B) IKB_CUDA(cudaMemcpyAsync(dst, src, (size_t)v.n * (size_t)B * sizeof(T), cudaMemcpyDeviceToHost, s));
+        else IKB_CUDA(cudaMemcpy2DAsync(dst, (size_t)v.es * sizeof(T), src, (size_t)B * sizeof(T), (size_t)B * sizeof(T), (size_t)v.n, cudaMemcpyDeviceToHost, s));
+    } else {
+        if (v.bs == v.n) IKB_CUDA(cudaMemcpyAsync(dst, src, (size_t)v.n * (size_t)B * sizeof(T), cudaMemcpyDeviceToHost, s));
+        else IKB_CUDA(cudaMemcpy2DAsync(dst, (size_t)v.bs * sizeof(T), src, (size_t)v.n * sizeof(T), (size_t)v.n * sizeof(T), (size_t)B, cudaMemcpyDeviceToHost, s));
+    }
+    return IKB_OK;
+}
+
+// The three views of a host batch, classified; IKB_ERR_INVALID_ARG for stridings the host entry points do not take.
+struct HostViews {
+    HostView q0, tg, q;
+    bool compact = false;
+};
+int classify_host_views(const ikb_problem *p, int64_t B, const ikb_batch_io *io, HostViews *out);
+// Stage the inputs of batch slice [b0, b1) on stream `s` (copy-in and, for compact targets, the SE3 expansion).
+template <typename T> int stage_inputs(const ikb_problem *p, Staging<T> &st, const HostViews &hv, long long B, long long b0, long long b1,
+                                       bool first, cudaStream_t s);
+// Make sure the staging buffers of `st` hold a batch of B problems; fills the device view `dio` (pointers + dense strides).
+template <typename T> int prepare_staging(const ikb_problem *p, Staging<T> &st, const HostViews &hv, long long B, ikb_batch_io *dio);
 template <typename T> int ensure(T *&ptr, size_t &cap, size_t need) {
     if (need <= cap) return IKB_OK;
     if (ptr) cudaFree(ptr);
@@ -141,9 +225,14 @@ bool two_phase(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, int *
 
 // Enqueue ik::dls for B problems on stream `s`: picks the kernels (specialised BULK + TAIL pair, latency configuration,
 // team kernel, generic kernel) and the scratch.  `io` holds DEVICE pointers (nullptr for a merged launch).
+// Extra outputs of the *_solve_ex calls (device pointers, [B][nv] / [B][rows] / [B][rows][nv]); forces the table-driven kernel.
+template <typename T> struct SolveAux {
+    T *dq = nullptr, *e = nullptr, *J = nullptr;
+};
 template <typename T>
 int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io, cudaStream_t s,
-                 const ChunkPlan *plan = nullptr, const Merged<T> *merged = nullptr, const double *pik_lambda = nullptr);
+                 const ChunkPlan *plan = nullptr, const Merged<T> *merged = nullptr, const double *pik_lambda = nullptr,
+                 const SolveAux<T> *aux = nullptr);
 // (pik_lambda != nullptr: ik::pik instead of ik::dls -- per-level damping, table-driven kernel only)
 
 // The table-driven team-per-problem kernel (ikb_coop.cu / dls_coop.cuh) for size class `cls`.

@@ -30,6 +30,9 @@ struct alignas(16) CoopTables {
     uint8_t path_len[kCoopMaxPaths];
     uint8_t path_joint[kCoopMaxPaths][kMaxJoints];
     uint8_t pair_task[kCoopMaxPairs], pair_joint[kCoopMaxPairs], pair_cc[kCoopMaxPairs];
+    // used frame f (index into f_parent / f_placement): 1 = its placement on the supporting joint is the identity (the
+    // joint's own frame, `universe`), so oMf = oMi[parent] needs no product; 2 = it is `universe` itself (oMf = identity)
+    uint8_t f_ident[kMaxFrames];
 };
 
 template <typename T> struct alignas(16) DevProblem {
@@ -99,6 +102,9 @@ template <typename T> struct SolveArgs {
     int *iters_ws;                    // step counts of suspended problems (the caller's `iters` or scratch)
     // ik::pik (generic kernel only): squared damping of every priority level (pik_data::lambda, pik.hpp:31)
     T pik_lambda2[7];
+    // ikb_dls_solve_ex / ikb_pik_solve_ex (team-per-problem kernel only): dls_data::dq [B][nv], stacked e [B][rows] and
+    // J [B][rows][nv] of the last evaluation (data.hpp:15-28); NULL = not wanted
+    T *aux_dq, *aux_e, *aux_J;
     // Merged launch: `nseg` > 0 batches, sorted by `begin`, B = their total size; q0 ... resid above are then unused and
     // iters_ws / list are indexed by the launch-wide problem index.  Unused entries have begin = LLONG_MAX.  The table
     // travels in the kernel parameters: the lookup is a handful of constant-bank compares, no memory traffic.

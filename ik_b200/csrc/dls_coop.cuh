@@ -67,7 +67,7 @@ template <typename T, class Cfg, bool EXTRA> struct alignas(16) CoopScratch {
     T e[Cfg::M + 2], y[Cfg::M + 2];
     T dq[Cfg::NV];
     T piv[2][Cfg::M + 2];     // SHFL = false: pivot column (+ right-hand side entry), double-buffered
-    T ms[Cfg::NJ], mc[Cfg::NJ][3], ctot[4];   // CentreOfMassTask: subtree mass, first moment, whole-body first moment
+    T ms[EXTRA ? Cfg::NJ : 1], mc[EXTRA ? Cfg::NJ : 1][3], ctot[4];   // CentreOfMassTask: subtree mass, first moment, whole-body first moment
     T W[EXTRA ? Cfg::M + kMaxConstraintRows : 1][Cfg::NV];  // ik::pik / FrameConstraint: orthonormal row-space bases (row-major)
     T Jb[EXTRA ? Cfg::NV : 1][Cfg::LDX];   // ik::pik: projected level Jacobian, column-major; FrameConstraint: Jc (rows <= 12)
 };
@@ -133,6 +133,19 @@ template <typename T> IKB_HD bool coop_world_axis(const DevProblem<T> &P, int j,
     return jt <= IKB_J_REV_UNALIGNED;
 }
 
+// World placement of used frame f (common.hpp:47-51: data.oMf[id]): oMi[parent] * placement, without the product when the
+// placement is the identity.
+template <typename T, class SCR> IKB_HD void coop_frame_placement(const DevProblem<T> &P, const SCR &S, int f, T *R, T *p) {
+    const int fj = P.f_parent[f];
+    const T *O = S.oM[fj];
+    if (P.coop.f_ident[f]) {
+        for (int i = 0; i < 9; ++i) R[i] = O[i];
+        p[0] = O[9]; p[1] = O[10]; p[2] = O[11];
+    } else {
+        se3_mul(O, O + 9, P.f_placement[f], P.f_placement[f] + 9, R, p);
+    }
+}
+
 // ---- phases 0-3: evaluate_problem_data (data.cpp:25-58) -> S.e (weighted), S.Jt (weighted, column-major) ----
 template <typename T, class Cfg, bool EXTRA, class Ctx>
 IKB_HD void coop_evaluate(const Ctx &cx, const DevProblem<T> &P, CoopScratch<T, Cfg, EXTRA> &S) {
@@ -164,7 +177,7 @@ IKB_HD void coop_evaluate(const Ctx &cx, const DevProblem<T> &P, CoopScratch<T, 
     }
     cx.sync();
     // phase 1b: centre of mass (centre_of_mass.hpp:24-38; pinocchio::jacobianCenterOfMass)
-    if (C.has_com) {
+    if constexpr (EXTRA) if (C.has_com) {
         for (int j = 1 + lane; j < P.njoints; j += TEAM) {
             T cw[3];
             rot_vec(S.oM[j], P.com[j], cw);
@@ -197,9 +210,10 @@ IKB_HD void coop_evaluate(const Ctx &cx, const DevProblem<T> &P, CoopScratch<T, 
             for (int i = 0; i < nj; ++i) S.e[row + i] = (S.q[nq - nj + i] - S.tg[toff + i]) * P.mask[P.t_moff[t] + i] * wgt[i];
             continue;
         }
-        const int r = P.t_ref[t], rj = P.f_parent[r];
+        const int r = P.t_ref[t];
+        const bool ref_universe = C.f_ident[r] == 2;
         T Rr[9], pr[3];
-        se3_mul(S.oM[rj], S.oM[rj] + 9, P.f_placement[r], P.f_placement[r] + 9, Rr, pr);
+        coop_frame_placement(P, S, r, Rr, pr);
         if (kind == IKB_TASK_COM) {
             const T inv_m = T(1) / P.total_mass;
             T d[3], lc[3];
@@ -213,15 +227,20 @@ IKB_HD void coop_evaluate(const Ctx &cx, const DevProblem<T> &P, CoopScratch<T, 
             }
             continue;
         }
-        const int f = P.t_frame[t], fj = P.f_parent[f];
+        const int f = P.t_frame[t];
         T Rf[9], pf[3];
-        se3_mul(S.oM[fj], S.oM[fj] + 9, P.f_placement[f], P.f_placement[f] + 9, Rf, pf);
+        coop_frame_placement(P, S, f, Rf, pf);
         S.tpf[t][0] = pf[0]; S.tpf[t][1] = pf[1]; S.tpf[t][2] = pf[2];
         if (kind == IKB_TASK_FRAME) {
             T Rt[9], pt[3], Rtg[9], ptg[3];
             for (int i = 0; i < 9; ++i) Rtg[i] = S.tg[toff + i];
             for (int i = 0; i < 3; ++i) ptg[i] = S.tg[toff + 9 + i];
-            se3_mul(Rr, pr, Rtg, ptg, Rt, pt);   // oMt = oMr * target (frame.hpp:48)
+            if (ref_universe) {                  // oMt = oMr * target (frame.hpp:48) with oMr = identity
+                for (int i = 0; i < 9; ++i) Rt[i] = Rtg[i];
+                pt[0] = ptg[0]; pt[1] = ptg[1]; pt[2] = ptg[2];
+            } else {
+                se3_mul(Rr, pr, Rtg, ptg, Rt, pt);
+            }
             T Re[9], pe[3], w[3], th, sth, cth, lin[3];
             se3_actinv(Rf, pf, Rt, pt, Re, pe);  // fMt (frame.hpp:50)
             log3(Re, w, th, sth, cth);
@@ -283,7 +302,7 @@ IKB_HD void coop_evaluate(const Ctx &cx, const DevProblem<T> &P, CoopScratch<T, 
         if (P.t_kind[t] == IKB_TASK_COM) {
             // velocity this coordinate gives the centre of mass of its subtree, weighted by the subtree's share of the mass
             T vel[3] = {T(0), T(0), T(0)};
-            if (S.ms[j] > T(0)) {
+            if constexpr (EXTRA) if (S.ms[j] > T(0)) {
                 const T share = S.ms[j] / P.total_mass, ims = T(1) / S.ms[j];
                 if (angular) {
                     const T dc[3] = {S.mc[j][0] * ims - O[9], S.mc[j][1] * ims - O[10], S.mc[j][2] * ims - O[11]};
@@ -313,6 +332,8 @@ IKB_HD void coop_evaluate(const Ctx &cx, const DevProblem<T> &P, CoopScratch<T, 
     (void)nv;
     cx.sync();
 }
+
+template <typename T> struct alignas(2 * sizeof(T)) Pair { T x, y; };   // one 128-bit (64-bit for float) shared-memory access
 
 // Broadcast of one scalar per row: either by shuffle from the owner lane's register or through shared memory.
 // Gram rows + Gauss-Jordan solve of (Jm Jm^T + lambda2 I) y = rhs for rows [0, M) of the column-major matrix Jm (rows
@@ -347,10 +368,13 @@ IKB_HD void coop_gram_solve(const Ctx &cx, const T (*Jm)[LDM], const uint64_t *c
         for (int blk = 0; blk < Cfg::NBLK; ++blk) {
             if ((mask >> (6 * blk)) & 63ULL) {
 #pragma unroll
-                for (int b = 6 * blk; b < (6 * blk + 6 < M ? 6 * blk + 6 : M); ++b) {
-                    const T v = col[b];
+                for (int b = 6 * blk; b < (6 * blk + 6 < M ? 6 * blk + 6 : M); b += 2) {   // M, LDM even: 16-byte pairs
+                    const Pair<T> v = *reinterpret_cast<const Pair<T> *>(col + b);
 #pragma unroll
-                    for (int rr = 0; rr < RPL; ++rr) g[rr][b] += a[rr] * v;
+                    for (int rr = 0; rr < RPL; ++rr) {
+                        g[rr][b] += a[rr] * v.x;
+                        g[rr][b + 1] += a[rr] * v.y;
+                    }
                 }
             }
         }
@@ -388,13 +412,29 @@ IKB_HD void coop_gram_solve(const Ctx &cx, const T (*Jm)[LDM], const uint64_t *c
             const int r = lane + rr * TEAM;
             f[rr] = (r == k) ? T(0) : g[rr][k] * inv;
         }
+        if constexpr (SHFL) {
 #pragma unroll
-        for (int b = k + 1; b < M; ++b) {
-            T pb;
-            if constexpr (SHFL) pb = cx.shfl(g[b / TEAM][k], b % TEAM);   // G[k][b] = G[b][k]: the trailing block stays symmetric
-            else pb = pv[b];
+            for (int b = k + 1; b < M; ++b) {
+                const T pb = cx.shfl(g[b / TEAM][k], b % TEAM);   // G[k][b] = G[b][k]: the trailing block stays symmetric
 #pragma unroll
-            for (int rr = 0; rr < RPL; ++rr) g[rr][b] -= f[rr] * pb;
+                for (int rr = 0; rr < RPL; ++rr) g[rr][b] -= f[rr] * pb;
+            }
+        } else {
+            const int first_pair = (k + 2) & ~1;   // first even index > k (k is a constant once the pivot loop is unrolled)
+            if ((k + 1) & 1) {
+                const T pb = pv[k + 1];
+#pragma unroll
+                for (int rr = 0; rr < RPL; ++rr) g[rr][k + 1] -= f[rr] * pb;
+            }
+#pragma unroll
+            for (int b = first_pair; b < M; b += 2) {
+                const Pair<T> pb = *reinterpret_cast<const Pair<T> *>(pv + b);
+#pragma unroll
+                for (int rr = 0; rr < RPL; ++rr) {
+                    g[rr][b] -= f[rr] * pb.x;
+                    g[rr][b + 1] -= f[rr] * pb.y;
+                }
+            }
         }
 #pragma unroll
         for (int rr = 0; rr < RPL; ++rr) rhs[rr] -= f[rr] * ek;
@@ -509,8 +549,8 @@ IKB_HD void coop_constraint_jacobian(const Ctx &cx, const DevProblem<T> &P, Coop
         const int f = P.c_frame[k], r = P.c_ref[k], fj = P.f_parent[f], rj = P.f_parent[r];
         const int full = P.c_type[k] == IKB_FULL, r0 = P.c_type[k] == IKB_ORIENTATION ? 3 : 0, dim = full ? 6 : 3;
         T Rf[9], pf[3], Rr[9], pr[3], Rm[9], pm[3];
-        se3_mul(S.oM[fj], S.oM[fj] + 9, P.f_placement[f], P.f_placement[f] + 9, Rf, pf);
-        se3_mul(S.oM[rj], S.oM[rj] + 9, P.f_placement[r], P.f_placement[r] + 9, Rr, pr);
+        coop_frame_placement(P, S, f, Rf, pf);
+        coop_frame_placement(P, S, r, Rr, pr);
         se3_actinv(Rr, pr, Rf, pf, Rm, pm);  // rMf (frame.hpp:407)
         // the two chains are walked by every lane; a lane handles the velocity coordinates it owns (col % TEAM == lane)
         for (int pass = 0; pass < 2; ++pass) {
@@ -756,12 +796,18 @@ __global__ void __launch_bounds__(CoopLaunch<T, Cfg, EXTRA>::kThreads, 1) dls_co
     const int nq = P.nq, tsz = P.tsz;
     long long b = 0;
     int it = 0;
-    bool have = false, need = true;
+    bool have = false, need = true, first = true;
+    // The first ticket of a team is static and strided over the CTAs (team t of CTA c starts with problem t * gridDim + c),
+    // so a batch smaller than the grid spreads over all SMs instead of filling the first CTAs; later tickets come from the
+    // global counter, offset by the number of static ones.
+    const unsigned long long n_static = (unsigned long long)gridDim.x * L::kTeams;
     for (;;) {
         unsigned long long t = 0;
-        if (need && lane == 0) t = atomicAdd(a.ticket, 1ULL);
+        if (need && !first && lane == 0) t = atomicAdd(a.ticket, 1ULL) + n_static;
         t = __shfl_sync(0xffffffffu, t, 0, TEAM);
         if (need) {
+            if (first) t = (unsigned long long)team * gridDim.x + blockIdx.x;
+            first = false;
             it = 0;
             have = (long long)t < a.B;
             b = (long long)t;
@@ -773,6 +819,10 @@ __global__ void __launch_bounds__(CoopLaunch<T, Cfg, EXTRA>::kThreads, 1) dls_co
             }
             need = false;
         }
+        // Warps run free of each other.  (Measured: a CTA-wide barrier per trip, which lets the warps share the ~85 KB of
+        // SASS they stream per iteration, takes `no_instruction` from 1.42 to 0.13 stalls per issue but costs 0.93 in
+        // barrier stalls, +1.0 in shared-memory scoreboard stalls -- every warp hits the same phase at once -- and +25 %
+        // executed instructions from teams idling in step: 3.31 -> 3.54 ms on 65 536 Cassie problems, profiles/r2_coop_*.)
         __syncwarp();
         if (!__any_sync(0xffffffffu, have)) break;
 
@@ -789,11 +839,15 @@ __global__ void __launch_bounds__(CoopLaunch<T, Cfg, EXTRA>::kThreads, 1) dls_co
                     if (a.iters) a.iters[b] = it;
                     if (a.resid) a.resid[b] = res;
                 }
+                // *_solve_ex: what the reference leaves in dls_data after the call (data.hpp:15-28) -- dq, e, J of the LAST evaluation
+                const int nv = P.nv, rows = P.rows;
+                if (a.aux_dq) for (int c = lane; c < nv; c += TEAM) a.aux_dq[b * nv + c] = S.dq[c];
+                if (a.aux_e) for (int r = lane; r < rows; r += TEAM) a.aux_e[b * rows + r] = S.e[r];
+                if (a.aux_J) for (int i = lane; i < rows * nv; i += TEAM) a.aux_J[(long long)b * rows * nv + i] = S.Jt[i % nv][i / nv];
                 need = true;
                 have = false;
             }
         }
-        __syncwarp();
     }
 }
 #endif  // __CUDACC__

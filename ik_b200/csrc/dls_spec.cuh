@@ -28,6 +28,8 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdio>
+#include <string>
 
 #include "dev_problem.hpp"
 #include "model.hpp"
@@ -276,6 +278,57 @@ template <class Spec> bool spec_matches(const HostProblem &hp) {
         if (!same_values(m.frame_placement[ht.ref].data(), Spec::sig_task_ref_placement() + 12 * t, 12)) return false;
         if (m.frame_parent[ht.frame] != Spec::sig_task_joint()[t]) return false;
         if (!same_values(m.frame_placement[ht.frame].data(), Spec::sig_task_placement() + 12 * t, 12)) return false;
+    }
+    return true;
+}
+
+// Near miss: the problem has this specialisation's topology, joint types and task list, but some placement differs
+// (slightly: a re-rounded URDF literal; or grossly: another robot of the same shape) from the values the straight-line
+// code was generated with, so spec_matches rejected it.  `why` names the first difference and its size.
+template <class Spec> bool spec_near_miss(const HostProblem &hp, std::string *why) {
+    const HostModel &m = hp.model;
+    if (m.njoints() != Spec::NJOINTS || m.nq != Spec::NQ || m.nv != Spec::NV) return false;
+    if ((int)hp.tasks.size() != Spec::NTASKS || hp.rows() != Spec::M || hp.e_size(0) != Spec::M0) return false;
+    if (!hp.constraints.empty()) return false;
+    const int *par = Spec::sig_parent(), *typ = Spec::sig_type();
+    for (int j = 0; j < Spec::NJOINTS; ++j)
+        if (m.parent[j] != par[j] || m.jtype[j] != typ[j]) return false;
+    const int kinds[3] = {IKB_TASK_FRAME, IKB_TASK_ALIGN_AXIS, IKB_TASK_POSTURE};
+    for (int t = 0; t < Spec::NTASKS; ++t) {
+        const HostTask &ht = hp.tasks[t];
+        if (ht.kind != kinds[Spec::sig_task_kind()[t]] || ht.type != Spec::sig_task_type()[t] || ht.priority != Spec::sig_task_priority()[t]) return false;
+        if (ht.kind == IKB_TASK_POSTURE) continue;
+        if (m.frame_parent[ht.ref] != Spec::sig_task_ref_joint()[t] || m.frame_parent[ht.frame] != Spec::sig_task_joint()[t]) return false;
+    }
+    // same structure: find the largest numeric difference
+    double worst = 0;
+    char where[160] = "";
+    auto scan = [&](const double *a, const double *b, int n, const char *what, int idx, const char *name) {
+        for (int i = 0; i < n; ++i) {
+            const double d = a[i] > b[i] ? a[i] - b[i] : b[i] - a[i];
+            if (d > worst) {
+                worst = d;
+                std::snprintf(where, sizeof where, "%s %d (%s), entry %d: %.17g here vs %.17g generated", what, idx, name, i, a[i], b[i]);
+            }
+        }
+    };
+    const double *pl = Spec::sig_placement();
+    for (int j = 0; j < Spec::NJOINTS; ++j) {
+        scan(m.placement[j].data(), pl + 15 * j, 12, "placement of joint", j, m.joint_names[j].c_str());
+        if (typ[j] == IKB_J_REV_UNALIGNED || typ[j] == IKB_J_PRIS_UNALIGNED) scan(m.axis[j].data(), pl + 15 * j + 12, 3, "axis of joint", j, m.joint_names[j].c_str());
+    }
+    for (int t = 0; t < Spec::NTASKS; ++t) {
+        const HostTask &ht = hp.tasks[t];
+        if (ht.kind == IKB_TASK_POSTURE) continue;
+        scan(m.frame_placement[ht.ref].data(), Spec::sig_task_ref_placement() + 12 * t, 12, "reference frame of task", t, m.frame_names[ht.ref].c_str());
+        scan(m.frame_placement[ht.frame].data(), Spec::sig_task_placement() + 12 * t, 12, "frame of task", t, m.frame_names[ht.frame].c_str());
+    }
+    if (!(worst > 0)) return false;   // equal values: not a miss at all (IKB_FORCE_GENERIC, task order, ...)
+    if (why) {
+        char buf[400];
+        std::snprintf(buf, sizeof buf, "specialisation '%s' has this problem's topology and task list but was generated for other placements "
+                      "(largest difference %.3g: %s); running the table-driven kernel", Spec::name(), worst, where);
+        *why = buf;
     }
     return true;
 }

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <mutex>
 #include <type_traits>
 #include <stdexcept>
@@ -107,6 +108,29 @@ const SpecializedKernel *select_specialized(const HostProblem &hp) {
     for (size_t i = 1; i < hp.tasks.size(); ++i)
         if (hp.tasks[i].priority < hp.tasks[i - 1].priority) return nullptr;
     return find_specialized(hp);
+}
+
+// Compact wire format of the targets (include/ikb200.h), per task in insertion order.
+ExpandTable build_expand_table(const HostProblem &hp) {
+    ExpandTable t;
+    t.ntasks = (int)hp.tasks.size();
+    int coff = 0;
+    for (int i = 0; i < t.ntasks && i < kMaxTasks; ++i) {
+        const HostTask &ht = hp.tasks[i];
+        t.toff[i] = hp.target_offset(i);
+        t.coff[i] = coff;
+        if (ht.kind == IKB_TASK_FRAME) {
+            t.mode[i] = ht.type == IKB_FULL ? 1 : (ht.type == IKB_POSITION ? 2 : 3);
+            t.n[i] = ht.type == IKB_FULL ? 7 : (ht.type == IKB_POSITION ? 3 : 4);
+        } else {
+            t.mode[i] = 0;
+            t.n[i] = ht.target_size;
+        }
+        coff += t.n[i];
+    }
+    t.csz = coff;
+    t.tsz = hp.target_size();
+    return t;
 }
 
 int check_weights(const double *w, int dim, std::vector<double> &out) {
@@ -285,17 +309,19 @@ int ikb_problem_create(const ikb_model *m, int max_priority_level, ikb_problem *
 
 void ikb_problem_free(ikb_problem *p) {
     if (!p) return;
-    if (p->finalized) {
+    if (p->device >= 0) {   // device state may be partially built when ikb_problem_finalize failed half-way: free whatever exists
         DeviceGuard g(p->device);
         cudaFree(p->d64); cudaFree(p->d32); cudaFree(p->d_frame_parent); cudaFree(p->d_frame_pl64);
         cudaFree(p->d_frame_pl32); cudaFree(p->d_tickets);
-        cudaFree(p->st64.q0); cudaFree(p->st64.targets); cudaFree(p->st64.q); cudaFree(p->st64.resid);
-        cudaFree(p->st32.q0); cudaFree(p->st32.targets); cudaFree(p->st32.q); cudaFree(p->st32.resid);
+        cudaFree(p->st64.q0); cudaFree(p->st64.targets); cudaFree(p->st64.q); cudaFree(p->st64.resid); cudaFree(p->st64.compact);
+        cudaFree(p->st32.q0); cudaFree(p->st32.targets); cudaFree(p->st32.q); cudaFree(p->st32.resid); cudaFree(p->st32.compact);
         cudaFree(p->st_success); cudaFree(p->st_iters);
         for (auto &sc : p->scratch) {
             cudaFree(sc.list); cudaFree(sc.iters);
             if (sc.ev) cudaEventDestroy(sc.ev);
         }
+        for (void *r : p->retired) cudaFree(r);
+        for (auto e : p->ticket_ev) if (e) cudaEventDestroy(e);
         if (p->stream) cudaStreamDestroy(p->stream);
         if (p->stream_in) cudaStreamDestroy(p->stream_in);
         if (p->stream_aux) cudaStreamDestroy(p->stream_aux);
@@ -457,23 +483,24 @@ int ikb_problem_finalize(ikb_problem *p, int device) {
     IKB_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10)
         return fail(IKB_ERR_NO_DEVICE, std::string("device ") + prop.name + " is not Blackwell-class (sm_100a code only)");
+    p->device = device;   // from here on ikb_problem_free releases whatever device state exists
     p->sm_count = prop.multiProcessorCount;
     if (const char *e = std::getenv("IKB_SM_LIMIT")) {  // measurement knob: persistent grids sized for fewer SMs (read at finalize)
         const int lim = std::atoi(e);
         if (lim >= 1 && lim < p->sm_count) p->sm_count = lim;
     }
 
-    auto *h64 = new DevProblem<double>();
-    auto *h32 = new DevProblem<float>();
-    fill_dev_problem(hp, order, used, *h64);
-    fill_dev_problem(hp, order, used, *h32);
-    p->coop_ok = h64->coop_ok != 0;
-    IKB_CUDA(cudaMalloc(&p->d64, sizeof(*h64)));
-    IKB_CUDA(cudaMalloc(&p->d32, sizeof(*h32)));
-    IKB_CUDA(cudaMemcpy(p->d64, h64, sizeof(*h64), cudaMemcpyHostToDevice));
-    IKB_CUDA(cudaMemcpy(p->d32, h32, sizeof(*h32), cudaMemcpyHostToDevice));
-    delete h64;
-    delete h32;
+    {
+        std::unique_ptr<DevProblem<double>> h64(new DevProblem<double>());
+        std::unique_ptr<DevProblem<float>> h32(new DevProblem<float>());
+        fill_dev_problem(hp, order, used, *h64);
+        fill_dev_problem(hp, order, used, *h32);
+        p->coop_ok = h64->coop_ok != 0;
+        IKB_CUDA(cudaMalloc(&p->d64, sizeof(*h64)));
+        IKB_CUDA(cudaMalloc(&p->d32, sizeof(*h32)));
+        IKB_CUDA(cudaMemcpy(p->d64, h64.get(), sizeof(*h64), cudaMemcpyHostToDevice));
+        IKB_CUDA(cudaMemcpy(p->d32, h32.get(), sizeof(*h32), cudaMemcpyHostToDevice));
+    }
 
     const int nf = m.nframes();
     std::vector<double> pl64((size_t)nf * 12);
@@ -491,6 +518,7 @@ int ikb_problem_finalize(ikb_problem *p, int device) {
     IKB_CUDA(cudaMemcpy(p->d_frame_pl32, pl32.data(), pl32.size() * sizeof(float), cudaMemcpyHostToDevice));
     IKB_CUDA(cudaMalloc(&p->d_tickets, kTicketSlots * 16 * sizeof(unsigned long long)));
     IKB_CUDA(cudaMemset(p->d_tickets, 0, kTicketSlots * 16 * sizeof(unsigned long long)));
+    for (auto &e : p->ticket_ev) IKB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     IKB_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     IKB_CUDA(cudaStreamCreateWithFlags(&p->stream_in, cudaStreamNonBlocking));
     IKB_CUDA(cudaStreamCreateWithFlags(&p->stream_aux, cudaStreamNonBlocking));
@@ -499,7 +527,7 @@ int ikb_problem_finalize(ikb_problem *p, int device) {
     IKB_CUDA(cudaEventCreateWithFlags(&p->ev_main, cudaEventDisableTiming));
 
     p->size_class = cls;
-    p->device = device;
+    p->expand = build_expand_table(hp);
     p->weight_stacked.clear();
     p->mask_stacked.clear();
     for (int t : order) {
@@ -508,6 +536,17 @@ int ikb_problem_finalize(ikb_problem *p, int device) {
             p->mask_stacked.push_back(hp.tasks[t].kind == IKB_TASK_POSTURE ? hp.tasks[t].mask[i] : 1.0);
     }
     p->spec = select_specialized(hp);
+    p->status.clear();
+    if (!p->spec) {
+        const char *forced = std::getenv("IKB_FORCE_GENERIC");
+        std::string why;
+        if (!(forced && forced[0] == '1') && hp.constraints.empty() && find_near_miss(hp, &why)) {
+            p->status = why;
+            const char *quiet = std::getenv("IKB_QUIET");
+            static std::atomic<bool> warned{false};
+            if (!(quiet && quiet[0] == '1') && !warned.exchange(true)) std::fprintf(stderr, "[ikb200] %s\n", why.c_str());
+        }
+    }
     char buf[96];
     const char *legacy = std::getenv("IKB_GENERIC_LEGACY");
     const int team[3] = {8, 16, 32};
@@ -525,6 +564,14 @@ const char *ikb_problem_specialisation(const ikb_problem *p) {
     if (!p || p->hp.tasks.empty()) return nullptr;
     const SpecializedKernel *k = select_specialized(p->hp);
     return k ? k->name : nullptr;
+}
+
+const char *ikb_problem_status_string(const ikb_problem *p) { return p ? p->status.c_str() : ""; }
+
+int ikb_problem_compact_target_size(const ikb_problem *p) { return p ? build_expand_table(p->hp).csz : -IKB_ERR_INVALID_ARG; }
+int ikb_problem_task_compact_target_offset(const ikb_problem *p, int t) {
+    if (!p || t < 0 || t >= (int)p->hp.tasks.size()) return -IKB_ERR_INVALID_ARG;
+    return build_expand_table(p->hp).coff[t];
 }
 
 const char *ikb_problem_kernel_name(const ikb_problem *p, int dtype) {

@@ -16,8 +16,7 @@ int launch_one(const DevProblem<T> *dP, const SolveArgs<T> &a, int sm_count, cud
     auto fn = dls_coop_kernel<T, Cfg, SHFL, PIK, EXTRA>;
     static DynSmemOptIn opt_in;
     if (!opt_in.ensure(fn, (int)L::kSmem)) return 1;
-    long long ctas = (a.B + L::kTeams - 1) / L::kTeams;
-    if (ctas > sm_count) ctas = sm_count;
+    long long ctas = a.B < sm_count ? a.B : sm_count;   // persistent: one CTA per SM; a small batch spreads one team per SM
     if (ctas < 1) ctas = 1;
     fn<<<(unsigned)ctas, L::kThreads, L::kSmem, s>>>(dP, a);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;

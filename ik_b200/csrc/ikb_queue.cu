@@ -24,6 +24,7 @@ struct ikb_queue {
         int64_t B = 0;
         ikb_batch_io dio{};   // device view of the batch
         ikb_batch_io hio{};   // host mode: the caller's buffers (copy-out targets)
+        HostViews hv;         // host mode: the caller's views, classified
         // host-mode staging (per scalar type, grown on demand)
         Staging<double> st64;
         Staging<float> st32;
@@ -58,11 +59,10 @@ bool same_params(const ikb_dls_params &a, const ikb_dls_params &b) {
 }
 
 template <typename T> int queue_copy_out(ikb_queue *q, ikb_queue::Slot &sl) {
-    const int nq = q->p->hp.model.nq;
     const ikb_batch_io &io = sl.hio;
     Staging<T> &st = slot_staging<T>(sl);
-    const size_t n_q = view_extent(nq, io.q_elem_stride, io.q_batch_stride, sl.B);
-    IKB_CUDA(cudaMemcpyAsync(io.q, st.q, n_q * sizeof(T), cudaMemcpyDeviceToHost, q->s_out));
+    int rc;
+    if ((rc = copy_view_out<T>(sl.hv.q, st.q, sl.B, q->s_out))) return rc;   // only the payload crosses PCIe (2-D copy for sliced views)
     if (io.success) IKB_CUDA(cudaMemcpyAsync(io.success, sl.success, (size_t)sl.B, cudaMemcpyDeviceToHost, q->s_out));
     if (io.iters) IKB_CUDA(cudaMemcpyAsync(io.iters, sl.iters, (size_t)sl.B * sizeof(int), cudaMemcpyDeviceToHost, q->s_out));
     if (io.resid) IKB_CUDA(cudaMemcpyAsync(io.resid, st.resid, (size_t)sl.B * sizeof(T), cudaMemcpyDeviceToHost, q->s_out));
@@ -119,7 +119,16 @@ template <typename T> int queue_flush_t(ikb_queue *q) {
 }
 int queue_flush(ikb_queue *q) {
     if (q->open.empty()) return IKB_OK;
-    return q->open_dtype == IKB_F64 ? queue_flush_t<double>(q) : queue_flush_t<float>(q);
+    const int rc = q->open_dtype == IKB_F64 ? queue_flush_t<double>(q) : queue_flush_t<float>(q);
+    if (rc != IKB_OK) {
+        // a failed launch leaves no batch in flight: release the group's slots so that a retry does not push them twice
+        for (int i : q->open) {
+            q->slots[i].pending = false;
+            q->slots[i].busy = false;
+        }
+        q->open.clear();
+    }
+    return rc;
 }
 
 // The slot of the next batch, free of its previous occupant (back-pressure: blocks while that batch is in flight).
@@ -152,15 +161,12 @@ int64_t queue_commit(ikb_queue *q, ikb_queue::Slot *sl) {
 
 template <typename T> int queue_stage_host(ikb_queue *q, ikb_queue::Slot &sl, int64_t B, const ikb_batch_io *io) {
     ikb_problem *p = q->p;
-    const int nq = p->hp.model.nq, tsz = p->hp.target_size();
     Staging<T> &st = slot_staging<T>(sl);
-    const size_t n_q0 = view_extent(nq, io->q0_elem_stride, io->q0_batch_stride, B);
-    const size_t n_tg = tsz > 0 ? view_extent(tsz, io->targets_elem_stride, io->targets_batch_stride, B) : 0;
-    const size_t n_q = view_extent(nq, io->q_elem_stride, io->q_batch_stride, B);
     int rc;
-    if ((rc = ensure(st.q0, st.q0_cap, n_q0)) || (rc = ensure(st.targets, st.tg_cap, std::max<size_t>(n_tg, 1))) ||
-        (rc = ensure(st.q, st.q_cap, n_q)) || (rc = ensure(st.resid, st.b_cap, (size_t)B)))
-        return rc;
+    if ((rc = classify_host_views(p, B, io, &sl.hv))) return rc;
+    sl.hio = *io;
+    sl.dio = *io;
+    if ((rc = prepare_staging<T>(p, st, sl.hv, B, &sl.dio))) return rc;
     if ((size_t)B > sl.flag_cap) {
         if (sl.success) cudaFree(sl.success);
         if (sl.iters) cudaFree(sl.iters);
@@ -178,13 +184,10 @@ template <typename T> int queue_stage_host(ikb_queue *q, ikb_queue::Slot &sl, in
         sl.tr_submit_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - q->tr_host_ref).count();
         IKB_CUDA(cudaEventRecord(sl.tr_in0, q->s_in));
     }
-    IKB_CUDA(cudaMemcpyAsync(st.q0, io->q0, n_q0 * sizeof(T), cudaMemcpyHostToDevice, q->s_in));
-    if (n_tg) IKB_CUDA(cudaMemcpyAsync(st.targets, io->targets, n_tg * sizeof(T), cudaMemcpyHostToDevice, q->s_in));
+    // copy-in (+ the SE3 expansion of compact targets) on the copy stream
+    if ((rc = stage_inputs<T>(p, st, sl.hv, B, 0, B, true, q->s_in))) return rc;
     IKB_CUDA(cudaEventRecord(sl.ev_in, q->s_in));
-    sl.hio = *io;
-    sl.dio = *io;
-    sl.dio.q0 = st.q0; sl.dio.targets = st.targets; sl.dio.q = st.q;
-    sl.dio.success = sl.success; sl.dio.iters = sl.iters; sl.dio.resid = st.resid;
+    sl.dio.success = sl.success; sl.dio.iters = sl.iters;
     return IKB_OK;
 }
 }  // namespace
@@ -234,8 +237,8 @@ void ikb_queue_free(ikb_queue *q) {
     for (auto &sl : q->slots) {
         for (cudaEvent_t e : {sl.ev_in, sl.ev_done, sl.tr_in0, sl.tr_c0, sl.tr_c1})
             if (e) cudaEventDestroy(e);
-        cudaFree(sl.st64.q0); cudaFree(sl.st64.targets); cudaFree(sl.st64.q); cudaFree(sl.st64.resid);
-        cudaFree(sl.st32.q0); cudaFree(sl.st32.targets); cudaFree(sl.st32.q); cudaFree(sl.st32.resid);
+        cudaFree(sl.st64.q0); cudaFree(sl.st64.targets); cudaFree(sl.st64.q); cudaFree(sl.st64.resid); cudaFree(sl.st64.compact);
+        cudaFree(sl.st32.q0); cudaFree(sl.st32.targets); cudaFree(sl.st32.q); cudaFree(sl.st32.resid); cudaFree(sl.st32.compact);
         cudaFree(sl.success); cudaFree(sl.iters);
     }
     delete q;
@@ -246,6 +249,7 @@ int64_t ikb_queue_submit(ikb_queue *q, int dtype, const ikb_dls_params *prm, int
     int rc = check_solve_args(q->p, dtype, prm, B, io);
     if (rc) return -rc;
     DeviceGuard g(q->p->device);
+    if (io->targets_format != IKB_TARGETS_SE3) return -fail(IKB_ERR_INVALID_ARG, "compact targets are a wire format of the HOST entry points");
     ikb_queue::Slot *sl;
     if ((rc = queue_acquire(q, dtype, prm, &sl))) return -rc;
     // the inputs are ready in `in_stream` order (NULL = the legacy default stream) at this point

@@ -45,6 +45,32 @@ template <> DevProblem<double> *dev_blob<double>(const ikb_problem *p) { return 
 template <> DevProblem<float> *dev_blob<float>(const ikb_problem *p) { return p->d32; }
 
 __global__ void set_ticket_kernel(unsigned long long *t, unsigned long long v) { *t = v; }
+
+// One thread per problem: expand the compact record (quaternion / translation per FrameTask) to the SE3 record the
+// kernels read.  Both arrays are dense, in the same orientation (strides passed in).
+template <typename T>
+__global__ void expand_targets_kernel(const __grid_constant__ ExpandTable tab, const T *__restrict__ c, long long c_es, long long c_bs,
+                                      T *__restrict__ o, long long o_es, long long o_bs, long long b0, long long b1) {
+    const long long b = b0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= b1) return;
+    const T *cb = c + b * c_bs;
+    T *ob = o + b * o_bs;
+    for (int t = 0; t < tab.ntasks; ++t) {
+        const T *ci = cb + tab.coff[t] * c_es;
+        T *oi = ob + tab.toff[t] * o_es;
+        const int mode = tab.mode[t];
+        if (mode == 0) {
+            for (int k = 0; k < tab.n[t]; ++k) oi[k * o_es] = ci[k * c_es];
+            continue;
+        }
+        T R[9] = {T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1)}, tr[3] = {T(0), T(0), T(0)};
+        if (mode == 1 || mode == 3) quat_to_rot(ci[0], ci[c_es], ci[2 * c_es], ci[3 * c_es], R);
+        if (mode == 1) { tr[0] = ci[4 * c_es]; tr[1] = ci[5 * c_es]; tr[2] = ci[6 * c_es]; }
+        if (mode == 2) { tr[0] = ci[0]; tr[1] = ci[c_es]; tr[2] = ci[2 * c_es]; }
+        for (int k = 0; k < 9; ++k) oi[k * o_es] = R[k];
+        for (int k = 0; k < 3; ++k) oi[(9 + k) * o_es] = tr[k];
+    }
+}
 }  // namespace
 
 namespace ikb {
@@ -69,16 +95,16 @@ bool two_phase(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, int *
 }
 
 // Scratch of a two-launch solve (suspended-problem list, step counts): slot `slot` of the problem's ring, grown to B
-// entries; stream `s` waits for the slot's previous user.
-static int acquire_scratch(const ikb_problem *p, unsigned slot, int64_t B, cudaStream_t s, SolveScratch **out) {
+// entries; stream `s` waits for the slot's previous user.  The descriptor is COPIED out under the lock, and a buffer that
+// is replaced by a larger one is retired (freed with the handle), never freed: another host thread may be about to launch
+// with the old pointers, and launches already in flight keep using them.
+static int acquire_scratch(const ikb_problem *p, unsigned slot, int64_t B, cudaStream_t s, SolveScratch *out) {
     ikb_problem *mp = const_cast<ikb_problem *>(p);
     std::lock_guard<std::mutex> lk(mp->scratch_mu);
     if (mp->scratch[0].cap < (size_t)B) {
-        // grow every slot at once (one synchronisation, on the first large batch only)
-        IKB_CUDA(cudaDeviceSynchronize());
         for (auto &x : mp->scratch) {
-            if (x.list) cudaFree(x.list);
-            if (x.iters) cudaFree(x.iters);
+            if (x.list) mp->retired.push_back(x.list);
+            if (x.iters) mp->retired.push_back(x.iters);
             x.list = nullptr; x.iters = nullptr; x.cap = 0;
             IKB_CUDA(cudaMalloc(&x.list, (size_t)B * sizeof(unsigned int)));
             IKB_CUDA(cudaMalloc(&x.iters, (size_t)B * sizeof(int)));
@@ -86,14 +112,15 @@ static int acquire_scratch(const ikb_problem *p, unsigned slot, int64_t B, cudaS
             if (!x.ev) IKB_CUDA(cudaEventCreateWithFlags(&x.ev, cudaEventDisableTiming));
         }
     }
-    *out = &mp->scratch[slot % kScratchSlots];
-    IKB_CUDA(cudaStreamWaitEvent(s, (*out)->ev, 0));  // the slot's previous user (any stream) must be done
+    *out = mp->scratch[slot % kScratchSlots];
+    IKB_CUDA(cudaStreamWaitEvent(s, out->ev, 0));  // the slot's previous user (any stream) must be done
     return IKB_OK;
 }
 
 template <typename T>
-int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io, cudaStream_t s,
-                 const ChunkPlan *plan, const Merged<T> *merged, const double *pik_lambda) {
+static int launch_solve_impl(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io, cudaStream_t s,
+                             const ChunkPlan *plan, const Merged<T> *merged, const double *pik_lambda, const SolveAux<T> *aux,
+                             unsigned slot) {
     SolveArgs<T> a{};
     if (!merged) {
         a.q0 = (const T *)io->q0; a.q0_es = io->q0_elem_stride; a.q0_bs = io->q0_batch_stride;
@@ -116,8 +143,8 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
     a.step_length = (T)prm->step_length;
     a.damping2 = (T)(prm->damping * prm->damping);
     a.tolerance = (T)prm->tolerance;
-    const unsigned slot = const_cast<ikb_problem *>(p)->ticket_next.fetch_add(1) % kTicketSlots;
     a.ticket = p->d_tickets + slot * 16;  // 128 B apart
+    if (aux) { a.aux_dq = aux->dq; a.aux_e = aux->e; a.aux_J = aux->J; }
     IKB_CUDA(cudaMemsetAsync(a.ticket, 0, sizeof(unsigned long long), s));
 
     if (prm->max_iterations <= 0) {
@@ -134,7 +161,7 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
     a.list_count = nullptr;
     a.iters_ws = merged ? nullptr : io->iters;
     for (int l = 0; l < 7; ++l) a.pik_lambda2[l] = pik_lambda ? (T)(pik_lambda[l] * pik_lambda[l]) : T(0);
-    if (p->spec && !pik_lambda) {
+    if (p->spec && !pik_lambda && !aux) {
         const SpecHostConsts hc{p->hp.model.lower.data(), p->hp.model.upper.data(), p->weight_stacked.data(), p->mask_stacked.data()};
         // Scheduling.  A batch that the latency configuration keeps resident in one wave runs there
         // directly.  A larger batch runs BULK (throughput configuration) with a step cap: the few problems still
@@ -153,8 +180,8 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
             rc = launch_specialized<T>(*p->spec, hc, a, SPEC_BULK, B, p->sm_count, s);
             if (rc == IKB_OK) g_launches.fetch_add(1);
         } else {
-            SolveScratch *sc;
-            if ((rc = acquire_scratch(p, slot, B, s, &sc))) return rc;
+            SolveScratch scv, *sc = &scv;
+            if ((rc = acquire_scratch(p, slot, B, s, sc))) return rc;
             IKB_CUDA(cudaMemsetAsync(a.ticket, 0, 3 * sizeof(unsigned long long), s));  // bulk ticket, tail ticket, list count
             a.it_cap = cap;
             a.list = sc->list;
@@ -199,10 +226,13 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
     // in registers).  IKB_GENERIC_LEGACY=1 keeps the thread-per-problem local-memory kernel (dls_generic.cuh) for A/B runs;
     // it is also the fallback for problems beyond the cooperative kernel's table capacities.
     const char *legacy_env = std::getenv("IKB_GENERIC_LEGACY");
-    if (p->coop_ok && !(legacy_env && legacy_env[0] == '1')) {
+    if (aux && !p->coop_ok) return fail(IKB_ERR_UNSUPPORTED, "dq / e / J outputs need the team-per-problem kernel (problem exceeds its table capacities)");
+    if (p->coop_ok && (aux || !(legacy_env && legacy_env[0] == '1'))) {
         const char *shfl_env = std::getenv("IKB_COOP_SHFL");
-        const bool shfl = shfl_env ? shfl_env[0] == '1' : true;
-        if (launch_coop<T>(p->size_class, dev_blob<T>(p), a, pik_lambda != nullptr, !p->hp.constraints.empty(), shfl, p->sm_count, s))
+        const bool shfl = shfl_env ? shfl_env[0] == '1' : false;   // measured: the shared-memory column is 3-8 % faster
+        bool extra = !p->hp.constraints.empty();   // the larger scratch: FrameConstraints, CentreOfMassTask (and always ik::pik)
+        for (const auto &t : p->hp.tasks) extra = extra || t.kind == IKB_TASK_COM;
+        if (launch_coop<T>(p->size_class, dev_blob<T>(p), a, pik_lambda != nullptr, extra, shfl, p->sm_count, s))
             return cuda_fail(cudaGetLastError(), "team-per-problem kernel launch");
         g_launches.fetch_add(1);
         return IKB_OK;
@@ -223,9 +253,9 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
     const char *cap_env = std::getenv("IKB_GENERIC_CAP");
     const int cap = cap_env ? std::atoi(cap_env) : 32;  // measured: profiles/r1_generic_two_launch.txt (16 suits quick problems, 32 never loses to one launch)
     if (cap > 0 && prm->max_iterations > cap && B > 2048) {
-        SolveScratch *sc;
+        SolveScratch scv, *sc = &scv;
         int rc;
-        if ((rc = acquire_scratch(p, slot, B, s, &sc))) return rc;
+        if ((rc = acquire_scratch(p, slot, B, s, sc))) return rc;
         IKB_CUDA(cudaMemsetAsync(a.ticket, 0, 3 * sizeof(unsigned long long), s));  // first ticket, second ticket, list count
         a.it_cap = cap;
         a.list = sc->list;
@@ -252,10 +282,84 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
     return IKB_OK;
 }
 
+// The slot's ticket counters (and, for a two-launch solve, its scratch) are reused every kTicketSlots launches, possibly
+// from another stream: stream `s` first waits for the event the slot's previous user recorded after its last kernel, and
+// records its own when everything that reads the counters has been enqueued (the memset used to race with a
+// long kernel of another stream).
+template <typename T>
+int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io, cudaStream_t s,
+                 const ChunkPlan *plan, const Merged<T> *merged, const double *pik_lambda, const SolveAux<T> *aux) {
+    const unsigned slot = const_cast<ikb_problem *>(p)->ticket_next.fetch_add(1) % kTicketSlots;
+    IKB_CUDA(cudaStreamWaitEvent(s, p->ticket_ev[slot], 0));
+    const int rc = launch_solve_impl<T>(p, prm, B, io, s, plan, merged, pik_lambda, aux, slot);
+    IKB_CUDA(cudaEventRecord(p->ticket_ev[slot], s));
+    return rc;
+}
+
 template int launch_solve<double>(const ikb_problem *, const ikb_dls_params *, int64_t, const ikb_batch_io *, cudaStream_t,
-                                  const ChunkPlan *, const Merged<double> *, const double *);
+                                  const ChunkPlan *, const Merged<double> *, const double *, const SolveAux<double> *);
 template int launch_solve<float>(const ikb_problem *, const ikb_dls_params *, int64_t, const ikb_batch_io *, cudaStream_t,
-                                 const ChunkPlan *, const Merged<float> *, const double *);
+                                 const ChunkPlan *, const Merged<float> *, const double *, const SolveAux<float> *);
+
+// ---- host views, staging, compact targets ----------------------------------------------------------------------------
+int classify_host_views(const ikb_problem *p, int64_t B, const ikb_batch_io *io, HostViews *out) {
+    const int nq = p->hp.model.nq;
+    out->compact = io->targets_format == IKB_TARGETS_COMPACT;
+    if (io->targets_format != IKB_TARGETS_SE3 && io->targets_format != IKB_TARGETS_COMPACT)
+        return fail(IKB_ERR_INVALID_ARG, "targets_format must be IKB_TARGETS_SE3 or IKB_TARGETS_COMPACT (zero-initialise ikb_batch_io)");
+    const int tsz = out->compact ? p->expand.csz : p->hp.target_size();
+    out->q0 = host_view(io->q0, io->q0_elem_stride, io->q0_batch_stride, nq, B, true);
+    out->tg = host_view(io->targets, io->targets_elem_stride, io->targets_batch_stride, tsz, B, true);
+    out->q = host_view(io->q, io->q_elem_stride, io->q_batch_stride, nq, B, false);
+    if (out->q0.kind == VIEW_BAD || out->tg.kind == VIEW_BAD || out->q.kind == VIEW_BAD)
+        return fail(IKB_ERR_INVALID_ARG, "host views must be SoA rows (batch_stride 1, elem_stride >= B), AoS records (elem_stride 1, "
+                                         "batch_stride >= element count) or, for inputs, a broadcast (batch_stride 0)");
+    return IKB_OK;
+}
+
+template <typename T>
+int prepare_staging(const ikb_problem *p, Staging<T> &st, const HostViews &hv, long long B, ikb_batch_io *dio) {
+    const int tsz = p->hp.target_size();
+    int rc;
+    // the SE3 targets the kernels read: as copied in, or expanded from the compact record in the same orientation
+    HostView tgd = hv.tg;
+    tgd.n = tsz;
+    if ((rc = ensure(st.q0, st.q0_cap, std::max<size_t>(hv.q0.dev_count(B), 1))) || (rc = ensure(st.targets, st.tg_cap, std::max<size_t>(tgd.dev_count(B), 1))) ||
+        (rc = ensure(st.q, st.q_cap, std::max<size_t>(hv.q.dev_count(B), 1))) || (rc = ensure(st.resid, st.b_cap, (size_t)std::max<long long>(B, 1))))
+        return rc;
+    if (hv.compact && (rc = ensure(st.compact, st.compact_cap, std::max<size_t>(hv.tg.dev_count(B), 1)))) return rc;
+    dio->q0 = st.q0; dio->q0_elem_stride = hv.q0.dev_es(B); dio->q0_batch_stride = hv.q0.dev_bs();
+    dio->targets = st.targets; dio->targets_elem_stride = tgd.dev_es(B); dio->targets_batch_stride = tgd.dev_bs();
+    dio->q = st.q; dio->q_elem_stride = hv.q.dev_es(B); dio->q_batch_stride = hv.q.dev_bs();
+    dio->resid = st.resid;
+    dio->targets_format = IKB_TARGETS_SE3;
+    return IKB_OK;
+}
+
+template <typename T>
+int stage_inputs(const ikb_problem *p, Staging<T> &st, const HostViews &hv, long long B, long long b0, long long b1, bool first, cudaStream_t s) {
+    int rc;
+    if ((rc = copy_view_in<T>(st.q0, hv.q0, B, b0, b1, first, s))) return rc;
+    if (!hv.compact) return copy_view_in<T>(st.targets, hv.tg, B, b0, b1, first, s);
+    if ((rc = copy_view_in<T>(st.compact, hv.tg, B, b0, b1, first, s))) return rc;
+    // a broadcast compact record expands to one broadcast SE3 record (one "problem")
+    const bool bc = hv.tg.kind == VIEW_BCAST;
+    if (bc && !first) return IKB_OK;
+    const long long e0 = bc ? 0 : b0, e1 = bc ? 1 : b1;
+    if (e1 <= e0) return IKB_OK;
+    HostView tgd = hv.tg;
+    tgd.n = p->hp.target_size();
+    const int threads = 128;
+    expand_targets_kernel<T><<<(unsigned)((e1 - e0 + threads - 1) / threads), threads, 0, s>>>(
+        p->expand, st.compact, hv.tg.dev_es(B), hv.tg.dev_bs(), st.targets, tgd.dev_es(B), tgd.dev_bs(), e0, e1);
+    IKB_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return IKB_OK;
+}
+template int prepare_staging<double>(const ikb_problem *, Staging<double> &, const HostViews &, long long, ikb_batch_io *);
+template int prepare_staging<float>(const ikb_problem *, Staging<float> &, const HostViews &, long long, ikb_batch_io *);
+template int stage_inputs<double>(const ikb_problem *, Staging<double> &, const HostViews &, long long, long long, long long, bool, cudaStream_t);
+template int stage_inputs<float>(const ikb_problem *, Staging<float> &, const HostViews &, long long, long long, long long, bool, cudaStream_t);
 
 }  // namespace capi
 }  // namespace ikb
@@ -264,33 +368,6 @@ namespace {
 template <typename T> Staging<T> &staging(ikb_problem *p);
 template <> Staging<double> &staging<double>(ikb_problem *p) { return p->st64; }
 template <> Staging<float> &staging<float>(ikb_problem *p) { return p->st32; }
-
-// A strided [n_elem][B] view of a host array (include/ikb200.h: element k of problem b at base[k * es + b * bs]).
-struct View {
-    const void *base;
-    long long es, bs;
-    int n_elem;
-    // can batch slices be copied on their own?  SoA rows (bs == 1), dense AoS (es == 1, bs == n_elem), broadcast (bs == 0)
-    bool sliceable(long long B) const {
-        if (n_elem <= 0 || bs == 0) return true;
-        if (bs == 1) return es >= B;
-        return es == 1 && bs == n_elem;
-    }
-};
-// Host-to-device copy of batch slice [b0, b1) of `v` into the staging buffer `dst` (same strides as the view).
-template <typename T> int copy_in_slice(T *dst, const View &v, long long B, long long b0, long long b1, bool first, cudaStream_t s) {
-    if (v.n_elem <= 0) return IKB_OK;
-    const T *src = (const T *)v.base;
-    if (v.bs == 0) {
-        if (first) IKB_CUDA(cudaMemcpyAsync(dst, src, view_extent(v.n_elem, v.es, 0, 1) * sizeof(T), cudaMemcpyHostToDevice, s));
-    } else if (v.bs == 1) {
-        IKB_CUDA(cudaMemcpy2DAsync(dst + b0, (size_t)v.es * sizeof(T), src + b0, (size_t)v.es * sizeof(T), (size_t)(b1 - b0) * sizeof(T),
-                                   (size_t)v.n_elem, cudaMemcpyHostToDevice, s));
-    } else {
-        IKB_CUDA(cudaMemcpyAsync(dst + b0 * v.bs, src + b0 * v.bs, (size_t)(b1 - b0) * v.bs * sizeof(T), cudaMemcpyHostToDevice, s));
-    }
-    return IKB_OK;
-}
 
 // IKB_HOST_TRACE=1: print the device-side timeline of one host-path solve (debug aid for the e2e numbers in DESIGN.md)
 struct HostTrace {
@@ -318,16 +395,14 @@ struct HostTrace {
 };
 
 template <typename T>
-int solve_host(ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io, const double *pik_lambda = nullptr) {
-    const int nq = p->hp.model.nq, tsz = p->hp.target_size();
+int solve_host(ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_batch_io *io, const double *pik_lambda = nullptr,
+               double *aux_dq = nullptr, double *aux_e = nullptr, double *aux_J = nullptr) {
     Staging<T> &st = staging<T>(p);
-    const size_t n_q0 = view_extent(nq, io->q0_elem_stride, io->q0_batch_stride, B);
-    const size_t n_tg = tsz > 0 ? view_extent(tsz, io->targets_elem_stride, io->targets_batch_stride, B) : 0;
-    const size_t n_q = view_extent(nq, io->q_elem_stride, io->q_batch_stride, B);
+    HostViews hv;
     int rc;
-    if ((rc = ensure(st.q0, st.q0_cap, n_q0)) || (rc = ensure(st.targets, st.tg_cap, std::max<size_t>(n_tg, 1))) ||
-        (rc = ensure(st.q, st.q_cap, n_q)) || (rc = ensure(st.resid, st.b_cap, (size_t)B)))
-        return rc;
+    if ((rc = classify_host_views(p, B, io, &hv))) return rc;
+    ikb_batch_io dio = *io;
+    if ((rc = prepare_staging<T>(p, st, hv, B, &dio))) return rc;
     if ((size_t)B > p->st_flag_cap) {
         if (p->st_success) cudaFree(p->st_success);
         if (p->st_iters) cudaFree(p->st_iters);
@@ -339,49 +414,57 @@ int solve_host(ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_b
     cudaStream_t s = p->stream;
     HostTrace tr;
     tr.mark("start", s);
-    ikb_batch_io dio = *io;
-    dio.q0 = st.q0;
-    dio.targets = st.targets;
-    dio.q = st.q;
     dio.success = p->st_success;
     dio.iters = p->st_iters;
-    dio.resid = st.resid;
-    // A two-launch solve whose input views can be cut into batch slices is pipelined: slice c + 1 crosses PCIe while the
-    // BULK launch of slice c runs (the staging buffers keep the caller's strides, so a slice is a 2-D or a dense copy).
-    const View vq{io->q0, (long long)io->q0_elem_stride, (long long)io->q0_batch_stride, nq};
-    const View vt{io->targets, (long long)io->targets_elem_stride, (long long)io->targets_batch_stride, tsz};
+    // extra outputs of the *_solve_ex calls (FP64, tiny batches): device scratch freed right after the call
+    SolveAux<T> aux;
+    const int nv = p->hp.model.nv, rows = p->hp.rows();
+    const bool want_aux = aux_dq || aux_e || aux_J;
+    if (want_aux) {
+        IKB_CUDA(cudaMalloc(&aux.dq, (size_t)B * nv * sizeof(T)));
+        IKB_CUDA(cudaMalloc(&aux.e, (size_t)B * rows * sizeof(T)));
+        IKB_CUDA(cudaMalloc(&aux.J, (size_t)B * rows * nv * sizeof(T)));
+    }
+    // A two-launch solve is pipelined by batch slices: slice c + 1 crosses PCIe while the BULK launch of slice c runs
+    // (the staging buffers are dense, so a slice is a 2-D or a contiguous copy).
     const char *slices_env = std::getenv("IKB_HOST_SLICES");
     const int nslice = (int)std::min<int64_t>(slices_env ? std::max(1, std::min(8, std::atoi(slices_env))) : 4, B / 8192);
     const char *pipe_env = std::getenv("IKB_HOST_PIPELINE");
-    if (!pik_lambda && two_phase(p, prm, B) && nslice >= 2 && vq.sliceable(B) && vt.sliceable(B) && !(pipe_env && pipe_env[0] == '0')) {
+    if (!pik_lambda && !want_aux && two_phase(p, prm, B) && nslice >= 2 && !(pipe_env && pipe_env[0] == '0')) {
         ChunkPlan plan;
         plan.n = nslice;
         plan.aux = p->stream_aux;
         plan.ev_aux = p->ev_aux;
         plan.ev_main = p->ev_main;
         for (int c = 0; c <= nslice; ++c) plan.begin[c] = c == nslice ? B : (B / nslice * c) / 32 * 32;
+        // the staging buffers may still be read by the previous call's kernels on `s`: order the copy stream behind it
+        IKB_CUDA(cudaEventRecord(p->ev_main, s));
+        IKB_CUDA(cudaStreamWaitEvent(p->stream_in, p->ev_main, 0));
         for (int c = 0; c < nslice; ++c) {
-            if ((rc = copy_in_slice<T>(st.q0, vq, B, plan.begin[c], plan.begin[c + 1], c == 0, p->stream_in)) ||
-                (rc = copy_in_slice<T>(st.targets, vt, B, plan.begin[c], plan.begin[c + 1], c == 0, p->stream_in)))
-                return rc;
+            if ((rc = stage_inputs<T>(p, st, hv, B, plan.begin[c], plan.begin[c + 1], c == 0, p->stream_in))) return rc;
             plan.ready[c] = p->ev_in[c];
             IKB_CUDA(cudaEventRecord(plan.ready[c], p->stream_in));
             tr.mark("h2d slice", p->stream_in);
         }
         if ((rc = launch_solve<T>(p, prm, B, &dio, s, &plan))) return rc;
     } else {
-        IKB_CUDA(cudaMemcpyAsync(st.q0, io->q0, n_q0 * sizeof(T), cudaMemcpyHostToDevice, s));
-        if (n_tg) IKB_CUDA(cudaMemcpyAsync(st.targets, io->targets, n_tg * sizeof(T), cudaMemcpyHostToDevice, s));
+        if ((rc = stage_inputs<T>(p, st, hv, B, 0, B, true, s))) return rc;
         tr.mark("h2d", s);
-        if ((rc = launch_solve<T>(p, prm, B, &dio, s, nullptr, nullptr, pik_lambda))) return rc;
+        if ((rc = launch_solve<T>(p, prm, B, &dio, s, nullptr, nullptr, pik_lambda, want_aux ? &aux : nullptr))) return rc;
     }
     tr.mark("solve", s);
-    IKB_CUDA(cudaMemcpyAsync(io->q, st.q, n_q * sizeof(T), cudaMemcpyDeviceToHost, s));
+    if ((rc = copy_view_out<T>(hv.q, st.q, B, s))) return rc;
     if (io->success) IKB_CUDA(cudaMemcpyAsync(io->success, p->st_success, (size_t)B, cudaMemcpyDeviceToHost, s));
     if (io->iters) IKB_CUDA(cudaMemcpyAsync(io->iters, p->st_iters, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, s));
     if (io->resid) IKB_CUDA(cudaMemcpyAsync(io->resid, st.resid, (size_t)B * sizeof(T), cudaMemcpyDeviceToHost, s));
+    if constexpr (std::is_same<T, double>::value) {
+        if (aux_dq) IKB_CUDA(cudaMemcpyAsync(aux_dq, aux.dq, (size_t)B * nv * sizeof(T), cudaMemcpyDeviceToHost, s));
+        if (aux_e) IKB_CUDA(cudaMemcpyAsync(aux_e, aux.e, (size_t)B * rows * sizeof(T), cudaMemcpyDeviceToHost, s));
+        if (aux_J) IKB_CUDA(cudaMemcpyAsync(aux_J, aux.J, (size_t)B * rows * nv * sizeof(T), cudaMemcpyDeviceToHost, s));
+    }
     tr.mark("d2h", s);
     IKB_CUDA(cudaStreamSynchronize(s));
+    if (want_aux) { cudaFree(aux.dq); cudaFree(aux.e); cudaFree(aux.J); }
     tr.dump();
     return IKB_OK;
 }
@@ -394,6 +477,7 @@ int ikb_dls_solve_batch(const ikb_problem *p, int dtype, const ikb_dls_params *p
     int rc = check_solve_args(p, dtype, prm, B, io);
     if (rc) return rc;
     if (B == 0) return IKB_OK;
+    if (io->targets_format != IKB_TARGETS_SE3) return fail(IKB_ERR_INVALID_ARG, "compact targets are a wire format of the HOST entry points");
     DeviceGuard g(p->device);
     cudaStream_t s = (cudaStream_t)cuda_stream;
     return dtype == IKB_F64 ? launch_solve<double>(p, prm, B, io, s) : launch_solve<float>(p, prm, B, io, s);
@@ -431,6 +515,7 @@ int ikb_pik_solve_batch(const ikb_problem *p, int dtype, const ikb_pik_params *p
     int rc = pik_to_dls(p, prm, &d);
     if (rc || (rc = check_solve_args(p, dtype, &d, B, io))) return rc;
     if (B == 0) return IKB_OK;
+    if (io->targets_format != IKB_TARGETS_SE3) return fail(IKB_ERR_INVALID_ARG, "compact targets are a wire format of the HOST entry points");
     DeviceGuard g(p->device);
     cudaStream_t s = (cudaStream_t)cuda_stream;
     return dtype == IKB_F64 ? launch_solve<double>(p, &d, B, io, s, nullptr, nullptr, prm->lambda)
@@ -446,26 +531,49 @@ int ikb_pik_solve_batch_host(ikb_problem *p, int dtype, const ikb_pik_params *pr
     return dtype == IKB_F64 ? solve_host<double>(p, &d, B, io, prm->lambda) : solve_host<float>(p, &d, B, io, prm->lambda);
 }
 
-int ikb_dls_solve(ikb_problem *p, const ikb_dls_params *prm, const double *q0, const double *targets, double *q_out,
-                  int *success, int *iters, double *resid) {
-    if (!p) return fail(IKB_ERR_INVALID_ARG, "null problem");
-    ikb_dls_params dflt;
-    ikb_dls_params_default(&dflt);
+static int solve_one(ikb_problem *p, const ikb_dls_params *prm, const double *pik_lambda, const double *q0, const double *targets,
+                     double *q_out, int *success, int *iters, double *resid, double *dq, double *e, double *J) {
     const int nq = p->hp.model.nq, tsz = p->hp.target_size();
     uint8_t ok = 0;
     int32_t it = 0;
     double r = 0;
-    ikb_batch_io io;
+    ikb_batch_io io = {};
     io.q0 = q0; io.q0_elem_stride = 1; io.q0_batch_stride = nq;
     io.targets = targets; io.targets_elem_stride = 1; io.targets_batch_stride = tsz;
     io.q = q_out; io.q_elem_stride = 1; io.q_batch_stride = nq;
     io.success = &ok; io.iters = &it; io.resid = &r;
-    int rc = ikb_dls_solve_batch_host(p, IKB_F64, prm ? prm : &dflt, 1, &io);
+    int rc = check_solve_args(p, IKB_F64, prm, 1, &io);
     if (rc) return rc;
+    DeviceGuard g(p->device);
+    if ((rc = solve_host<double>(p, prm, 1, &io, pik_lambda, dq, e, J))) return rc;
     if (success) *success = ok;
     if (iters) *iters = it;
     if (resid) *resid = r;
     return IKB_OK;
+}
+
+int ikb_dls_solve(ikb_problem *p, const ikb_dls_params *prm, const double *q0, const double *targets, double *q_out,
+                  int *success, int *iters, double *resid) {
+    return ikb_dls_solve_ex(p, prm, q0, targets, q_out, success, iters, resid, nullptr, nullptr, nullptr);
+}
+
+int ikb_dls_solve_ex(ikb_problem *p, const ikb_dls_params *prm, const double *q0, const double *targets, double *q_out,
+                     int *success, int *iters, double *resid, double *dq, double *e, double *J) {
+    if (!p) return fail(IKB_ERR_INVALID_ARG, "null problem");
+    ikb_dls_params dflt;
+    ikb_dls_params_default(&dflt);
+    return solve_one(p, prm ? prm : &dflt, nullptr, q0, targets, q_out, success, iters, resid, dq, e, J);
+}
+
+int ikb_pik_solve_ex(ikb_problem *p, const ikb_pik_params *prm, const double *q0, const double *targets, double *q_out,
+                     int *success, int *iters, double *resid, double *dq, double *e, double *J) {
+    ikb_pik_params dflt;
+    ikb_pik_params_default(&dflt);
+    if (!prm) prm = &dflt;
+    ikb_dls_params d;
+    int rc = pik_to_dls(p, prm, &d);
+    if (rc) return rc;
+    return solve_one(p, &d, prm->lambda, q0, targets, q_out, success, iters, resid, dq, e, J);
 }
 
 }  // extern "C"

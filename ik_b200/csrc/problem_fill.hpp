@@ -41,6 +41,15 @@ inline std::vector<int> used_frames(const HostProblem &hp) {
 inline bool build_coop_tables(const HostProblem &hp, const std::vector<int> &order, CoopTables &C) {
     const HostModel &m = hp.model;
     std::memset(&C, 0, sizeof(C));
+    {
+        const std::vector<int> used = used_frames(hp);
+        const SE3d id = se3_identity();
+        for (size_t f = 0; f < used.size() && f < (size_t)kMaxFrames; ++f) {
+            bool is_id = true;
+            for (int k = 0; k < 12; ++k) is_id = is_id && m.frame_placement[used[f]][k] == id[k];
+            C.f_ident[f] = is_id ? (m.frame_parent[used[f]] == 0 ? 2 : 1) : 0;
+        }
+    }
     const int nj = m.njoints();
     std::vector<char> need(nj, 0);
     auto mark = [&](int frame) {

@@ -108,5 +108,5 @@ int l32(const SpecHostConsts &hc, const SolveArgs<float> &a, int v, long long n,
     return launch<float>(hc, a, v, n, sms, s, 3);  // with presolve the 3-role split wins in FP32 too (156 vs 145 M solves/s merged)
 }
 }  // namespace
-extern const SpecializedKernel kSpecCassieFeetPelvis = {S3::name(), spec_matches<S3>, l64, l32};
+extern const SpecializedKernel kSpecCassieFeetPelvis = {S3::name(), spec_matches<S3>, l64, l32, spec_near_miss<S3>};
 }  // namespace ikb

@@ -16,5 +16,5 @@ template <typename T> int launch(const SpecHostConsts &hc, const SolveArgs<T> &a
 int l64(const SpecHostConsts &hc, const SolveArgs<double> &a, int v, long long n, int sms, cudaStream_t s) { return launch<double>(hc, a, v, n, sms, s); }
 int l32(const SpecHostConsts &hc, const SolveArgs<float> &a, int v, long long n, int sms, cudaStream_t s) { return launch<float>(hc, a, v, n, sms, s); }
 }  // namespace
-extern const SpecializedKernel kSpecHumanoidLimbs = {S::name(), spec_matches<S>, l64, l32};
+extern const SpecializedKernel kSpecHumanoidLimbs = {S::name(), spec_matches<S>, l64, l32, spec_near_miss<S>};
 }  // namespace ikb

@@ -28,4 +28,10 @@ const SpecializedKernel *find_specialized(const HostProblem &hp) {
     return nullptr;
 }
 
+const SpecializedKernel *find_near_miss(const HostProblem &hp, std::string *why) {
+    for (const SpecializedKernel *const *k = kRegistry; *k; ++k)
+        if ((*k)->near_miss && (*k)->near_miss(hp, why)) return *k;
+    return nullptr;
+}
+
 }  // namespace ikb

@@ -4,6 +4,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <string>
+
 #include "dev_problem.hpp"
 #include "model.hpp"
 
@@ -26,7 +28,11 @@ struct SpecializedKernel {
     // n = upper bound on the number of problems the launch will see (sizes the grid)
     int (*launch64)(const SpecHostConsts &hc, const SolveArgs<double> &a, int variant, long long n, int sm_count, cudaStream_t s);
     int (*launch32)(const SpecHostConsts &hc, const SolveArgs<float> &a, int variant, long long n, int sm_count, cudaStream_t s);
+    // same topology / task list, other placement values (dls_spec.cuh spec_near_miss): `why` explains
+    bool (*near_miss)(const HostProblem &hp, std::string *why);
 };
+// the first compiled specialisation that is a near miss for `hp` (nullptr: none)
+const SpecializedKernel *find_near_miss(const HostProblem &hp, std::string *why);
 
 const SpecializedKernel *find_specialized(const HostProblem &hp);
 // all compiled specialisations (NULL-terminated), for introspection / tests

@@ -22,8 +22,13 @@
 //   ik::vector_t ik::dls(problem, q0, data, visitor, p)  ik/ik/dls.hpp:111-114          same signature
 //   -- extension the reference lacks --                                                 ik::dls_batch (host arrays), ik::dls_batch_queue;  ik::pik / pik_data / pik_parameters (pik.hpp)
 //
-// Not provided (outside the hot path): pik, FrameConstraint, CentreOfMassTask.  Eigen is not a
-// dependency: vector_t / se3_t are minimal value types with the accessors the reference's callers use.
+//   -- several GPUs --                                                                  ik::dls_batch(..., devices): the batch is sharded over the listed GPUs (ikb_multi_*)
+//
+// Eigen is not a dependency: vector_t / se3_t are minimal value types with the accessors the reference's callers use.
+// Where <Eigen/Core> is available (the reference's own environment, common.hpp:23-38) the header also provides the
+// Eigen / Pinocchio-shaped overloads: dls(problem, Eigen::VectorXd, ...) -> Eigen::VectorXd, se3_t from / to
+// (Eigen::Matrix3d, Eigen::Vector3d), dls_data::e_eigen() / J_eigen() / dq_eigen() -- so the reference's call sites
+// (cassie.cpp:95-113) compile unchanged.
 #pragma once
 #include <array>
 #include <cstddef>
@@ -35,6 +40,13 @@
 #include <vector>
 
 #include "../ikb200.h"
+
+#if defined(__has_include)
+#if __has_include(<Eigen/Core>) && !defined(IK_NO_EIGEN)
+#include <Eigen/Core>
+#define IK_HAVE_EIGEN 1
+#endif
+#endif
 
 namespace ik {
 
@@ -56,6 +68,18 @@ struct se3_t {  // pinocchio::SE3: rotation row-major, translation
     const std::array<number_t, 9> &rotation() const { return R; }
     std::array<number_t, 3> &translation() { return p; }
     const std::array<number_t, 3> &translation() const { return p; }
+#ifdef IK_HAVE_EIGEN
+    // pinocchio::SE3(R, p) / .rotation() / .translation() for Eigen callers (cassie.cpp:95-99 writes target.translation())
+    se3_t() = default;
+    se3_t(const Eigen::Matrix3d &Rm, const Eigen::Vector3d &pv) {
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) R[3 * i + j] = Rm(i, j);
+            p[i] = pv[i];
+        }
+    }
+    Eigen::Map<Eigen::Matrix<number_t, 3, 3, Eigen::RowMajor>> rotation_eigen() { return Eigen::Map<Eigen::Matrix<number_t, 3, 3, Eigen::RowMajor>>(R.data()); }
+    Eigen::Map<Eigen::Matrix<number_t, 3, 1>> translation_eigen() { return Eigen::Map<Eigen::Matrix<number_t, 3, 1>>(p.data()); }
+#endif
 };
 
 // Flattened kinematic tree; copies share the immutable handle (the reference copies the Pinocchio model by value).
@@ -273,9 +297,12 @@ class InverseKinematicsProblem {  // ik/ik/problem.hpp:9-206
     const std::vector<std::pair<std::shared_ptr<Task>, std::size_t>> &ordered_tasks() const { return ordered_; }
     // Finalized C handle for `device`; rebuilt when tasks or weights changed since the last call.
     ikb_problem *handle(int device = 0) {
-        vector_t w;
-        for (const auto &tp : ordered_)
+        vector_t w;   // everything finalize bakes into the handle: row weights and posture masks (data.cpp:49-50, posture.hpp:52)
+        for (const auto &tp : ordered_) {
             for (number_t x : tp.first->weighting()) w.push_back(x);
+            if (tp.first->kind() == Task::Kind::Posture)
+                for (number_t x : static_cast<const PostureTask &>(*tp.first).mask) w.push_back(x);
+        }
         if (h_ && w == baked_weights_ && device == device_) return h_;
         release();
         check(ikb_problem_create(model_.handle(), (int)max_priority_level_, &h_), "ikb_problem_create");
@@ -376,12 +403,24 @@ class InverseKinematicsProblem {  // ik/ik/problem.hpp:9-206
     int device_ = 0;
 };
 
-// ik/ik/visitor.hpp:7-24.  The stop test runs inside the kernel, so it cannot be an arbitrary virtual call: the
-// default test  ||e[0]||^2 < tolerance  (priority-0 rows, 1e-4 in the reference) is what is supported.
+// ik/ik/visitor.hpp:7-24.  The stock stop test  ||e[0]||^2 < tolerance  (priority-0 rows, 1e-4 in the reference) runs
+// inside the kernel.  A class that OVERRIDES should_stop is honoured by ik::dls / ik::pik: the loop of dls.cpp:14-74 then
+// runs on the host, one device iteration per step, and the override sees e and dq where the reference calls it.
+class InverseKinematicsProblem;
 class inverse_kinematics_visitor {
    public:
     inverse_kinematics_visitor() = default;
+    virtual ~inverse_kinematics_visitor() = default;
     number_t tolerance = 1e-4;
+    // visitor.hpp:15-21: e = the weighted error vector of every priority level, dq = the step just computed
+    virtual bool should_stop(const InverseKinematicsProblem &problem, const std::vector<vector_t> &e, const vector_t &dq) const {
+        (void)problem; (void)dq;
+        number_t s = 0;
+        for (number_t x : e.at(0)) s += x * x;
+        return s < tolerance;
+    }
+    // true for the stock test (which the kernel evaluates); an overriding class returns false
+    virtual bool is_default_test() const { return true; }
 };
 class default_inverse_kinematics_visitor : public inverse_kinematics_visitor {};
 
@@ -397,12 +436,43 @@ struct dls_info {  // ik/ik/dls.hpp:71-74 (never filled by the reference; filled
 
 class dls_data {  // ik/ik/dls.hpp:34-65 + ik/ik/data.hpp:8-28: the user-owned per-solve record
    public:
-    explicit dls_data(const InverseKinematicsProblem &problem) : q(problem.model().nq, 0.0), dq(problem.model().nv, 0.0) {}
+    explicit dls_data(const InverseKinematicsProblem &problem) : q(problem.model().nq, 0.0), dq(problem.model().nv, 0.0) {
+        std::size_t rows = 0;
+        for (std::size_t l = 0; l <= problem.max_priority_level(); ++l) {
+            e.emplace_back(problem.e_size(l), 0.0);                                // data.hpp:24, data.cpp:15-18
+            J.emplace_back(problem.e_size(l) * (std::size_t)problem.model().nv, 0.0);
+            rows += problem.e_size(l);
+        }
+        et.assign(rows, 0.0);
+        Jt.assign(rows * (std::size_t)problem.model().nv, 0.0);
+    }
     bool success = false;
     vector_t q;
-    vector_t dq;  // kept for layout compatibility; the batched kernels do not export the last step
+    vector_t dq;                 // problem_data::dq: the last step direction computed (dls.cpp:52)
+    std::vector<vector_t> e;     // weighted task errors per priority level, as of the last evaluation (data.hpp:24)
+    std::vector<vector_t> J;     // weighted task Jacobians per priority level, row-major [e_size(l)][nv] (data.hpp:26)
+    vector_t et, Jt;             // the stacked copies ik::dls works on (dls.hpp:54-57, dls.cpp:18-24), Jt row-major [rows][nv]
     dls_info info;
     number_t residual = 0;  // ||e[0]||^2 at the last evaluation (visitor.hpp:19)
+#ifdef IK_HAVE_EIGEN
+    Eigen::Map<const Eigen::VectorXd> q_eigen() const { return Eigen::Map<const Eigen::VectorXd>(q.data(), (Eigen::Index)q.size()); }
+    Eigen::Map<const Eigen::VectorXd> dq_eigen() const { return Eigen::Map<const Eigen::VectorXd>(dq.data(), (Eigen::Index)dq.size()); }
+    Eigen::Map<const Eigen::VectorXd> e_eigen(std::size_t level) const { return Eigen::Map<const Eigen::VectorXd>(e.at(level).data(), (Eigen::Index)e.at(level).size()); }
+    Eigen::Map<const Eigen::Matrix<number_t, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor>> J_eigen(std::size_t level) const {
+        const Eigen::Index nv = (Eigen::Index)dq.size();
+        return Eigen::Map<const Eigen::Matrix<number_t, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor>>(J.at(level).data(), (Eigen::Index)e.at(level).size(), nv);
+    }
+#endif
+    // (bridge) split the stacked e / J of the last evaluation into the per-level members
+    void scatter_levels(std::size_t nv) {
+        std::size_t r0 = 0;
+        for (std::size_t l = 0; l < e.size(); ++l) {
+            const std::size_t m = e[l].size();
+            for (std::size_t i = 0; i < m; ++i) e[l][i] = et[r0 + i];
+            for (std::size_t i = 0; i < m * nv; ++i) J[l][i] = Jt[r0 * nv + i];
+            r0 += m;
+        }
+    }
 };
 
 inline ikb_dls_params to_c(const dls_parameters &p, const inverse_kinematics_visitor &v) {
@@ -417,21 +487,54 @@ inline ikb_dls_params to_c(const dls_parameters &p, const inverse_kinematics_vis
     return c;
 }
 
-// vector_t ik::dls(problem, q0, data, visitor, p) -- reference ik/ik/dls.hpp:111-114, dls.cpp:5-78.
+// vector_t ik::dls(problem, q0, data, visitor, p) -- reference ik/ik/dls.hpp:111-114, dls.cpp:5-78.  `data` receives what
+// the reference leaves in it: success, q, dq, e, J of the last evaluation (data.hpp:15-28).
 inline vector_t dls(InverseKinematicsProblem &problem, const vector_t &q0, dls_data &data,
                     const inverse_kinematics_visitor &visitor = inverse_kinematics_visitor(),
                     const dls_parameters &p = dls_parameters()) {
     if ((int)q0.size() != problem.model().nq) throw std::invalid_argument("dls: q0 has the wrong size");
-    const ikb_dls_params c = to_c(p, visitor);
     const vector_t targets = problem.gather_targets();
+    const std::size_t nv = (std::size_t)problem.model().nv;
     int ok = 0, it = 0;
     data.q.assign(q0.size(), 0.0);
-    check(ikb_dls_solve(problem.handle(), &c, q0.data(), targets.data(), data.q.data(), &ok, &it, &data.residual), "ikb_dls_solve");
+    data.dq.assign(nv, 0.0);
+    if (visitor.is_default_test()) {
+        const ikb_dls_params c = to_c(p, visitor);
+        check(ikb_dls_solve_ex(problem.handle(), &c, q0.data(), targets.data(), data.q.data(), &ok, &it, &data.residual, data.dq.data(),
+                               data.et.data(), data.Jt.data()), "ikb_dls_solve_ex");
+        data.scatter_levels(nv);
+    } else {
+        // overridden stop test: dls.cpp:14-74 on the host, one device iteration (tolerance < 0: never stops itself) per step
+        dls_parameters one = p;
+        one.max_iterations = 1;
+        inverse_kinematics_visitor never;
+        never.tolerance = -1.0;
+        const ikb_dls_params c = to_c(one, never);
+        vector_t q = q0, qn(q0.size());
+        for (std::size_t i = 0; i < p.max_iterations && !ok; ++i) {
+            int ok1 = 0, it1 = 0;
+            check(ikb_dls_solve_ex(problem.handle(), &c, q.data(), targets.data(), qn.data(), &ok1, &it1, &data.residual, data.dq.data(),
+                                   data.et.data(), data.Jt.data()), "ikb_dls_solve_ex");
+            data.scatter_levels(nv);
+            if (visitor.should_stop(problem, data.e, data.dq)) ok = 1;   // dls.cpp:61-64: the un-stepped iterate is returned
+            else { q = qn; ++it; }
+        }
+        data.q = q;
+    }
     data.success = ok != 0;
     data.info.success = data.success;
     data.info.iterations = it;
     return data.q;
 }
+#ifdef IK_HAVE_EIGEN
+// the reference's exact signature: vector_t = Eigen::VectorXd (common.hpp:28, dls.hpp:111-114)
+inline Eigen::VectorXd dls(InverseKinematicsProblem &problem, const Eigen::Ref<const Eigen::VectorXd> &q0, dls_data &data,
+                           const inverse_kinematics_visitor &visitor = inverse_kinematics_visitor(),
+                           const dls_parameters &p = dls_parameters()) {
+    const vector_t q = dls(problem, vector_t(q0.data(), q0.data() + q0.size()), data, visitor, p);
+    return Eigen::Map<const Eigen::VectorXd>(q.data(), (Eigen::Index)q.size());
+}
+#endif
 
 // Batched extension: B independent problems sharing the task list; host arrays, row-major [B][nq] / [B][target_size]
 // (target layout: tasks in insertion order; FrameTask = 9 rotation (row-major) + 3 translation scalars).
@@ -452,12 +555,39 @@ inline dls_batch_result dls_batch(InverseKinematicsProblem &problem, std::size_t
     r.iterations.resize(B);
     r.residual.resize(B);
     const ikb_dls_params c = to_c(p, visitor);
-    ikb_batch_io io;
+    ikb_batch_io io = {};
     io.q0 = q0; io.q0_elem_stride = 1; io.q0_batch_stride = nq;
     io.targets = targets; io.targets_elem_stride = 1; io.targets_batch_stride = tsz;
     io.q = r.q.data(); io.q_elem_stride = 1; io.q_batch_stride = nq;
     io.success = r.success.data(); io.iters = r.iterations.data(); io.resid = r.residual.data();
     check(ikb_dls_solve_batch_host(h, IKB_F64, &c, (int64_t)B, &io), "ikb_dls_solve_batch_host");
+    return r;
+}
+
+// The same batch sharded over several GPUs (north_star: "the batch shards naturally across the 8 GPUs of one box"):
+// contiguous slices, one per listed device, solved concurrently; results land in the returned host arrays (ikb_multi_*).
+inline dls_batch_result dls_batch(InverseKinematicsProblem &problem, std::size_t B, const number_t *q0, const number_t *targets,
+                                  const std::vector<int> &devices,
+                                  const inverse_kinematics_visitor &visitor = inverse_kinematics_visitor(),
+                                  const dls_parameters &p = dls_parameters()) {
+    ikb_problem *h = problem.handle(devices.empty() ? 0 : devices[0]);
+    const int nq = problem.model().nq, tsz = ikb_problem_target_size(h);
+    dls_batch_result r;
+    r.q.resize(B * nq);
+    r.success.resize(B);
+    r.iterations.resize(B);
+    r.residual.resize(B);
+    const ikb_dls_params c = to_c(p, visitor);
+    ikb_batch_io io = {};
+    io.q0 = q0; io.q0_elem_stride = 1; io.q0_batch_stride = nq;
+    io.targets = targets; io.targets_elem_stride = 1; io.targets_batch_stride = tsz;
+    io.q = r.q.data(); io.q_elem_stride = 1; io.q_batch_stride = nq;
+    io.success = r.success.data(); io.iters = r.iterations.data(); io.resid = r.residual.data();
+    ikb_multi *m = nullptr;
+    const int rc = ikb_multi_create(h, devices.data(), (int)devices.size(), 2, 1, &m);
+    std::unique_ptr<ikb_multi, void (*)(ikb_multi *)> guard(m, ikb_multi_free);
+    check(rc, "ikb_multi_create");
+    check(ikb_multi_dls_solve_batch_host(m, IKB_F64, &c, (int64_t)B, &io), "ikb_multi_dls_solve_batch_host");
     return r;
 }
 
@@ -495,15 +625,12 @@ inline vector_t pik(InverseKinematicsProblem &problem, const vector_t &q0, pik_d
     c.tolerance = visitor.tolerance;
     for (std::size_t l = 0; l < data.lambda.size() && l < 7; ++l) c.lambda[l] = data.lambda[l];
     const vector_t targets = problem.gather_targets();
-    std::uint8_t ok = 0;
-    std::int32_t it = 0;
+    int ok = 0, it = 0;
     data.q.assign(q0.size(), 0.0);
-    ikb_batch_io io;
-    io.q0 = q0.data(); io.q0_elem_stride = 1; io.q0_batch_stride = nq;
-    io.targets = targets.data(); io.targets_elem_stride = 1; io.targets_batch_stride = tsz;
-    io.q = data.q.data(); io.q_elem_stride = 1; io.q_batch_stride = nq;
-    io.success = &ok; io.iters = &it; io.resid = &data.residual;
-    check(ikb_pik_solve_batch_host(h, IKB_F64, &c, 1, &io), "ikb_pik_solve_batch_host");
+    data.dq.assign((std::size_t)problem.model().nv, 0.0);
+    (void)nq; (void)tsz;
+    check(ikb_pik_solve_ex(h, &c, q0.data(), targets.data(), data.q.data(), &ok, &it, &data.residual, data.dq.data(), nullptr, nullptr),
+          "ikb_pik_solve_ex");
     data.success = ok != 0;
     data.info.success = data.success;
     data.info.iterations = it;
@@ -538,7 +665,7 @@ class dls_batch_queue {
         out.iterations.resize(B);
         out.residual.resize(B);
         const ikb_dls_params c = to_c(p, visitor);
-        ikb_batch_io io;
+        ikb_batch_io io = {};
         io.q0 = q0; io.q0_elem_stride = 1; io.q0_batch_stride = nq;
         io.targets = targets; io.targets_elem_stride = 1; io.targets_batch_stride = tsz;
         io.q = out.q.data(); io.q_elem_stride = 1; io.q_batch_stride = nq;

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define IKB_VERSION 100 /* 0.1.0 */
+#define IKB_VERSION 200 /* 0.2.0 */
 
 typedef enum {
     IKB_OK = 0,
@@ -147,13 +147,24 @@ int ikb_problem_finalize(ikb_problem *p, int device);
 /* Host-only query (no device needed, before or after finalize): name of the compiled topology-specialised kernel
  * that matches this problem's tree and task list exactly, or NULL when the generic table-driven kernel will run. */
 const char *ikb_problem_specialisation(const ikb_problem *p);
-/* Name of the kernel variant ikb_dls_solve_batch will launch for `dtype` ("generic<...>", "cassie_feet_pelvis", ...) */
+/* Name of the kernel variant ikb_dls_solve_batch will launch for `dtype` ("coop<...>", "cassie_feet_pelvis", ...) */
 const char *ikb_problem_kernel_name(const ikb_problem *p, int dtype);
+/* Human-readable note on the kernel selection, "" when there is nothing to say.  A problem that has the topology and
+ * task list of a compiled specialisation but whose placements differ from the ones it was generated from (a re-rounded
+ * URDF literal, a moved frame) falls back to the table-driven kernel: the note names the specialisation, the first
+ * differing joint / frame and the size of the difference, and ikb_problem_finalize prints it once to stderr
+ * (IKB_QUIET=1 silences it).  Host-only; valid after ikb_problem_finalize. */
+const char *ikb_problem_status_string(const ikb_problem *p);
 
 /* ---- batched solve ------------------------------------------------------------------------------- */
 /* Strided views: element k of problem b lives at base[k*elem_stride + b*batch_stride] (strides in elements).
  * SoA batch-major [k][B] is (elem_stride=B, batch_stride=1) -- the coalesced layout the kernels are tuned for;
  * AoS [B][k] is (1, k_count).  batch_stride = 0 broadcasts one vector to the whole batch. */
+typedef enum {
+    IKB_TARGETS_SE3 = 0,     /* per FrameTask 12 scalars: rotation row-major (9) + translation (3) -- se3_t target, frame.hpp:189 */
+    IKB_TARGETS_COMPACT = 1  /* wire format of the HOST entry points, see ikb_problem_compact_target_size */
+} ikb_targets_format;
+
 typedef struct {
     const void *q0;      int64_t q0_elem_stride, q0_batch_stride;           /* nq scalars per problem */
     const void *targets; int64_t targets_elem_stride, targets_batch_stride; /* ikb_problem_target_size scalars */
@@ -161,7 +172,25 @@ typedef struct {
     uint8_t *success;  /* [B] problem_data::success (data.hpp:18); may be NULL */
     int32_t *iters;    /* [B] steps taken (dls.cpp:14 loop index at exit); may be NULL */
     void *resid;       /* [B] ||e[0]||^2 at the last evaluation (visitor.hpp:19); may be NULL */
+    int32_t targets_format; /* ikb_targets_format; 0 = IKB_TARGETS_SE3.  Zero-initialise the struct (ikb_batch_io io = {0}). */
+    int32_t reserved_;
 } ikb_batch_io;
+
+/* HOST views (the *_host entry points, ikb_queue_submit_host, ikb_multi_*): q0 / targets / q must be one of
+ *   SoA rows      batch_stride 1, elem_stride >= B   (a [k][B] array or a column slice of a wider one),
+ *   AoS records   elem_stride 1, batch_stride >= the element count (a [B][k] array or a row slice of a wider one),
+ *   a broadcast   batch_stride 0 (inputs only; elem_stride >= 1).
+ * Only the payload crosses PCIe (2-D copies skip the gaps of a sliced view); other stridings return
+ * IKB_ERR_INVALID_ARG.  DEVICE views (ikb_dls_solve_batch, ikb_queue_submit) may use any strides.
+ *
+ * Compact targets (IKB_TARGETS_COMPACT): what the reference's callers actually set (ik_ros/src/cassie.cpp:95-99: a
+ * translation for a Position task, identity pose for the pelvis) instead of 12 scalars per FrameTask.  Per task, in
+ * insertion order: FrameTask Full = unit quaternion x,y,z,w + translation (7 scalars); Position = translation (3;
+ * rotation = identity, FrameTask's default target); Orientation = quaternion (4; zero translation); AlignAxisTask,
+ * PostureTask and CentreOfMassTask targets are unchanged (3 / nj / 3).  The device expands them to SE3 before the
+ * solve (R = quaternion.toRotationMatrix()).  Cassie feet+pelvis: 13 scalars per problem instead of 36. */
+int ikb_problem_compact_target_size(const ikb_problem *p);
+int ikb_problem_task_compact_target_offset(const ikb_problem *p, int task);
 
 /* Batched ik::dls (reference dls.cpp:5-78 looped over B independent problems).  All pointers in `io` are DEVICE
  * pointers of scalar type `dtype`; the call enqueues on `cuda_stream` (a cudaStream_t, NULL = default stream)
@@ -174,9 +203,17 @@ int ikb_dls_solve_batch(const ikb_problem *p, int dtype, const ikb_dls_params *p
 int ikb_dls_solve_batch_host(ikb_problem *p, int dtype, const ikb_dls_params *params, int64_t B,
                              const ikb_batch_io *io);
 /* vector_t ik::dls(problem, q0, data, visitor, params) for ONE problem in FP64 (reference dls.hpp:111-114):
- * a batch of 1 through the host path.  dq (nv, may be NULL) receives problem_data::dq. */
+ * a batch of 1 through the host path. */
 int ikb_dls_solve(ikb_problem *p, const ikb_dls_params *params, const double *q0, const double *targets,
                   double *q_out, int *success, int *iters, double *resid);
+/* The same, also returning what the reference leaves in its public dls_data / problem_data after the call (data.hpp:15-28,
+ * dls.hpp:34-65): dq [nv] = the last step direction computed (dls.cpp:52 -- on success the one at the returned iterate,
+ * never applied), e [ikb_problem_rows] = the stacked weighted task errors and J [rows][nv] row-major = the stacked weighted
+ * task Jacobian of the last evaluation (dls.cpp:18-24).  Any of the three may be NULL.  Runs on the table-driven
+ * team-per-problem kernel (one team, the state is read out of its shared memory), also for problems that have a
+ * compiled specialisation; ikb_pik_solve_ex is the ik::pik twin (pik_data, pik.hpp:29-57). */
+int ikb_dls_solve_ex(ikb_problem *p, const ikb_dls_params *params, const double *q0, const double *targets,
+                     double *q_out, int *success, int *iters, double *resid, double *dq, double *e, double *J);
 
 /* ---- ik::pik: priority-based IK (reference ik/ik/pik.cpp:31-96, pik.hpp:13-57) ----------------
  * Per iteration: dq = 0, P = I; for every priority level i: de = e_i - J_i dq, Jb = J_i P,
@@ -195,6 +232,10 @@ int ikb_pik_solve_batch(const ikb_problem *p, int dtype, const ikb_pik_params *p
                         const ikb_batch_io *io, void *cuda_stream);
 int ikb_pik_solve_batch_host(ikb_problem *p, int dtype, const ikb_pik_params *params, int64_t B,
                              const ikb_batch_io *io);
+/* vector_t ik::pik(problem, q0, data, visitor, params) for ONE problem in FP64 (pik.hpp:59-66) with the pik_data outputs
+ * dq, e, J as ikb_dls_solve_ex (any may be NULL) */
+int ikb_pik_solve_ex(ikb_problem *p, const ikb_pik_params *params, const double *q0, const double *targets,
+                     double *q_out, int *success, int *iters, double *resid, double *dq, double *e, double *J);
 
 /* ---- pipelined queue --------------------------------------------------------------------------------
  * The reference's only caller runs ik::dls once per control tick, one call after the other
@@ -227,6 +268,33 @@ int ikb_queue_flush(ikb_queue *q);
 int ikb_queue_wait(ikb_queue *q, int64_t ticket);
 int ikb_queue_wait_on_stream(ikb_queue *q, int64_t ticket, void *cuda_stream);
 int ikb_queue_drain(ikb_queue *q);
+
+/* ---- several GPUs behind one handle ------------------------------------------------------------------------
+ * north_star: "the batch shards naturally across the 8 GPUs of one box with no NCCL beyond an optional final result
+ * gather".  An ikb_multi owns one finalized copy of the problem and one pipelined queue (depth, merge as
+ * ikb_queue_create) per listed device; every submitted HOST batch is cut into contiguous slices [r*B/G, (r+1)*B/G)
+ * (SURVEY 8e), slice r is copied to, solved on and copied back from device r on that device's own streams -- all
+ * devices run concurrently under one host thread -- and the results land directly in the caller's host arrays, so
+ * there is no gather step and no collective.  The same device may be listed more than once (its slices then share
+ * it).  ikb_multi_gather_device is the optional device-side gather of DEVICE-resident slices onto one GPU
+ * (cudaMemcpyPeerAsync over NVLink). */
+typedef struct ikb_multi ikb_multi;
+int ikb_multi_create(const ikb_problem *p /* not yet finalized, or finalized: it is copied */, const int *devices, int ndevices,
+                     int depth, int merge, ikb_multi **out);
+void ikb_multi_free(ikb_multi *m);
+int ikb_multi_device_count(const ikb_multi *m);
+ikb_problem *ikb_multi_problem(ikb_multi *m, int index); /* the finalized per-device copy (for the device-pointer API) */
+/* as ikb_queue_submit_host / ikb_queue_wait / ikb_queue_drain; one ticket covers all slices of the batch */
+int64_t ikb_multi_submit_host(ikb_multi *m, int dtype, const ikb_dls_params *params, int64_t B, const ikb_batch_io *io);
+int ikb_multi_wait(ikb_multi *m, int64_t ticket);
+int ikb_multi_drain(ikb_multi *m);
+/* blocking: submit + wait (the multi-GPU twin of ikb_dls_solve_batch_host) */
+int ikb_multi_dls_solve_batch_host(ikb_multi *m, int dtype, const ikb_dls_params *params, int64_t B, const ikb_batch_io *io);
+/* Optional result gather for DEVICE-resident sharded solves: slice r (rows [r*B/G, (r+1)*B/G) of a dense
+ * [count][B] SoA array of `elem_bytes`-sized scalars living on device r) is copied into the same rows of `dst` on
+ * device `dst_device` with cudaMemcpyPeerAsync on that slice's stream; returns after all copies have completed. */
+int ikb_multi_gather_device(ikb_multi *m, const void *const *src /* [ndevices] device pointers, each [count][B_r] */,
+                            int count, int64_t B, int elem_bytes, int dst_device, void *dst /* [count][B] */);
 
 /* pinocchio::framesForwardKinematics (reference data.cpp:28-29) for a batch: placements of `nf` frames.
  * q: device, strided as above; out: device SoA [nf*12][B] (frame-major, then the 12 SE3 scalars). */

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_version_and_defaults():
-    assert capi.lib.ikb_version() == 100
+    assert capi.lib.ikb_version() == 200
     p = capi.DlsParams()
     capi.lib.ikb_dls_params_default(C.byref(p))
     # common.hpp:61-65, dls.hpp:25, visitor.hpp:19
@@ -146,6 +146,10 @@ def test_cpp_facade_demo_matches_oracle():
         assert np.abs(np.array([float(x) for x in l[9:13]]) - q[7:11]).max() < 1e-6
     assert len([l for l in r.stdout.splitlines() if l.startswith("batch")]) == 4
     assert "queue: 3 of 3 merged batches identical" in r.stdout
+    assert "sharded batch identical 1" in r.stdout       # ik::dls_batch(..., devices) through ikb_multi_*
+    dl = [l.split() for l in r.stdout.splitlines() if l.startswith("data:")][0]
+    assert int(dl[2]) == 10 and int(dl[4]) == 220 and float(dl[6]) < 1e-15      # dls_data::e / J of the last evaluation
+    assert int(dl[13]) == 1 and int(dl[15]) != int(dl[8]) and float(dl[17]) < 5e-2   # the overridden should_stop decided
     # ik::pik through the facade (cassie.cpp:114-124): same problem, demo parameters, lambda = 1 per level
     pl = [l.split() for l in r.stdout.splitlines() if l.startswith("pik ")][0]
     tgp = np.concatenate([np.eye(3).reshape(-1), [0.0, 0.1, -0.6], np.eye(3).reshape(-1), np.zeros(3), [1.0, 0.0, 0.0]])
@@ -168,3 +172,34 @@ def test_cpp_facade_demo_matches_oracle():
     qb, okb, itb, resb, _ = O.dls(opm, om.neutral(), np.concatenate([[0.02, 0.01, -0.25], O.se3()]), O.params(step_length=0.5))
     assert int(bl[2]) == 6 and int(bl[4]) == int(okb) and int(bl[6]) == itb and abs(float(bl[8]) - resb) < 1e-9
     assert np.abs(np.array([float(x) for x in bl[10:14]]) - qb[[0, 1, 2, 7]]).max() < 1e-6
+
+
+def test_facade_eigen_branch_compiles(tmp_path):
+    """include/ik/ik.hpp offers Eigen-shaped overloads where <Eigen/Core> exists (the reference's environment,
+    common.hpp:23-38).  Eigen is not installed in this image, so the branch is compiled against tests/eigen_stub -- a
+    syntax / overload-resolution check, not a numerical one."""
+    src = tmp_path / "eig.cpp"
+    src.write_text("""
+#include <type_traits>
+#include <utility>
+#include "ik/ik.hpp"
+#ifndef IK_HAVE_EIGEN
+#error "the Eigen branch was not taken"
+#endif
+int main() {
+    Eigen::Matrix3d R; Eigen::Vector3d p;
+    ik::se3_t t(R, p);
+    (void)t.rotation_eigen(); (void)t.translation_eigen();
+    ik::model_t m;
+    if (false) {
+        ik::InverseKinematicsProblem pb(m, 0);
+        ik::dls_data d(pb);
+        Eigen::VectorXd q0(3);
+        Eigen::VectorXd q = ik::dls(pb, q0, d);
+        (void)d.e_eigen(0); (void)d.J_eigen(0); (void)d.dq_eigen(); (void)d.q_eigen(); (void)q;
+    }
+    return 0;
+}
+""")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           "-I" + os.path.join(ROOT, "tests", "eigen_stub"), "-c", str(src), "-o", str(tmp_path / "eig.o")])

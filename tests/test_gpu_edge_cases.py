@@ -141,10 +141,12 @@ def test_tight_iteration_budgets(cassie):
 
 
 def test_table_driven_kernel_two_launch_schedule(monkeypatch):
-    """Above 2 048 problems the table-driven kernel parks problems unfinished after 32 steps and continues them in a
-    second launch.  Same answers as the single launch (bit for bit) and as the oracle -- with the caller's
+    """The thread-per-problem table-driven kernel (dls_generic.cuh; since r2 only the fallback for problems beyond the
+    team-per-problem kernel's table capacities, pinned here with IKB_GENERIC_LEGACY=1): above 2 048 problems it parks
+    problems unfinished after 32 steps and continues them in a second launch.  Same answers as the single launch (bit for bit) and as the oracle -- with the caller's
     `iters` buffer and without it (internal scratch), for ik::dls and ik::pik."""
     torch = _torch()
+    monkeypatch.setenv("IKB_GENERIC_LEGACY", "1")
     m = W.cassie_model()
     pb = ik.InverseKinematicsProblem(m, 1)
     pb.add_frame_task("pelvis", ik.FrameTask(m, "pelvis", ik.KinematicType.Full))
@@ -152,6 +154,7 @@ def test_table_driven_kernel_two_launch_schedule(monkeypatch):
     pb.add_frame_task("fr", ik.FrameTask(m, "RightFootFront", ik.KinematicType.Orientation), 1)
     assert pb.specialisation() is None
     pb.finalize(0)
+    assert pb.kernel_name().startswith("generic<")
     om = oracle_model("cassie")
     opb = oracle_problem_like(pb, om)
     B = 3000
