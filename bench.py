@@ -558,31 +558,31 @@ def main():
         barrier()
         if rank == 0 and torch.cuda.device_count() >= max(world, 1):
             G = max(world, 1)
-            multi = ik.MultiGPU(pb, devices=list(range(G)), depth=4, merge=2)
+            multi = ik.MultiGPU(pb, devices=list(range(G)), depth=8, merge=4)
             Bm = B * G
             mq0 = pinned_array((nq,), np.float64)
             mq0[:] = q0_np[0]
-            mtg = [pinned_array((csz, Bm), np.float64) for _ in range(4)]
-            mout = [{"q": pinned_array((nq, Bm), np.float64), "success": pinned_array((Bm,), np.uint8)} for _ in range(4)]
-            for i in range(4):
+            mtg = [pinned_array((csz, Bm), np.float64) for _ in range(8)]
+            mout = [{"q": pinned_array((nq, Bm), np.float64), "success": pinned_array((Bm,), np.uint8)} for _ in range(8)]
+            for i in range(8):
                 mtg[i][:] = np.tile(pb.compact_targets(host_tg[i % len(host_tg)]).T, (1, G))
             def mrun(n):
                 got, tk = 0, []
                 for k in range(n):
-                    t, _ = multi.submit_host(mq0, mtg[k % 4], prm, "f64", "soa", mout[k % 4], compact=True, outputs=("q", "success"))
+                    t, _ = multi.submit_host(mq0, mtg[k % 8], prm, "f64", "soa", mout[k % 8], compact=True, outputs=("q", "success"))
                     tk.append(t)
-                    if k >= 3:
-                        multi.wait(tk[k - 3])
-                        got += int(mout[(k - 3) % 4]["success"].sum())
-                for k in range(max(0, n - 3), n):
+                    if k >= 7:
+                        multi.wait(tk[k - 7])
+                        got += int(mout[(k - 7) % 8]["success"].sum())
+                for k in range(max(0, n - 7), n):
                     multi.wait(tk[k])
-                    got += int(mout[k % 4]["success"].sum())
+                    got += int(mout[k % 8]["success"].sum())
                 return got
-            mrun(6)
+            mrun(12)
             t0 = time.perf_counter()
-            got = mrun(16)
+            got = mrun(24)
             ms_ = (time.perf_counter() - t0)
-            product_multi = {"value": got / ms_, "unit": UNIT, "devices": G, "global_batch_per_step": Bm, "steps": 16,
+            product_multi = {"value": got / ms_, "unit": UNIT, "devices": G, "global_batch_per_step": Bm, "steps": 24,
                              "api": "ikb_multi_submit_host / ikb_multi_wait from ONE host thread (compact targets, shared q0, q + success back)",
                              "note": "measured on rank 0 while the other ranks idle; no collective, results land in the caller's host arrays"}
             del multi

@@ -9,9 +9,10 @@
 // compile-time alternative, through a double-buffered shared-memory column (SHFL = false; both measured).
 // Every phase of ik::dls (reference dls.cpp:14-74) is split by DATA over the lanes (SPMD, __syncwarp between phases):
 //
-//   phase 0  lane <-> joint: liMi = placement * M_j(q) for every joint some task needs           (data.cpp:28-29)
+//   phase 0  lane <-> joint: sin / cos of the revolute coordinates of the joints some task needs
 //   phase 1  lane <-> (root-to-leaf path, row i): world placements by ROWS -- row i of R_world(j) and component i of
-//            p_world(j) depend only on row i of the parent's rotation, so a lane walks its path without communication
+//            p_world(j) depend only on row i of the parent's rotation, so a lane walks its path without communication,
+//            applying placement and joint motion on the fly                                     (data.cpp:28-29)
 //   (1b)     CentreOfMassTask only: subtree masses / first moments, leaves to root              (data.cpp:31-34)
 //   phase 2  lane <-> task: frame placements, SE3-log error (frame.hpp:37-62), Jlog6 blocks folded with the frame
 //            rotation into one (X_r, Y_r) pair of 3-vectors per task ROW: J[r][c] = X_r . d_c + Y_r . w_c with
@@ -58,7 +59,7 @@ template <> struct CoopClass<2> { using Cfg = CoopCfg<32, 36, 30, 32>; };   // h
 // row-space bases) -- they would halve the residency of the plain ik::dls kernel.
 template <typename T, class Cfg, bool EXTRA> struct alignas(16) CoopScratch {
     T Jt[Cfg::NV][Cfg::LD];   // weighted stacked task Jacobian, column-major; structural zeros are written once per kernel
-    T lM[Cfg::NJ][12];        // liMi
+    T sc[Cfg::NJ][2];         // (sin, cos) of every needed revolute joint's coordinate
     T oM[Cfg::NJ][12];        // oMi: R row-major (9) + p (3)
     T XY[Cfg::M][6];          // per task row: X (3), Y (3)
     T tpf[Cfg::M][3];         // per task: world origin of the task frame
@@ -71,49 +72,6 @@ template <typename T, class Cfg, bool EXTRA> struct alignas(16) CoopScratch {
     T W[EXTRA ? Cfg::M + kMaxConstraintRows : 1][Cfg::NV];  // ik::pik / FrameConstraint: orthonormal row-space bases (row-major)
     T Jb[EXTRA ? Cfg::NV : 1][Cfg::LDX];   // ik::pik: projected level Jacobian, column-major; FrameConstraint: Jc (rows <= 12)
 };
-
-// ---- joint transform liMi = placement * M_j(q) for every joint type the flattener emits (pinocchio JointModel*::calc) ----
-template <typename T> IKB_HD void coop_joint_local(const DevProblem<T> &P, int j, const T *q, T *L) {
-    const T *PR = P.placement[j], *Pp = PR + 9;
-    const int t = P.jtype[j];
-    const T *qj = q + P.idx_q[j];
-    T *Rl = L, *pl = L + 9;
-    if (t == IKB_J_FREEFLYER) {
-        T Rj[9];
-        quat_to_rot(qj[3], qj[4], qj[5], qj[6], Rj);
-        se3_mul(PR, Pp, Rj, qj, Rl, pl);
-    } else if (t >= IKB_J_RX && t <= IKB_J_REV_UNALIGNED) {
-        T s, c, Rj[9];
-        sincos_(qj[0], &s, &c);
-        if (t == IKB_J_RX) {
-            Rj[0] = 1; Rj[1] = 0; Rj[2] = 0; Rj[3] = 0; Rj[4] = c; Rj[5] = -s; Rj[6] = 0; Rj[7] = s; Rj[8] = c;
-        } else if (t == IKB_J_RY) {
-            Rj[0] = c; Rj[1] = 0; Rj[2] = s; Rj[3] = 0; Rj[4] = 1; Rj[5] = 0; Rj[6] = -s; Rj[7] = 0; Rj[8] = c;
-        } else if (t == IKB_J_RZ) {
-            Rj[0] = c; Rj[1] = -s; Rj[2] = 0; Rj[3] = s; Rj[4] = c; Rj[5] = 0; Rj[6] = 0; Rj[7] = 0; Rj[8] = 1;
-        } else {
-            const T *a = P.axis[j];
-            const T v = 1 - c;
-            Rj[0] = a[0] * a[0] * v + c;        Rj[1] = a[0] * a[1] * v - a[2] * s; Rj[2] = a[0] * a[2] * v + a[1] * s;
-            Rj[3] = a[0] * a[1] * v + a[2] * s; Rj[4] = a[1] * a[1] * v + c;        Rj[5] = a[1] * a[2] * v - a[0] * s;
-            Rj[6] = a[0] * a[2] * v - a[1] * s; Rj[7] = a[1] * a[2] * v + a[0] * s; Rj[8] = a[2] * a[2] * v + c;
-        }
-        mat3_mul(PR, Rj, Rl);
-        pl[0] = Pp[0]; pl[1] = Pp[1]; pl[2] = Pp[2];
-    } else if (t >= IKB_J_PX) {  // prismatic
-        T a[3] = {T(0), T(0), T(0)};
-        if (t == IKB_J_PX) a[0] = 1;
-        else if (t == IKB_J_PY) a[1] = 1;
-        else if (t == IKB_J_PZ) a[2] = 1;
-        else { a[0] = P.axis[j][0]; a[1] = P.axis[j][1]; a[2] = P.axis[j][2]; }
-        T d[3] = {a[0] * qj[0], a[1] * qj[0], a[2] * qj[0]}, o[3];
-        rot_vec(PR, d, o);
-        for (int i = 0; i < 9; ++i) Rl[i] = PR[i];
-        pl[0] = Pp[0] + o[0]; pl[1] = Pp[1] + o[1]; pl[2] = Pp[2] + o[2];
-    } else {  // universe
-        for (int i = 0; i < 12; ++i) L[i] = PR[i];
-    }
-}
 
 // World twist of velocity coordinate cc of joint j (data.cpp:30: oMi.act(S_i)) as (axis direction `ax`, origin `p`):
 // angular coordinates (revolute, free-flyer 3-5) give (v, w) = (p x ax, ax), linear ones (prismatic, free-flyer 0-2) (ax, 0).
@@ -152,25 +110,58 @@ IKB_HD void coop_evaluate(const Ctx &cx, const DevProblem<T> &P, CoopScratch<T, 
     constexpr int TEAM = Cfg::TEAM;
     const CoopTables &C = P.coop;
     const int lane = cx.lane;
-    // phase 0
+    // phase 0: lane <-> joint, sin / cos of the revolute coordinates
     for (int i = lane; i < C.n_fkj; i += TEAM) {
-        const int j = C.fkj[i];
-        coop_joint_local(P, j, S.q, S.lM[j]);
+        const int j = C.fkj[i], t = P.jtype[j];
+        if (t >= IKB_J_RX && t <= IKB_J_REV_UNALIGNED) sincos_(S.q[P.idx_q[j]], &S.sc[j][0], &S.sc[j][1]);
     }
     cx.sync();
-    // phase 1
+    // phase 1: lane <-> (path, row i).  oMi = oMi[parent] * placement * M_j(q) by rows: with r = row i of the parent's
+    // rotation, a = r * placement.R is row i of (parent * placement) and the joint motion mixes two of its entries
+    // (aligned revolutes), multiplies it by the free-flyer's rotation, or leaves it alone (prismatic).
     for (int w = lane; w < 3 * C.npaths; w += TEAM) {
         const int p = w / 3, i = w - 3 * p;
         T r0 = i == 0 ? T(1) : T(0), r1 = i == 1 ? T(1) : T(0), r2 = i == 2 ? T(1) : T(0), pp = T(0);
         const int len = C.path_len[p];
         for (int k = 0; k < len; ++k) {
-            const int j = C.path_joint[p][k];
-            const T *L = S.lM[j];
-            const T a0 = r0 * L[0] + r1 * L[3] + r2 * L[6];
-            const T a1 = r0 * L[1] + r1 * L[4] + r2 * L[7];
-            const T a2 = r0 * L[2] + r1 * L[5] + r2 * L[8];
-            pp = pp + (r0 * L[9] + r1 * L[10] + r2 * L[11]);
-            r0 = a0; r1 = a1; r2 = a2;
+            const int j = C.path_joint[p][k], t = P.jtype[j];
+            const T *PR = P.placement[j];
+            const T a0 = r0 * PR[0] + r1 * PR[3] + r2 * PR[6];
+            const T a1 = r0 * PR[1] + r1 * PR[4] + r2 * PR[7];
+            const T a2 = r0 * PR[2] + r1 * PR[5] + r2 * PR[8];
+            pp = pp + (r0 * PR[9] + r1 * PR[10] + r2 * PR[11]);
+            if (t == IKB_J_RZ) {
+                const T s = S.sc[j][0], c = S.sc[j][1];
+                r0 = a0 * c + a1 * s; r1 = a1 * c - a0 * s; r2 = a2;
+            } else if (t == IKB_J_RX) {
+                const T s = S.sc[j][0], c = S.sc[j][1];
+                r0 = a0; r1 = a1 * c + a2 * s; r2 = a2 * c - a1 * s;
+            } else if (t == IKB_J_RY) {
+                const T s = S.sc[j][0], c = S.sc[j][1];
+                r0 = a0 * c - a2 * s; r1 = a1; r2 = a0 * s + a2 * c;
+            } else if (t == IKB_J_FREEFLYER) {
+                const T *qj = S.q + P.idx_q[j];
+                T Rq[9];
+                quat_to_rot(qj[3], qj[4], qj[5], qj[6], Rq);
+                pp = pp + (a0 * qj[0] + a1 * qj[1] + a2 * qj[2]);
+                r0 = a0 * Rq[0] + a1 * Rq[3] + a2 * Rq[6];
+                r1 = a0 * Rq[1] + a1 * Rq[4] + a2 * Rq[7];
+                r2 = a0 * Rq[2] + a1 * Rq[5] + a2 * Rq[8];
+            } else if (t == IKB_J_REV_UNALIGNED) {
+                const T s = S.sc[j][0], c = S.sc[j][1], v = 1 - c;
+                const T *ax = P.axis[j];
+                const T R00 = ax[0] * ax[0] * v + c, R01 = ax[0] * ax[1] * v - ax[2] * s, R02 = ax[0] * ax[2] * v + ax[1] * s;
+                const T R10 = ax[0] * ax[1] * v + ax[2] * s, R11 = ax[1] * ax[1] * v + c, R12 = ax[1] * ax[2] * v - ax[0] * s;
+                const T R20 = ax[0] * ax[2] * v - ax[1] * s, R21 = ax[1] * ax[2] * v + ax[0] * s, R22 = ax[2] * ax[2] * v + c;
+                r0 = a0 * R00 + a1 * R10 + a2 * R20;
+                r1 = a0 * R01 + a1 * R11 + a2 * R21;
+                r2 = a0 * R02 + a1 * R12 + a2 * R22;
+            } else {   // prismatic: the rotation is the placement's, the origin moves along the joint axis
+                const T qd = S.q[P.idx_q[j]];
+                const T d = t == IKB_J_PX ? a0 : (t == IKB_J_PY ? a1 : (t == IKB_J_PZ ? a2 : a0 * P.axis[j][0] + a1 * P.axis[j][1] + a2 * P.axis[j][2]));
+                pp = pp + d * qd;
+                r0 = a0; r1 = a1; r2 = a2;
+            }
             T *O = S.oM[j];
             O[3 * i] = r0; O[3 * i + 1] = r1; O[3 * i + 2] = r2; O[9 + i] = pp;
         }

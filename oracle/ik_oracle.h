@@ -14,6 +14,30 @@
  * round trips, finite-difference Jacobians, hand-derived FK) and against the
  * provisional known answers recorded in SURVEY.md 8c.
  *
+ * Which Pinocchio is restated.  The reference pins no version (find_package(pinocchio
+ * REQUIRED), ik/ik/CMakeLists.txt:3); its toolchain markers (GLOG_USE_GLOG_EXPORT,
+ * task.hpp:3; Eigen::Vector<T,N>, common.hpp:23) put it in the Pinocchio 2.7 / 3.x era,
+ * and the formulas below are those of that era's spatial/explog.hpp, explog-quaternion.hpp,
+ * multibody/liegroup/special-euclidean.hpp and math/taylor-expansion.hpp, with these
+ * switches (so that a reader who has Pinocchio can check them one by one):
+ *   log3:   theta = acos((tr R - 1)/2), clamped to [0, pi] when the trace leaves [-1, 3];
+ *           theta >= pi - 1e-2 -> the diagonal-based formula  w_i = sign(R_kj - R_jk) *
+ *           theta * sqrt(max(0, (R_ii - cos theta) / (1 - cos theta)));  else
+ *           w = (theta > precision<2>() ? theta / (2 sin theta) : 1/2) * vee(R - R^T)
+ *   Taylor switches: TaylorSeriesExpansion<double>::precision<n>() = eps^(1/(n+1)):
+ *           precision<3>() = 1.2207e-4 (log6 alpha/beta, Jlog3 / Jlog6 coefficients, exp3 /
+ *           exp6 coefficients), precision<2>() = 6.0555e-6 (log3 scale factor)
+ *   log6:   alpha = 1 - t^2/12 - t^4/720, beta = 1/12 + t^2/720 below the switch, the closed
+ *           forms with sin / cos of theta above it; Jlog6 block B = C A with beta_dot =
+ *           1/360 below the switch
+ *   integrate (SE3): M1 = M0 exp6(v); quaternion from the rotation matrix (Eigen's branch
+ *           on the trace), sign chosen so that dot(q_new, q_old) >= 0, then the first-order
+ *           renormalisation q *= (3 - |q|^2)/2 (quaternion::firstOrderNormalize)
+ *   LDLT:   Eigen::LDLT with its diagonal pivoting (largest |diagonal| first) and D^+ with
+ *           the tolerance 1 / numeric_limits::highest (Eigen 3.4 solveInPlace)
+ * Releases of Pinocchio older than 2.6 use fixed 1e-8-style switches instead of the
+ * precision<n>() ones; results then differ at the 1e-12 level near theta = 1e-4 only.
+ *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
  * reference legs may load this library; the product (ik_b200/) never does.
  *

@@ -114,7 +114,7 @@ def _check(lib, pb, urdf, ff, q0, tg, prm=None, oprm=None, shfl=True, qtol=1e-8,
 def test_cassie_feet_pelvis(lib, shfl, params):
     pb = W.cassie_feet_pelvis_problem()
     om = oracle_model("cassie")
-    q0, tg, _ = make_workload(pb, om, 60, standing=W.CASSIE_STANDING)
+    q0, tg, _ = make_workload(pb, om, 24 if params == "defaults" else 6, standing=W.CASSIE_STANDING)
     oprm = O.params() if params == "defaults" else O.params(200, 0.1, 0.1)
     _check(lib, pb, "cassie", True, q0, tg, oprm=oprm, shfl=shfl, cls=1)
 
@@ -122,14 +122,14 @@ def test_cassie_feet_pelvis(lib, shfl, params):
 def test_cassie_demo_tasks_moving_reference_and_align_axis(lib):
     pb = W.cassie_demo_problem()
     om = oracle_model("cassie")
-    q0, tg, _ = make_workload(pb, om, 40, seed=31, standing=W.CASSIE_STANDING)
+    q0, tg, _ = make_workload(pb, om, 16, seed=31, standing=W.CASSIE_STANDING)
     _check(lib, pb, "cassie", True, q0, tg, qtol=1e-7, converged_only=True, cls=1)
 
 
 def test_cassie_demo_with_posture_on_level_1(lib):
     pb = W.cassie_demo_posture_problem()
     om = oracle_model("cassie")
-    q0, tg, _ = make_workload(pb, om, 24, seed=57, standing=W.CASSIE_STANDING)
+    q0, tg, _ = make_workload(pb, om, 8, seed=57, standing=W.CASSIE_STANDING)
     _check(lib, pb, "cassie", True, q0, tg, converged_only=True, cls=2)   # 26 rows: the 30-row class, a warp per problem
 
 
@@ -137,14 +137,14 @@ def test_cassie_demo_with_posture_on_level_1(lib):
 def test_humanoid(lib, shfl):
     pb = W.humanoid_problem()
     om = oracle_model("humanoid")
-    q0, tg, _ = make_workload(pb, om, 12 if shfl else 24, seed=5, start="near")
+    q0, tg, _ = make_workload(pb, om, 4 if shfl else 8, seed=5, start="near")
     _check(lib, pb, "humanoid", True, q0, tg, shfl=shfl, cls=2)
 
 
 def test_manipulator_and_ur5(lib):
     pb = W.manipulator_problem()
     om = oracle_model("manipulator", free_flyer=False)
-    q0, tg, _ = make_workload(pb, om, 64, seed=11, start="near")
+    q0, tg, _ = make_workload(pb, om, 24, seed=11, start="near")
     _check(lib, pb, "manipulator", False, q0, tg, cls=0)
     m = ik.Model.builtin("ur5", free_flyer=False)
     pb = ik.InverseKinematicsProblem(m, 1)
@@ -158,7 +158,7 @@ def test_manipulator_and_ur5(lib):
     om.flat["lower"][:] = m.lowerPositionLimit
     om.flat["upper"][:] = m.upperPositionLimit
     om = O.Model(om.flat)
-    q0, tg, _ = make_workload(pb, om, 64, seed=21, start="near")
+    q0, tg, _ = make_workload(pb, om, 24, seed=21, start="near")
     _check(lib, pb, "ur5", False, q0, tg, converged_only=True, cls=0)
 
 
@@ -166,7 +166,7 @@ def test_f32_build_is_close(lib):
     pb = W.cassie_feet_pelvis_problem()
     om = oracle_model("cassie")
     opb = oracle_problem_like(pb, om)
-    q0, tg, _ = make_workload(pb, om, 60, standing=W.CASSIE_STANDING)
+    q0, tg, _ = make_workload(pb, om, 32, standing=W.CASSIE_STANDING)
     q_ref, ok_ref, it_ref, _ = O.dls_batch(opb, q0, tg)
     q, ok, it, res, _, _, _ = coop_solve(lib, pb, "cassie", True, q0, tg, f32=True)
     same = (it == it_ref) & ok & ok_ref
@@ -183,7 +183,7 @@ def test_frame_constraint_projection(lib, ktype, ref):
     pb.add_frame_task("fl", ik.FrameTask(m, "LeftFootFront", ik.KinematicType.Position))
     pb.add_frame_constraint("fr", ik.FrameConstraint(m, "RightFootFront", getattr(ik.KinematicType, ktype), ref))
     om = oracle_model("cassie")
-    B = 24
+    B = 8
     q0, tg, _ = make_workload(pb, om, B, seed=91, standing=W.CASSIE_STANDING)
     s0 = W.standing_configuration(m, W.CASSIE_STANDING)
     lf = om.frame_placement(s0, om.frame_id("LeftFootFront"))[9:]
@@ -203,7 +203,7 @@ def test_centre_of_mass_task(lib):
     pb.add_frame_task("pelvis", ik.FrameTask(m, "pelvis", ik.KinematicType.Orientation))
     com.weighting()[:] = [2.0, 2.0, 0.5]
     om = oracle_model("cassie")
-    B = 24
+    B = 10
     q0, tg, qstar = make_workload(pb, om, B, seed=17, standing=W.CASSIE_STANDING)
     off = pb.target_offset(com)
     for b in range(B):
@@ -218,9 +218,9 @@ def test_pik_priority_recursion(lib, lambdas):
     pb = W.cassie_demo_posture_problem()
     om = oracle_model("cassie")
     opb = oracle_problem_like(pb, om)
-    B = 16
+    B = 6
     q0, tg, _ = make_workload(pb, om, B, seed=57, standing=W.CASSIE_STANDING)
-    mi = 40
+    mi = 30
     q_ref, ok_ref, it_ref, res_ref = O.pik_batch(opb, q0, tg, O.pik_params(mi, 1.0, lambdas))
     q, ok, it, res, _, _, _ = coop_solve(lib, pb, "cassie", True, q0, tg, O.params(max_iterations=mi), pik_lambdas=lambdas)
     assert (ok == ok_ref).all() and (it == it_ref).all()
