@@ -102,6 +102,7 @@ SIGNATURES = {
     "ikb_dls_solve_ex": (C.c_int, [_vp, C.POINTER(DlsParams), _dp, _dp, _dp, C.POINTER(C.c_int), C.POINTER(C.c_int), _dp, _dp, _dp, _dp]),
     "ikb_pik_solve_ex": (C.c_int, [_vp, C.POINTER(PikParams), _dp, _dp, _dp, C.POINTER(C.c_int), C.POINTER(C.c_int), _dp, _dp, _dp, _dp]),
     "ikb_problem_status_string": (C.c_char_p, [_vp]),
+    "ikb_load_specialisation": (C.c_int, [C.c_char_p]),
     "ikb_problem_compact_target_size": (C.c_int, [_vp]),
     "ikb_problem_task_compact_target_offset": (C.c_int, [_vp, C.c_int]),
     "ikb_multi_create": (C.c_int, [_vp, _i32p, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),

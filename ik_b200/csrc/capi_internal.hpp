@@ -88,6 +88,8 @@ struct ikb_problem {
     unsigned char *st_success = nullptr;
     int *st_iters = nullptr;
     size_t st_flag_cap = 0;
+    void *st_aux = nullptr;   // dq / e / J of the *_solve_ex calls (host path only; grown on demand)
+    size_t st_aux_cap = 0;
 };
 
 namespace ikb {

@@ -315,7 +315,7 @@ void ikb_problem_free(ikb_problem *p) {
         cudaFree(p->d_frame_pl32); cudaFree(p->d_tickets);
         cudaFree(p->st64.q0); cudaFree(p->st64.targets); cudaFree(p->st64.q); cudaFree(p->st64.resid); cudaFree(p->st64.compact);
         cudaFree(p->st32.q0); cudaFree(p->st32.targets); cudaFree(p->st32.q); cudaFree(p->st32.resid); cudaFree(p->st32.compact);
-        cudaFree(p->st_success); cudaFree(p->st_iters);
+        cudaFree(p->st_success); cudaFree(p->st_iters); cudaFree(p->st_aux);
         for (auto &sc : p->scratch) {
             cudaFree(sc.list); cudaFree(sc.iters);
             if (sc.ev) cudaEventDestroy(sc.ev);
@@ -564,6 +564,13 @@ const char *ikb_problem_specialisation(const ikb_problem *p) {
     if (!p || p->hp.tasks.empty()) return nullptr;
     const SpecializedKernel *k = select_specialized(p->hp);
     return k ? k->name : nullptr;
+}
+
+int ikb_load_specialisation(const char *path) {
+    if (!path) return fail(IKB_ERR_INVALID_ARG, "null path");
+    std::string err;
+    if (load_specialisation_plugin(path, &err)) return fail(IKB_ERR_INVALID_ARG, err);
+    return IKB_OK;
 }
 
 const char *ikb_problem_status_string(const ikb_problem *p) { return p ? p->status.c_str() : ""; }

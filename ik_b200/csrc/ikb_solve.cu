@@ -420,10 +420,17 @@ int solve_host(ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_b
     SolveAux<T> aux;
     const int nv = p->hp.model.nv, rows = p->hp.rows();
     const bool want_aux = aux_dq || aux_e || aux_J;
-    if (want_aux) {
-        IKB_CUDA(cudaMalloc(&aux.dq, (size_t)B * nv * sizeof(T)));
-        IKB_CUDA(cudaMalloc(&aux.e, (size_t)B * rows * sizeof(T)));
-        IKB_CUDA(cudaMalloc(&aux.J, (size_t)B * rows * nv * sizeof(T)));
+    if (want_aux) {   // one buffer owned by the handle (a cudaMalloc per call would dominate a single solve)
+        const size_t need = (size_t)B * ((size_t)nv + rows + (size_t)rows * nv) * sizeof(T);
+        if (need > p->st_aux_cap) {
+            if (p->st_aux) cudaFree(p->st_aux);
+            p->st_aux = nullptr; p->st_aux_cap = 0;
+            IKB_CUDA(cudaMalloc(&p->st_aux, need));
+            p->st_aux_cap = need;
+        }
+        aux.dq = (T *)p->st_aux;
+        aux.e = aux.dq + (size_t)B * nv;
+        aux.J = aux.e + (size_t)B * rows;
     }
     // A two-launch solve is pipelined by batch slices: slice c + 1 crosses PCIe while the BULK launch of slice c runs
     // (the staging buffers are dense, so a slice is a 2-D or a contiguous copy).
@@ -464,7 +471,6 @@ int solve_host(ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_b
     }
     tr.mark("d2h", s);
     IKB_CUDA(cudaStreamSynchronize(s));
-    if (want_aux) { cudaFree(aux.dq); cudaFree(aux.e); cudaFree(aux.J); }
     tr.dump();
     return IKB_OK;
 }

@@ -31,6 +31,9 @@ struct SpecializedKernel {
     // same topology / task list, other placement values (dls_spec.cuh spec_near_miss): `why` explains
     bool (*near_miss)(const HostProblem &hp, std::string *why);
 };
+// Load a specialisation compiled after the library was built (a shared object exporting
+// `extern "C" const ikb::SpecializedKernel *ikb_spec_plugin()`, made by ik_b200/specialise.py).  0 on success.
+int load_specialisation_plugin(const char *path, std::string *err);
 // the first compiled specialisation that is a near miss for `hp` (nullptr: none)
 const SpecializedKernel *find_near_miss(const HostProblem &hp, std::string *why);
 

@@ -149,6 +149,11 @@ int ikb_problem_finalize(ikb_problem *p, int device);
 const char *ikb_problem_specialisation(const ikb_problem *p);
 /* Name of the kernel variant ikb_dls_solve_batch will launch for `dtype` ("coop<...>", "cassie_feet_pelvis", ...) */
 const char *ikb_problem_kernel_name(const ikb_problem *p, int dtype);
+/* Load a topology-specialised kernel that was generated and compiled AFTER the library was built: a shared object made by
+ * `python -m ik_b200.specialise` (tools/gen_kernel.py -> nvcc) for one (URDF, task list) pair.  Problems finalized
+ * afterwards that match it exactly take its straight-line kernels instead of the table-driven one -- any robot at the
+ * speed of the built-in specialisations.  Also: IKB_SPEC_PLUGINS=a.so:b.so in the environment. */
+int ikb_load_specialisation(const char *path);
 /* Human-readable note on the kernel selection, "" when there is nothing to say.  A problem that has the topology and
  * task list of a compiled specialisation but whose placements differ from the ones it was generated from (a re-rounded
  * URDF literal, a moved frame) falls back to the table-driven kernel: the note names the specialisation, the first

@@ -203,3 +203,24 @@ int main() {
 """)
     subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
                            "-I" + os.path.join(ROOT, "tests", "eigen_stub"), "-c", str(src), "-o", str(tmp_path / "eig.o")])
+
+
+def test_plugin_specialisation_builds_and_registers():
+    """ik_b200.specialise (host side, no GPU needed: nvcc cross-compiles): generator -> nvcc -> plugin .so ->
+    ikb_load_specialisation; the host-only query then names the plugin for a problem built from the same URDF, and a
+    problem with another task list still has none."""
+    from ik_b200 import specialise as SP
+
+    m = ik.Model.builtin("ur5", free_flyer=False)
+    pb = ik.InverseKinematicsProblem(m, 0)
+    pb.add_frame_task("tool", ik.FrameTask(m, "tool0", ik.KinematicType.Full))
+    assert pb.specialisation() is None
+    so = SP.build_plugin(pb, "ur5_pose_plugin")
+    assert os.path.exists(so) and SP.build_plugin(pb, "ur5_pose_plugin") == so      # cached by content hash
+    SP.load_plugin(so)
+    SP.load_plugin(so)                                                             # idempotent
+    assert pb.specialisation() == "ur5_pose_plugin"
+    other = ik.InverseKinematicsProblem(m, 0)
+    other.add_frame_task("tool", ik.FrameTask(m, "tool0", ik.KinematicType.Position))
+    assert other.specialisation() is None
+    assert capi.lib.ikb_load_specialisation(b"/nonexistent/plugin.so") == capi.ERR_INVALID_ARG

@@ -243,3 +243,58 @@ def test_ticket_slots_survive_many_small_solves_beside_a_long_one(cassie):
         assert np.abs(q[sl] - ref[0]).max() < 1e-6
     for o in smalls:
         assert np.array_equal(o["iters"].cpu().numpy(), ref[2][:Bsmall]) and np.abs(o["q"].cpu().numpy().T - ref[0][:Bsmall]).max() < 1e-6
+
+
+def test_plugin_specialisation_for_another_robot():
+    """ik_b200.specialise: the generator + nvcc build a specialised kernel for a robot / task list the library was not
+    compiled for (UR5: RY joints, Position on level 0 + weighted Orientation on level 1); after ikb_load_specialisation the
+    problem leaves the table-driven kernel and still matches the oracle."""
+    from ik_b200 import specialise as SP
+
+    torch = _torch()
+
+    def make():
+        m = ik.Model.builtin("ur5", free_flyer=False)
+        m.set_limits(np.maximum(m.lowerPositionLimit, -3.0), np.minimum(m.upperPositionLimit, 3.0))
+        pb = ik.InverseKinematicsProblem(m, 1)
+        t_pos = ik.FrameTask(m, "tool0", ik.KinematicType.Position)
+        t_pos.weighting()[:] = [1.0, 0.5, 2.0]
+        pb.add_frame_task("pos", t_pos, 0)
+        pb.add_frame_task("ori", ik.FrameTask(m, "ee_link", ik.KinematicType.Orientation), 1)
+        return m, pb
+
+    m, pb = make()
+    pb.finalize(0)
+    assert pb.kernel_name().startswith("coop<")
+    SP.load_plugin(SP.build_plugin(pb, "ur5_tool_plugin"))
+    m2, pb2 = make()
+    assert pb2.specialisation() == "ur5_tool_plugin"
+    pb2.finalize(0)
+    assert pb2.kernel_name() == "ur5_tool_plugin"
+    om = oracle_model("ur5", free_flyer=False)
+    om.flat["lower"][:] = m.lowerPositionLimit
+    om.flat["upper"][:] = m.upperPositionLimit
+    om = O.Model(om.flat)
+    opb = oracle_problem_like(pb2, om)
+    B = 30000
+    q0, tg, _ = make_workload(pb2, om, B, seed=21, start="near")
+    ref = O.dls_batch(opb, q0, tg, nthreads=NT)
+    dq0, dtg = torch.tensor(q0.T.copy(), device="cuda:0"), torch.tensor(tg.T.copy(), device="cuda:0")
+    outs = {}
+    for name, p in (("coop", pb), ("plugin", pb2)):
+        o = ik.dls_batch(p, dq0, dtg)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            o = ik.dls_batch(p, dq0, dtg)
+        e1.record()
+        torch.cuda.synchronize()
+        ok, it = o["success"].cpu().numpy().astype(bool), o["iters"].cpu().numpy()
+        agree = (ok == ref[1]) & (it == ref[2])
+        err = np.abs(o["q"].cpu().numpy().T - ref[0])[agree & ok].max(axis=1)
+        outs[name] = e0.elapsed_time(e1) / 3
+        print("ur5 %s: %.3f ms for %d problems, agree %.5f, |dq| p99.9 %.2e max %.2e" % (name, outs[name], B, agree.mean(), np.percentile(err, 99.9), err.max()))
+        # a 6R arm: a few problems per 10,000 pass near a singularity and amplify rounding (as in the full-size manipulator test)
+        assert agree.mean() > 0.999 and np.percentile(err, 99.9) < 1e-6 and err.max() < 1e-4
+    assert outs["plugin"] < outs["coop"]
