@@ -239,7 +239,8 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
 
 // The table-driven team-per-problem kernel (ikb_coop.cu / dls_coop.cuh) for size class `cls`.
 template <typename T>
-int launch_coop(int cls, const DevProblem<T> *dP, const SolveArgs<T> &a, bool pik, bool constraints, bool shfl, int sm_count, cudaStream_t s);
+int launch_coop(int cls, const DevProblem<T> *dP, const SolveArgs<T> &a, bool pik, int extra /* 0 plain, 1 CoM, 2 constraints */, bool shfl, int sm_count,
+                cudaStream_t s);
 
 }  // namespace capi
 }  // namespace ikb

@@ -55,9 +55,10 @@ template <> struct CoopClass<0> { using Cfg = CoopCfg<10, 8, 6, 8>; };      // s
 template <> struct CoopClass<1> { using Cfg = CoopCfg<20, 24, 12, 16>; };   // Cassie-sized: 12 rows, half a warp per problem
 template <> struct CoopClass<2> { using Cfg = CoopCfg<32, 36, 30, 32>; };   // humanoid-sized: 30 rows, a warp per problem
 
-// Per-team block of shared memory.  EXTRA: the buffers only ik::pik and FrameConstraints need (projected Jacobian,
-// row-space bases) -- they would halve the residency of the plain ik::dls kernel.
-template <typename T, class Cfg, bool EXTRA> struct alignas(16) CoopScratch {
+// Per-team block of shared memory.  EXTRA = 0: plain ik::dls; 1: + the subtree mass / moment arrays of a
+// CentreOfMassTask; 2: + the buffers only ik::pik and FrameConstraints need (projected Jacobian, row-space bases) -- each
+// level costs residency, so a problem gets the smallest scratch that serves it.
+template <typename T, class Cfg, int EXTRA> struct alignas(16) CoopScratch {
     T Jt[Cfg::NV][Cfg::LD];   // weighted stacked task Jacobian, column-major; structural zeros are written once per kernel
     T sc[Cfg::NJ][2];         // (sin, cos) of every needed revolute joint's coordinate
     T oM[Cfg::NJ][12];        // oMi: R row-major (9) + p (3)
@@ -68,9 +69,9 @@ template <typename T, class Cfg, bool EXTRA> struct alignas(16) CoopScratch {
     T e[Cfg::M + 2], y[Cfg::M + 2];
     T dq[Cfg::NV];
     T piv[2][Cfg::M + 2];     // SHFL = false: pivot column (+ right-hand side entry), double-buffered
-    T ms[EXTRA ? Cfg::NJ : 1], mc[EXTRA ? Cfg::NJ : 1][3], ctot[4];   // CentreOfMassTask: subtree mass, first moment, whole-body first moment
-    T W[EXTRA ? Cfg::M + kMaxConstraintRows : 1][Cfg::NV];  // ik::pik / FrameConstraint: orthonormal row-space bases (row-major)
-    T Jb[EXTRA ? Cfg::NV : 1][Cfg::LDX];   // ik::pik: projected level Jacobian, column-major; FrameConstraint: Jc (rows <= 12)
+    T ms[EXTRA >= 1 ? Cfg::NJ : 1], mc[EXTRA >= 1 ? Cfg::NJ : 1][3], ctot[4];   // CentreOfMassTask: subtree mass, first moment, whole-body first moment
+    T W[EXTRA >= 2 ? Cfg::M + kMaxConstraintRows : 1][Cfg::NV];  // ik::pik / FrameConstraint: orthonormal row-space bases (row-major)
+    T Jb[EXTRA >= 2 ? Cfg::NV : 1][Cfg::LDX];   // ik::pik: projected level Jacobian, column-major; FrameConstraint: Jc (rows <= 12)
 };
 
 // World twist of velocity coordinate cc of joint j (data.cpp:30: oMi.act(S_i)) as (axis direction `ax`, origin `p`):
@@ -105,7 +106,7 @@ template <typename T, class SCR> IKB_HD void coop_frame_placement(const DevProbl
 }
 
 // ---- phases 0-3: evaluate_problem_data (data.cpp:25-58) -> S.e (weighted), S.Jt (weighted, column-major) ----
-template <typename T, class Cfg, bool EXTRA, class Ctx>
+template <typename T, class Cfg, int EXTRA, class Ctx>
 IKB_HD void coop_evaluate(const Ctx &cx, const DevProblem<T> &P, CoopScratch<T, Cfg, EXTRA> &S) {
     constexpr int TEAM = Cfg::TEAM;
     const CoopTables &C = P.coop;
@@ -168,7 +169,7 @@ IKB_HD void coop_evaluate(const Ctx &cx, const DevProblem<T> &P, CoopScratch<T, 
     }
     cx.sync();
     // phase 1b: centre of mass (centre_of_mass.hpp:24-38; pinocchio::jacobianCenterOfMass)
-    if constexpr (EXTRA) if (C.has_com) {
+    if constexpr (EXTRA >= 1) if (C.has_com) {
         for (int j = 1 + lane; j < P.njoints; j += TEAM) {
             T cw[3];
             rot_vec(S.oM[j], P.com[j], cw);
@@ -293,7 +294,7 @@ IKB_HD void coop_evaluate(const Ctx &cx, const DevProblem<T> &P, CoopScratch<T, 
         if (P.t_kind[t] == IKB_TASK_COM) {
             // velocity this coordinate gives the centre of mass of its subtree, weighted by the subtree's share of the mass
             T vel[3] = {T(0), T(0), T(0)};
-            if constexpr (EXTRA) if (S.ms[j] > T(0)) {
+            if constexpr (EXTRA >= 1) if (S.ms[j] > T(0)) {
                 const T share = S.ms[j] / P.total_mass, ims = T(1) / S.ms[j];
                 if (angular) {
                     const T dc[3] = {S.mc[j][0] * ims - O[9], S.mc[j][1] * ims - O[10], S.mc[j][2] * ims - O[11]};
@@ -528,7 +529,7 @@ IKB_HD int coop_rowspace_basis(const Ctx &cx, T (*A)[Cfg::LDX], int mi, int nv, 
 
 // Stacked FrameConstraint Jacobian (frame.hpp:398-440) into Jc (column-major): frame Jacobian minus the reference frame's
 // moved by rMf^-1, both LOCAL, rows by KinematicType.  lane <-> (constraint, column).
-template <typename T, class Cfg, bool EXTRA, class Ctx>
+template <typename T, class Cfg, int EXTRA, class Ctx>
 IKB_HD void coop_constraint_jacobian(const Ctx &cx, const DevProblem<T> &P, CoopScratch<T, Cfg, EXTRA> &S) {
     constexpr int TEAM = Cfg::TEAM;
     const int lane = cx.lane, nv = P.nv;
@@ -596,7 +597,7 @@ IKB_HD void coop_project_out(const Ctx &cx, const T (*W)[Cfg::NV], int rank, int
 
 // One iteration of ik::dls (dls.cpp:16-71) or ik::pik (pik.cpp:41-86) of one problem by its TEAM lanes.  Returns ||e[0]||^2
 // (identical in all lanes).  Below `tol` the state is left untouched (dls.cpp:61-64), else q has been stepped and clamped.
-template <typename T, class Cfg, bool SHFL, bool PIK, bool EXTRA, class Ctx>
+template <typename T, class Cfg, bool SHFL, bool PIK, int EXTRA, class Ctx>
 IKB_HD T coop_iteration(const Ctx &cx, const DevProblem<T> &P, CoopScratch<T, Cfg, EXTRA> &S, T step, T damping2, const T *pik_lambda2, T tol) {
     constexpr int TEAM = Cfg::TEAM, RPL = Cfg::RPL, M = Cfg::M;
     const int lane = cx.lane, nv = P.nv, rows = P.rows;
@@ -621,13 +622,13 @@ IKB_HD T coop_iteration(const Ctx &cx, const DevProblem<T> &P, CoopScratch<T, Cf
             S.dq[c] = -s;
         }
         cx.sync();
-        if constexpr (EXTRA) if (P.nconstraints > 0) {   // dq <- (I - Jc^+ Jc) dq (dls.cpp:26-34,44-52)
+        if constexpr (EXTRA >= 2) if (P.nconstraints > 0) {   // dq <- (I - Jc^+ Jc) dq (dls.cpp:26-34,44-52)
             coop_constraint_jacobian<T, Cfg, EXTRA>(cx, P, S);
             const int rank = coop_rowspace_basis<T, Cfg>(cx, S.Jb, P.crows, nv, S.W, S.y);
             coop_project_out<T, Cfg>(cx, S.W, rank, nv, S.dq);
         }
     } else {
-        static_assert(EXTRA, "ik::pik needs the EXTRA scratch");
+        static_assert(EXTRA >= 2, "ik::pik needs the EXTRA = 2 scratch");
         // ik::pik step (pik.cpp:43-65): dq = 0, P = I; per priority level i: de = e_i - J_i dq; Jb = J_i P;
         // dq -= damp_pinv(Jb, lambda_i) de = Jb^T (Jb Jb^T + lambda_i^2 I)^-1 de; P -= pinv(Jb) Jb.  P is kept factored,
         // P = I - sum w w^T over the orthonormal row-space bases of the levels done so far.
@@ -700,7 +701,7 @@ IKB_HD T coop_iteration(const Ctx &cx, const DevProblem<T> &P, CoopScratch<T, Cf
 }
 
 // Once per kernel (per team): the structural zeros and the constant entries of J.
-template <typename T, class Cfg, bool EXTRA, class Ctx> IKB_HD void coop_init_scratch(const Ctx &cx, const DevProblem<T> &P, CoopScratch<T, Cfg, EXTRA> &S) {
+template <typename T, class Cfg, int EXTRA, class Ctx> IKB_HD void coop_init_scratch(const Ctx &cx, const DevProblem<T> &P, CoopScratch<T, Cfg, EXTRA> &S) {
     constexpr int TEAM = Cfg::TEAM;
     T *z = &S.Jt[0][0];
     for (int i = cx.lane; i < Cfg::NV * Cfg::LD; i += TEAM) z[i] = T(0);
@@ -729,7 +730,7 @@ template <int TEAM> struct CoopDevCtx {
     __device__ __forceinline__ float shfl(float v, int src) const { return __shfl_sync(0xffffffffu, v, src, TEAM); }
 };
 
-template <typename T, class Cfg, bool EXTRA> struct CoopLaunch {
+template <typename T, class Cfg, int EXTRA> struct CoopLaunch {
     static constexpr size_t kBlob = (sizeof(DevProblem<T>) + 15) / 16 * 16 + 16;   // + mbarrier
     static constexpr size_t kScratch = sizeof(CoopScratch<T, Cfg, EXTRA>);
     static constexpr int kTeamsPerWarp = 32 / Cfg::TEAM;
@@ -771,7 +772,7 @@ __device__ __forceinline__ void coop_stage_blob(void *smem_dst, const void *gmem
 }
 
 // Persistent teams; every team pulls problem indices from a global ticket counter (as dls_team.cuh).
-template <typename T, class Cfg, bool SHFL, bool PIK, bool EXTRA>
+template <typename T, class Cfg, bool SHFL, bool PIK, int EXTRA>
 __global__ void __launch_bounds__(CoopLaunch<T, Cfg, EXTRA>::kThreads, 1) dls_coop_kernel(const DevProblem<T> *__restrict__ gP, const __grid_constant__ SolveArgs<T> a) {
     using L = CoopLaunch<T, Cfg, EXTRA>;
     constexpr int TEAM = Cfg::TEAM;

@@ -9,7 +9,7 @@ using namespace ikb::capi;
 
 namespace {
 
-template <typename T, int CLS, bool SHFL, bool PIK, bool EXTRA>
+template <typename T, int CLS, bool SHFL, bool PIK, int EXTRA>
 int launch_one(const DevProblem<T> *dP, const SolveArgs<T> &a, int sm_count, cudaStream_t s) {
     using Cfg = typename CoopClass<CLS>::Cfg;
     using L = CoopLaunch<T, Cfg, EXTRA>;
@@ -23,18 +23,19 @@ int launch_one(const DevProblem<T> *dP, const SolveArgs<T> &a, int sm_count, cud
 }
 
 template <typename T, int CLS, bool SHFL>
-int launch_cls(const DevProblem<T> *dP, const SolveArgs<T> &a, bool pik, bool constraints, int sm_count, cudaStream_t s) {
-    if (pik) return launch_one<T, CLS, SHFL, true, true>(dP, a, sm_count, s);
-    if (constraints) return launch_one<T, CLS, SHFL, false, true>(dP, a, sm_count, s);
-    return launch_one<T, CLS, SHFL, false, false>(dP, a, sm_count, s);
+int launch_cls(const DevProblem<T> *dP, const SolveArgs<T> &a, bool pik, int extra, int sm_count, cudaStream_t s) {
+    if (pik) return launch_one<T, CLS, SHFL, true, 2>(dP, a, sm_count, s);
+    if (extra >= 2) return launch_one<T, CLS, SHFL, false, 2>(dP, a, sm_count, s);
+    if (extra == 1) return launch_one<T, CLS, SHFL, false, 1>(dP, a, sm_count, s);
+    return launch_one<T, CLS, SHFL, false, 0>(dP, a, sm_count, s);
 }
 
 template <typename T, bool SHFL>
-int launch_shfl(int cls, const DevProblem<T> *dP, const SolveArgs<T> &a, bool pik, bool constraints, int sm_count, cudaStream_t s) {
+int launch_shfl(int cls, const DevProblem<T> *dP, const SolveArgs<T> &a, bool pik, int extra, int sm_count, cudaStream_t s) {
     switch (cls) {
-        case 0: return launch_cls<T, 0, SHFL>(dP, a, pik, constraints, sm_count, s);
-        case 1: return launch_cls<T, 1, SHFL>(dP, a, pik, constraints, sm_count, s);
-        default: return launch_cls<T, 2, SHFL>(dP, a, pik, constraints, sm_count, s);
+        case 0: return launch_cls<T, 0, SHFL>(dP, a, pik, extra, sm_count, s);
+        case 1: return launch_cls<T, 1, SHFL>(dP, a, pik, extra, sm_count, s);
+        default: return launch_cls<T, 2, SHFL>(dP, a, pik, extra, sm_count, s);
     }
 }
 }  // namespace
@@ -43,12 +44,12 @@ namespace ikb {
 namespace capi {
 
 template <typename T>
-int launch_coop(int cls, const DevProblem<T> *dP, const SolveArgs<T> &a, bool pik, bool constraints, bool shfl, int sm_count, cudaStream_t s) {
-    return shfl ? launch_shfl<T, true>(cls, dP, a, pik, constraints, sm_count, s)
-                : launch_shfl<T, false>(cls, dP, a, pik, constraints, sm_count, s);
+int launch_coop(int cls, const DevProblem<T> *dP, const SolveArgs<T> &a, bool pik, int extra, bool shfl, int sm_count, cudaStream_t s) {
+    return shfl ? launch_shfl<T, true>(cls, dP, a, pik, extra, sm_count, s)
+                : launch_shfl<T, false>(cls, dP, a, pik, extra, sm_count, s);
 }
-template int launch_coop<double>(int, const DevProblem<double> *, const SolveArgs<double> &, bool, bool, bool, int, cudaStream_t);
-template int launch_coop<float>(int, const DevProblem<float> *, const SolveArgs<float> &, bool, bool, bool, int, cudaStream_t);
+template int launch_coop<double>(int, const DevProblem<double> *, const SolveArgs<double> &, bool, int, bool, int, cudaStream_t);
+template int launch_coop<float>(int, const DevProblem<float> *, const SolveArgs<float> &, bool, int, bool, int, cudaStream_t);
 
 }  // namespace capi
 }  // namespace ikb

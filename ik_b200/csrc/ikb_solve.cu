@@ -230,8 +230,9 @@ static int launch_solve_impl(const ikb_problem *p, const ikb_dls_params *prm, in
     if (p->coop_ok && (aux || !(legacy_env && legacy_env[0] == '1'))) {
         const char *shfl_env = std::getenv("IKB_COOP_SHFL");
         const bool shfl = shfl_env ? shfl_env[0] == '1' : false;   // measured: the shared-memory column is 3-8 % faster
-        bool extra = !p->hp.constraints.empty();   // the larger scratch: FrameConstraints, CentreOfMassTask (and always ik::pik)
-        for (const auto &t : p->hp.tasks) extra = extra || t.kind == IKB_TASK_COM;
+        int extra = p->hp.constraints.empty() ? 0 : 2;   // scratch level: 1 = CentreOfMassTask arrays, 2 = + projection buffers (and always ik::pik)
+        for (const auto &t : p->hp.tasks)
+            if (t.kind == IKB_TASK_COM && extra < 1) extra = 1;
         if (launch_coop<T>(p->size_class, dev_blob<T>(p), a, pik_lambda != nullptr, extra, shfl, p->sm_count, s))
             return cuda_fail(cudaGetLastError(), "team-per-problem kernel launch");
         g_launches.fetch_add(1);

@@ -97,7 +97,7 @@ template <typename T, class Cfg, bool SHFL, bool PIK>
 void solve_all(const DevProblem<T> &P, const Params &prm, int B, const double *q0, const double *targets, double *q_out, int *success,
                int *iters, double *resid, double *e_first, double *J_first) {
     constexpr int TEAM = Cfg::TEAM;
-    constexpr bool EXTRA = true;   // one scratch layout for all host runs (the buffers are simply unused by plain ik::dls)
+    constexpr int EXTRA = 2;   // one scratch layout for all host runs (the buffers are simply unused by plain ik::dls)
     auto S = std::make_unique<CoopScratch<T, Cfg, EXTRA>>();
     double xd[32];
     float xf[32];
