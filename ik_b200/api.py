@@ -252,6 +252,7 @@ class InverseKinematicsProblem:  # problem.hpp:9-206
         self._constraints = []  # (name, FrameConstraint) in insertion order
         self._h = None
         self._device = None
+        self._sig = None
 
     def __del__(self):
         if getattr(self, "_h", None) and capi is not None and getattr(capi, "lib", None) is not None:
@@ -391,14 +392,35 @@ class InverseKinematicsProblem:  # problem.hpp:9-206
             capi.lib.ikb_problem_free(h)
 
     # ---- device side ----
+    def _signature(self):
+        """Everything ikb_problem_finalize bakes into the handle: the task list, row weights, posture masks, joint limits.
+        The reference reads `task->weighting()` and `mask` at every evaluation (data.cpp:49-50, posture.hpp:52) and the
+        limits at every clamp (common.hpp:54-55), so edits between solves must take effect."""
+        parts = [np.asarray(self._model.lowerPositionLimit, dtype=np.float64).tobytes(),
+                 np.asarray(self._model.upperPositionLimit, dtype=np.float64).tobytes()]
+        for name, t, prio in self._tasks:
+            parts.append(("%s|%s|%d" % (name, type(t).__name__, prio)).encode())
+            parts.append(_as_f64(t.weighting()).tobytes())
+            if isinstance(t, PostureTask):
+                parts.append(_as_f64(t.mask).tobytes())
+        parts.append(str(len(self._constraints)).encode())
+        return b"".join(parts)
+
     def finalize(self, device=0):
         if self._h is not None:
             if device is not None and self._device is not None and device != self._device:
                 raise ValueError("problem is finalized on cuda:%d; its buffers / tensors must live there (got cuda:%d)"
                                  % (self._device, device))
-            return self
+            if self._signature() == self._sig:
+                return self
+            # weights / masks / limits were edited since the handle was built: rebuild it (queues created from the old
+            # handle keep solving the old problem -- create them after the last edit)
+            capi.lib.ikb_problem_free(self._h)
+            self._h = None
+            device = self._device
         self._h = self._build_handle(device)
         self._device = device
+        self._sig = self._signature()
         return self
 
     def status_string(self):

@@ -156,9 +156,12 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
             if constexpr (Spec::PRE > 0)
                 if (role == Spec::SOLVER) Spec::presolve(sJ, sL, sE, a.damping2);
         }
-        group_sync();                                       // J and e of all roles visible
+        // (an ARROW step starts with role-local work on the role's own rows: it needs no barrier here, and its stop test
+        // runs as a hook behind the one barrier inside psolve())
+        if constexpr (!Spec::ARROW) group_sync();           // J and e of all roles visible
         T sres_mine = T(0);
-        if (role == Spec::SOLVER && have) {
+        auto stop_test = [&]() {
+            if (role == Spec::SOLVER && have) {
             // The stop-test quantity first: a slot that is about to finish (converged, or on its last iteration) pulls
             // its next ticket NOW, so the atomic's latency hides behind the solve and no slot ever hoards a ticket.
             T res = T(0);
@@ -175,8 +178,18 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
                 susp = *(volatile unsigned long long *)a.ticket >= (unsigned long long)a.B;
             if (res < a.tolerance || it + 1 >= a.max_iterations || susp) *sNext = (long long)atomicAdd(a.ticket, 1ULL);
             sres_mine = susp ? -res : res;
-        }
-        if constexpr (NW > 1 && Spec::PSOLVE) {
+            if constexpr (Spec::ARROW) *sRes = sres_mine;
+            }
+        };
+        if constexpr (!Spec::ARROW) stop_test();
+        if constexpr (NW > 1 && Spec::ARROW) {
+            // Bordered-block-diagonal step (gen_solve_arrow): phase 1 on the role's own rows, ONE barrier, the stop test
+            // (solver role, all of e visible), the small shared-column system in every role, y for the role's own rows.
+            T y[M];
+            Spec::psolve(role, sJ, sL, sE, a.damping2, y, group_sync, stop_test);
+            group_sync();                                   // s and ||e||^2 visible (y is role-private)
+            if (have && !(abs_(*sRes) < a.tolerance)) Spec::step_role(role, sJ, sL, q, a.step_length, c);  // dls.cpp:52,61-71
+        } else if constexpr (NW > 1 && Spec::PSOLVE) {
             // dls.cpp:39-41,53 distributed over the roles (cyclic row ownership, two barriers per block column).  Every
             // lane of every warp takes part in the barriers, also lanes without a problem (their arithmetic is garbage
             // that nobody reads).
@@ -200,7 +213,8 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
                 step_and_publish(y, sres_mine);
             }
         }
-        group_sync();                                       // ||e||^2, dq (and the next ticket) visible; J, e, factor dead
+        // (ARROW: nothing a role writes from here to the CTA-wide barrier at the top of the loop is read by another role)
+        if constexpr (!Spec::ARROW) group_sync();           // ||e||^2, dq (and the next ticket) visible; J, e, factor dead
         if (have) {
             const T sres = *sRes;
             const bool suspend = sres < T(0);               // bulk launch: hand the straggler to the tail launch

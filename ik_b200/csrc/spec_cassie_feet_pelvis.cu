@@ -13,14 +13,20 @@
 #include "dls_spec.cuh"
 #include "dls_team.cuh"
 #include "gen/cassie_feet_pelvis.cuh"
+#include "gen/cassie_feet_pelvis_arrow.cuh"
 #include "gen/cassie_feet_pelvis_w1.cuh"
 #include "gen/cassie_feet_pelvis_w2.cuh"
 
 namespace ikb {
 namespace {
 using S3 = SpecCassieFeetPelvis;
+using SA = SpecCassieFeetPelvisArrow;  // three roles, bordered-block-diagonal step (gen_solve_arrow) instead of the dense 12 x 12 solve
 using S2 = SpecCassieFeetPelvisW2;
 using S1 = SpecCassieFeetPelvisW1;
+bool use_arrow() {  // IKB_CASSIE_SOLVE=dense|arrow (A/B runs)
+    const char *e = std::getenv("IKB_CASSIE_SOLVE");
+    return !(e && e[0] == 'd');
+}
 int roles(int dflt) {
     const char *e = std::getenv("IKB_CASSIE_ROLES");
     return (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : dflt;
@@ -93,10 +99,10 @@ template <typename T> int launch(const SpecHostConsts &hc, const SolveArgs<T> &a
                                  int bulk_roles) {
     if (variant == SPEC_TAIL) {
         if (use_team(sizeof(T) == 8, a.resume != 0)) return launch_team<T>(team_consts<T>(hc), a, n, sms, s);
-        return launch_spec_tail<S3, T>(hc, a, n, sms, s);
+        return use_arrow() ? launch_spec_tail<SA, T>(hc, a, n, sms, s) : launch_spec_tail<S3, T>(hc, a, n, sms, s);
     }
     switch (roles(bulk_roles)) {
-        case 3: return launch_spec_bulk<S3, T>(hc, a, n, sms, s);
+        case 3: return use_arrow() ? launch_spec_bulk<SA, T>(hc, a, n, sms, s) : launch_spec_bulk<S3, T>(hc, a, n, sms, s);
         case 2: return launch_spec_bulk<S2, T>(hc, a, n, sms, s);
         default: return launch_spec_bulk<S1, T>(hc, a, n, sms, s);
     }

@@ -7,9 +7,11 @@
 #include <vector>
 
 #include "../../ik_b200/csrc/gen/cassie_feet_pelvis.cuh"
+#include "../../ik_b200/csrc/gen/cassie_feet_pelvis_arrow.cuh"
 #include "../../ik_b200/csrc/gen/cassie_feet_pelvis_w1.cuh"
 #include "../../ik_b200/csrc/gen/cassie_feet_pelvis_w2.cuh"
 #include "../../ik_b200/csrc/gen/humanoid_limbs.cuh"
+#include "../../ik_b200/csrc/gen/humanoid_limbs_arrow.cuh"
 #include "../../ik_b200/csrc/gen/manipulator_tool.cuh"
 #include "../../ik_b200/csrc/gen/cassie_demo.cuh"
 #include "../../ik_b200/csrc/gen/cassie_demo_posture.cuh"
@@ -21,6 +23,7 @@ static int spec_solve(const double *lower, const double *upper, const double *we
                       const double *targets, int max_it, double step, double damping, double tol, double *q_out, int *iters,
                       double *resid, double *e_first, bool parallel = false) {
     constexpr int NQ = Spec::NQ, NV = Spec::NV, M = Spec::M;
+    if (Spec::ARROW) parallel = true;  // the arrow specs have no serial solve (their strip has no room for a dense factor)
     SpecConsts<T, NQ, M> c;
     for (int k = 0; k < NQ; ++k) { c.lower[k] = (T)lower[k]; c.upper[k] = (T)upper[k]; }
     for (int i = 0; i < M; ++i) {
@@ -56,12 +59,17 @@ static int spec_solve(const double *lower, const double *upper, const double *we
                 th.emplace_back([&, role]() {
                     T yl[M];
                     auto sync = [&]() { bar.arrive_and_wait(); };
-                    Spec::psolve(role, sJ, sL, sE, (T)(damping * damping), yl, sync);
+                    if constexpr (Spec::ARROW) {
+                        auto hook = []() {};
+                        Spec::psolve(role, sJ, sL, sE, (T)(damping * damping), yl, sync, hook);
+                    } else {
+                        Spec::psolve(role, sJ, sL, sE, (T)(damping * damping), yl, sync);
+                    }
                     if (role == Spec::SOLVER) for (int i = 0; i < M; ++i) y[i] = yl[i];
                 });
             for (auto &t : th) t.join();
         } else {
-            res = Spec::solve(sJ, sL, sE, (T)(damping * damping), y);
+            if constexpr (!Spec::ARROW) res = Spec::solve(sJ, sL, sE, (T)(damping * damping), y);
         }
         if (res < (T)tol) { success = 1; break; }
         if constexpr (Spec::DSTEP) {
@@ -125,9 +133,11 @@ static void spec_eval(const double *weight, const double *q0, const double *targ
     }
 
 IKB_SPEC_EXPORT(h_spec_cassie_feet_pelvis, SpecCassieFeetPelvis)
+IKB_SPEC_EXPORT(h_spec_cassie_feet_pelvis_arrow, SpecCassieFeetPelvisArrow)
 IKB_SPEC_EXPORT(h_spec_cassie_feet_pelvis_w1, SpecCassieFeetPelvisW1)
 IKB_SPEC_EXPORT(h_spec_cassie_feet_pelvis_w2, SpecCassieFeetPelvisW2)
 IKB_SPEC_EXPORT(h_spec_manipulator_tool, SpecManipulatorTool)
 IKB_SPEC_EXPORT(h_spec_humanoid_limbs, SpecHumanoidLimbs)
+IKB_SPEC_EXPORT(h_spec_humanoid_limbs_arrow, SpecHumanoidLimbsArrow)
 IKB_SPEC_EXPORT(h_spec_cassie_demo, SpecCassieDemo)
 IKB_SPEC_EXPORT(h_spec_cassie_demo_posture, SpecCassieDemoPosture)

@@ -113,10 +113,12 @@ def _spec_solve(lib, name, dtype, pb, q0, tg, prm):
 
 
 CASES = [("cassie_feet_pelvis", "cassie", True, W.cassie_feet_pelvis_problem, W.CASSIE_STANDING),      # 3 warp roles
+         ("cassie_feet_pelvis_arrow", "cassie", True, W.cassie_feet_pelvis_problem, W.CASSIE_STANDING),   # 3 roles, shared / private column split
          ("cassie_feet_pelvis_w1", "cassie", True, W.cassie_feet_pelvis_problem, W.CASSIE_STANDING),   # 1 role, legs interleaved
          ("cassie_feet_pelvis_w2", "cassie", True, W.cassie_feet_pelvis_problem, W.CASSIE_STANDING),   # 2 roles
          ("manipulator_tool", "manipulator", False, W.manipulator_problem, "near"),
          ("humanoid_limbs", "humanoid", True, W.humanoid_problem, "near"),                              # 5 roles, 30 rows
+         ("humanoid_limbs_arrow", "humanoid", True, W.humanoid_problem, "near"),   # 5 roles, shared / private column split (no dense factor)
          ("cassie_demo", "cassie", True, W.cassie_demo_problem, W.CASSIE_STANDING),   # moving reference frame + align-axis task
          ("cassie_demo_posture", "cassie", True, W.cassie_demo_posture_problem, W.CASSIE_STANDING)]  # + masked posture, level 1
 
@@ -240,8 +242,8 @@ def test_branch_free_sincos_and_atan2(math_lib):
         assert abs(math_lib.h_acos_d(float(x)) - ref) <= 4e-16 * max(ref, 1e-8) + 1e-300, x
 
 
-@pytest.mark.parametrize("name,robot,ff,make,standing", [c for c in CASES if c[0] in ("cassie_feet_pelvis", "cassie_feet_pelvis_w2",
-                                                                                     "humanoid_limbs")])
+@pytest.mark.parametrize("name,robot,ff,make,standing", [c for c in CASES if c[0] in ("cassie_feet_pelvis", "cassie_feet_pelvis_w2", "cassie_feet_pelvis_arrow",
+                                                                                     "humanoid_limbs", "humanoid_limbs_arrow")])
 def test_role_distributed_solve_matches_oracle(spec_lib, name, robot, ff, make, standing):
     """psolve_w<k>: the factorisation split over the warp roles (one host thread per role, std::barrier = group barrier)
     gives the oracle's trajectory too."""

@@ -298,3 +298,26 @@ def test_plugin_specialisation_for_another_robot():
         # a 6R arm: a few problems per 10,000 pass near a singularity and amplify rounding (as in the full-size manipulator test)
         assert agree.mean() > 0.999 and np.percentile(err, 99.9) < 1e-6 and err.max() < 1e-4
     assert outs["plugin"] < outs["coop"]
+
+
+def test_weights_masks_and_limits_edited_between_solves_take_effect():
+    """The reference reads task->weighting(), PostureTask::mask and the position limits at every evaluation; the Python
+    mirror rebuilds its finalized handle when any of them changed since the last solve."""
+    pb = W.cassie_demo_posture_problem()
+    om = oracle_model("cassie")
+    q0, tg, _ = make_workload(pb, om, 64, seed=57, standing=W.CASSIE_STANDING)
+    first = ik.dls_batch_host(pb, q0, tg, None, "f64", "aos")
+    posture = pb.get_posture_task("posture")
+    posture.weighting()[:] = 0.2
+    posture.mask[3] = 0.0
+    m = pb.model()
+    hi = m.upperPositionLimit.copy()
+    hi[10] = min(hi[10], -0.9)
+    m.set_limits(m.lowerPositionLimit, hi)
+    second = ik.dls_batch_host(pb, q0, tg, None, "f64", "aos")
+    om.flat["upper"][:] = hi
+    om2 = O.Model(om.flat)
+    ref = O.dls_batch(oracle_problem_like(pb, om2), q0, tg, nthreads=NT)
+    assert not np.array_equal(first["q"], second["q"])
+    assert np.array_equal(second["success"].astype(bool), ref[1]) and np.array_equal(second["iters"], ref[2])
+    assert np.abs(second["q"] - ref[0])[ref[1]].max() < 1e-6 and (second["q"][:, 10] <= -0.9 + 1e-15)[second["iters"] > 0].all()

@@ -1118,6 +1118,302 @@ class Generator:
         self.rhs_off = RHS
         return grams, L
 
+    def gen_solve_arrow(self, groups, solver):
+        """Spec "arrow_solve": the step WITHOUT the dense M x M factorisation, for task sets whose Jacobian is "bordered block
+        diagonal": a few columns (the free-flyer; joints that several limbs' tasks share) are touched by several warp
+        roles, every other column by ONE role only.  With U_a / C_a the shared / private columns of role a's rows,
+        G = J J^T + l^2 I = blockdiag(D_a) + U U^T, D_a = C_a C_a^T + l^2 I, and the step dq = -J^T G^-1 e is
+
+            s = -dq_shared = (l^2 I + sum_a l^2 U_a^T D_a^-1 U_a)^-1  sum_a l^2 U_a^T D_a^-1 e_a      (k x k, k = #shared columns)
+            y_a = D_a^-1 (e_a - U_a s),   dq_private(a) = -C_a^T y_a                                  (role-local)
+
+        (the push-through / Woodbury identity; it is the SAME dq as dls.cpp:52-53 up to rounding, and -- written with the
+        l^2 factor on both sides -- well scaled: a role without private columns contributes U^T U and U^T e, no 1 / l^2).
+        Work per role: one m_a x m_a LDL^T (m_a = its rows) and k_a + 1 substitutions; then, identically in every role, the
+        k x k system.  ONE group barrier (the contributions are published) instead of one or two per block column, and
+        no role waits for another one's factor columns.
+          phase 1  role a, reading ONLY its own rows of J and e (so it follows the role's evaluate without a barrier):
+                   D_a, its LDL^T, X = D_a^-1 U_a column by column, S'_a = l^2 U_a^T X, t'_a = l^2 X^T e_a -> published   -> sync
+          phase 2  every role, same code: C = l^2 I + sum S'_a, b = sum t'_a, LDL^T, s = C^-1 b
+          phase 3  role a with private columns: y_a = D_a^-1 (e_a - U_a s) -> its own (dead) factor slots; the solver role stores s.
+        step_role() then takes dq_shared = -s and its private columns from y (gen_step_roles_arrow).
+        Strip layout (sL): e (M, written by evaluate, never overwritten) | s (k) | per role: published S'_a, t'_a and, for a
+        role with private columns, the factor of D_a (whose slots finally carry y_a).  A role WITHOUT private columns
+        publishes into its own Jacobian slots instead (nobody else reads them, and it has them in registers by then).
+        Roles of a mirrored task pair share one body (`side` rebases the strips), as their evaluate does."""
+        M = self.rows
+        R = len(groups)
+        ind = "        "
+        role_rows = [[self.tasks[t]["row"] + i for t in sorted(g) for i in range(self.tasks[t]["dim"])] for g in groups]
+        row_role = {r: k for k, rows in enumerate(role_rows) for r in rows}
+        col_roles = {}
+        for (r, c) in self.slots:
+            col_roles.setdefault(c, set()).add(row_role[r])
+        shared = sorted(c for c, rs in col_roles.items() if len(rs) > 1)
+        ks = len(shared)
+        if ks == 0 or ks > 12:
+            raise ValueError("arrow_solve: %d shared columns (needs 1..12)" % ks)
+        spos = {c: i for i, c in enumerate(shared)}
+        KK = ks * (ks + 1) // 2
+        per = KK + ks
+
+        def Sidx(i, j):
+            return i * (i + 1) // 2 + j
+
+        def has(r, c):
+            return (r, c) in self.slots
+
+        privs = [sorted(c for c, rs in col_roles.items() if rs == {k}) for k in range(R)]
+        ushs = [[c for c in shared if any(has(r, c) for r in role_rows[k])] for k in range(R)]
+        # ---- strip layout ----
+        SOFF = M
+        off = M + ks
+        pub = {}     # role -> ("J", [slots]) | ("L", base)
+        facb = {}    # role -> base of its factor (m (m + 1) / 2 slots) in sL
+        for k in range(R):
+            own = sorted(self.slots[(r, c)] for (r, c) in self.slots if row_role[r] == k)
+            if not privs[k] and len(own) >= per and self.spec.get("arrow_pub_in_j", True):
+                pub[k] = ("J", own[:per])
+            else:
+                pub[k] = ("L", off)
+                off += per
+            if privs[k]:
+                m = len(role_rows[k])
+                facb[k] = off
+                off += m * (m + 1) // 2
+        nfact = off
+        self.arrow_y = {}   # row -> sL slot of y[row] (rows of roles with private columns)
+
+        def pub_at(k, idx):
+            kind, where = pub[k]
+            return ("sJ", where[idx]) if kind == "J" else ("sL", where + idx)
+
+        entries = {}   # (ci, cj) -> roles that publish it ; ('t', ci) -> roles
+        nf = [0] * R
+
+        def emit_role(k, dJ=0, dR=0, dL=0):
+            """(phase 1, phase 3) of role k; strip indices are emitted minus (dJ, dR, dL) and go through the rebased strips
+            sJr / sEr / sLr, so that a mirrored role can run the body of its partner."""
+            rows = role_rows[k]
+            m = len(rows)
+            priv, ush = privs[k], ushs[k]
+            L, F = [], []
+
+            def jget(r, c):
+                return "sJr.get(%d)" % (self.slots[(r, c)] - dJ)
+
+            def pset(idx, expr):
+                strip, at = pub_at(k, idx)
+                return ind + ("sJr.set(%d, %s);" % (at - dJ, expr) if strip == "sJ" else "sLr.set(%d, %s);" % (at - dL, expr))
+
+            for i, r in enumerate(rows):
+                L.append(ind + "const T e%d = sEr.get(%d);" % (i, r - dR))
+
+            def u(i, c):   # expression of U_a[i][c] (None = structural zero); loads are emitted per column
+                return "u%d_%d" % (i, spos[c]) if has(rows[i], c) else None
+
+            if not priv:
+                # D_a = l^2 I: l^2 U^T D^-1 U = U^T U, l^2 U^T D^-1 e = U^T e -- no division by the damping
+                for c in ush:
+                    for i in range(m):
+                        if has(rows[i], c):
+                            L.append(ind + "const T u%d_%d = %s;" % (i, spos[c], jget(rows[i], c)))
+                L.append(ind + "IKB_PHASE_FENCE();   // every entry is in registers: the slots may be overwritten")
+                for a_, c in enumerate(ush):
+                    for c2 in ush[:a_ + 1]:
+                        terms = ["%s * %s" % (u(i, c), u(i, c2)) for i in range(m) if u(i, c) and u(i, c2)]
+                        if terms:
+                            L.append(pset(Sidx(spos[c], spos[c2]), " + ".join(terms)))
+                            entries.setdefault((spos[c], spos[c2]), set()).add(k)
+                            nf[k] += len(terms)
+                    terms = ["%s * e%d" % (u(i, c), i) for i in range(m) if u(i, c)]
+                    L.append(pset(KK + spos[c], " + ".join(terms)))
+                    entries.setdefault(("t", spos[c]), set()).add(k)
+                    nf[k] += len(terms)
+                return L, F
+            # ---- D_a = C_a C_a^T + l^2 I ----
+            for i in range(m):
+                for j in range(i + 1):
+                    L.append(ind + "T d%d_%d = %s;" % (i, j, "damping2" if i == j else "T(0)"))
+            for pc, c in enumerate(priv):
+                need = [i for i in range(m) if has(rows[i], c)]
+                L.append(ind + "{  // private column #%d" % pc)
+                for i in need:
+                    L.append(ind + "    const T a%d = %s;" % (i, jget(rows[i], c)))
+                for i in need:
+                    for j in need:
+                        if i >= j:
+                            L.append(ind + "    d%d_%d += a%d * a%d;" % (i, j, i, j))
+                            nf[k] += 1
+                L.append(ind + "}")
+            # ---- LDL^T in registers (SPD thanks to the damping: no pivoting) ----
+            fi = 0
+            fac_l, fac_inv = {}, {}
+            for j in range(m):
+                L.append(ind + "const T inv%d = rcp_(d%d_%d);" % (j, j, j))
+                fac_inv[j] = facb[k] + fi
+                L.append(ind + "sLr.set(%d, inv%d);" % (fac_inv[j] - dL, j))
+                fi += 1
+                for i in range(j + 1, m):
+                    L.append(ind + "const T l%d_%d = d%d_%d * inv%d;" % (i, j, i, j, j))
+                    fac_l[(i, j)] = facb[k] + fi
+                    L.append(ind + "sLr.set(%d, l%d_%d);" % (fac_l[(i, j)] - dL, i, j))
+                    fi += 1
+                for j2 in range(j + 1, m):
+                    for i in range(j2, m):
+                        L.append(ind + "d%d_%d -= l%d_%d * d%d_%d;" % (i, j2, i, j, j2, j))
+                        nf[k] += 1
+
+            def solve_lines(out, rhs, x, lname=lambda i, j: "l%d_%d" % (i, j), iname=lambda j: "inv%d" % j):
+                """x = D_a^-1 rhs : forward substitution, D^-1, back substitution; rhs[i] = expression or None (zero)."""
+                z = []
+                for i in range(m):
+                    terms = ["%s * %s" % (lname(i, j), z[j]) for j in range(i) if z[j]]
+                    if rhs[i] is None and not terms:
+                        z.append(None)
+                        continue
+                    nm = "%sz%d" % (x, i)
+                    out.append(ind + "const T %s = %s%s;" % (nm, rhs[i] if rhs[i] is not None else "T(0)", "".join(" - " + t for t in terms)))
+                    nf[k] += len(terms)
+                    z.append(nm)
+                w = [None] * m
+                for i in range(m - 1, -1, -1):
+                    terms = ["%s * %s" % (lname(j, i), w[j]) for j in range(i + 1, m) if w[j]]
+                    if z[i] is None and not terms:
+                        continue
+                    nm = "%s%d" % (x, i)
+                    base = "%s * %s" % (z[i], iname(i)) if z[i] else "T(0)"
+                    out.append(ind + "const T %s = %s%s;" % (nm, base, "".join(" - " + t for t in terms)))
+                    nf[k] += len(terms) + 1
+                    w[i] = nm
+                return w
+
+            # One shared column at a time (short live ranges: x_c lives only inside its block, the other columns' entries are
+            # re-read from the strip): x_c = D_a^-1 u_c, then S'[c][c2] = l^2 x_c . u_c2 for c2 <= c (D_a^-1 is symmetric) and
+            # t'[c] = l^2 x_c . e_a -- so D_a^-1 e_a is never formed.
+            for a_, c in enumerate(ush):
+                L.append(ind + "IKB_PHASE_FENCE();")
+                L.append(ind + "{  // shared column %d" % c)
+                for i in range(m):
+                    if has(rows[i], c):
+                        L.append(ind + "const T u%d_%d = %s;" % (i, spos[c], jget(rows[i], c)))
+                x = solve_lines(L, [u(i, c) for i in range(m)], "x%d_" % spos[c])
+                for c2 in ush[:a_ + 1]:
+                    terms = ["%s * %s" % (x[i], u(i, c2) if c2 == c else jget(rows[i], c2))
+                             for i in range(m) if x[i] and has(rows[i], c2)]
+                    if terms:
+                        L.append(pset(Sidx(spos[c], spos[c2]), "damping2 * (%s)" % " + ".join(terms)))
+                        entries.setdefault((spos[c], spos[c2]), set()).add(k)
+                        nf[k] += len(terms)
+                terms = ["%s * e%d" % (x[i], i) for i in range(m) if x[i]]
+                L.append(pset(KK + spos[c], "damping2 * (%s)" % (" + ".join(terms) if terms else "T(0)")))
+                entries.setdefault(("t", spos[c]), set()).add(k)
+                nf[k] += len(terms)
+                L.append(ind + "}")
+            # ---- phase 3: y_a = D_a^-1 (e_a - U_a s) ----
+            for i in range(m):
+                terms = ["%s * s[%d]" % (jget(rows[i], c), spos[c]) for c in ush if has(rows[i], c)]
+                F.append(ind + "const T r%d = sEr.get(%d)%s;" % (i, rows[i] - dR, "".join(" - " + t for t in terms)))
+                nf[k] += len(terms)
+            for (i, j), idx in sorted(fac_l.items()):
+                F.append(ind + "const T fl%d_%d = sLr.get(%d);" % (i, j, idx - dL))
+            for j, idx in sorted(fac_inv.items()):
+                F.append(ind + "const T fi%d = sLr.get(%d);" % (j, idx - dL))
+            w = solve_lines(F, ["r%d" % i for i in range(m)], "y_", lname=lambda i, j: "fl%d_%d" % (i, j), iname=lambda j: "fi%d" % j)
+            F.append(ind + "IKB_PHASE_FENCE();   // the factor is in registers: its slots now carry y")
+            for i in range(m):
+                F.append(ind + "sLr.set(%d, %s);" % (facb[k] + i - dL, w[i] if w[i] else "T(0)"))
+                self.arrow_y[rows[i]] = facb[k] + i
+            return L, F
+
+        # mirrored pairs: (role a, role b) whose bodies are identical up to constant strip offsets
+        mirror_of = {}    # role b -> (role a, dJ, dR, dL)
+        for pair in self.spec.get("mirror", []):
+            ra = next((k for k, g in enumerate(groups) if list(g) == [pair[0]]), None)
+            rb = next((k for k, g in enumerate(groups) if list(g) == [pair[1]]), None)
+            if ra is None or rb is None or not privs[ra] or not privs[rb] or pub[ra][0] != "L" or pub[rb][0] != "L":
+                continue
+            try:
+                dJ = self.slots[(role_rows[rb][0], shared[0])] - self.slots[(role_rows[ra][0], shared[0])]
+            except KeyError:
+                continue
+            dR = role_rows[rb][0] - role_rows[ra][0]
+            dL = pub[rb][1] - pub[ra][1]
+            save = (dict(entries), list(nf), dict(self.arrow_y))
+            try:
+                same = emit_role(ra) == emit_role(rb, dJ, dR, dL)
+            except KeyError:
+                same = False
+            entries.clear()
+            entries.update(save[0])
+            nf[:] = save[1]
+            self.arrow_y = save[2]
+            if same:
+                mirror_of[rb] = (ra, dJ, dR, dL)
+        locals_, finishes = [], []
+        for k in range(R):
+            hdr = ind + "// role %d: rows %s, private columns %s, shared columns %s" % (k, role_rows[k], privs[k], ushs[k])
+            L, F = emit_role(k)
+            locals_.append([hdr] + L)
+            finishes.append(F)
+        # ---- phase 2: the k x k system, identical in every role ----
+        Cc = []
+
+        def pget(k, idx):
+            strip, at = pub_at(k, idx)
+            return "%s.get(%d)" % (strip, at)
+
+        for i in range(ks):
+            for j in range(i + 1):
+                terms = [pget(k, Sidx(i, j)) for k in sorted(entries.get((i, j), []))]
+                Cc.append(ind + "T c%d_%d = %s%s;" % (i, j, "damping2" if i == j else "T(0)", "".join(" + " + t for t in terms)))
+            terms = [pget(k, KK + i) for k in sorted(entries.get(("t", i), []))]
+            Cc.append(ind + "const T b%d = %s;" % (i, " + ".join(terms) if terms else "T(0)"))
+        for j in range(ks):
+            Cc.append(ind + "const T ci%d = rcp_(c%d_%d);" % (j, j, j))
+            for i in range(j + 1, ks):
+                Cc.append(ind + "const T cl%d_%d = c%d_%d * ci%d;" % (i, j, i, j, j))
+            for j2 in range(j + 1, ks):
+                for i in range(j2, ks):
+                    Cc.append(ind + "c%d_%d -= cl%d_%d * c%d_%d;" % (i, j2, i, j, j2, j))
+        for i in range(ks):
+            Cc.append(ind + "const T cz%d = b%d%s;" % (i, i, "".join(" - cl%d_%d * cz%d" % (i, j, j) for j in range(i))))
+        for i in range(ks - 1, -1, -1):
+            Cc.append(ind + "s[%d] = cz%d * ci%d%s;" % (i, i, i, "".join(" - cl%d_%d * s[%d]" % (j, i, j) for j in range(i + 1, ks))))
+        self.arrow = dict(shared=shared, spos=spos, soff=SOFF, ks=ks, nfact=nfact, fma=nf, mirror_of=mirror_of,
+                          pub=pub, facb=facb)
+        self.rhs_off = 0
+        return locals_, Cc, finishes
+
+    def gen_step_roles_arrow(self, groups, solver):
+        """step_role() of spec "arrow_solve": dq of a shared column is -s (from the strip), a private column's comes from the
+        role's own rows of y; the joints common to all roles (the free-flyer) are stepped by everybody, redundantly."""
+        A = self.arrow
+        chains = [sorted(set(j for t in g for j in self.tasks[t]["chain"])) for g in groups]
+        common = sorted(set.intersection(*[set(ch) for ch in chains]))
+        covered = set(j for ch in chains for j in ch)
+        loose = [j for j, jt in enumerate(self.joints) if jt["type"] != J_UNIVERSE and j not in covered]
+        ind = "        "
+
+        def dq_lines(cols, ind_):
+            L = []
+            for c in cols:
+                if c in A["spos"]:
+                    L.append(ind_ + "dq[%d] = -s[%d];" % (c, A["spos"][c]))
+                else:
+                    L.extend(self.gen_dq([c], ind_)[1:])
+            return L
+
+        ccols, cqs = self.joint_cols(common)
+        C = [ind + "IKB_PHASE_FENCE();"] + dq_lines(ccols, ind) + self.gen_integrate(common, ind)
+        roles, qsets = [], []
+        for k, ch in enumerate(chains):
+            own = [j for j in ch if j not in common] + (loose if k == solver else [])
+            cols, qs = self.joint_cols(own)
+            roles.append(dq_lines(cols, ind + "    ") + self.gen_integrate(own, ind + "    "))
+            qsets.append(qs + (cqs if k == solver else []))
+        return C, roles, qsets
+
     def gen_dq(self, cols=None, ind="        "):
         L = []
         L.append(ind + "IKB_PHASE_FENCE();")
@@ -1237,6 +1533,12 @@ class Generator:
         used = self.signature()
         nfact = max(rows * (rows + 1) // 2, rows + self.nq)  # the factor strip also carries e (M) and the stepped q (NQ)
         uniform = bool(self.spec.get("uniform_solve")) and bool(self.spec.get("parallel_solve")) and len(groups) > 1
+        arrow = bool(self.spec.get("arrow_solve")) and len(groups) > 1
+        if arrow:
+            uniform = False
+            arrow_code = self.gen_solve_arrow(groups, solver)
+            nfact = max(self.arrow["nfact"], rows + self.nq)   # layout: see gen_solve_arrow
+            self.eoff = 0
         if uniform:
             nfact = nstrict + 3 * rows                        # L | d | rhs (e, then yp) | Gram diagonal (gen_solve_uniform)
             self.eoff = nstrict + rows
@@ -1257,9 +1559,11 @@ class Generator:
         out.append("    static constexpr int NWARPS = %d, SOLVER = %d;" % (len(groups), solver))
         out.append("    // PSOLVE: distribute the factorisation over the roles (pays off for large M; for M = 12 the ~7 extra group")
         out.append("    // barriers cost more than the shorter critical path saves -- measured, DESIGN.md 4.1)")
-        out.append("    static constexpr bool PSOLVE = %s;" % ("true" if self.spec.get("parallel_solve") and len(groups) > 1 else "false"))
+        out.append("    static constexpr bool PSOLVE = %s;" % ("true" if (self.spec.get("parallel_solve") or arrow) and len(groups) > 1 else "false"))
         out.append("    // DSTEP: after psolve() y sits in the strip and every role steps its own coordinates (step_role / store_q)")
-        out.append("    static constexpr bool DSTEP = %s;" % ("true" if uniform else "false"))
+        out.append("    static constexpr bool DSTEP = %s;" % ("true" if (uniform or arrow) else "false"))
+        out.append("    // ARROW: psolve() is the bordered-block-diagonal step (gen_solve_arrow); the serial solve() is not laid out for its strip")
+        out.append("    static constexpr bool ARROW = %s;" % ("true" if arrow else "false"))
         out.append("    // PRE: leading rows whose P x P factor block the SOLVER role computes in presolve(), before the first barrier;")
         out.append("    // EOFF: slot of the factor strip where e starts (rows >= PRE of L, written only after e has been read)")
         out.append("    static constexpr int PRE = %d, EOFF = %d;" % (P, self.eoff))
@@ -1312,10 +1616,11 @@ class Generator:
         out.append("    }")
         out.append("    // y = (J J^T + damping^2 I)^-1 e: fused Gram + blocked LDL^T (factor -> strip sL) + substitutions.")
         out.append("    // Reads e from sE (may alias the start of sL), returns ||e[0..M0)||^2 (the stop-test quantity, visitor.hpp:19).")
-        out.append("    template <typename T, typename S>")
-        out.append("    static IKB_HD T solve(const S &sJ, const S &sL, const S &sE, T damping2, T (&y)[M]) {")
-        out.extend(solve)
-        out.append("    }")
+        if not arrow:   # (an arrow spec's strip has no room for the dense factor; its step is psolve())
+            out.append("    template <typename T, typename S>")
+            out.append("    static IKB_HD T solve(const S &sJ, const S &sL, const S &sE, T damping2, T (&y)[M]) {")
+            out.extend(solve)
+            out.append("    }")
         if uniform:
             grams, ubody = self.gen_solve_uniform(len(groups), solver)
             out.append("    // The same solve distributed over the warp roles with ONE factorisation body (see gen_solve_uniform).")
@@ -1332,17 +1637,83 @@ class Generator:
             out.append("        sync();  // the normal equations are in the strip")
             out.extend(ubody)
             out.append("    }")
-        psolve = [] if uniform else self.gen_solve_parallel(int(self.spec.get("parallel_block_width", self.spec.get("block_width", 4))), len(groups), solver)
+        if arrow:
+            locals_, cap, finishes = arrow_code
+            A = self.arrow
+            out.append("    // Bordered-block-diagonal step (see gen_solve_arrow): shared columns %s; FMAs per role %s" % (A["shared"], A["fma"]))
+            out.append("    // strip sL: e [0, %d) | s [%d, %d) | published contributions %s | factors / y %s" %
+                       (rows, A["soff"], A["soff"] + A["ks"], {k: v if v[0] == "L" else "own J slots" for k, v in A["pub"].items()}, A["facb"]))
+            partner = {ra: rb for rb, (ra, _, _, _) in A["mirror_of"].items()}
+            for k in range(len(groups)):
+                if k in A["mirror_of"]:
+                    continue   # runs the body of its mirror partner
+                if k in partner:
+                    _, dJ, dR, dL = A["mirror_of"][partner[k]]
+                    sig = "const int side, "
+                    reb = ["        const S sJr{sJ.base + side * (%d * S::kStride)}, sEr{sE.base + side * (%d * S::kStride)}, sLr{sL.base + side * (%d * S::kStride)};"
+                           % (dJ, dR, dL)]
+                    nm = "m%d" % k
+                else:
+                    sig = ""
+                    reb = ["        const S &sJr = sJ, &sEr = sE, &sLr = sL;"]
+                    nm = "w%d" % k
+                out.append("    template <typename T, typename S>")
+                out.append("    static IKB_HD void arrow_local_%s(%sconst S &sJ, const S &sL, const S &sE, T damping2) {" % (nm, sig))
+                out.extend(reb)
+                out.extend(locals_[k])
+                out.append("    }")
+                if finishes[k]:
+                    out.append("    template <typename T, typename S>")
+                    out.append("    static IKB_HD void arrow_finish_%s(%sconst S &sJ, const S &sL, const S &sE, const T (&s)[%d]) {" % (nm, sig, A["ks"]))
+                    out.extend(reb)
+                    out.extend(finishes[k])
+                    out.append("    }")
+
+            def call(fn, k, args):
+                if k in A["mirror_of"]:
+                    return "%s_m%d(1, %s)" % (fn, A["mirror_of"][k][0], args)
+                if k in partner:
+                    return "%s_m%d(0, %s)" % (fn, k, args)
+                return "%s_w%d(%s)" % (fn, k, args)
+
+            out.append("    // phase 1 reads only the role's own rows of J and e: no barrier between evaluate() and psolve().  `hook` runs")
+            out.append("    // right after the one barrier (all of e is visible and stays intact): the kernel's stop test and ticket prefetch.")
+            out.append("    template <typename T, typename S, typename SYNC, typename HOOK>")
+            out.append("    static IKB_HD void psolve(int role, const S &sJ, const S &sL, const S &sE, T damping2, T (&y)[M], SYNC &sync, HOOK &hook) {")
+            out.append("        T s[%d];" % A["ks"])
+            for k in range(len(groups)):
+                if k in A["mirror_of"]:
+                    continue
+                cond = "role == %d || role == %d" % (k, partner[k]) if k in partner else "role == %d" % k
+                fn = "arrow_local_m%d(role == %d ? 1 : 0, sJ, sL, sE, damping2)" % (k, partner[k]) if k in partner else "arrow_local_w%d(sJ, sL, sE, damping2)" % k
+                out.append("        if (%s) %s;" % (cond, fn))
+            out.append("        sync();  // every role's contribution to the shared-column system is in the strip")
+            out.append("        hook();")
+            out.extend(cap)
+            out.append("        IKB_PHASE_FENCE();")
+            for k in range(len(groups)):
+                if k in A["mirror_of"] or not finishes[k]:
+                    continue
+                cond = "role == %d || role == %d" % (k, partner[k]) if k in partner else "role == %d" % k
+                fn = "arrow_finish_m%d(role == %d ? 1 : 0, sJ, sL, sE, s)" % (k, partner[k]) if k in partner else "arrow_finish_w%d(sJ, sL, sE, s)" % k
+                out.append("        if (%s) %s;" % (cond, fn))
+            out.append("        if (role == %d) {" % solver)
+            out.append("#pragma unroll")
+            out.append("            for (int i = 0; i < %d; ++i) sL.set(%d + i, s[i]);" % (A["ks"], A["soff"]))
+            out.append("        }")
+            out.append("        (void)y;")
+            out.append("    }")
+        psolve = [] if (uniform or arrow) else self.gen_solve_parallel(int(self.spec.get("parallel_block_width", self.spec.get("block_width", 4))), len(groups), solver)
         out.append("    // The same solve distributed over the warp roles (cyclic row ownership; see gen_solve_parallel): every role")
         out.append("    // calls psolve(role, ...) with a group barrier `sync`; y is produced in the SOLVER role's registers only.")
-        if not uniform:
+        if not (uniform or arrow):
             out.append("    // FMAs per role: %s" % self.psolve_fma)
         for k, code in enumerate(psolve):
             out.append("    template <typename T, typename S, typename SYNC>")
             out.append("    static IKB_HD void psolve_w%d(const S &sJ, const S &sL, const S &sE, T damping2, T (&y)[M], SYNC &sync) {" % k)
             out.extend(code)
             out.append("    }")
-        if not uniform:
+        if not (uniform or arrow):
             out.append("    template <typename T, typename S, typename SYNC>")
             out.append("    static IKB_HD void psolve(int role, const S &sJ, const S &sL, const S &sE, T damping2, T (&y)[M], SYNC &sync) {")
             for k in range(len(groups)):
@@ -1358,17 +1729,28 @@ class Generator:
         out.append("    static IKB_HD void integrate(T (&q)[NQ], const T (&dq)[NV], T step, const SpecConsts<T, NQ, M> &c) {")
         out.extend(integ)
         out.append("    }")
-        if uniform:
-            C, roles, qsets = self.gen_step_roles(groups, solver)
+        if uniform or arrow:
+            C, roles, qsets = self.gen_step_roles_arrow(groups, solver) if arrow else self.gen_step_roles(groups, solver)
             out.append("    // Distributed step (see gen_step_roles): y from the strip; common joints by every role, the others by their role.")
             out.append("    template <typename T, typename S>")
             out.append("    static IKB_HD void step_role(int role, const S &sJ, const S &sL, T (&q)[NQ], T step, const SpecConsts<T, NQ, M> &c) {")
             out.append("        T y[M], dq[NV];")
-            out.append("        #pragma unroll")
-            out.append("        for (int i = 0; i < M; ++i) y[i] = sL.get(%d + i);" % self.rhs_off)
+            if not arrow:
+                out.append("        #pragma unroll")
+                out.append("        for (int i = 0; i < M; ++i) y[i] = sL.get(%d + i);" % self.rhs_off)
+            if arrow:
+                out.append("        T s[%d];" % self.arrow["ks"])
+                out.append("        #pragma unroll")
+                out.append("        for (int i = 0; i < %d; ++i) s[i] = sL.get(%d + i);" % (self.arrow["ks"], self.arrow["soff"]))
             out.extend(C)
             for k, code in enumerate(roles):
                 out.append("        if (role == %d) {" % k)
+                if arrow:   # y of the role's own rows (phase 3 left it in the role's factor slots)
+                    for t in sorted(groups[k]):
+                        for i in range(self.tasks[t]["dim"]):
+                            r = self.tasks[t]["row"] + i
+                            if r in self.arrow_y:
+                                out.append("            y[%d] = sL.get(%d);" % (r, self.arrow_y[r]))
                 out.extend(code)
                 out.append("        }")
             out.append("    }")
