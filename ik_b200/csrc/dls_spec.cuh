@@ -29,6 +29,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 
 #include "dev_problem.hpp"
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
             __syncwarp();
     };
 
-    T q[NQ];
+    T q[Spec::NQL];                                       // (arrow specs: only the coordinates this role reads and steps)
     long long b;
     int it = 0;
     bool have;
@@ -118,14 +119,14 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
             const ProblemIO<T> io = problem_io<SEG>(a, b);
             const T *src = a.resume ? io.q : io.q0;       // a suspended problem continues from its saved iterate
             const long long es = a.resume ? io.q_es : io.q0_es;
-#pragma unroll
-            for (int k = 0; k < NQ; ++k) q[k] = src[k * es];
+            Spec::load_q(role, src, es, q);
             Spec::load_targets(role, io.targets, io.tg_es, sT);
         }
     };
     // SOLVER role, after the solve: dq = -J^T y, the manifold step and the clamp on ITS copy of q, which it then publishes
     // in the (dead) factor strip -- the other roles only copy it (no second and third integrate on the critical path).
     auto step_and_publish = [&](const T(&y)[M], T sres) {
+        if constexpr (!Spec::DSTEP)
         if (!(abs_(sres) < a.tolerance)) {                           // dls.cpp:61-64: a converged iterate is returned as is
             T dq[NV];
             Spec::step_direction(sJ, y, dq);                         // dls.cpp:52
@@ -148,7 +149,18 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
     // instruction cache in front of L2, so every warp streams it from L2 on every trip.  Warps that start a trip together
     // stay in step (same instruction count whatever their lanes do) and share each fetched line; left alone they drift
     // apart and each pulls its own copy (ncu: no_instruction stalls 0.4 -> 1.1 per issue).
-    while (__syncthreads_or(have)) {
+    auto any_left = [&]() -> bool {
+        if (GROUPS == 1 || a.loop_sync == 0) return __syncthreads_or(have) != 0;
+        if constexpr (NW > 1) {   // the group's own barrier with an OR reduction (bar.red on a named barrier)
+            unsigned r;
+            asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(r) : "r"((unsigned)have), "r"(group + 1), "n"(NW * 32) : "memory");
+            return r != 0;
+        } else {
+            return __any_sync(0xffffffffu, have) != 0;
+        }
+    };
+    while (any_left()) {
         if (have) {
             Spec::evaluate(role, q, sT, c, sJ, sE);         // data.cpp:25-58, this role's tasks
             // The solver role's own tasks are the cheap ones: while the others still evaluate, it factorises the leading
@@ -368,7 +380,9 @@ int launch_spec_cfg_seg(const SpecHostConsts &hc, const SolveArgs<T> &a, long lo
         c.mask[i] = (T)hc.mask[i];
     }
     if (ctas < 1) ctas = 1;
-    fn<<<(unsigned)ctas, GROUPS * Spec::NWARPS * 32, kSmem, s>>>(c, a);
+    SolveArgs<T> a2 = a;
+    if (const char *e = std::getenv("IKB_LOOP_SYNC")) a2.loop_sync = e[0] == 'g' ? 1 : 0;   // cta | group (A/B runs)
+    fn<<<(unsigned)ctas, GROUPS * Spec::NWARPS * 32, kSmem, s>>>(c, a2);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

@@ -38,14 +38,17 @@ static int spec_solve(const double *lower, const double *upper, const double *we
     for (int k = 0; k < NQ; ++k) q[k] = (T)q0[k];
     // distributed step (Spec::DSTEP): every role keeps its own copy of q and steps only the coordinates it owns, as in the kernel
     const bool dstep = parallel && Spec::NWARPS > 1 && Spec::DSTEP;
-    std::vector<T> qr_buf((size_t)Spec::NWARPS * NQ);
-    auto qr = [&](int role) -> T(&)[NQ] { return *reinterpret_cast<T(*)[NQ]>(qr_buf.data() + (size_t)role * NQ); };
-    for (int role = 0; role < Spec::NWARPS; ++role)
-        for (int k = 0; k < NQ; ++k) qr(role)[k] = q[k];
+    constexpr int NQL = Spec::NQL;   // (arrow specs: a role keeps only the coordinates it reads and steps)
+    std::vector<T> qr_buf((size_t)Spec::NWARPS * NQL);
+    auto qr = [&](int role) -> T(&)[NQL] { return *reinterpret_cast<T(*)[NQL]>(qr_buf.data() + (size_t)role * NQL); };
+    for (int role = 0; role < Spec::NWARPS; ++role) Spec::load_q(role, q, 1LL, qr(role));
     int it = 0, success = 0;
     T res = 0;
     while (it < max_it) {
-        for (int role = 0; role < Spec::NWARPS; ++role) Spec::evaluate(role, dstep ? qr(role) : q, sT, c, sJ, sE);  // the warp roles, in turn
+        for (int role = 0; role < Spec::NWARPS; ++role) {   // the warp roles, in turn
+            if constexpr (NQL == NQ) Spec::evaluate(role, dstep ? qr(role) : q, sT, c, sJ, sE);
+            else Spec::evaluate(role, qr(role), sT, c, sJ, sE);
+        }
         if (Spec::PRE > 0) Spec::presolve(sJ, sL, sE, (T)(damping * damping));                      // solver role, before the barrier
         if (it == 0 && e_first) for (int i = 0; i < M; ++i) e_first[i] = (double)sE.get(i);
         T y[M], dq[NV];
@@ -79,8 +82,10 @@ static int spec_solve(const double *lower, const double *upper, const double *we
                 continue;
             }
         }
-        Spec::step_direction(sJ, y, dq);
-        Spec::integrate(q, dq, (T)step, c);
+        if constexpr (NQL == NQ) {
+            Spec::step_direction(sJ, y, dq);
+            Spec::integrate(q, dq, (T)step, c);
+        }
         ++it;
     }
     if constexpr (Spec::DSTEP) {
@@ -104,9 +109,11 @@ static void spec_eval(const double *weight, const double *q0, const double *targ
     }
     std::vector<double> bufJ(Spec::NSLOT), bufT(targets, targets + Spec::TSZ), bufE(M);
     const Strip<double, 1> sJ{bufJ.data()}, sT{bufT.data()}, sE{bufE.data()};
-    double q[NQ];
-    for (int k = 0; k < NQ; ++k) q[k] = q0[k];
-    for (int role = 0; role < Spec::NWARPS; ++role) Spec::evaluate(role, q, sT, c, sJ, sE);
+    for (int role = 0; role < Spec::NWARPS; ++role) {
+        double q[Spec::NQL];
+        Spec::load_q(role, q0, 1LL, q);
+        Spec::evaluate(role, q, sT, c, sJ, sE);
+    }
     for (int i = 0; i < M; ++i) e_out[i] = bufE[i];
     for (int i = 0; i < M * NV; ++i) J_out[i] = 0;
     for (int k = 0; k < Spec::NSLOT; ++k) J_out[Spec::slot_rc()[2 * k] * NV + Spec::slot_rc()[2 * k + 1]] = bufJ[k];

@@ -207,6 +207,12 @@ class Generator:
         # mirror mode (gen_evaluate_mirrored): while the body of task A is emitted for the pair (A, B), quantities that
         # differ between the two sides are emitted as side-dependent variables
         self.mir = None
+        # role-local configuration registers (arrow specs): global q index -> index into the role's own T q[NQL]
+        self.qmap = None
+
+    def ql(self, iq):
+        """register index of configuration scalar iq in the code being emitted (role-local for arrow specs)"""
+        return self.qmap[iq] if self.qmap is not None else iq
 
     def slot(self, row, col):
         key = (row, col)
@@ -235,10 +241,10 @@ class Generator:
         p = matvec(E, parR, Pp, "p%d" % j, add=parp)
         if t == J_FF:
             E.raw("T Rq%d[9];" % j)
-            E.raw("quat_to_rot(q[%d], q[%d], q[%d], q[%d], Rq%d);" % (iq + 3, iq + 4, iq + 5, iq + 6, j))
+            E.raw("quat_to_rot(q[%d], q[%d], q[%d], q[%d], Rq%d);" % (self.ql(iq + 3), self.ql(iq + 4), self.ql(iq + 5), self.ql(iq + 6), j))
             Rq = ["Rq%d[%d]" % (j, k) for k in range(9)]
             R = matmul(E, A, Rq, "R%d" % j)
-            p = matvec(E, A, ["q[%d]" % (iq + k) for k in range(3)], "p%d" % j, add=p)
+            p = matvec(E, A, ["q[%d]" % self.ql(iq + k) for k in range(3)], "p%d" % j, add=p)
             w = dict(R=R, p=p, z=None, type=t)
         elif t in (J_RX, J_RY, J_RZ, J_RU):
             E.raw("T s%d, c%d;" % (j, j))
@@ -281,7 +287,7 @@ class Generator:
         """Expression of the configuration scalar of (revolute / prismatic) joint j."""
         if self.mir and j in self.mir["jmap"]:
             return "qm%d" % j
-        return "q[%d]" % iq
+        return "q[%d]" % self.ql(iq)
 
     def mirror_placement(self, E, j, P):
         """Placement of joint j; in mirror mode entries that differ on the other side become side-dependent variables."""
@@ -322,7 +328,12 @@ class Generator:
         E = Emitter()
         E.comment("side 0: task %d (%s), side 1: task %d (%s)" % (ta, A["name"], tb, B["name"]))
         for ja, jb in jmap.items():
-            E.raw("const T qm%d = side ? q[%d] : q[%d];" % (ja, self.joints[jb]["idx_q"], self.joints[ja]["idx_q"]))
+            if self.qmap is not None:   # role-local registers: both sides keep the joint at the same index
+                if self.qmap_b[self.joints[jb]["idx_q"]] != self.qmap[self.joints[ja]["idx_q"]]:
+                    raise ValueError("mirror: joints %d / %d sit in different local registers" % (ja, jb))
+                E.raw("const T qm%d = q[%d];" % (ja, self.qmap[self.joints[ja]["idx_q"]]))
+            else:
+                E.raw("const T qm%d = side ? q[%d] : q[%d];" % (ja, self.joints[jb]["idx_q"], self.joints[ja]["idx_q"]))
         for i in range(A["dim"]):
             E.raw("const T wm%d = side ? c.weight[%d] : c.weight[%d];" % (i, B["row"] + i, A["row"] + i))
         s0 = len(self.slots)
@@ -1405,13 +1416,16 @@ class Generator:
             return L
 
         ccols, cqs = self.joint_cols(common)
+        self.qmap = self.qmaps[0] if self.qmaps else None      # the common joints sit in the same registers in every role
         C = [ind + "IKB_PHASE_FENCE();"] + dq_lines(ccols, ind) + self.gen_integrate(common, ind)
         roles, qsets = [], []
         for k, ch in enumerate(chains):
             own = [j for j in ch if j not in common] + (loose if k == solver else [])
             cols, qs = self.joint_cols(own)
+            self.qmap = self.qmaps[k] if self.qmaps else None
             roles.append(dq_lines(cols, ind + "    ") + self.gen_integrate(own, ind + "    "))
             qsets.append(qs + (cqs if k == solver else []))
+        self.qmap = None
         return C, roles, qsets
 
     def gen_dq(self, cols=None, ind="        "):
@@ -1467,14 +1481,16 @@ class Generator:
                 L.append(ind + "{")
                 L.append(ind + "    T v6[6], R0[9];")
                 L.append(ind + "    for (int k = 0; k < 6; ++k) v6[k] = step * dq[%d + k];" % iv)
-                L.append(ind + "    quat_to_rot(q[%d], q[%d], q[%d], q[%d], R0);" % (iq + 3, iq + 4, iq + 5, iq + 6))
-                L.append(ind + "    integrate_freeflyer(R0, &q[%d], &q[%d], v6);" % (iq, iq + 3))
+                L.append(ind + "    quat_to_rot(q[%d], q[%d], q[%d], q[%d], R0);" % (self.ql(iq + 3), self.ql(iq + 4), self.ql(iq + 5), self.ql(iq + 6)))
+                if [self.ql(iq + k) for k in range(7)] != list(range(self.ql(iq), self.ql(iq) + 7)):
+                    raise ValueError("free-flyer coordinates must be contiguous in the local registers")
+                L.append(ind + "    integrate_freeflyer(R0, &q[%d], &q[%d], v6);" % (self.ql(iq), self.ql(iq + 3)))
                 L.append(ind + "}")
             else:
-                L.append(ind + "q[%d] += step * dq[%d];" % (iq, iv))
+                L.append(ind + "q[%d] += step * dq[%d];" % (self.ql(iq), iv))
         if joints is not None:
             for k in self.joint_cols(joints)[1]:
-                L.append(ind + "q[%d] = min_(c.upper[%d], max_(q[%d], c.lower[%d]));" % (k, k, k, k))
+                L.append(ind + "q[%d] = min_(c.upper[%d], max_(q[%d], c.lower[%d]));" % (self.ql(k), k, self.ql(k), k))
             return L
         L.append(ind + "#pragma unroll")
         L.append(ind + "for (int k = 0; k < %d; ++k) q[k] = min_(c.upper[k], max_(q[k], c.lower[k]));" % self.nq)
@@ -1500,16 +1516,40 @@ class Generator:
             mirrors[ra] = (len(shared), 0)
             mirrors[rb] = (len(shared), 1)
             shared.append(None)
+        arrow = bool(self.spec.get("arrow_solve")) and len(groups) > 1
+        self.qmaps = None
+        nql = self.nq
+        if arrow and self.spec.get("local_q", True):
+            # Role-local configuration registers: a role keeps only the coordinates its evaluate reads (and its step_role
+            # writes) -- the joints common to all roles first (same registers in every role), then its own chains; mirrored
+            # roles keep corresponding joints in the same registers, so their shared body needs no select.  (With one
+            # T q[NQ] for all roles every coordinate is live in every warp: 2 NQ registers in FP64.)
+            chains = [sorted(set(j for t in g for j in self.tasks[t]["chain"])) for g in groups]
+            common = sorted(set.intersection(*[set(ch) for ch in chains]))
+            covered = set(j for ch in chains for j in ch)
+            loose = [j for j, jt in enumerate(self.joints) if jt["type"] != J_UNIVERSE and j not in covered]
+            self.qmaps = []
+            for k, ch in enumerate(chains):
+                mp = {}
+                for j in common + [j for j in ch if j not in common] + (loose if k == solver else []):
+                    for iq in self.joint_cols([j])[1]:
+                        mp[iq] = len(mp)
+                self.qmaps.append(mp)
+            nql = max(len(mp) for mp in self.qmaps)
         evs = []
         for k, g in enumerate(groups):
+            self.qmap = self.qmaps[k] if self.qmaps else None
             if k in mirrors:
                 bid, side = mirrors[k]
                 if side == 0:
                     pair = self.spec["mirror"][bid]
+                    rb = next(r for r, v in mirrors.items() if v == (bid, 1))
+                    self.qmap_b = self.qmaps[rb] if self.qmaps else None
                     shared[bid] = self.gen_evaluate_mirrored(pair[0], pair[1])
                 evs.append(None)
             else:
                 evs.append(self.gen_evaluate(g))
+        self.qmap = None
         dq = self.gen_dq()
         integ = self.gen_integrate()
         rows, nslot = self.rows, len(self.slots)
@@ -1533,7 +1573,6 @@ class Generator:
         used = self.signature()
         nfact = max(rows * (rows + 1) // 2, rows + self.nq)  # the factor strip also carries e (M) and the stepped q (NQ)
         uniform = bool(self.spec.get("uniform_solve")) and bool(self.spec.get("parallel_solve")) and len(groups) > 1
-        arrow = bool(self.spec.get("arrow_solve")) and len(groups) > 1
         if arrow:
             uniform = False
             arrow_code = self.gen_solve_arrow(groups, solver)
@@ -1555,6 +1594,8 @@ class Generator:
         out.append("struct %s {" % struct_name)
         out.append("    static constexpr int NQ = %d, NV = %d, M = %d, M0 = %d, TSZ = %d, NSLOT = %d, NFACT = %d;" %
                    (self.nq, self.nv, rows, self.rows_p0, self.tsz, nslot, nfact))
+        out.append("    // NQL: configuration registers per thread (arrow specs: a role keeps only the coordinates it reads and steps)")
+        out.append("    static constexpr int NQL = %d;" % nql)
         out.append("    // warp roles: the tasks are split over NWARPS warps that evaluate concurrently; role SOLVER solves")
         out.append("    static constexpr int NWARPS = %d, SOLVER = %d;" % (len(groups), solver))
         out.append("    // PSOLVE: distribute the factorisation over the roles (pays off for large M; for M = 12 the ~7 extra group")
@@ -1585,13 +1626,13 @@ class Generator:
                 continue
             out.append("    // FK + task errors (-> sE) + weighted task Jacobian non-zeros (-> sJ)")
             out.append("    template <typename T, typename S>")
-            out.append("    static IKB_HD void evaluate_w%d(const T (&q)[NQ], const S &tg, const SpecConsts<T, NQ, M> &c, const S &sJ, const S &sE) {" % k)
+            out.append("    static IKB_HD void evaluate_w%d(const T (&q)[NQL], const S &tg, const SpecConsts<T, NQ, M> &c, const S &sJ, const S &sE) {" % k)
             out.extend(ev)
             out.append("    }")
         for bid, body in enumerate(shared):
             out.append("    // ---- shared by the roles of the mirrored tasks %s (side = 0 / 1) ----" % (self.spec["mirror"][bid],))
             out.append("    template <typename T, typename S>")
-            out.append("    static IKB_HD void evaluate_m%d(const int side, const T (&q)[NQ], const S &tg, const SpecConsts<T, NQ, M> &c, const S &sJ, const S &sE) {" % bid)
+            out.append("    static IKB_HD void evaluate_m%d(const int side, const T (&q)[NQL], const S &tg, const SpecConsts<T, NQ, M> &c, const S &sJ, const S &sE) {" % bid)
             out.extend(body)
             out.append("    }")
         out.append("    // role dispatch (warp-uniform)")
@@ -1601,7 +1642,7 @@ class Generator:
             out.append("        if (role == %d) load_targets_w%d(tg, es, sT);" % (k, k))
         out.append("    }")
         out.append("    template <typename T, typename S>")
-        out.append("    static IKB_HD void evaluate(int role, const T (&q)[NQ], const S &tg, const SpecConsts<T, NQ, M> &c, const S &sJ, const S &sE) {")
+        out.append("    static IKB_HD void evaluate(int role, const T (&q)[NQL], const S &tg, const SpecConsts<T, NQ, M> &c, const S &sJ, const S &sE) {")
         for k in range(len(groups)):
             if k not in mirrors:
                 out.append("        if (role == %d) evaluate_w%d(q, tg, c, sJ, sE);" % (k, k))
@@ -1733,7 +1774,7 @@ class Generator:
             C, roles, qsets = self.gen_step_roles_arrow(groups, solver) if arrow else self.gen_step_roles(groups, solver)
             out.append("    // Distributed step (see gen_step_roles): y from the strip; common joints by every role, the others by their role.")
             out.append("    template <typename T, typename S>")
-            out.append("    static IKB_HD void step_role(int role, const S &sJ, const S &sL, T (&q)[NQ], T step, const SpecConsts<T, NQ, M> &c) {")
+            out.append("    static IKB_HD void step_role(int role, const S &sJ, const S &sL, T (&q)[NQL], T step, const SpecConsts<T, NQ, M> &c) {")
             out.append("        T y[M], dq[NV];")
             if not arrow:
                 out.append("        #pragma unroll")
@@ -1756,13 +1797,28 @@ class Generator:
             out.append("    }")
             out.append("    // the entries of q a role owns (its step_role keeps exactly these current), written to the result")
             out.append("    template <typename T>")
-            out.append("    static IKB_HD void store_q(int role, const T (&q)[NQ], T *dst, long long es) {")
+            out.append("    static IKB_HD void store_q(int role, const T (&q)[NQL], T *dst, long long es) {")
             for k, qs in enumerate(qsets):
                 out.append("        if (role == %d) {" % k)
                 for iq in sorted(qs):
-                    out.append("            dst[%d * es] = q[%d];" % (iq, iq))
+                    out.append("            dst[%d * es] = q[%d];" % (iq, self.qmaps[k][iq] if self.qmaps else iq))
                 out.append("        }")
             out.append("    }")
+        out.append("    // the configuration of a problem into a role's registers (arrow specs: only the coordinates the role keeps)")
+        out.append("    template <typename T>")
+        out.append("    static IKB_HD void load_q(int role, const T *src, long long es, T (&q)[NQL]) {")
+        if self.qmaps:
+            for k, mp in enumerate(self.qmaps):
+                out.append("        if (role == %d) {" % k)
+                for iq, l in sorted(mp.items()):
+                    out.append("            q[%d] = src[%d * es];" % (l, iq))
+                for l in range(len(mp), nql):
+                    out.append("            q[%d] = T(0);" % l)
+                out.append("        }")
+        else:
+            out.append("#pragma unroll")
+            out.append("        for (int k = 0; k < NQ; ++k) q[k] = src[k * es];")
+        out.append("    }")
         # signature data for matches()
         out.append("    // ---- signature (host): the tree and task list this code was generated for ----")
         out.append("    static constexpr int NJOINTS = %d, NTASKS = %d;" % (len(self.joints), len(self.tasks)))
