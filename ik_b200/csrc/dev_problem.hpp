@@ -109,8 +109,8 @@ template <typename T> struct SolveArgs {
     // iters_ws / list are indexed by the launch-wide problem index.  Unused entries have begin = LLONG_MAX.  The table
     // travels in the kernel parameters: the lookup is a handful of constant-bank compares, no memory traffic.
     int nseg;
-    // dls_spec.cuh: 0 = the CTA's groups start every trip together (they share the instruction lines they fetch),
-    // 1 = every group loops on its own (phases of different groups interleave on the schedulers)
+    // dls_spec.cuh: 0 = every group of the CTA loops on its own (phases of different groups interleave on the schedulers:
+    // measured +3 % on the Cassie bulk launch), 1 = the CTA's groups start every trip together (IKB_LOOP_SYNC=cta)
     int loop_sync;
     BatchSeg<T> seg[kMaxSegments];
 };

@@ -102,10 +102,12 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
     long long b;
     int it = 0;
     bool have;
+    bool refetch = false;   // Spec::QCOMMON: this slot's problem was stepped in the last trip and goes on
 
     // b holds a ticket on entry: a problem index (fresh problems) or an index into the suspended list (tail launch)
     auto load_problem = [&]() {
         it = 0;
+        refetch = false;
         if (!a.resume) {
             have = b < a.B;
         } else {
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
     // stay in step (same instruction count whatever their lanes do) and share each fetched line; left alone they drift
     // apart and each pulls its own copy (ncu: no_instruction stalls 0.4 -> 1.1 per issue).
     auto any_left = [&]() -> bool {
-        if (GROUPS == 1 || a.loop_sync == 0) return __syncthreads_or(have) != 0;
+        if (GROUPS == 1 || a.loop_sync == 1) return __syncthreads_or(have) != 0;
         if constexpr (NW > 1) {   // the group's own barrier with an OR reduction (bar.red on a named barrier)
             unsigned r;
             asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -161,6 +163,10 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
         }
     };
     while (any_left()) {
+        if constexpr (Spec::QCOMMON) {
+            if (have && refetch) Spec::fetch_common(role, sL, q);   // the coordinates the solver role stepped for everybody
+            refetch = false;
+        }
         if (have) {
             Spec::evaluate(role, q, sT, c, sJ, sE);         // data.cpp:25-58, this role's tasks
             // The solver role's own tasks are the cheap ones: while the others still evaluate, it factorises the leading
@@ -197,10 +203,14 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
         if constexpr (NW > 1 && Spec::ARROW) {
             // Bordered-block-diagonal step (gen_solve_arrow): phase 1 on the role's own rows, ONE barrier, the stop test
             // (solver role, all of e visible), the small shared-column system in every role, y for the role's own rows.
-            T y[M];
+            T y[Spec::MY];
             Spec::psolve(role, sJ, sL, sE, a.damping2, y, group_sync, stop_test);
             group_sync();                                   // s and ||e||^2 visible (y is role-private)
-            if (have && !(abs_(*sRes) < a.tolerance)) Spec::step_role(role, sJ, sL, q, a.step_length, c);  // dls.cpp:52,61-71
+            if (have && !(abs_(*sRes) < a.tolerance)) {     // dls.cpp:52,61-71
+                if constexpr (Spec::MY != M) Spec::step_role(role, sJ, sL, q, a.step_length, c, y);   // y in the role's registers
+                else Spec::step_role(role, sJ, sL, q, a.step_length, c);
+                refetch = true;
+            }
         } else if constexpr (NW > 1 && Spec::PSOLVE) {
             // dls.cpp:39-41,53 distributed over the roles (cyclic row ownership, two barriers per block column).  Every
             // lane of every warp takes part in the barriers, also lanes without a problem (their arithmetic is garbage
@@ -381,7 +391,7 @@ int launch_spec_cfg_seg(const SpecHostConsts &hc, const SolveArgs<T> &a, long lo
     }
     if (ctas < 1) ctas = 1;
     SolveArgs<T> a2 = a;
-    if (const char *e = std::getenv("IKB_LOOP_SYNC")) a2.loop_sync = e[0] == 'g' ? 1 : 0;   // cta | group (A/B runs)
+    if (const char *e = std::getenv("IKB_LOOP_SYNC")) a2.loop_sync = e[0] == 'c' ? 1 : 0;   // cta | group (A/B runs)
     fn<<<(unsigned)ctas, GROUPS * Spec::NWARPS * 32, kSmem, s>>>(c, a2);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
@@ -405,6 +415,18 @@ template <class Spec, typename T> int launch_spec_tail(const SpecHostConsts &hc,
     // two CTAs per SM only if shared memory allows it and every thread still gets the full 255-register budget
     constexpr int kPerSm = (2 * (L::smem_bytes(1) + 1024) <= 228 * 1024 && 2 * Spec::NWARPS * 32 * 255 <= 65536) ? 2 : 1;
     long long ctas = (n + 31) / 32;
+    if constexpr (kPerSm == 2) {
+        // more groups than SMs: pair them in one CTA that starts every trip together, so the two groups share the
+        // instruction lines they fetch (a lone group streams ~40 KB of straight-line code per trip); IKB_TAIL_PAIR=0|1
+        const char *e = std::getenv("IKB_TAIL_PAIR");
+        if (ctas > sm_count && !(e && e[0] == '0')) {
+            ctas = (ctas + 1) / 2;
+            if (ctas > sm_count) ctas = sm_count;
+            SolveArgs<T> a2 = a;
+            a2.loop_sync = 1;
+            return launch_spec_cfg<Spec, T, 2, 1>(hc, a2, ctas, s);
+        }
+    }
     if (ctas > (long long)kPerSm * sm_count) ctas = (long long)kPerSm * sm_count;
     return launch_spec_cfg<Spec, T, 1, kPerSm>(hc, a, ctas, s);
 }

@@ -9,11 +9,14 @@
 // launch suspends and for batches too small to fill the GPU.  IKB_CASSIE_TAIL=0 selects the previous latency
 // configuration (W3, one 32-problem group per CTA) for A/B measurements.
 #include <cstdlib>
+#include <cstring>
 
 #include "dls_spec.cuh"
 #include "dls_team.cuh"
 #include "gen/cassie_feet_pelvis.cuh"
 #include "gen/cassie_feet_pelvis_arrow.cuh"
+#include "gen/cassie_feet_pelvis_arrow_b.cuh"
+#include "gen/cassie_feet_pelvis_arrow_c.cuh"
 #include "gen/cassie_feet_pelvis_w1.cuh"
 #include "gen/cassie_feet_pelvis_w2.cuh"
 
@@ -23,9 +26,18 @@ using S3 = SpecCassieFeetPelvis;
 using SA = SpecCassieFeetPelvisArrow;  // three roles, bordered-block-diagonal step (gen_solve_arrow) instead of the dense 12 x 12 solve
 using S2 = SpecCassieFeetPelvisW2;
 using S1 = SpecCassieFeetPelvisW1;
-bool use_arrow() {  // IKB_CASSIE_SOLVE=dense|arrow (A/B runs)
+using SB = SpecCassieFeetPelvisArrowB;  // ... factor / y in registers, free-flyer stepped once by the pelvis role
+using SC = SpecCassieFeetPelvisArrowC;  // ... factor / y in registers
+// IKB_CASSIE_SOLVE=dense|arrow|arrowb|arrowc (A/B runs); default: arrow in FP64, arrowb in FP32 (measured)
+int solve_variant(bool f64, bool tail) {
     const char *e = std::getenv("IKB_CASSIE_SOLVE");
-    return !(e && e[0] == 'd');
+    if (e && std::strcmp(e, "dense") == 0) return 0;
+    if (e && std::strcmp(e, "arrow") == 0) return 1;
+    if (e && std::strcmp(e, "arrowb") == 0) return 2;
+    if (e && std::strcmp(e, "arrowc") == 0) return 3;
+    // the throughput launch in FP64 is register-bound (168 per thread): factor in shared memory; everything else has
+    // registers to spare (the three arrow variants run the same arithmetic: bit-identical results, measured)
+    return (f64 && !tail) ? 1 : 2;
 }
 int roles(int dflt) {
     const char *e = std::getenv("IKB_CASSIE_ROLES");
@@ -99,10 +111,21 @@ template <typename T> int launch(const SpecHostConsts &hc, const SolveArgs<T> &a
                                  int bulk_roles) {
     if (variant == SPEC_TAIL) {
         if (use_team(sizeof(T) == 8, a.resume != 0)) return launch_team<T>(team_consts<T>(hc), a, n, sms, s);
-        return use_arrow() ? launch_spec_tail<SA, T>(hc, a, n, sms, s) : launch_spec_tail<S3, T>(hc, a, n, sms, s);
+        switch (solve_variant(sizeof(T) == 8, true)) {
+            case 0: return launch_spec_tail<S3, T>(hc, a, n, sms, s);
+            case 1: return launch_spec_tail<SA, T>(hc, a, n, sms, s);
+            case 2: return launch_spec_tail<SB, T>(hc, a, n, sms, s);
+            default: return launch_spec_tail<SC, T>(hc, a, n, sms, s);
+        }
     }
     switch (roles(bulk_roles)) {
-        case 3: return use_arrow() ? launch_spec_bulk<SA, T>(hc, a, n, sms, s) : launch_spec_bulk<S3, T>(hc, a, n, sms, s);
+        case 3:
+            switch (solve_variant(sizeof(T) == 8, false)) {
+                case 0: return launch_spec_bulk<S3, T>(hc, a, n, sms, s);
+                case 1: return launch_spec_bulk<SA, T>(hc, a, n, sms, s);
+                case 2: return launch_spec_bulk<SB, T>(hc, a, n, sms, s);
+                default: return launch_spec_bulk<SC, T>(hc, a, n, sms, s);
+            }
         case 2: return launch_spec_bulk<S2, T>(hc, a, n, sms, s);
         default: return launch_spec_bulk<S1, T>(hc, a, n, sms, s);
     }

@@ -52,6 +52,8 @@ static int spec_solve(const double *lower, const double *upper, const double *we
         if (Spec::PRE > 0) Spec::presolve(sJ, sL, sE, (T)(damping * damping));                      // solver role, before the barrier
         if (it == 0 && e_first) for (int i = 0; i < M; ++i) e_first[i] = (double)sE.get(i);
         T y[M], dq[NV];
+        std::vector<T> yr_buf((size_t)Spec::NWARPS * Spec::MY);   // arrow specs with y in the roles' registers
+        auto yr = [&](int role) -> T(&)[Spec::MY] { return *reinterpret_cast<T(*)[Spec::MY]>(yr_buf.data() + (size_t)role * Spec::MY); };
         if (parallel && Spec::NWARPS > 1) {
             // the role-distributed solve: one host thread per warp role, a std::barrier as the group barrier
             res = 0;
@@ -64,7 +66,7 @@ static int spec_solve(const double *lower, const double *upper, const double *we
                     auto sync = [&]() { bar.arrive_and_wait(); };
                     if constexpr (Spec::ARROW) {
                         auto hook = []() {};
-                        Spec::psolve(role, sJ, sL, sE, (T)(damping * damping), yl, sync, hook);
+                        Spec::psolve(role, sJ, sL, sE, (T)(damping * damping), yr(role), sync, hook);
                     } else {
                         Spec::psolve(role, sJ, sL, sE, (T)(damping * damping), yl, sync);
                     }
@@ -77,7 +79,12 @@ static int spec_solve(const double *lower, const double *upper, const double *we
         if (res < (T)tol) { success = 1; break; }
         if constexpr (Spec::DSTEP) {
             if (dstep) {
-                for (int role = 0; role < Spec::NWARPS; ++role) Spec::step_role(role, sJ, sL, qr(role), (T)step, c);
+                for (int role = 0; role < Spec::NWARPS; ++role) {
+                    if constexpr (Spec::MY != M) Spec::step_role(role, sJ, sL, qr(role), (T)step, c, yr(role));
+                    else Spec::step_role(role, sJ, sL, qr(role), (T)step, c);
+                }
+                if constexpr (Spec::QCOMMON)   // (the kernel does this behind the barrier at the top of the next trip)
+                    for (int role = 0; role < Spec::NWARPS; ++role) Spec::fetch_common(role, sL, qr(role));
                 ++it;
                 continue;
             }

@@ -540,6 +540,31 @@ def test_two_phase_scheduling_matches_oracle(params):
             assert np.array_equal(plain[k], piped[k]), (layout, k)
 
 
+@pytest.mark.parametrize("variant", ["dense", "arrow", "arrowb", "arrowc"])
+def test_cassie_solve_variants_match_oracle(variant, monkeypatch):
+    """Every compiled form of the Cassie step -- the dense 12 x 12 LDL^T on the solver role (r1) and the three layouts of
+    the bordered-block-diagonal step (gen_solve_arrow: factor in shared memory / in registers, free-flyer stepped once
+    or by every role) -- reproduces the oracle's flags, iteration counts and q on a BULK + TAIL batch, FP64."""
+    monkeypatch.setenv("IKB_CASSIE_SOLVE", variant)
+    pb = W.cassie_feet_pelvis_problem()
+    om = oracle_model("cassie")
+    B = 24000
+    q0, tg, _ = make_workload(pb, om, B, seed=777, standing=W.CASSIE_STANDING)
+    ref = O.dls_batch(oracle_problem_like(pb, om), q0, tg, nthreads=NT)
+    _compare("cassie solve variant %s" % variant, _solve_gpu(pb, q0, tg), ref, 1e-6)
+
+
+@pytest.mark.parametrize("variant", ["uniform", "arrow"])
+def test_humanoid_solve_variants_match_oracle(variant, monkeypatch):
+    """The humanoid's two compiled steps (dense factorisation distributed over the roles / bordered block diagonal)."""
+    monkeypatch.setenv("IKB_HUMANOID_SOLVE", variant)
+    pb = W.humanoid_problem()
+    om = oracle_model("humanoid")
+    q0, tg, _ = make_workload(pb, om, 2048, seed=31, start="near")
+    ref = O.dls_batch(oracle_problem_like(pb, om), q0, tg, nthreads=NT)
+    _compare("humanoid solve variant %s" % variant, _solve_gpu(pb, q0, tg), ref, 1e-6, converged_only=True)
+
+
 @pytest.mark.parametrize("ref", ["universe", "pelvis"])
 @pytest.mark.parametrize("ktype", ["Full", "Position"])
 def test_frame_constraint_null_space_projection(ktype, ref):

@@ -1179,6 +1179,21 @@ class Generator:
         # ---- strip layout ----
         SOFF = M
         off = M + ks
+        # "arrow_common_once": the joints common to all roles (the free-flyer) are stepped by the solver role alone, which
+        # publishes their new coordinates here; the other roles fetch them behind the barrier at the top of the next trip
+        # "arrow_fac_regs": the factor of D_a and y_a stay in the role's registers between the phases (few rows per role)
+        fac_regs = bool(self.spec.get("arrow_fac_regs", False))
+        self.arrow_qc = None      # one set of slots every role reads (factor in registers), or ...
+        self.arrow_mail = None    # ... role -> slots of its own copy ("mailbox": the role's factor slots and e rows, which are
+        #                               private to it and dead between the second barrier and its next evaluate -- no extra slots)
+        ncq = 0
+        if self.spec.get("arrow_common_once", True):
+            chains_ = [sorted(set(j for t in g for j in self.tasks[t]["chain"])) for g in groups]
+            ncq = len(self.joint_cols(sorted(set.intersection(*[set(ch) for ch in chains_])))[1])
+            if ncq and fac_regs:
+                self.arrow_qc = off
+                off += ncq
+        y_regs = fac_regs
         pub = {}     # role -> ("J", [slots]) | ("L", base)
         facb = {}    # role -> base of its factor (m (m + 1) / 2 slots) in sL
         for k in range(R):
@@ -1191,8 +1206,24 @@ class Generator:
             if privs[k]:
                 m = len(role_rows[k])
                 facb[k] = off
-                off += m * (m + 1) // 2
+                if not fac_regs:
+                    off += m * (m + 1) // 2
         nfact = off
+        mmax = max([len(role_rows[k]) for k in range(R) if privs[k]] or [1])
+        if ncq and not fac_regs:
+            mail = {}
+            for k in range(R):
+                if k == solver:
+                    continue
+                m = len(role_rows[k])
+                own = ([facb[k] + i for i in range(m * (m + 1) // 2)] if privs[k] else []) + list(role_rows[k])   # (e row r sits in slot r)
+                if len(own) < ncq:
+                    mail = None
+                    break
+                mail[k] = own[:ncq]
+            if mail is not None and not privs[solver]:
+                self.arrow_mail = mail
+                y_regs = True      # (y must not sit in the factor slots: the solver role fills the mailboxes while the others step)
         self.arrow_y = {}   # row -> sL slot of y[row] (rows of roles with private columns)
 
         def pub_at(k, idx):
@@ -1262,13 +1293,13 @@ class Generator:
             fac_l, fac_inv = {}, {}
             for j in range(m):
                 L.append(ind + "const T inv%d = rcp_(d%d_%d);" % (j, j, j))
-                fac_inv[j] = facb[k] + fi
-                L.append(ind + "sLr.set(%d, inv%d);" % (fac_inv[j] - dL, j))
+                fac_inv[j] = fi if fac_regs else facb[k] + fi
+                L.append(ind + ("fac[%d] = inv%d;" % (fi, j) if fac_regs else "sLr.set(%d, inv%d);" % (fac_inv[j] - dL, j)))
                 fi += 1
                 for i in range(j + 1, m):
                     L.append(ind + "const T l%d_%d = d%d_%d * inv%d;" % (i, j, i, j, j))
-                    fac_l[(i, j)] = facb[k] + fi
-                    L.append(ind + "sLr.set(%d, l%d_%d);" % (fac_l[(i, j)] - dL, i, j))
+                    fac_l[(i, j)] = fi if fac_regs else facb[k] + fi
+                    L.append(ind + ("fac[%d] = l%d_%d;" % (fi, i, j) if fac_regs else "sLr.set(%d, l%d_%d);" % (fac_l[(i, j)] - dL, i, j)))
                     fi += 1
                 for j2 in range(j + 1, m):
                     for i in range(j2, m):
@@ -1327,10 +1358,15 @@ class Generator:
                 F.append(ind + "const T r%d = sEr.get(%d)%s;" % (i, rows[i] - dR, "".join(" - " + t for t in terms)))
                 nf[k] += len(terms)
             for (i, j), idx in sorted(fac_l.items()):
-                F.append(ind + "const T fl%d_%d = sLr.get(%d);" % (i, j, idx - dL))
+                F.append(ind + ("const T fl%d_%d = fac[%d];" % (i, j, idx) if fac_regs else "const T fl%d_%d = sLr.get(%d);" % (i, j, idx - dL)))
             for j, idx in sorted(fac_inv.items()):
-                F.append(ind + "const T fi%d = sLr.get(%d);" % (j, idx - dL))
+                F.append(ind + ("const T fi%d = fac[%d];" % (j, idx) if fac_regs else "const T fi%d = sLr.get(%d);" % (j, idx - dL)))
             w = solve_lines(F, ["r%d" % i for i in range(m)], "y_", lname=lambda i, j: "fl%d_%d" % (i, j), iname=lambda j: "fi%d" % j)
+            if y_regs:
+                for i in range(m):
+                    F.append(ind + "y[%d] = %s;" % (i, w[i] if w[i] else "T(0)"))
+                    self.arrow_y[rows[i]] = ("reg", i)
+                return L, F
             F.append(ind + "IKB_PHASE_FENCE();   // the factor is in registers: its slots now carry y")
             for i in range(m):
                 F.append(ind + "sLr.set(%d, %s);" % (facb[k] + i - dL, w[i] if w[i] else "T(0)"))
@@ -1392,7 +1428,7 @@ class Generator:
         for i in range(ks - 1, -1, -1):
             Cc.append(ind + "s[%d] = cz%d * ci%d%s;" % (i, i, i, "".join(" - cl%d_%d * s[%d]" % (j, i, j) for j in range(i + 1, ks))))
         self.arrow = dict(shared=shared, spos=spos, soff=SOFF, ks=ks, nfact=nfact, fma=nf, mirror_of=mirror_of,
-                          pub=pub, facb=facb)
+                          pub=pub, facb=facb, fac_regs=fac_regs, y_regs=y_regs, nfac=mmax * (mmax + 1) // 2 if fac_regs else 1, my=mmax)
         self.rhs_off = 0
         return locals_, Cc, finishes
 
@@ -1423,9 +1459,12 @@ class Generator:
             own = [j for j in ch if j not in common] + (loose if k == solver else [])
             cols, qs = self.joint_cols(own)
             self.qmap = self.qmaps[k] if self.qmaps else None
+            self.ymap = {r: v[1] for r, v in self.arrow_y.items() if isinstance(v, tuple)} or None   # y in the role's registers
             roles.append(dq_lines(cols, ind + "    ") + self.gen_integrate(own, ind + "    "))
             qsets.append(qs + (cqs if k == solver else []))
         self.qmap = None
+        self.ymap = None
+        self.arrow_common = (cqs, ccols)
         return C, roles, qsets
 
     def gen_dq(self, cols=None, ind="        "):
@@ -1436,7 +1475,8 @@ class Generator:
             if not rs:
                 L.append(ind + "dq[%d] = T(0);" % c)
                 continue
-            expr = " + ".join("sJ.get(%d) * y[%d]" % (self.slots[(r, c)], r) for r in rs)
+            ymap = getattr(self, "ymap", None)
+            expr = " + ".join("sJ.get(%d) * y[%d]" % (self.slots[(r, c)], ymap[r] if ymap else r) for r in rs)
             L.append(ind + "dq[%d] = -(%s);" % (c, expr))
         return L
 
@@ -1596,6 +1636,8 @@ class Generator:
                    (self.nq, self.nv, rows, self.rows_p0, self.tsz, nslot, nfact))
         out.append("    // NQL: configuration registers per thread (arrow specs: a role keeps only the coordinates it reads and steps)")
         out.append("    static constexpr int NQL = %d;" % nql)
+        out.append("    // MY: entries of y a role keeps between psolve() and step_role() (arrow specs with the factor in registers: its own rows)")
+        out.append("    static constexpr int MY = %d;" % (self.arrow["my"] if arrow and self.arrow["y_regs"] else rows))
         out.append("    // warp roles: the tasks are split over NWARPS warps that evaluate concurrently; role SOLVER solves")
         out.append("    static constexpr int NWARPS = %d, SOLVER = %d;" % (len(groups), solver))
         out.append("    // PSOLVE: distribute the factorisation over the roles (pays off for large M; for M = 12 the ~7 extra group")
@@ -1699,13 +1741,13 @@ class Generator:
                     reb = ["        const S &sJr = sJ, &sEr = sE, &sLr = sL;"]
                     nm = "w%d" % k
                 out.append("    template <typename T, typename S>")
-                out.append("    static IKB_HD void arrow_local_%s(%sconst S &sJ, const S &sL, const S &sE, T damping2) {" % (nm, sig))
+                out.append("    static IKB_HD void arrow_local_%s(%sconst S &sJ, const S &sL, const S &sE, T damping2, T (&fac)[%d]) {" % (nm, sig, A["nfac"]))
                 out.extend(reb)
                 out.extend(locals_[k])
                 out.append("    }")
                 if finishes[k]:
                     out.append("    template <typename T, typename S>")
-                    out.append("    static IKB_HD void arrow_finish_%s(%sconst S &sJ, const S &sL, const S &sE, const T (&s)[%d]) {" % (nm, sig, A["ks"]))
+                    out.append("    static IKB_HD void arrow_finish_%s(%sconst S &sJ, const S &sL, const S &sE, const T (&s)[%d], const T (&fac)[%d], T (&y)[MY]) {" % (nm, sig, A["ks"], A["nfac"]))
                     out.extend(reb)
                     out.extend(finishes[k])
                     out.append("    }")
@@ -1720,13 +1762,13 @@ class Generator:
             out.append("    // phase 1 reads only the role's own rows of J and e: no barrier between evaluate() and psolve().  `hook` runs")
             out.append("    // right after the one barrier (all of e is visible and stays intact): the kernel's stop test and ticket prefetch.")
             out.append("    template <typename T, typename S, typename SYNC, typename HOOK>")
-            out.append("    static IKB_HD void psolve(int role, const S &sJ, const S &sL, const S &sE, T damping2, T (&y)[M], SYNC &sync, HOOK &hook) {")
-            out.append("        T s[%d];" % A["ks"])
+            out.append("    static IKB_HD void psolve(int role, const S &sJ, const S &sL, const S &sE, T damping2, T (&y)[MY], SYNC &sync, HOOK &hook) {")
+            out.append("        T s[%d], fac[%d];" % (A["ks"], A["nfac"]))
             for k in range(len(groups)):
                 if k in A["mirror_of"]:
                     continue
                 cond = "role == %d || role == %d" % (k, partner[k]) if k in partner else "role == %d" % k
-                fn = "arrow_local_m%d(role == %d ? 1 : 0, sJ, sL, sE, damping2)" % (k, partner[k]) if k in partner else "arrow_local_w%d(sJ, sL, sE, damping2)" % k
+                fn = "arrow_local_m%d(role == %d ? 1 : 0, sJ, sL, sE, damping2, fac)" % (k, partner[k]) if k in partner else "arrow_local_w%d(sJ, sL, sE, damping2, fac)" % k
                 out.append("        if (%s) %s;" % (cond, fn))
             out.append("        sync();  // every role's contribution to the shared-column system is in the strip")
             out.append("        hook();")
@@ -1736,13 +1778,14 @@ class Generator:
                 if k in A["mirror_of"] or not finishes[k]:
                     continue
                 cond = "role == %d || role == %d" % (k, partner[k]) if k in partner else "role == %d" % k
-                fn = "arrow_finish_m%d(role == %d ? 1 : 0, sJ, sL, sE, s)" % (k, partner[k]) if k in partner else "arrow_finish_w%d(sJ, sL, sE, s)" % k
+                fn = "arrow_finish_m%d(role == %d ? 1 : 0, sJ, sL, sE, s, fac, y)" % (k, partner[k]) if k in partner else "arrow_finish_w%d(sJ, sL, sE, s, fac, y)" % k
                 out.append("        if (%s) %s;" % (cond, fn))
             out.append("        if (role == %d) {" % solver)
             out.append("#pragma unroll")
             out.append("            for (int i = 0; i < %d; ++i) sL.set(%d + i, s[i]);" % (A["ks"], A["soff"]))
             out.append("        }")
             out.append("        (void)y;")
+            out.append("        (void)fac;")
             out.append("    }")
         psolve = [] if (uniform or arrow) else self.gen_solve_parallel(int(self.spec.get("parallel_block_width", self.spec.get("block_width", 4))), len(groups), solver)
         out.append("    // The same solve distributed over the warp roles (cyclic row ownership; see gen_solve_parallel): every role")
@@ -1774,8 +1817,10 @@ class Generator:
             C, roles, qsets = self.gen_step_roles_arrow(groups, solver) if arrow else self.gen_step_roles(groups, solver)
             out.append("    // Distributed step (see gen_step_roles): y from the strip; common joints by every role, the others by their role.")
             out.append("    template <typename T, typename S>")
-            out.append("    static IKB_HD void step_role(int role, const S &sJ, const S &sL, T (&q)[NQL], T step, const SpecConsts<T, NQ, M> &c) {")
-            out.append("        T y[M], dq[NV];")
+            yreg = arrow and self.arrow["y_regs"]
+            out.append("    static IKB_HD void step_role(int role, const S &sJ, const S &sL, T (&q)[NQL], T step, const SpecConsts<T, NQ, M> &c%s) {" %
+                       (", const T (&y)[MY]" if yreg else ""))
+            out.append("        T dq[NV];" if yreg else "        T y[M], dq[NV];")
             if not arrow:
                 out.append("        #pragma unroll")
                 out.append("        for (int i = 0; i < M; ++i) y[i] = sL.get(%d + i);" % self.rhs_off)
@@ -1783,10 +1828,23 @@ class Generator:
                 out.append("        T s[%d];" % self.arrow["ks"])
                 out.append("        #pragma unroll")
                 out.append("        for (int i = 0; i < %d; ++i) s[i] = sL.get(%d + i);" % (self.arrow["ks"], self.arrow["soff"]))
-            out.extend(C)
+            once = arrow and (self.arrow_qc is not None or self.arrow_mail is not None)
+            if once:   # the common joints: the solver role alone, which publishes the stepped coordinates (fetch_common)
+                out.append("        if (role == %d) {" % solver)
+                out.extend(C)
+                for i, iq in enumerate(self.arrow_common[0]):
+                    src = "q[%d]" % (self.qmaps[solver][iq] if self.qmaps else iq)
+                    if self.arrow_qc is not None:
+                        out.append("            sL.set(%d, %s);" % (self.arrow_qc + i, src))
+                    else:
+                        for k in sorted(self.arrow_mail):
+                            out.append("            sL.set(%d, %s);  // role %d's copy" % (self.arrow_mail[k][i], src, k))
+                out.append("        }")
+            else:
+                out.extend(C)
             for k, code in enumerate(roles):
                 out.append("        if (role == %d) {" % k)
-                if arrow:   # y of the role's own rows (phase 3 left it in the role's factor slots)
+                if arrow and not yreg:   # y of the role's own rows (phase 3 left it in the role's factor slots)
                     for t in sorted(groups[k]):
                         for i in range(self.tasks[t]["dim"]):
                             r = self.tasks[t]["row"] + i
@@ -1804,6 +1862,24 @@ class Generator:
                     out.append("            dst[%d * es] = q[%d];" % (iq, self.qmaps[k][iq] if self.qmaps else iq))
                 out.append("        }")
             out.append("    }")
+        out.append("    // QCOMMON: the coordinates common to all roles are stepped by the SOLVER role alone; after the barrier at the top of")
+        out.append("    // the next trip the other roles copy them from the strip (fetch_common)")
+        once = arrow and (self.arrow_qc is not None or self.arrow_mail is not None)
+        out.append("    static constexpr bool QCOMMON = %s;" % ("true" if once else "false"))
+        out.append("    template <typename T, typename S>")
+        out.append("    static IKB_HD void fetch_common(int role, const S &sL, T (&q)[NQL]) {")
+        if once and self.arrow_qc is not None:
+            out.append("        if (role != %d) {" % solver)
+            for i, iq in enumerate(self.arrow_common[0]):
+                out.append("            q[%d] = sL.get(%d);" % (self.qmaps[0][iq] if self.qmaps else iq, self.arrow_qc + i))
+            out.append("        }")
+        elif once:
+            for k in sorted(self.arrow_mail):
+                out.append("        if (role == %d) {" % k)
+                for i, iq in enumerate(self.arrow_common[0]):
+                    out.append("            q[%d] = sL.get(%d);" % (self.qmaps[0][iq] if self.qmaps else iq, self.arrow_mail[k][i]))
+                out.append("        }")
+        out.append("    }")
         out.append("    // the configuration of a problem into a role's registers (arrow specs: only the coordinates the role keeps)")
         out.append("    template <typename T>")
         out.append("    static IKB_HD void load_q(int role, const T *src, long long es, T (&q)[NQL]) {")
