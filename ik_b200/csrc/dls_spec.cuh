@@ -36,6 +36,12 @@
 #include "model.hpp"
 #include "spec_common.hpp"
 #include "specialized.hpp"
+#include "tmem_scratch.cuh"
+
+// 1: FP64 arrow kernels park the configuration registers in tensor memory between evaluate and step (tmem_scratch.cuh)
+#ifndef IKB_TMEM_Q
+#define IKB_TMEM_Q 1
+#endif
 
 namespace ikb {
 
@@ -99,6 +105,16 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
     };
 
     T q[Spec::NQL];                                       // (arrow specs: only the coordinates this role reads and steps)
+    // FP64 arrow kernels: q lives in tensor memory (32 columns of this thread's lane) whenever no phase needs it -- in
+    // registers only from the top of a trip to the end of evaluate, and from the step to the end of the trip
+    constexpr bool kTmemQ = IKB_TMEM_Q && Spec::ARROW && sizeof(T) == 8 && Spec::NQL <= 16;
+    constexpr int kTmemCols = (GROUPS * NW + 3) / 4 * 32 <= 32 ? 32 : (GROUPS * NW + 3) / 4 * 32 <= 64 ? 64 : (GROUPS * NW + 3) / 4 * 32 <= 128 ? 128 : 256;
+    uint32_t tmem_base = 0, tmem_q = 0;
+    if constexpr (kTmemQ) {
+        static_assert((GROUPS * NW + 3) / 4 * 32 <= 256, "too many warps for one 32-column slot each");
+        tmem_base = tmem_provision<kTmemCols>(reinterpret_cast<uint32_t *>(smem_raw), warp);
+        tmem_q = tmem_base + ((uint32_t)(warp & 3) * 32u << 16) + (uint32_t)(warp >> 2) * 32u;   // lane quarter | column slot
+    }
     long long b;
     int it = 0;
     bool have;
@@ -121,8 +137,9 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
             const ProblemIO<T> io = problem_io<SEG>(a, b);
             const T *src = a.resume ? io.q : io.q0;       // a suspended problem continues from its saved iterate
             const long long es = a.resume ? io.q_es : io.q0_es;
-            Spec::load_q(role, src, es, q);
-            Spec::load_targets(role, io.targets, io.tg_es, sT);
+            Spec::load_targets(role, io.targets, io.tg_es, sT);   // cp.async: the whole pose in flight at once ...
+            Spec::load_q(role, src, es, q);                        // ... under the loads of the configuration
+            strip_copies_wait();
         }
     };
     // SOLVER role, after the solve: dq = -J^T y, the manifold step and the clamp on ITS copy of q, which it then publishes
@@ -146,6 +163,7 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
     group_sync();
     b = *sNext;
     load_problem();
+    if constexpr (kTmemQ) tmem_park(tmem_q, q);
 
     // CTA-wide barrier at the top of every trip: the body is ~100 KB of straight-line code, far more than the 32 KB
     // instruction cache in front of L2, so every warp streams it from L2 on every trip.  Warps that start a trip together
@@ -163,6 +181,7 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
         }
     };
     while (any_left()) {
+        if constexpr (kTmemQ) tmem_fetch(tmem_q, q);        // (all lanes: the transfer is warp-wide)
         if constexpr (Spec::QCOMMON) {
             if (have && refetch) Spec::fetch_common(role, sL, q);   // the coordinates the solver role stepped for everybody
             refetch = false;
@@ -194,7 +213,10 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
             bool susp = false;
             if (it + 1 >= a.it_cap && !(res < a.tolerance) && it + 1 < a.max_iterations)
                 susp = *(volatile unsigned long long *)a.ticket >= (unsigned long long)a.B;
-            if (res < a.tolerance || it + 1 >= a.max_iterations || susp) *sNext = (long long)atomicAdd(a.ticket, 1ULL);
+            if (res < a.tolerance || it + 1 >= a.max_iterations || susp) {
+                const long long nb = (long long)atomicAdd(a.ticket, 1ULL);
+                *sNext = nb;
+            }
             sres_mine = susp ? -res : res;
             if constexpr (Spec::ARROW) *sRes = sres_mine;
             }
@@ -205,7 +227,9 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
             // (solver role, all of e visible), the small shared-column system in every role, y for the role's own rows.
             T y[Spec::MY];
             Spec::psolve(role, sJ, sL, sE, a.damping2, y, group_sync, stop_test);
-            group_sync();                                   // s and ||e||^2 visible (y is role-private)
+            if constexpr (!Spec::CAPSOLO) group_sync();     // s and ||e||^2 visible (y is role-private)
+            if constexpr (kTmemQ) tmem_fetch(tmem_q, q);    // back for the step (a non-solver role's copy of the common
+                                                            // coordinates is stale here: it neither steps nor stores them)
             if (have && !(abs_(*sRes) < a.tolerance)) {     // dls.cpp:52,61-71
                 if constexpr (Spec::MY != M) Spec::step_role(role, sJ, sL, q, a.step_length, c, y);   // y in the role's registers
                 else Spec::step_role(role, sJ, sL, q, a.step_length, c);
@@ -277,7 +301,9 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
                 load_problem();
             }
         }
+        if constexpr (kTmemQ) tmem_park(tmem_q, q);         // stepped, refilled or unchanged: out of the registers again
     }
+    if constexpr (kTmemQ) tmem_release<kTmemCols>(tmem_base, warp);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------

@@ -16,7 +16,6 @@
 #include "gen/cassie_feet_pelvis.cuh"
 #include "gen/cassie_feet_pelvis_arrow.cuh"
 #include "gen/cassie_feet_pelvis_arrow_b.cuh"
-#include "gen/cassie_feet_pelvis_arrow_c.cuh"
 #include "gen/cassie_feet_pelvis_w1.cuh"
 #include "gen/cassie_feet_pelvis_w2.cuh"
 
@@ -27,14 +26,13 @@ using SA = SpecCassieFeetPelvisArrow;  // three roles, bordered-block-diagonal s
 using S2 = SpecCassieFeetPelvisW2;
 using S1 = SpecCassieFeetPelvisW1;
 using SB = SpecCassieFeetPelvisArrowB;  // ... factor / y in registers, free-flyer stepped once by the pelvis role
-using SC = SpecCassieFeetPelvisArrowC;  // ... factor / y in registers
-// IKB_CASSIE_SOLVE=dense|arrow|arrowb|arrowc (A/B runs); default: arrow in FP64, arrowb in FP32 (measured)
+// IKB_CASSIE_SOLVE=dense|arrow|arrowb (A/B runs).  (Solving the shared-column system on the pelvis role alone --
+// spec option arrow_cap_solo -- was measured too: 3.13 ms against 3.10 ms for 8 x 65 536, not kept.)
 int solve_variant(bool f64, bool tail) {
     const char *e = std::getenv("IKB_CASSIE_SOLVE");
     if (e && std::strcmp(e, "dense") == 0) return 0;
     if (e && std::strcmp(e, "arrow") == 0) return 1;
     if (e && std::strcmp(e, "arrowb") == 0) return 2;
-    if (e && std::strcmp(e, "arrowc") == 0) return 3;
     // the throughput launch in FP64 is register-bound (168 per thread): factor in shared memory; everything else has
     // registers to spare (the three arrow variants run the same arithmetic: bit-identical results, measured)
     return (f64 && !tail) ? 1 : 2;
@@ -114,8 +112,7 @@ template <typename T> int launch(const SpecHostConsts &hc, const SolveArgs<T> &a
         switch (solve_variant(sizeof(T) == 8, true)) {
             case 0: return launch_spec_tail<S3, T>(hc, a, n, sms, s);
             case 1: return launch_spec_tail<SA, T>(hc, a, n, sms, s);
-            case 2: return launch_spec_tail<SB, T>(hc, a, n, sms, s);
-            default: return launch_spec_tail<SC, T>(hc, a, n, sms, s);
+            default: return launch_spec_tail<SB, T>(hc, a, n, sms, s);
         }
     }
     switch (roles(bulk_roles)) {
@@ -123,8 +120,7 @@ template <typename T> int launch(const SpecHostConsts &hc, const SolveArgs<T> &a
             switch (solve_variant(sizeof(T) == 8, false)) {
                 case 0: return launch_spec_bulk<S3, T>(hc, a, n, sms, s);
                 case 1: return launch_spec_bulk<SA, T>(hc, a, n, sms, s);
-                case 2: return launch_spec_bulk<SB, T>(hc, a, n, sms, s);
-                default: return launch_spec_bulk<SC, T>(hc, a, n, sms, s);
+                default: return launch_spec_bulk<SB, T>(hc, a, n, sms, s);
             }
         case 2: return launch_spec_bulk<S2, T>(hc, a, n, sms, s);
         default: return launch_spec_bulk<S1, T>(hc, a, n, sms, s);

@@ -28,6 +28,26 @@ template <typename T, int STRIDE> struct Strip {
     IKB_HD void set(int k, T v) const { base[k * STRIDE] = v; }
     IKB_HD T get(int k) const { return base[k * STRIDE]; }
     IKB_HD T operator[](int k) const { return base[k * STRIDE]; }
+    // element k <- *src, asynchronously on the device (cp.async: global -> shared without a register in between, so a
+    // whole pose is in flight at once and its latency is paid once); the copying thread calls strip_copies_wait() before
+    // it reads the strip.  The strips are only ever read by the thread that filled them, so no barrier is involved.
+    IKB_HD void copy_in(int k, const T *src) const {
+#if defined(__CUDA_ARCH__)
+        static_assert(sizeof(T) == 4 || sizeof(T) == 8, "cp.async copies 4, 8 or 16 bytes");
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(base + k * STRIDE);
+        if (sizeof(T) == 8)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+        else
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+#else
+        base[k * STRIDE] = *src;
+#endif
+    }
 };
+IKB_HD void strip_copies_wait() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
 
 }  // namespace ikb

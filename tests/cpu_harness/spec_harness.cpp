@@ -8,6 +8,7 @@
 
 #include "../../ik_b200/csrc/gen/cassie_feet_pelvis.cuh"
 #include "../../ik_b200/csrc/gen/cassie_feet_pelvis_arrow.cuh"
+#include "../../ik_b200/csrc/gen/cassie_feet_pelvis_arrow_b.cuh"
 #include "../../ik_b200/csrc/gen/cassie_feet_pelvis_w1.cuh"
 #include "../../ik_b200/csrc/gen/cassie_feet_pelvis_w2.cuh"
 #include "../../ik_b200/csrc/gen/humanoid_limbs.cuh"
@@ -148,6 +149,7 @@ static void spec_eval(const double *weight, const double *q0, const double *targ
 
 IKB_SPEC_EXPORT(h_spec_cassie_feet_pelvis, SpecCassieFeetPelvis)
 IKB_SPEC_EXPORT(h_spec_cassie_feet_pelvis_arrow, SpecCassieFeetPelvisArrow)
+IKB_SPEC_EXPORT(h_spec_cassie_feet_pelvis_arrow_b, SpecCassieFeetPelvisArrowB)
 IKB_SPEC_EXPORT(h_spec_cassie_feet_pelvis_w1, SpecCassieFeetPelvisW1)
 IKB_SPEC_EXPORT(h_spec_cassie_feet_pelvis_w2, SpecCassieFeetPelvisW2)
 IKB_SPEC_EXPORT(h_spec_manipulator_tool, SpecManipulatorTool)

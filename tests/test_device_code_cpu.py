@@ -114,6 +114,7 @@ def _spec_solve(lib, name, dtype, pb, q0, tg, prm):
 
 CASES = [("cassie_feet_pelvis", "cassie", True, W.cassie_feet_pelvis_problem, W.CASSIE_STANDING),      # 3 warp roles
          ("cassie_feet_pelvis_arrow", "cassie", True, W.cassie_feet_pelvis_problem, W.CASSIE_STANDING),   # 3 roles, shared / private column split
+         ("cassie_feet_pelvis_arrow_b", "cassie", True, W.cassie_feet_pelvis_problem, W.CASSIE_STANDING),   # ... factor / y in registers
          ("cassie_feet_pelvis_w1", "cassie", True, W.cassie_feet_pelvis_problem, W.CASSIE_STANDING),   # 1 role, legs interleaved
          ("cassie_feet_pelvis_w2", "cassie", True, W.cassie_feet_pelvis_problem, W.CASSIE_STANDING),   # 2 roles
          ("manipulator_tool", "manipulator", False, W.manipulator_problem, "near"),
@@ -243,6 +244,7 @@ def test_branch_free_sincos_and_atan2(math_lib):
 
 
 @pytest.mark.parametrize("name,robot,ff,make,standing", [c for c in CASES if c[0] in ("cassie_feet_pelvis", "cassie_feet_pelvis_w2", "cassie_feet_pelvis_arrow",
+                                                                                     "cassie_feet_pelvis_arrow_b",
                                                                                      "humanoid_limbs", "humanoid_limbs_arrow")])
 def test_role_distributed_solve_matches_oracle(spec_lib, name, robot, ff, make, standing):
     """psolve_w<k>: the factorisation split over the warp roles (one host thread per role, std::barrier = group barrier)

@@ -1217,6 +1217,10 @@ class Generator:
                     continue
                 m = len(role_rows[k])
                 own = ([facb[k] + i for i in range(m * (m + 1) // 2)] if privs[k] else []) + list(role_rows[k])   # (e row r sits in slot r)
+                if self.spec.get("arrow_cap_solo"):
+                    # the solver role alone reads the published contributions, before the second barrier of psolve(); the
+                    # factor and e are still being read by the role's phase 3 when the solver role steps
+                    own = [pub[k][1] + i for i in range(per)] if pub[k][0] == "L" else []
                 if len(own) < ncq:
                     mail = None
                     break
@@ -1647,6 +1651,8 @@ class Generator:
         out.append("    static constexpr bool DSTEP = %s;" % ("true" if (uniform or arrow) else "false"))
         out.append("    // ARROW: psolve() is the bordered-block-diagonal step (gen_solve_arrow); the serial solve() is not laid out for its strip")
         out.append("    static constexpr bool ARROW = %s;" % ("true" if arrow else "false"))
+        out.append("    // CAPSOLO: psolve() ends behind a barrier of its own (the shared-column system is solved by the SOLVER role alone)")
+        out.append("    static constexpr bool CAPSOLO = %s;" % ("true" if arrow and self.spec.get("arrow_cap_solo") else "false"))
         out.append("    // PRE: leading rows whose P x P factor block the SOLVER role computes in presolve(), before the first barrier;")
         out.append("    // EOFF: slot of the factor strip where e starts (rows >= PRE of L, written only after e has been read)")
         out.append("    static constexpr int PRE = %d, EOFF = %d;" % (P, self.eoff))
@@ -1661,8 +1667,8 @@ class Generator:
             out.append("    static IKB_HD void load_targets_w%d(const T *tg, long long es, const S &sT) {" % k)
             for t in g:
                 toff = self.tasks[t]["toff"]
-                out.append("#pragma unroll 4")
-                out.append("        for (int k = %d; k < %d; ++k) sT.set(k, tg[k * es]);" % (toff, toff + self.tasks[t]["tsize"]))
+                out.append("#pragma unroll")
+                out.append("        for (int k = %d; k < %d; ++k) sT.copy_in(k, tg + k * es);  // asynchronous: strip_copies_wait() before evaluate" % (toff, toff + self.tasks[t]["tsize"]))
             out.append("    }")
             if ev is None:
                 continue
@@ -1772,7 +1778,20 @@ class Generator:
                 out.append("        if (%s) %s;" % (cond, fn))
             out.append("        sync();  // every role's contribution to the shared-column system is in the strip")
             out.append("        hook();")
-            out.extend(cap)
+            if self.spec.get("arrow_cap_solo"):
+                # the small system on the solver role alone (the others wait at a second barrier instead of repeating it)
+                out.append("        if (role == %d) {" % solver)
+                out.extend(cap)
+                out.append("#pragma unroll")
+                out.append("            for (int i = 0; i < %d; ++i) sL.set(%d + i, s[i]);" % (A["ks"], A["soff"]))
+                out.append("        }")
+                out.append("        sync();  // s, ||e||^2 and the next ticket are visible: the kernel needs no barrier behind psolve()")
+                out.append("        if (role != %d) {" % solver)
+                out.append("#pragma unroll")
+                out.append("            for (int i = 0; i < %d; ++i) s[i] = sL.get(%d + i);" % (A["ks"], A["soff"]))
+                out.append("        }")
+            else:
+                out.extend(cap)
             out.append("        IKB_PHASE_FENCE();")
             for k in range(len(groups)):
                 if k in A["mirror_of"] or not finishes[k]:
@@ -1780,10 +1799,11 @@ class Generator:
                 cond = "role == %d || role == %d" % (k, partner[k]) if k in partner else "role == %d" % k
                 fn = "arrow_finish_m%d(role == %d ? 1 : 0, sJ, sL, sE, s, fac, y)" % (k, partner[k]) if k in partner else "arrow_finish_w%d(sJ, sL, sE, s, fac, y)" % k
                 out.append("        if (%s) %s;" % (cond, fn))
-            out.append("        if (role == %d) {" % solver)
-            out.append("#pragma unroll")
-            out.append("            for (int i = 0; i < %d; ++i) sL.set(%d + i, s[i]);" % (A["ks"], A["soff"]))
-            out.append("        }")
+            if not self.spec.get("arrow_cap_solo"):
+                out.append("        if (role == %d) {" % solver)
+                out.append("#pragma unroll")
+                out.append("            for (int i = 0; i < %d; ++i) sL.set(%d + i, s[i]);" % (A["ks"], A["soff"]))
+                out.append("        }")
             out.append("        (void)y;")
             out.append("        (void)fac;")
             out.append("    }")
