@@ -179,7 +179,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the `configs` / `strong` / product multi-GPU sections")
     ap.add_argument("--merge", type=int, default=8, help="consecutive batches per kernel pair in the pipelined queue (1 = off)")
-    ap.add_argument("--depth", type=int, default=16, help="batches in flight in the pipelined queue")
+    ap.add_argument("--depth", type=int, default=24, help="batches in flight in the pipelined queue")
     ap.add_argument("--e2e-merge", type=int, default=4, help="the same for the host-buffer (e2e) arm: smaller groups keep the "
                     "PCIe pipeline's fill / drain short")
     ap.add_argument("--e2e-depth", type=int, default=8)

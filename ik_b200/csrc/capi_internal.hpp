@@ -237,6 +237,29 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
                  const SolveAux<T> *aux = nullptr);
 // (pik_lambda != nullptr: ik::pik instead of ik::dls -- per-level damping, table-driven kernel only)
 
+// Carried stragglers (pipelined queue): a merged BULK launch whose stragglers have not been continued yet.  `tail` is
+// the complete argument block of the TAIL launch that would finish them (resume = 1: suspended list, its count, the
+// saved step counts, the group's segment table, the solver parameters); the NEXT merged launch of the queue continues
+// them instead (launch_merged_carry), beside its own problems, and only a queue that runs empty launches the TAIL.
+template <typename T> struct CarryState {
+    bool valid = false;
+    SolveArgs<T> tail;
+};
+// Queue-owned scratch of one merged launch (two sets, used alternately): suspended list, step counts, 4 counters.
+struct CarryScratch {
+    unsigned int *list = nullptr;
+    int *iters = nullptr;
+    unsigned long long *counters = nullptr;
+    size_t cap = 0;
+};
+// BULK launch of a merged group that first continues `in`'s stragglers (in may be null / invalid); its own stragglers
+// are left suspended and described by `out`.  Requires a specialised kernel and two_phase(p, prm, B).
+template <typename T>
+int launch_merged_carry(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, const Merged<T> *merged, cudaStream_t s,
+                        const CarryScratch &own, const CarryState<T> *in, CarryState<T> *out);
+// The TAIL launch that finishes `c`'s stragglers.
+template <typename T> int launch_carry_tail(const ikb_problem *p, const CarryState<T> &c, cudaStream_t s);
+
 // The table-driven team-per-problem kernel (ikb_coop.cu / dls_coop.cuh) for size class `cls`.
 template <typename T>
 int launch_coop(int cls, const DevProblem<T> *dP, const SolveArgs<T> &a, bool pik, int extra /* 0 plain, 1 CoM, 2 constraints */, bool shfl, int sm_count,

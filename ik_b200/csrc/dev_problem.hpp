@@ -113,6 +113,14 @@ template <typename T> struct SolveArgs {
     // measured +3 % on the Cassie bulk launch), 1 = the CTA's groups start every trip together (IKB_LOOP_SYNC=cta)
     int loop_sync;
     BatchSeg<T> seg[kMaxSegments];
+    // Carried stragglers (pipelined queue, ikb_queue.cu): the problems the PREVIOUS merged launch suspended when its
+    // ticket queue ran dry are not given a TAIL launch of their own; this launch continues them first -- tickets
+    // [0, *carry_count) -- beside its own fresh problems, from the iterates / step counts the previous launch saved.  They
+    // live in the previous launch's buffers (`cseg`) and are never suspended again.  carry_list == NULL: nothing carried.
+    const unsigned int *carry_list;
+    const unsigned long long *carry_count;
+    const int *carry_iters;
+    BatchSeg<T> cseg[kMaxSegments];
 };
 
 // Buffers of ONE problem, resolved from its launch-wide index (all pointers already point at the problem).
@@ -125,6 +133,15 @@ template <typename T> struct ProblemIO {
     T *resid;
 };
 #if defined(__CUDACC__)
+template <typename T> __device__ __forceinline__ ProblemIO<T> segment_io(const BatchSeg<T> (&seg)[kMaxSegments], long long b) {
+    int s = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxSegments; ++i) s += b >= seg[i].begin ? 1 : 0;
+    const BatchSeg<T> &g = seg[s];
+    const long long l = b - g.begin;
+    return {g.q0 + l * g.q0_bs, g.q0_es, g.targets + l * g.tg_bs, g.tg_es, g.q + l * g.q_bs, g.q_es,
+            g.success ? g.success + l : nullptr, g.iters ? g.iters + l : nullptr, g.resid ? g.resid + l : nullptr};
+}
 // SEG = false: one batch, plain pointer arithmetic on the launch arguments.
 // SEG = true : merged launch, segment lookup in the (constant-bank) kernel parameters.
 template <bool SEG, typename T> __device__ __forceinline__ ProblemIO<T> problem_io(const SolveArgs<T> &a, long long b) {

@@ -121,11 +121,30 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
     bool refetch = false;   // Spec::QCOMMON: this slot's problem was stepped in the last trip and goes on
 
     // b holds a ticket on entry: a problem index (fresh problems) or an index into the suspended list (tail launch)
+    // (merged launches only) the stragglers carried over from the previous launch take the first tickets
+    long long ncarry = 0;
+    if constexpr (SEG)
+        if (a.carry_list) ncarry = (long long)*a.carry_count;
+    bool carried = false;   // this slot's problem is one of them: it lives in the previous launch's buffers
+    auto pio = [&](long long idx) -> ProblemIO<T> {
+        if constexpr (SEG)
+            if (carried) return segment_io<T>(a.cseg, idx);
+        return problem_io<SEG>(a, idx);
+    };
     auto load_problem = [&]() {
         it = 0;
         refetch = false;
+        carried = false;
         if (!a.resume) {
-            have = b < a.B;
+            if (SEG && b < ncarry) {
+                carried = true;
+                have = true;
+                b = a.carry_list[b];
+                it = a.carry_iters[b];
+            } else {
+                b -= ncarry;
+                have = b < a.B;
+            }
         } else {
             have = b < (long long)*a.list_count;
             if (have) {
@@ -134,9 +153,9 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
             }
         }
         if (have) {
-            const ProblemIO<T> io = problem_io<SEG>(a, b);
-            const T *src = a.resume ? io.q : io.q0;       // a suspended problem continues from its saved iterate
-            const long long es = a.resume ? io.q_es : io.q0_es;
+            const ProblemIO<T> io = pio(b);
+            const T *src = (a.resume || carried) ? io.q : io.q0;       // a suspended problem continues from its saved iterate
+            const long long es = (a.resume || carried) ? io.q_es : io.q0_es;
             Spec::load_targets(role, io.targets, io.tg_es, sT);   // cp.async: the whole pose in flight at once ...
             Spec::load_q(role, src, es, q);                        // ... under the loads of the configuration
             strip_copies_wait();
@@ -211,8 +230,8 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
             // straggler -- suspend it after this step and let the tail launch continue it (res >= tolerance > 0 here, so
             // the decision travels to the other roles in the sign of the residual).
             bool susp = false;
-            if (it + 1 >= a.it_cap && !(res < a.tolerance) && it + 1 < a.max_iterations)
-                susp = *(volatile unsigned long long *)a.ticket >= (unsigned long long)a.B;
+            if (it + 1 >= a.it_cap && !(res < a.tolerance) && it + 1 < a.max_iterations && !carried)
+                susp = *(volatile unsigned long long *)a.ticket >= (unsigned long long)(a.B + ncarry);
             if (res < a.tolerance || it + 1 >= a.max_iterations || susp) {
                 const long long nb = (long long)atomicAdd(a.ticket, 1ULL);
                 *sNext = nb;
@@ -279,11 +298,11 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
             }
             if (finished || suspend) {
                 if constexpr (Spec::DSTEP) {                // every role holds (and writes) its own coordinates
-                    const ProblemIO<T> io = problem_io<SEG>(a, b);
+                    const ProblemIO<T> io = pio(b);
                     Spec::store_q(role, q, io.q, io.q_es);
                 }
                 if (role == Spec::SOLVER) {
-                    const ProblemIO<T> io = problem_io<SEG>(a, b);
+                    const ProblemIO<T> io = pio(b);
                     if constexpr (!Spec::DSTEP) {
 #pragma unroll
                         for (int k = 0; k < NQ; ++k) io.q[k * io.q_es] = q[k];

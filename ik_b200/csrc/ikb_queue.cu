@@ -20,6 +20,7 @@ struct ikb_queue {
         cudaEvent_t tr_in0 = nullptr, tr_c0 = nullptr, tr_c1 = nullptr;  // IKB_QUEUE_TRACE only
         double tr_submit_ms = 0;
         bool busy = false, pending = false, host = false;
+        bool deferred = false;  // launched, but its group's stragglers are still carried (ev_done not recorded yet)
         int64_t ticket = -1;  // the batch occupying the slot
         int64_t B = 0;
         ikb_batch_io dio{};   // device view of the batch
@@ -41,6 +42,18 @@ struct ikb_queue {
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
     cudaEvent_t ev_user = nullptr, ev_comp = nullptr;
     int64_t next = 0;
+    // Carried stragglers: the last merged device-buffer group was launched WITHOUT its TAIL; the next such group's BULK
+    // launch continues its stragglers (capi_internal.hpp, CarryState), and whoever needs the group's results before that
+    // (wait, flush, drain, slot reuse, a group that cannot carry) launches the TAIL (queue_finish_carry).
+    bool carry_on = true;           // IKB_QUEUE_CARRY=0 disables it (A/B runs)
+    bool carry_valid = false;
+    int carry_dtype = -1;
+    ikb_dls_params carry_prm{};
+    std::vector<int> carry_slots;
+    CarryState<double> carry64;
+    CarryState<float> carry32;
+    CarryScratch cscratch[2];
+    int cscratch_next = 0;
     // IKB_QUEUE_TRACE=1: device timeline of every host batch on stderr (printed by ikb_queue_wait)
     bool trace = false, tr_started = false;
     cudaEvent_t tr_ref = nullptr;
@@ -69,6 +82,60 @@ template <typename T> int queue_copy_out(ikb_queue *q, ikb_queue::Slot &sl) {
     return IKB_OK;
 }
 
+template <typename T> CarryState<T> &carry_state(ikb_queue *q);
+template <> CarryState<double> &carry_state<double>(ikb_queue *q) { return q->carry64; }
+template <> CarryState<float> &carry_state<float>(ikb_queue *q) { return q->carry32; }
+
+// The carried group's results become final with what has been enqueued on the compute stream so far: device batches
+// are done there, host batches get their copy-out behind it.
+int queue_complete_carry(ikb_queue *q) {
+    bool any_host = false;
+    for (int i : q->carry_slots) any_host |= q->slots[i].host;
+    if (any_host) {
+        IKB_CUDA(cudaEventRecord(q->ev_comp, q->s_comp));
+        IKB_CUDA(cudaStreamWaitEvent(q->s_out, q->ev_comp, 0));
+    }
+    for (int i : q->carry_slots) {
+        ikb_queue::Slot &sl = q->slots[i];
+        if (sl.host) {
+            int rc = IKB_OK;
+            if (sl.B > 0) rc = q->carry_dtype == IKB_F64 ? queue_copy_out<double>(q, sl) : queue_copy_out<float>(q, sl);
+            if (rc) return rc;
+            IKB_CUDA(cudaEventRecord(sl.ev_done, q->s_out));
+        } else {
+            IKB_CUDA(cudaEventRecord(sl.ev_done, q->s_comp));
+        }
+        sl.deferred = false;
+    }
+    q->carry_slots.clear();
+    q->carry_valid = false;
+    q->carry64.valid = false;
+    q->carry32.valid = false;
+    return IKB_OK;
+}
+// Nobody will continue the carried stragglers: give them their TAIL launch.
+int queue_finish_carry(ikb_queue *q) {
+    if (!q->carry_valid) return IKB_OK;
+    const int rc = q->carry_dtype == IKB_F64 ? launch_carry_tail<double>(q->p, q->carry64, q->s_comp) : launch_carry_tail<float>(q->p, q->carry32, q->s_comp);
+    const int rc2 = queue_complete_carry(q);
+    return rc ? rc : rc2;
+}
+int carry_scratch_reserve(CarryScratch &c, size_t n) {
+    if (!c.counters) {
+        IKB_CUDA(cudaMalloc(&c.counters, 4 * sizeof(unsigned long long)));
+        IKB_CUDA(cudaMemset(c.counters, 0, 4 * sizeof(unsigned long long)));
+    }
+    if (c.cap >= n) return IKB_OK;
+    // (the old buffers may still be read by kernels in flight: the queue's streams are drained first)
+    IKB_CUDA(cudaDeviceSynchronize());
+    cudaFree(c.list); cudaFree(c.iters);
+    c.list = nullptr; c.iters = nullptr; c.cap = 0;
+    IKB_CUDA(cudaMalloc(&c.list, n * sizeof(unsigned int)));
+    IKB_CUDA(cudaMalloc(&c.iters, n * sizeof(int)));
+    c.cap = n;
+    return IKB_OK;
+}
+
 // Launch the open group: one merged BULK + TAIL pair when the problem has a specialised kernel, else batch by batch.
 template <typename T> int queue_flush_t(ikb_queue *q) {
     const int n = (int)q->open.size();
@@ -89,8 +156,41 @@ template <typename T> int queue_flush_t(ikb_queue *q) {
             total += sl.B;
         }
         const Merged<T> m{tab, n};
+        // (host batches do not carry: measured, their copy-out one launch later costs the host pipeline more -- 114 M against
+        // 137 M solves / s end to end -- than the TAIL launch it saves)
+        bool any_host_ = false;
+        for (int i : q->open) any_host_ |= q->slots[i].host;
+        const bool can_carry = q->carry_on && !any_host_ && !q->trace && two_phase(q->p, &q->open_prm, total);
+        // a carried group that this launch cannot continue gets its TAIL now
+        if (q->carry_valid && !(can_carry && q->carry_dtype == q->open_dtype && same_params(q->carry_prm, q->open_prm)) && (rc = queue_finish_carry(q)))
+            return rc;
+        if (can_carry) {
+            CarryScratch &own = q->cscratch[q->cscratch_next];
+            if ((size_t)total > own.cap) {   // growing the scratch synchronises: finish what is carried first; both sets, with head room
+                if ((rc = queue_finish_carry(q))) return rc;
+                const size_t want = (size_t)total + (size_t)total / 2;
+                for (auto &c : q->cscratch)
+                    if ((rc = carry_scratch_reserve(c, want))) return rc;
+            }
+            CarryState<T> out;
+            if ((rc = launch_merged_carry<T>(q->p, &q->open_prm, total, &m, q->s_comp, own, q->carry_valid ? &carry_state<T>(q) : nullptr, &out))) return rc;
+            q->cscratch_next ^= 1;
+            if (q->carry_valid && (rc = queue_complete_carry(q))) return rc;   // the previous group's stragglers ran in this launch
+            carry_state<T>(q) = out;
+            q->carry_valid = true;
+            q->carry_dtype = q->open_dtype;
+            q->carry_prm = q->open_prm;
+            q->carry_slots = q->open;
+            for (int i : q->open) {
+                q->slots[i].pending = false;
+                q->slots[i].deferred = true;
+            }
+            q->open.clear();
+            return IKB_OK;
+        }
         if ((rc = launch_solve<T>(q->p, &q->open_prm, total, nullptr, q->s_comp, nullptr, &m))) return rc;
     } else {
+        if (q->carry_valid && (rc = queue_finish_carry(q))) return rc;
         for (int i : q->open) {
             ikb_queue::Slot &sl = q->slots[i];
             if (sl.B > 0 && (rc = launch_solve<T>(q->p, &q->open_prm, sl.B, &sl.dio, q->s_comp))) return rc;
@@ -136,6 +236,7 @@ int queue_acquire(ikb_queue *q, int dtype, const ikb_dls_params *prm, ikb_queue:
     int rc;
     ikb_queue::Slot *sl = &q->slots[q->next % q->depth];
     if (sl->pending && (rc = queue_flush(q))) return rc;
+    if (sl->deferred && (rc = queue_finish_carry(q))) return rc;
     if (sl->busy) {
         IKB_CUDA(cudaEventSynchronize(sl->ev_done));
         sl->busy = false;
@@ -197,7 +298,7 @@ extern "C" {
 int ikb_queue_create(ikb_problem *p, int depth, int merge, ikb_queue **out) {
     if (!p || !out) return fail(IKB_ERR_INVALID_ARG, "null argument");
     if (!p->finalized) return fail(IKB_ERR_NOT_FINALIZED, "call ikb_problem_finalize first");
-    if (depth < 1 || depth > 16) return fail(IKB_ERR_INVALID_ARG, "queue depth must be between 1 and 16");
+    if (depth < 1 || depth > 32) return fail(IKB_ERR_INVALID_ARG, "queue depth must be between 1 and 32");
     if (merge < 1 || merge > kMaxMerge || merge > depth) return fail(IKB_ERR_INVALID_ARG, "merge must be between 1 and min(depth, 8)");
     DeviceGuard g(p->device);
     ikb_queue *q = new ikb_queue;
@@ -209,6 +310,8 @@ int ikb_queue_create(ikb_problem *p, int depth, int merge, ikb_queue **out) {
     for (cudaStream_t *s : {&q->s_in, &q->s_comp, &q->s_out}) IKB_CUDA(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking));
     const char *tr = std::getenv("IKB_QUEUE_TRACE");
     q->trace = tr && tr[0] == '1';
+    const char *ce = std::getenv("IKB_QUEUE_CARRY");
+    q->carry_on = !(ce && ce[0] == '0');
     const unsigned evf = q->trace ? cudaEventDefault : cudaEventDisableTiming;
     IKB_CUDA(cudaEventCreateWithFlags(&q->ev_user, cudaEventDisableTiming));
     IKB_CUDA(cudaEventCreateWithFlags(&q->ev_comp, cudaEventDisableTiming));
@@ -226,6 +329,7 @@ void ikb_queue_free(ikb_queue *q) {
     if (!q) return;
     DeviceGuard g(q->p->device);
     queue_flush(q);
+    queue_finish_carry(q);
     for (cudaStream_t s : {q->s_in, q->s_comp, q->s_out})
         if (s) {
             cudaStreamSynchronize(s);
@@ -240,6 +344,9 @@ void ikb_queue_free(ikb_queue *q) {
         cudaFree(sl.st64.q0); cudaFree(sl.st64.targets); cudaFree(sl.st64.q); cudaFree(sl.st64.resid); cudaFree(sl.st64.compact);
         cudaFree(sl.st32.q0); cudaFree(sl.st32.targets); cudaFree(sl.st32.q); cudaFree(sl.st32.resid); cudaFree(sl.st32.compact);
         cudaFree(sl.success); cudaFree(sl.iters);
+    }
+    for (auto &c : q->cscratch) {
+        cudaFree(c.list); cudaFree(c.iters); cudaFree(c.counters);
     }
     delete q;
 }
@@ -282,7 +389,8 @@ int64_t ikb_queue_submit_host(ikb_queue *q, int dtype, const ikb_dls_params *prm
 int ikb_queue_flush(ikb_queue *q) {
     if (!q) return fail(IKB_ERR_INVALID_ARG, "null queue");
     DeviceGuard g(q->p->device);
-    return queue_flush(q);
+    const int rc = queue_flush(q);
+    return rc ? rc : queue_finish_carry(q);   // an explicit flush leaves nothing behind: carried stragglers get their TAIL
 }
 
 int ikb_queue_wait(ikb_queue *q, int64_t ticket) {
@@ -292,6 +400,7 @@ int ikb_queue_wait(ikb_queue *q, int64_t ticket) {
     DeviceGuard g(q->p->device);
     int rc;
     if (sl.pending && (rc = queue_flush(q))) return rc;
+    if (sl.deferred && (rc = queue_finish_carry(q))) return rc;
     IKB_CUDA(cudaEventSynchronize(sl.ev_done));
     if (q->trace && sl.host && sl.busy) {
         float a = 0, b = 0, c = 0, d = 0, e = 0;
@@ -315,6 +424,7 @@ int ikb_queue_wait_on_stream(ikb_queue *q, int64_t ticket, void *cuda_stream) {
     DeviceGuard g(q->p->device);
     int rc;
     if (sl.pending && (rc = queue_flush(q))) return rc;
+    if (sl.deferred && (rc = queue_finish_carry(q))) return rc;
     IKB_CUDA(cudaStreamWaitEvent((cudaStream_t)cuda_stream, sl.ev_done, 0));
     return IKB_OK;
 }
@@ -324,6 +434,7 @@ int ikb_queue_drain(ikb_queue *q) {
     DeviceGuard g(q->p->device);
     int rc = queue_flush(q);
     if (rc) return rc;
+    if ((rc = queue_finish_carry(q))) return rc;
     for (cudaStream_t s : {q->s_in, q->s_comp, q->s_out}) IKB_CUDA(cudaStreamSynchronize(s));
     for (auto &sl : q->slots) sl.busy = false;
     return IKB_OK;

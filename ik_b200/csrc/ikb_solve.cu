@@ -297,6 +297,64 @@ int launch_solve(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, con
     return rc;
 }
 
+template <typename T>
+int launch_merged_carry(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, const Merged<T> *merged, cudaStream_t s,
+                        const CarryScratch &own, const CarryState<T> *in, CarryState<T> *out) {
+    int cap = 0;
+    if (!p->spec || !merged || !two_phase(p, prm, B, &cap) || own.cap < (size_t)B)
+        return fail(IKB_ERR_INVALID_ARG, "internal: carried launch needs a specialised two-launch solve and scratch for the group");
+    SolveArgs<T> a{};
+    a.nseg = merged->nseg;
+    for (int i = 0; i < kMaxSegments; ++i) {
+        if (i < merged->nseg) a.seg[i] = merged->seg[i];
+        else a.seg[i].begin = LLONG_MAX;
+        a.cseg[i].begin = LLONG_MAX;
+    }
+    a.B = B;
+    a.max_iterations = prm->max_iterations;
+    a.step_length = (T)prm->step_length;
+    a.damping2 = (T)(prm->damping * prm->damping);
+    a.tolerance = (T)prm->tolerance;
+    a.ticket = own.counters;             // [0] bulk tickets, [1] tail tickets, [2] suspended count
+    IKB_CUDA(cudaMemsetAsync(own.counters, 0, 4 * sizeof(unsigned long long), s));
+    a.it_cap = cap;
+    a.resume = 0;
+    a.list = own.list;
+    a.list_count = own.counters + 2;
+    a.iters_ws = own.iters;
+    if (in && in->valid) {
+        a.carry_list = in->tail.list;
+        a.carry_count = in->tail.list_count;
+        a.carry_iters = in->tail.iters_ws;
+        for (int i = 0; i < kMaxSegments; ++i) a.cseg[i] = in->tail.seg[i];
+    }
+    const SpecHostConsts hc{p->hp.model.lower.data(), p->hp.model.upper.data(), p->weight_stacked.data(), p->mask_stacked.data()};
+    if (launch_specialized<T>(*p->spec, hc, a, SPEC_BULK, B, p->sm_count, s) != IKB_OK) return cuda_fail(cudaGetLastError(), "specialised kernel launch");
+    g_launches.fetch_add(1);
+    out->valid = true;
+    out->tail = a;
+    out->tail.resume = 1;
+    out->tail.it_cap = INT_MAX;
+    out->tail.ticket = own.counters + 1;
+    out->tail.carry_list = nullptr;
+    out->tail.carry_count = nullptr;
+    out->tail.carry_iters = nullptr;
+    return IKB_OK;
+}
+template <typename T> int launch_carry_tail(const ikb_problem *p, const CarryState<T> &c, cudaStream_t s) {
+    if (!c.valid) return IKB_OK;
+    const SpecHostConsts hc{p->hp.model.lower.data(), p->hp.model.upper.data(), p->weight_stacked.data(), p->mask_stacked.data()};
+    if (launch_specialized<T>(*p->spec, hc, c.tail, SPEC_TAIL, c.tail.B, p->sm_count, s) != IKB_OK) return cuda_fail(cudaGetLastError(), "specialised kernel launch");
+    g_launches.fetch_add(1);
+    return IKB_OK;
+}
+template int launch_merged_carry<double>(const ikb_problem *, const ikb_dls_params *, int64_t, const Merged<double> *, cudaStream_t, const CarryScratch &,
+                                         const CarryState<double> *, CarryState<double> *);
+template int launch_merged_carry<float>(const ikb_problem *, const ikb_dls_params *, int64_t, const Merged<float> *, cudaStream_t, const CarryScratch &,
+                                        const CarryState<float> *, CarryState<float> *);
+template int launch_carry_tail<double>(const ikb_problem *, const CarryState<double> &, cudaStream_t);
+template int launch_carry_tail<float>(const ikb_problem *, const CarryState<float> &, cudaStream_t);
+
 template int launch_solve<double>(const ikb_problem *, const ikb_dls_params *, int64_t, const ikb_batch_io *, cudaStream_t,
                                   const ChunkPlan *, const Merged<double> *, const double *, const SolveAux<double> *);
 template int launch_solve<float>(const ikb_problem *, const ikb_dls_params *, int64_t, const ikb_batch_io *, cudaStream_t,

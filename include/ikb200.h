@@ -255,7 +255,7 @@ int ikb_pik_solve_ex(ikb_problem *p, const ikb_pik_params *params, const double 
  * may run the thread-per-problem kernels where a lone small batch runs the team-per-problem one, and in FP32 the step
  * at which a straggler changes kernels depends on scheduling.  One thread drives a queue. */
 typedef struct ikb_queue ikb_queue;
-int ikb_queue_create(ikb_problem *p, int depth /* 1..16 batches in flight */, int merge /* 1..min(depth, 8) */,
+int ikb_queue_create(ikb_problem *p, int depth /* 1..32 batches in flight */, int merge /* 1..min(depth, 8) */,
                      ikb_queue **out);
 void ikb_queue_free(ikb_queue *q);
 /* DEVICE buffers (as ikb_dls_solve_batch).  The inputs must be complete in `in_stream` order at the time of the

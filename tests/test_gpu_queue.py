@@ -211,3 +211,68 @@ def test_queue_argument_errors(cassie):
     assert capi.lib.ikb_queue_wait(queue._h, 0) == 1                          # no such ticket yet
     assert capi.lib.ikb_queue_wait(queue._h, -1) == 1
     queue.drain()                                                             # draining an empty queue is fine
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_carried_stragglers_match_per_batch_calls(cassie, dtype, monkeypatch):
+    """Device-buffer groups that take the two-launch path are launched WITHOUT their TAIL: the next group's BULK launch
+    continues their stragglers (ikb_queue.cu, CarryState), and a wait / flush / drain / slot reuse that needs them earlier
+    launches the TAIL.  Every route gives the results of the per-batch call -- bit for bit in FP64 -- and of the queue
+    with IKB_QUEUE_CARRY=0."""
+    torch = _torch()
+    pb, om, opb = cassie
+    pb.finalize(0)
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    sizes = [12000, 9800, 20000, 9600, 15000, 10000, 11000, 13000, 9900, 17000]   # each larger than one resident wave (9 472): the lone call takes BULK + TAIL too
+    data = [make_workload(pb, om, B, seed=900 + i, standing=W.CASSIE_STANDING) for i, B in enumerate(sizes)]
+    dev = [(_dev(torch, q0, tdt), _dev(torch, tg, tdt)) for q0, tg, _ in data]
+    ref = [ik.dls_batch(pb, a, b) for a, b in dev]
+    torch.cuda.synchronize()
+
+    def check(got):
+        for (t, out), r in zip(got, ref):
+            if dtype == "f64":
+                for k in ("q", "success", "iters", "resid"):
+                    assert torch.equal(out[k], r[k]), k
+            else:   # FP32: the step at which a straggler changes kernels depends on scheduling (ikb200.h)
+                same = (out["success"] == r["success"]) & (out["iters"] == r["iters"])
+                assert same.float().mean() > 0.97
+                assert (out["q"] - r["q"]).abs()[:, r["success"].bool() & same].max() < 3e-3
+
+    # five groups of two: each group's stragglers ride in the next group's launch, the last group's get a TAIL at drain
+    queue = ik.SolveQueue(pb, depth=6, merge=2)
+    launches0 = ik.kernel_launch_count()
+    got = [queue.submit(a, b) for a, b in dev]
+    queue.drain()
+    assert ik.kernel_launch_count() - launches0 == 5 + 1      # five BULK launches, ONE TAIL (the scratch is sized by the first group)
+    check(got)
+    # waiting for a ticket of the group that is being carried forces its TAIL; later groups go on carrying
+    queue = ik.SolveQueue(pb, depth=6, merge=2)
+    got = []
+    for i, (a, b) in enumerate(dev):
+        got.append(queue.submit(a, b))
+        if i == 3:
+            queue.wait(got[2][0])
+    for t, _ in reversed(got):
+        queue.wait(t)
+    check(got)
+    # a change of solver parameters cannot be carried across: results of both parameter sets are right
+    demo = ik.dls_parameters(max_iterations=40, step_length=0.5, damping=1e-2)
+    ref_demo = [ik.dls_batch(pb, a, b, demo) for a, b in dev[:4]]
+    queue = ik.SolveQueue(pb, depth=8, merge=2)
+    g1 = [queue.submit(a, b) for a, b in dev[:4]]
+    g2 = [queue.submit(a, b, demo) for a, b in dev[:4]]
+    queue.drain()
+    check(g1)
+    for (t, out), r in zip(g2, ref_demo):
+        if dtype == "f64":
+            for k in ("q", "success", "iters"):
+                assert torch.equal(out[k], r[k]), k
+    # ... and with the feature switched off
+    monkeypatch.setenv("IKB_QUEUE_CARRY", "0")
+    queue = ik.SolveQueue(pb, depth=6, merge=2)
+    launches0 = ik.kernel_launch_count()
+    got = [queue.submit(a, b) for a, b in dev]
+    queue.drain()
+    assert ik.kernel_launch_count() - launches0 == 10
+    check(got)
