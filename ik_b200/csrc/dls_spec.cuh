@@ -31,6 +31,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <type_traits>
 
 #include "dev_problem.hpp"
 #include "model.hpp"
@@ -63,9 +64,29 @@ struct DynSmemOptIn {
     }
 };
 
+// Does the FP64 kernel of this spec keep the Jacobian strip in tensor memory?  (IKB_TMEM_J=0: never)
+#ifndef IKB_TMEM_J
+#define IKB_TMEM_J 1
+#endif
+template <class Spec, typename T> constexpr bool spec_tmem_j() { return IKB_TMEM_J && IKB_TMEM_Q && Spec::ARROW && Spec::TMEMJ && sizeof(T) == 8 && Spec::NQL <= 16; }
+// tensor-memory columns of a warp role: 32 for the parked configuration + two per Jacobian slot of the role
+template <class Spec, typename T> constexpr int spec_tmem_width(int role) { return 32 + (spec_tmem_j<Spec, T>() ? 2 * Spec::j_count(role) : 0); }
+// columns in use in lane quarter `quarter` when the CTA has `nwarps` warps (warp w: quarter w % 4, role w % NWARPS)
+template <class Spec, typename T> constexpr int spec_tmem_quarter(int quarter, int nwarps) {
+    int c = 0;
+    for (int w = quarter; w < nwarps; w += 4) c += spec_tmem_width<Spec, T>(w % Spec::NWARPS);
+    return c;
+}
+template <class Spec, typename T> constexpr int spec_tmem_cols(int nwarps) {
+    int m = 0;
+    for (int qd = 0; qd < 4; ++qd) m = spec_tmem_quarter<Spec, T>(qd, nwarps) > m ? spec_tmem_quarter<Spec, T>(qd, nwarps) : m;
+    return m <= 32 ? 32 : m <= 64 ? 64 : m <= 128 ? 128 : m <= 256 ? 256 : 512;
+}
+
 template <class Spec, typename T> struct SpecLaunch {
     static constexpr int NW = Spec::NWARPS;
-    static constexpr int kStrip = Spec::NSLOT + Spec::NFACT + Spec::TSZ + 1;              // scalars per problem (+ ||e||^2)
+    static constexpr bool kTmemJ = spec_tmem_j<Spec, T>();
+    static constexpr int kStrip = (kTmemJ ? 0 : Spec::NSLOT) + Spec::NFACT + Spec::TSZ + 1;   // scalars per problem (+ ||e||^2)
     static constexpr int kBytesPerProblem = kStrip * (int)sizeof(T) + (int)sizeof(long long);  // + prefetched ticket
     static constexpr int kBySmem = kSmemPerCtaMax / (32 * kBytesPerProblem);               // groups that fit
     // register budget: 168 per thread for double, 128 for float -> at most 384 / 512 threads per (single) CTA
@@ -89,13 +110,14 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
     const int slot = group * 32 + lane;
     T *sm = reinterpret_cast<T *>(smem_raw) + slot;
     using S = Strip<T, SLOTS>;
-    const S sJ{sm};                                         // weighted task Jacobian, non-zeros only
-    const S sL{sm + Spec::NSLOT * SLOTS};                   // LDL^T factor
-    const S sE{sm + (Spec::NSLOT + Spec::EOFF) * SLOTS};    //   ... M of whose slots carry e until the solve starts
-    const S sD{sm + (Spec::NSLOT + M) * SLOTS};             //   ... and whose next NQ slots carry the stepped q after it
-    const S sT{sm + (Spec::NSLOT + Spec::NFACT) * SLOTS};   // target poses
-    T *sRes = sm + (Spec::NSLOT + Spec::NFACT + Spec::TSZ) * SLOTS;  // ||e[0]||^2 of the current evaluation
-    long long *sNext = reinterpret_cast<long long *>(smem_raw + (size_t)(Spec::NSLOT + Spec::NFACT + Spec::TSZ + 1) * SLOTS * sizeof(T)) + slot;
+    constexpr bool kTmemJ = spec_tmem_j<Spec, T>();         // the Jacobian strip lives in tensor memory, not here
+    constexpr int kJS = kTmemJ ? 0 : Spec::NSLOT;
+    const S sL{sm + kJS * SLOTS};                           // LDL^T factor
+    const S sE{sm + (kJS + Spec::EOFF) * SLOTS};            //   ... M of whose slots carry e until the solve starts
+    const S sD{sm + (kJS + M) * SLOTS};                     //   ... and whose next NQ slots carry the stepped q after it
+    const S sT{sm + (kJS + Spec::NFACT) * SLOTS};           // target poses
+    T *sRes = sm + (kJS + Spec::NFACT + Spec::TSZ) * SLOTS;  // ||e[0]||^2 of the current evaluation
+    long long *sNext = reinterpret_cast<long long *>(smem_raw + (size_t)(kJS + Spec::NFACT + Spec::TSZ + 1) * SLOTS * sizeof(T)) + slot;
 
     auto group_sync = [&]() {
         if constexpr (NW > 1)
@@ -108,13 +130,22 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
     // FP64 arrow kernels: q lives in tensor memory (32 columns of this thread's lane) whenever no phase needs it -- in
     // registers only from the top of a trip to the end of evaluate, and from the step to the end of the trip
     constexpr bool kTmemQ = IKB_TMEM_Q && Spec::ARROW && sizeof(T) == 8 && Spec::NQL <= 16;
-    constexpr int kTmemCols = (GROUPS * NW + 3) / 4 * 32 <= 32 ? 32 : (GROUPS * NW + 3) / 4 * 32 <= 64 ? 64 : (GROUPS * NW + 3) / 4 * 32 <= 128 ? 128 : 256;
+    constexpr int kTmemCols = spec_tmem_cols<Spec, T>(GROUPS * NW);
     uint32_t tmem_base = 0, tmem_q = 0;
     if constexpr (kTmemQ) {
-        static_assert((GROUPS * NW + 3) / 4 * 32 <= 256, "too many warps for one 32-column slot each");
+        static_assert(spec_tmem_quarter<Spec, T>(0, GROUPS * NW) <= 512 && spec_tmem_quarter<Spec, T>(1, GROUPS * NW) <= 512 &&
+                      spec_tmem_quarter<Spec, T>(2, GROUPS * NW) <= 512 && spec_tmem_quarter<Spec, T>(3, GROUPS * NW) <= 512,
+                      "the warps of one lane quarter need more than 512 tensor-memory columns");
         tmem_base = tmem_provision<kTmemCols>(reinterpret_cast<uint32_t *>(smem_raw), warp);
-        tmem_q = tmem_base + ((uint32_t)(warp & 3) * 32u << 16) + (uint32_t)(warp >> 2) * 32u;   // lane quarter | column slot
+        uint32_t col = 0;                                   // the columns of the warps before this one in its lane quarter
+        for (int w = warp & 3; w < warp; w += 4) col += (uint32_t)spec_tmem_width<Spec, T>(w % NW);
+        tmem_q = tmem_base + ((uint32_t)(warp & 3) * 32u << 16) + col;   // lane quarter | first column of this warp
     }
+    // weighted task Jacobian, non-zeros only: a shared-memory strip, or the role's own slots in tensor memory
+    using SJ = typename std::conditional<kTmemJ, TStrip<double>, S>::type;
+    SJ sJ;
+    if constexpr (kTmemJ) sJ.base = tmem_q + 32u - 2u * (uint32_t)Spec::j_first(role);
+    else sJ.base = sm;
     long long b;
     int it = 0;
     bool have;
@@ -205,7 +236,12 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
             if (have && refetch) Spec::fetch_common(role, sL, q);   // the coordinates the solver role stepped for everybody
             refetch = false;
         }
-        if (have) {
+        if constexpr (kTmemJ) {
+            // tensor-memory transfers are warp-wide (.sync.aligned): every lane evaluates, also the ones without a problem
+            // (on stale or arbitrary inputs; nobody reads what they produce)
+            Spec::evaluate(role, q, sT, c, sJ, sE);
+            sJ.flush();
+        } else if (have) {
             Spec::evaluate(role, q, sT, c, sJ, sE);         // data.cpp:25-58, this role's tasks
             // The solver role's own tasks are the cheap ones: while the others still evaluate, it factorises the leading
             // block of the normal equations, which involves its rows only (off the critical path, no extra barrier).
@@ -249,7 +285,18 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
             if constexpr (!Spec::CAPSOLO) group_sync();     // s and ||e||^2 visible (y is role-private)
             if constexpr (kTmemQ) tmem_fetch(tmem_q, q);    // back for the step (a non-solver role's copy of the common
                                                             // coordinates is stale here: it neither steps nor stores them)
-            if (have && !(abs_(*sRes) < a.tolerance)) {     // dls.cpp:52,61-71
+            if constexpr (kTmemJ) {
+                // (warp-wide again: every lane steps a copy, the lanes whose problem goes on keep it)
+                T qn[Spec::NQL];
+#pragma unroll
+                for (int k = 0; k < Spec::NQL; ++k) qn[k] = q[k];
+                if constexpr (Spec::MY != M) Spec::step_role(role, sJ, sL, qn, a.step_length, c, y);
+                else Spec::step_role(role, sJ, sL, qn, a.step_length, c);
+                const bool go = have && !(abs_(*sRes) < a.tolerance);
+#pragma unroll
+                for (int k = 0; k < Spec::NQL; ++k) q[k] = go ? qn[k] : q[k];
+                if (go) refetch = true;
+            } else if (have && !(abs_(*sRes) < a.tolerance)) {     // dls.cpp:52,61-71
                 if constexpr (Spec::MY != M) Spec::step_role(role, sJ, sL, q, a.step_length, c, y);   // y in the role's registers
                 else Spec::step_role(role, sJ, sL, q, a.step_length, c);
                 refetch = true;

@@ -17,15 +17,21 @@ namespace ikb {
 namespace {
 using SU = SpecHumanoidLimbs;
 using SA = SpecHumanoidLimbsArrow;
-bool use_arrow() {
+// (A third build -- spec option "tmem_j": the Jacobian strip of every role in tensor memory, which frees enough shared
+// memory for two groups per SM in FP64 -- was measured and dropped: ten warps get 168 registers each, the body spills 1.7 KB
+// per thread and 262 144 problems take 21.1 ms against 13.5 ms.  Generator and kernel support remain: TStrip, TMEMJ.)
+int variant_of() {   // IKB_HUMANOID_SOLVE=uniform|arrow
     const char *e = std::getenv("IKB_HUMANOID_SOLVE");
-    return !(e && std::strcmp(e, "uniform") == 0);
+    return (e && std::strcmp(e, "uniform") == 0) ? 0 : 1;
 }
 template <class S, typename T> int launch_s(const SpecHostConsts &hc, const SolveArgs<T> &a, int variant, long long n, int sms, cudaStream_t s) {
     return variant == SPEC_TAIL ? launch_spec_tail<S, T>(hc, a, n, sms, s) : launch_spec_bulk<S, T>(hc, a, n, sms, s);
 }
 template <typename T> int launch(const SpecHostConsts &hc, const SolveArgs<T> &a, int variant, long long n, int sms, cudaStream_t s) {
-    return use_arrow() ? launch_s<SA, T>(hc, a, variant, n, sms, s) : launch_s<SU, T>(hc, a, variant, n, sms, s);
+    switch (variant_of()) {
+        case 0: return launch_s<SU, T>(hc, a, variant, n, sms, s);
+        default: return launch_s<SA, T>(hc, a, variant, n, sms, s);
+    }
 }
 int l64(const SpecHostConsts &hc, const SolveArgs<double> &a, int v, long long n, int sms, cudaStream_t s) { return launch<double>(hc, a, v, n, sms, s); }
 int l32(const SpecHostConsts &hc, const SolveArgs<float> &a, int v, long long n, int sms, cudaStream_t s) { return launch<float>(hc, a, v, n, sms, s); }

@@ -75,6 +75,29 @@ template <int N> __device__ __forceinline__ void tmem_fetch(uint32_t addr, doubl
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]);
 }
+// A thread-private strip in tensor memory with the interface of Strip (spec_common.hpp): element k of the calling thread
+// lives in columns [base + k * kStride, + kStride) of its lane.  The generated bodies use it for the rows of the task
+// Jacobian a warp role evaluates, factorises against and steps with -- data no other warp ever reads -- which frees
+// that much shared memory for a second group of problems per SM (humanoid: 303 of 706 doubles per problem).
+// set() is asynchronous (flush() before the first get of what was written); get() waits for its own load.
+template <typename T> struct TStrip {
+    static_assert(sizeof(T) == 8, "tensor-memory strips hold doubles (two 32-bit columns per element)");
+    static constexpr int kStride = 2;
+    uint32_t base;
+    __device__ __forceinline__ void set(int k, T v) const {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(base + (uint32_t)(k * 2)), "r"((uint32_t)__double2loint(v)),
+                     "r"((uint32_t)__double2hiint(v))
+                     : "memory");
+    }
+    __device__ __forceinline__ T get(int k) const {
+        uint32_t lo, hi;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(base + (uint32_t)(k * 2)) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        return __hiloint2double((int)hi, (int)lo);
+    }
+    __device__ __forceinline__ void flush() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+};
+
 // (single precision has registers to spare: never parked)
 template <int N> __device__ __forceinline__ void tmem_park(uint32_t, const float (&)[N]) {}
 template <int N> __device__ __forceinline__ void tmem_fetch(uint32_t, float (&)[N]) {}

@@ -1198,7 +1198,7 @@ class Generator:
         facb = {}    # role -> base of its factor (m (m + 1) / 2 slots) in sL
         for k in range(R):
             own = sorted(self.slots[(r, c)] for (r, c) in self.slots if row_role[r] == k)
-            if not privs[k] and len(own) >= per and self.spec.get("arrow_pub_in_j", True):
+            if not privs[k] and len(own) >= per and self.spec.get("arrow_pub_in_j", True) and not self.spec.get("tmem_j"):
                 pub[k] = ("J", own[:per])
             else:
                 pub[k] = ("L", off)
@@ -1651,6 +1651,18 @@ class Generator:
         out.append("    static constexpr bool DSTEP = %s;" % ("true" if (uniform or arrow) else "false"))
         out.append("    // ARROW: psolve() is the bordered-block-diagonal step (gen_solve_arrow); the serial solve() is not laid out for its strip")
         out.append("    static constexpr bool ARROW = %s;" % ("true" if arrow else "false"))
+        # Jacobian slots per role (every slot belongs to the role that evaluates its row; a role's slots are consecutive)
+        row_role_ = {self.tasks[t]["row"] + i: k for k, g in enumerate(groups) for t in g for i in range(self.tasks[t]["dim"])}
+        jslots = [sorted(sl for (r, c_), sl in self.slots.items() if row_role_[r] == k) for k in range(len(groups))]
+        contiguous = all(js == list(range(js[0], js[0] + len(js))) for js in jslots if js)
+        tmemj = bool(arrow and self.spec.get("tmem_j") and contiguous)
+        out.append("    // TMEMJ: every role reads and writes only its own rows of J, and this spec asks the FP64 kernel to keep them in")
+        out.append("    // tensor memory (tmem_scratch.cuh, TStrip) instead of shared memory; j_first / j_count: a role's slots")
+        out.append("    static constexpr bool TMEMJ = %s;" % ("true" if tmemj else "false"))
+        out.append("    static constexpr int j_first(int role) { return %s; }" %
+                   " : ".join(["role == %d ? %d" % (k, js[0] if js else 0) for k, js in enumerate(jslots)] + ["0"]))
+        out.append("    static constexpr int j_count(int role) { return %s; }" %
+                   " : ".join(["role == %d ? %d" % (k, len(js)) for k, js in enumerate(jslots)] + ["0"]))
         out.append("    // CAPSOLO: psolve() ends behind a barrier of its own (the shared-column system is solved by the SOLVER role alone)")
         out.append("    static constexpr bool CAPSOLO = %s;" % ("true" if arrow and self.spec.get("arrow_cap_solo") else "false"))
         out.append("    // PRE: leading rows whose P x P factor block the SOLVER role computes in presolve(), before the first barrier;")
@@ -1956,6 +1968,27 @@ class Generator:
                    ", ".join(repr(float(x)) for x in fpl))
         out.append("};")
         out.append("}  // namespace ikb")
+        # The Jacobian strip has a type of its own (SJ): the kernel may keep it in tensor memory (TStrip, tmem_scratch.cuh)
+        # while the other strips are shared memory.  Every function that takes sJ gets the extra template parameter.
+        import re
+        for i, ln in enumerate(out):
+            if "const S &sJ" in ln and "static IKB_HD" in ln:
+                out[i] = ln.replace("const S &sJ", "const SJ &sJ")
+                j = i - 1
+                while not out[j].lstrip().startswith("template <"):
+                    j -= 1
+                if "typename SJ" not in out[j]:
+                    if "const S &" not in out[i] and " S " not in out[i]:   # sJ was the only strip: S is no longer deducible
+                        out[j] = out[j].replace("typename S>", "typename SJ>").replace("typename S,", "typename SJ,", 1)
+                    else:
+                        out[j] = (out[j].replace("typename S>", "typename S, typename SJ>") if "typename S>" in out[j]
+                                  else out[j].replace("typename S,", "typename S, typename SJ,", 1))
+            ln = out[i]
+            ln = re.sub(r"const S sJm\{sJ\.base \+ side \* \((\d+) \* S::kStride\)\}", r"const SJ sJm{sJ.base + side * (\1 * SJ::kStride)}", ln)
+            ln = re.sub(r"const S sJr\{sJ\.base \+ side \* \((-?\d+) \* S::kStride\)\}, ", r"const SJ sJr{sJ.base + side * (\1 * SJ::kStride)}; const S ", ln)
+            ln = ln.replace("const S &sJr = sJ, &sEr = sE, &sLr = sL;", "const SJ &sJr = sJ; const S &sEr = sE, &sLr = sL;")
+            ln = re.sub(r"const S sC(\d+)\{sJ\.base \+ k \* (\d+) \* S::kStride\}", r"const SJ sC\1{sJ.base + k * \2 * SJ::kStride}", ln)
+            out[i] = ln
         return "\n".join(out) + "\n"
 
 
