@@ -9,10 +9,11 @@ seeded random reachable targets PER GPU (weak scaling: rank r solves problem ind
 
 A "step" = one batched ik::dls over one batch of B problems.
   value     K timed steps through the pipelined queue (ikb_queue_*, include/ikb200.h): `--merge` consecutive batches, each
-            with its own buffers, share ONE BULK + TAIL kernel pair, so the stragglers' serial chain (a problem that never
-            converges runs all 100 steps, dls.cpp:14) is paid once per group.  Inputs resident in HBM, CUDA events, max
-            over ranks.  `details.isolated_ms_per_batch` = the same steps through the plain per-batch call, one kernel
-            pair per batch.
+            with its own buffers, share ONE BULK launch, and the stragglers a launch leaves suspended when its ticket
+            queue runs dry (a problem that never converges runs all 100 steps, dls.cpp:14) are continued by the NEXT
+            group's launch beside its fresh problems; the last group's stragglers get one TAIL launch, inside the timed
+            region.  Inputs resident in HBM, CUDA events, max over ranks.  `details.isolated_ms_per_batch` = the same
+            steps through the plain per-batch call, one BULK + TAIL kernel pair per batch.
   e2e       the same metric through the HOST entry point (ikb_queue_submit_host / ikb_queue_wait): every step's inputs are
             copied from pinned host memory and its results are copied back and read inside the timed region.  The wire
             format is what a caller of the reference supplies and receives (cassie.cpp:95-113): per problem the pelvis pose
@@ -43,9 +44,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum per FP64 step, from the committed ncu --set full capture
-# profiles/r1_queue_full.txt: the BULK + TAIL launches of a group of 4 steps move 177.9 + 48.2 MB -> 56.5 MB per step
-NCU_TRAFFIC_BYTES_F64 = 56.5e6
+# dram__bytes_read.sum + dram__bytes_write.sum per FP64 step, from the committed ncu --set full capture of this command
+# (profiles/r2_final_merged_full.txt): one merged BULK launch of 8 steps moves 316.7 + 102.4 MB -> 52.4 MB per step
+NCU_TRAFFIC_BYTES_F64 = 52.4e6
 METRIC = "converged IK solves/sec (Cassie, batch 65,536)"
 UNIT = "solves/s"
 NOMINAL_TFLOPS = {"f64": 37.2, "f32": 74.4}
@@ -638,7 +639,8 @@ def main():
             "config": config,
             "details": {"kernel": pb.kernel_name(args.dtype),
                         "l2": "inputs/outputs rotate over %d distinct batches (%.0f MB > 126 MB L2)" % (nsets, nsets * per_set / 1e6),
-                        "pipeline": "ikb_queue, depth %d, %d consecutive batches per BULK+TAIL kernel pair" % (depth, args.merge),
+                        "pipeline": "ikb_queue, depth %d, %d consecutive batches per BULK launch; stragglers carried into the next launch, "
+                                    "one TAIL launch at the end" % (depth, args.merge),
                         "isolated_ms_per_batch": isolated_ms,
                         "isolated_value": conv / args.steps / (isolated_ms * 1e-3) * world,
                         "isolated_roofline_frac": F_ITER * iso_evals / (isolated_ms * 1e-3) / 1e12 / peak,
@@ -662,8 +664,9 @@ def main():
                          "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak if peak else None,
                          "traffic": NCU_TRAFFIC_BYTES_F64 if (args.dtype == "f64" and B == 65536) else None,
-                         "traffic_source": "ncu --set full, profiles/r1_queue_full.txt: DRAM bytes of the BULK + TAIL launches of a group of 4 steps (177.9 + 48.2 MB) / 4; algorithmic 43.8 MB",
-                         "kernels": "BULK %s + TAIL per group of %d steps; kernel_ms = device time of the timed region / steps"
+                         "traffic_source": "ncu --set full of this command, profiles/r2_final_merged_full.txt: DRAM bytes of one merged BULK launch (8 steps + the stragglers carried over from the previous launch): (316.7 + 102.4 MB) / 8; algorithmic 43.8 MB",
+                         "kernels": "one BULK launch of %s per group of %d steps, which also continues the stragglers the previous group left "
+                                    "suspended; ONE TAIL launch when the queue runs empty; kernel_ms = device time of the timed region / steps"
                                     % (pb.kernel_name(args.dtype), args.merge),
                          "peak_source": "measured in this run (ikb_measure_fma_peak); nominal %.1f"
                                         % NOMINAL_TFLOPS[args.dtype],
