@@ -346,10 +346,12 @@ IKB_HD void coop_gram_solve(const Ctx &cx, const T (*Jm)[LDM], const uint64_t *c
         rhs[rr] = r < nrhs ? rhs_in[r] : T(0);
         yinv[rr] = T(0);
     }
+    // rows >= nrhs are structurally zero: their Gram blocks and their pivots (identity rows, multipliers exactly 0) are skipped
+    const uint64_t live = nrhs >= 60 ? ~0ULL : (1ULL << (6 * ((nrhs + 5) / 6))) - 1ULL;
     // ---- Gram (dls.cpp:39): columns in ascending order, only row blocks the column can touch ----
     for (int c = 0; c < nv; ++c) {
         const T *col = Jm[c];
-        const uint64_t mask = col_rows ? col_rows[c] : ~0ULL;
+        const uint64_t mask = (col_rows ? col_rows[c] : ~0ULL) & live;
         T a[RPL];
 #pragma unroll
         for (int rr = 0; rr < RPL; ++rr) {
@@ -380,6 +382,7 @@ IKB_HD void coop_gram_solve(const Ctx &cx, const T (*Jm)[LDM], const uint64_t *c
     // ---- Gauss-Jordan by rows ----
 #pragma unroll
     for (int k = 0; k < M; ++k) {
+        if (k >= nrhs) break;   // (uniform: nrhs is a property of the problem)
         const int ko = k % TEAM, kr = k / TEAM;
         T d, ek;
         T *pv = piv[k & 1];
@@ -439,7 +442,7 @@ IKB_HD void coop_gram_solve(const Ctx &cx, const T (*Jm)[LDM], const uint64_t *c
 // Orthonormal basis (rows of Wout, returned count = rank) of the row space of the numerically rank-r part of the mi x nv
 // matrix A (column-major with stride LD, destroyed): what A.completeOrthogonalDecomposition().pseudoInverse() * A projects
 // onto (pik.cpp:59-61, dls.cpp:44-49).  Householder QR with column pivoting, lane <-> column; rank from Eigen's threshold
-// eps * min(m, n) * max pivot; the first r rows of R (columns back in place) orthonormalised by modified Gram-Schmidt, twice.
+// eps * min(m, n) * max pivot; the first r rows of R (columns back in place) orthonormalised by Gram-Schmidt with re-orthogonalisation.
 template <typename T, class Cfg, class Ctx>
 IKB_HD int coop_rowspace_basis(const Ctx &cx, T (*A)[Cfg::LDX], int mi, int nv, T (*Wout)[Cfg::NV], T *diag /* >= mi */) {
     constexpr int TEAM = Cfg::TEAM;
@@ -508,21 +511,38 @@ IKB_HD int coop_rowspace_basis(const Ctx &cx, T (*A)[Cfg::LDX], int mi, int nv, 
     for (int c = lane; c < nv; c += TEAM)
         for (int r = 0; r < rank; ++r) Wout[r][perm[c]] = c >= r ? A[perm[c]][r] : T(0);
     cx.sync();
-    // modified Gram-Schmidt, twice; lane <-> column, dot products by butterfly
-    for (int pass = 0; pass < 2; ++pass)
-        for (int r = 0; r < rank; ++r) {
-            for (int p2 = 0; p2 < r; ++p2) {
-                T s = T(0);
-                for (int c = lane; c < nv; c += TEAM) s += Wout[r][c] * Wout[p2][c];
-                for (int off = TEAM / 2; off >= 1; off >>= 1) s += cx.shfl(s, lane ^ off);
-                for (int c = lane; c < nv; c += TEAM) Wout[r][c] -= s * Wout[p2][c];
+    // Classical Gram-Schmidt with re-orthogonalisation ("twice is enough"), row by row against the finished rows.  The r
+    // dot products of a row are taken by r lanes at once (lane <-> finished row, serial over the columns, no reduction
+    // across lanes) and the update by lane <-> column; one butterfly per row (its norm) instead of one per PAIR of rows and
+    // pass -- the modified Gram-Schmidt that stood here spent a third of an ik::pik iteration in shuffles
+    // (profiles/r2_s3_pik_lines.txt).  `diag` is free once the rank is known and carries the coefficients.
+    for (int r = 0; r < rank; ++r) {
+        for (int pass = 0; pass < 2 && r > 0; ++pass) {
+            for (int p2 = lane; p2 < r; p2 += TEAM) {
+                T s0 = T(0), s1 = T(0);
+                int c = 0;
+                for (; c + 1 < nv; c += 2) {
+                    s0 += Wout[r][c] * Wout[p2][c];
+                    s1 += Wout[r][c + 1] * Wout[p2][c + 1];
+                }
+                if (c < nv) s0 += Wout[r][c] * Wout[p2][c];
+                diag[p2] = s0 + s1;
             }
-            T nr = T(0);
-            for (int c = lane; c < nv; c += TEAM) nr += Wout[r][c] * Wout[r][c];
-            for (int off = TEAM / 2; off >= 1; off >>= 1) nr += cx.shfl(nr, lane ^ off);
-            const T inr = T(1) / sqrt_(nr);
-            for (int c = lane; c < nv; c += TEAM) Wout[r][c] *= inr;
+            cx.sync();
+            for (int c = lane; c < nv; c += TEAM) {
+                T w = Wout[r][c];
+                for (int p2 = 0; p2 < r; ++p2) w -= diag[p2] * Wout[p2][c];
+                Wout[r][c] = w;
+            }
+            cx.sync();
         }
+        T nr = T(0);
+        for (int c = lane; c < nv; c += TEAM) nr += Wout[r][c] * Wout[r][c];
+        for (int off = TEAM / 2; off >= 1; off >>= 1) nr += cx.shfl(nr, lane ^ off);
+        const T inr = T(1) / sqrt_(nr);
+        for (int c = lane; c < nv; c += TEAM) Wout[r][c] *= inr;
+        cx.sync();
+    }
     cx.sync();
     return rank;
 }

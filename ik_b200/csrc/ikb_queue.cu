@@ -46,6 +46,7 @@ struct ikb_queue {
     // launch continues its stragglers (capi_internal.hpp, CarryState), and whoever needs the group's results before that
     // (wait, flush, drain, slot reuse, a group that cannot carry) launches the TAIL (queue_finish_carry).
     bool carry_on = true;           // IKB_QUEUE_CARRY=0 disables it (A/B runs)
+    bool carry_host = false;        // IKB_QUEUE_CARRY_HOST=1: host batches carry too (A/B runs; see queue_flush_t)
     bool carry_valid = false;
     int carry_dtype = -1;
     ikb_dls_params carry_prm{};
@@ -160,7 +161,7 @@ template <typename T> int queue_flush_t(ikb_queue *q) {
         // 137 M solves / s end to end -- than the TAIL launch it saves)
         bool any_host_ = false;
         for (int i : q->open) any_host_ |= q->slots[i].host;
-        const bool can_carry = q->carry_on && !any_host_ && !q->trace && two_phase(q->p, &q->open_prm, total);
+        const bool can_carry = q->carry_on && (!any_host_ || q->carry_host) && !q->trace && two_phase(q->p, &q->open_prm, total);
         // a carried group that this launch cannot continue gets its TAIL now
         if (q->carry_valid && !(can_carry && q->carry_dtype == q->open_dtype && same_params(q->carry_prm, q->open_prm)) && (rc = queue_finish_carry(q)))
             return rc;
@@ -312,6 +313,8 @@ int ikb_queue_create(ikb_problem *p, int depth, int merge, ikb_queue **out) {
     q->trace = tr && tr[0] == '1';
     const char *ce = std::getenv("IKB_QUEUE_CARRY");
     q->carry_on = !(ce && ce[0] == '0');
+    const char *ch = std::getenv("IKB_QUEUE_CARRY_HOST");
+    q->carry_host = ch && ch[0] == '1';
     const unsigned evf = q->trace ? cudaEventDefault : cudaEventDisableTiming;
     IKB_CUDA(cudaEventCreateWithFlags(&q->ev_user, cudaEventDisableTiming));
     IKB_CUDA(cudaEventCreateWithFlags(&q->ev_comp, cudaEventDisableTiming));

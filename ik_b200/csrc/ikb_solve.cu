@@ -86,6 +86,8 @@ int check_solve_args(const ikb_problem *p, int dtype, const ikb_dls_params *prm,
     return IKB_OK;
 }
 
+constexpr int kCarryCapDefault = 1;   // step cap of a BULK launch whose stragglers are carried into the next one (measured: tools/carry_sweep.sh, profiles/r2_s3_carry_sweep.txt)
+
 // Is this solve going to take the two-launch (BULK + TAIL) path?  (the only one that can be pipelined by slices)
 bool two_phase(const ikb_problem *p, const ikb_dls_params *prm, int64_t B, int *cap_out) {
     const char *cap_env = std::getenv("IKB_BULK_CAP");
@@ -303,6 +305,15 @@ int launch_merged_carry(const ikb_problem *p, const ikb_dls_params *prm, int64_t
     int cap = 0;
     if (!p->spec || !merged || !two_phase(p, prm, B, &cap) || own.cap < (size_t)B)
         return fail(IKB_ERR_INVALID_ARG, "internal: carried launch needs a specialised two-launch solve and scratch for the group");
+    // A carried launch hands its stragglers to the NEXT launch, where they run among fresh problems at the throughput
+    // configuration's rate: suspending early costs nothing, and it cuts the end of this launch, where ever fewer slots are
+    // busy, to a few trips.  (The TAIL launch of the two-launch schedule is latency-bound instead: there a late
+    // hand-over, IKB_BULK_CAP = 16, keeps the list short.)  IKB_CARRY_CAP overrides the measured default.
+    {
+        const char *e = std::getenv("IKB_CARRY_CAP");
+        const int ccap = e ? std::atoi(e) : kCarryCapDefault;
+        if (ccap >= 1 && ccap < cap) cap = ccap;
+    }
     SolveArgs<T> a{};
     a.nseg = merged->nseg;
     for (int i = 0; i < kMaxSegments; ++i) {

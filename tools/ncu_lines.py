@@ -17,7 +17,11 @@ for r in rows:
         line = int(r[0])
     except ValueError:
         continue
-    g = lambda k: float(r[hdr[k]] or 0) if k in hdr and r[hdr[k]] not in ("", "-") else 0.0
+    def g(k):
+        try:
+            return float(r[hdr[k]] or 0) if k in hdr and r[hdr[k]] not in ("", "-") else 0.0
+        except ValueError:   # (a column that lists access sizes, e.g. "32(18),64(72)")
+            return 0.0
     d = files.setdefault(cur, {}).setdefault(line, {"src": r[1].strip(), "samples": 0.0, "inst": 0.0, "thr": 0.0, "wf": 0.0, "wfx": 0.0})
     d["samples"] += g("# Samples"); d["inst"] += g("Instructions Executed"); d["thr"] += g("Thread Instructions Executed")
     d["wf"] += g("L1 Wavefronts Shared"); d["wfx"] += g("L1 Wavefronts Shared Excessive")
