@@ -447,6 +447,36 @@ def main():
                         "converged_fraction": cv / nB, "mean_iterations": mean_it, "f_iter": fi,
                         "roofline": {"bound": "%s_fma_pipe" % ("fp64" if dt_name == "f64" else "fp32"), "achieved": tf,
                                      "peak": peaks[dt_name], "unit": "TFLOP/s", "frac": tf / peaks[dt_name]}, "note": note}
+        return cv, ev_
+
+    def queued_entry(name, pbx, setsx, dt_name, fi, cv, ev_, merge, nst):
+        """The same batches through the pipelined queue (`merge` per BULK launch, stragglers carried): adds queued_* to
+        extras[name].  One set per batch in flight -- a carried straggler lives in its batch's output buffers."""
+        depth = 2 * merge
+        assert len(setsx) >= depth
+        qx = ik.SolveQueue(pbx, depth, merge, local_rank)
+        for w in range(depth):
+            sx = setsx[w % len(setsx)]
+            qx.submit(sx[0], sx[1], prm, sx[2])
+        qx.drain()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lastt = None
+        for k in range(nst):
+            sx = setsx[k % len(setsx)]
+            lastt, _ = qx.submit(sx[0], sx[1], prm, sx[2])
+        qx.flush()
+        for t in range(max(0, lastt - depth + 1), lastt + 1):
+            qx.wait_on_stream(t)
+        e1.record()
+        torch.cuda.synchronize()
+        qx.drain()
+        qms = e0.elapsed_time(e1) / nst
+        tf = fi * ev_ / (qms * 1e-3) / 1e12
+        extras[name].update({"queued_ms_per_batch": qms, "queued_value": cv / (qms * 1e-3), "queued_roofline_frac": tf / peaks[dt_name],
+                             "queued_note": "%d timed batches through ikb_queue, %d per BULK launch, stragglers carried into the next launch, "
+                                            "final TAIL inside the timed region" % (nst, merge)})
 
     if not args.no_extras and rank == 0:
         lone = "one lone batch per launch (per-batch call, L2 flushed between launches)"
@@ -459,8 +489,11 @@ def main():
         entry("cassie_4096_f64", pb, build_sets(pb, 4096, 8, "standing", torch.float64), "f64", 8, F_ITER, lone + "; BASELINE config 2 (latency configuration: team-per-problem kernel)")
         hpb = W.humanoid_problem()
         hpb.finalize(local_rank)
-        entry("humanoid_262144_f64", hpb, build_sets(hpb, 262144, 2, "near", torch.float64), "f64", 3, f_iter(hpb.model(), hpb),
-              lone + "; BASELINE config 4, warm-started (W.near_start)")
+        hsets = build_sets(hpb, 262144, 4, "near", torch.float64)
+        hcv, hev = entry("humanoid_262144_f64", hpb, hsets, "f64", 4, f_iter(hpb.model(), hpb),
+                         lone + "; BASELINE config 4, warm-started (W.near_start)")
+        queued_entry("humanoid_262144_f64", hpb, hsets, "f64", f_iter(hpb.model(), hpb), hcv, hev, 2, 8)
+        del hsets
         mpb = W.manipulator_problem()
         mpb.finalize(local_rank)
         msets = build_sets(mpb, 1048576, 2, "near", torch.float64)
@@ -510,7 +543,8 @@ def main():
     # slice, the job time is the max over ranks
     def strong_entry(name, pbx, Bglob, start):
         nloc = Bglob // world
-        setsx = build_sets(pbx, nloc, 3 if nloc * 700 < 120e6 else 2, start, torch.float64, b0=rank * nloc)
+        setsx = build_sets(pbx, nloc, 8, start, torch.float64, b0=rank * nloc)   # one per batch in flight (depth 8): a carried
+        #                                                                         straggler lives in its batch's output buffers
         barrier()
         ms, cv, _, _ = time_lone(pbx, setsx, prm, 5)
         qx = ik.SolveQueue(pbx, 8, 4, local_rank)

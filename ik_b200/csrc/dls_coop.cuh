@@ -331,7 +331,7 @@ template <typename T> struct alignas(2 * sizeof(T)) Pair { T x, y; };   // one 1
 // Gram rows + Gauss-Jordan solve of (Jm Jm^T + lambda2 I) y = rhs for rows [0, M) of the column-major matrix Jm (rows
 // beyond the problem's are structurally zero: they factor to lambda2 and give y = 0).  Lane owns rows lane + rr * TEAM.
 // On return y_out[rr] holds the solution entries of the lane's rows.
-template <typename T, class Cfg, bool SHFL, int LDM, class Ctx>
+template <typename T, class Cfg, bool SHFL, int LDM, bool SKIP, class Ctx>
 IKB_HD void coop_gram_solve(const Ctx &cx, const T (*Jm)[LDM], const uint64_t *col_rows, int nv, const T *rhs_in, int nrhs, T lambda2,
                             T (*piv)[Cfg::M + 2], T *y_out) {
     constexpr int TEAM = Cfg::TEAM, M = Cfg::M, RPL = Cfg::RPL;
@@ -346,8 +346,10 @@ IKB_HD void coop_gram_solve(const Ctx &cx, const T (*Jm)[LDM], const uint64_t *c
         rhs[rr] = r < nrhs ? rhs_in[r] : T(0);
         yinv[rr] = T(0);
     }
-    // rows >= nrhs are structurally zero: their Gram blocks and their pivots (identity rows, multipliers exactly 0) are skipped
-    const uint64_t live = nrhs >= 60 ? ~0ULL : (1ULL << (6 * ((nrhs + 5) / 6))) - 1ULL;
+    // rows >= nrhs are structurally zero.  SKIP (the levels of ik::pik, 10 + 16 rows in a 30-row size class): their Gram
+    // blocks and their pivots (identity rows, multipliers exactly 0) are skipped.  Not for ik::dls, whose problems fill their
+    // size class: the per-pivot test costs the straight-line pivot loop its schedule (measured: Cassie 3.06 -> 3.94 ms).
+    const uint64_t live = (!SKIP || nrhs >= 60) ? ~0ULL : (1ULL << (6 * ((nrhs + 5) / 6))) - 1ULL;
     // ---- Gram (dls.cpp:39): columns in ascending order, only row blocks the column can touch ----
     for (int c = 0; c < nv; ++c) {
         const T *col = Jm[c];
@@ -382,7 +384,7 @@ IKB_HD void coop_gram_solve(const Ctx &cx, const T (*Jm)[LDM], const uint64_t *c
     // ---- Gauss-Jordan by rows ----
 #pragma unroll
     for (int k = 0; k < M; ++k) {
-        if (k >= nrhs) break;   // (uniform: nrhs is a property of the problem)
+        if (SKIP && k >= nrhs) break;   // (uniform: nrhs is a property of the problem)
         const int ko = k % TEAM, kr = k / TEAM;
         T d, ek;
         T *pv = piv[k & 1];
@@ -628,7 +630,7 @@ IKB_HD T coop_iteration(const Ctx &cx, const DevProblem<T> &P, CoopScratch<T, Cf
 
     if constexpr (!PIK) {
         T y[RPL];
-        coop_gram_solve<T, Cfg, SHFL, Cfg::LD>(cx, S.Jt, P.col_rows, nv, S.e, rows, damping2, S.piv, y);
+        coop_gram_solve<T, Cfg, SHFL, Cfg::LD, false>(cx, S.Jt, P.col_rows, nv, S.e, rows, damping2, S.piv, y);
 #pragma unroll
         for (int rr = 0; rr < RPL; ++rr) {
             const int r = lane + rr * TEAM;
@@ -682,7 +684,7 @@ IKB_HD T coop_iteration(const Ctx &cx, const DevProblem<T> &P, CoopScratch<T, Cf
             }
             cx.sync();
             T z[RPL];
-            coop_gram_solve<T, Cfg, SHFL, Cfg::LDX>(cx, S.Jb, (const uint64_t *)nullptr, nv, S.y, mi, pik_lambda2[lvl], S.piv, z);
+            coop_gram_solve<T, Cfg, SHFL, Cfg::LDX, true>(cx, S.Jb, (const uint64_t *)nullptr, nv, S.y, mi, pik_lambda2[lvl], S.piv, z);
             cx.sync();   // everybody has read the right-hand side from S.y
 #pragma unroll
             for (int rr = 0; rr < RPL; ++rr) {

@@ -64,6 +64,11 @@ struct DynSmemOptIn {
     }
 };
 
+// 1: arrow kernels stage a converged slot's next problem one trip ahead (kPrefetch below); 0 for A/B builds
+#ifndef IKB_PREFETCH
+#define IKB_PREFETCH 1
+#endif
+
 // Does the FP64 kernel of this spec keep the Jacobian strip in tensor memory?  (IKB_TMEM_J=0: never)
 #ifndef IKB_TMEM_J
 #define IKB_TMEM_J 1
@@ -118,6 +123,19 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
     const S sT{sm + (kJS + Spec::NFACT) * SLOTS};           // target poses
     T *sRes = sm + (kJS + Spec::NFACT + Spec::TSZ) * SLOTS;  // ||e[0]||^2 of the current evaluation
     long long *sNext = reinterpret_cast<long long *>(smem_raw + (size_t)(kJS + Spec::NFACT + Spec::TSZ + 1) * SLOTS * sizeof(T)) + slot;
+
+    // One-trip-ahead refill (arrow specs).  The SOLVER role learns in the middle of a trip -- behind the barrier inside
+    // psolve() -- that a slot's problem has converged, and pulls the slot's next ticket right there.  For a converged
+    // problem the slot's target strip and the Jacobian rows of the other roles are dead from that point on (no step is
+    // taken), so the same thread starts the copy of the NEXT problem into them at once (cp.async: the new targets into
+    // sT, the new configuration into Spec::QSTAGE .. + NQ of the Jacobian strip) and waits for it before the group's next
+    // barrier -- on the role that idles most of the trip.  At the end of the trip every role picks its coordinates out
+    // of the staged configuration with shared-memory loads; the global round trip that used to end every trip of every
+    // role (3-4 of a group's 32 slots refill per trip) is gone from the critical roles' path.  Slots that finish
+    // without converging, carried stragglers and the TAIL launch take the direct path (load_problem).
+    constexpr bool kPrefetch = Spec::ARROW && NW > 1 && !kTmemJ && !Spec::CAPSOLO && Spec::QSTAGE >= 0 && IKB_PREFETCH;
+    const S sQ{sm + (kPrefetch ? Spec::QSTAGE : 0) * SLOTS};
+    constexpr long long kStagedBit = 1LL << 62;             // in *sNext: the ticket's problem is already staged
 
     auto group_sync = [&]() {
         if constexpr (NW > 1)
@@ -269,7 +287,17 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
             if (it + 1 >= a.it_cap && !(res < a.tolerance) && it + 1 < a.max_iterations && !carried)
                 susp = *(volatile unsigned long long *)a.ticket >= (unsigned long long)(a.B + ncarry);
             if (res < a.tolerance || it + 1 >= a.max_iterations || susp) {
-                const long long nb = (long long)atomicAdd(a.ticket, 1ULL);
+                long long nb = (long long)atomicAdd(a.ticket, 1ULL);
+                if constexpr (kPrefetch) {
+                    if (res < a.tolerance && !a.resume && nb >= ncarry && nb - ncarry < a.B) {   // converged here, a fresh problem next
+                        const ProblemIO<T> io = problem_io<SEG>(a, nb - ncarry);
+#pragma unroll
+                        for (int r = 0; r < NW; ++r) Spec::load_targets(r, io.targets, io.tg_es, sT);
+#pragma unroll
+                        for (int k = 0; k < NQ; ++k) sQ.copy_in(k, io.q0 + k * io.q0_es);
+                        nb |= kStagedBit;
+                    }
+                }
                 *sNext = nb;
             }
             sres_mine = susp ? -res : res;
@@ -282,6 +310,8 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
             // (solver role, all of e visible), the small shared-column system in every role, y for the role's own rows.
             T y[Spec::MY];
             Spec::psolve(role, sJ, sL, sE, a.damping2, y, group_sync, stop_test);
+            if constexpr (kPrefetch)
+                if (role == Spec::SOLVER) strip_copies_wait();   // the staged problems have landed before the others look
             if constexpr (!Spec::CAPSOLO) group_sync();     // s and ||e||^2 visible (y is role-private)
             if constexpr (kTmemQ) tmem_fetch(tmem_q, q);    // back for the step (a non-solver role's copy of the common
                                                             // coordinates is stale here: it neither steps nor stores them)
@@ -364,7 +394,20 @@ __global__ void __launch_bounds__(GROUPS *Spec::NWARPS * 32, MINB)
                     }
                 }
                 b = *sNext;
-                load_problem();
+                if constexpr (kPrefetch) {
+                    if (b & kStagedBit) {                    // staged by the SOLVER role during this trip
+                        b = (b & ~kStagedBit) - ncarry;
+                        it = 0;
+                        refetch = false;
+                        carried = false;
+                        have = true;
+                        Spec::load_q(role, sQ.base, (long long)SLOTS, q);
+                    } else {
+                        load_problem();
+                    }
+                } else {
+                    load_problem();
+                }
             }
         }
         if constexpr (kTmemQ) tmem_park(tmem_q, q);         // stepped, refilled or unchanged: out of the registers again
@@ -508,10 +551,12 @@ template <class Spec, typename T> int launch_spec_tail(const SpecHostConsts &hc,
     constexpr int kPerSm = (2 * (L::smem_bytes(1) + 1024) <= 228 * 1024 && 2 * Spec::NWARPS * 32 * 255 <= 65536) ? 2 : 1;
     long long ctas = (n + 31) / 32;
     if constexpr (kPerSm == 2) {
-        // more groups than SMs: pair them in one CTA that starts every trip together, so the two groups share the
-        // instruction lines they fetch (a lone group streams ~40 KB of straight-line code per trip); IKB_TAIL_PAIR=0|1
+        // more groups than SMs: IKB_TAIL_PAIR=1 pairs them in one CTA that starts every trip together, so that the two groups
+        // share the instruction lines they fetch (a lone group streams ~40 KB of straight-line code per trip).  Off by
+        // default: 40 interleaved lone batches (tools/pair_ab.py, profiles/r2_s4_pair_ab.txt) take 0.811 ms with two
+        // independent one-group CTAs per SM against 0.840 ms paired -- the lock step costs more than the shared fetch saves.
         const char *e = std::getenv("IKB_TAIL_PAIR");
-        if (ctas > sm_count && !(e && e[0] == '0')) {
+        if (ctas > sm_count && e && e[0] == '1') {
             ctas = (ctas + 1) / 2;
             if (ctas > sm_count) ctas = sm_count;
             SolveArgs<T> a2 = a;

@@ -1663,6 +1663,18 @@ class Generator:
                    " : ".join(["role == %d ? %d" % (k, js[0] if js else 0) for k, js in enumerate(jslots)] + ["0"]))
         out.append("    static constexpr int j_count(int role) { return %s; }" %
                    " : ".join(["role == %d ? %d" % (k, len(js)) for k, js in enumerate(jslots)] + ["0"]))
+        # QSTAGE: NQ consecutive Jacobian slots that are dead, for a problem that has CONVERGED, from the barrier inside psolve()
+        # to the next evaluate -- the rows of a role that publishes its contributions in the factor strip (not in its own
+        # Jacobian slots) and reads its rows afterwards only to step.  The kernel stages the configuration of the slot's NEXT
+        # problem there one trip ahead (dls_spec.cuh, kPrefetch); -1: no such run of slots.
+        qstage = -1
+        if arrow and contiguous and not tmemj and not self.spec.get("arrow_cap_solo"):
+            for k, js in enumerate(jslots):
+                if k != solver and self.arrow["pub"][k][0] == "L" and len(js) >= self.nq:
+                    qstage = js[0]
+                    break
+        out.append("    // QSTAGE: first of NQ Jacobian slots where the kernel may stage the next problem's configuration (-1: none)")
+        out.append("    static constexpr int QSTAGE = %d;" % qstage)
         out.append("    // CAPSOLO: psolve() ends behind a barrier of its own (the shared-column system is solved by the SOLVER role alone)")
         out.append("    static constexpr bool CAPSOLO = %s;" % ("true" if arrow and self.spec.get("arrow_cap_solo") else "false"))
         out.append("    // PRE: leading rows whose P x P factor block the SOLVER role computes in presolve(), before the first barrier;")
