@@ -260,6 +260,14 @@ int launch_merged_carry(const ikb_problem *p, const ikb_dls_params *prm, int64_t
 // The TAIL launch that finishes `c`'s stragglers.
 template <typename T> int launch_carry_tail(const ikb_problem *p, const CarryState<T> &c, cudaStream_t s);
 
+// Size class of the team-per-problem kernel: the problem's class, except that a class-2 problem (up to 30 rows) on a
+// Cassie-sized tree takes the smaller scratch of CoopClass<3> (dls_coop.cuh).  IKB_COOP_CLASS3=0 disables it (A/B runs).
+inline int coop_class(const ikb_problem *p) {
+    const char *e = std::getenv("IKB_COOP_CLASS3");
+    if (p->size_class == 2 && p->hp.model.njoints() <= 20 && p->hp.model.nv <= 24 && !(e && e[0] == '0')) return 3;
+    return p->size_class;
+}
+
 // The table-driven team-per-problem kernel (ikb_coop.cu / dls_coop.cuh) for size class `cls`.
 template <typename T>
 int launch_coop(int cls, const DevProblem<T> *dP, const SolveArgs<T> &a, bool pik, int extra /* 0 plain, 1 CoM, 2 constraints */, bool shfl, int sm_count,

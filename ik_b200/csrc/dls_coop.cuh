@@ -54,6 +54,9 @@ template <int CLS> struct CoopClass;
 template <> struct CoopClass<0> { using Cfg = CoopCfg<10, 8, 6, 8>; };      // serial arms, one or two frame tasks
 template <> struct CoopClass<1> { using Cfg = CoopCfg<20, 24, 12, 16>; };   // Cassie-sized: 12 rows, half a warp per problem
 template <> struct CoopClass<2> { using Cfg = CoopCfg<32, 36, 30, 32>; };   // humanoid-sized: 30 rows, a warp per problem
+// (coop kernel only; ikb_solve.cu picks it for class-2 problems on a small tree) Cassie-sized TREE with up to 30 rows -- the
+// demo's task set with its posture level, ik::pik on it: the scratch shrinks from 17.6 / 38.8 KB to 13.1 / 27.1 KB per team
+template <> struct CoopClass<3> { using Cfg = CoopCfg<20, 24, 30, 32>; };
 
 // Per-team block of shared memory.  EXTRA = 0: plain ik::dls; 1: + the subtree mass / moment arrays of a
 // CentreOfMassTask; 2: + the buffers only ik::pik and FrameConstraints need (projected Jacobian, row-space bases) -- each

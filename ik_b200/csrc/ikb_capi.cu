@@ -550,8 +550,11 @@ int ikb_problem_finalize(ikb_problem *p, int device) {
     char buf[96];
     const char *legacy = std::getenv("IKB_GENERIC_LEGACY");
     const int team[3] = {8, 16, 32};
-    if (p->coop_ok && !(legacy && legacy[0] == '1'))
-        std::snprintf(buf, sizeof buf, "coop<NJ=%d,NV=%d,M=%d,TEAM=%d>", kClasses[cls].nj, kClasses[cls].nv, kClasses[cls].m, team[cls]);
+    if (p->coop_ok && !(legacy && legacy[0] == '1')) {
+        p->size_class = cls;   // (coop_class reads it)
+        const int cc = coop_class(p);   // a class-2 problem on a Cassie-sized tree runs with class 1's tree capacities
+        std::snprintf(buf, sizeof buf, "coop<NJ=%d,NV=%d,M=%d,TEAM=%d>", kClasses[cc == 3 ? 1 : cls].nj, kClasses[cc == 3 ? 1 : cls].nv, kClasses[cls].m, team[cls]);
+    }
     else
         std::snprintf(buf, sizeof buf, "generic<NJ=%d,NV=%d,M=%d>", kClasses[cls].nj, kClasses[cls].nv, kClasses[cls].m);
     p->kernel_name[0] = p->spec ? p->spec->name : buf;

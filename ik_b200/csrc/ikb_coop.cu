@@ -35,6 +35,7 @@ int launch_shfl(int cls, const DevProblem<T> *dP, const SolveArgs<T> &a, bool pi
     switch (cls) {
         case 0: return launch_cls<T, 0, SHFL>(dP, a, pik, extra, sm_count, s);
         case 1: return launch_cls<T, 1, SHFL>(dP, a, pik, extra, sm_count, s);
+        case 3: return launch_cls<T, 3, SHFL>(dP, a, pik, extra, sm_count, s);
         default: return launch_cls<T, 2, SHFL>(dP, a, pik, extra, sm_count, s);
     }
 }

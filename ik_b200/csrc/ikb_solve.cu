@@ -235,7 +235,7 @@ static int launch_solve_impl(const ikb_problem *p, const ikb_dls_params *prm, in
         int extra = p->hp.constraints.empty() ? 0 : 2;   // scratch level: 1 = CentreOfMassTask arrays, 2 = + projection buffers (and always ik::pik)
         for (const auto &t : p->hp.tasks)
             if (t.kind == IKB_TASK_COM && extra < 1) extra = 1;
-        if (launch_coop<T>(p->size_class, dev_blob<T>(p), a, pik_lambda != nullptr, extra, shfl, p->sm_count, s))
+        if (launch_coop<T>(coop_class(p), dev_blob<T>(p), a, pik_lambda != nullptr, extra, shfl, p->sm_count, s))
             return cuda_fail(cudaGetLastError(), "team-per-problem kernel launch");
         g_launches.fetch_add(1);
         return IKB_OK;

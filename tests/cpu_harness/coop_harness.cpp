@@ -182,11 +182,12 @@ extern "C" int coop_solve(const char *urdf, int free_flyer, int max_priority, in
         for (int c = 0; c < 3 && cls < 0; ++c)
             if (hp.model.njoints() <= caps[c][0] && hp.model.nv <= caps[c][1] && hp.rows() <= caps[c][2]) cls = c;
         if (cls < 0) return 2;
+        if (cls == 2 && hp.model.njoints() <= 20 && hp.model.nv <= 24) cls = 3;   // the product's choice (ikb_solve.cu, coop_class)
         if (cls_out) *cls_out = cls;
         const Params prm{max_it, step, damping, tol, lambdas};
 #define CALL(T_, C_) solve_cls<T_, C_>(hp, shfl, pik, prm, B, q0, targets, q_out, success, iters, resid, e_first, J_first)
-        if (f32) { if (cls == 0) CALL(float, 0); else if (cls == 1) CALL(float, 1); else CALL(float, 2); }
-        else { if (cls == 0) CALL(double, 0); else if (cls == 1) CALL(double, 1); else CALL(double, 2); }
+        if (f32) { if (cls == 0) CALL(float, 0); else if (cls == 1) CALL(float, 1); else if (cls == 3) CALL(float, 3); else CALL(float, 2); }
+        else { if (cls == 0) CALL(double, 0); else if (cls == 1) CALL(double, 1); else if (cls == 3) CALL(double, 3); else CALL(double, 2); }
 #undef CALL
         return 0;
     } catch (const std::exception &e) {

@@ -13,7 +13,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --c
     python bench.py $ARGS > $out/${tag}_ncu_launches.log 2>&1
 python tools/ncu_summary.py launches $out/${tag}_launches.csv > $out/${tag}_launches.txt 2>&1
 # the merged BULK launches of the timed region: kernel <..., 4, 1, 1> (SEG = true); skip the warm-up group
-timeout 900 ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k regex:"Arrow, double, 4, 1, 1" \
+timeout 900 ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k regex:"SpecCassieFeetPelvisArrow, double, .int.4, .int.1, .bool.1" \
     --launch-skip 1 -c 2 -f -o $out/${tag}_merged python bench.py $ARGS > $out/${tag}_ncu_merged.log 2>&1
 python tools/ncu_summary.py report $out/${tag}_merged.ncu-rep > $out/${tag}_merged_full.txt 2>&1
 tail -2 $out/${tag}_ncu_merged.log
