@@ -1802,6 +1802,7 @@ class Generator:
                 out.append("        if (%s) %s;" % (cond, fn))
             out.append("        sync();  // every role's contribution to the shared-column system is in the strip")
             out.append("        hook();")
+            s_storer = None
             if self.spec.get("arrow_cap_solo"):
                 # the small system on the solver role alone (the others wait at a second barrier instead of repeating it)
                 out.append("        if (role == %d) {" % solver)
@@ -1814,6 +1815,15 @@ class Generator:
                 out.append("#pragma unroll")
                 out.append("            for (int i = 0; i < %d; ++i) s[i] = sL.get(%d + i);" % (A["ks"], A["soff"]))
                 out.append("        }")
+            elif not finishes[solver] and any(finishes[k] for k in range(len(groups)) if k != solver) and self.spec.get("arrow_solver_skips_cap", True):
+                # The SOLVER role has no rows of its own to finish (no private columns): it needs s only for its step, which
+                # reads it from the strip behind the next barrier.  It skips the shared-column system, so its time between the
+                # two barriers belongs to the stop test, the ticket and the staged refill (dls_spec.cuh, kPrefetch) -- latency
+                # that used to sit in front of 400 instructions the other roles were running too.
+                s_storer = [k for k in range(len(groups)) if k != solver and finishes[k] and k not in A["mirror_of"]][0]
+                out.append("        if (role != %d) {" % solver)
+                out.extend("    " + ln for ln in cap)
+                out.append("        }")
             else:
                 out.extend(cap)
             out.append("        IKB_PHASE_FENCE();")
@@ -1824,7 +1834,7 @@ class Generator:
                 fn = "arrow_finish_m%d(role == %d ? 1 : 0, sJ, sL, sE, s, fac, y)" % (k, partner[k]) if k in partner else "arrow_finish_w%d(sJ, sL, sE, s, fac, y)" % k
                 out.append("        if (%s) %s;" % (cond, fn))
             if not self.spec.get("arrow_cap_solo"):
-                out.append("        if (role == %d) {" % solver)
+                out.append("        if (role == %d) {" % (s_storer if s_storer is not None else solver))
                 out.append("#pragma unroll")
                 out.append("            for (int i = 0; i < %d; ++i) sL.set(%d + i, s[i]);" % (A["ks"], A["soff"]))
                 out.append("        }")
