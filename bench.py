@@ -45,8 +45,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per FP64 step, from the committed ncu --set full capture of this command
-# (profiles/r2_s6_merged_full.txt): one merged BULK launch of 8 steps, stragglers of the previous one included, moves 319.8 + 105.7 MB -> 53.2 MB per step
-NCU_TRAFFIC_BYTES_F64 = 53.2e6
+# (profiles/r2_s10_merged_full.txt): one merged BULK launch of 8 steps, stragglers of the previous one included, moves 320.0 + 107.5 MB -> 53.4 MB per step
+NCU_TRAFFIC_BYTES_F64 = 53.4e6
 METRIC = "converged IK solves/sec (Cassie, batch 65,536)"
 UNIT = "solves/s"
 NOMINAL_TFLOPS = {"f64": 37.2, "f32": 74.4}
@@ -698,7 +698,7 @@ def main():
                          "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak if peak else None,
                          "traffic": NCU_TRAFFIC_BYTES_F64 if (args.dtype == "f64" and B == 65536) else None,
-                         "traffic_source": "ncu --set full of this command, profiles/r2_s6_merged_full.txt: DRAM bytes of one merged BULK launch (8 steps + the stragglers carried over from the previous launch): (319.8 + 105.7 MB) / 8; algorithmic 43.8 MB",
+                         "traffic_source": "ncu --set full of this command, profiles/r2_s10_merged_full.txt: DRAM bytes of one merged BULK launch (8 steps + the stragglers carried over from the previous launch): (320.0 + 107.5 MB) / 8; algorithmic 43.8 MB",
                          "kernels": "one BULK launch of %s per group of %d steps, which also continues the stragglers the previous group left "
                                     "suspended; ONE TAIL launch when the queue runs empty; kernel_ms = device time of the timed region / steps"
                                     % (pb.kernel_name(args.dtype), args.merge),
