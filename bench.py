@@ -183,7 +183,7 @@ def main():
     ap.add_argument("--depth", type=int, default=24, help="batches in flight in the pipelined queue")
     ap.add_argument("--e2e-merge", type=int, default=4, help="the same for the host-buffer (e2e) arm: smaller groups keep the "
                     "PCIe pipeline's fill / drain short")
-    ap.add_argument("--e2e-depth", type=int, default=8)
+    ap.add_argument("--e2e-depth", type=int, default=12, help="three groups in flight: host batches carry their stragglers too (ikb_queue_create)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -373,6 +373,10 @@ def main():
     # kernels of its neighbours.  Headline wire format: compact targets, one shared q0, q + success back. ----
     e2e_depth = max(args.e2e_depth, args.e2e_merge)
     queue_h = ik.SolveQueue(pb, e2e_depth, args.e2e_merge, local_rank)
+    # the round-1 wire format (669 B per solve) is bound by the link, not by the kernels: two groups in flight keep the copy
+    # pipeline's fill / drain short (and a queue this shallow launches a TAIL per host group instead of carrying)
+    full_depth = max(8, args.e2e_merge)
+    queue_f = ik.SolveQueue(pb, full_depth, args.e2e_merge, local_rank)
     nbuf = e2e_depth
     csz = pb.compact_target_size
     host_tg = [np.ascontiguousarray(sets[s][3], dtype=np.float64) for s in range(min(nsets, 3))]
@@ -393,18 +397,20 @@ def main():
     def e2e_run(nsteps, lean):
         got = 0
         tickets = []
+        qh = queue_h if lean else queue_f
+        lg = lag if lean else max(1, full_depth - 1)
         for k in range(nsteps):
             i = k % nbuf
             if lean:
-                t, _ = queue_h.submit_host(h_q0_one, h_ctg[i], prm, args.dtype, "soa", h_outs[i], compact=True, outputs=("q", "success"))
+                t, _ = qh.submit_host(h_q0_one, h_ctg[i], prm, args.dtype, "soa", h_outs[i], compact=True, outputs=("q", "success"))
             else:
-                t, _ = queue_h.submit_host(h_q0[i], h_tg[i], prm, args.dtype, "soa", h_outs[i])
+                t, _ = qh.submit_host(h_q0[i], h_tg[i], prm, args.dtype, "soa", h_outs[i])
             tickets.append(t)
-            if k >= lag:
-                queue_h.wait(tickets[k - lag])
-                got += int(h_outs[(k - lag) % nbuf]["success"].sum())
-        for k in range(max(0, nsteps - lag), nsteps):
-            queue_h.wait(tickets[k])
+            if k >= lg:
+                qh.wait(tickets[k - lg])
+                got += int(h_outs[(k - lg) % nbuf]["success"].sum())
+        for k in range(max(0, nsteps - lg), nsteps):
+            qh.wait(tickets[k])
             got += int(h_outs[k % nbuf]["success"].sum())
         return got
 
@@ -593,7 +599,7 @@ def main():
         barrier()
         if rank == 0 and torch.cuda.device_count() >= max(world, 1):
             G = max(world, 1)
-            multi = ik.MultiGPU(pb, devices=list(range(G)), depth=8, merge=4)
+            multi = ik.MultiGPU(pb, devices=list(range(G)), depth=12, merge=4)
             Bm = B * G
             mq0 = pinned_array((nq,), np.float64)
             mq0[:] = q0_np[0]
@@ -687,7 +693,9 @@ def main():
                     "api": "ikb_queue_submit_host + ikb_queue_wait (pinned host buffers; H2D, SE3 expansion, solve, D2H of every step)",
                     "wire_format": "compact targets (pelvis quaternion + translation, two foot positions: %d scalars), one shared q0, "
                                    "q + success read back -- what a caller of the reference supplies and receives" % csz,
-                    "pipeline": "ikb_queue, depth %d, %d consecutive batches per BULK+TAIL kernel pair" % (e2e_depth, args.e2e_merge),
+                    "pipeline": "ikb_queue, depth %d, %d consecutive host batches per BULK launch; their stragglers are carried into the next "
+                                "group's launch (depth >= 3 x merge), the copy-out of a group follows that launch; the SE3 expansion of the "
+                                "compact targets runs on the compute stream" % (e2e_depth, args.e2e_merge),
                     "isolated_ms_per_batch": e2e_isolated_ms,
                     "isolated_api": "ikb_dls_solve_batch_host (blocking, one batch at a time, full_io format)",
                     "full_io": {"value": full_conv_all / full_s_max, "h2d_bytes_per_step": int(B * (nq + tsz) * itemsize),

@@ -189,7 +189,10 @@ struct HostViews {
 int classify_host_views(const ikb_problem *p, int64_t B, const ikb_batch_io *io, HostViews *out);
 // Stage the inputs of batch slice [b0, b1) on stream `s` (copy-in and, for compact targets, the SE3 expansion).
 template <typename T> int stage_inputs(const ikb_problem *p, Staging<T> &st, const HostViews &hv, long long B, long long b0, long long b1,
-                                       bool first, cudaStream_t s);
+                                       bool first, cudaStream_t s, bool expand = true);
+// The SE3 expansion alone (expand = false above leaves it to the caller's compute stream).
+template <typename T> int expand_staged(const ikb_problem *p, Staging<T> &st, const HostViews &hv, long long B, long long b0, long long b1,
+                                        bool first, cudaStream_t s);
 // Make sure the staging buffers of `st` hold a batch of B problems; fills the device view `dio` (pointers + dense strides).
 template <typename T> int prepare_staging(const ikb_problem *p, Staging<T> &st, const HostViews &hv, long long B, ikb_batch_io *dio);
 template <typename T> int ensure(T *&ptr, size_t &cap, size_t need) {

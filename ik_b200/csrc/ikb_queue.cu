@@ -46,7 +46,7 @@ struct ikb_queue {
     // launch continues its stragglers (capi_internal.hpp, CarryState), and whoever needs the group's results before that
     // (wait, flush, drain, slot reuse, a group that cannot carry) launches the TAIL (queue_finish_carry).
     bool carry_on = true;           // IKB_QUEUE_CARRY=0 disables it (A/B runs)
-    bool carry_host = false;        // IKB_QUEUE_CARRY_HOST=1: host batches carry too (A/B runs; see queue_flush_t)
+    bool carry_host = false;        // host batches carry too: depth >= 3 * merge, or IKB_QUEUE_CARRY_HOST=0|1 (ikb_queue_create)
     bool carry_valid = false;
     int carry_dtype = -1;
     ikb_dls_params carry_prm{};
@@ -142,7 +142,11 @@ template <typename T> int queue_flush_t(ikb_queue *q) {
     const int n = (int)q->open.size();
     int rc;
     for (int i : q->open)
-        if (q->slots[i].host) IKB_CUDA(cudaStreamWaitEvent(q->s_comp, q->slots[i].ev_in, 0));
+        if (q->slots[i].host) {
+            ikb_queue::Slot &sl = q->slots[i];
+            IKB_CUDA(cudaStreamWaitEvent(q->s_comp, sl.ev_in, 0));
+            if (sl.B > 0 && (rc = expand_staged<T>(q->p, slot_staging<T>(sl), sl.hv, sl.B, 0, sl.B, true, q->s_comp))) return rc;
+        }
     if (q->trace)
         for (int i : q->open) IKB_CUDA(cudaEventRecord(q->slots[i].tr_c0, q->s_comp));
     if (n >= 2 && q->p->spec && q->open_prm.max_iterations > 0) {
@@ -157,8 +161,8 @@ template <typename T> int queue_flush_t(ikb_queue *q) {
             total += sl.B;
         }
         const Merged<T> m{tab, n};
-        // (host batches do not carry: measured, their copy-out one launch later costs the host pipeline more -- 114 M against
-        // 137 M solves / s end to end -- than the TAIL launch it saves)
+        // (host batches carry only in a deep queue, see ikb_queue_create.  An earlier measurement -- 114 M against 137 M solves / s
+        // end to end -- blamed the later copy-out; the real cause was the SE3 expansion kernel in the copy stream, queue_stage_host)
         bool any_host_ = false;
         for (int i : q->open) any_host_ |= q->slots[i].host;
         const bool can_carry = q->carry_on && (!any_host_ || q->carry_host) && !q->trace && two_phase(q->p, &q->open_prm, total);
@@ -286,8 +290,11 @@ template <typename T> int queue_stage_host(ikb_queue *q, ikb_queue::Slot &sl, in
         sl.tr_submit_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - q->tr_host_ref).count();
         IKB_CUDA(cudaEventRecord(sl.tr_in0, q->s_in));
     }
-    // copy-in (+ the SE3 expansion of compact targets) on the copy stream
-    if ((rc = stage_inputs<T>(p, st, sl.hv, B, 0, B, true, q->s_in))) return rc;
+    // copy-in on the copy stream: copies ONLY.  The SE3 expansion of compact targets is a kernel; in the copy stream it could not
+    // start while a persistent solve kernel holds every SM's registers, and the copies of the following batches would queue up
+    // behind it until that kernel ends (measured: 0.5-0.7 ms of idle GPU per group).  It runs on the compute stream, in front of
+    // the group's launch (queue_flush_t).
+    if ((rc = stage_inputs<T>(p, st, sl.hv, B, 0, B, true, q->s_in, false))) return rc;
     IKB_CUDA(cudaEventRecord(sl.ev_in, q->s_in));
     sl.dio.success = sl.success; sl.dio.iters = sl.iters;
     return IKB_OK;
@@ -313,8 +320,11 @@ int ikb_queue_create(ikb_problem *p, int depth, int merge, ikb_queue **out) {
     q->trace = tr && tr[0] == '1';
     const char *ce = std::getenv("IKB_QUEUE_CARRY");
     q->carry_on = !(ce && ce[0] == '0');
+    // Host batches carry too when the queue is deep enough to hide the later copy-out (a carried group's results leave the
+    // device one launch later): three groups in flight.  Measured (tools/e2e_host_probe.py, compact wire format): depth 12,
+    // merge 4 -- 0.38 ms per step against 0.47 with a TAIL launch per group; depth 8, merge 4 would stall on the host's waits.
     const char *ch = std::getenv("IKB_QUEUE_CARRY_HOST");
-    q->carry_host = ch && ch[0] == '1';
+    q->carry_host = ch ? ch[0] == '1' : depth >= 3 * merge;
     const unsigned evf = q->trace ? cudaEventDefault : cudaEventDisableTiming;
     IKB_CUDA(cudaEventCreateWithFlags(&q->ev_user, cudaEventDisableTiming));
     IKB_CUDA(cudaEventCreateWithFlags(&q->ev_comp, cudaEventDisableTiming));

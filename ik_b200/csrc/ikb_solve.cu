@@ -407,11 +407,21 @@ int prepare_staging(const ikb_problem *p, Staging<T> &st, const HostViews &hv, l
 }
 
 template <typename T>
-int stage_inputs(const ikb_problem *p, Staging<T> &st, const HostViews &hv, long long B, long long b0, long long b1, bool first, cudaStream_t s) {
+int stage_inputs(const ikb_problem *p, Staging<T> &st, const HostViews &hv, long long B, long long b0, long long b1, bool first, cudaStream_t s,
+                 bool expand) {
     int rc;
     if ((rc = copy_view_in<T>(st.q0, hv.q0, B, b0, b1, first, s))) return rc;
     if (!hv.compact) return copy_view_in<T>(st.targets, hv.tg, B, b0, b1, first, s);
     if ((rc = copy_view_in<T>(st.compact, hv.tg, B, b0, b1, first, s))) return rc;
+    if (!expand) return IKB_OK;   // the caller runs expand_staged on its compute stream
+    return expand_staged<T>(p, st, hv, B, b0, b1, first, s);
+}
+
+// Compact targets -> SE3 records on the device (one thread per problem).  A KERNEL: in a copy stream it would sit behind a
+// persistent solve kernel that holds every SM's registers, and the stream's later copies behind it (ikb_queue.cu).
+template <typename T>
+int expand_staged(const ikb_problem *p, Staging<T> &st, const HostViews &hv, long long B, long long b0, long long b1, bool first, cudaStream_t s) {
+    if (!hv.compact) return IKB_OK;
     // a broadcast compact record expands to one broadcast SE3 record (one "problem")
     const bool bc = hv.tg.kind == VIEW_BCAST;
     if (bc && !first) return IKB_OK;
@@ -428,8 +438,10 @@ int stage_inputs(const ikb_problem *p, Staging<T> &st, const HostViews &hv, long
 }
 template int prepare_staging<double>(const ikb_problem *, Staging<double> &, const HostViews &, long long, ikb_batch_io *);
 template int prepare_staging<float>(const ikb_problem *, Staging<float> &, const HostViews &, long long, ikb_batch_io *);
-template int stage_inputs<double>(const ikb_problem *, Staging<double> &, const HostViews &, long long, long long, long long, bool, cudaStream_t);
-template int stage_inputs<float>(const ikb_problem *, Staging<float> &, const HostViews &, long long, long long, long long, bool, cudaStream_t);
+template int stage_inputs<double>(const ikb_problem *, Staging<double> &, const HostViews &, long long, long long, long long, bool, cudaStream_t, bool);
+template int stage_inputs<float>(const ikb_problem *, Staging<float> &, const HostViews &, long long, long long, long long, bool, cudaStream_t, bool);
+template int expand_staged<double>(const ikb_problem *, Staging<double> &, const HostViews &, long long, long long, long long, bool, cudaStream_t);
+template int expand_staged<float>(const ikb_problem *, Staging<float> &, const HostViews &, long long, long long, long long, bool, cudaStream_t);
 
 }  // namespace capi
 }  // namespace ikb

@@ -288,3 +288,53 @@ def test_carried_stragglers_match_per_batch_calls(cassie, dtype, monkeypatch):
     queue.drain()
     assert ik.kernel_launch_count() - launches0 == 10
     check(got)
+
+
+def test_host_batches_carry_in_a_deep_queue(cassie):
+    """A queue with three groups in flight (depth >= 3 x merge) carries the stragglers of HOST batches too: a group's results
+    leave the device after the NEXT group's launch has finished them (or after the TAIL that wait / drain launch on demand).
+    Whatever the route -- waiting in order, out of order, draining, compact or SE3 targets -- the host arrays hold the results
+    of the blocking per-batch call, bit for bit in FP64."""
+    _torch()
+    pb, om, opb = cassie
+    pb.finalize(0)
+    sizes = [12000, 9800, 15000, 10000, 11000, 9900, 13000]   # each larger than one resident wave: two-launch batches
+    data = [make_workload(pb, om, B, seed=700 + i, standing=W.CASSIE_STANDING) for i, B in enumerate(sizes)]
+    ref = [ik.dls_batch_host(pb, q0, tg, None, "f64", "aos") for q0, tg, _ in data]
+
+    def same(out, r, layout):
+        q = out["q"].T if layout == "soa" else out["q"]
+        assert np.array_equal(q, r["q"]) and np.array_equal(out["success"], r["success"])
+        if "iters" in out and out["iters"] is not None:
+            assert np.array_equal(out["iters"], r["iters"]) and np.array_equal(out["resid"], r["resid"])
+
+    launches0 = ik.kernel_launch_count()
+    queue = ik.SolveQueue(pb, depth=6, merge=2)
+    jobs = []
+    for k, (q0, tg, _) in enumerate(data):
+        if k % 2:
+            jobs.append((queue.submit_host(np.ascontiguousarray(q0.T), np.ascontiguousarray(tg.T), None, "f64", "soa"), "soa"))
+        else:
+            jobs.append((queue.submit_host(q0, tg, None, "f64", "aos"), "aos"))
+    queue.drain()
+    # 7 batches = 3 full groups + 1 open batch: 3 carried BULK launches; the odd batch takes the per-batch pair, in front of which
+    # the carried stragglers get their TAIL (no TAIL per group: 3 + 1 + 2 launches, not 3 x 2 + 2)
+    assert ik.kernel_launch_count() - launches0 <= 3 + 1 + 2
+    for ((t, out), layout), r in zip(jobs, ref):
+        same(out, r, layout)
+    # compact targets, one shared initial guess, waits out of order (a wait on a carried group launches its TAIL)
+    queue = ik.SolveQueue(pb, depth=6, merge=2)
+    assert all((q0 == q0[0]).all() for q0, _, _ in data)
+    one = np.ascontiguousarray(data[0][0][0])
+    ctg = [pb.compact_targets(tg) for _, tg, _ in data[:6]]
+    ref_c = [ik.dls_batch_host(pb, one, c, None, "f64", "aos", compact=True, outputs=("q", "success")) for c in ctg]
+    jobs = [queue.submit_host(one, c, None, "f64", "aos", compact=True, outputs=("q", "success")) for c in ctg]
+    for i in (1, 0, 5, 3, 2, 4):
+        queue.wait(jobs[i][0])
+        same(jobs[i][1], ref_c[i], "aos")
+    # a shallow queue (depth < 3 x merge) launches a TAIL per host group, same results
+    queue = ik.SolveQueue(pb, depth=4, merge=2)
+    jobs = [queue.submit_host(q0, tg, None, "f64", "aos") for q0, tg, _ in data[:4]]
+    queue.drain()
+    for (t, out), r in zip(jobs, ref):
+        same(out, r, "aos")
