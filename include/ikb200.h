@@ -254,8 +254,9 @@ int ikb_pik_solve_ex(ikb_problem *p, const ikb_pik_params *params, const double 
  * for batches larger than the latency configuration holds), to rounding otherwise -- a merged group of small batches
  * may run the thread-per-problem kernels where a lone small batch runs the team-per-problem one, and in FP32 the step
  * at which a straggler changes kernels depends on scheduling.  One thread drives a queue.
- * DEVICE-buffer groups are launched without their own straggler launch: the problems a group's launch suspends (their
- * iterate and step count stay in the batch's own output buffers) continue at the head of the NEXT group's launch, and
+ * Groups of device buffers -- and of host buffers when depth >= 3 * merge -- are launched without their own straggler
+ * launch: the problems a group's launch suspends (their iterate and step count stay in the batch's own output buffers, for
+ * host batches in the slot's staging) continue at the head of the NEXT group's launch, and
  * ikb_queue_wait / _wait_on_stream / _flush / _drain / the reuse of a slot finish them on demand -- a ticket is complete
  * exactly when its wait returns, as before, but two batches in flight must not share output buffers. */
 typedef struct ikb_queue ikb_queue;
