@@ -9,6 +9,7 @@
 #include <climits>
 #include <cstdint>
 #include <cstdlib>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -216,6 +217,9 @@ struct ChunkPlan {
     cudaEvent_t ready[8] = {};
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_aux = nullptr, ev_main = nullptr;
+    // work that must precede slice c's launch on ITS compute stream (the SE3 expansion of compact targets: a kernel, which
+    // in the copy stream would wait for the previous slice's persistent launch and hold the next slices' copies back)
+    std::function<int(int, cudaStream_t)> pre;
 };
 
 // Merged launch of the pipelined queue (ikb_queue_*): `nseg` batches, each with its own buffers (host array of segment

@@ -200,6 +200,7 @@ static int launch_solve_impl(const ikb_problem *p, const ikb_dls_params *prm, in
                 for (int c = 0; c < plan->n && rc == IKB_OK; ++c) {
                     cudaStream_t cs = (c & 1) ? plan->aux : s;
                     IKB_CUDA(cudaStreamWaitEvent(cs, plan->ready[c], 0));
+                    if (plan->pre && (rc = plan->pre(c, cs)) != IKB_OK) break;
                     SolveArgs<T> ac = a;
                     ac.ticket = a.ticket + 3 + c;
                     ac.B = plan->begin[c + 1];
@@ -519,7 +520,12 @@ int solve_host(ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_b
     const char *slices_env = std::getenv("IKB_HOST_SLICES");
     const int nslice = (int)std::min<int64_t>(slices_env ? std::max(1, std::min(8, std::atoi(slices_env))) : 4, B / 8192);
     const char *pipe_env = std::getenv("IKB_HOST_PIPELINE");
-    if (!pik_lambda && !want_aux && two_phase(p, prm, B) && nslice >= 2 && !(pipe_env && pipe_env[0] == '0')) {
+    // (worth it only when the copy-in is long: the lean wire format -- compact targets, one shared q0: 6.8 MB for 65 536 Cassie
+    // problems -- takes 1.17 ms unsliced against 1.26 ms in four slices, each with its own BULK launch; tools/blocking_compact.py)
+    const double in_bytes = (double)sizeof(T) * (double)B *
+                            ((hv.q0.kind == VIEW_BCAST ? 0.0 : (double)hv.q0.n) + (hv.tg.kind == VIEW_BCAST ? 0.0 : (double)hv.tg.n));
+    const bool long_copy = slices_env || in_bytes >= 16e6;
+    if (!pik_lambda && !want_aux && two_phase(p, prm, B) && nslice >= 2 && long_copy && !(pipe_env && pipe_env[0] == '0')) {
         ChunkPlan plan;
         plan.n = nslice;
         plan.aux = p->stream_aux;
@@ -529,8 +535,10 @@ int solve_host(ikb_problem *p, const ikb_dls_params *prm, int64_t B, const ikb_b
         // the staging buffers may still be read by the previous call's kernels on `s`: order the copy stream behind it
         IKB_CUDA(cudaEventRecord(p->ev_main, s));
         IKB_CUDA(cudaStreamWaitEvent(p->stream_in, p->ev_main, 0));
+        if (hv.compact)
+            plan.pre = [&, p](int c, cudaStream_t cs) { return expand_staged<T>(p, st, hv, B, plan.begin[c], plan.begin[c + 1], c == 0, cs); };
         for (int c = 0; c < nslice; ++c) {
-            if ((rc = stage_inputs<T>(p, st, hv, B, plan.begin[c], plan.begin[c + 1], c == 0, p->stream_in))) return rc;
+            if ((rc = stage_inputs<T>(p, st, hv, B, plan.begin[c], plan.begin[c + 1], c == 0, p->stream_in, false))) return rc;
             plan.ready[c] = p->ev_in[c];
             IKB_CUDA(cudaEventRecord(plan.ready[c], p->stream_in));
             tr.mark("h2d slice", p->stream_in);

@@ -535,7 +535,11 @@ def test_two_phase_scheduling_matches_oracle(params):
         os.environ["IKB_HOST_PIPELINE"] = "0"
         plain = ik.dls_batch_host(pb, a, b, prm, "f64", layout)
         del os.environ["IKB_HOST_PIPELINE"]
-        piped = ik.dls_batch_host(pb, a, b, prm, "f64", layout)
+        os.environ["IKB_HOST_SLICES"] = "2"      # (a copy-in this short is not sliced by default: force the slices)
+        try:
+            piped = ik.dls_batch_host(pb, a, b, prm, "f64", layout)
+        finally:
+            del os.environ["IKB_HOST_SLICES"]
         for k in ("q", "success", "iters", "resid"):
             assert np.array_equal(plain[k], piped[k]), (layout, k)
 
