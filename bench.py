@@ -603,23 +603,24 @@ def main():
             Bm = B * G
             mq0 = pinned_array((nq,), np.float64)
             mq0[:] = q0_np[0]
-            mtg = [pinned_array((csz, Bm), np.float64) for _ in range(8)]
-            mout = [{"q": pinned_array((nq, Bm), np.float64), "success": pinned_array((Bm,), np.uint8)} for _ in range(8)]
-            for i in range(8):
+            NB = 12                                  # host buffers = queue depth: three groups in flight (host batches carry)
+            mtg = [pinned_array((csz, Bm), np.float64) for _ in range(NB)]
+            mout = [{"q": pinned_array((nq, Bm), np.float64), "success": pinned_array((Bm,), np.uint8)} for _ in range(NB)]
+            for i in range(NB):
                 mtg[i][:] = np.tile(pb.compact_targets(host_tg[i % len(host_tg)]).T, (1, G))
             def mrun(n):
                 got, tk = 0, []
                 for k in range(n):
-                    t, _ = multi.submit_host(mq0, mtg[k % 8], prm, "f64", "soa", mout[k % 8], compact=True, outputs=("q", "success"))
+                    t, _ = multi.submit_host(mq0, mtg[k % NB], prm, "f64", "soa", mout[k % NB], compact=True, outputs=("q", "success"))
                     tk.append(t)
-                    if k >= 7:
-                        multi.wait(tk[k - 7])
-                        got += int(mout[(k - 7) % 8]["success"].sum())
-                for k in range(max(0, n - 7), n):
+                    if k >= NB - 1:
+                        multi.wait(tk[k - (NB - 1)])
+                        got += int(mout[(k - (NB - 1)) % NB]["success"].sum())
+                for k in range(max(0, n - (NB - 1)), n):
                     multi.wait(tk[k])
-                    got += int(mout[k % 8]["success"].sum())
+                    got += int(mout[k % NB]["success"].sum())
                 return got
-            mrun(12)
+            mrun(NB + 4)
             t0 = time.perf_counter()
             got = mrun(24)
             ms_ = (time.perf_counter() - t0)
