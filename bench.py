@@ -714,6 +714,11 @@ def main():
                          "peak_source": "measured in this run (ikb_measure_fma_peak); nominal %.1f"
                                         % NOMINAL_TFLOPS[args.dtype],
                          "frac_of_nominal": achieved_tf / NOMINAL_TFLOPS[args.dtype],
+                         "executed_pipe_busy_ncu": 0.40 if (args.dtype == "f64" and B == 65536) else None,
+                         "executed_note": "`frac` counts ALGORITHMIC FLOPs (SURVEY 8d: the dense J J^T + LDL^T of the reference's step); the arrow "
+                                          "step reaches the same dq with fewer executed FLOPs, so ncu's FP64-pipe utilisation of the merged launch "
+                                          "(sm__pipe_fp64_cycles_active 39.5-39.9 %, profiles/r2_s15_merged_full.txt) is lower than `frac`",
+
                          "flops_per_launch": flops_per_launch, "kernel_ms": k_ms,
                          "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": hbm_achieved / hbm_peak, "peak_source": hbm_src}},
