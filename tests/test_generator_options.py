@@ -109,3 +109,55 @@ def test_two_barrier_variant_still_generates(inputs, rolled, extra):
     assert _const(src, "NFACT") == M * (M + 1) // 2 + extra * M        # + yp for the rolled left-looking loops
     assert ("minus column k of the factor" in src) == bool(rolled)
     assert all(" psolve_w%d(" % k in src for k in range(5))
+
+
+# ---- arrow specs (round 2): staging slots of the one-trip-ahead refill, the SOLVER role off the shared-column system ----
+ARROW = [("cassie_feet_pelvis_arrow", "cassie_feet_pelvis_arrow"), ("cassie_feet_pelvis_arrow_b", "cassie_feet_pelvis_arrow_b"),
+         ("humanoid_limbs_arrow", "humanoid_limbs_arrow")]
+
+
+def _arrow_inputs(name):
+    model = os.path.join(ROOT, "build", "models", "%s.json" % name)
+    spec = os.path.join(ROOT, "ik_b200", "specs", "%s.json" % name)
+    if not os.path.exists(model):
+        pytest.skip("flattened model of %s not built" % name)
+    return json.load(open(model)), json.load(open(spec))
+
+
+def _role_fn(src, name):
+    m = re.search(r"static constexpr int %s\(int role\) \{ return (.*?); \}" % name, src)
+    return {int(a): int(b) for a, b in re.findall(r"role == (\d+) \? (-?\d+)", m.group(1))}
+
+
+@pytest.mark.parametrize("name,_", ARROW)
+def test_staging_slots_belong_to_a_role_that_publishes_in_the_factor_strip(name, _):
+    """dls_spec.cuh (kPrefetch) copies a converged slot's NEXT configuration into Spec::QSTAGE .. + NQ of the Jacobian strip
+    in the middle of a trip.  Those slots must be rows of ONE non-solver role that does not publish its contribution there
+    (a role without private columns does: the other roles read it while the copy is in flight)."""
+    model, spec = _arrow_inputs(name)
+    g, src = _emit(model, spec)
+    q0, NQ, solver = _const(src, "QSTAGE"), _const(src, "NQ"), _const(src, "SOLVER")
+    assert q0 >= 0
+    first, count = _role_fn(src, "j_first"), _role_fn(src, "j_count")
+    owners = [k for k in first if first[k] <= q0 and q0 + NQ <= first[k] + count[k]]
+    assert len(owners) == 1 and owners[0] != solver
+    assert g.arrow["pub"][owners[0]][0] == "L"
+    # the option that keeps the strip out of shared memory or ends psolve() behind its own barrier switches the staging off
+    assert _const(_emit(model, spec, arrow_cap_solo=True)[1], "QSTAGE") == -1
+
+
+@pytest.mark.parametrize("name,_", ARROW)
+def test_solver_role_skips_the_shared_system_only_when_the_spec_says_so(name, _):
+    """`arrow_solver_skips_cap` (default on; off in the humanoid spec, where it measured slower): a SOLVER role without private
+    columns leaves the shared-column system to the other roles, and the first of them stores s for everybody's step."""
+    model, spec = _arrow_inputs(name)
+    for on in (True, False):
+        g, src = _emit(model, spec, arrow_solver_skips_cap=on)
+        solver = _const(src, "SOLVER")
+        body = _body(src, "psolve")
+        assert ("if (role != %d) {" % solver in body) == on
+        storer = re.search(r"if \(role == (\d+)\) \{\n#pragma unroll\n\s+for \(int i = 0; i < \d+; \+\+i\) sL\.set\(", body)
+        assert storer and (int(storer.group(1)) != solver) == on
+        assert body.count("sync();") == 1                      # still ONE barrier inside psolve()
+    committed = json.load(open(os.path.join(ROOT, "ik_b200", "specs", "%s.json" % name)))
+    assert committed.get("arrow_solver_skips_cap", True) == (not name.startswith("humanoid"))
