@@ -59,4 +59,4 @@ run(depth + merge, False)
 l0 = ik.kernel_launch_count()
 tot = run(steps, True)
 print("solve-kernel launches in the timed loop: %d" % (ik.kernel_launch_count() - l0))
-print("carry_host=%s depth=%d merge=%d steps=%d: %.3f ms total, %.4f ms per step" % (os.environ.get("IKB_QUEUE_CARRY_HOST", "0"), depth, merge, steps, tot, tot / steps))
+print("carry_host=%s depth=%d merge=%d steps=%d: %.3f ms total, %.4f ms per step" % (os.environ.get("IKB_QUEUE_CARRY_HOST", "default (on when depth >= 3 x merge)"), depth, merge, steps, tot, tot / steps))
